@@ -1,0 +1,770 @@
+// C-ABI implementation (include/bmc.h) of the B200-native particle loop.
+// Host side: context, device memory, launch sequencing of one cycleProcess.
+// No CPU fallback exists: every entry point that computes runs CUDA kernels and
+// reports BMC_ERR_CUDA if the device is unavailable.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/bmc.h"
+#include "bmc_kernels.cuh"
+
+using namespace bmc;
+
+namespace {
+
+struct ModelVT {
+  int n_var, n_c, vec;
+  const void* cycle_fn;
+  void (*launch_cycle)(const CycleParams&, int grid, size_t smem, cudaStream_t);
+  void (*launch_init)(float*, size_t, uint32_t*, uint8_t*, float*, float*, unsigned long long, uint32_t, const float*,
+                      uint32_t, uint32_t, uint32_t, DevState*, int, cudaStream_t);
+};
+
+template <class M, int VEC> static void launch_cycle_t(const CycleParams& p, int grid, size_t smem, cudaStream_t s) {
+  cycle_kernel<M, VEC><<<grid, kBlock, smem, s>>>(p);
+}
+template <class M>
+static void launch_init_t(float* props, size_t cap, uint32_t* pos, uint8_t* status, float* ah, float* ad, unsigned long long n,
+                          uint32_t ncomp_hi, const float* linit, uint32_t slo, uint32_t shi, uint32_t rank, DevState* st, int grid,
+                          cudaStream_t s) {
+  init_kernel<M><<<grid, 256, 0, s>>>(props, cap, pos, status, ah, ad, n, ncomp_hi, linit, slo, shi, rank, st);
+}
+template <class M, int VEC> static ModelVT make_vt() {
+  ModelVT v;
+  v.n_var = M::n_var; v.n_c = M::n_c; v.vec = VEC;
+  v.cycle_fn = (const void*)cycle_kernel<M, VEC>;
+  v.launch_cycle = &launch_cycle_t<M, VEC>;
+  v.launch_init = &launch_init_t<M>;
+  return v;
+}
+
+static bool pick_model(int model, int n_var_udf, ModelVT& vt) {
+  switch (model) {
+    case BMC_MODEL_FIXED_LENGTH: vt = make_vt<FixedLength, 4>(); return true;
+    case BMC_MODEL_MONOD: vt = make_vt<Monod, 4>(); return true;
+    case BMC_MODEL_SIMPLE_ACETATE: vt = make_vt<SimpleAcetate, 4>(); return true;
+    case BMC_MODEL_WIDE_UDF:
+      switch (n_var_udf) {
+        case 8: vt = make_vt<WideUdf<8>, 4>(); return true;
+        case 16: vt = make_vt<WideUdf<16>, 2>(); return true;
+        case 32: vt = make_vt<WideUdf<32>, 1>(); return true;
+        case 64: vt = make_vt<WideUdf<64>, 1>(); return true;
+        default: return false;
+      }
+    default: return false;
+  }
+}
+
+}  // namespace
+
+static int (*g_nccl_destroy)(void*) = nullptr;
+
+struct bmc_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int model = 0;
+  ModelVT vt{};
+  uint64_t n_species = 1, n_comp = 1;
+  uint64_t seed = 0; uint32_t rank = 0;
+  double allocation_factor = 1.5, buffer_ratio = 0.6, dead_ratio = 0.01;
+  uint64_t min_removal = 0;
+  // container
+  size_t cap = 0, buf_cap = 0;
+  float* props = nullptr; uint32_t* pos = nullptr; uint8_t* status = nullptr; float* age_hyd = nullptr; float* age_div = nullptr;
+  float* buf_props = nullptr; uint32_t* buf_pos = nullptr; uint32_t* buf_mother = nullptr;
+  uint32_t *div_mask = nullptr, *tile_div = nullptr, *tile_off = nullptr, *blk_total = nullptr;
+  uint32_t *tile_gap_off = nullptr, *tile_idle_off = nullptr, *blk_gap = nullptr, *blk_idle = nullptr, *src = nullptr;
+  // domain
+  int m = 0; bool domain_set = false; double table_dt = -1.0;
+  double *d_vol = nullptr, *d_diag = nullptr, *d_cdf = nullptr;
+  float *d_pleave = nullptr, *d_cdf_f = nullptr; uint32_t* d_neigh = nullptr;
+  std::vector<bmc_leaving_flow> flows;
+  // liquid
+  double *d_conc = nullptr, *d_sources = nullptr;
+  float weight = 1.0f;
+  // state
+  DevState* st = nullptr;
+  DevState* h_st[2] = {nullptr, nullptr}; cudaEvent_t ev_mirror[2] = {nullptr, nullptr}; int mirror_next = 0; bool mirror_valid[2] = {false, false};
+  uint64_t host_step = 0;
+  uint64_t known_n_used = 0, known_max_add = 0;
+  // launch config
+  int n_sm = 148, grid_cycle = 148, blocks_per_sm = 1; size_t smem_bins = 0; int bins_in_smem = 0;
+  uint64_t launches = 0;
+  // staging
+  void* d_stage = nullptr; size_t stage_bytes = 0;
+  // profiling
+  bool profile = false; std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events; double prof_ms = 0.0; uint64_t prof_n = 0;
+  // nccl
+  void* nccl_comm = nullptr; int nccl_ranks = 0;
+  std::string err;
+};
+
+namespace {
+
+#define CK(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e__ = (call);                                                                          \
+    if (e__ != cudaSuccess) {                                                                          \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                                  \
+      return (e__ == cudaErrorMemoryAllocation) ? BMC_ERR_NOMEM : BMC_ERR_CUDA;                        \
+    }                                                                                                  \
+  } while (0)
+
+static size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+template <class T> static int dev_alloc(bmc_ctx* ctx, T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  CK(cudaMalloc((void**)p, n * sizeof(T)));
+  return BMC_OK;
+}
+template <class T> static void dev_free(T*& p) { if (p) cudaFree(p); p = nullptr; }
+
+static int check_launch(bmc_ctx* ctx, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { ctx->err = std::string(what) + ": " + cudaGetErrorString(e); return BMC_ERR_CUDA; }
+  ctx->launches++;
+  return BMC_OK;
+}
+
+static void free_container(bmc_ctx* c) {
+  dev_free(c->props); dev_free(c->pos); dev_free(c->status); dev_free(c->age_hyd); dev_free(c->age_div);
+  dev_free(c->buf_props); dev_free(c->buf_pos); dev_free(c->buf_mother);
+  dev_free(c->div_mask); dev_free(c->tile_div); dev_free(c->tile_off);
+  dev_free(c->tile_gap_off); dev_free(c->tile_idle_off); dev_free(c->src);
+  c->cap = 0; c->buf_cap = 0;
+}
+
+// ParticlesContainer::_resize + __allocate_buffer__ (particles_container.hpp:601-643, 669-685):
+// (re)allocate every column for `new_cap` slots, keeping the first `keep` slots.
+static int resize_container(bmc_ctx* ctx, size_t new_cap, size_t keep) {
+  new_cap = round_up(std::max<size_t>(new_cap, kTile), kTile);
+  if (new_cap > 0xFFFFFFF0ull) { ctx->err = "capacity exceeds 2^32 slots per context"; return BMC_ERR_RANGE; }
+  const int nv = ctx->vt.n_var;
+  float* props = nullptr; uint32_t* pos = nullptr; uint8_t* status = nullptr; float *ah = nullptr, *ad = nullptr;
+  int rc;
+  if ((rc = dev_alloc(ctx, &props, new_cap * nv))) return rc;
+  if ((rc = dev_alloc(ctx, &pos, new_cap))) return rc;
+  if ((rc = dev_alloc(ctx, &status, new_cap))) return rc;
+  if ((rc = dev_alloc(ctx, &ah, new_cap))) return rc;
+  if ((rc = dev_alloc(ctx, &ad, new_cap))) return rc;
+  cudaStream_t s = ctx->stream;
+  CK(cudaMemsetAsync(status, 0, new_cap, s));
+  CK(cudaMemsetAsync(pos, 0, new_cap * 4, s));
+  CK(cudaMemsetAsync(ah, 0, new_cap * 4, s));
+  CK(cudaMemsetAsync(ad, 0, new_cap * 4, s));
+  CK(cudaMemsetAsync(props, 0, new_cap * nv * 4, s));
+  if (keep && ctx->props) {
+    for (int k = 0; k < nv; ++k)
+      CK(cudaMemcpyAsync(props + (size_t)k * new_cap, ctx->props + (size_t)k * ctx->cap, keep * 4, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(pos, ctx->pos, keep * 4, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(status, ctx->status, keep, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(ah, ctx->age_hyd, keep * 4, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(ad, ctx->age_div, keep * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  free_container(ctx);
+  ctx->props = props; ctx->pos = pos; ctx->status = status; ctx->age_hyd = ah; ctx->age_div = ad;
+  ctx->cap = new_cap;
+  // division buffer: ceil(buffer_ratio * n_allocated)
+  ctx->buf_cap = round_up((size_t)std::ceil(ctx->buffer_ratio * (double)new_cap), 4);
+  if ((rc = dev_alloc(ctx, &ctx->buf_props, ctx->buf_cap * nv))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->buf_pos, ctx->buf_cap))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->buf_mother, ctx->buf_cap))) return rc;
+  const size_t n_tiles = new_cap / kTile;
+  if ((rc = dev_alloc(ctx, &ctx->div_mask, new_cap / 32))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->tile_div, n_tiles))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->tile_off, n_tiles))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->tile_gap_off, n_tiles))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->tile_idle_off, n_tiles))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->src, new_cap))) return rc;
+  CK(cudaMemsetAsync(ctx->div_mask, 0, new_cap / 32 * 4, s));
+  CK(cudaMemsetAsync(ctx->tile_div, 0, n_tiles * 4, s));
+  CK(cudaMemsetAsync(ctx->tile_off, 0, n_tiles * 4, s));
+  CK(cudaStreamSynchronize(s));
+  return BMC_OK;
+}
+
+static int ensure_stage(bmc_ctx* ctx, size_t bytes) {
+  if (ctx->stage_bytes >= bytes) return BMC_OK;
+  if (ctx->d_stage) cudaFree(ctx->d_stage);
+  ctx->d_stage = nullptr; ctx->stage_bytes = 0;
+  CK(cudaMalloc(&ctx->d_stage, bytes));
+  ctx->stage_bytes = bytes;
+  return BMC_OK;
+}
+
+// pick the persistent grid and the shared-memory source bins for the cycle kernel
+static int configure_launch(bmc_ctx* ctx) {
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, ctx->device));
+  ctx->n_sm = prop.multiProcessorCount;
+  const size_t bins_bytes = ctx->n_species * ctx->n_comp * sizeof(double);
+  // Keep >= 2 resident blocks per SM when the bins live in shared memory.
+  const size_t smem_budget = (size_t)prop.sharedMemPerBlockOptin;
+  ctx->bins_in_smem = (ctx->n_comp > 1 && bins_bytes <= std::min<size_t>(smem_budget, 100 * 1024)) ? 1 : 0;
+  ctx->smem_bins = ctx->bins_in_smem ? bins_bytes : 0;
+  if (ctx->smem_bins > 48 * 1024)
+    CK(cudaFuncSetAttribute(ctx->vt.cycle_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bins));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ctx->vt.cycle_fn, kBlock, ctx->smem_bins));
+  if (occ < 1) occ = 1;
+  const char* env = getenv("BMC_BLOCKS_PER_SM");
+  if (env && atoi(env) > 0) occ = std::min(occ, atoi(env));
+  ctx->blocks_per_sm = occ;
+  ctx->grid_cycle = std::min(ctx->n_sm * occ, kMaxGrid);
+  return BMC_OK;
+}
+
+static int refresh_mirror(bmc_ctx* ctx, bool block) {
+  // read the most recent completed asynchronous copy of DevState
+  for (int t = 0; t < 2; ++t) {
+    const int i = (ctx->mirror_next + 1 - t) & 1;  // most recent first
+    if (!ctx->mirror_valid[i]) continue;
+    cudaError_t q = block ? cudaEventSynchronize(ctx->ev_mirror[i]) : cudaEventQuery(ctx->ev_mirror[i]);
+    if (q == cudaSuccess) {
+      ctx->known_n_used = ctx->h_st[i]->n_used;
+      ctx->known_max_add = std::max<uint64_t>(ctx->known_max_add, ctx->h_st[i]->n_add);
+      return BMC_OK;
+    }
+    if (q != cudaErrorNotReady) { ctx->err = std::string("mirror: ") + cudaGetErrorString(q); return BMC_ERR_CUDA; }
+  }
+  return BMC_OK;
+}
+
+static int sync_state(bmc_ctx* ctx, DevState* out) {
+  CK(cudaMemcpyAsync(ctx->h_st[0], ctx->st, sizeof(DevState), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->mirror_valid[0] = ctx->mirror_valid[1] = false;
+  *out = *ctx->h_st[0];
+  ctx->known_n_used = out->n_used;
+  if (out->error & 2u) { ctx->err = "compaction found fewer idle tail particles than gaps (inactive counter inconsistent)"; return BMC_ERR_INVALID; }
+  return BMC_OK;
+}
+
+static int grow_if_needed(bmc_ctx* ctx) {
+  // Lazy capacity growth (ParticlesContainer::_resize on merge): the device clamps
+  // newborns to the free room, so this only has to run before the room runs out.
+  int rc = refresh_mirror(ctx, false);
+  if (rc) return rc;
+  const uint64_t margin = std::max<uint64_t>(4 * ctx->known_max_add, ctx->cap / 16);
+  if (ctx->known_n_used + margin <= ctx->cap) return BMC_OK;
+  DevState s;
+  if ((rc = sync_state(ctx, &s))) return rc;
+  if (s.n_used + margin <= ctx->cap) return BMC_OK;
+  const size_t new_cap = (size_t)std::ceil((double)(s.n_used + margin) * ctx->allocation_factor);
+  return resize_container(ctx, new_cap, (size_t)s.n_used);
+}
+
+}  // namespace
+
+// =============================================================================
+extern "C" {
+
+int bmc_create(bmc_ctx** out, const bmc_config* cfg) {
+  if (!out || !cfg) return BMC_ERR_INVALID;
+  *out = nullptr;
+  if (cfg->n_species == 0 || cfg->n_compartments == 0 || cfg->n_compartments > 0xFFFFFFF0ull) return BMC_ERR_INVALID;
+  bmc_ctx* ctx = new (std::nothrow) bmc_ctx();
+  if (!ctx) return BMC_ERR_NOMEM;
+  auto fail = [&](int rc) { fprintf(stderr, "bmc_create: %s\n", ctx->err.c_str()); bmc_ctx* t = ctx; bmc_destroy(&t); return rc; };
+  if (cfg->model == BMC_MODEL_UDF) { ctx->err = "BMC_MODEL_UDF (NVRTC) is not built in this round"; return fail(BMC_ERR_UNSUPPORTED); }
+  if (!pick_model(cfg->model, cfg->n_var_udf, ctx->vt)) { ctx->err = "unknown model / unsupported n_var_udf"; return fail(BMC_ERR_INVALID); }
+  if ((uint64_t)ctx->vt.n_c > cfg->n_species) { ctx->err = "model n_c exceeds n_species"; return fail(BMC_ERR_INVALID); }
+  ctx->device = cfg->device; ctx->model = cfg->model;
+  ctx->n_species = cfg->n_species; ctx->n_comp = cfg->n_compartments;
+  ctx->seed = cfg->seed; ctx->rank = cfg->rank;
+  if (cfg->allocation_factor > 0) ctx->allocation_factor = std::max(1.0, cfg->allocation_factor);
+  if (cfg->buffer_ratio > 0) ctx->buffer_ratio = std::min(1.0, cfg->buffer_ratio);
+  if (cfg->dead_particle_ratio_threshold > 0) ctx->dead_ratio = cfg->dead_particle_ratio_threshold;
+  ctx->min_removal = cfg->minimum_dead_particle_removal;
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e != cudaSuccess) { ctx->err = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return fail(BMC_ERR_CUDA); }
+  auto ck = [&](cudaError_t e2, const char* w) { if (e2 != cudaSuccess) { ctx->err = std::string(w) + ": " + cudaGetErrorString(e2); return false; } return true; };
+  if (!ck(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return fail(BMC_ERR_CUDA);
+  if (!ck(cudaMalloc((void**)&ctx->st, sizeof(DevState)), "cudaMalloc state")) return fail(BMC_ERR_NOMEM);
+  if (!ck(cudaMemset(ctx->st, 0, sizeof(DevState)), "memset state")) return fail(BMC_ERR_CUDA);
+  for (int i = 0; i < 2; ++i) {
+    if (!ck(cudaMallocHost((void**)&ctx->h_st[i], sizeof(DevState)), "cudaMallocHost")) return fail(BMC_ERR_NOMEM);
+    if (!ck(cudaEventCreateWithFlags(&ctx->ev_mirror[i], cudaEventDisableTiming), "cudaEventCreate")) return fail(BMC_ERR_CUDA);
+  }
+  const size_t nb = ctx->n_species * ctx->n_comp;
+  int rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_conc, nb)) || (rc = dev_alloc(ctx, &ctx->d_sources, nb)) ||
+      (rc = dev_alloc(ctx, &ctx->d_vol, ctx->n_comp)) || (rc = dev_alloc(ctx, &ctx->d_diag, ctx->n_comp)) ||
+      (rc = dev_alloc(ctx, &ctx->d_pleave, ctx->n_comp)) || (rc = dev_alloc(ctx, &ctx->blk_total, kMaxGrid + 1)) ||
+      (rc = dev_alloc(ctx, &ctx->blk_gap, kMaxGrid + 1)) || (rc = dev_alloc(ctx, &ctx->blk_idle, kMaxGrid + 1)))
+    return fail(rc);
+  cudaMemset(ctx->d_conc, 0, nb * 8); cudaMemset(ctx->d_sources, 0, nb * 8);
+  cudaMemset(ctx->d_pleave, 0, ctx->n_comp * 4);
+  cudaMemset(ctx->blk_total, 0, (kMaxGrid + 1) * 4);
+  if ((rc = configure_launch(ctx))) return fail(rc);
+  if (cfg->capacity) { if ((rc = resize_container(ctx, cfg->capacity, 0))) return fail(rc); }
+  *out = ctx;
+  return BMC_OK;
+}
+
+int bmc_destroy(bmc_ctx** h) {
+  if (!h || !*h) return BMC_ERR_INVALID;
+  bmc_ctx* c = *h;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->nccl_comm && g_nccl_destroy) g_nccl_destroy(c->nccl_comm);
+  free_container(c);
+  dev_free(c->d_conc); dev_free(c->d_sources); dev_free(c->d_vol); dev_free(c->d_diag); dev_free(c->d_cdf);
+  dev_free(c->d_pleave); dev_free(c->d_cdf_f); dev_free(c->d_neigh);
+  dev_free(c->blk_total); dev_free(c->blk_gap); dev_free(c->blk_idle);
+  dev_free(c->st);
+  if (c->d_stage) cudaFree(c->d_stage);
+  for (int i = 0; i < 2; ++i) { if (c->h_st[i]) cudaFreeHost(c->h_st[i]); if (c->ev_mirror[i]) cudaEventDestroy(c->ev_mirror[i]); }
+  for (auto& pr : c->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  *h = nullptr;
+  return BMC_OK;
+}
+
+const char* bmc_last_error(const bmc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int bmc_model_dims(const bmc_ctx* ctx, int32_t* n_var, int32_t* n_c) {
+  if (!ctx) return BMC_ERR_INVALID;
+  if (n_var) *n_var = ctx->vt.n_var;
+  if (n_c) *n_c = ctx->vt.n_c;
+  return BMC_OK;
+}
+
+int bmc_reserve(bmc_ctx* ctx, uint64_t capacity) {
+  if (!ctx) return BMC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  DevState s; int rc;
+  if ((rc = sync_state(ctx, &s))) return rc;
+  if (capacity <= ctx->cap) return BMC_OK;
+  return resize_container(ctx, capacity, (size_t)s.n_used);
+}
+
+int bmc_set_particles(bmc_ctx* ctx, uint64_t n, const float* props, const uint64_t* position, const uint8_t* status,
+                      const float* age_h, const float* age_d) {
+  if (!ctx || (n && !props)) return BMC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  int rc;
+  const size_t want = (size_t)std::ceil((double)n * ctx->allocation_factor);
+  if (want > ctx->cap || ctx->cap == 0) { if ((rc = resize_container(ctx, std::max<size_t>(want, n), 0))) return rc; }
+  cudaStream_t s = ctx->stream;
+  const int nv = ctx->vt.n_var;
+  for (int k = 0; k < nv; ++k)
+    CK(cudaMemcpyAsync(ctx->props + (size_t)k * ctx->cap, props + (size_t)k * n, n * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(ctx->st, 0, sizeof(DevState), s));
+  if (position) {
+    const size_t chunk = 1u << 22;
+    if ((rc = ensure_stage(ctx, chunk * 8))) return rc;
+    for (size_t o = 0; o < n; o += chunk) {
+      const size_t c = std::min<size_t>(chunk, n - o);
+      CK(cudaMemcpyAsync(ctx->d_stage, position + o, c * 8, cudaMemcpyHostToDevice, s));
+      pos_narrow_kernel<<<(unsigned)((c + 255) / 256), 256, 0, s>>>((const unsigned long long*)ctx->d_stage, ctx->pos + o, c,
+                                                                    (uint32_t)ctx->n_comp, &ctx->st->error);
+      if ((rc = check_launch(ctx, "pos_narrow"))) return rc;
+      CK(cudaStreamSynchronize(s));
+    }
+  } else {
+    CK(cudaMemsetAsync(ctx->pos, 0, n * 4, s));
+  }
+  if (status) CK(cudaMemcpyAsync(ctx->status, status, n, cudaMemcpyHostToDevice, s)); else CK(cudaMemsetAsync(ctx->status, 0, n, s));
+  if (age_h) CK(cudaMemcpyAsync(ctx->age_hyd, age_h, n * 4, cudaMemcpyHostToDevice, s)); else CK(cudaMemsetAsync(ctx->age_hyd, 0, n * 4, s));
+  if (age_d) CK(cudaMemcpyAsync(ctx->age_div, age_d, n * 4, cudaMemcpyHostToDevice, s)); else CK(cudaMemsetAsync(ctx->age_div, 0, n * 4, s));
+  // slots beyond n must be Idle (appended newborns rely on it)
+  if (ctx->cap > n) CK(cudaMemsetAsync(ctx->status + n, 0, ctx->cap - n, s));
+  if (status && n) {
+    count_inactive_kernel<<<std::min<unsigned>(1024, (unsigned)((n + 255) / 256)), 256, 0, s>>>(ctx->status, n, ctx->st);
+    if ((rc = check_launch(ctx, "count_inactive"))) return rc;
+  }
+  CK(cudaMemcpyAsync(&ctx->st->n_used, &n, 8, cudaMemcpyHostToDevice, s));
+  DevState hs;
+  if ((rc = sync_state(ctx, &hs))) return rc;
+  if (hs.error & 1u) { ctx->err = "particle position out of range"; return BMC_ERR_RANGE; }
+  ctx->host_step = 0; ctx->known_max_add = 0;
+  return BMC_OK;
+}
+
+int bmc_get_particles(bmc_ctx* ctx, uint64_t n, float* props, uint64_t* position, uint8_t* status, float* age_h, float* age_d) {
+  if (!ctx) return BMC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  DevState hs; int rc;
+  if ((rc = sync_state(ctx, &hs))) return rc;
+  if (n > hs.n_used) { ctx->err = "bmc_get_particles: n exceeds n_used"; return BMC_ERR_RANGE; }
+  cudaStream_t s = ctx->stream;
+  const int nv = ctx->vt.n_var;
+  if (props) for (int k = 0; k < nv; ++k)
+    CK(cudaMemcpyAsync(props + (size_t)k * n, ctx->props + (size_t)k * ctx->cap, n * 4, cudaMemcpyDeviceToHost, s));
+  if (position) {
+    const size_t chunk = 1u << 22;
+    if ((rc = ensure_stage(ctx, chunk * 8))) return rc;
+    for (size_t o = 0; o < n; o += chunk) {
+      const size_t c = std::min<size_t>(chunk, n - o);
+      pos_widen_kernel<<<(unsigned)((c + 255) / 256), 256, 0, s>>>(ctx->pos + o, (unsigned long long*)ctx->d_stage, c);
+      if ((rc = check_launch(ctx, "pos_widen"))) return rc;
+      CK(cudaMemcpyAsync(position + o, ctx->d_stage, c * 8, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+    }
+  }
+  if (status) CK(cudaMemcpyAsync(status, ctx->status, n, cudaMemcpyDeviceToHost, s));
+  if (age_h) CK(cudaMemcpyAsync(age_h, ctx->age_hyd, n * 4, cudaMemcpyDeviceToHost, s));
+  if (age_d) CK(cudaMemcpyAsync(age_d, ctx->age_div, n * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return BMC_OK;
+}
+
+int bmc_init_particles(bmc_ctx* ctx, uint64_t n, int uniform_position, const float* linit, double* total_mass) {
+  if (!ctx || n == 0) return BMC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  int rc;
+  const size_t want = (size_t)std::ceil((double)n * ctx->allocation_factor);
+  if (want > ctx->cap || ctx->cap == 0) { if ((rc = resize_container(ctx, want, 0))) return rc; }
+  cudaStream_t s = ctx->stream;
+  float* d_linit = nullptr;
+  if (linit) {
+    if ((rc = ensure_stage(ctx, n * 4))) return rc;
+    d_linit = (float*)ctx->d_stage;
+    CK(cudaMemcpyAsync(d_linit, linit, n * 4, cudaMemcpyHostToDevice, s));
+  }
+  CK(cudaMemsetAsync(ctx->st, 0, sizeof(DevState), s));
+  CK(cudaMemsetAsync(ctx->status, 0, ctx->cap, s));
+  const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->n_sm * 8);
+  ctx->vt.launch_init(ctx->props, ctx->cap, ctx->pos, ctx->status, ctx->age_hyd, ctx->age_div, n,
+                      uniform_position ? (uint32_t)ctx->n_comp : 1u, d_linit, (uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32),
+                      ctx->rank, ctx->st, grid, s);
+  if ((rc = check_launch(ctx, "init_kernel"))) return rc;
+  CK(cudaMemcpyAsync(&ctx->st->n_used, &n, 8, cudaMemcpyHostToDevice, s));
+  DevState hs;
+  if ((rc = sync_state(ctx, &hs))) return rc;
+  if (total_mass) *total_mass = hs.init_mass;
+  ctx->host_step = 0; ctx->known_max_add = 0;
+  return BMC_OK;
+}
+
+int bmc_set_weight(bmc_ctx* ctx, double w) {
+  if (!ctx || !(w > 0)) return BMC_ERR_INVALID;
+  ctx->weight = (float)w;  // deep_copy(container.weights, new_weight): float view
+  return BMC_OK;
+}
+
+int bmc_domain_update(bmc_ctx* ctx, const double* volumes, const uint64_t* neighbors_flat, const double* out_flows,
+                      const double* proba_flat, uint64_t n_cols) {
+  if (!ctx || !volumes || !out_flows) return BMC_ERR_INVALID;
+  if (ctx->n_comp > 1 && (!neighbors_flat || !proba_flat || n_cols == 0)) return BMC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  CK(cudaStreamSynchronize(s));  // tables may be in use by enqueued cycles
+  const size_t nc = ctx->n_comp, nn = nc * n_cols;
+  CK(cudaMemcpyAsync(ctx->d_vol, volumes, nc * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->d_diag, out_flows, nc * 8, cudaMemcpyHostToDevice, s));
+  if (nn) {
+    std::vector<uint32_t> nb(nn);
+    for (size_t i = 0; i < nn; ++i) {
+      if (neighbors_flat[i] >= nc) { ctx->err = "neighbor index out of range"; return BMC_ERR_RANGE; }
+      nb[i] = (uint32_t)neighbors_flat[i];
+    }
+    if ((int)n_cols != ctx->m) {
+      dev_free(ctx->d_cdf); dev_free(ctx->d_cdf_f); dev_free(ctx->d_neigh);
+      int rc;
+      if ((rc = dev_alloc(ctx, &ctx->d_cdf, nn)) || (rc = dev_alloc(ctx, &ctx->d_cdf_f, nn)) || (rc = dev_alloc(ctx, &ctx->d_neigh, nn))) return rc;
+      ctx->m = (int)n_cols;
+    }
+    CK(cudaMemcpyAsync(ctx->d_cdf, proba_flat, nn * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_neigh, nb.data(), nn * 4, cudaMemcpyHostToDevice, s));
+    derive_cdf_table_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(ctx->d_cdf, ctx->d_cdf_f, nn);
+    int rc;
+    if ((rc = check_launch(ctx, "derive_cdf"))) return rc;
+    CK(cudaStreamSynchronize(s));  // nb goes out of scope
+  }
+  ctx->domain_set = true;
+  ctx->table_dt = -1.0;  // leave table depends on dt: rebuilt by the next cycle
+  return BMC_OK;
+}
+
+int bmc_set_leaving_flows(bmc_ctx* ctx, uint64_t n, const bmc_leaving_flow* f) {
+  if (!ctx || (n && !f)) return BMC_ERR_INVALID;
+  if (n > (uint64_t)kMaxFlows) { ctx->err = "too many leaving flows (max 16)"; return BMC_ERR_UNSUPPORTED; }
+  for (uint64_t i = 0; i < n; ++i) if (f[i].index >= ctx->n_comp) { ctx->err = "leaving flow index out of range"; return BMC_ERR_RANGE; }
+  ctx->flows.assign(f, f + n);
+  return BMC_OK;
+}
+
+int bmc_set_concentrations(bmc_ctx* ctx, const double* c) {
+  if (!ctx || !c) return BMC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  // pageable source: the runtime stages the bytes before returning, so the caller's
+  // buffer is free on return; ordering with enqueued cycles is by stream order.
+  CK(cudaMemcpyAsync(ctx->d_conc, c, ctx->n_species * ctx->n_comp * 8, cudaMemcpyHostToDevice, ctx->stream));
+  return BMC_OK;
+}
+
+int bmc_get_sources(bmc_ctx* ctx, double* out) {
+  if (!ctx || !out) return BMC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(out, ctx->d_sources, ctx->n_species * ctx->n_comp * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return BMC_OK;
+}
+
+int bmc_cycle(bmc_ctx* ctx, double d_t) {
+  if (!ctx || !(d_t >= 0)) return BMC_ERR_INVALID;
+  if (ctx->cap == 0) { ctx->err = "no particles: call bmc_set_particles / bmc_init_particles first"; return BMC_ERR_INVALID; }
+  if (ctx->n_comp > 1 && !ctx->domain_set) { ctx->err = "multi-compartment case without bmc_domain_update"; return BMC_ERR_INVALID; }
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = grow_if_needed(ctx))) return rc;
+  cudaStream_t s = ctx->stream;
+  const uint32_t n_bins = (uint32_t)(ctx->n_species * ctx->n_comp);
+  const bool enable_move = ctx->n_comp > 1;        // kernels.hpp:53-55
+  const bool enable_leave = !ctx->flows.empty();   // kernels.hpp:56
+  if (enable_move && ctx->table_dt != d_t) {
+    derive_leave_table_kernel<<<(unsigned)((ctx->n_comp + 255) / 256), 256, 0, s>>>(ctx->d_diag, ctx->d_vol, d_t, ctx->d_pleave, (uint32_t)ctx->n_comp);
+    if ((rc = check_launch(ctx, "derive_leave"))) return rc;
+    ctx->table_dt = d_t;
+  }
+  prepare_kernel<<<(n_bins + 255) / 256, 256, 0, s>>>(ctx->st, ctx->d_sources, n_bins, ctx->cap, ctx->buf_cap, (unsigned)ctx->grid_cycle);
+  if ((rc = check_launch(ctx, "prepare"))) return rc;
+
+  CycleParams p;
+  memset(&p, 0, sizeof(p));
+  p.props = ctx->props; p.cap = ctx->cap; p.pos = ctx->pos; p.status = ctx->status; p.age_hyd = ctx->age_hyd; p.age_div = ctx->age_div;
+  p.st = ctx->st;
+  p.buf_props = ctx->buf_props; p.buf_stride = ctx->buf_cap; p.buf_pos = ctx->buf_pos; p.buf_mother = ctx->buf_mother;
+  p.div_mask = ctx->div_mask; p.tile_div = ctx->tile_div; p.tile_off = ctx->tile_off; p.blk_total = ctx->blk_total;
+  p.p_leave = ctx->d_pleave; p.cdf = ctx->d_cdf_f; p.neigh = ctx->d_neigh; p.m = ctx->m; p.n_comp = (uint32_t)ctx->n_comp;
+  p.n_flows = (int)ctx->flows.size();
+  for (int i = 0; i < p.n_flows; ++i) {
+    p.outlets[i].index = (uint32_t)ctx->flows[i].index;
+    p.outlets[i].flow = ctx->flows[i].flow;
+    p.outlets[i].dt_flow = d_t * ctx->flows[i].flow;  // (dt * flow), probability_leaving.hpp:28
+    p.outlets[i].volume = ctx->flows[i].volume;
+  }
+  p.conc = ctx->d_conc; p.n_species = (uint32_t)ctx->n_species; p.sources = ctx->d_sources;
+  p.weight = ctx->weight; p.dt = d_t; p.dt_f = (float)d_t;
+  p.step = (uint32_t)ctx->host_step; p.rank = ctx->rank; p.seed_lo = (uint32_t)ctx->seed; p.seed_hi = (uint32_t)(ctx->seed >> 32);
+  p.enable_move = enable_move; p.enable_leave = enable_leave; p.bins_in_smem = ctx->bins_in_smem;
+
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx->profile) {
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, s));
+  }
+  ctx->vt.launch_cycle(p, ctx->grid_cycle, ctx->smem_bins, s);
+  if ((rc = check_launch(ctx, "cycle_kernel"))) return rc;
+  if (ctx->profile) { CK(cudaEventRecord(e1, s)); ctx->prof_events.emplace_back(e0, e1); }
+
+  post_plan_kernel<<<1, 32, 0, s>>>(ctx->st, ctx->min_removal, ctx->dead_ratio);
+  if ((rc = check_launch(ctx, "post_plan"))) return rc;
+
+  CompactParams cp;
+  cp.props = ctx->props; cp.cap = ctx->cap; cp.n_var = ctx->vt.n_var; cp.pos = ctx->pos; cp.status = ctx->status;
+  cp.age_hyd = ctx->age_hyd; cp.age_div = ctx->age_div; cp.st = ctx->st;
+  cp.tile_gap_off = ctx->tile_gap_off; cp.tile_idle_off = ctx->tile_idle_off; cp.blk_gap = ctx->blk_gap; cp.blk_idle = ctx->blk_idle; cp.src = ctx->src;
+  {
+    // Exits only happen with outlets, but inactive particles may also come from the
+    // caller's initial statuses; the kernels return immediately unless triggered.
+    const int gc = std::min(ctx->n_sm * 2, kMaxGrid);
+    compact_count_kernel<<<gc, 1024, 0, s>>>(cp);
+    if ((rc = check_launch(ctx, "compact_count"))) return rc;
+    compact_src_kernel<<<gc, 1024, 0, s>>>(cp);
+    if ((rc = check_launch(ctx, "compact_src"))) return rc;
+    compact_move_kernel<<<gc, 1024, 0, s>>>(cp);
+    if ((rc = check_launch(ctx, "compact_move"))) return rc;
+    compact_commit_kernel<<<ctx->n_sm, 256, 0, s>>>(cp);
+    if ((rc = check_launch(ctx, "compact_commit"))) return rc;
+  }
+  InsertParams ip;
+  ip.props = ctx->props; ip.cap = ctx->cap; ip.n_var = ctx->vt.n_var; ip.pos = ctx->pos; ip.status = ctx->status;
+  ip.age_hyd = ctx->age_hyd; ip.age_div = ctx->age_div; ip.st = ctx->st;
+  ip.buf_props = ctx->buf_props; ip.buf_stride = ctx->buf_cap; ip.buf_pos = ctx->buf_pos; ip.buf_mother = ctx->buf_mother;
+  ip.div_mask = ctx->div_mask; ip.tile_div = ctx->tile_div; ip.tile_off = ctx->tile_off; ip.blk_total = ctx->blk_total;
+  ip.count_step = 1;
+  insert_kernel<<<ctx->n_sm * 2, 256, 0, s>>>(ip);
+  if ((rc = check_launch(ctx, "insert"))) return rc;
+  finalize_kernel<<<ctx->n_sm * 2, 256, 0, s>>>(ip);
+  if ((rc = check_launch(ctx, "finalize"))) return rc;
+
+  // asynchronous mirror of the device bookkeeping (never waited on here)
+  const int mi = ctx->mirror_next;
+  CK(cudaMemcpyAsync(ctx->h_st[mi], ctx->st, sizeof(DevState), cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(ctx->ev_mirror[mi], s));
+  ctx->mirror_valid[mi] = true;
+  ctx->mirror_next ^= 1;
+  ctx->host_step++;
+  return BMC_OK;
+}
+
+int bmc_sync(bmc_ctx* ctx) {
+  if (!ctx) return BMC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return BMC_OK;
+}
+
+int bmc_get_counters(bmc_ctx* ctx, bmc_counters* out) {
+  if (!ctx || !out) return BMC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  DevState s; int rc;
+  if ((rc = sync_state(ctx, &s))) return rc;
+  for (int i = 0; i < BMC_N_EVENTS; ++i) out->events[i] = s.events[i];
+  out->n_used = s.n_used; out->n_inactive = s.inactive; out->last_out = s.last_out; out->last_dead = s.last_dead;
+  out->last_waiting_allocation = s.last_waiting; out->buffer_index = 0; out->capacity = ctx->cap;
+  out->total_out = s.total_out; out->total_new = s.total_new; out->n_compactions = s.n_compactions; out->step = s.step;
+  out->buffer_capacity = ctx->buf_cap;
+  return BMC_OK;
+}
+
+int bmc_repartition(bmc_ctx* ctx, uint64_t* out) {
+  if (!ctx || !out) return BMC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = ensure_stage(ctx, ctx->n_comp * 8))) return rc;
+  cudaStream_t s = ctx->stream;
+  CK(cudaMemsetAsync(ctx->d_stage, 0, ctx->n_comp * 8, s));
+  if (ctx->cap) {
+    repartition_kernel<<<ctx->n_sm * 4, 256, 0, s>>>(ctx->pos, ctx->status, ctx->st, (unsigned long long*)ctx->d_stage);
+    if ((rc = check_launch(ctx, "repartition"))) return rc;
+  }
+  CK(cudaMemcpyAsync(out, ctx->d_stage, ctx->n_comp * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return BMC_OK;
+}
+
+int bmc_compact(bmc_ctx* ctx) {
+  if (!ctx || ctx->cap == 0) return BMC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  int rc;
+  const unsigned int one = 1;
+  CK(cudaMemcpyAsync(&ctx->st->force_compact, &one, 4, cudaMemcpyHostToDevice, s));
+  const unsigned long long zero = 0;
+  CK(cudaMemcpyAsync(&ctx->st->step_exit, &zero, 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(&ctx->st->buf_index, &zero, 8, cudaMemcpyHostToDevice, s));
+  post_plan_kernel<<<1, 32, 0, s>>>(ctx->st, ctx->min_removal, ctx->dead_ratio);
+  if ((rc = check_launch(ctx, "post_plan"))) return rc;
+  CompactParams cp;
+  cp.props = ctx->props; cp.cap = ctx->cap; cp.n_var = ctx->vt.n_var; cp.pos = ctx->pos; cp.status = ctx->status;
+  cp.age_hyd = ctx->age_hyd; cp.age_div = ctx->age_div; cp.st = ctx->st;
+  cp.tile_gap_off = ctx->tile_gap_off; cp.tile_idle_off = ctx->tile_idle_off; cp.blk_gap = ctx->blk_gap; cp.blk_idle = ctx->blk_idle; cp.src = ctx->src;
+  const int gc = std::min(ctx->n_sm * 2, kMaxGrid);
+  compact_count_kernel<<<gc, 1024, 0, s>>>(cp); if ((rc = check_launch(ctx, "compact_count"))) return rc;
+  compact_src_kernel<<<gc, 1024, 0, s>>>(cp); if ((rc = check_launch(ctx, "compact_src"))) return rc;
+  compact_move_kernel<<<gc, 1024, 0, s>>>(cp); if ((rc = check_launch(ctx, "compact_move"))) return rc;
+  compact_commit_kernel<<<ctx->n_sm, 256, 0, s>>>(cp); if ((rc = check_launch(ctx, "compact_commit"))) return rc;
+  InsertParams ip;
+  memset(&ip, 0, sizeof(ip));
+  ip.st = ctx->st; ip.buf_mother = ctx->buf_mother; ip.div_mask = ctx->div_mask; ip.tile_div = ctx->tile_div;
+  // n_add is 0 here: finalize only commits n_used / inactive
+  ip.count_step = 0;
+  finalize_kernel<<<1, 256, 0, s>>>(ip); if ((rc = check_launch(ctx, "finalize"))) return rc;
+  DevState hs;
+  return sync_state(ctx, &hs);
+}
+
+int bmc_sources_device(bmc_ctx* ctx, double** ptr, uint64_t* n) {
+  if (!ctx || !ptr) return BMC_ERR_INVALID;
+  *ptr = ctx->d_sources; if (n) *n = ctx->n_species * ctx->n_comp;
+  return BMC_OK;
+}
+int bmc_concentrations_device(bmc_ctx* ctx, double** ptr, uint64_t* n) {
+  if (!ctx || !ptr) return BMC_ERR_INVALID;
+  *ptr = ctx->d_conc; if (n) *n = ctx->n_species * ctx->n_comp;
+  return BMC_OK;
+}
+int bmc_stream(bmc_ctx* ctx, void** s) {
+  if (!ctx || !s) return BMC_ERR_INVALID;
+  *s = (void*)ctx->stream;
+  return BMC_OK;
+}
+int bmc_launch_count(const bmc_ctx* ctx, uint64_t* n) {
+  if (!ctx || !n) return BMC_ERR_INVALID;
+  *n = ctx->launches;
+  return BMC_OK;
+}
+int bmc_profile_enable(bmc_ctx* ctx, int on) {
+  if (!ctx) return BMC_ERR_INVALID;
+  ctx->profile = on != 0;
+  return BMC_OK;
+}
+int bmc_profile_read(bmc_ctx* ctx, double* ms_total, uint64_t* n) {
+  if (!ctx) return BMC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (auto& pr : ctx->prof_events) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) { ctx->prof_ms += ms; ctx->prof_n++; }
+    cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+  }
+  ctx->prof_events.clear();
+  if (ms_total) *ms_total = ctx->prof_ms;
+  if (n) *n = ctx->prof_n;
+  ctx->prof_ms = 0.0; ctx->prof_n = 0;
+  return BMC_OK;
+}
+
+// ---- NCCL (resolved lazily with dlopen so the library has no link-time
+// dependency and shares whatever libnccl the process already loaded) ----------
+namespace {
+struct NcclId { char b[128]; };  // ncclUniqueId (NCCL_UNIQUE_ID_BYTES = 128), passed by value
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+}  // namespace
+static NcclApi g_nccl;
+static bool load_nccl(std::string& err) {
+  if (g_nccl.lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nme : names) { g_nccl.lib = dlopen(nme, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.lib) break; }
+  if (!g_nccl.lib) { err = "libnccl.so.2 not found"; return false; }
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(g_nccl.lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl_destroy = g_nccl.CommDestroy;
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) { err = "libnccl symbols missing"; return false; }
+  return true;
+}
+int bmc_nccl_unique_id(uint8_t* id128) {
+  std::string err;
+  if (!id128 || !load_nccl(err)) return BMC_ERR_NCCL;
+  return g_nccl.GetUniqueId(id128) == 0 ? BMC_OK : BMC_ERR_NCCL;
+}
+int bmc_comm_init(bmc_ctx* ctx, int n_ranks, int rank, const uint8_t* id128) {
+  if (!ctx || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return BMC_ERR_INVALID;
+  if (!load_nccl(ctx->err)) return BMC_ERR_NCCL;
+  CK(cudaSetDevice(ctx->device));
+  NcclId id; memcpy(id.b, id128, 128);
+  const int r = g_nccl.CommInitRank(&ctx->nccl_comm, n_ranks, id, rank);
+  if (r != 0) { ctx->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return BMC_ERR_NCCL; }
+  ctx->nccl_ranks = n_ranks;
+  return BMC_OK;
+}
+int bmc_allreduce_sources(bmc_ctx* ctx) {
+  if (!ctx) return BMC_ERR_INVALID;
+  if (!ctx->nccl_comm) { ctx->err = "bmc_comm_init not called"; return BMC_ERR_INVALID; }
+  CK(cudaSetDevice(ctx->device));
+  // ncclFloat64 = 8, ncclSum = 0
+  const int r = g_nccl.AllReduce(ctx->d_sources, ctx->d_sources, ctx->n_species * ctx->n_comp, 8, 0, ctx->nccl_comm, ctx->stream);
+  if (r != 0) { ctx->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return BMC_ERR_NCCL; }
+  ctx->launches++;
+  return BMC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,189 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.
+
+Deterministic mode (north_star): RNG-free model update/division, fixed flow map,
+shared Philox uniforms for move/exit -> compartment indices, statuses and all
+counters bit-exact; float properties and ages required to 1e-6 relative and in
+fact compared BIT-EXACT (both sides are IEEE without contraction); source terms
+to 1e-9 relative (fp64 accumulation, different summation order).
+"""
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+SRC_RTOL = 1e-9
+
+
+def _pair(bmc, orc, case, **kw):
+    g = bmc.ParticleLoop(case["model"], case["n_species"], case["n_comp"], seed=case["seed"], n_var_udf=case["n_var_udf"], **kw)
+    o = orc.OracleLoop(case["model"], case["n_species"], case["n_comp"], seed=case["seed"], n_var_udf=case["n_var_udf"],
+                       n_threads=4, **kw)
+    return g, o
+
+
+def _compare(g, o, exact=True):
+    cg, co = g.counters(), o.counters()
+    util.assert_counters_equal(cg, co)
+    n = co["n_used"]
+    util.assert_state_equal(g.get_particles(n), o.get_particles(n), n, exact_props=exact)
+    assert np.array_equal(g.repartition(), o.repartition())
+
+
+def _compare_sources(sg, so):
+    for a, b in zip(sg, so):
+        scale = np.max(np.abs(b)) + 1e-300
+        assert np.max(np.abs(a - b)) <= SRC_RTOL * scale, np.max(np.abs(a - b)) / scale
+
+
+@pytest.mark.parametrize("model", ["fixed_length", "monod", "simple_acetate", "wide_udf"])
+def test_single_step_multi_compartment(bmc, orc, synth, model):
+    case = util.make_case(synth, model, 50_000, 500, p_move=0.2, p_exit=0.05)
+    g, o = _pair(bmc, orc, case)
+    util.load_case(g, case); util.load_case(o, case)
+    sg = util.run_steps(g, case, 1, collect=True); so = util.run_steps(o, case, 1, collect=True)
+    _compare_sources(sg, so)
+    _compare(g, o)
+
+
+@pytest.mark.parametrize("model", ["fixed_length", "monod", "wide_udf"])
+def test_many_steps_division_exit_compaction(bmc, orc, synth, model):
+    # dt large enough that cells divide, leave through the outlet, and the 1 % dead
+    # threshold triggers compaction several times
+    case = util.make_case(synth, model, 120_000, 500, dt=20.0, near_division=0.8, p_move=0.3, p_exit=0.3)
+    g, o = _pair(bmc, orc, case)
+    util.load_case(g, case); util.load_case(o, case)
+    for blk in range(4):
+        sg = util.run_steps(g, case, 5, collect=True); so = util.run_steps(o, case, 5, collect=True)
+        _compare_sources(sg, so)
+        _compare(g, o)
+    c = o.counters()
+    assert c["total_new"] > 0 and c["total_out"] > 0 and c["n_compactions"] >= 2, c
+
+
+def test_simple_acetate_deterministic_part(bmc, orc, synth):
+    # division of simple_acetate draws random numbers (stochastic mode); with no
+    # division in range the whole step is deterministic and must be bit-exact
+    case = util.make_case(synth, "simple_acetate", 80_000, 500, dt=0.5, p_move=0.2, p_exit=0.2)
+    case["props"][1, :] = 1.0  # l_max far away: no division
+    g, o = _pair(bmc, orc, case)
+    util.load_case(g, case); util.load_case(o, case)
+    sg = util.run_steps(g, case, 12, collect=True); so = util.run_steps(o, case, 12, collect=True)
+    _compare_sources(sg, so)
+    _compare(g, o)
+    assert o.counters()["total_new"] == 0
+
+
+@pytest.mark.parametrize("model", ["fixed_length", "monod"])
+def test_zero_d_batch_and_chemostat(bmc, orc, synth, model):
+    # BASELINE configs[0]: 0D single compartment, 1e5 particles
+    for outlet in (False, True):
+        case = util.make_case(synth, model, 100_000, 1, dt=5.0, near_division=0.7, outlet=outlet, p_exit=0.02)
+        g, o = _pair(bmc, orc, case)
+        util.load_case(g, case); util.load_case(o, case)
+        sg = util.run_steps(g, case, 10, collect=True); so = util.run_steps(o, case, 10, collect=True)
+        _compare_sources(sg, so)
+        _compare(g, o)
+        if outlet:
+            assert o.counters()["total_out"] > 0
+        assert o.counters()["events"]["Move"] == 0
+
+
+@pytest.mark.parametrize("n", [1, 3, 31, 1023, 1024, 1025, 4097])
+def test_ragged_sizes(bmc, orc, synth, n):
+    # the reference refuses N <= 1024 (kernels.hpp:163-167, Q8); we accept any N
+    case = util.make_case(synth, "monod", n, 16, dt=30.0, near_division=0.9, p_move=0.5, p_exit=0.3)
+    g, o = _pair(bmc, orc, case)
+    util.load_case(g, case); util.load_case(o, case)
+    sg = util.run_steps(g, case, 6, collect=True); so = util.run_steps(o, case, 6, collect=True)
+    _compare_sources(sg, so)
+    _compare(g, o)
+
+
+def test_initial_inactive_particles_and_forced_compaction(bmc, orc, synth):
+    case = util.make_case(synth, "fixed_length", 30_000, 64, dt=1.0, p_move=0.3, outlet=False)
+    rng = np.random.default_rng(7)
+    status = np.where(rng.random(case["n"]) < 0.3, 2, 0).astype(np.uint8)
+    status[-5:] = 2
+    g, o = _pair(bmc, orc, case, dead_ratio=0.9)
+    util.load_case(g, case, status); util.load_case(o, case, status)
+    util.run_steps(g, case, 2); util.run_steps(o, case, 2)
+    _compare(g, o)                      # no compaction yet (threshold 90 %)
+    assert o.counters()["n_compactions"] == 0
+    g.compact(); o.compact()            # force_remove_dead
+    _compare(g, o)
+    assert g.counters()["n_inactive"] == 0
+    util.run_steps(g, case, 2); util.run_steps(o, case, 2)
+    _compare(g, o)
+
+
+def test_all_particles_exit(bmc, orc, synth):
+    case = util.make_case(synth, "fixed_length", 5_000, 1, dt=1.0, outlet=True, p_exit=1e9)
+    g, o = _pair(bmc, orc, case)
+    util.load_case(g, case); util.load_case(o, case)
+    util.run_steps(g, case, 2); util.run_steps(o, case, 2)
+    cg, co = g.counters(), o.counters()
+    util.assert_counters_equal(cg, co)
+
+
+def test_division_buffer_overflow_counts(bmc, orc, synth):
+    # every cell divides in the first step; buffer_ratio 0.1 cannot hold them.
+    # Which mothers overflow is order dependent (also in the reference), the counts are not.
+    case = util.make_case(synth, "fixed_length", 20_000, 8, dt=1.0, outlet=False)
+    case["props"][0, :] = 2.5e-6
+    kw = dict(buffer_ratio=0.1, allocation_factor=1.5)
+    g, o = _pair(bmc, orc, case, **kw)
+    util.load_case(g, case); util.load_case(o, case)
+    util.run_steps(g, case, 1); util.run_steps(o, case, 1)
+    cg, co = g.counters(), o.counters()
+    assert cg["buffer_capacity"] >= co["buffer_capacity"]  # device rounds capacity up to whole tiles
+    assert cg["events"]["NewParticle"] == co["events"]["NewParticle"] == 20_000
+    assert cg["events"]["Overflow"] == 20_000 - cg["total_new"]
+    assert cg["last_waiting_allocation"] == cg["events"]["Overflow"] > 0
+    assert cg["n_used"] == 20_000 + cg["total_new"]
+    # overflowed mothers keep l >= l_max and retry: after enough steps everybody has divided once
+    for _ in range(12):
+        util.run_steps(g, case, 1)
+    assert g.counters()["total_new"] == 20_000 or g.counters()["n_used"] >= 40_000
+
+
+def test_philox_stream_identity(bmc, orc, synth):
+    # different seed / rank -> different trajectories; same seed -> identical reruns
+    case = util.make_case(synth, "monod", 20_000, 100, p_move=0.3, p_exit=0.2)
+    outs = []
+    for seed, rank in ((1, 0), (1, 0), (2, 0), (1, 1)):
+        g = bmc.ParticleLoop("monod", 1, 100, seed=seed, rank=rank)
+        util.load_case(g, case)
+        util.run_steps(g, case, 3)
+        outs.append(g.get_particles()["position"].copy())
+        o = orc.OracleLoop("monod", 1, 100, seed=seed, rank=rank)
+        util.load_case(o, case); util.run_steps(o, case, 3)
+        assert np.array_equal(outs[-1], o.get_particles()["position"])
+    assert np.array_equal(outs[0], outs[1])
+    assert not np.array_equal(outs[0], outs[2])
+    assert not np.array_equal(outs[0], outs[3])
+
+
+def test_particle_balance_identity(bmc, synth):
+    # apps/core/src/post_process.cpp:92-117: sum(repartition) == new - removed + N0
+    case = util.make_case(synth, "monod", 200_000, 500, dt=20.0, near_division=0.8, p_move=0.3, p_exit=0.3)
+    g = bmc.ParticleLoop("monod", 1, 500)
+    util.load_case(g, case)
+    util.run_steps(g, case, 15)
+    c = g.counters()
+    assert int(g.repartition().sum()) == c["total_new"] - c["total_out"] + case["n"]
+    assert c["n_used"] - c["n_inactive"] == int(g.repartition().sum())
+
+
+def test_device_init_matches_oracle_deterministic_model(bmc, orc, synth):
+    # mc_init_first: fixed_length is configurable (lengths given) -> positions (integer) bit-exact, mass to 1e-12
+    n, nc = 50_000, 500
+    rng = np.random.default_rng(3)
+    linit = (1e-6 + 1e-6 * rng.random(n)).astype(np.float32)
+    g = bmc.ParticleLoop("fixed_length", 1, nc, seed=77)
+    o = orc.OracleLoop("fixed_length", 1, nc, seed=77)
+    mg = g.init_particles(n, True, linit); mo = o.init_particles(n, True, linit)
+    assert abs(mg - mo) <= 1e-12 * abs(mo)
+    util.assert_state_equal(g.get_particles(n), o.get_particles(n), n)
+    assert len(np.unique(g.get_particles(n)["position"])) == nc
