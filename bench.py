@@ -53,15 +53,22 @@ def peaks():
 
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -70,7 +77,7 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
     def stop(self):
         if not self.proc:
@@ -80,21 +87,31 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nme, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
+
+        def collect(lines):
+            sm, mx, reasons = [], [], set()
+            for _, ln in lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for nme, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            return sm, mx, reasons
+        # samples are printed ~one period after they were taken: accept [begin, end + 0.15 s]
+        inside = [x for x in self.lines if self.t_begin is not None and self.t_begin <= x[0] <= (self.t_end or 1e30) + 0.15]
+        sm, mx, reasons = collect(inside)
+        scope = "timed region"
+        if not sm:
+            sm, mx, reasons = collect(self.lines)
+            scope = "whole run (timed region shorter than the sampling period)"
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "scope": scope}
 
 
 def build_case(synth, model, n_comp, dt, p_exit):
@@ -159,8 +176,8 @@ def run_reference(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--particles", type=int, default=0, help="override particles per GPU")
@@ -223,24 +240,25 @@ def main():
             loop.allreduce_sources()
 
     # ---------------- value: device-resident steps -----------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step_resident()
     barrier()
     n_live0 = loop.counters()["n_used"]
     launches0 = loop.launch_count()
     loop.profile_enable(True)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record(stream)
     for _ in range(args.steps):
         step_resident()
     e1.record(stream)
     barrier()
+    sampler.mark_end()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     kernel_ms, kernel_n = loop.profile_read()
     loop.profile_enable(False)
     launches = loop.launch_count() - launches0
@@ -266,6 +284,8 @@ def main():
     ms_e2e = f0.elapsed_time(f1)
     n_e1 = loop.counters()["n_used"]
     live_e2e = 0.5 * (n_e0 + n_e1)
+
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---------------- reduce over ranks (max time, sum particles) ---------------
     stats = torch.tensor([ms, ms_e2e, live_avg, live_e2e, kernel_ms / max(1, kernel_n), float(launches)], dtype=torch.float64,

@@ -72,7 +72,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("BMC_LIB") or LIB_PATH  # BMC_LIB: tuning builds of the same ABI
     if not os.path.exists(p):
         raise FileNotFoundError(
             f"{p} not found: the CUDA extension is not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "

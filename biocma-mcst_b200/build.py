@@ -33,12 +33,13 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in DEPS if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    if out is None and not force and not needs_build():
         return OUT
+    out = out or OUT
     cmd = [nvcc_path(), "-std=c++17", "-O3", "-lineinfo", "-fmad=false",
            "-gencode", "arch=compute_100a,code=sm_100a",
-           "-Xcompiler", "-fPIC", "-shared", "-o", OUT] + SOURCES + ["-ldl"]
+           "-Xcompiler", "-fPIC", "-shared", "-o", out] + [f"-D{d}" for d in defines] + SOURCES + ["-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     env = dict(os.environ)
@@ -51,8 +52,10 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libbmc_b200.so")
     if verbose:
         sys.stderr.write(r.stdout + r.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[2:] for a in sys.argv[1:] if a.startswith("-o")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))

@@ -27,10 +27,12 @@ struct ModelVT {
   void (*launch_cycle)(const CycleParams&, int grid, size_t smem, cudaStream_t);
   void (*launch_init)(float*, size_t, uint32_t*, uint8_t*, float*, float*, unsigned long long, uint32_t, const float*,
                       uint32_t, uint32_t, uint32_t, DevState*, int, cudaStream_t);
+  int ct;  // floats per compartment-table row
+  void (*launch_ctab)(const double*, const double*, double, const double*, uint32_t, float*, uint32_t, int, cudaStream_t);
 };
 
-template <class M, int VEC> static void launch_cycle_t(const CycleParams& p, int grid, size_t smem, cudaStream_t s) {
-  cycle_kernel<M, VEC><<<grid, kBlock, smem, s>>>(p);
+template <class M, int VEC, int MINB> static void launch_cycle_t(const CycleParams& p, int grid, size_t smem, cudaStream_t s) {
+  cycle_kernel<M, VEC, MINB><<<grid, kBlock, smem, s>>>(p);
 }
 template <class M>
 static void launch_init_t(float* props, size_t cap, uint32_t* pos, uint8_t* status, float* ah, float* ad, unsigned long long n,
@@ -38,19 +40,39 @@ static void launch_init_t(float* props, size_t cap, uint32_t* pos, uint8_t* stat
                           cudaStream_t s) {
   init_kernel<M><<<grid, 256, 0, s>>>(props, cap, pos, status, ah, ad, n, ncomp_hi, linit, slo, shi, rank, st);
 }
-template <class M, int VEC> static ModelVT make_vt() {
+template <class M>
+static void launch_ctab_t(const double* diag, const double* vol, double dt, const double* conc, uint32_t ns, float* ctab, uint32_t nc,
+                          int enable_move, cudaStream_t s) {
+  compartment_table_kernel<M><<<(nc + 127) / 128, 128, 0, s>>>(diag, vol, dt, conc, ns, ctab, nc, enable_move);
+}
+template <class M, int VEC, int MINB = 1> static ModelVT make_vt() {
   ModelVT v;
   v.n_var = M::n_var; v.n_c = M::n_c; v.vec = VEC;
-  v.cycle_fn = (const void*)cycle_kernel<M, VEC>;
-  v.launch_cycle = &launch_cycle_t<M, VEC>;
+  v.cycle_fn = (const void*)cycle_kernel<M, VEC, MINB>;
+  v.launch_cycle = &launch_cycle_t<M, VEC, MINB>;
   v.launch_init = &launch_init_t<M>;
+  v.ct = 1 + M::n_pre;
+  v.launch_ctab = &launch_ctab_t<M>;
   return v;
 }
 
 static bool pick_model(int model, int n_var_udf, ModelVT& vt) {
   switch (model) {
     case BMC_MODEL_FIXED_LENGTH: vt = make_vt<FixedLength, 4>(); return true;
-    case BMC_MODEL_MONOD: vt = make_vt<Monod, 4>(); return true;
+    case BMC_MODEL_MONOD: {
+      const char* v = getenv("BMC_VARIANT");  // tuning experiments only
+      const std::string var = v ? v : "";
+      if (var == "v4b3") vt = make_vt<Monod, 4, 3>();
+      else if (var == "v4b4") vt = make_vt<Monod, 4, 4>();
+      else if (var == "v2b4") vt = make_vt<Monod, 2, 4>();
+      else if (var == "v2b6") vt = make_vt<Monod, 2, 6>();
+      else if (var == "v2b8") vt = make_vt<Monod, 2, 8>();
+      else if (var == "v1b8") vt = make_vt<Monod, 1, 8>();
+      else if (var == "v4b1") vt = make_vt<Monod, 4, 1>();
+      else if (var == "v4b2") vt = make_vt<Monod, 4, 2>();
+      else vt = make_vt<Monod, 4, 3>();  // 80 registers -> 3 blocks (24 warps) per SM
+      return true;
+    }
     case BMC_MODEL_SIMPLE_ACETATE: vt = make_vt<SimpleAcetate, 4>(); return true;
     case BMC_MODEL_WIDE_UDF:
       switch (n_var_udf) {
@@ -86,7 +108,7 @@ struct bmc_ctx {
   // domain
   int m = 0; bool domain_set = false; double table_dt = -1.0;
   double *d_vol = nullptr, *d_diag = nullptr, *d_cdf = nullptr;
-  float *d_pleave = nullptr, *d_cdf_f = nullptr; uint32_t* d_neigh = nullptr;
+  float *d_ctab = nullptr, *d_cdf_f = nullptr; uint32_t* d_neigh = nullptr;
   std::vector<bmc_leaving_flow> flows;
   // liquid
   double *d_conc = nullptr, *d_sources = nullptr;
@@ -99,6 +121,7 @@ struct bmc_ctx {
   // launch config
   int n_sm = 148, grid_cycle = 148, blocks_per_sm = 1; size_t smem_bins = 0; int bins_in_smem = 0;
   uint64_t launches = 0;
+  int prefetch_ahead = 1;
   // staging
   void* d_stage = nullptr; size_t stage_bytes = 0;
   // profiling
@@ -218,6 +241,7 @@ static int configure_launch(bmc_ctx* ctx) {
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ctx->vt.cycle_fn, kBlock, ctx->smem_bins));
   if (occ < 1) occ = 1;
+  if (const char* pf = getenv("BMC_PREFETCH")) ctx->prefetch_ahead = std::max(0, atoi(pf));
   const char* env = getenv("BMC_BLOCKS_PER_SM");
   if (env && atoi(env) > 0) occ = std::min(occ, atoi(env));
   ctx->blocks_per_sm = occ;
@@ -301,11 +325,12 @@ int bmc_create(bmc_ctx** out, const bmc_config* cfg) {
   int rc;
   if ((rc = dev_alloc(ctx, &ctx->d_conc, nb)) || (rc = dev_alloc(ctx, &ctx->d_sources, nb)) ||
       (rc = dev_alloc(ctx, &ctx->d_vol, ctx->n_comp)) || (rc = dev_alloc(ctx, &ctx->d_diag, ctx->n_comp)) ||
-      (rc = dev_alloc(ctx, &ctx->d_pleave, ctx->n_comp)) || (rc = dev_alloc(ctx, &ctx->blk_total, kMaxGrid + 1)) ||
+      (rc = dev_alloc(ctx, &ctx->d_ctab, ctx->n_comp * (size_t)ctx->vt.ct)) || (rc = dev_alloc(ctx, &ctx->blk_total, kMaxGrid + 1)) ||
       (rc = dev_alloc(ctx, &ctx->blk_gap, kMaxGrid + 1)) || (rc = dev_alloc(ctx, &ctx->blk_idle, kMaxGrid + 1)))
     return fail(rc);
   cudaMemset(ctx->d_conc, 0, nb * 8); cudaMemset(ctx->d_sources, 0, nb * 8);
-  cudaMemset(ctx->d_pleave, 0, ctx->n_comp * 4);
+  cudaMemset(ctx->d_ctab, 0, ctx->n_comp * (size_t)ctx->vt.ct * 4);
+  cudaMemset(ctx->d_vol, 0, ctx->n_comp * 8); cudaMemset(ctx->d_diag, 0, ctx->n_comp * 8);
   cudaMemset(ctx->blk_total, 0, (kMaxGrid + 1) * 4);
   if ((rc = configure_launch(ctx))) return fail(rc);
   if (cfg->capacity) { if ((rc = resize_container(ctx, cfg->capacity, 0))) return fail(rc); }
@@ -321,7 +346,7 @@ int bmc_destroy(bmc_ctx** h) {
   if (c->nccl_comm && g_nccl_destroy) g_nccl_destroy(c->nccl_comm);
   free_container(c);
   dev_free(c->d_conc); dev_free(c->d_sources); dev_free(c->d_vol); dev_free(c->d_diag); dev_free(c->d_cdf);
-  dev_free(c->d_pleave); dev_free(c->d_cdf_f); dev_free(c->d_neigh);
+  dev_free(c->d_ctab); dev_free(c->d_cdf_f); dev_free(c->d_neigh);
   dev_free(c->blk_total); dev_free(c->blk_gap); dev_free(c->blk_idle);
   dev_free(c->st);
   if (c->d_stage) cudaFree(c->d_stage);
@@ -528,11 +553,11 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   const uint32_t n_bins = (uint32_t)(ctx->n_species * ctx->n_comp);
   const bool enable_move = ctx->n_comp > 1;        // kernels.hpp:53-55
   const bool enable_leave = !ctx->flows.empty();   // kernels.hpp:56
-  if (enable_move && ctx->table_dt != d_t) {
-    derive_leave_table_kernel<<<(unsigned)((ctx->n_comp + 255) / 256), 256, 0, s>>>(ctx->d_diag, ctx->d_vol, d_t, ctx->d_pleave, (uint32_t)ctx->n_comp);
-    if ((rc = check_launch(ctx, "derive_leave"))) return rc;
-    ctx->table_dt = d_t;
-  }
+  // per-compartment rows {leave threshold, model terms}: depends on dt, the flow map and this
+  // step's concentrations -> rebuilt every step (n_comp threads)
+  ctx->vt.launch_ctab(ctx->d_diag, ctx->d_vol, d_t, ctx->d_conc, (uint32_t)ctx->n_species, ctx->d_ctab, (uint32_t)ctx->n_comp,
+                      enable_move ? 1 : 0, s);
+  if ((rc = check_launch(ctx, "compartment_table"))) return rc;
   prepare_kernel<<<(n_bins + 255) / 256, 256, 0, s>>>(ctx->st, ctx->d_sources, n_bins, ctx->cap, ctx->buf_cap, (unsigned)ctx->grid_cycle);
   if ((rc = check_launch(ctx, "prepare"))) return rc;
 
@@ -542,7 +567,7 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   p.st = ctx->st;
   p.buf_props = ctx->buf_props; p.buf_stride = ctx->buf_cap; p.buf_pos = ctx->buf_pos; p.buf_mother = ctx->buf_mother;
   p.div_mask = ctx->div_mask; p.tile_div = ctx->tile_div; p.tile_off = ctx->tile_off; p.blk_total = ctx->blk_total;
-  p.p_leave = ctx->d_pleave; p.cdf = ctx->d_cdf_f; p.neigh = ctx->d_neigh; p.m = ctx->m; p.n_comp = (uint32_t)ctx->n_comp;
+  p.ctab = ctx->d_ctab; p.cdf = ctx->d_cdf_f; p.neigh = ctx->d_neigh; p.m = ctx->m; p.n_comp = (uint32_t)ctx->n_comp;
   p.n_flows = (int)ctx->flows.size();
   for (int i = 0; i < p.n_flows; ++i) {
     p.outlets[i].index = (uint32_t)ctx->flows[i].index;
@@ -554,6 +579,7 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   p.weight = ctx->weight; p.dt = d_t; p.dt_f = (float)d_t;
   p.step = (uint32_t)ctx->host_step; p.rank = ctx->rank; p.seed_lo = (uint32_t)ctx->seed; p.seed_hi = (uint32_t)(ctx->seed >> 32);
   p.enable_move = enable_move; p.enable_leave = enable_leave; p.bins_in_smem = ctx->bins_in_smem;
+  p.prefetch_ahead = ctx->prefetch_ahead;
 
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx->profile) {

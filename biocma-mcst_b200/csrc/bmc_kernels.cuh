@@ -31,6 +31,20 @@
 
 namespace bmc {
 
+#ifndef BMC_SCATTER_MODE
+#define BMC_SCATTER_MODE 1  // 1 = shared-memory fp64 bins (product); others are timing experiments
+#endif
+#ifndef BMC_STREAM_HINTS
+#define BMC_STREAM_HINTS 1
+#endif
+#if BMC_STREAM_HINTS
+#define BMC_LD(p) __ldcs(p)
+#define BMC_ST(p, v) __stcs(p, v)
+#else
+#define BMC_LD(p) (*(p))
+#define BMC_ST(p, v) (*(p) = (v))
+#endif
+
 constexpr int kTile = 1024;         // particles per rank-tile (bitmask / prefix granularity)
 constexpr int kBlock = 256;         // threads per block
 constexpr int kMaxFlows = 16;       // outlets (reference: n_flows <= ~10)
@@ -78,7 +92,7 @@ struct CycleParams {
   uint32_t* tile_off;   // per tile: exclusive prefix inside the owning block
   uint32_t* blk_total;  // per block: divisions in its range
   // domain (DomainState, domain.hpp:28-35) in derived single-precision form
-  const float* p_leave;    // ceil_f32(dt * diag_transition / liquid_volume)
+  const float* ctab;       // compartment table rows {leave threshold, model terms...}
   const float* cdf;        // floor_f32(cumulative_probability), row-major n_comp x m
   const uint32_t* neigh;   // neighbors, row-major n_comp x m
   int m; uint32_t n_comp;
@@ -89,6 +103,7 @@ struct CycleParams {
   double dt; float dt_f;
   uint32_t step, rank, seed_lo, seed_hi;
   int enable_move, enable_leave, bins_in_smem;
+  int prefetch_ahead;  // tiles of L2 prefetch distance (0 = off)
 };
 
 __device__ __forceinline__ unsigned warp_excl_scan(unsigned v, unsigned& total) {
@@ -103,34 +118,48 @@ __device__ __forceinline__ unsigned warp_excl_scan(unsigned v, unsigned& total) 
   return incl - v;
 }
 
+__device__ __forceinline__ uint32_t pick4(const uint32_t (&w)[4], unsigned k) {
+  return k == 0 ? w[0] : (k == 1 ? w[1] : (k == 2 ? w[2] : w[3]));
+}
+
+// Particle columns are streamed exactly once per step: load/store them with the
+// cache-streaming policy (ld/st.global.cs) so the gathered tables (concentrations,
+// leave thresholds, CDF rows, neighbours) stay resident in L1/L2.
 template <int VEC> struct VecIO;
+
+// cp.async.bulk.prefetch.L2: one thread asks the memory system to pull a whole
+// column chunk of the NEXT tile into L2 while the current tile is being computed
+// (SASS: UBLKPF).  Address and size must be multiples of 16 B.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* ptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+}
 template <> struct VecIO<4> {
   static __device__ __forceinline__ void ldf(const float* p, float (&v)[4]) {
-    const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    const float4 t = BMC_LD(reinterpret_cast<const float4*>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
   static __device__ __forceinline__ void stf(float* p, const float (&v)[4]) {
-    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    BMC_ST(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
   }
   static __device__ __forceinline__ void ldu(const uint32_t* p, uint32_t (&v)[4]) {
-    const uint4 t = *reinterpret_cast<const uint4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    const uint4 t = BMC_LD(reinterpret_cast<const uint4*>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
-  static __device__ __forceinline__ uint32_t ldb(const uint8_t* p) { return *reinterpret_cast<const uint32_t*>(p); }
+  static __device__ __forceinline__ uint32_t ldb(const uint8_t* p) { return BMC_LD(reinterpret_cast<const unsigned int*>(p)); }
 };
 template <> struct VecIO<2> {
   static __device__ __forceinline__ void ldf(const float* p, float (&v)[2]) {
-    const float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y;
+    const float2 t = BMC_LD(reinterpret_cast<const float2*>(p)); v[0] = t.x; v[1] = t.y;
   }
-  static __device__ __forceinline__ void stf(float* p, const float (&v)[2]) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+  static __device__ __forceinline__ void stf(float* p, const float (&v)[2]) { BMC_ST(reinterpret_cast<float2*>(p), make_float2(v[0], v[1])); }
   static __device__ __forceinline__ void ldu(const uint32_t* p, uint32_t (&v)[2]) {
-    const uint2 t = *reinterpret_cast<const uint2*>(p); v[0] = t.x; v[1] = t.y;
+    const uint2 t = BMC_LD(reinterpret_cast<const uint2*>(p)); v[0] = t.x; v[1] = t.y;
   }
-  static __device__ __forceinline__ uint32_t ldb(const uint8_t* p) { return *reinterpret_cast<const uint16_t*>(p); }
+  static __device__ __forceinline__ uint32_t ldb(const uint8_t* p) { return BMC_LD(reinterpret_cast<const unsigned short*>(p)); }
 };
 template <> struct VecIO<1> {
-  static __device__ __forceinline__ void ldf(const float* p, float (&v)[1]) { v[0] = *p; }
-  static __device__ __forceinline__ void stf(float* p, const float (&v)[1]) { *p = v[0]; }
-  static __device__ __forceinline__ void ldu(const uint32_t* p, uint32_t (&v)[1]) { v[0] = *p; }
-  static __device__ __forceinline__ uint32_t ldb(const uint8_t* p) { return *p; }
+  static __device__ __forceinline__ void ldf(const float* p, float (&v)[1]) { v[0] = BMC_LD(p); }
+  static __device__ __forceinline__ void stf(float* p, const float (&v)[1]) { BMC_ST(p, v[0]); }
+  static __device__ __forceinline__ void ldu(const uint32_t* p, uint32_t (&v)[1]) { v[0] = BMC_LD(p); }
+  static __device__ __forceinline__ uint32_t ldb(const uint8_t* p) { return BMC_LD(p); }
 };
 
 // -----------------------------------------------------------------------------
@@ -152,6 +181,28 @@ __global__ void prepare_kernel(DevState* st, double* sources, uint32_t n_bins, u
 }
 
 // -----------------------------------------------------------------------------
+// compartment table: everything the particle pass needs per compartment, one row
+// per compartment, rebuilt once per step (n_comp rows — 500 .. 10k — not N):
+//   col 0        ceil_f32(dt * diag_transition / liquid_volume)   leave threshold
+//   col 1..n_pre M::compartment_terms(c, compartment)             optional model hook
+// A model whose update starts with a function of the local concentration only
+// (Monod: mu = mu_max*s/(k_s+s)) can hoist it here: the IEEE division then runs once
+// per compartment instead of once per particle, with bit-identical results.
+// -----------------------------------------------------------------------------
+template <class M>
+__global__ void compartment_table_kernel(const double* diag, const double* vol, double dt, const double* conc, uint32_t n_species,
+                                         float* ctab, uint32_t n_comp, int enable_move) {
+  constexpr int CT = 1 + M::n_pre;
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_comp) return;
+  float row[CT];
+  row[0] = enable_move ? __double2float_ru(dt * diag[c] / vol[c]) : 0.0f;
+  if constexpr (M::n_pre > 0) M::compartment_terms(ConcView{conc, n_species, nullptr}, (size_t)c, row + 1);
+#pragma unroll
+  for (int k = 0; k < CT; ++k) ctab[(size_t)c * CT + k] = row[k];
+}
+
+// -----------------------------------------------------------------------------
 // cycle: the fused hot kernel.
 //   model   : CycleFunctor::operator()(TagCycle) + exec_per_particle
 //             (model_kernel.hpp:163-217, 230-268), handle_division
@@ -167,10 +218,16 @@ __global__ void prepare_kernel(DevState* st, double* sources, uint32_t n_bins, u
 // leave (post-move position), identical to the reference's kernel order because
 // particles only interact through the atomically allocated division buffer and
 // the additive source terms.
+//
+// Structure of the per-thread body (VEC particles per thread, 128-bit column
+// accesses): the common path — load, model update, age updates, leave/outlet
+// tests — is straight-line code over the VEC particles so that their dependency
+// chains interleave; everything rare (division, the neighbour pick of a mover,
+// the outlet exit draw, partially idle groups) sits behind warp-level votes.
 // -----------------------------------------------------------------------------
-template <class M, int VEC>
-__global__ void __launch_bounds__(kBlock) cycle_kernel(const __grid_constant__ CycleParams p) {
-  constexpr int NV = M::n_var, NC = M::n_c;
+template <class M, int VEC, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) cycle_kernel(const __grid_constant__ CycleParams p) {
+  constexpr int NV = M::n_var, NC = M::n_c, NP = M::n_pre, CT = 1 + M::n_pre;
   constexpr int SUB = kTile / (kBlock * VEC);  // sub-iterations per tile
   extern __shared__ double s_bins[];           // [n_species * n_comp] when bins_in_smem
   __shared__ unsigned long long s_cnt[4];      // move, exit, new, overflow
@@ -183,9 +240,10 @@ __global__ void __launch_bounds__(kBlock) cycle_kernel(const __grid_constant__ C
   const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
   const uint32_t n_bins = p.n_species * p.n_comp;
   const bool single_comp = (p.n_comp == 1);
+  const bool smem_bins = p.bins_in_smem && !single_comp;
 
   if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0ull;
-  if (p.bins_in_smem && !single_comp)
+  if (smem_bins)
     for (uint32_t k = threadIdx.x; k < n_bins; k += kBlock) s_bins[k] = 0.0;
   __syncthreads();
 
@@ -194,77 +252,113 @@ __global__ void __launch_bounds__(kBlock) cycle_kernel(const __grid_constant__ C
 #pragma unroll
   for (int j = 0; j < NC; ++j) acc0d[j] = 0.0;
   const double w = (double)p.weight;  // `const double weight = get_weight(p)` contribution_kernel.hpp:179
-  const ConcView conc{p.conc, p.n_species};
   const BufRows bufrows{p.buf_props, p.buf_stride};
+  const uint32_t outlet0 = p.n_flows > 0 ? p.outlets[0].index : 0xffffffffu;
+  const bool outlet0_live = p.n_flows > 0 && p.outlets[0].flow != 0.;
 
   for (uint32_t tile = t0; tile < t1; ++tile) {
+    if (p.prefetch_ahead && tile + p.prefetch_ahead < t1) {  // optional L2 bulk prefetch of a later tile
+      const size_t nb = (size_t)(tile + p.prefetch_ahead) * kTile;
+      const int col = (int)threadIdx.x;
+      if (col < 4 + NV) {
+        if (col == 0) l2_prefetch_bulk(p.status + nb, kTile);
+        else if (col == 1) l2_prefetch_bulk(p.pos + nb, kTile * 4);
+        else if (col == 2) l2_prefetch_bulk(p.age_div + nb, kTile * 4);
+        else if (col == 3) { if (p.enable_leave) l2_prefetch_bulk(p.age_hyd + nb, kTile * 4); }
+        else if (!((M::write_only_mask >> (col - 4)) & 1u)) l2_prefetch_bulk(p.props + (size_t)(col - 4) * p.cap + nb, kTile * 4);
+      }
+    }
 #pragma unroll 1
     for (int sub = 0; sub < SUB; ++sub) {
-      const size_t i0 = (size_t)tile * kTile + ((size_t)sub * (kBlock / 32) + warp) * (32 * VEC) + (size_t)lane * VEC;
-      const bool any_valid = i0 < n_used;
+      const size_t i_raw = (size_t)tile * kTile + ((size_t)sub * (kBlock / 32) + warp) * (32 * VEC) + (size_t)lane * VEC;
+      const bool live = i_raw < n_used;    // false only in the ragged end of the last tile
+      const size_t i0 = live ? i_raw : 0;  // dead lanes shadow slot 0 (loads stay in range, nothing is stored)
 
       // ---- front-batched loads (all independent; MLP = 4 + #columns read) ----
-      uint32_t stw = 0; uint32_t pos[VEC]; float adiv[VEC], ahyd[VEC]; float v[VEC][NV], old[VEC][NV];
+      uint32_t pos[VEC]; float adiv[VEC], ahyd[VEC]; float v[VEC][NV], old[VEC][NV];
+      const uint32_t stw = VecIO<VEC>::ldb(p.status + i0);
+      VecIO<VEC>::ldu(p.pos + i0, pos);
+      VecIO<VEC>::ldf(p.age_div + i0, adiv);
+      if (p.enable_leave) VecIO<VEC>::ldf(p.age_hyd + i0, ahyd);
+      else {
 #pragma unroll
-      for (int q = 0; q < VEC; ++q) { pos[q] = 0; adiv[q] = 0.f; ahyd[q] = 0.f; }
-      if (any_valid) {
-        stw = VecIO<VEC>::ldb(p.status + i0);
-        VecIO<VEC>::ldu(p.pos + i0, pos);
-        VecIO<VEC>::ldf(p.age_div + i0, adiv);
-        if (p.enable_leave) VecIO<VEC>::ldf(p.age_hyd + i0, ahyd);
+        for (int q = 0; q < VEC; ++q) ahyd[q] = 0.f;
+      }
 #pragma unroll
-        for (int k = 0; k < NV; ++k) {
-          float col[VEC];
-          if ((M::write_only_mask >> k) & 1u) {
+      for (int k = 0; k < NV; ++k) {
+        float col[VEC];
+        if ((M::write_only_mask >> k) & 1u) {
 #pragma unroll
-            for (int q = 0; q < VEC; ++q) col[q] = 0.f;
-          } else {
-            VecIO<VEC>::ldf(p.props + (size_t)k * p.cap + i0, col);
-          }
-#pragma unroll
-          for (int q = 0; q < VEC; ++q) { v[q][k] = col[q]; old[q][k] = col[q]; }
+          for (int q = 0; q < VEC; ++q) col[q] = 0.f;
+        } else {
+          VecIO<VEC>::ldf(p.props + (size_t)k * p.cap + i0, col);
         }
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) { v[q][k] = col[q]; old[q][k] = col[q]; }
       }
       uint32_t pos_old[VEC]; float adiv_old[VEC], ahyd_old[VEC];
-      bool valid[VEC], idle[VEC];
-      unsigned div_nib = 0;
+      bool idle[VEC];
+      unsigned valid_m = 0, idle_m = 0;
 #pragma unroll
       for (int q = 0; q < VEC; ++q) {
         pos_old[q] = pos[q]; adiv_old[q] = adiv[q]; ahyd_old[q] = ahyd[q];
-        valid[q] = (i0 + q) < n_used;
-        idle[q] = valid[q] && (((stw >> (8 * q)) & 0xffu) == (unsigned)Idle);
+        const bool valid = live && (i0 + q) < n_used;
+        idle[q] = valid && (((stw >> (8 * q)) & 0xffu) == (unsigned)Idle);
+        valid_m |= (unsigned)valid << q; idle_m |= (unsigned)idle[q] << q;
+        if (!valid) pos[q] = 0;  // slots past n_used hold unspecified bytes: keep the gathers in range
       }
+      constexpr unsigned kAll = (1u << VEC) - 1u;
 
-      // ---- random words: Philox block 0 of (slot, step) ----------------------
-      uint32_t rw[VEC][4];
-      if (p.enable_move || p.enable_leave) {
-#pragma unroll
-        for (int q = 0; q < VEC; ++q)
-          philox4x32_10((uint32_t)(i0 + q), p.step, 0u, p.rank, p.seed_lo, p.seed_hi, rw[q]);
-      }
-
-      // ---- model update + contribution --------------------------------------
+      // ---- compartment rows: leave threshold + model terms, one gather per particle
+      float ctab[VEC][CT];
 #pragma unroll
       for (int q = 0; q < VEC; ++q) {
-        if (idle[q]) {
-          adiv[q] += p.dt_f;  // ages(i,1) += _d_t  (model_kernel.hpp:191)
-          float contrib[NC];
-          Gen gen(p.seed_lo, p.seed_hi, p.rank, (uint32_t)(i0 + q), p.step, 0u);
-          const Status s = M::update(gen, p.dt_f, i0 + q, RegRow{v[q]}, RegRow{contrib}, (size_t)pos[q], conc);
-          if (s == Division) div_nib |= 1u << q;
-          if (single_comp) {
+        const float* row = p.ctab + (size_t)pos[q] * CT;
+        if constexpr (CT == 2) { const float2 t = __ldg(reinterpret_cast<const float2*>(row)); ctab[q][0] = t.x; ctab[q][1] = t.y; }
+        else if constexpr (CT == 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(row)); ctab[q][0] = t.x; ctab[q][1] = t.y; ctab[q][2] = t.z; ctab[q][3] = t.w; }
+        else {
 #pragma unroll
-            for (int j = 0; j < NC; ++j) acc0d[j] += w * (double)contrib[j];
-          } else if (p.bins_in_smem) {  // block-private fp64 bins, flushed once per block
-#pragma unroll
-            for (int j = 0; j < NC; ++j)
-              atomicAdd(&s_bins[(uint32_t)j + p.n_species * pos[q]], w * (double)contrib[j]);
-          } else {  // table too large for shared memory: L2 atomics (RED.F64)
-#pragma unroll
-            for (int j = 0; j < NC; ++j)
-              atomicAdd(p.sources + (size_t)j + (size_t)p.n_species * pos[q], w * (double)contrib[j]);
-          }
+          for (int k = 0; k < CT; ++k) ctab[q][k] = __ldg(row + k);
         }
+      }
+
+      // ---- u1: ONE Philox block per group of four slots (draw_block 0) ---------
+      uint32_t rw1[4] = {0u, 0u, 0u, 0u};
+      if (p.enable_move) philox4x32_10((uint32_t)(i0 >> 2), p.step, 0u, p.rank, p.seed_lo, p.seed_hi, rw1);
+
+      // ---- model update: unconditional straight-line code over the VEC particles;
+      // results of non-idle slots are never stored (model_kernel.hpp:186-196)
+      float contrib[VEC][NC];
+      unsigned div_nib = 0;
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) {
+        adiv[q] = idle[q] ? adiv[q] + p.dt_f : adiv[q];  // ages(i,1) += _d_t  (model_kernel.hpp:191)
+        Gen gen(p.seed_lo, p.seed_hi, p.rank, (uint32_t)(i0 + q), p.step, 2u);
+        const ConcView conc{p.conc, p.n_species, &ctab[q][1]};
+        const Status s = M::update(gen, p.dt_f, i0 + q, RegRow{v[q]}, RegRow{contrib[q]}, (size_t)pos[q], conc);
+        div_nib |= (unsigned)(idle[q] && s == Division) << q;
+      }
+
+      // ---- contribution scatter at the PRE-move position (Q15) -----------------
+      if (single_comp) {
+#pragma unroll
+        for (int q = 0; q < VEC; ++q)
+#pragma unroll
+          for (int j = 0; j < NC; ++j) acc0d[j] += idle[q] ? w * (double)contrib[q][j] : 0.0;
+      } else if (smem_bins) {  // block-private fp64 bins (LDS/DADD/ATOMS.CAST.SPIN), flushed once per block
+#pragma unroll
+        for (int q = 0; q < VEC; ++q)
+          if (idle[q]) {
+#pragma unroll
+            for (int j = 0; j < NC; ++j) atomicAdd(&s_bins[(uint32_t)j + p.n_species * pos[q]], w * (double)contrib[q][j]);
+          }
+      } else {  // table too large for shared memory: L2 atomics (RED.F64)
+#pragma unroll
+        for (int q = 0; q < VEC; ++q)
+          if (idle[q]) {
+#pragma unroll
+            for (int j = 0; j < NC; ++j) atomicAdd(p.sources + (size_t)j + (size_t)p.n_species * pos[q], w * (double)contrib[q][j]);
+          }
       }
 
       // ---- division: handle_division (particles_container.hpp:559-573) -------
@@ -273,7 +367,7 @@ __global__ void __launch_bounds__(kBlock) cycle_kernel(const __grid_constant__ C
       // particle order inside the warp; final newborn placement is re-ranked by
       // mother index in insert_kernel, so the result does not depend on the
       // order warps hit the atomic.
-      if (__ballot_sync(0xffffffffu, div_nib != 0u)) {
+      if (__any_sync(0xffffffffu, div_nib != 0u)) {
         const unsigned cnt = __popc(div_nib);
         unsigned total;
         const unsigned excl = warp_excl_scan(cnt, total);
@@ -299,54 +393,78 @@ __global__ void __launch_bounds__(kBlock) cycle_kernel(const __grid_constant__ C
             }
           }
         }
-        // division bitmask: bit (slot & 31) of word (slot >> 5)
-        constexpr int LPW = 32 / VEC;  // lanes per 32-slot word
+        // division bitmask: bit (slot & 31) of word (slot >> 5); a word is owned by 32/VEC lanes
+        constexpr int LPW = 32 / VEC;
         unsigned word = ok_nib << (VEC * (lane % LPW));
 #pragma unroll
         for (int o = 1; o < LPW; o <<= 1) word |= __shfl_xor_sync(0xffffffffu, word, o);
         const unsigned n_ok = __reduce_add_sync(0xffffffffu, __popc(ok_nib));
-        if ((lane % LPW) == 0 && word != 0u) p.div_mask[(i0 >> 5)] = word;
+        if (live && (lane % LPW) == 0 && word != 0u) p.div_mask[(i0 >> 5)] = word;
         if (lane == 0 && n_ok) atomicAdd(&p.tile_div[tile], n_ok);
       }
 
       // ---- move (all slots, no status check: move_kernel.hpp:392-437) --------
       if (p.enable_move) {
+        unsigned mv = 0;
 #pragma unroll
         for (int q = 0; q < VEC; ++q) {
-          if (valid[q]) {
-            const uint32_t c = pos[q];
-            const float u1 = u01f(rw[q][0]);
-            if (u1 < __ldg(p.p_leave + c)) {  // (dt*flow/volume) > rng1
-              const float u2 = u01f(rw[q][1]);
-              const float* row = p.cdf + (size_t)c * p.m;
-              int left = 0, right = p.m - 1;
-              while (left < right) {  // __find_next_compartment, move_kernel.hpp:87-95
-                const int mid = (left + right) >> 1;
-                if (u2 > __ldg(row + mid)) left = mid + 1; else right = mid;
-              }
-              pos[q] = __ldg(p.neigh + (size_t)c * p.m + left);
-              ++c_move;  // events.wrap_incr<Move>() (Q20: aggregated)
-            }
+          const float u1 = u01f(pick4(rw1, (unsigned)((i0 + q) & 3)));
+          mv |= (unsigned)(u1 < ctab[q][0]) << q;  // (dt*flow/volume) > rng1
+        }
+        mv &= valid_m;
+        // movers are rare (dt*F/V ~ 1e-2): their neighbour pick draws its own block
+        while (mv) {
+          const int q = __ffs(mv) - 1;
+          mv &= mv - 1;
+          uint32_t c = pos[0];
+#pragma unroll
+          for (int qq = 1; qq < VEC; ++qq) if (qq == q) c = pos[qq];
+          uint32_t r2[4];
+          philox4x32_10((uint32_t)(i0 + q), p.step, 2u, p.rank, p.seed_lo, p.seed_hi, r2);
+          const float u2 = u01f(r2[0]);
+          const float* row = p.cdf + (size_t)c * p.m;
+          int left = 0, right = p.m - 1;
+          while (left < right) {  // __find_next_compartment, move_kernel.hpp:87-95
+            const int mid = (left + right) >> 1;
+            if (u2 > __ldg(row + mid)) left = mid + 1; else right = mid;
           }
+          const uint32_t np = __ldg(p.neigh + (size_t)c * p.m + left);
+#pragma unroll
+          for (int qq = 0; qq < VEC; ++qq) if (qq == q) pos[qq] = np;
+          ++c_move;  // events.wrap_incr<Move>() (Q20: aggregated)
         }
       }
 
       // ---- leave (Idle only, post-move position: move_kernel.hpp:347-359) ----
       unsigned exit_nib = 0;
       if (p.enable_leave) {
+        unsigned in_outlet = 0; int fsel[VEC];
 #pragma unroll
         for (int q = 0; q < VEC; ++q) {
-          if (idle[q]) {
-            ahyd[q] = (float)((double)ahyd[q] + p.dt);  // ages(idx,0) += d_t (double)
-            double dt_flow = 0., flow = 0., vol = 0.;
-            for (int f = 0; f < p.n_flows; ++f) {  // find_flow: first match wins
-              if (p.outlets[f].index == pos[q]) { flow = p.outlets[f].flow; dt_flow = p.outlets[f].dt_flow; vol = p.outlets[f].volume; break; }
-            }
-            if (flow != 0.) {
-              const float u3 = u01f(rw[q][2]);
+          ahyd[q] = idle[q] ? (float)((double)ahyd[q] + p.dt) : ahyd[q];  // ages(idx,0) += d_t (double)
+          fsel[q] = 0;
+        }
+        if (p.n_flows == 1) {  // the usual case (0D reactor or a single outlet, move_kernel.hpp:113)
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) in_outlet |= (unsigned)(outlet0_live && pos[q] == outlet0) << q;
+        } else {
+#pragma unroll
+          for (int q = 0; q < VEC; ++q)
+            for (int f = 0; f < p.n_flows; ++f)  // find_flow: first match wins
+              if (p.outlets[f].index == pos[q]) { if (p.outlets[f].flow != 0.) { in_outlet |= 1u << q; fsel[q] = f; } break; }
+        }
+        in_outlet &= idle_m;
+        if (in_outlet) {  // u3: draw_block 1 of the group of four
+          uint32_t rw3[4];
+          philox4x32_10((uint32_t)(i0 >> 2), p.step, 1u, p.rank, p.seed_lo, p.seed_hi, rw3);
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) {
+            if ((in_outlet >> q) & 1u) {
+              const float u3 = u01f(pick4(rw3, (unsigned)((i0 + q) & 3)));
               const float lnu = (float)log((double)u3);  // Kokkos::log(float), see oracle ln_f32
-              if (dt_flow > (double)(-lnu) * vol) {       // probability_leaving<precision_tag>
-                ahyd[q] = ahyd[q] * 0.0f;                 // ages(idx,0) *= (1 - leave_mask)
+              const Outlet& o = p.outlets[fsel[q]];
+              if (o.dt_flow > (double)(-lnu) * o.volume) {  // probability_leaving<precision_tag>
+                ahyd[q] = ahyd[q] * 0.0f;                   // ages(idx,0) *= (1 - leave_mask)
                 exit_nib |= 1u << q;
                 ++c_exit;
               }
@@ -356,59 +474,55 @@ __global__ void __launch_bounds__(kBlock) cycle_kernel(const __grid_constant__ C
       }
 
       // ---- write back only what changed -------------------------------------
-      if (any_valid) {
-        bool all_idle = true;
+      const bool all_idle = (idle_m == kAll);
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) all_idle = all_idle && idle[q];
+      for (int k = 0; k < NV; ++k) {
+        float col[VEC];
 #pragma unroll
-        for (int k = 0; k < NV; ++k) {
-          float col[VEC];
+        for (int q = 0; q < VEC; ++q) col[q] = v[q][k];
+        float* dst = p.props + (size_t)k * p.cap + i0;
+        bool ch = false;
+        if ((M::write_only_mask >> k) & 1u) ch = idle_m != 0u;
+        else {
 #pragma unroll
-          for (int q = 0; q < VEC; ++q) col[q] = v[q][k];
-          float* dst = p.props + (size_t)k * p.cap + i0;
-          if ((M::write_only_mask >> k) & 1u) {
-            if (all_idle) VecIO<VEC>::stf(dst, col);
-            else {
+          for (int q = 0; q < VEC; ++q) ch = ch || (idle[q] && __float_as_uint(v[q][k]) != __float_as_uint(old[q][k]));
+        }
+        if (ch) {
+          if (all_idle) VecIO<VEC>::stf(dst, col);
+          else {  // group with exited / out-of-range slots: their columns stay untouched
 #pragma unroll
-              for (int q = 0; q < VEC; ++q) if (idle[q]) dst[q] = col[q];
-            }
-          } else {
-            bool ch = false;
-#pragma unroll
-            for (int q = 0; q < VEC; ++q) ch = ch || (__float_as_uint(v[q][k]) != __float_as_uint(old[q][k]));
-            if (ch) VecIO<VEC>::stf(dst, col);
+            for (int q = 0; q < VEC; ++q) if (idle[q]) dst[q] = col[q];
           }
         }
-        bool ch_ad = false, ch_ah = false, ch_pos = false;
+      }
+      bool ch_ad = false, ch_ah = false, ch_pos = false;
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) {
-          ch_ad = ch_ad || (__float_as_uint(adiv[q]) != __float_as_uint(adiv_old[q]));
-          ch_ah = ch_ah || (__float_as_uint(ahyd[q]) != __float_as_uint(ahyd_old[q]));
-          ch_pos = ch_pos || (pos[q] != pos_old[q]);
-        }
-        if (ch_ad) VecIO<VEC>::stf(p.age_div + i0, adiv);
-        if (ch_ah) VecIO<VEC>::stf(p.age_hyd + i0, ahyd);
-        if (ch_pos) {  // Q14: position written only when it changed
+      for (int q = 0; q < VEC; ++q) {
+        ch_ad = ch_ad || (__float_as_uint(adiv[q]) != __float_as_uint(adiv_old[q]));
+        ch_ah = ch_ah || (__float_as_uint(ahyd[q]) != __float_as_uint(ahyd_old[q]));
+        ch_pos = ch_pos || (pos[q] != pos_old[q]);
+      }
+      if (ch_ad) VecIO<VEC>::stf(p.age_div + i0, adiv);  // unchanged lanes rewrite their own value
+      if (ch_ah) VecIO<VEC>::stf(p.age_hyd + i0, ahyd);
+      if (ch_pos) {  // Q14: position written only when it changed (never for slots >= n_used: mv is masked)
 #pragma unroll
-          for (int q = 0; q < VEC; ++q) if (pos[q] != pos_old[q]) p.pos[i0 + q] = pos[q];
-        }
-        if (exit_nib) {
+        for (int q = 0; q < VEC; ++q) if (pos[q] != pos_old[q] && ((valid_m >> q) & 1u)) p.pos[i0 + q] = pos[q];
+      }
+      if (exit_nib) {
 #pragma unroll
-          for (int q = 0; q < VEC; ++q) if ((exit_nib >> q) & 1u) p.status[i0 + q] = (uint8_t)Exit;
-        }
+        for (int q = 0; q < VEC; ++q) if ((exit_nib >> q) & 1u) p.status[i0 + q] = (uint8_t)Exit;
       }
     }
   }
 
   // ---- block epilogue: counters, source flush, block-local tile prefix -------
-  unsigned long long cm = c_move, ce = c_exit, cn = c_new, co = c_over;
-  cm = __reduce_add_sync(0xffffffffu, (unsigned)cm); ce = __reduce_add_sync(0xffffffffu, (unsigned)ce);
-  cn = __reduce_add_sync(0xffffffffu, (unsigned)cn); co = __reduce_add_sync(0xffffffffu, (unsigned)co);
+  const unsigned cm = __reduce_add_sync(0xffffffffu, c_move), ce = __reduce_add_sync(0xffffffffu, c_exit);
+  const unsigned cn = __reduce_add_sync(0xffffffffu, c_new), co = __reduce_add_sync(0xffffffffu, c_over);
   if (lane == 0) {
-    if (cm) atomicAdd(&s_cnt[0], cm);
-    if (ce) atomicAdd(&s_cnt[1], ce);
-    if (cn) atomicAdd(&s_cnt[2], cn);
-    if (co) atomicAdd(&s_cnt[3], co);
+    if (cm) atomicAdd(&s_cnt[0], (unsigned long long)cm);
+    if (ce) atomicAdd(&s_cnt[1], (unsigned long long)ce);
+    if (cn) atomicAdd(&s_cnt[2], (unsigned long long)cn);
+    if (co) atomicAdd(&s_cnt[3], (unsigned long long)co);
   }
   if (single_comp) {
 #pragma unroll
@@ -422,12 +536,12 @@ __global__ void __launch_bounds__(kBlock) cycle_kernel(const __grid_constant__ C
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    if (s_cnt[0]) atomicAdd(&p.st->events[2], s_cnt[0]);                           // Move
-    if (s_cnt[1]) { atomicAdd(&p.st->events[1], s_cnt[1]); atomicAdd(&p.st->step_exit, s_cnt[1]); }  // Exit
-    if (s_cnt[2]) atomicAdd(&p.st->events[0], s_cnt[2]);                           // NewParticle
+    if (s_cnt[0]) atomicAdd(&p.st->events[2], s_cnt[0]);                                               // Move
+    if (s_cnt[1]) { atomicAdd(&p.st->events[1], s_cnt[1]); atomicAdd(&p.st->step_exit, s_cnt[1]); }     // Exit
+    if (s_cnt[2]) atomicAdd(&p.st->events[0], s_cnt[2]);                                               // NewParticle
     if (s_cnt[3]) { atomicAdd(&p.st->events[4], s_cnt[3]); atomicAdd(&p.st->step_waiting, s_cnt[3]); }  // Overflow
   }
-  if (p.bins_in_smem && !single_comp) {
+  if (smem_bins) {
     for (uint32_t k = threadIdx.x; k < n_bins; k += kBlock) {
       const double a = s_bins[k];
       if (a != 0.0) atomicAdd(p.sources + k, a);
@@ -690,13 +804,9 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ I
 // Domain tables: ReactorDomain::update (mc/src/domain.cpp:43-74) -> derived
 // single-precision tables that reproduce the double-precision comparisons
 // bit-exactly for float uniforms:
-//   (dt*flow/volume) > (double)u   <=>  u < ceil_f32(dt*flow/volume)
+//   (dt*flow/volume) > (double)u   <=>  u < ceil_f32(dt*flow/volume)   (compartment_table_kernel)
 //   (double)u > cdf                <=>  u > floor_f32(cdf)
 // -----------------------------------------------------------------------------
-__global__ void derive_leave_table_kernel(const double* diag, const double* vol, double dt, float* p_leave, uint32_t n) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p_leave[i] = __double2float_ru(dt * diag[i] / vol[i]);
-}
 __global__ void derive_cdf_table_kernel(const double* cdf, float* out, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = __double2float_rd(cdf[i]);
@@ -714,7 +824,7 @@ __global__ void __launch_bounds__(256) init_kernel(float* props, size_t cap, uin
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (unsigned long long)gridDim.x * blockDim.x) {
     float v[M::n_var];
-    Gen gen(seed_lo, seed_hi, rank, (uint32_t)i, 0xFFFFFFFFu, 0u);
+    Gen gen(seed_lo, seed_hi, rank, (uint32_t)i, 0xFFFFFFFFu, 2u);
     M::init(gen, (size_t)i, RegRow{v}, ConfigView{linit});
     m += M::mass((size_t)i, RegRow{v});
     const uint32_t c = (uint32_t)gen.urand64(0ull, (unsigned long long)n_comp_hi);

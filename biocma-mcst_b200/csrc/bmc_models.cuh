@@ -15,10 +15,13 @@
 // division buffer in global memory, `c` gathers from the replicated
 // concentration table, and `random_pool` is a counter-based Philox generator.
 //
-// Optional per-model hint:
+// Optional per-model hints (extensions; a model that omits them is still correct):
 //   write_only_mask : bit k set => property k is never read by update/division
 //                     before being written; the kernel then skips loading that
 //                     column (SURVEY.md §8d algorithmic bytes).
+//   n_pre + compartment_terms(c, position, out[n_pre]) : sub-expressions of update
+//                     that depend on the local concentration only; evaluated once
+//                     per compartment per step and handed back through c.term(k).
 //
 // All arithmetic is compiled with -fmad=false: IEEE single/double without
 // contraction, so deterministic models are bit-reproducible against the oracle.
@@ -46,9 +49,11 @@ struct BufRows {
 struct ConcView {
   const double* base;
   uint32_t n_species;
+  const float* pre;  // this particle's compartment_terms (optional model hook), else nullptr
   __device__ __forceinline__ double operator()(size_t s, size_t pos) const {
     return __ldg(base + s + (size_t)n_species * pos);
   }
+  __device__ __forceinline__ float term(int k) const { return pre[k]; }
 };
 // Config view of configurable models (fixed_length.hpp:25): config(idx)
 struct ConfigView {
@@ -97,7 +102,7 @@ __device__ __forceinline__ double lognormal(Gen& g, double mu, double sigma) { r
 // fixed_length — apps/libs/models/public/models/fixed_length.hpp:19-161
 // =============================================================================
 struct FixedLength {
-  static constexpr int n_var = 2, n_c = 1;
+  static constexpr int n_var = 2, n_c = 1, n_pre = 1;
   static constexpr uint32_t write_only_mask = 0u;
   enum particle_var { length = 0, l_max = 1 };
   static constexpr float l_dot_max = (float)(2e-6 / 3600.);
@@ -118,14 +123,17 @@ struct FixedLength {
                                   size_t position_index, const Conc& c) {  // :122-142
     float& l = arr(idx, length);
     const float lmax = arr(idx, l_max);
-    const float s = (float)c(0, position_index);
     float& c_phi_s = arr_contribs(idx, 0);
-    const float g = s / (k + s);
+    const float g = c.term(0);  // s / (k + s), hoisted to compartment_terms
     const float phi_s = phi_s_max * g;
     const float ldot = l_dot_max * g;
     l += d_t * ldot;
     c_phi_s = -phi_s;
     return check_div(l, lmax);
+  }
+  template <class Conc> __device__ static void compartment_terms(const Conc& c, size_t position_index, float* out) {
+    const float s = (float)c(0, position_index);  // :133 (no clamp, Q17)
+    out[0] = s / (k + s);
   }
   template <class A, class B>
   __device__ static void division(Gen&, size_t idx, size_t idx2, const A& arr, const B& buffer_arr) {  // :144-160
@@ -143,7 +151,7 @@ struct FixedLength {
 // Q1): contribs(idx,0) = phi_s_c, which is also kept as property 5.
 // =============================================================================
 struct Monod {
-  static constexpr int n_var = 6, n_c = 1;
+  static constexpr int n_var = 6, n_c = 1, n_pre = 1;
   enum particle_var { l = 0, l_max, mu_p, mue, cell_lenghtening, phi_s_c };
   static constexpr uint32_t write_only_mask = (1u << mue) | (1u << phi_s_c);
   static constexpr float y_s_x = 2.0f;
@@ -168,8 +176,7 @@ struct Monod {
   template <class A, class C, class Conc>
   __device__ static Status update(Gen&, float d_t, size_t idx, const A& arr, const C& arr_contribs,
                                   size_t position_index, const Conc& c) {  // :122-160
-    const float s = (float)fmax(0., c(0, position_index));
-    const float mu = mu_max * s / (k_s + s);
+    const float mu = c.term(0);  // mu_max * s / (k_s + s), hoisted to compartment_terms
     const float mu_eff = fminf(arr(idx, mu_p), mu);
     arr(idx, l) += d_t * (mu_eff * arr(idx, cell_lenghtening));
     // `d_t * (1.0 / tau_meta) * (mu - mu_p)` promotes to double (:144-146)
@@ -180,6 +187,10 @@ struct Monod {
     arr(idx, phi_s_c) = ph;
     arr_contribs(idx, 0) = ph;
     return check_div(arr(idx, l), arr(idx, l_max));
+  }
+  template <class Conc> __device__ static void compartment_terms(const Conc& c, size_t position_index, float* out) {
+    const float s = (float)fmax(0., c(0, position_index));  // :130-131 bounded
+    out[0] = mu_max * s / (k_s + s);                        // :132 instantaneous mu from Monod
   }
   template <class A, class B>
   __device__ static void division(Gen&, size_t idx, size_t idx2, const A& arr, const B& buffer_arr) {  // :162-192
@@ -199,7 +210,7 @@ struct Monod {
 // simple_acetate — apps/libs/models/public/models/simple_acetate.hpp:26-248
 // =============================================================================
 struct SimpleAcetate {
-  static constexpr int n_var = 9, n_c = 2;
+  static constexpr int n_var = 9, n_c = 2, n_pre = 0;
   enum particle_var { length = 0, l_max, a_p, a_max, a_e, a_e_s, a_e_a, phi_s, phi_a };
   // a_e is read by division AFTER update wrote it in the same cycle -> still write-only for loading
   static constexpr uint32_t write_only_mask = (1u << a_e) | (1u << a_e_s) | (1u << a_e_a) | (1u << phi_s) | (1u << phi_a);
@@ -286,7 +297,7 @@ struct SimpleAcetate {
 // Same definition as oracle/bmc_oracle.cpp `WideUdf`.
 // =============================================================================
 template <int P> struct WideUdf {
-  static constexpr int n_var = P, n_c = 4;
+  static constexpr int n_var = P, n_c = 4, n_pre = 4;
   static constexpr uint32_t write_only_mask = 0u;
   enum { length = 0, l_max = 1, first_pool = 2 };
   static constexpr float l_dot_max = (float)(2e-6 / 3600.);
@@ -304,10 +315,7 @@ template <int P> struct WideUdf {
                                   size_t position_index, const Conc& c) {
     float sat[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float s = (float)fmax(0., c((size_t)j % c.n_species, position_index));
-      sat[j] = s / ((float)1e-3 * (float)(j + 1) + s);
-    }
+    for (int j = 0; j < 4; ++j) sat[j] = c.term(j);  // hoisted to compartment_terms
     float acc = 0.0f;
 #pragma unroll
     for (int k = first_pool; k < P; ++k) {
@@ -322,6 +330,13 @@ template <int P> struct WideUdf {
 #pragma unroll
     for (int j = 0; j < 4; ++j) arr_contribs(idx, j) = -phi_max * sat[j] * act * (1.0f / (float)(j + 1));
     return check_div(arr(idx, length), arr(idx, l_max));
+  }
+  template <class Conc> __device__ static void compartment_terms(const Conc& c, size_t position_index, float* out) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float s = (float)fmax(0., c((size_t)j % c.n_species, position_index));
+      out[j] = s / ((float)1e-3 * (float)(j + 1) + s);
+    }
   }
   template <class A, class B>
   __device__ static void division(Gen&, size_t idx, size_t idx2, const A& arr, const B& buffer_arr) {

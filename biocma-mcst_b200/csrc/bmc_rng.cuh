@@ -5,10 +5,13 @@
 // no pool acquire/release (move_kernel.hpp:237-259) — every draw is a pure
 // function of (seed, rank | slot, step, draw-block), held in registers.
 //   key = { seed_lo, seed_hi }
-//   ctr = { slot, step, draw_block, rank }
-// draw_block 0: word0 = u1 (leave-compartment test), word1 = u2 (neighbour pick),
-//               word2 = u3 (outlet test).
-// draw_block 1.. : generator handed to M::update / M::init;
+//   ctr = { index, step, draw_block, rank }
+// draw_block 0: index = slot >> 2; word (slot & 3) = u1 of that slot (leave-compartment
+//               test).  One Philox block serves the four slots a thread owns.
+// draw_block 1: index = slot >> 2; word (slot & 3) = u3 (outlet test), computed only by
+//               warps that have a particle sitting in an outlet compartment.
+// draw_block 2: index = slot; word 0 = u2 (neighbour pick), computed only for movers.
+// draw_block 3.. (index = slot): generator handed to M::update / M::init;
 // draw_block 0x40000001.. : generator handed to M::division.
 #pragma once
 #include <cstdint>

@@ -55,10 +55,13 @@ namespace orc {
 // MC::pool_type = Kokkos::Random_XorShift1024_Pool (apps/libs/mc/public/mc/
 // alias.hpp:98-102).  Counter layout shared by oracle and CUDA path:
 //   key = { seed_lo, seed_hi }
-//   ctr = { slot, step, draw_block, rank }
-// draw_block 0 belongs to the cycle itself: word0 = u1 (leave-compartment
-// test), word1 = u2 (neighbour pick), word2 = u3 (outlet test), word3 spare.
-// draw_block >= 1 feeds the model hooks' generator (init/update/division).
+//   ctr = { index, step, draw_block, rank }
+// draw_block 0: index = slot >> 2, word (slot & 3) = u1 of that slot (leave-
+//               compartment test); one block serves four neighbouring slots.
+// draw_block 1: index = slot >> 2, word (slot & 3) = u3 (outlet test).
+// draw_block 2: index = slot, word 0 = u2 (neighbour pick, movers only).
+// draw_block >= 3 (index = slot) feeds the model hooks' generator: update/init
+// use 3.., division uses 0x40000001...
 // ---------------------------------------------------------------------------
 struct Philox {
   static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
@@ -98,7 +101,7 @@ struct Gen {
   int have;
   Gen(uint64_t seed, uint32_t rank, uint32_t slot, uint32_t step) {
     key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32);
-    ctr[0] = slot; ctr[1] = step; ctr[2] = 0; ctr[3] = rank;
+    ctr[0] = slot; ctr[1] = step; ctr[2] = 2; ctr[3] = rank;  // first block drawn is 3
     have = 0;
   }
   inline uint32_t next32() {
@@ -499,7 +502,7 @@ template <class M> static void cycle_model(Ctx& c, double d_t_in) {
       if (!flag[i]) continue;
       if (j < c.buffer_cap) {  // handle_division :562-570
         Gen g(c.seed, c.rank, (uint32_t)i, c.step);
-        g.ctr[2] = 0x40000000u;  // division draws: blocks 0x40000001.. (update draws use 1..)
+        g.ctr[2] = 0x40000000u;  // division draws: blocks 0x40000001.. (update draws use 3..)
         ModelOps<M>::division(g, i, j, arr, buf);
         c.buffer_position[j] = c.position[i];
         c.age_div[i] = 0.0f;
@@ -573,19 +576,25 @@ static inline bool p_leave_precise(float rnd, double volume, double flow, double
 
 // --- cycle_move: move_kernel.hpp:209-273 (TagMove) + :392-437 (handle_move).
 // Applies to every slot < n_used regardless of status (the functor has no
-// status check).  u1,u2 = Philox block 0 words 0,1.
+// status check).  u1 = block 0 of the slot's group of four, u2 = block 2 of the slot.
 static uint64_t cycle_move(Ctx& c, double d_t) {
   const size_t n = c.n_used;
   const uint32_t key[2] = {(uint32_t)c.seed, (uint32_t)(c.seed >> 32)};
   uint64_t moved = 0;
 #pragma omp parallel for schedule(static) num_threads(c.n_threads) reduction(+ : moved)
   for (long i = 0; i < (long)n; ++i) {
-    const uint32_t ctr[4] = {(uint32_t)i, c.step, 0u, c.rank};
+    const uint32_t ctr[4] = {(uint32_t)i >> 2, c.step, 0u, c.rank};
     uint32_t r[4];
     Philox::block(ctr, key, r);
-    const float rng1 = u01f(r[0]), rng2 = u01f(r[1]);
+    const float rng1 = u01f(r[i & 3]);
     const size_t ic = c.position[i];
     const bool mask_next = p_leave_fast(rng1, c.liquid_volume[ic], c.diag_transition[ic], d_t);
+    float rng2 = 0.0f;
+    if (mask_next) {  // the draw is a pure function of (slot, step): skipping it is harmless (Q13)
+      const uint32_t ctr2[4] = {(uint32_t)i, c.step, 2u, c.rank};
+      Philox::block(ctr2, key, r);
+      rng2 = u01f(r[0]);
+    }
     c.position[i] = find_next_compartment(mask_next, c, ic, rng2);
     if (mask_next) ++moved;
   }
@@ -611,10 +620,10 @@ static uint64_t cycle_leave(Ctx& c, double d_t) {
       if (pos == lf.index) { flow = lf.flow; vol = lf.volume; break; }
     } while (k < nf);
     if (flow != 0.) {
-      const uint32_t ctr[4] = {(uint32_t)i, c.step, 0u, c.rank};
+      const uint32_t ctr[4] = {(uint32_t)i >> 2, c.step, 1u, c.rank};
       uint32_t r[4];
       Philox::block(ctr, key, r);
-      const float rng1 = u01f(r[2]);
+      const float rng1 = u01f(r[i & 3]);
       const int leave_mask = (int)p_leave_precise(rng1, vol, flow, d_t);
       dead += leave_mask;
       c.age_hyd[i] *= (float)(1 - leave_mask);
@@ -633,7 +642,7 @@ static uint64_t cycle_leave(Ctx& c, double d_t) {
 static void remove_inactive(Ctx& c, size_t to_remove) {
   if (to_remove == 0) return;
   if (to_remove == c.n_used) {
-    c.n_used = 0; c.inactive_counter = 0; return;
+    c.n_used = 0; c.inactive_counter = 0; c.n_compactions++; return;
   }
   if (to_remove > c.n_used) { c.err = "remove_inactive_particles: cannot remove more element than existing"; return; }
   const size_t last = c.n_used - 1;

@@ -52,7 +52,7 @@ def test_many_steps_division_exit_compaction(bmc, orc, synth, model):
     # dt large enough that cells divide, leave through the outlet, and the 1 % dead
     # threshold triggers compaction several times
     case = util.make_case(synth, model, 120_000, 500, dt=20.0, near_division=0.8, p_move=0.3, p_exit=0.3)
-    g, o = _pair(bmc, orc, case)
+    g, o = _pair(bmc, orc, case, dead_ratio=0.0005)
     util.load_case(g, case); util.load_case(o, case)
     for blk in range(4):
         sg = util.run_steps(g, case, 5, collect=True); so = util.run_steps(o, case, 5, collect=True)
