@@ -28,7 +28,7 @@ struct ModelVT {
   void (*launch_init)(float*, size_t, uint32_t*, uint8_t*, float*, float*, unsigned long long, uint32_t, const float*,
                       uint32_t, uint32_t, uint32_t, DevState*, int, cudaStream_t);
   int ct;  // floats per compartment-table row
-  void (*launch_ctab)(const double*, const double*, double, const double*, uint32_t, float*, uint32_t, int, cudaStream_t);
+  void (*launch_pre)(const PreParams&, int grid, cudaStream_t);
 };
 
 template <class M, int VEC, int MINB> static void launch_cycle_t(const CycleParams& p, int grid, size_t smem, cudaStream_t s) {
@@ -40,10 +40,8 @@ static void launch_init_t(float* props, size_t cap, uint32_t* pos, uint8_t* stat
                           cudaStream_t s) {
   init_kernel<M><<<grid, 256, 0, s>>>(props, cap, pos, status, ah, ad, n, ncomp_hi, linit, slo, shi, rank, st);
 }
-template <class M>
-static void launch_ctab_t(const double* diag, const double* vol, double dt, const double* conc, uint32_t ns, float* ctab, uint32_t nc,
-                          int enable_move, cudaStream_t s) {
-  compartment_table_kernel<M><<<(nc + 127) / 128, 128, 0, s>>>(diag, vol, dt, conc, ns, ctab, nc, enable_move);
+template <class M> static void launch_pre_t(const PreParams& p, int grid, cudaStream_t s) {
+  pre_step_kernel<M><<<grid, 256, 0, s>>>(p);
 }
 template <class M, int VEC, int MINB = 1> static ModelVT make_vt() {
   ModelVT v;
@@ -52,7 +50,7 @@ template <class M, int VEC, int MINB = 1> static ModelVT make_vt() {
   v.launch_cycle = &launch_cycle_t<M, VEC, MINB>;
   v.launch_init = &launch_init_t<M>;
   v.ct = 1 + M::n_pre;
-  v.launch_ctab = &launch_ctab_t<M>;
+  v.launch_pre = &launch_pre_t<M>;
   return v;
 }
 
@@ -118,6 +116,8 @@ struct bmc_ctx {
   DevState* h_st[2] = {nullptr, nullptr}; cudaEvent_t ev_mirror[2] = {nullptr, nullptr}; int mirror_next = 0; bool mirror_valid[2] = {false, false};
   uint64_t host_step = 0;
   uint64_t known_n_used = 0, known_max_add = 0;
+  bool maybe_inactive = false;  // false only when the host KNOWS no slot is inactive (compaction kernels skipped)
+  int mirror_period = 8;        // asynchronous DevState mirror every this many cycles
   // launch config
   int n_sm = 148, grid_cycle = 148, blocks_per_sm = 1; size_t smem_bins = 0; int bins_in_smem = 0;
   uint64_t launches = 0;
@@ -213,6 +213,7 @@ static int resize_container(bmc_ctx* ctx, size_t new_cap, size_t keep) {
   CK(cudaMemsetAsync(ctx->div_mask, 0, new_cap / 32 * 4, s));
   CK(cudaMemsetAsync(ctx->tile_div, 0, n_tiles * 4, s));
   CK(cudaMemsetAsync(ctx->tile_off, 0, n_tiles * 4, s));
+  CK(cudaMemsetAsync(&ctx->st->clear_n, 0, sizeof(unsigned long long), s));  // bitmask arrays are fresh
   CK(cudaStreamSynchronize(s));
   return BMC_OK;
 }
@@ -271,6 +272,7 @@ static int sync_state(bmc_ctx* ctx, DevState* out) {
   ctx->mirror_valid[0] = ctx->mirror_valid[1] = false;
   *out = *ctx->h_st[0];
   ctx->known_n_used = out->n_used;
+  if (out->inactive == 0 && ctx->flows.empty()) ctx->maybe_inactive = false;
   if (out->error & 2u) { ctx->err = "compaction found fewer idle tail particles than gaps (inactive counter inconsistent)"; return BMC_ERR_INVALID; }
   return BMC_OK;
 }
@@ -416,6 +418,7 @@ int bmc_set_particles(bmc_ctx* ctx, uint64_t n, const float* props, const uint64
   DevState hs;
   if ((rc = sync_state(ctx, &hs))) return rc;
   if (hs.error & 1u) { ctx->err = "particle position out of range"; return BMC_ERR_RANGE; }
+  ctx->maybe_inactive = hs.inactive != 0;
   ctx->host_step = 0; ctx->known_max_add = 0;
   return BMC_OK;
 }
@@ -473,6 +476,7 @@ int bmc_init_particles(bmc_ctx* ctx, uint64_t n, int uniform_position, const flo
   DevState hs;
   if ((rc = sync_state(ctx, &hs))) return rc;
   if (total_mass) *total_mass = hs.init_mass;
+  ctx->maybe_inactive = false;
   ctx->host_step = 0; ctx->known_max_add = 0;
   return BMC_OK;
 }
@@ -553,13 +557,18 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   const uint32_t n_bins = (uint32_t)(ctx->n_species * ctx->n_comp);
   const bool enable_move = ctx->n_comp > 1;        // kernels.hpp:53-55
   const bool enable_leave = !ctx->flows.empty();   // kernels.hpp:56
-  // per-compartment rows {leave threshold, model terms}: depends on dt, the flow map and this
-  // step's concentrations -> rebuilt every step (n_comp threads)
-  ctx->vt.launch_ctab(ctx->d_diag, ctx->d_vol, d_t, ctx->d_conc, (uint32_t)ctx->n_species, ctx->d_ctab, (uint32_t)ctx->n_comp,
-                      enable_move ? 1 : 0, s);
-  if ((rc = check_launch(ctx, "compartment_table"))) return rc;
-  prepare_kernel<<<(n_bins + 255) / 256, 256, 0, s>>>(ctx->st, ctx->d_sources, n_bins, ctx->cap, ctx->buf_cap, (unsigned)ctx->grid_cycle);
-  if ((rc = check_launch(ctx, "prepare"))) return rc;
+  PreParams pp;
+  pp.st = ctx->st; pp.sources = ctx->d_sources; pp.n_bins = n_bins; pp.cap = ctx->cap; pp.buf_cap = ctx->buf_cap;
+  pp.grid_cycle = (unsigned)ctx->grid_cycle;
+  pp.diag = ctx->d_diag; pp.vol = ctx->d_vol; pp.dt = d_t; pp.conc = ctx->d_conc; pp.n_species = (uint32_t)ctx->n_species;
+  pp.ctab = ctx->d_ctab; pp.n_comp = (uint32_t)ctx->n_comp; pp.enable_move = enable_move ? 1 : 0;
+  pp.buf_mother = ctx->buf_mother; pp.div_mask = ctx->div_mask; pp.tile_div = ctx->tile_div;
+  {
+    const uint32_t work = std::max<uint32_t>(std::max<uint32_t>(n_bins, (uint32_t)ctx->n_comp), 256u);
+    const int grid = (int)std::min<uint32_t>((work + 255) / 256, (uint32_t)ctx->n_sm * 2);
+    ctx->vt.launch_pre(pp, grid, s);
+    if ((rc = check_launch(ctx, "pre_step"))) return rc;
+  }
 
   CycleParams p;
   memset(&p, 0, sizeof(p));
@@ -580,6 +589,7 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   p.step = (uint32_t)ctx->host_step; p.rank = ctx->rank; p.seed_lo = (uint32_t)ctx->seed; p.seed_hi = (uint32_t)(ctx->seed >> 32);
   p.enable_move = enable_move; p.enable_leave = enable_leave; p.bins_in_smem = ctx->bins_in_smem;
   p.prefetch_ahead = ctx->prefetch_ahead;
+  p.min_removal = ctx->min_removal; p.dead_ratio = ctx->dead_ratio;
 
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx->profile) {
@@ -590,16 +600,15 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   if ((rc = check_launch(ctx, "cycle_kernel"))) return rc;
   if (ctx->profile) { CK(cudaEventRecord(e1, s)); ctx->prof_events.emplace_back(e0, e1); }
 
-  post_plan_kernel<<<1, 32, 0, s>>>(ctx->st, ctx->min_removal, ctx->dead_ratio);
-  if ((rc = check_launch(ctx, "post_plan"))) return rc;
-
-  CompactParams cp;
-  cp.props = ctx->props; cp.cap = ctx->cap; cp.n_var = ctx->vt.n_var; cp.pos = ctx->pos; cp.status = ctx->status;
-  cp.age_hyd = ctx->age_hyd; cp.age_div = ctx->age_div; cp.st = ctx->st;
-  cp.tile_gap_off = ctx->tile_gap_off; cp.tile_idle_off = ctx->tile_idle_off; cp.blk_gap = ctx->blk_gap; cp.blk_idle = ctx->blk_idle; cp.src = ctx->src;
-  {
-    // Exits only happen with outlets, but inactive particles may also come from the
-    // caller's initial statuses; the kernels return immediately unless triggered.
+  if (enable_leave) ctx->maybe_inactive = true;  // exits may happen from now on
+  if (ctx->maybe_inactive) {
+    // The trigger is evaluated on the device (cycle kernel's last block); these kernels return
+    // immediately unless it fired.  They are skipped entirely only when the host knows that no
+    // inactive slot can exist (no outlet so far and none in the initial statuses).
+    CompactParams cp;
+    cp.props = ctx->props; cp.cap = ctx->cap; cp.n_var = ctx->vt.n_var; cp.pos = ctx->pos; cp.status = ctx->status;
+    cp.age_hyd = ctx->age_hyd; cp.age_div = ctx->age_div; cp.st = ctx->st;
+    cp.tile_gap_off = ctx->tile_gap_off; cp.tile_idle_off = ctx->tile_idle_off; cp.blk_gap = ctx->blk_gap; cp.blk_idle = ctx->blk_idle; cp.src = ctx->src;
     const int gc = std::min(ctx->n_sm * 2, kMaxGrid);
     compact_count_kernel<<<gc, 1024, 0, s>>>(cp);
     if ((rc = check_launch(ctx, "compact_count"))) return rc;
@@ -607,8 +616,6 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
     if ((rc = check_launch(ctx, "compact_src"))) return rc;
     compact_move_kernel<<<gc, 1024, 0, s>>>(cp);
     if ((rc = check_launch(ctx, "compact_move"))) return rc;
-    compact_commit_kernel<<<ctx->n_sm, 256, 0, s>>>(cp);
-    if ((rc = check_launch(ctx, "compact_commit"))) return rc;
   }
   InsertParams ip;
   ip.props = ctx->props; ip.cap = ctx->cap; ip.n_var = ctx->vt.n_var; ip.pos = ctx->pos; ip.status = ctx->status;
@@ -616,17 +623,17 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   ip.buf_props = ctx->buf_props; ip.buf_stride = ctx->buf_cap; ip.buf_pos = ctx->buf_pos; ip.buf_mother = ctx->buf_mother;
   ip.div_mask = ctx->div_mask; ip.tile_div = ctx->tile_div; ip.tile_off = ctx->tile_off; ip.blk_total = ctx->blk_total;
   ip.count_step = 1;
-  insert_kernel<<<ctx->n_sm * 2, 256, 0, s>>>(ip);
-  if ((rc = check_launch(ctx, "insert"))) return rc;
-  finalize_kernel<<<ctx->n_sm * 2, 256, 0, s>>>(ip);
-  if ((rc = check_launch(ctx, "finalize"))) return rc;
+  post_kernel<<<ctx->n_sm, 256, 0, s>>>(ip);
+  if ((rc = check_launch(ctx, "post"))) return rc;
 
   // asynchronous mirror of the device bookkeeping (never waited on here)
-  const int mi = ctx->mirror_next;
-  CK(cudaMemcpyAsync(ctx->h_st[mi], ctx->st, sizeof(DevState), cudaMemcpyDeviceToHost, s));
-  CK(cudaEventRecord(ctx->ev_mirror[mi], s));
-  ctx->mirror_valid[mi] = true;
-  ctx->mirror_next ^= 1;
+  if (ctx->host_step % (uint64_t)ctx->mirror_period == 0) {
+    const int mi = ctx->mirror_next;
+    CK(cudaMemcpyAsync(ctx->h_st[mi], ctx->st, sizeof(DevState), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(ctx->ev_mirror[mi], s));
+    ctx->mirror_valid[mi] = true;
+    ctx->mirror_next ^= 1;
+  }
   ctx->host_step++;
   return BMC_OK;
 }
@@ -674,11 +681,8 @@ int bmc_compact(bmc_ctx* ctx) {
   int rc;
   const unsigned int one = 1;
   CK(cudaMemcpyAsync(&ctx->st->force_compact, &one, 4, cudaMemcpyHostToDevice, s));
-  const unsigned long long zero = 0;
-  CK(cudaMemcpyAsync(&ctx->st->step_exit, &zero, 8, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(&ctx->st->buf_index, &zero, 8, cudaMemcpyHostToDevice, s));
-  post_plan_kernel<<<1, 32, 0, s>>>(ctx->st, ctx->min_removal, ctx->dead_ratio);
-  if ((rc = check_launch(ctx, "post_plan"))) return rc;
+  plan_kernel<<<1, 32, 0, s>>>(ctx->st, ctx->min_removal, ctx->dead_ratio);
+  if ((rc = check_launch(ctx, "plan"))) return rc;
   CompactParams cp;
   cp.props = ctx->props; cp.cap = ctx->cap; cp.n_var = ctx->vt.n_var; cp.pos = ctx->pos; cp.status = ctx->status;
   cp.age_hyd = ctx->age_hyd; cp.age_div = ctx->age_div; cp.st = ctx->st;
@@ -687,13 +691,12 @@ int bmc_compact(bmc_ctx* ctx) {
   compact_count_kernel<<<gc, 1024, 0, s>>>(cp); if ((rc = check_launch(ctx, "compact_count"))) return rc;
   compact_src_kernel<<<gc, 1024, 0, s>>>(cp); if ((rc = check_launch(ctx, "compact_src"))) return rc;
   compact_move_kernel<<<gc, 1024, 0, s>>>(cp); if ((rc = check_launch(ctx, "compact_move"))) return rc;
-  compact_commit_kernel<<<ctx->n_sm, 256, 0, s>>>(cp); if ((rc = check_launch(ctx, "compact_commit"))) return rc;
   InsertParams ip;
   memset(&ip, 0, sizeof(ip));
-  ip.st = ctx->st; ip.buf_mother = ctx->buf_mother; ip.div_mask = ctx->div_mask; ip.tile_div = ctx->tile_div;
-  // n_add is 0 here: finalize only commits n_used / inactive
-  ip.count_step = 0;
-  finalize_kernel<<<1, 256, 0, s>>>(ip); if ((rc = check_launch(ctx, "finalize"))) return rc;
+  ip.status = ctx->status; ip.st = ctx->st; ip.buf_mother = ctx->buf_mother; ip.div_mask = ctx->div_mask; ip.tile_div = ctx->tile_div;
+  ip.blk_total = ctx->blk_total;
+  ip.count_step = 0;  // n_add is 0 here (the plan cleared buffer_index): post only commits n_used / inactive
+  post_kernel<<<ctx->n_sm, 256, 0, s>>>(ip); if ((rc = check_launch(ctx, "post"))) return rc;
   DevState hs;
   return sync_state(ctx, &hs);
 }

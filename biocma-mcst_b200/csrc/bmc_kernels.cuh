@@ -8,14 +8,14 @@
 // structure-of-arrays state followed by O(events) bookkeeping kernels, with no
 // host synchronisation:
 //
-//   prepare      zero the source accumulators, fix this step's buffer capacity
+//   pre_step     zero the source accumulators, build the per-compartment table,
+//                clear last step's division bits, fix this step's buffer capacity
 //   cycle        fused model update + division + contribution scatter + move +
-//                outlet exit                      [HBM-bound, dominant kernel]
-//   post_plan    update_and_remove_inactive decision (1 thread)
-//   compact_*    deterministic stream compaction of exited particles (early-exit
-//                when not triggered)
-//   insert       merge_buffer: append newborns in ascending-mother order
-//   finalize     counters, clear the division bitmask
+//                outlet exit                      [HBM-bound, dominant kernel];
+//                its last block decides update_and_remove_inactive (the "plan")
+//   compact_*    deterministic stream compaction of exited particles (launched only
+//                when inactive particles can exist; early-exit when not triggered)
+//   post         merge_buffer: append newborns in ascending-mother order, commit
 //
 // Work distribution: a persistent grid (multiple of the SM count); block b owns
 // the contiguous 1024-particle tiles [b*T/G, (b+1)*T/G).  Contiguous ownership
@@ -76,6 +76,9 @@ struct DevState {
   unsigned int cmp_total_idle;      // idle particles found in the compaction tail
   unsigned int error;               // sticky device-side error flags (1 = bad position, 2 = compaction mismatch)
   double init_mass;                 // total mass reduce of mc_init_first
+  unsigned int done_blocks;         // ticket counter: the last cycle block to finish writes the plan
+  unsigned int pad0;
+  unsigned long long clear_n;       // division records whose bitmask bits the next pre_step clears
 };
 
 struct Outlet { uint32_t index; uint32_t pad; double flow; double dt_flow; double volume; };
@@ -104,6 +107,7 @@ struct CycleParams {
   uint32_t step, rank, seed_lo, seed_hi;
   int enable_move, enable_leave, bins_in_smem;
   int prefetch_ahead;  // tiles of L2 prefetch distance (0 = off)
+  unsigned long long min_removal; double dead_ratio;  // RuntimeParameters used by the post-cycle plan
 };
 
 __device__ __forceinline__ unsigned warp_excl_scan(unsigned v, unsigned& total) {
@@ -163,43 +167,80 @@ template <> struct VecIO<1> {
 };
 
 // -----------------------------------------------------------------------------
-// prepare: contribs_scatter.reset() (simulation.hpp:201) + per-step bookkeeping
+// pre_step: everything that must happen before the particle pass, in one launch:
+//   * contribs_scatter.reset() (simulation.hpp:201): zero the source accumulators
+//   * compartment table, one row per compartment (n_comp rows — 500 .. 10k — not N):
+//       col 0        ceil_f32(dt * diag_transition / liquid_volume)   leave threshold
+//       col 1..n_pre M::compartment_terms(c, compartment)             optional model hook
+//     A model whose update starts with a function of the local concentration only
+//     (Monod: mu = mu_max*s/(k_s+s)) hoists it here: the IEEE division then runs once
+//     per compartment instead of once per particle, with bit-identical results.
+//   * clear the division bitmask bits of the previous step's newborn records
+//   * this step's usable buffer capacity and the per-step counters
 // -----------------------------------------------------------------------------
-__global__ void prepare_kernel(DevState* st, double* sources, uint32_t n_bins, unsigned long long cap,
-                               unsigned long long buf_cap, unsigned int grid_cycle) {
+struct PreParams {
+  DevState* st; double* sources; uint32_t n_bins;
+  unsigned long long cap, buf_cap; unsigned int grid_cycle;
+  const double* diag; const double* vol; double dt; const double* conc; uint32_t n_species; float* ctab; uint32_t n_comp;
+  int enable_move;
+  const uint32_t* buf_mother; uint32_t* div_mask; uint32_t* tile_div;
+};
+
+template <class M>
+__global__ void __launch_bounds__(256) pre_step_kernel(const __grid_constant__ PreParams p) {
+  constexpr int CT = 1 + M::n_pre;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_bins) sources[i] = 0.0;
+  const uint32_t nthreads = gridDim.x * blockDim.x;
+  for (uint32_t k = i; k < p.n_bins; k += nthreads) p.sources[k] = 0.0;
+  for (uint32_t c = i; c < p.n_comp; c += nthreads) {
+    float row[CT];
+    row[0] = p.enable_move ? __double2float_ru(p.dt * p.diag[c] / p.vol[c]) : 0.0f;
+    if constexpr (M::n_pre > 0) M::compartment_terms(ConcView{p.conc, p.n_species, nullptr}, (size_t)c, row + 1);
+#pragma unroll
+    for (int k = 0; k < CT; ++k) p.ctab[(size_t)c * CT + k] = row[k];
+  }
+  const unsigned long long n_clear = p.st->clear_n;
+  for (unsigned long long j = i; j < n_clear; j += nthreads) {
+    const uint32_t mother = p.buf_mother[j];
+    p.div_mask[mother >> 5] = 0u;
+    p.tile_div[mother >> 10] = 0u;
+  }
   if (i == 0) {
+    DevState* st = p.st;
     const unsigned long long n = st->n_used;
-    const unsigned long long room = cap > n ? cap - n : 0ull;
-    st->buf_cap_eff = buf_cap < room ? buf_cap : room;
+    const unsigned long long room = p.cap > n ? p.cap - n : 0ull;
+    st->buf_cap_eff = p.buf_cap < room ? p.buf_cap : room;
     st->buf_index = 0; st->step_exit = 0; st->step_waiting = 0;
     st->cyc_n_used = n;
     st->cyc_tiles = (unsigned int)((n + kTile - 1) / kTile);
-    st->cyc_grid = grid_cycle;
+    st->cyc_grid = p.grid_cycle;
   }
 }
 
-// -----------------------------------------------------------------------------
-// compartment table: everything the particle pass needs per compartment, one row
-// per compartment, rebuilt once per step (n_comp rows — 500 .. 10k — not N):
-//   col 0        ceil_f32(dt * diag_transition / liquid_volume)   leave threshold
-//   col 1..n_pre M::compartment_terms(c, compartment)             optional model hook
-// A model whose update starts with a function of the local concentration only
-// (Monod: mu = mu_max*s/(k_s+s)) can hoist it here: the IEEE division then runs once
-// per compartment instead of once per particle, with bit-identical results.
-// -----------------------------------------------------------------------------
-template <class M>
-__global__ void compartment_table_kernel(const double* diag, const double* vol, double dt, const double* conc, uint32_t n_species,
-                                         float* ctab, uint32_t n_comp, int enable_move) {
-  constexpr int CT = 1 + M::n_pre;
-  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_comp) return;
-  float row[CT];
-  row[0] = enable_move ? __double2float_ru(dt * diag[c] / vol[c]) : 0.0f;
-  if constexpr (M::n_pre > 0) M::compartment_terms(ConcView{conc, n_species, nullptr}, (size_t)c, row + 1);
-#pragma unroll
-  for (int k = 0; k < CT; ++k) ctab[(size_t)c * CT + k] = row[k];
+// update_and_remove_inactive (particles_container.hpp:539-557) and the merge_buffer size
+// (:575-581), decided on the device by ONE thread once every particle has been processed.
+__device__ __forceinline__ void make_plan(DevState* st, unsigned long long min_removal, double dead_ratio) {
+  const unsigned long long out = st->step_exit;
+  st->last_out = out; st->last_dead = 0; st->last_waiting = st->step_waiting;
+  st->total_out += out;
+  st->inactive += out;  // inactive_counter += out; += dead (always 0, Q3)
+  st->step_exit = 0;
+  const unsigned long long n = st->n_used;
+  unsigned long long thr = (unsigned long long)((double)n * dead_ratio);
+  if (min_removal > thr) thr = min_removal;
+  const bool trig = (st->inactive > thr) || (st->force_compact && st->inactive > 0);
+  st->force_compact = 0;
+  st->cmp_old_n = n;
+  if (trig) {
+    st->do_compact = 1;
+    st->cmp_new_n = n - st->inactive;
+    st->cmp_tiles = (unsigned int)((n + kTile - 1) / kTile);
+  } else {
+    st->do_compact = 0; st->cmp_new_n = n;
+  }
+  const unsigned long long bi = st->buf_index;
+  st->n_add = bi < st->buf_cap_eff ? bi : st->buf_cap_eff;
+  st->buf_index = 0;
 }
 
 // -----------------------------------------------------------------------------
@@ -560,33 +601,25 @@ __global__ void __launch_bounds__(kBlock, MINB) cycle_kernel(const __grid_consta
     }
     if (lane == 0) p.blk_total[blockIdx.x] = run;
   }
+  // last block to finish: every block's counters are visible (fence + ticket) -> write the
+  // post-cycle plan (compaction trigger, newborn count) for the kernels that follow
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned ticket = atomicAdd(&p.st->done_blocks, 1u);
+    if (ticket == gridDim.x - 1) {
+      __threadfence();
+      p.st->done_blocks = 0;
+      p.st->clear_n = 0;
+      make_plan(p.st, p.min_removal, p.dead_ratio);
+    }
+  }
 }
 
-// -----------------------------------------------------------------------------
-// post_plan: update_and_remove_inactive (particles_container.hpp:539-557) and the
-// merge_buffer size (:575-581), decided on the device.
-// -----------------------------------------------------------------------------
-__global__ void post_plan_kernel(DevState* st, unsigned long long min_removal, double dead_ratio) {
+// plan without a particle pass (ParticlesContainer::force_remove_dead path)
+__global__ void plan_kernel(DevState* st, unsigned long long min_removal, double dead_ratio) {
   if (blockIdx.x || threadIdx.x) return;
-  const unsigned long long out = st->step_exit;
-  st->last_out = out; st->last_dead = 0; st->last_waiting = st->step_waiting;
-  st->total_out += out;
-  st->inactive += out;  // inactive_counter += out; += dead (always 0)
-  const unsigned long long n = st->n_used;
-  unsigned long long thr = (unsigned long long)((double)n * dead_ratio);
-  if (min_removal > thr) thr = min_removal;
-  const bool trig = (st->inactive > thr) || (st->force_compact && st->inactive > 0);
-  st->force_compact = 0;
-  st->cmp_old_n = n;
-  if (trig) {
-    st->do_compact = 1;
-    st->cmp_new_n = n - st->inactive;
-    st->cmp_tiles = (unsigned int)((n + kTile - 1) / kTile);
-  } else {
-    st->do_compact = 0; st->cmp_new_n = n;
-  }
-  const unsigned long long bi = st->buf_index;
-  st->n_add = bi < st->buf_cap_eff ? bi : st->buf_cap_eff;
+  make_plan(st, min_removal, dead_ratio);
 }
 
 // -----------------------------------------------------------------------------
@@ -645,16 +678,24 @@ __global__ void __launch_bounds__(1024) compact_count_kernel(const __grid_consta
   if (threadIdx.x == 0) { p.blk_gap[blockIdx.x] = run_g; p.blk_idle[blockIdx.x] = run_i; }
 }
 
-// exclusive prefix of per-block totals in shared memory (grid <= kMaxGrid)
+// exclusive prefix of per-block totals in shared memory (grid <= kMaxGrid): warp 0 scans 32
+// entries per step with shuffles; executed by the whole block
 __device__ __forceinline__ unsigned block_prefix_of(const uint32_t* blk_tot, unsigned nblk, unsigned b, unsigned* s_tmp,
                                                     unsigned& grand_total) {
-  // s_tmp has kMaxGrid entries; executed by the whole block
-  for (unsigned k = threadIdx.x; k < nblk; k += blockDim.x) s_tmp[k] = blk_tot[k];
+  for (unsigned k = threadIdx.x; k < nblk; k += blockDim.x) s_tmp[k] = __ldcg(blk_tot + k);  // one parallel pass
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
+    const unsigned lane = threadIdx.x;
     unsigned run = 0;
-    for (unsigned k = 0; k < nblk; ++k) { const unsigned t = s_tmp[k]; s_tmp[k] = run; run += t; }
-    s_tmp[nblk] = run;
+    for (unsigned base = 0; base < nblk; base += 32) {
+      const unsigned k = base + lane;
+      const unsigned v = k < nblk ? s_tmp[k] : 0u;
+      unsigned tot;
+      const unsigned ex = warp_excl_scan(v, tot);
+      if (k < nblk) s_tmp[k] = run + ex;
+      run += tot;
+    }
+    if (lane == 0) s_tmp[nblk] = run;
   }
   __syncthreads();
   grand_total = s_tmp[nblk];
@@ -730,17 +771,6 @@ __global__ void __launch_bounds__(1024) compact_move_kernel(const __grid_constan
   }
 }
 
-// slots [new_n, old_n) leave the container: mark them Idle so that appended
-// newborns never inherit a stale status (the reference relies on zero-initialised
-// storage, particles_container.hpp:403-443), then commit n_used.
-__global__ void compact_commit_kernel(const __grid_constant__ CompactParams p) {
-  if (!p.st->do_compact) return;
-  const unsigned long long old_n = p.st->cmp_old_n, new_n = p.st->cmp_new_n;
-  for (unsigned long long i = new_n + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < old_n;
-       i += (unsigned long long)gridDim.x * blockDim.x)
-    p.status[i] = (uint8_t)Idle;
-}
-
 // -----------------------------------------------------------------------------
 // insert: merge_buffer + InsertFunctor (particles_container.hpp:575-599,
 // 403-443).  Newborn of mother i goes to new_n + (number of dividing mothers with
@@ -756,46 +786,48 @@ struct InsertParams {
   int count_step;  // 1 when called from a cycle, 0 from force_remove_dead
 };
 
-__global__ void __launch_bounds__(256) insert_kernel(const __grid_constant__ InsertParams p) {
-  const unsigned long long n_add = p.st->n_add;
-  if (n_add == 0) return;
+__global__ void __launch_bounds__(256) post_kernel(const __grid_constant__ InsertParams p) {
   __shared__ unsigned s_pref[kMaxGrid + 1];
-  const unsigned G = p.st->cyc_grid;
-  const unsigned T = p.st->cyc_tiles;
-  unsigned total;
-  block_prefix_of(p.blk_total, G, 0, s_pref, total);
-  const unsigned long long base = p.st->cmp_new_n;
-  for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < n_add;
-       j += (unsigned long long)gridDim.x * blockDim.x) {
-    const uint32_t mother = p.buf_mother[j];
-    const uint32_t tile = mother >> 10;
-    const unsigned b = (unsigned)((((unsigned long long)tile + 1ull) * G - 1ull) / T);  // owner block of the tile
-    const uint32_t* words = p.div_mask + (size_t)tile * (kTile / 32);
-    const unsigned wi = (mother & (kTile - 1)) >> 5, bit = mother & 31u;
-    unsigned rank = 0;
-    for (unsigned k = 0; k < wi; ++k) rank += __popc(words[k]);
-    rank += __popc(words[wi] & ((1u << bit) - 1u));
-    const unsigned long long dst = base + s_pref[b] + p.tile_off[tile] + rank;
-    for (int c = 0; c < p.n_var; ++c) p.props[(size_t)c * p.cap + dst] = p.buf_props[(size_t)c * p.buf_stride + j];
-    p.pos[dst] = p.buf_pos[j];
-    p.age_hyd[dst] = 0.f; p.age_div[dst] = 0.f;  // InsertFunctor: both ages reset
-    p.status[dst] = (uint8_t)Idle;
-  }
-}
-
-__global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ InsertParams p) {
   const unsigned long long n_add = p.st->n_add;
-  for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < n_add;
-       j += (unsigned long long)gridDim.x * blockDim.x) {
-    const uint32_t mother = p.buf_mother[j];
-    p.div_mask[mother >> 5] = 0u;
-    p.tile_div[mother >> 10] = 0u;
+  const unsigned long long base = p.st->cmp_new_n;
+  const unsigned long long gtid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long gstride = (unsigned long long)gridDim.x * blockDim.x;
+  // slots [new_n, old_n) left the container in a compaction: mark them Idle so that appended
+  // newborns never inherit a stale status (the reference relies on zero-initialised storage,
+  // particles_container.hpp:403-443).  Newborn slots below are written Idle as well, so the
+  // two writers agree where they overlap.
+  if (p.st->do_compact) {
+    const unsigned long long old_n = p.st->cmp_old_n;
+    for (unsigned long long i = base + gtid; i < old_n; i += gstride) p.status[i] = (uint8_t)Idle;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (n_add) {  // uniform across the grid
+    const unsigned G = p.st->cyc_grid;
+    const unsigned T = p.st->cyc_tiles;
+    unsigned total;
+    block_prefix_of(p.blk_total, G, 0, s_pref, total);
+    for (unsigned long long j = gtid; j < n_add; j += gstride) {
+      const uint32_t mother = p.buf_mother[j];
+      const uint32_t tile = mother >> 10;
+      const unsigned b = (unsigned)((((unsigned long long)tile + 1ull) * G - 1ull) / T);  // owner block of the tile
+      const uint32_t* words = p.div_mask + (size_t)tile * (kTile / 32);
+      const unsigned wi = (mother & (kTile - 1)) >> 5, bit = mother & 31u;
+      unsigned rank = 0;
+      for (unsigned k = 0; k < wi; ++k) rank += __popc(words[k]);
+      rank += __popc(words[wi] & ((1u << bit) - 1u));
+      const unsigned long long dst = base + s_pref[b] + p.tile_off[tile] + rank;
+      for (int c = 0; c < p.n_var; ++c) p.props[(size_t)c * p.cap + dst] = p.buf_props[(size_t)c * p.buf_stride + j];
+      p.pos[dst] = p.buf_pos[j];
+      p.age_hyd[dst] = 0.f; p.age_div[dst] = 0.f;  // InsertFunctor: both ages reset
+      p.status[dst] = (uint8_t)Idle;
+    }
+  }
+  // commit (one thread).  Only fields no other thread of this kernel reads are modified.
+  if (gtid == 0) {
     DevState* st = p.st;
     if (st->do_compact) { st->inactive -= (st->cmp_old_n - st->cmp_new_n); st->n_compactions += 1; }
-    st->n_used = st->cmp_new_n + n_add;
+    st->n_used = base + n_add;
     st->total_new += n_add;
+    if (n_add > st->clear_n) st->clear_n = n_add;  // bits cleared by the next pre_step
     st->step += (unsigned long long)p.count_step;
   }
 }
