@@ -114,6 +114,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "scope": scope}
 
 
+def host_threads():
+    """all host cores this process may use (torchrun exports OMP_NUM_THREADS=1: ignore it)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def build_case(synth, model, n_comp, dt, p_exit):
     fm = synth.make_flowmap(n_comp, dt, p_move=0.01, seed=2024)
     flows = []
@@ -144,7 +152,7 @@ def run_reference(args, wl):
     from _bmc_loader import load_synth
     synth = load_synth()
     model, n_comp, n_full, dt, near, p_exit = WORKLOADS[wl]
-    threads = oracle.max_threads()
+    threads = host_threads()
     n = min(n_full, args.cpu_sample)
     fm, flows, conc = build_case(synth, model, n_comp, dt, p_exit)
     props, pos = synth.make_population(model, n, n_comp, seed=11, near_division=near)
@@ -323,7 +331,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import oracle
-            threads = oracle.max_threads()
+            threads = host_threads()
             n = min(n_per_gpu, args.cpu_sample)
             props, pos = synth.make_population(model, n, n_comp, seed=11, near_division=near)
             o = oracle.OracleLoop(model, 1, n_comp, n_threads=threads)

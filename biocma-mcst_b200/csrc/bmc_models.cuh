@@ -294,7 +294,7 @@ struct SimpleAcetate {
 // Wide UDF — synthetic multi-metabolite user model (BASELINE.json configs[4]),
 // written against the UDF hook surface (apps/udf_model/minimal.cpp:59-155):
 // P float properties all read and written every step, n_c = 4 contributions.
-// Same definition as oracle/bmc_oracle.cpp `WideUdf`.
+// The test oracle carries an independent restatement of the same definition.
 // =============================================================================
 template <int P> struct WideUdf {
   static constexpr int n_var = P, n_c = 4, n_pre = 4;

@@ -1,0 +1,73 @@
+"""N>1 host logic on CPU: two gloo ranks, particles sharded with the reference's
+balancing rule, replicated compartment state, one all-reduce of the source vector.
+The per-rank compute is the oracle (tests may use it); the GPU path replaces it by
+ParticleLoop + bmc_allreduce_sources (NCCL)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_counts_follow_load_balancer(bmc):
+    from biocma_mcst_b200 import sharding
+    for n, w in ((10_000_000, 10), (1_000_003, 8), (7, 2), (5_000_000, 3)):
+        counts, offs = sharding.shard_offsets(n, w)
+        assert sum(counts) == n and offs[-1] == n                       # test_load_balancing.cpp:19-20
+        base = int(float(n) * (1.0 / w))
+        assert counts[1:] == [base] * (w - 1) and counts[0] == base + (n - base * w)  # remainder on rank 0
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from _bmc_loader import load_pkg, load_synth
+    load_pkg(); synth = load_synth()
+    from biocma_mcst_b200 import sharding
+    import oracle, util
+    case = util.make_case(synth, "monod", 60_001, 100, dt=5.0, near_division=0.5)
+    counts, offs = sharding.shard_offsets(case["n"], world)
+    lo, hi = offs[rank], offs[rank + 1]
+    o = oracle.OracleLoop("monod", 1, 100, rank=rank)
+    o.set_particles(case["props"][:, lo:hi], case["pos"][lo:hi])
+    o.set_weight(case["weight"])
+    fm = case["fm"]
+    o.domain_update(fm["volumes"], fm["neighbors"], fm["out_flows"], fm["cdf"])
+    o.set_leaving_flows(case["flows"]); o.set_concentrations(case["conc"])
+    o.cycle(case["dt"])
+    total = sharding.allreduce_sources_torch(o.get_sources())
+    n_tot = np.array([o.counters()["n_used"]], np.float64)
+    n_tot = sharding.allreduce_sources_torch(n_tot)
+    if rank == 0:
+        q.put((total, float(n_tot[0]), counts))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_source_allreduce_matches_single_rank(orc, synth):
+    import util
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    total, n_tot, counts = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-rank reference: contributions are taken at the pre-move position of this step, so the
+    # sharded sum must equal the unsharded one up to fp64 summation order
+    case = util.make_case(synth, "monod", 60_001, 100, dt=5.0, near_division=0.5)
+    o = orc.OracleLoop("monod", 1, 100)
+    util.load_case(o, case)
+    o.cycle(case["dt"])
+    ref = o.get_sources()
+    assert counts == [30_001, 30_000]
+    assert np.allclose(total, ref, rtol=1e-12, atol=0)
+    assert n_tot == o.counters()["n_used"]  # same number of divisions in total
