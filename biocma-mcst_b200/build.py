@@ -6,52 +6,74 @@ nvcc cross-compiles for sm_100a without a GPU.  Flags that matter:
                                             deterministic models are bit-exact
                                             against the oracle (-ffp-contract=off)
   -lineinfo                                 ncu source page maps to the .cuh files
+Each model's kernels live in their own translation unit; the units compile in parallel.
 """
+import glob
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libbmc_b200.so")
-SOURCES = [os.path.join(CSRC, "bmc_api.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("bmc_kernels.cuh", "bmc_models.cuh", "bmc_rng.cuh")] + [
-    os.path.join(HERE, "..", "include", "bmc.h")]
+OBJ_DIR = os.path.join(HERE, "build")
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def deps():
+    return sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(HERE, "..", "include", "bmc.h")]
 
 
 def nvcc_path():
-    for p in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
-        if p and (os.path.isabs(p) and os.path.exists(p) or not os.path.isabs(p)):
+    for p in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc"):
+        if p and os.path.exists(p):
             return p
     return "nvcc"
 
 
-def needs_build():
-    if not os.path.exists(OUT):
+def needs_build(out=OUT):
+    if not os.path.exists(out):
         return True
-    t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(d) > t for d in DEPS if os.path.exists(d))
+    t = os.path.getmtime(out)
+    return any(os.path.getmtime(d) > t for d in deps() if os.path.exists(d))
 
 
 def build(force=False, verbose=False, defines=(), out=None):
     if out is None and not force and not needs_build():
         return OUT
     out = out or OUT
-    cmd = [nvcc_path(), "-std=c++17", "-O3", "-lineinfo", "-fmad=false",
-           "-gencode", "arch=compute_100a,code=sm_100a",
-           "-Xcompiler", "-fPIC", "-shared", "-o", out] + [f"-D{d}" for d in defines] + SOURCES + ["-ldl"]
+    tag = os.path.splitext(os.path.basename(out))[0]
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    common = [nvcc_path()]
+    if os.path.exists("/usr/bin/g++"):  # the image exports CC/CXX=/opt/gcc; nvcc is happy with the distro g++
+        common += ["-ccbin", "/usr/bin/g++"]
+    common += ["-std=c++17", "-O3", "-lineinfo", "-fmad=false", "-gencode", "arch=compute_100a,code=sm_100a",
+               "-Xcompiler", "-fPIC"] + [f"-D{d}" for d in defines]
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    env = dict(os.environ)
-    # the image exports CC/CXX=/opt/gcc (no libgomp spec); nvcc is happy with the distro g++
-    if os.path.exists("/usr/bin/g++"):
-        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
-    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        common += ["-Xptxas=-v"]
+
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, f"{tag}_{os.path.splitext(os.path.basename(src))[0]}.o")
+        r = subprocess.run(common + ["-c", src, "-o", obj], capture_output=True, text=True)
+        return src, obj, r
+
+    with ThreadPoolExecutor(max_workers=min(8, len(sources()))) as ex:
+        results = list(ex.map(compile_one, sources()))
+    objs = []
+    for src, obj, r in results:
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}")
+        objs.append(obj)
+    r = subprocess.run(common[:3] + ["-shared", "-o", out] + objs + ["-ldl"], capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libbmc_b200.so")
-    if verbose:
-        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link of libbmc_b200.so failed")
     return out
 
 

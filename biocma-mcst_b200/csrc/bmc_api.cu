@@ -15,71 +15,21 @@
 #include <cuda_runtime.h>
 
 #include "../../include/bmc.h"
-#include "bmc_kernels.cuh"
+#include "bmc_kernels_common.cuh"
+#include "bmc_model_vt.cuh"
 
 using namespace bmc;
 
 namespace {
 
-struct ModelVT {
-  int n_var, n_c, vec;
-  const void* cycle_fn;
-  void (*launch_cycle)(const CycleParams&, int grid, size_t smem, cudaStream_t);
-  void (*launch_init)(float*, size_t, uint32_t*, uint8_t*, float*, float*, unsigned long long, uint32_t, const float*,
-                      uint32_t, uint32_t, uint32_t, DevState*, int, cudaStream_t);
-  int ct;  // floats per compartment-table row
-  void (*launch_pre)(const PreParams&, int grid, cudaStream_t);
-};
-
-template <class M, int VEC, int MINB> static void launch_cycle_t(const CycleParams& p, int grid, size_t smem, cudaStream_t s) {
-  cycle_kernel<M, VEC, MINB><<<grid, kBlock, smem, s>>>(p);
-}
-template <class M>
-static void launch_init_t(float* props, size_t cap, uint32_t* pos, uint8_t* status, float* ah, float* ad, unsigned long long n,
-                          uint32_t ncomp_hi, const float* linit, uint32_t slo, uint32_t shi, uint32_t rank, DevState* st, int grid,
-                          cudaStream_t s) {
-  init_kernel<M><<<grid, 256, 0, s>>>(props, cap, pos, status, ah, ad, n, ncomp_hi, linit, slo, shi, rank, st);
-}
-template <class M> static void launch_pre_t(const PreParams& p, int grid, cudaStream_t s) {
-  pre_step_kernel<M><<<grid, 256, 0, s>>>(p);
-}
-template <class M, int VEC, int MINB = 1> static ModelVT make_vt() {
-  ModelVT v;
-  v.n_var = M::n_var; v.n_c = M::n_c; v.vec = VEC;
-  v.cycle_fn = (const void*)cycle_kernel<M, VEC, MINB>;
-  v.launch_cycle = &launch_cycle_t<M, VEC, MINB>;
-  v.launch_init = &launch_init_t<M>;
-  v.ct = 1 + M::n_pre;
-  v.launch_pre = &launch_pre_t<M>;
-  return v;
-}
-
 static bool pick_model(int model, int n_var_udf, ModelVT& vt) {
+  const char* v = getenv("BMC_VARIANT");
+  const std::string var = v ? v : "";
   switch (model) {
-    case BMC_MODEL_FIXED_LENGTH: vt = make_vt<FixedLength, 4>(); return true;
-    case BMC_MODEL_MONOD: {
-      const char* v = getenv("BMC_VARIANT");  // tuning experiments only
-      const std::string var = v ? v : "";
-      if (var == "v4b3") vt = make_vt<Monod, 4, 3>();
-      else if (var == "v4b4") vt = make_vt<Monod, 4, 4>();
-      else if (var == "v2b4") vt = make_vt<Monod, 2, 4>();
-      else if (var == "v2b6") vt = make_vt<Monod, 2, 6>();
-      else if (var == "v2b8") vt = make_vt<Monod, 2, 8>();
-      else if (var == "v1b8") vt = make_vt<Monod, 1, 8>();
-      else if (var == "v4b1") vt = make_vt<Monod, 4, 1>();
-      else if (var == "v4b2") vt = make_vt<Monod, 4, 2>();
-      else vt = make_vt<Monod, 4, 3>();  // 80 registers -> 3 blocks (24 warps) per SM
-      return true;
-    }
-    case BMC_MODEL_SIMPLE_ACETATE: vt = make_vt<SimpleAcetate, 4>(); return true;
-    case BMC_MODEL_WIDE_UDF:
-      switch (n_var_udf) {
-        case 8: vt = make_vt<WideUdf<8>, 4>(); return true;
-        case 16: vt = make_vt<WideUdf<16>, 2>(); return true;
-        case 32: vt = make_vt<WideUdf<32>, 1>(); return true;
-        case 64: vt = make_vt<WideUdf<64>, 1>(); return true;
-        default: return false;
-      }
+    case BMC_MODEL_FIXED_LENGTH: return pick_fixed_length(var, vt);
+    case BMC_MODEL_MONOD: return pick_monod(var, vt);
+    case BMC_MODEL_SIMPLE_ACETATE: return pick_simple_acetate(var, vt);
+    case BMC_MODEL_WIDE_UDF: return n_var_udf <= 16 ? pick_wide_udf_small(var, n_var_udf, vt) : pick_wide_udf_large(var, n_var_udf, vt);
     default: return false;
   }
 }
@@ -121,7 +71,7 @@ struct bmc_ctx {
   // launch config
   int n_sm = 148, grid_cycle = 148, blocks_per_sm = 1; size_t smem_bins = 0; int bins_in_smem = 0;
   uint64_t launches = 0;
-  int prefetch_ahead = 1;
+  size_t stage_offset = 0, smem_total = 0;
   // staging
   void* d_stage = nullptr; size_t stage_bytes = 0;
   // profiling
@@ -237,12 +187,14 @@ static int configure_launch(bmc_ctx* ctx) {
   const size_t smem_budget = (size_t)prop.sharedMemPerBlockOptin;
   ctx->bins_in_smem = (ctx->n_comp > 1 && bins_bytes <= std::min<size_t>(smem_budget, 100 * 1024)) ? 1 : 0;
   ctx->smem_bins = ctx->bins_in_smem ? bins_bytes : 0;
-  if (ctx->smem_bins > 48 * 1024)
-    CK(cudaFuncSetAttribute(ctx->vt.cycle_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bins));
+  ctx->stage_offset = (ctx->smem_bins + 15) / 16 * 16;
+  ctx->smem_total = ctx->stage_offset + ctx->vt.stage_bytes;
+  if (ctx->smem_total > smem_budget) { ctx->err = "shared memory budget exceeded"; return BMC_ERR_UNSUPPORTED; }
+  if (ctx->smem_total > 48 * 1024)
+    CK(cudaFuncSetAttribute(ctx->vt.cycle_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_total));
   int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ctx->vt.cycle_fn, kBlock, ctx->smem_bins));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ctx->vt.cycle_fn, kBlock, ctx->smem_total));
   if (occ < 1) occ = 1;
-  if (const char* pf = getenv("BMC_PREFETCH")) ctx->prefetch_ahead = std::max(0, atoi(pf));
   const char* env = getenv("BMC_BLOCKS_PER_SM");
   if (env && atoi(env) > 0) occ = std::min(occ, atoi(env));
   ctx->blocks_per_sm = occ;
@@ -588,7 +540,7 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   p.weight = ctx->weight; p.dt = d_t; p.dt_f = (float)d_t;
   p.step = (uint32_t)ctx->host_step; p.rank = ctx->rank; p.seed_lo = (uint32_t)ctx->seed; p.seed_hi = (uint32_t)(ctx->seed >> 32);
   p.enable_move = enable_move; p.enable_leave = enable_leave; p.bins_in_smem = ctx->bins_in_smem;
-  p.prefetch_ahead = ctx->prefetch_ahead;
+  p.stage_offset = (uint32_t)ctx->stage_offset;
   p.min_removal = ctx->min_removal; p.dead_ratio = ctx->dead_ratio;
 
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -596,7 +548,7 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, s));
   }
-  ctx->vt.launch_cycle(p, ctx->grid_cycle, ctx->smem_bins, s);
+  ctx->vt.launch_cycle(p, ctx->grid_cycle, ctx->smem_total, s);
   if ((rc = check_launch(ctx, "cycle_kernel"))) return rc;
   if (ctx->profile) { CK(cudaEventRecord(e1, s)); ctx->prof_events.emplace_back(e0, e1); }
 

@@ -1,0 +1,6 @@
+// Kernel instantiations of one model (own translation unit: the models build in parallel).
+#include "bmc_model_vt.cuh"
+
+namespace bmc {
+bool pick_fixed_length(const std::string& var, ModelVT& vt) { return pick_variant<FixedLength, 4>(var, 4, vt); }
+}  // namespace bmc

@@ -1,0 +1,6 @@
+// Kernel instantiations of one model (own translation unit: the models build in parallel).
+#include "bmc_model_vt.cuh"
+
+namespace bmc {
+bool pick_simple_acetate(const std::string& var, ModelVT& vt) { return pick_variant<SimpleAcetate, 4>(var, 3, vt); }
+}  // namespace bmc

@@ -25,6 +25,7 @@
 // without a global scan.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 #include "bmc_models.cuh"
 #include "bmc_rng.cuh"
@@ -106,7 +107,7 @@ struct CycleParams {
   double dt; float dt_f;
   uint32_t step, rank, seed_lo, seed_hi;
   int enable_move, enable_leave, bins_in_smem;
-  int prefetch_ahead;  // tiles of L2 prefetch distance (0 = off)
+  uint32_t stage_offset;  // byte offset of the cp.async staging buffers inside dynamic shared memory
   unsigned long long min_removal; double dead_ratio;  // RuntimeParameters used by the post-cycle plan
 };
 
@@ -130,13 +131,6 @@ __device__ __forceinline__ uint32_t pick4(const uint32_t (&w)[4], unsigned k) {
 // cache-streaming policy (ld/st.global.cs) so the gathered tables (concentrations,
 // leave thresholds, CDF rows, neighbours) stay resident in L1/L2.
 template <int VEC> struct VecIO;
-
-// cp.async.bulk.prefetch.L2: one thread asks the memory system to pull a whole
-// column chunk of the NEXT tile into L2 while the current tile is being computed
-// (SASS: UBLKPF).  Address and size must be multiples of 16 B.
-__device__ __forceinline__ void l2_prefetch_bulk(const void* ptr, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
-}
 template <> struct VecIO<4> {
   static __device__ __forceinline__ void ldf(const float* p, float (&v)[4]) {
     const float4 t = BMC_LD(reinterpret_cast<const float4*>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -148,6 +142,12 @@ template <> struct VecIO<4> {
     const uint4 t = BMC_LD(reinterpret_cast<const uint4*>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
   static __device__ __forceinline__ uint32_t ldb(const uint8_t* p) { return BMC_LD(reinterpret_cast<const unsigned int*>(p)); }
+  static __device__ __forceinline__ void ldf_plain(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void ldu_plain(const uint32_t* p, uint32_t (&v)[4]) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
 };
 template <> struct VecIO<2> {
   static __device__ __forceinline__ void ldf(const float* p, float (&v)[2]) {
@@ -158,13 +158,22 @@ template <> struct VecIO<2> {
     const uint2 t = BMC_LD(reinterpret_cast<const uint2*>(p)); v[0] = t.x; v[1] = t.y;
   }
   static __device__ __forceinline__ uint32_t ldb(const uint8_t* p) { return BMC_LD(reinterpret_cast<const unsigned short*>(p)); }
+  static __device__ __forceinline__ void ldf_plain(const float* p, float (&v)[2]) {
+    const float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y;
+  }
+  static __device__ __forceinline__ void ldu_plain(const uint32_t* p, uint32_t (&v)[2]) {
+    const uint2 t = *reinterpret_cast<const uint2*>(p); v[0] = t.x; v[1] = t.y;
+  }
 };
 template <> struct VecIO<1> {
   static __device__ __forceinline__ void ldf(const float* p, float (&v)[1]) { v[0] = BMC_LD(p); }
   static __device__ __forceinline__ void stf(float* p, const float (&v)[1]) { BMC_ST(p, v[0]); }
   static __device__ __forceinline__ void ldu(const uint32_t* p, uint32_t (&v)[1]) { v[0] = BMC_LD(p); }
   static __device__ __forceinline__ uint32_t ldb(const uint8_t* p) { return BMC_LD(p); }
+  static __device__ __forceinline__ void ldf_plain(const float* p, float (&v)[1]) { v[0] = *p; }
+  static __device__ __forceinline__ void ldu_plain(const uint32_t* p, uint32_t (&v)[1]) { v[0] = *p; }
 };
+
 
 // -----------------------------------------------------------------------------
 // pre_step: everything that must happen before the particle pass, in one launch:
@@ -266,11 +275,29 @@ __device__ __forceinline__ void make_plan(DevState* st, unsigned long long min_r
 // chains interleave; everything rare (division, the neighbour pick of a mover,
 // the outlet exit draw, partially idle groups) sits behind warp-level votes.
 // -----------------------------------------------------------------------------
-template <class M, int VEC, int MINB>
+__host__ __device__ constexpr int popcount_c(uint32_t x) { return x == 0u ? 0 : (int)(x & 1u) + popcount_c(x >> 1); }
+// columns actually loaded per slot: every property that is not write-only
+template <class M> struct ReadCols {
+  static constexpr uint32_t all = M::n_var >= 32 ? 0xffffffffu : ((1u << M::n_var) - 1u);
+  static constexpr int value = M::n_var - popcount_c(M::write_only_mask & all);
+};
+// bytes of one staging buffer of the software pipeline: pos, age_div, age_hyd + the read columns
+template <class M, int VEC> struct StageBytes { static constexpr size_t value = (size_t)(3 + ReadCols<M>::value) * kBlock * 4 * VEC; };
+
+template <int BYTES> __device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <class M, int VEC, int MINB, bool PIPE>
 __global__ void __launch_bounds__(kBlock, MINB) cycle_kernel(const __grid_constant__ CycleParams p) {
-  constexpr int NV = M::n_var, NC = M::n_c, NP = M::n_pre, CT = 1 + M::n_pre;
+  constexpr int NV = M::n_var, NC = M::n_c, CT = 1 + M::n_pre;
   constexpr int SUB = kTile / (kBlock * VEC);  // sub-iterations per tile
-  extern __shared__ double s_bins[];           // [n_species * n_comp] when bins_in_smem
+  constexpr int kColStride = kBlock * 4 * VEC;  // bytes between staged columns
+  constexpr size_t kStage = StageBytes<M, VEC>::value;
+  extern __shared__ double s_bins[];           // [n_species * n_comp] when bins_in_smem, then 2 staging buffers
   __shared__ unsigned long long s_cnt[4];      // move, exit, new, overflow
 
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -297,45 +324,88 @@ __global__ void __launch_bounds__(kBlock, MINB) cycle_kernel(const __grid_consta
   const uint32_t outlet0 = p.n_flows > 0 ? p.outlets[0].index : 0xffffffffu;
   const bool outlet0_live = p.n_flows > 0 && p.outlets[0].flow != 0.;
 
-  for (uint32_t tile = t0; tile < t1; ++tile) {
-    if (p.prefetch_ahead && tile + p.prefetch_ahead < t1) {  // optional L2 bulk prefetch of a later tile
-      const size_t nb = (size_t)(tile + p.prefetch_ahead) * kTile;
-      const int col = (int)threadIdx.x;
-      if (col < 4 + NV) {
-        if (col == 0) l2_prefetch_bulk(p.status + nb, kTile);
-        else if (col == 1) l2_prefetch_bulk(p.pos + nb, kTile * 4);
-        else if (col == 2) l2_prefetch_bulk(p.age_div + nb, kTile * 4);
-        else if (col == 3) { if (p.enable_leave) l2_prefetch_bulk(p.age_hyd + nb, kTile * 4); }
-        else if (!((M::write_only_mask >> (col - 4)) & 1u)) l2_prefetch_bulk(p.props + (size_t)(col - 4) * p.cap + nb, kTile * 4);
-      }
-    }
-#pragma unroll 1
-    for (int sub = 0; sub < SUB; ++sub) {
-      const size_t i_raw = (size_t)tile * kTile + ((size_t)sub * (kBlock / 32) + warp) * (32 * VEC) + (size_t)lane * VEC;
-      const bool live = i_raw < n_used;    // false only in the ragged end of the last tile
-      const size_t i0 = live ? i_raw : 0;  // dead lanes shadow slot 0 (loads stay in range, nothing is stored)
+  // PIPE: two-stage software pipeline.  Each thread copies ITS OWN next group of slots
+  // global -> shared with cp.async (LDGSTS: no registers held while the bytes are in flight),
+  // then computes the current group out of shared memory.  A thread only ever reads what it
+  // copied itself, so cp.async.wait_group is the only synchronisation needed.
+  unsigned char* const s_stage = reinterpret_cast<unsigned char*>(s_bins) + p.stage_offset;
+  const uint32_t n_used32 = (uint32_t)n_used;
+  auto slot_base = [&](uint32_t tile, int sub) -> uint32_t {
+    return tile * (uint32_t)kTile + ((uint32_t)sub * (kBlock / 32) + warp) * (32 * VEC) + lane * VEC;
+  };
+  auto issue = [&](uint32_t it, int buf) -> uint32_t {  // returns the status bytes of that group
+    const uint32_t i_raw = slot_base(t0 + it / SUB, (int)(it % SUB));
+    const size_t i0 = i_raw < n_used32 ? i_raw : 0u;
+    unsigned char* dst = s_stage + (size_t)buf * kStage + threadIdx.x * (4 * VEC);
+    cp_async<4 * VEC>(dst, p.pos + i0);
+    cp_async<4 * VEC>(dst + kColStride, p.age_div + i0);
+    if (p.enable_leave) cp_async<4 * VEC>(dst + 2 * kColStride, p.age_hyd + i0);
+    int c = 3;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+      if (!((M::write_only_mask >> k) & 1u)) { cp_async<4 * VEC>(dst + c * kColStride, p.props + (size_t)k * p.cap + i0); ++c; }
+    cp_async_commit();
+    return VecIO<VEC>::ldb(p.status + i0);
+  };
 
-      // ---- front-batched loads (all independent; MLP = 4 + #columns read) ----
+  {
+    // Every tile but the last is entirely below n_used: the body is instantiated twice so that the
+    // common case carries no per-slot range checks (FULL), the ragged tail keeps them.
+    auto body = [&](auto full_tag, const uint32_t tile, const int sub, const int buf, const uint32_t stw_in) {
+      constexpr bool FULL = decltype(full_tag)::value;
+      const uint32_t i_raw = slot_base(tile, sub);
+      const bool live = FULL || i_raw < n_used32;  // false only in the ragged end of the last tile
+      const size_t i0 = live ? i_raw : 0u;         // dead lanes shadow slot 0 (loads stay in range, nothing is stored)
+
       uint32_t pos[VEC]; float adiv[VEC], ahyd[VEC]; float v[VEC][NV], old[VEC][NV];
-      const uint32_t stw = VecIO<VEC>::ldb(p.status + i0);
-      VecIO<VEC>::ldu(p.pos + i0, pos);
-      VecIO<VEC>::ldf(p.age_div + i0, adiv);
-      if (p.enable_leave) VecIO<VEC>::ldf(p.age_hyd + i0, ahyd);
-      else {
+      uint32_t stw;
+      if constexpr (PIPE) {
+        // ---- operands were staged in shared memory by this thread one iteration ago ----
+        const unsigned char* src = s_stage + (size_t)buf * kStage + threadIdx.x * (4 * VEC);
+        stw = stw_in;
+        VecIO<VEC>::ldu_plain(reinterpret_cast<const uint32_t*>(src), pos);
+        VecIO<VEC>::ldf_plain(reinterpret_cast<const float*>(src + kColStride), adiv);
+        if (p.enable_leave) VecIO<VEC>::ldf_plain(reinterpret_cast<const float*>(src + 2 * kColStride), ahyd);
+        else {
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) ahyd[q] = 0.f;
-      }
+          for (int q = 0; q < VEC; ++q) ahyd[q] = 0.f;
+        }
+        int c = 3;
 #pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        float col[VEC];
-        if ((M::write_only_mask >> k) & 1u) {
+        for (int k = 0; k < NV; ++k) {
+          float col[VEC];
+          if ((M::write_only_mask >> k) & 1u) {
 #pragma unroll
-          for (int q = 0; q < VEC; ++q) col[q] = 0.f;
-        } else {
-          VecIO<VEC>::ldf(p.props + (size_t)k * p.cap + i0, col);
+            for (int q = 0; q < VEC; ++q) col[q] = 0.f;
+          } else {
+            VecIO<VEC>::ldf_plain(reinterpret_cast<const float*>(src + c * kColStride), col);
+            ++c;
+          }
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) { v[q][k] = col[q]; old[q][k] = col[q]; }
+        }
+      } else {
+        // ---- front-batched global loads (all independent; MLP = 4 + #columns read) ----
+        stw = VecIO<VEC>::ldb(p.status + i0);
+        VecIO<VEC>::ldu(p.pos + i0, pos);
+        VecIO<VEC>::ldf(p.age_div + i0, adiv);
+        if (p.enable_leave) VecIO<VEC>::ldf(p.age_hyd + i0, ahyd);
+        else {
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) ahyd[q] = 0.f;
         }
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) { v[q][k] = col[q]; old[q][k] = col[q]; }
+        for (int k = 0; k < NV; ++k) {
+          float col[VEC];
+          if ((M::write_only_mask >> k) & 1u) {
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) col[q] = 0.f;
+          } else {
+            VecIO<VEC>::ldf(p.props + (size_t)k * p.cap + i0, col);
+          }
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) { v[q][k] = col[q]; old[q][k] = col[q]; }
+        }
       }
       uint32_t pos_old[VEC]; float adiv_old[VEC], ahyd_old[VEC];
       bool idle[VEC];
@@ -343,10 +413,10 @@ __global__ void __launch_bounds__(kBlock, MINB) cycle_kernel(const __grid_consta
 #pragma unroll
       for (int q = 0; q < VEC; ++q) {
         pos_old[q] = pos[q]; adiv_old[q] = adiv[q]; ahyd_old[q] = ahyd[q];
-        const bool valid = live && (i0 + q) < n_used;
+        const bool valid = FULL || (live && (i0 + q) < n_used);
         idle[q] = valid && (((stw >> (8 * q)) & 0xffu) == (unsigned)Idle);
         valid_m |= (unsigned)valid << q; idle_m |= (unsigned)idle[q] << q;
-        if (!valid) pos[q] = 0;  // slots past n_used hold unspecified bytes: keep the gathers in range
+        if (!FULL && !valid) pos[q] = 0;  // slots past n_used hold unspecified bytes: keep the gathers in range
       }
       constexpr unsigned kAll = (1u << VEC) - 1u;
 
@@ -553,6 +623,30 @@ __global__ void __launch_bounds__(kBlock, MINB) cycle_kernel(const __grid_consta
 #pragma unroll
         for (int q = 0; q < VEC; ++q) if ((exit_nib >> q) & 1u) p.status[i0 + q] = (uint8_t)Exit;
       }
+    };
+    if constexpr (PIPE) {
+      const uint32_t n_it = (t1 - t0) * SUB;
+      uint32_t stw_next = n_it ? issue(0, 0) : 0u;
+#pragma unroll 1
+      for (uint32_t it = 0; it < n_it; ++it) {
+        const uint32_t stw_cur = stw_next;
+        if (it + 1 < n_it) { stw_next = issue(it + 1, (int)((it + 1) & 1u)); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        const uint32_t tile = t0 + it / SUB;
+        if ((unsigned long long)(tile + 1) * kTile <= n_used) body(std::true_type{}, tile, (int)(it % SUB), (int)(it & 1u), stw_cur);
+        else body(std::false_type{}, tile, (int)(it % SUB), (int)(it & 1u), stw_cur);
+      }
+    } else {
+#pragma unroll 1
+      for (uint32_t tile = t0; tile < t1; ++tile) {
+        if ((unsigned long long)(tile + 1) * kTile <= n_used) {
+#pragma unroll 1
+          for (int sub = 0; sub < SUB; ++sub) body(std::true_type{}, tile, sub, 0, 0u);
+        } else {
+#pragma unroll 1
+          for (int sub = 0; sub < SUB; ++sub) body(std::false_type{}, tile, sub, 0, 0u);
+        }
+      }
     }
   }
 
@@ -616,234 +710,6 @@ __global__ void __launch_bounds__(kBlock, MINB) cycle_kernel(const __grid_consta
   }
 }
 
-// plan without a particle pass (ParticlesContainer::force_remove_dead path)
-__global__ void plan_kernel(DevState* st, unsigned long long min_removal, double dead_ratio) {
-  if (blockIdx.x || threadIdx.x) return;
-  make_plan(st, min_removal, dead_ratio);
-}
-
-// -----------------------------------------------------------------------------
-// Compaction: remove_inactive_particles + CompactParticlesFunctor
-// (particles_container.hpp:735-796, 292-385), made exact and deterministic
-// (SURVEY Q4): the k-th non-idle slot below new_n (ascending) receives the k-th
-// idle particle of the tail [new_n, old_n) counted from the end — the pairing a
-// serial execution of the reference functor produces.
-//   compact_count : per-tile counts (gaps below new_n, idle in the tail), with
-//                   block-local prefix (contiguous tile ranges)
-//   compact_src   : tail tiles -> src[k] = slot of the k-th idle from the end
-//   compact_move  : low tiles  -> gap with rank k pulls src[k]
-// -----------------------------------------------------------------------------
-struct CompactParams {
-  float* props; size_t cap; int n_var;
-  uint32_t* pos; uint8_t* status; float* age_hyd; float* age_div;
-  DevState* st;
-  uint32_t* tile_gap_off; uint32_t* tile_idle_off; uint32_t* blk_gap; uint32_t* blk_idle;
-  uint32_t* src;
-};
-
-__device__ __forceinline__ void compact_tile_flags(const CompactParams& p, uint32_t tile, unsigned long long old_n,
-                                                   unsigned long long new_n, unsigned q, bool& gap, bool& tail_idle) {
-  const unsigned long long i = (unsigned long long)tile * kTile + q;
-  gap = false; tail_idle = false;
-  if (i < old_n) {
-    const bool is_idle = p.status[i] == (uint8_t)Idle;
-    if (i < new_n) gap = !is_idle; else tail_idle = is_idle;
-  }
-}
-
-// blocks of 1024 threads: thread q handles slot q of the tile
-__global__ void __launch_bounds__(1024) compact_count_kernel(const __grid_constant__ CompactParams p) {
-  if (!p.st->do_compact) return;
-  __shared__ unsigned s_g[32], s_i[32];
-  const unsigned long long old_n = p.st->cmp_old_n, new_n = p.st->cmp_new_n;
-  const uint32_t n_tiles = p.st->cmp_tiles;
-  const uint32_t t0 = (uint32_t)(((unsigned long long)blockIdx.x * n_tiles) / gridDim.x);
-  const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned run_g = 0, run_i = 0;
-  for (uint32_t tile = t0; tile < t1; ++tile) {
-    bool gap, ti;
-    compact_tile_flags(p, tile, old_n, new_n, threadIdx.x, gap, ti);
-    const unsigned bg = __popc(__ballot_sync(0xffffffffu, gap)), bi = __popc(__ballot_sync(0xffffffffu, ti));
-    if (lane == 0) { s_g[warp] = bg; s_i[warp] = bi; }
-    __syncthreads();
-    unsigned tg = 0, tii = 0;
-    if (warp == 0) {
-      tg = __reduce_add_sync(0xffffffffu, s_g[lane]); tii = __reduce_add_sync(0xffffffffu, s_i[lane]);
-      if (lane == 0) { p.tile_gap_off[tile] = run_g; p.tile_idle_off[tile] = run_i; }
-      run_g += tg; run_i += tii;
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) { p.blk_gap[blockIdx.x] = run_g; p.blk_idle[blockIdx.x] = run_i; }
-}
-
-// exclusive prefix of per-block totals in shared memory (grid <= kMaxGrid): warp 0 scans 32
-// entries per step with shuffles; executed by the whole block
-__device__ __forceinline__ unsigned block_prefix_of(const uint32_t* blk_tot, unsigned nblk, unsigned b, unsigned* s_tmp,
-                                                    unsigned& grand_total) {
-  for (unsigned k = threadIdx.x; k < nblk; k += blockDim.x) s_tmp[k] = __ldcg(blk_tot + k);  // one parallel pass
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const unsigned lane = threadIdx.x;
-    unsigned run = 0;
-    for (unsigned base = 0; base < nblk; base += 32) {
-      const unsigned k = base + lane;
-      const unsigned v = k < nblk ? s_tmp[k] : 0u;
-      unsigned tot;
-      const unsigned ex = warp_excl_scan(v, tot);
-      if (k < nblk) s_tmp[k] = run + ex;
-      run += tot;
-    }
-    if (lane == 0) s_tmp[nblk] = run;
-  }
-  __syncthreads();
-  grand_total = s_tmp[nblk];
-  return s_tmp[b];
-}
-
-__global__ void __launch_bounds__(1024) compact_src_kernel(const __grid_constant__ CompactParams p) {
-  if (!p.st->do_compact) return;
-  __shared__ unsigned s_pref[kMaxGrid + 1];
-  __shared__ unsigned s_w[32];
-  const unsigned long long old_n = p.st->cmp_old_n, new_n = p.st->cmp_new_n;
-  const uint32_t n_tiles = p.st->cmp_tiles;
-  const uint32_t t0 = (uint32_t)(((unsigned long long)blockIdx.x * n_tiles) / gridDim.x);
-  const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
-  unsigned total_idle;
-  const unsigned blk_off = block_prefix_of(p.blk_idle, gridDim.x, blockIdx.x, s_pref, total_idle);
-  if (blockIdx.x == 0 && threadIdx.x == 0) p.st->cmp_total_idle = total_idle;
-  const uint32_t first_tail_tile = (uint32_t)(new_n / kTile);
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (uint32_t tile = (t0 > first_tail_tile ? t0 : first_tail_tile); tile < t1; ++tile) {
-    bool gap, ti;
-    compact_tile_flags(p, tile, old_n, new_n, threadIdx.x, gap, ti);
-    const unsigned bal = __ballot_sync(0xffffffffu, ti);
-    if (lane == 0) s_w[warp] = __popc(bal);
-    __syncthreads();
-    unsigned woff = 0;
-    for (unsigned k = 0; k < warp; ++k) woff += s_w[k];
-    if (ti) {
-      const unsigned asc = blk_off + p.tile_idle_off[tile] + woff + __popc(bal & ((1u << lane) - 1u));
-      p.src[total_idle - 1u - asc] = (uint32_t)((unsigned long long)tile * kTile + threadIdx.x);
-    }
-    __syncthreads();
-  }
-}
-
-__global__ void __launch_bounds__(1024) compact_move_kernel(const __grid_constant__ CompactParams p) {
-  if (!p.st->do_compact) return;
-  __shared__ unsigned s_pref[kMaxGrid + 1];
-  __shared__ unsigned s_w[32];
-  const unsigned long long old_n = p.st->cmp_old_n, new_n = p.st->cmp_new_n;
-  const uint32_t n_tiles = p.st->cmp_tiles;
-  const uint32_t t0 = (uint32_t)(((unsigned long long)blockIdx.x * n_tiles) / gridDim.x);
-  const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
-  unsigned total_gap;
-  const unsigned blk_off = block_prefix_of(p.blk_gap, gridDim.x, blockIdx.x, s_pref, total_gap);
-  const uint32_t last_low_tile = (uint32_t)((new_n + kTile - 1) / kTile);  // exclusive
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (uint32_t tile = t0; tile < t1; ++tile) {
-    const unsigned long long i = (unsigned long long)tile * kTile + threadIdx.x;
-    if (tile < last_low_tile) {
-      bool gap, ti;
-      compact_tile_flags(p, tile, old_n, new_n, threadIdx.x, gap, ti);
-      const unsigned bal = __ballot_sync(0xffffffffu, gap);
-      if (lane == 0) s_w[warp] = __popc(bal);
-      __syncthreads();
-      unsigned woff = 0;
-      for (unsigned k = 0; k < warp; ++k) woff += s_w[k];
-      if (gap) {
-        const unsigned k = blk_off + p.tile_gap_off[tile] + woff + __popc(bal & ((1u << lane) - 1u));
-        if (k >= p.st->cmp_total_idle) {
-          atomicOr(&p.st->error, 2u);  // inactive counter inconsistent with the status column
-        } else {
-          const size_t r = p.src[k];
-          p.status[i] = (uint8_t)Idle;
-          p.pos[i] = p.pos[r];
-          for (int c = 0; c < p.n_var; ++c) p.props[(size_t)c * p.cap + i] = p.props[(size_t)c * p.cap + r];
-          p.age_hyd[i] = p.age_hyd[r];
-          p.age_div[i] = p.age_div[r];
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
-// -----------------------------------------------------------------------------
-// insert: merge_buffer + InsertFunctor (particles_container.hpp:575-599,
-// 403-443).  Newborn of mother i goes to new_n + (number of dividing mothers with
-// a smaller slot index) — the order the reference's buffer has under serial
-// execution.
-// -----------------------------------------------------------------------------
-struct InsertParams {
-  float* props; size_t cap; int n_var;
-  uint32_t* pos; uint8_t* status; float* age_hyd; float* age_div;
-  DevState* st;
-  const float* buf_props; size_t buf_stride; const uint32_t* buf_pos; const uint32_t* buf_mother;
-  uint32_t* div_mask; uint32_t* tile_div; const uint32_t* tile_off; const uint32_t* blk_total;
-  int count_step;  // 1 when called from a cycle, 0 from force_remove_dead
-};
-
-__global__ void __launch_bounds__(256) post_kernel(const __grid_constant__ InsertParams p) {
-  __shared__ unsigned s_pref[kMaxGrid + 1];
-  const unsigned long long n_add = p.st->n_add;
-  const unsigned long long base = p.st->cmp_new_n;
-  const unsigned long long gtid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned long long gstride = (unsigned long long)gridDim.x * blockDim.x;
-  // slots [new_n, old_n) left the container in a compaction: mark them Idle so that appended
-  // newborns never inherit a stale status (the reference relies on zero-initialised storage,
-  // particles_container.hpp:403-443).  Newborn slots below are written Idle as well, so the
-  // two writers agree where they overlap.
-  if (p.st->do_compact) {
-    const unsigned long long old_n = p.st->cmp_old_n;
-    for (unsigned long long i = base + gtid; i < old_n; i += gstride) p.status[i] = (uint8_t)Idle;
-  }
-  if (n_add) {  // uniform across the grid
-    const unsigned G = p.st->cyc_grid;
-    const unsigned T = p.st->cyc_tiles;
-    unsigned total;
-    block_prefix_of(p.blk_total, G, 0, s_pref, total);
-    for (unsigned long long j = gtid; j < n_add; j += gstride) {
-      const uint32_t mother = p.buf_mother[j];
-      const uint32_t tile = mother >> 10;
-      const unsigned b = (unsigned)((((unsigned long long)tile + 1ull) * G - 1ull) / T);  // owner block of the tile
-      const uint32_t* words = p.div_mask + (size_t)tile * (kTile / 32);
-      const unsigned wi = (mother & (kTile - 1)) >> 5, bit = mother & 31u;
-      unsigned rank = 0;
-      for (unsigned k = 0; k < wi; ++k) rank += __popc(words[k]);
-      rank += __popc(words[wi] & ((1u << bit) - 1u));
-      const unsigned long long dst = base + s_pref[b] + p.tile_off[tile] + rank;
-      for (int c = 0; c < p.n_var; ++c) p.props[(size_t)c * p.cap + dst] = p.buf_props[(size_t)c * p.buf_stride + j];
-      p.pos[dst] = p.buf_pos[j];
-      p.age_hyd[dst] = 0.f; p.age_div[dst] = 0.f;  // InsertFunctor: both ages reset
-      p.status[dst] = (uint8_t)Idle;
-    }
-  }
-  // commit (one thread).  Only fields no other thread of this kernel reads are modified.
-  if (gtid == 0) {
-    DevState* st = p.st;
-    if (st->do_compact) { st->inactive -= (st->cmp_old_n - st->cmp_new_n); st->n_compactions += 1; }
-    st->n_used = base + n_add;
-    st->total_new += n_add;
-    if (n_add > st->clear_n) st->clear_n = n_add;  // bits cleared by the next pre_step
-    st->step += (unsigned long long)p.count_step;
-  }
-}
-
-// -----------------------------------------------------------------------------
-// Domain tables: ReactorDomain::update (mc/src/domain.cpp:43-74) -> derived
-// single-precision tables that reproduce the double-precision comparisons
-// bit-exactly for float uniforms:
-//   (dt*flow/volume) > (double)u   <=>  u < ceil_f32(dt*flow/volume)   (compartment_table_kernel)
-//   (double)u > cdf                <=>  u > floor_f32(cdf)
-// -----------------------------------------------------------------------------
-__global__ void derive_cdf_table_kernel(const double* cdf, float* out, size_t n) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __double2float_rd(cdf[i]);
-}
-
 // -----------------------------------------------------------------------------
 // mc_init_first: InitFunctor (mc/src/unit.cpp:102-144): M::init, random
 // compartment, total-mass reduce.
@@ -867,36 +733,6 @@ __global__ void __launch_bounds__(256) init_kernel(float* props, size_t cap, uin
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
   if ((threadIdx.x & 31) == 0 && m != 0.0) atomicAdd(&st->init_mass, m);
-}
-
-// get_repartition: NcellFunctor (mc/src/unit.cpp:48-100, 190-230)
-__global__ void __launch_bounds__(256) repartition_kernel(const uint32_t* pos, const uint8_t* status, const DevState* st,
-                                                          unsigned long long* out) {
-  const unsigned long long n = st->n_used;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (unsigned long long)gridDim.x * blockDim.x)
-    if (status[i] == (uint8_t)Idle) atomicAdd(out + pos[i], 1ull);
-}
-
-// u64 <-> u32 position conversion for the host boundary
-__global__ void pos_narrow_kernel(const unsigned long long* in, uint32_t* out, size_t n, uint32_t n_comp, unsigned int* err) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { const unsigned long long v = in[i]; if (v >= n_comp) atomicOr(err, 1u); out[i] = (uint32_t)v; }
-}
-__global__ void pos_widen_kernel(const uint32_t* in, unsigned long long* out, size_t n) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = in[i];
-}
-__global__ void count_inactive_kernel(const uint8_t* status, size_t n, DevState* st) {
-  unsigned c = 0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    c += status[i] != (uint8_t)Idle;
-  c = __reduce_add_sync(0xffffffffu, c);
-  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&st->inactive, (unsigned long long)c);
-}
-__global__ void fill_u8_kernel(uint8_t* p, size_t n, uint8_t v) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
 }
 
 }  // namespace bmc

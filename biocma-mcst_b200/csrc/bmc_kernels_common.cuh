@@ -1,0 +1,268 @@
+// Non-template kernels of the particle step (compaction, spawn/commit, domain tables,
+// repartition, host-boundary conversions).  Included by bmc_api.cu only; the per-model
+// translation units include bmc_kernels.cuh (template kernels) alone.
+#pragma once
+#include "bmc_kernels.cuh"
+
+namespace bmc {
+
+// plan without a particle pass (ParticlesContainer::force_remove_dead path)
+__global__ void plan_kernel(DevState* st, unsigned long long min_removal, double dead_ratio) {
+  if (blockIdx.x || threadIdx.x) return;
+  make_plan(st, min_removal, dead_ratio);
+}
+
+// -----------------------------------------------------------------------------
+// Compaction: remove_inactive_particles + CompactParticlesFunctor
+// (particles_container.hpp:735-796, 292-385), made exact and deterministic
+// (SURVEY Q4): the k-th non-idle slot below new_n (ascending) receives the k-th
+// idle particle of the tail [new_n, old_n) counted from the end — the pairing a
+// serial execution of the reference functor produces.
+//   compact_count : per-tile counts (gaps below new_n, idle in the tail), with
+//                   block-local prefix (contiguous tile ranges)
+//   compact_src   : tail tiles -> src[k] = slot of the k-th idle from the end
+//   compact_move  : low tiles  -> gap with rank k pulls src[k]
+// -----------------------------------------------------------------------------
+struct CompactParams {
+  float* props; size_t cap; int n_var;
+  uint32_t* pos; uint8_t* status; float* age_hyd; float* age_div;
+  DevState* st;
+  uint32_t* tile_gap_off; uint32_t* tile_idle_off; uint32_t* blk_gap; uint32_t* blk_idle;
+  uint32_t* src;
+};
+
+__device__ __forceinline__ void compact_tile_flags(const CompactParams& p, uint32_t tile, unsigned long long old_n,
+                                                   unsigned long long new_n, unsigned q, bool& gap, bool& tail_idle) {
+  const unsigned long long i = (unsigned long long)tile * kTile + q;
+  gap = false; tail_idle = false;
+  if (i < old_n) {
+    const bool is_idle = p.status[i] == (uint8_t)Idle;
+    if (i < new_n) gap = !is_idle; else tail_idle = is_idle;
+  }
+}
+
+// blocks of 1024 threads: thread q handles slot q of the tile
+__global__ void __launch_bounds__(1024) compact_count_kernel(const __grid_constant__ CompactParams p) {
+  if (!p.st->do_compact) return;
+  __shared__ unsigned s_g[32], s_i[32];
+  const unsigned long long old_n = p.st->cmp_old_n, new_n = p.st->cmp_new_n;
+  const uint32_t n_tiles = p.st->cmp_tiles;
+  const uint32_t t0 = (uint32_t)(((unsigned long long)blockIdx.x * n_tiles) / gridDim.x);
+  const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned run_g = 0, run_i = 0;
+  for (uint32_t tile = t0; tile < t1; ++tile) {
+    bool gap, ti;
+    compact_tile_flags(p, tile, old_n, new_n, threadIdx.x, gap, ti);
+    const unsigned bg = __popc(__ballot_sync(0xffffffffu, gap)), bi = __popc(__ballot_sync(0xffffffffu, ti));
+    if (lane == 0) { s_g[warp] = bg; s_i[warp] = bi; }
+    __syncthreads();
+    unsigned tg = 0, tii = 0;
+    if (warp == 0) {
+      tg = __reduce_add_sync(0xffffffffu, s_g[lane]); tii = __reduce_add_sync(0xffffffffu, s_i[lane]);
+      if (lane == 0) { p.tile_gap_off[tile] = run_g; p.tile_idle_off[tile] = run_i; }
+      run_g += tg; run_i += tii;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { p.blk_gap[blockIdx.x] = run_g; p.blk_idle[blockIdx.x] = run_i; }
+}
+
+// exclusive prefix of per-block totals in shared memory (grid <= kMaxGrid): warp 0 scans 32
+// entries per step with shuffles; executed by the whole block
+__device__ __forceinline__ unsigned block_prefix_of(const uint32_t* blk_tot, unsigned nblk, unsigned b, unsigned* s_tmp,
+                                                    unsigned& grand_total) {
+  for (unsigned k = threadIdx.x; k < nblk; k += blockDim.x) s_tmp[k] = __ldcg(blk_tot + k);  // one parallel pass
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const unsigned lane = threadIdx.x;
+    unsigned run = 0;
+    for (unsigned base = 0; base < nblk; base += 32) {
+      const unsigned k = base + lane;
+      const unsigned v = k < nblk ? s_tmp[k] : 0u;
+      unsigned tot;
+      const unsigned ex = warp_excl_scan(v, tot);
+      if (k < nblk) s_tmp[k] = run + ex;
+      run += tot;
+    }
+    if (lane == 0) s_tmp[nblk] = run;
+  }
+  __syncthreads();
+  grand_total = s_tmp[nblk];
+  return s_tmp[b];
+}
+
+__global__ void __launch_bounds__(1024) compact_src_kernel(const __grid_constant__ CompactParams p) {
+  if (!p.st->do_compact) return;
+  __shared__ unsigned s_pref[kMaxGrid + 1];
+  __shared__ unsigned s_w[32];
+  const unsigned long long old_n = p.st->cmp_old_n, new_n = p.st->cmp_new_n;
+  const uint32_t n_tiles = p.st->cmp_tiles;
+  const uint32_t t0 = (uint32_t)(((unsigned long long)blockIdx.x * n_tiles) / gridDim.x);
+  const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
+  unsigned total_idle;
+  const unsigned blk_off = block_prefix_of(p.blk_idle, gridDim.x, blockIdx.x, s_pref, total_idle);
+  if (blockIdx.x == 0 && threadIdx.x == 0) p.st->cmp_total_idle = total_idle;
+  const uint32_t first_tail_tile = (uint32_t)(new_n / kTile);
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t tile = (t0 > first_tail_tile ? t0 : first_tail_tile); tile < t1; ++tile) {
+    bool gap, ti;
+    compact_tile_flags(p, tile, old_n, new_n, threadIdx.x, gap, ti);
+    const unsigned bal = __ballot_sync(0xffffffffu, ti);
+    if (lane == 0) s_w[warp] = __popc(bal);
+    __syncthreads();
+    unsigned woff = 0;
+    for (unsigned k = 0; k < warp; ++k) woff += s_w[k];
+    if (ti) {
+      const unsigned asc = blk_off + p.tile_idle_off[tile] + woff + __popc(bal & ((1u << lane) - 1u));
+      p.src[total_idle - 1u - asc] = (uint32_t)((unsigned long long)tile * kTile + threadIdx.x);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(1024) compact_move_kernel(const __grid_constant__ CompactParams p) {
+  if (!p.st->do_compact) return;
+  __shared__ unsigned s_pref[kMaxGrid + 1];
+  __shared__ unsigned s_w[32];
+  const unsigned long long old_n = p.st->cmp_old_n, new_n = p.st->cmp_new_n;
+  const uint32_t n_tiles = p.st->cmp_tiles;
+  const uint32_t t0 = (uint32_t)(((unsigned long long)blockIdx.x * n_tiles) / gridDim.x);
+  const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
+  unsigned total_gap;
+  const unsigned blk_off = block_prefix_of(p.blk_gap, gridDim.x, blockIdx.x, s_pref, total_gap);
+  const uint32_t last_low_tile = (uint32_t)((new_n + kTile - 1) / kTile);  // exclusive
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t tile = t0; tile < t1; ++tile) {
+    const unsigned long long i = (unsigned long long)tile * kTile + threadIdx.x;
+    if (tile < last_low_tile) {
+      bool gap, ti;
+      compact_tile_flags(p, tile, old_n, new_n, threadIdx.x, gap, ti);
+      const unsigned bal = __ballot_sync(0xffffffffu, gap);
+      if (lane == 0) s_w[warp] = __popc(bal);
+      __syncthreads();
+      unsigned woff = 0;
+      for (unsigned k = 0; k < warp; ++k) woff += s_w[k];
+      if (gap) {
+        const unsigned k = blk_off + p.tile_gap_off[tile] + woff + __popc(bal & ((1u << lane) - 1u));
+        if (k >= p.st->cmp_total_idle) {
+          atomicOr(&p.st->error, 2u);  // inactive counter inconsistent with the status column
+        } else {
+          const size_t r = p.src[k];
+          p.status[i] = (uint8_t)Idle;
+          p.pos[i] = p.pos[r];
+          for (int c = 0; c < p.n_var; ++c) p.props[(size_t)c * p.cap + i] = p.props[(size_t)c * p.cap + r];
+          p.age_hyd[i] = p.age_hyd[r];
+          p.age_div[i] = p.age_div[r];
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// -----------------------------------------------------------------------------
+// insert: merge_buffer + InsertFunctor (particles_container.hpp:575-599,
+// 403-443).  Newborn of mother i goes to new_n + (number of dividing mothers with
+// a smaller slot index) — the order the reference's buffer has under serial
+// execution.
+// -----------------------------------------------------------------------------
+struct InsertParams {
+  float* props; size_t cap; int n_var;
+  uint32_t* pos; uint8_t* status; float* age_hyd; float* age_div;
+  DevState* st;
+  const float* buf_props; size_t buf_stride; const uint32_t* buf_pos; const uint32_t* buf_mother;
+  uint32_t* div_mask; uint32_t* tile_div; const uint32_t* tile_off; const uint32_t* blk_total;
+  int count_step;  // 1 when called from a cycle, 0 from force_remove_dead
+};
+
+__global__ void __launch_bounds__(256) post_kernel(const __grid_constant__ InsertParams p) {
+  __shared__ unsigned s_pref[kMaxGrid + 1];
+  const unsigned long long n_add = p.st->n_add;
+  const unsigned long long base = p.st->cmp_new_n;
+  const unsigned long long gtid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long gstride = (unsigned long long)gridDim.x * blockDim.x;
+  // slots [new_n, old_n) left the container in a compaction: mark them Idle so that appended
+  // newborns never inherit a stale status (the reference relies on zero-initialised storage,
+  // particles_container.hpp:403-443).  Newborn slots below are written Idle as well, so the
+  // two writers agree where they overlap.
+  if (p.st->do_compact) {
+    const unsigned long long old_n = p.st->cmp_old_n;
+    for (unsigned long long i = base + gtid; i < old_n; i += gstride) p.status[i] = (uint8_t)Idle;
+  }
+  if (n_add) {  // uniform across the grid
+    const unsigned G = p.st->cyc_grid;
+    const unsigned T = p.st->cyc_tiles;
+    unsigned total;
+    block_prefix_of(p.blk_total, G, 0, s_pref, total);
+    for (unsigned long long j = gtid; j < n_add; j += gstride) {
+      const uint32_t mother = p.buf_mother[j];
+      const uint32_t tile = mother >> 10;
+      const unsigned b = (unsigned)((((unsigned long long)tile + 1ull) * G - 1ull) / T);  // owner block of the tile
+      const uint32_t* words = p.div_mask + (size_t)tile * (kTile / 32);
+      const unsigned wi = (mother & (kTile - 1)) >> 5, bit = mother & 31u;
+      unsigned rank = 0;
+      for (unsigned k = 0; k < wi; ++k) rank += __popc(words[k]);
+      rank += __popc(words[wi] & ((1u << bit) - 1u));
+      const unsigned long long dst = base + s_pref[b] + p.tile_off[tile] + rank;
+      for (int c = 0; c < p.n_var; ++c) p.props[(size_t)c * p.cap + dst] = p.buf_props[(size_t)c * p.buf_stride + j];
+      p.pos[dst] = p.buf_pos[j];
+      p.age_hyd[dst] = 0.f; p.age_div[dst] = 0.f;  // InsertFunctor: both ages reset
+      p.status[dst] = (uint8_t)Idle;
+    }
+  }
+  // commit (one thread).  Only fields no other thread of this kernel reads are modified.
+  if (gtid == 0) {
+    DevState* st = p.st;
+    if (st->do_compact) { st->inactive -= (st->cmp_old_n - st->cmp_new_n); st->n_compactions += 1; }
+    st->n_used = base + n_add;
+    st->total_new += n_add;
+    if (n_add > st->clear_n) st->clear_n = n_add;  // bits cleared by the next pre_step
+    st->step += (unsigned long long)p.count_step;
+  }
+}
+
+// -----------------------------------------------------------------------------
+// Domain tables: ReactorDomain::update (mc/src/domain.cpp:43-74) -> derived
+// single-precision tables that reproduce the double-precision comparisons
+// bit-exactly for float uniforms:
+//   (dt*flow/volume) > (double)u   <=>  u < ceil_f32(dt*flow/volume)   (compartment_table_kernel)
+//   (double)u > cdf                <=>  u > floor_f32(cdf)
+// -----------------------------------------------------------------------------
+__global__ void derive_cdf_table_kernel(const double* cdf, float* out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __double2float_rd(cdf[i]);
+}
+
+// get_repartition: NcellFunctor (mc/src/unit.cpp:48-100, 190-230)
+__global__ void __launch_bounds__(256) repartition_kernel(const uint32_t* pos, const uint8_t* status, const DevState* st,
+                                                          unsigned long long* out) {
+  const unsigned long long n = st->n_used;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x)
+    if (status[i] == (uint8_t)Idle) atomicAdd(out + pos[i], 1ull);
+}
+
+// u64 <-> u32 position conversion for the host boundary
+__global__ void pos_narrow_kernel(const unsigned long long* in, uint32_t* out, size_t n, uint32_t n_comp, unsigned int* err) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const unsigned long long v = in[i]; if (v >= n_comp) atomicOr(err, 1u); out[i] = (uint32_t)v; }
+}
+__global__ void pos_widen_kernel(const uint32_t* in, unsigned long long* out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+__global__ void count_inactive_kernel(const uint8_t* status, size_t n, DevState* st) {
+  unsigned c = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    c += status[i] != (uint8_t)Idle;
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&st->inactive, (unsigned long long)c);
+}
+__global__ void fill_u8_kernel(uint8_t* p, size_t n, uint8_t v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+
+}  // namespace bmc

@@ -187,3 +187,51 @@ def test_device_init_matches_oracle_deterministic_model(bmc, orc, synth):
     assert abs(mg - mo) <= 1e-12 * abs(mo)
     util.assert_state_equal(g.get_particles(n), o.get_particles(n), n)
     assert len(np.unique(g.get_particles(n)["position"])) == nc
+
+
+# ---------------------------------------------------------------------------------------------
+# Stochastic mode (north_star): agreement in distribution — two-sample KS on property histograms,
+# occupancy and event counts within a stated tolerance.  simple_acetate's division draws
+# LogNormal/TruncatedNormal variates through exp/log/erfc, which differ in the last bit between
+# CUDA and glibc, so trajectories are not bit-comparable once cells have divided.
+# ---------------------------------------------------------------------------------------------
+KS_P_MIN = 1e-3        # reject only on strong evidence
+COUNT_RTOL = 0.01      # event counts / occupancy within 1 %
+
+
+def test_simple_acetate_division_in_distribution(bmc, orc, synth):
+    from scipy.stats import ks_2samp
+    case = util.make_case(synth, "simple_acetate", 200_000, 100, dt=30.0, near_division=0.6, p_move=0.2, p_exit=0.2)
+    g, o = _pair(bmc, orc, case)
+    util.load_case(g, case); util.load_case(o, case)
+    util.run_steps(g, case, 25); util.run_steps(o, case, 25)
+    cg, co = g.counters(), o.counters()
+    assert co["total_new"] > 20_000
+    for k in ("total_new", "total_out", "n_used"):
+        assert abs(cg[k] - co[k]) <= COUNT_RTOL * co[k] + 30, (k, cg[k], co[k])
+    assert abs(cg["events"]["Move"] - co["events"]["Move"]) <= COUNT_RTOL * co["events"]["Move"]
+    pg, po = g.get_particles(), o.get_particles()
+    ig, io = pg["status"] == 0, po["status"] == 0
+    for col, name in ((0, "length"), (1, "l_max"), (2, "a_p"), (4, "a_e")):
+        r = ks_2samp(pg["props"][col][ig].astype(np.float64), po["props"][col][io].astype(np.float64))
+        assert r.pvalue > KS_P_MIN, (name, r)
+    occ_g, occ_o = g.repartition().astype(np.float64), o.repartition().astype(np.float64)
+    assert np.max(np.abs(occ_g - occ_o)) <= 6 * np.sqrt(occ_o.max())  # compartment occupancy
+    sg, so = g.get_sources(), o.get_sources()
+    assert abs(sg.sum() - so.sum()) <= 0.01 * abs(so.sum())            # total uptake within 1 %
+
+
+def test_monod_device_init_in_distribution(bmc, orc):
+    from scipy.stats import ks_2samp, chisquare
+    n, nc = 400_000, 200
+    g = bmc.ParticleLoop("monod", 1, nc, seed=5)
+    o = orc.OracleLoop("monod", 1, nc, seed=5)
+    mg = g.init_particles(n, True); mo = o.init_particles(n, True)
+    assert abs(mg - mo) <= 1e-4 * mo                     # total mass (TruncatedNormal lengths)
+    pg, po = g.get_particles(n), o.get_particles(n)
+    assert ks_2samp(pg["props"][0].astype(np.float64), po["props"][0].astype(np.float64)).pvalue > KS_P_MIN
+    lo, hi = np.float32(1e-6), np.float32(2e-6)
+    assert pg["props"][0].min() > lo * 0.98 and pg["props"][0].max() < hi * 1.02
+    assert np.all(pg["props"][1] == np.float32(2e-6)) and np.all(pg["props"][2] == np.float32(0.77 / 3600.0))
+    assert np.array_equal(pg["position"], po["position"])  # urand64 from the same Philox words: exact
+    assert chisquare(np.bincount(pg["position"].astype(np.int64), minlength=nc)).pvalue > 1e-4

@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 libs = os.environ.get("SWEEP_LIBS", "libbmc_b200.so").split(",")
 variants = os.environ.get("SWEEP_VARIANTS", "v4b1").split(",")
-prefetch = os.environ.get("SWEEP_PREFETCH", "1").split(",")
+prefetch = os.environ.get("SWEEP_PREFETCH", "0").split(",")
 extra = sys.argv[1:]
 for lib, var, pf in itertools.product(libs, variants, prefetch):
     env = dict(os.environ, BMC_LIB=os.path.join(ROOT, "biocma-mcst_b200", lib), BMC_VARIANT=var, BMC_PREFETCH=pf)
