@@ -77,7 +77,30 @@ def build(force=False, verbose=False, defines=(), out=None):
     return out
 
 
+def build_host(force=False):
+    """C++ host layer (biocma-mcst_b200/host): CLI driver and the container test, g++ -std=c++17,
+    linked against libbmc_b200.so with an rpath to this directory."""
+    host = os.path.join(HERE, "host")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    outs = []
+    for src, exe in (("biocma_b200_cli.cpp", "biocma_b200"), ("test_container.cpp", "test_container")):
+        out = os.path.join(host, exe)
+        srcp = os.path.join(host, src)
+        hdr = os.path.join(host, "bmc_host.hpp")
+        if force or not os.path.exists(out) or max(os.path.getmtime(srcp), os.path.getmtime(hdr), os.path.getmtime(OUT)) > os.path.getmtime(out):
+            r = subprocess.run([cxx, "-std=c++17", "-O2", "-Wall", "-o", out, srcp, "-L" + HERE, "-lbmc_b200",
+                                "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/..", "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"],
+                               capture_output=True, text=True)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError(f"g++ failed on {src}")
+        outs.append(out)
+    return outs
+
+
 if __name__ == "__main__":
     defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
     outs = [a[2:] for a in sys.argv[1:] if a.startswith("-o")]
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))
+    if not outs:
+        print(build_host(force="--force" in sys.argv))

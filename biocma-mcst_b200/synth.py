@@ -143,3 +143,15 @@ def initial_weight(props, x0, v_total, lin_density=None):
         lin_density = np.float32(1000.0) * np.float32(np.pi) * np.float32(0.6e-6) * np.float32(0.6e-6) / np.float32(4.0)
     m_tot = float(np.sum(props[0].astype(np.float64) * float(lin_density)))
     return x0 * v_total / m_tot
+
+
+def write_case(directory, fm):
+    """Flat little-endian arrays in the layout the C++ host layer reads (CmaUtils::FlowMap::load)."""
+    import os
+    os.makedirs(directory, exist_ok=True)
+    rows, cols, vals = fm["coo"]
+    for name, arr, dt in (("volumes", fm["volumes"], np.float64), ("out_flows", fm["out_flows"], np.float64),
+                          ("neighbors", fm["neighbors"], np.uint64), ("proba", fm["cdf"], np.float64),
+                          ("transition_rows", rows, np.uint64), ("transition_cols", cols, np.uint64),
+                          ("transition_vals", vals, np.float64)):
+        np.ascontiguousarray(arr, dt).tofile(os.path.join(directory, name + ".raw"))
