@@ -30,6 +30,7 @@ ABI_SYMBOLS = (
     "bmc_get_sources", "bmc_cycle", "bmc_sync", "bmc_get_counters", "bmc_repartition", "bmc_compact", "bmc_reserve",
     "bmc_sources_device", "bmc_concentrations_device", "bmc_stream", "bmc_launch_count", "bmc_profile_enable",
     "bmc_profile_read", "bmc_nccl_unique_id", "bmc_comm_init", "bmc_allreduce_sources",
+    "bmc_liquid_set_transition", "bmc_liquid_set_feeds", "bmc_liquid_step", "bmc_get_concentrations",
 )
 
 
@@ -46,6 +47,12 @@ class BmcConfig(ctypes.Structure):
 
 class BmcLeavingFlow(ctypes.Structure):
     _fields_ = [("index", ctypes.c_uint64), ("flow", ctypes.c_double), ("volume", ctypes.c_double)]
+
+
+class BmcFeed(ctypes.Structure):
+    _fields_ = [("species", ctypes.c_uint64), ("input_position", ctypes.c_uint64), ("flow", ctypes.c_double),
+                ("concentration", ctypes.c_double), ("output_position", ctypes.c_uint64), ("has_output", ctypes.c_int32),
+                ("first_of_feed", ctypes.c_int32)]
 
 
 class BmcCounters(ctypes.Structure):
@@ -108,6 +115,10 @@ def load_library(path=None):
     lib.bmc_nccl_unique_id.argtypes = [vp]
     lib.bmc_comm_init.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
     lib.bmc_allreduce_sources.argtypes = [vp]
+    lib.bmc_liquid_set_transition.argtypes = [vp, u64, vp, vp, vp]
+    lib.bmc_liquid_set_feeds.argtypes = [vp, u64, P(BmcFeed)]
+    lib.bmc_liquid_step.argtypes = [vp, dbl]
+    lib.bmc_get_concentrations.argtypes = [vp, vp]
     for name in ABI_SYMBOLS:
         if name != "bmc_last_error":
             getattr(lib, name).restype = ctypes.c_int
@@ -223,6 +234,30 @@ class ParticleLoop:
     def get_sources(self):
         out = np.empty(self.n_species * self.n_compartments, np.float64)
         self._ck(self.lib.bmc_get_sources(self.h, _ptr(out)))
+        return out
+
+    # ---- liquid phase on the device ---------------------------------------------
+    def liquid_set_transition(self, coo):
+        rows = np.ascontiguousarray(coo[0], np.uint64); cols = np.ascontiguousarray(coo[1], np.uint64)
+        vals = np.ascontiguousarray(coo[2], np.float64)
+        self._ck(self.lib.bmc_liquid_set_transition(self.h, vals.size, _ptr(rows), _ptr(cols), _ptr(vals)))
+
+    def liquid_set_feeds(self, feeds):
+        """feeds: iterable of dicts(species, input_position, flow, concentration, output_position=None)"""
+        feeds = list(feeds)
+        arr = (BmcFeed * max(1, len(feeds)))()
+        for i, f in enumerate(feeds):
+            out = f.get("output_position")
+            arr[i] = BmcFeed(int(f.get("species", 0)), int(f["input_position"]), float(f["flow"]), float(f["concentration"]),
+                             0 if out is None else int(out), 0 if out is None else 1, int(f.get("first_of_feed", 1)))
+        self._ck(self.lib.bmc_liquid_set_feeds(self.h, len(feeds), arr))
+
+    def liquid_step(self, d_t):
+        self._ck(self.lib.bmc_liquid_step(self.h, float(d_t)))
+
+    def get_concentrations(self):
+        out = np.empty(self.n_species * self.n_compartments, np.float64)
+        self._ck(self.lib.bmc_get_concentrations(self.h, _ptr(out)))
         return out
 
     # ---- hot path ------------------------------------------------------------

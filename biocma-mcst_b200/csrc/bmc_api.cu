@@ -60,6 +60,9 @@ struct bmc_ctx {
   std::vector<bmc_leaving_flow> flows;
   // liquid
   double *d_conc = nullptr, *d_sources = nullptr;
+  double *d_conc_next = nullptr, *d_mass = nullptr; bool mass_dirty = true;
+  uint32_t *d_csc_ptr = nullptr, *d_csc_row = nullptr; double* d_csc_val = nullptr; bool transition_set = false;
+  std::vector<bmc_feed> feeds; std::vector<double> h_vol;
   float weight = 1.0f;
   // state
   DevState* st = nullptr;
@@ -278,11 +281,14 @@ int bmc_create(bmc_ctx** out, const bmc_config* cfg) {
   const size_t nb = ctx->n_species * ctx->n_comp;
   int rc;
   if ((rc = dev_alloc(ctx, &ctx->d_conc, nb)) || (rc = dev_alloc(ctx, &ctx->d_sources, nb)) ||
+      (rc = dev_alloc(ctx, &ctx->d_conc_next, nb)) || (rc = dev_alloc(ctx, &ctx->d_mass, nb)) || (rc = dev_alloc(ctx, &ctx->d_csc_ptr, ctx->n_comp + 1)) ||
       (rc = dev_alloc(ctx, &ctx->d_vol, ctx->n_comp)) || (rc = dev_alloc(ctx, &ctx->d_diag, ctx->n_comp)) ||
       (rc = dev_alloc(ctx, &ctx->d_ctab, ctx->n_comp * (size_t)ctx->vt.ct)) || (rc = dev_alloc(ctx, &ctx->blk_total, kMaxGrid + 1)) ||
       (rc = dev_alloc(ctx, &ctx->blk_gap, kMaxGrid + 1)) || (rc = dev_alloc(ctx, &ctx->blk_idle, kMaxGrid + 1)))
     return fail(rc);
   cudaMemset(ctx->d_conc, 0, nb * 8); cudaMemset(ctx->d_sources, 0, nb * 8);
+  cudaMemset(ctx->d_mass, 0, nb * 8); cudaMemset(ctx->d_csc_ptr, 0, (ctx->n_comp + 1) * 4);
+  ctx->h_vol.assign(ctx->n_comp, 1.0);
   cudaMemset(ctx->d_ctab, 0, ctx->n_comp * (size_t)ctx->vt.ct * 4);
   cudaMemset(ctx->d_vol, 0, ctx->n_comp * 8); cudaMemset(ctx->d_diag, 0, ctx->n_comp * 8);
   cudaMemset(ctx->blk_total, 0, (kMaxGrid + 1) * 4);
@@ -299,7 +305,9 @@ int bmc_destroy(bmc_ctx** h) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->nccl_comm && g_nccl_destroy) g_nccl_destroy(c->nccl_comm);
   free_container(c);
-  dev_free(c->d_conc); dev_free(c->d_sources); dev_free(c->d_vol); dev_free(c->d_diag); dev_free(c->d_cdf);
+  dev_free(c->d_conc); dev_free(c->d_sources); dev_free(c->d_conc_next); dev_free(c->d_mass);
+  dev_free(c->d_csc_ptr); dev_free(c->d_csc_row); dev_free(c->d_csc_val);
+  dev_free(c->d_vol); dev_free(c->d_diag); dev_free(c->d_cdf);
   dev_free(c->d_ctab); dev_free(c->d_cdf_f); dev_free(c->d_neigh);
   dev_free(c->blk_total); dev_free(c->blk_gap); dev_free(c->blk_idle);
   dev_free(c->st);
@@ -448,6 +456,7 @@ int bmc_domain_update(bmc_ctx* ctx, const double* volumes, const uint64_t* neigh
   CK(cudaStreamSynchronize(s));  // tables may be in use by enqueued cycles
   const size_t nc = ctx->n_comp, nn = nc * n_cols;
   CK(cudaMemcpyAsync(ctx->d_vol, volumes, nc * 8, cudaMemcpyHostToDevice, s));
+  ctx->h_vol.assign(volumes, volumes + nc);
   CK(cudaMemcpyAsync(ctx->d_diag, out_flows, nc * 8, cudaMemcpyHostToDevice, s));
   if (nn) {
     std::vector<uint32_t> nb(nn);
@@ -487,6 +496,85 @@ int bmc_set_concentrations(bmc_ctx* ctx, const double* c) {
   // pageable source: the runtime stages the bytes before returning, so the caller's
   // buffer is free on return; ordering with enqueued cycles is by stream order.
   CK(cudaMemcpyAsync(ctx->d_conc, c, ctx->n_species * ctx->n_comp * 8, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->mass_dirty = true;  // total_mass = C * V is rebuilt by the next bmc_liquid_step
+  return BMC_OK;
+}
+
+int bmc_get_concentrations(bmc_ctx* ctx, double* out) {
+  if (!ctx || !out) return BMC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(out, ctx->d_conc, ctx->n_species * ctx->n_comp * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return BMC_OK;
+}
+
+int bmc_liquid_set_transition(bmc_ctx* ctx, uint64_t nnz, const uint64_t* rows, const uint64_t* cols, const double* vals) {
+  if (!ctx || (nnz && (!rows || !cols || !vals))) return BMC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  const size_t nc = ctx->n_comp;
+  std::vector<uint32_t> ptr(nc + 1, 0), row(nnz);
+  std::vector<double> val(nnz);
+  for (uint64_t e = 0; e < nnz; ++e) {
+    if (rows[e] >= nc || cols[e] >= nc) { ctx->err = "transition index out of range"; return BMC_ERR_RANGE; }
+    ptr[cols[e] + 1]++;
+  }
+  for (size_t j = 0; j < nc; ++j) ptr[j + 1] += ptr[j];
+  std::vector<uint32_t> fill(ptr.begin(), ptr.end() - 1);
+  for (uint64_t e = 0; e < nnz; ++e) { const uint32_t d = fill[cols[e]]++; row[d] = (uint32_t)rows[e]; val[d] = vals[e]; }  // stable: COO order kept per column
+  CK(cudaStreamSynchronize(ctx->stream));
+  dev_free(ctx->d_csc_row); dev_free(ctx->d_csc_val);
+  int rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_csc_row, nnz)) || (rc = dev_alloc(ctx, &ctx->d_csc_val, nnz))) return rc;
+  CK(cudaMemcpy(ctx->d_csc_ptr, ptr.data(), (nc + 1) * 4, cudaMemcpyHostToDevice));
+  if (nnz) {
+    CK(cudaMemcpy(ctx->d_csc_row, row.data(), nnz * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_csc_val, val.data(), nnz * 8, cudaMemcpyHostToDevice));
+  }
+  ctx->transition_set = true;
+  return BMC_OK;
+}
+
+int bmc_liquid_set_feeds(bmc_ctx* ctx, uint64_t n, const bmc_feed* f) {
+  if (!ctx || (n && !f)) return BMC_ERR_INVALID;
+  if (n > (uint64_t)kMaxFlows) { ctx->err = "too many feed entries (max 16)"; return BMC_ERR_UNSUPPORTED; }
+  std::vector<bmc_leaving_flow> out;
+  for (uint64_t i = 0; i < n; ++i) {
+    if (f[i].species >= ctx->n_species || f[i].input_position >= ctx->n_comp || (f[i].has_output && f[i].output_position >= ctx->n_comp)) {
+      ctx->err = "feed index out of range"; return BMC_ERR_RANGE;
+    }
+    if (f[i].flow < 0) { ctx->err = "negative feed flow"; return BMC_ERR_INVALID; }
+    if (f[i].has_output && f[i].first_of_feed)  // set_leaving_flow(mc_flow_counter, output_position, flow, volume)
+      out.push_back(bmc_leaving_flow{f[i].output_position, f[i].flow, ctx->h_vol[f[i].output_position]});
+  }
+  ctx->feeds.assign(f, f + n);
+  ctx->flows = out;
+  return BMC_OK;
+}
+
+int bmc_liquid_step(bmc_ctx* ctx, double d_t) {
+  if (!ctx || !(d_t >= 0)) return BMC_ERR_INVALID;
+  if (ctx->n_comp > 1 && !ctx->transition_set) { ctx->err = "bmc_liquid_set_transition not called"; return BMC_ERR_INVALID; }
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const uint32_t nb = (uint32_t)(ctx->n_species * ctx->n_comp);
+  int rc;
+  if (ctx->mass_dirty) {
+    liquid_mass_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ctx->d_conc, ctx->d_vol, ctx->d_mass, (uint32_t)ctx->n_species, nb);
+    if ((rc = check_launch(ctx, "liquid_mass"))) return rc;
+    ctx->mass_dirty = false;
+  }
+  LiquidParams lp;
+  memset(&lp, 0, sizeof(lp));
+  lp.c_old = ctx->d_conc; lp.c_new = ctx->d_conc_next; lp.mass = ctx->d_mass; lp.vol = ctx->d_vol; lp.sources = ctx->d_sources;
+  lp.csc_ptr = ctx->d_csc_ptr; lp.csc_row = ctx->d_csc_row; lp.csc_val = ctx->d_csc_val;
+  lp.n_species = (uint32_t)ctx->n_species; lp.n_comp = (uint32_t)ctx->n_comp; lp.dt = d_t; lp.n_feeds = (int)ctx->feeds.size();
+  for (int i = 0; i < lp.n_feeds; ++i) {
+    const bmc_feed& f = ctx->feeds[i];
+    lp.feeds[i] = FeedDev{(uint32_t)f.species, (uint32_t)f.input_position, (uint32_t)f.output_position, f.has_output, f.first_of_feed, f.flow, f.concentration};
+  }
+  liquid_step_kernel<<<(nb + 255) / 256, 256, 0, s>>>(lp);
+  if ((rc = check_launch(ctx, "liquid_step"))) return rc;
+  std::swap(ctx->d_conc, ctx->d_conc_next);
   return BMC_OK;
 }
 

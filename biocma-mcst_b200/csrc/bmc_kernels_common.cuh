@@ -234,6 +234,42 @@ __global__ void derive_cdf_table_kernel(const double* cdf, float* out, size_t n)
   if (i < n) out[i] = __double2float_rd(cdf[i]);
 }
 
+// -----------------------------------------------------------------------------
+// Liquid phase: ScalarSimulation::performStep (implScalar.cpp:251-266) preceded by the
+// scalar part of update_feed (simulation.model.cpp:55-69) and followed by clearContribution
+// (sync.cpp:89-116).  One thread per (species, compartment); the transition matrix is stored
+// by destination column (CSC, entries in COO order) so that every element accumulates its
+// inflow terms in the same order a sequential COO sweep does -> bit-identical to the oracle.
+// -----------------------------------------------------------------------------
+struct FeedDev { uint32_t species, input_position, output_position; int has_output, first_of_feed; double flow, concentration; };
+struct LiquidParams {
+  const double* c_old; double* c_new; double* mass; const double* vol; double* sources;
+  const uint32_t* csc_ptr; const uint32_t* csc_row; const double* csc_val;
+  uint32_t n_species, n_comp; double dt; int n_feeds; FeedDev feeds[kMaxFlows];
+};
+__global__ void __launch_bounds__(256) liquid_step_kernel(const __grid_constant__ LiquidParams p) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= p.n_species * p.n_comp) return;
+  const uint32_t s = k % p.n_species, j = k / p.n_species;
+  double src = p.sources[k], sink = 0.0;
+  for (int f = 0; f < p.n_feeds; ++f) {  // set_feed / set_sink
+    if (p.feeds[f].input_position == j && p.feeds[f].species == s) src += p.feeds[f].flow * p.feeds[f].concentration;
+    if (p.feeds[f].has_output && p.feeds[f].first_of_feed && p.feeds[f].output_position == j) sink += p.feeds[f].flow;
+  }
+  double dm = 0.0;
+  for (uint32_t e = p.csc_ptr[j]; e < p.csc_ptr[j + 1]; ++e) dm += p.c_old[s + p.n_species * p.csc_row[e]] * p.csc_val[e];
+  const double c = p.c_old[k];
+  dm += -c * sink + src;
+  const double m = p.mass[k] + p.dt * dm;
+  p.mass[k] = m;
+  p.c_new[k] = m * (1.0 / p.vol[j]);
+  p.sources[k] = 0.0;  // clearContribution
+}
+__global__ void liquid_mass_kernel(const double* c, const double* vol, double* mass, uint32_t n_species, uint32_t n) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) mass[k] = c[k] * vol[k / n_species];
+}
+
 // get_repartition: NcellFunctor (mc/src/unit.cpp:48-100, 190-230)
 __global__ void __launch_bounds__(256) repartition_kernel(const uint32_t* pos, const uint8_t* status, const DevState* st,
                                                           unsigned long long* out) {
