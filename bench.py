@@ -32,14 +32,22 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-B_ALG = {"monod": 57, "fixed_length": 37, "simple_acetate": 65}     # SURVEY.md §8d, multi-compartment + outlet
-B_ALG_0D = {"monod": 45, "fixed_length": 25, "simple_acetate": 53}  # 0D batch
+B_ALG = {"monod": 57, "fixed_length": 37, "simple_acetate": 65, "wide_udf": 8 * 32 + 25}     # SURVEY.md §8d, multi-compartment + outlet
+B_ALG_0D = {"monod": 45, "fixed_length": 25, "simple_acetate": 53, "wide_udf": 8 * 32 + 13}  # 0D batch
+N_SPECIES = {"monod": 1, "fixed_length": 1, "simple_acetate": 2, "wide_udf": 4}
 
 WORKLOADS = {
     # name: (model, n_comp, particles per GPU, dt, near_division, p_exit)
     "c2": ("monod", 500, 10_000_000, 0.1, 0.0, 1e-3),
     "c3": ("monod", 500, 100_000_000, 1.0, 0.5, 1e-3),
     "c1": ("monod", 1, 100_000, 0.1, 0.0, 1e-3),
+    # configs[3]: 10k compartments, 1e9 particles over 8 GPUs -> 1.25e8 per GPU
+    "c4": ("monod", 10_000, 125_000_000, 0.1, 0.0, 1e-3),
+    # configs[4]: wide UDF (32 properties), 2e9 particles over 8 GPUs -> 2.5e8 per GPU
+    "c5": ("wide_udf", 500, 250_000_000, 0.1, 0.0, 1e-3),
+    # other built-in models on the c2 shape
+    "fl": ("fixed_length", 500, 10_000_000, 0.1, 0.0, 1e-3),
+    "sa": ("simple_acetate", 500, 10_000_000, 0.1, 0.0, 1e-3),
 }
 
 
@@ -128,7 +136,8 @@ def build_case(synth, model, n_comp, dt, p_exit):
     if p_exit > 0:
         o = n_comp - 1
         flows = [(o, p_exit * fm["volumes"][o] / dt, fm["volumes"][o])]
-    conc = np.full(n_comp, 3.0) * (0.8 + 0.4 * np.random.default_rng(5).random(n_comp))
+    ns = N_SPECIES[model]
+    conc = np.full(ns * n_comp, 3.0) * (0.8 + 0.4 * np.random.default_rng(5).random(ns * n_comp))
     return fm, flows, conc
 
 
@@ -156,7 +165,7 @@ def run_reference(args, wl):
     n = min(n_full, args.cpu_sample)
     fm, flows, conc = build_case(synth, model, n_comp, dt, p_exit)
     props, pos = synth.make_population(model, n, n_comp, seed=11, near_division=near)
-    o = oracle.OracleLoop(model, 1, n_comp, n_threads=threads)
+    o = oracle.OracleLoop(model, N_SPECIES[model], n_comp, n_threads=threads)
     o.set_particles(props, pos)
     o.set_weight(synth.initial_weight(props, 0.5, float(fm["volumes"].sum())))
     setup_loop(o, fm, flows, conc, n_comp)
@@ -217,9 +226,13 @@ def main():
     if args.particles:
         n_per_gpu = args.particles
     fm, flows, conc = build_case(synth, model, n_comp, dt, p_exit)
-    loop = pkg.ParticleLoop(model, 1, n_comp, device=local, seed=2024, rank=rank)
+    loop = pkg.ParticleLoop(model, N_SPECIES[model], n_comp, device=local, seed=2024, rank=rank)
     # population: device-side mc_init_first (monod draws its TruncatedNormal lengths on the GPU)
-    total_mass = loop.init_particles(n_per_gpu, uniform_position=True)
+    linit = None
+    if model in ("fixed_length", "wide_udf"):  # configurable models take their lengths from a Config view
+        linit = (1e-6 + 1e-6 * np.random.default_rng(3 + rank).random(n_per_gpu)).astype(np.float32)
+    total_mass = loop.init_particles(n_per_gpu, uniform_position=True, linit=linit)
+    del linit
     if near > 0:  # c3: bring cells close to division through the host path once
         props, pos = synth.make_population(model, n_per_gpu, n_comp, seed=11 + rank, near_division=near)
         loop.set_particles(props, pos)
@@ -312,19 +325,19 @@ def main():
         peak, peak_src = peaks()
         b_alg = B_ALG[model] if n_comp > 1 else B_ALG_0D[model]
         achieved = (live_avg * b_alg) / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-        nb = n_comp * 8
+        nb = N_SPECIES[model] * n_comp * 8
         line = {
             "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{wl}: {n_comp}-compartment stirred-tank CMA, {model}, {n_per_gpu} particles/GPU, dt={dt}",
                        "parallelism": f"particle-sharded x{world}, replicated liquid state, 1 NCCL all-reduce/step" if world > 1 else "single GPU",
-                       "l2_policy": f"inputs larger than L2 ({n_per_gpu * 37 / 1e6:.0f} MB of particle state per GPU)"},
+                       "l2_policy": f"inputs larger than L2 ({n_per_gpu * (loop.n_var * 4 + 13) / 1e6:.0f} MB of particle state per GPU)"},
             "e2e": {"value": e2e_v, "unit": "particle-steps/s", "h2d_bytes_per_step": nb, "d2h_bytes_per_step": nb,
                     "ms_per_step": ms_e2e / e2e_steps},
             "gpu_launches": int(launches_tot),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "cycle_kernel<Monod,4>", "kernel_ms": k_ms, "bytes_per_particle": b_alg,
+                         "traffic": None, "kernel": f"cycle_kernel<{model}>", "kernel_ms": k_ms, "bytes_per_particle": b_alg,
                          "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", "kernel_share_of_step": k_ms * args.steps / ms},
             "clocks": clocks,
         }
@@ -334,7 +347,7 @@ def main():
             threads = host_threads()
             n = min(n_per_gpu, args.cpu_sample)
             props, pos = synth.make_population(model, n, n_comp, seed=11, near_division=near)
-            o = oracle.OracleLoop(model, 1, n_comp, n_threads=threads)
+            o = oracle.OracleLoop(model, N_SPECIES[model], n_comp, n_threads=threads)
             o.set_particles(props, pos)
             o.set_weight(1.0)
             setup_loop(o, fm, flows, conc, n_comp)

@@ -227,6 +227,7 @@ static int sync_state(bmc_ctx* ctx, DevState* out) {
   ctx->mirror_valid[0] = ctx->mirror_valid[1] = false;
   *out = *ctx->h_st[0];
   ctx->known_n_used = out->n_used;
+  ctx->known_max_add = std::max<uint64_t>(ctx->known_max_add, out->n_add);
   if (out->inactive == 0 && ctx->flows.empty()) ctx->maybe_inactive = false;
   if (out->error & 2u) { ctx->err = "compaction found fewer idle tail particles than gaps (inactive counter inconsistent)"; return BMC_ERR_INVALID; }
   return BMC_OK;

@@ -235,3 +235,33 @@ def test_monod_device_init_in_distribution(bmc, orc):
     assert np.all(pg["props"][1] == np.float32(2e-6)) and np.all(pg["props"][2] == np.float32(0.77 / 3600.0))
     assert np.array_equal(pg["position"], po["position"])  # urand64 from the same Philox words: exact
     assert chisquare(np.bincount(pg["position"].astype(np.int64), minlength=nc)).pvalue > 1e-4
+
+
+def test_large_compartment_tables(bmc, orc, synth):
+    # 4 species x 4000 compartments x 8 B = 128 KB of source bins: does not fit the shared-memory
+    # budget -> the scatter falls back to L2 atomics; 10k x 1 species (80 KB) still uses shared bins
+    for model, n_comp in (("wide_udf", 4000), ("monod", 10_000)):
+        case = util.make_case(synth, model, 60_000, n_comp, dt=20.0, near_division=0.8, p_move=0.3, p_exit=0.3)
+        g, o = _pair(bmc, orc, case, dead_ratio=0.0005)
+        util.load_case(g, case); util.load_case(o, case)
+        sg = util.run_steps(g, case, 6, collect=True); so = util.run_steps(o, case, 6, collect=True)
+        _compare_sources(sg, so)
+        _compare(g, o)
+        assert o.counters()["total_new"] > 0
+
+
+def test_capacity_growth_is_transparent(bmc, orc, synth):
+    # population doubles several times: the device container is grown by the host from its view of
+    # n_used (ParticlesContainer::_resize, particles_container.hpp:601-643) and the state survives
+    # every reallocation.  The device never writes past the capacity: newborns beyond the free room
+    # would be counted as Overflow (like a full buffer), so the case leaves room for a doubling.
+    case = util.make_case(synth, "fixed_length", 30_000, 16, dt=600.0, near_division=0.5, p_move=0.3, outlet=False)
+    g, o = _pair(bmc, orc, case, allocation_factor=2.5)
+    util.load_case(g, case); util.load_case(o, case)
+    for s in range(14):
+        util.run_steps(g, case, 1); util.run_steps(o, case, 1)
+        g.counters()  # synchronous read refreshes the host's view -> growth happens before it is needed
+    cg, co = g.counters(), o.counters()
+    assert co["n_used"] > 4 * case["n"] and cg["capacity"] > 2.5 * case["n"] * 2 and cg["events"]["Overflow"] == 0
+    util.assert_counters_equal(cg, co)
+    util.assert_state_equal(g.get_particles(co["n_used"]), o.get_particles(co["n_used"]), co["n_used"])
