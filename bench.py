@@ -326,6 +326,14 @@ def main():
         b_alg = B_ALG[model] if n_comp > 1 else B_ALG_0D[model]
         achieved = (live_avg * b_alg) / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
         nb = N_SPECIES[model] * n_comp * 8
+        traffic = None  # DRAM bytes per launch of the cycle kernel from the committed ncu capture of this workload
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                t = json.load(f).get(wl)
+            if t and t["particles"] == n_per_gpu:
+                traffic = t["bytes_per_launch"]
+        except Exception:
+            pass
         line = {
             "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -337,7 +345,7 @@ def main():
                     "ms_per_step": ms_e2e / e2e_steps},
             "gpu_launches": int(launches_tot),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": f"cycle_kernel<{model}>", "kernel_ms": k_ms, "bytes_per_particle": b_alg,
+                         "traffic": traffic, "kernel": f"cycle_kernel<{model}>", "kernel_ms": k_ms, "bytes_per_particle": b_alg,
                          "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", "kernel_share_of_step": k_ms * args.steps / ms},
             "clocks": clocks,
         }
