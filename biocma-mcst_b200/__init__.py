@@ -31,6 +31,7 @@ ABI_SYMBOLS = (
     "bmc_sources_device", "bmc_concentrations_device", "bmc_stream", "bmc_launch_count", "bmc_profile_enable",
     "bmc_profile_read", "bmc_nccl_unique_id", "bmc_comm_init", "bmc_allreduce_sources",
     "bmc_liquid_set_transition", "bmc_liquid_set_feeds", "bmc_liquid_step", "bmc_get_concentrations",
+    "bmc_udf_check",
 )
 
 
@@ -119,6 +120,7 @@ def load_library(path=None):
     lib.bmc_liquid_set_feeds.argtypes = [vp, u64, P(BmcFeed)]
     lib.bmc_liquid_step.argtypes = [vp, dbl]
     lib.bmc_get_concentrations.argtypes = [vp, vp]
+    lib.bmc_udf_check.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
     for name in ABI_SYMBOLS:
         if name != "bmc_last_error":
             getattr(lib, name).restype = ctypes.c_int
@@ -131,6 +133,15 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
+def udf_check(source_path):
+    """Compile-only check of a user model source (NVRTC, sm_100a; no device needed).
+    Returns (ok, compiler log or error text)."""
+    lib = load_library()
+    buf = ctypes.create_string_buffer(1 << 16)
+    rc = lib.bmc_udf_check(os.fsencode(source_path), buf, len(buf))
+    return rc == 0, buf.value.decode(errors="replace")
+
+
 class ParticleLoop:
     """One GPU context of the Monte-Carlo particle loop (wraps ``bmc_ctx``).
 
@@ -139,14 +150,16 @@ class ParticleLoop:
     """
 
     def __init__(self, model, n_species=1, n_compartments=1, *, device=0, seed=2024, rank=0, capacity=0,
-                 n_var_udf=32, allocation_factor=0.0, buffer_ratio=0.0, dead_ratio=0.0, min_removal=0):
+                 n_var_udf=32, allocation_factor=0.0, buffer_ratio=0.0, dead_ratio=0.0, min_removal=0, udf_source=None):
         self.lib = load_library()
         self.model = MODEL_IDS[model] if isinstance(model, str) else int(model)
+        # `-mn udf_model`: source path from the argument, else env BIOMC_LIB_UDF (read by the library)
+        self._udf = None if udf_source is None else os.fsencode(udf_source)
         cfg = BmcConfig(device=device, model=self.model, n_var_udf=n_var_udf, n_species=n_species,
                         n_compartments=n_compartments, capacity=capacity, seed=seed, rank=rank,
                         allocation_factor=allocation_factor, buffer_ratio=buffer_ratio,
                         dead_particle_ratio_threshold=dead_ratio, shrink_ratio=0.0,
-                        minimum_dead_particle_removal=min_removal, udf_source_path=None)
+                        minimum_dead_particle_removal=min_removal, udf_source_path=self._udf)
         self.h = ctypes.c_void_p()
         rc = self.lib.bmc_create(ctypes.byref(self.h), ctypes.byref(cfg))
         if rc != 0:

@@ -196,7 +196,10 @@ static int configure_launch(bmc_ctx* ctx) {
   if (ctx->smem_total > 48 * 1024)
     CK(cudaFuncSetAttribute(ctx->vt.cycle_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_total));
   int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ctx->vt.cycle_fn, kBlock, ctx->smem_total));
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ctx->vt.cycle_fn, kBlock, ctx->smem_total) != cudaSuccess) {
+    (void)cudaGetLastError();
+    occ = ctx->vt.minb;  // JIT kernel handle not accepted by the occupancy query: trust __launch_bounds__
+  }
   if (occ < 1) occ = 1;
   const char* env = getenv("BMC_BLOCKS_PER_SM");
   if (env && atoi(env) > 0) occ = std::min(occ, atoi(env));
@@ -259,8 +262,16 @@ int bmc_create(bmc_ctx** out, const bmc_config* cfg) {
   bmc_ctx* ctx = new (std::nothrow) bmc_ctx();
   if (!ctx) return BMC_ERR_NOMEM;
   auto fail = [&](int rc) { fprintf(stderr, "bmc_create: %s\n", ctx->err.c_str()); bmc_ctx* t = ctx; bmc_destroy(&t); return rc; };
-  if (cfg->model == BMC_MODEL_UDF) { ctx->err = "BMC_MODEL_UDF (NVRTC) is not built in this round"; return fail(BMC_ERR_UNSUPPORTED); }
-  if (!pick_model(cfg->model, cfg->n_var_udf, ctx->vt)) { ctx->err = "unknown model / unsupported n_var_udf"; return fail(BMC_ERR_INVALID); }
+  {
+    cudaError_t e0 = cudaSetDevice(cfg->device);
+    if (e0 != cudaSuccess) { ctx->err = std::string("cudaSetDevice: ") + cudaGetErrorString(e0); return fail(BMC_ERR_CUDA); }
+  }
+  if (cfg->model == BMC_MODEL_UDF) {
+    // `-mn udf_model` + BIOMC_LIB_UDF (apps/api/src/udf_handle.cpp:22-39): the path names the model SOURCE
+    const char* path = cfg->udf_source_path ? cfg->udf_source_path : getenv("BIOMC_LIB_UDF");
+    if (!path) { ctx->err = "BMC_MODEL_UDF needs udf_source_path or BIOMC_LIB_UDF"; return fail(BMC_ERR_INVALID); }
+    if (!load_udf_model(path, ctx->vt, ctx->err)) return fail(BMC_ERR_UNSUPPORTED);
+  } else if (!pick_model(cfg->model, cfg->n_var_udf, ctx->vt)) { ctx->err = "unknown model / unsupported n_var_udf"; return fail(BMC_ERR_INVALID); }
   if ((uint64_t)ctx->vt.n_c > cfg->n_species) { ctx->err = "model n_c exceeds n_species"; return fail(BMC_ERR_INVALID); }
   ctx->device = cfg->device; ctx->model = cfg->model;
   ctx->n_species = cfg->n_species; ctx->n_comp = cfg->n_compartments;
@@ -305,6 +316,7 @@ int bmc_destroy(bmc_ctx** h) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->nccl_comm && g_nccl_destroy) g_nccl_destroy(c->nccl_comm);
+  unload_udf_model(c->vt);
   free_container(c);
   dev_free(c->d_conc); dev_free(c->d_sources); dev_free(c->d_conc_next); dev_free(c->d_mass);
   dev_free(c->d_csc_ptr); dev_free(c->d_csc_row); dev_free(c->d_csc_val);
@@ -429,9 +441,10 @@ int bmc_init_particles(bmc_ctx* ctx, uint64_t n, int uniform_position, const flo
   CK(cudaMemsetAsync(ctx->st, 0, sizeof(DevState), s));
   CK(cudaMemsetAsync(ctx->status, 0, ctx->cap, s));
   const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->n_sm * 8);
-  ctx->vt.launch_init(ctx->props, ctx->cap, ctx->pos, ctx->status, ctx->age_hyd, ctx->age_div, n,
-                      uniform_position ? (uint32_t)ctx->n_comp : 1u, d_linit, (uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32),
-                      ctx->rank, ctx->st, grid, s);
+  InitParams ipar{ctx->props, ctx->cap, ctx->pos, ctx->status, ctx->age_hyd, ctx->age_div, n,
+                  uniform_position ? (uint32_t)ctx->n_comp : 1u, d_linit, (uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32), ctx->rank, ctx->st};
+  void* iargs[] = {&ipar};
+  CK(cudaLaunchKernel(ctx->vt.init_fn, dim3(grid), dim3(256), iargs, 0, s));
   if ((rc = check_launch(ctx, "init_kernel"))) return rc;
   CK(cudaMemcpyAsync(&ctx->st->n_used, &n, 8, cudaMemcpyHostToDevice, s));
   DevState hs;
@@ -607,7 +620,8 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   {
     const uint32_t work = std::max<uint32_t>(std::max<uint32_t>(n_bins, (uint32_t)ctx->n_comp), 256u);
     const int grid = (int)std::min<uint32_t>((work + 255) / 256, (uint32_t)ctx->n_sm * 2);
-    ctx->vt.launch_pre(pp, grid, s);
+    void* pargs[] = {&pp};
+    CK(cudaLaunchKernel(ctx->vt.pre_fn, dim3(grid), dim3(256), pargs, 0, s));
     if ((rc = check_launch(ctx, "pre_step"))) return rc;
   }
 
@@ -637,7 +651,8 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, s));
   }
-  ctx->vt.launch_cycle(p, ctx->grid_cycle, ctx->smem_total, s);
+  void* cargs[] = {&p};
+  CK(cudaLaunchKernel(ctx->vt.cycle_fn, dim3(ctx->grid_cycle), dim3(kBlock), cargs, ctx->smem_total, s));
   if ((rc = check_launch(ctx, "cycle_kernel"))) return rc;
   if (ctx->profile) { CK(cudaEventRecord(e1, s)); ctx->prof_events.emplace_back(e0, e1); }
 

@@ -24,9 +24,6 @@
 // prefix sums of division counts so that newborn placement is deterministic
 // without a global scan.
 #pragma once
-#include <cstdint>
-#include <type_traits>
-#include <cuda_runtime.h>
 #include "bmc_models.cuh"
 #include "bmc_rng.cuh"
 
@@ -45,6 +42,9 @@ namespace bmc {
 #define BMC_LD(p) (*(p))
 #define BMC_ST(p, v) (*(p) = (v))
 #endif
+
+struct FullTile { static constexpr bool value = true; };
+struct RaggedTile { static constexpr bool value = false; };
 
 constexpr int kTile = 1024;         // particles per rank-tile (bitmask / prefix granularity)
 constexpr int kBlock = 256;         // threads per block
@@ -195,8 +195,7 @@ struct PreParams {
   const uint32_t* buf_mother; uint32_t* div_mask; uint32_t* tile_div;
 };
 
-template <class M>
-__global__ void __launch_bounds__(256) pre_step_kernel(const __grid_constant__ PreParams p) {
+template <class M> __device__ __forceinline__ void pre_step_body(const PreParams& p) {
   constexpr int CT = 1 + M::n_pre;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t nthreads = gridDim.x * blockDim.x;
@@ -291,8 +290,7 @@ template <int BYTES> __device__ __forceinline__ void cp_async(void* smem_dst, co
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <class M, int VEC, int MINB, bool PIPE>
-__global__ void __launch_bounds__(kBlock, MINB) cycle_kernel(const __grid_constant__ CycleParams p) {
+template <class M, int VEC, bool PIPE> __device__ __forceinline__ void cycle_body(const CycleParams& p) {
   constexpr int NV = M::n_var, NC = M::n_c, CT = 1 + M::n_pre;
   constexpr int SUB = kTile / (kBlock * VEC);  // sub-iterations per tile
   constexpr int kColStride = kBlock * 4 * VEC;  // bytes between staged columns
@@ -633,18 +631,18 @@ __global__ void __launch_bounds__(kBlock, MINB) cycle_kernel(const __grid_consta
         if (it + 1 < n_it) { stw_next = issue(it + 1, (int)((it + 1) & 1u)); cp_async_wait<1>(); }
         else cp_async_wait<0>();
         const uint32_t tile = t0 + it / SUB;
-        if ((unsigned long long)(tile + 1) * kTile <= n_used) body(std::true_type{}, tile, (int)(it % SUB), (int)(it & 1u), stw_cur);
-        else body(std::false_type{}, tile, (int)(it % SUB), (int)(it & 1u), stw_cur);
+        if ((unsigned long long)(tile + 1) * kTile <= n_used) body(FullTile{}, tile, (int)(it % SUB), (int)(it & 1u), stw_cur);
+        else body(RaggedTile{}, tile, (int)(it % SUB), (int)(it & 1u), stw_cur);
       }
     } else {
 #pragma unroll 1
       for (uint32_t tile = t0; tile < t1; ++tile) {
         if ((unsigned long long)(tile + 1) * kTile <= n_used) {
 #pragma unroll 1
-          for (int sub = 0; sub < SUB; ++sub) body(std::true_type{}, tile, sub, 0, 0u);
+          for (int sub = 0; sub < SUB; ++sub) body(FullTile{}, tile, sub, 0, 0u);
         } else {
 #pragma unroll 1
-          for (int sub = 0; sub < SUB; ++sub) body(std::false_type{}, tile, sub, 0, 0u);
+          for (int sub = 0; sub < SUB; ++sub) body(RaggedTile{}, tile, sub, 0, 0u);
         }
       }
     }
@@ -714,25 +712,33 @@ __global__ void __launch_bounds__(kBlock, MINB) cycle_kernel(const __grid_consta
 // mc_init_first: InitFunctor (mc/src/unit.cpp:102-144): M::init, random
 // compartment, total-mass reduce.
 // -----------------------------------------------------------------------------
-template <class M>
-__global__ void __launch_bounds__(256) init_kernel(float* props, size_t cap, uint32_t* pos, uint8_t* status, float* age_hyd,
-                                                   float* age_div, unsigned long long n, uint32_t n_comp_hi, const float* linit,
-                                                   uint32_t seed_lo, uint32_t seed_hi, uint32_t rank, DevState* st) {
+struct InitParams {
+  float* props; size_t cap; uint32_t* pos; uint8_t* status; float* age_hyd; float* age_div;
+  unsigned long long n; uint32_t n_comp_hi; const float* linit; uint32_t seed_lo, seed_hi, rank; DevState* st;
+};
+template <class M> __device__ __forceinline__ void init_body(const InitParams& p) {
   double m = 0.0;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n;
        i += (unsigned long long)gridDim.x * blockDim.x) {
     float v[M::n_var];
-    Gen gen(seed_lo, seed_hi, rank, (uint32_t)i, 0xFFFFFFFFu, 2u);
-    M::init(gen, (size_t)i, RegRow{v}, ConfigView{linit});
+    Gen gen(p.seed_lo, p.seed_hi, p.rank, (uint32_t)i, 0xFFFFFFFFu, 2u);
+    M::init(gen, (size_t)i, RegRow{v}, ConfigView{p.linit});
     m += M::mass((size_t)i, RegRow{v});
-    const uint32_t c = (uint32_t)gen.urand64(0ull, (unsigned long long)n_comp_hi);
+    const uint32_t c = (uint32_t)gen.urand64(0ull, (unsigned long long)p.n_comp_hi);
 #pragma unroll
-    for (int k = 0; k < M::n_var; ++k) props[(size_t)k * cap + i] = v[k];
-    pos[i] = c; status[i] = (uint8_t)Idle; age_hyd[i] = 0.f; age_div[i] = 0.f;
+    for (int k = 0; k < M::n_var; ++k) p.props[(size_t)k * p.cap + i] = v[k];
+    p.pos[i] = c; p.status[i] = (uint8_t)Idle; p.age_hyd[i] = 0.f; p.age_div[i] = 0.f;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
-  if ((threadIdx.x & 31) == 0 && m != 0.0) atomicAdd(&st->init_mass, m);
+  if ((threadIdx.x & 31) == 0 && m != 0.0) atomicAdd(&p.st->init_mass, m);
 }
+
+// __global__ entry points of the built-in models (the NVRTC path of user models wraps the same
+// bodies in extern "C" kernels, see bmc_udf.cu)
+template <class M> __global__ void __launch_bounds__(256) pre_step_kernel(const __grid_constant__ PreParams p) { pre_step_body<M>(p); }
+template <class M, int VEC, int MINB, bool PIPE>
+__global__ void __launch_bounds__(kBlock, MINB) cycle_kernel(const __grid_constant__ CycleParams p) { cycle_body<M, VEC, PIPE>(p); }
+template <class M> __global__ void __launch_bounds__(256) init_kernel(const __grid_constant__ InitParams p) { init_body<M>(p); }
 
 }  // namespace bmc

@@ -2,42 +2,32 @@
 // unit (bmc_inst_*.cu, compiled in parallel); bmc_api.cu only sees these function pointers.
 #pragma once
 #include <string>
+#include <cuda_runtime.h>
 #include "bmc_kernels.cuh"
 
 namespace bmc {
 
 struct ModelVT {
-  int n_var, n_c, vec;
-  const void* cycle_fn;
-  void (*launch_cycle)(const CycleParams&, int grid, size_t smem, cudaStream_t);
-  void (*launch_init)(float*, size_t, uint32_t*, uint8_t*, float*, float*, unsigned long long, uint32_t, const float*,
-                      uint32_t, uint32_t, uint32_t, DevState*, int, cudaStream_t);
+  int n_var, n_c, vec, minb;
   int ct;              // floats per compartment-table row
   size_t stage_bytes;  // dynamic shared memory of the cp.async pipeline (0 = direct loads)
-  void (*launch_pre)(const PreParams&, int grid, cudaStream_t);
+  // kernel handles: addresses of __global__ instantiations, or cudaKernel_t of a JIT-compiled
+  // user model; all launched with cudaLaunchKernel(handle, grid, block, {&params}, smem, stream)
+  const void* cycle_fn;   // (CycleParams)  block = kBlock
+  const void* pre_fn;     // (PreParams)    block = 256
+  const void* init_fn;    // (InitParams)   block = 256
+  void* jit_library;      // cudaLibrary_t of a user model (unloaded with the context), else nullptr
 };
 
-template <class M, int VEC, int MINB, bool PIPE> static void launch_cycle_t(const CycleParams& p, int grid, size_t smem, cudaStream_t s) {
-  cycle_kernel<M, VEC, MINB, PIPE><<<grid, kBlock, smem, s>>>(p);
-}
-template <class M>
-static void launch_init_t(float* props, size_t cap, uint32_t* pos, uint8_t* status, float* ah, float* ad, unsigned long long n,
-                          uint32_t ncomp_hi, const float* linit, uint32_t slo, uint32_t shi, uint32_t rank, DevState* st, int grid,
-                          cudaStream_t s) {
-  init_kernel<M><<<grid, 256, 0, s>>>(props, cap, pos, status, ah, ad, n, ncomp_hi, linit, slo, shi, rank, st);
-}
-template <class M> static void launch_pre_t(const PreParams& p, int grid, cudaStream_t s) {
-  pre_step_kernel<M><<<grid, 256, 0, s>>>(p);
-}
 template <class M, int VEC, int MINB = 1, bool PIPE = false> static ModelVT make_vt() {
   ModelVT v;
-  v.n_var = M::n_var; v.n_c = M::n_c; v.vec = VEC;
-  v.cycle_fn = (const void*)cycle_kernel<M, VEC, MINB, PIPE>;
-  v.launch_cycle = &launch_cycle_t<M, VEC, MINB, PIPE>;
-  v.stage_bytes = PIPE ? 2 * StageBytes<M, VEC>::value : 0;
-  v.launch_init = &launch_init_t<M>;
+  v.n_var = M::n_var; v.n_c = M::n_c; v.vec = VEC; v.minb = MINB;
   v.ct = 1 + M::n_pre;
-  v.launch_pre = &launch_pre_t<M>;
+  v.stage_bytes = PIPE ? 2 * StageBytes<M, VEC>::value : 0;
+  v.cycle_fn = (const void*)cycle_kernel<M, VEC, MINB, PIPE>;
+  v.pre_fn = (const void*)pre_step_kernel<M>;
+  v.init_fn = (const void*)init_kernel<M>;
+  v.jit_library = nullptr;
   return v;
 }
 
@@ -64,5 +54,8 @@ bool pick_monod(const std::string& var, ModelVT& vt);
 bool pick_simple_acetate(const std::string& var, ModelVT& vt);
 bool pick_wide_udf_small(const std::string& var, int n_var, ModelVT& vt);   // P = 8, 16
 bool pick_wide_udf_large(const std::string& var, int n_var, ModelVT& vt);   // P = 32, 64
+// BMC_MODEL_UDF: NVRTC-compile a user model source against these headers (bmc_udf.cu)
+bool load_udf_model(const char* source_path, ModelVT& vt, std::string& err);
+void unload_udf_model(ModelVT& vt);
 
 }  // namespace bmc

@@ -26,8 +26,6 @@
 // All arithmetic is compiled with -fmad=false: IEEE single/double without
 // contraction, so deterministic models are bit-reproducible against the oracle.
 #pragma once
-#include <cstdint>
-#include <cuda_runtime.h>
 #include "bmc_rng.cuh"
 
 namespace bmc {

@@ -14,8 +14,15 @@
 // draw_block 3.. (index = slot): generator handed to M::update / M::init;
 // draw_block 0x40000001.. : generator handed to M::division.
 #pragma once
+#ifdef __CUDACC_RTC__  // NVRTC (user-defined models are JIT-compiled): no host headers
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+#else
 #include <cstdint>
 #include <cuda_runtime.h>
+#endif
 
 namespace bmc {
 

@@ -113,7 +113,7 @@ def make_population(model, n, n_comp, *, seed=2024, n_var_udf=32, near_division=
     lo = 1e-6 + near_division * 0.95e-6
     length = truncated_normal(rng, n, max(1.5e-6, lo + 0.02e-6), 0.375e-6, lo, 2e-6).astype(np.float32)
     pos = rng.integers(0, n_comp, size=n, dtype=np.uint64)
-    if model in ("fixed_length", 0):
+    if model in ("fixed_length", 0, "udf_model", 4):  # the example UDF has fixed_length's property layout
         props = np.stack([length, np.full(n, l_max, np.float32)])
     elif model in ("monod", 1):
         mu_max = np.float32(0.77 / 3600.0)

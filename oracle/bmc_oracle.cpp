@@ -386,7 +386,41 @@ struct WideUdf {
 };
 int WideUdf::n_var_rt = 32;
 
-enum ModelId { M_FIXED_LENGTH = 0, M_MONOD = 1, M_SIMPLE_ACETATE = 2, M_WIDE_UDF = 3 };
+// The reference's example user-defined model, apps/udf_model/minimal.cpp:24-121 (loaded through
+// `-mn udf_model` + BIOMC_LIB_UDF).  The CUDA path compiles its own source-level version of it
+// (biocma-mcst_b200/udf/minimal_udf.cu) with NVRTC; this is the independent CPU restatement.
+struct UdfMinimal {
+  static constexpr int n_var = 2, n_c = 1;
+  enum { length = 0, l_max = 1 };
+  static float l_dot_max() { return (float)(2e-6 / 3600.); }
+  static float l_max_m() { return (float)2e-6; }
+  static float k() { return (float)1e-3; }
+  static float lin_density() { return c_linear_density(1000.0f, (float)0.6e-6); }
+  static float phi_s_max() { return (l_dot_max() * lin_density()) / 0.5f; }  // :36-37
+  static void init(Gen&, size_t idx, const Arr& arr, float linit) {  // :59-67
+    arr(idx, length) = linit; arr(idx, l_max) = l_max_m();
+  }
+  static double mass(size_t idx, const Arr& arr) { return arr(idx, length) * lin_density(); }  // :110-113
+  static Status update(Gen&, float d_t, size_t idx, const Arr& arr, const Arr& contribs, size_t pos,
+                       const Conc& c) {  // :69-89
+    const float s = (float)c(0, pos);
+    const float g = s / (k() + s);
+    const float phi_s = phi_s_max() * g;
+    const float ldot = l_dot_max() * g;
+    const float d_length = d_t * ldot;
+    // `length += d_length / (1.0 + d_t * ldot)`: the 1.0 literal promotes the quotient and the sum to double (:82)
+    arr(idx, length) = (float)((double)arr(idx, length) + (double)d_length / (1.0 + (double)(d_t * ldot)));
+    contribs(idx, 0) = -phi_s;
+    return check_div(arr(idx, length), arr(idx, l_max));
+  }
+  static void division(Gen&, size_t idx, size_t idx2, const Arr& arr, const Arr& buf) {  // :91-108
+    const float nl = arr(idx, length) / 2.0f;
+    buf(idx2, length) = nl; buf(idx2, l_max) = l_max_m();
+    arr(idx, length) = nl; arr(idx, l_max) = l_max_m();
+  }
+};
+
+enum ModelId { M_FIXED_LENGTH = 0, M_MONOD = 1, M_SIMPLE_ACETATE = 2, M_WIDE_UDF = 3, M_UDF_MINIMAL = 4 };
 
 // ---------------------------------------------------------------------------
 // LeavingFlow — domain.hpp:17-23
@@ -717,6 +751,7 @@ static void dispatch_cycle(Ctx& c, double d_t) {
     case M_MONOD: cycle_process<Monod>(c, d_t); break;
     case M_SIMPLE_ACETATE: cycle_process<SimpleAcetate>(c, d_t); break;
     case M_WIDE_UDF: cycle_process<WideUdf>(c, d_t); break;
+    case M_UDF_MINIMAL: cycle_process<UdfMinimal>(c, d_t); break;
   }
 }
 
@@ -759,6 +794,7 @@ void* orc_create(int model, int n_var_udf, uint64_t n_species, uint64_t n_comp, 
     case M_MONOD: c->n_var = Monod::n_var; c->n_c = Monod::n_c; break;
     case M_SIMPLE_ACETATE: c->n_var = SimpleAcetate::n_var; c->n_c = SimpleAcetate::n_c; break;
     case M_WIDE_UDF: c->n_var = n_var_udf; c->n_c = WideUdf::n_c; WideUdf::n_var_rt = n_var_udf; break;
+    case M_UDF_MINIMAL: c->n_var = UdfMinimal::n_var; c->n_c = UdfMinimal::n_c; break;
     default: delete c; return nullptr;
   }
   c->n_species = n_species; c->n_comp = n_comp; c->seed = seed; c->rank = rank;
@@ -887,6 +923,7 @@ int orc_handle_division(void* h, uint64_t idx) {
       case M_MONOD: Monod::division(g, idx, j, arr, buf); break;
       case M_SIMPLE_ACETATE: SimpleAcetate::division(g, idx, j, arr, buf); break;
       case M_WIDE_UDF: WideUdf::division(g, idx, j, arr, buf); break;
+      case M_UDF_MINIMAL: UdfMinimal::division(g, idx, j, arr, buf); break;
     }
     c.buffer_position[j] = c.position[idx]; c.age_div[idx] = 0;
     return 1;
@@ -918,6 +955,7 @@ int orc_init_particles(void* h, uint64_t n, int uniform_pos, const float* linit,
       case M_MONOD: Monod::init(g, i, arr); m += Monod::mass(i, arr); break;
       case M_SIMPLE_ACETATE: SimpleAcetate::init(g, i, arr); m += SimpleAcetate::mass(i, arr); break;
       case M_WIDE_UDF: WideUdf::init(g, i, arr, linit ? linit[i] : 1.5e-6f); m += WideUdf::mass(i, arr); break;
+      case M_UDF_MINIMAL: UdfMinimal::init(g, i, arr, linit ? linit[i] : 1.5e-6f); m += UdfMinimal::mass(i, arr); break;
     }
     c.position[i] = g.urand64(0, max_c);
   }

@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbmc_oracle.so")
 EVENTS = ("NewParticle", "Exit", "Move", "Death", "Overflow", "ChangeWeight")
-MODEL_IDS = {"fixed_length": 0, "monod": 1, "simple_acetate": 2, "wide_udf": 3}
+MODEL_IDS = {"fixed_length": 0, "monod": 1, "simple_acetate": 2, "wide_udf": 3, "udf_model": 4}
 _lib = None
 
 

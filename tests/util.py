@@ -1,7 +1,7 @@
 """Shared helpers: build one synthetic case and drive a loop (oracle or CUDA) through it."""
 import numpy as np
 
-N_SPECIES = {"fixed_length": 1, "monod": 1, "simple_acetate": 2, "wide_udf": 4}
+N_SPECIES = {"fixed_length": 1, "monod": 1, "simple_acetate": 2, "wide_udf": 4, "udf_model": 1}
 
 
 def make_case(synth, model, n, n_comp, *, dt=0.1, seed=2024, near_division=0.0, outlet=True, p_move=0.01,
