@@ -75,10 +75,15 @@ struct bmc_ctx {
   int n_sm = 148, grid_cycle = 148, blocks_per_sm = 1; size_t smem_bins = 0; int bins_in_smem = 0;
   uint64_t launches = 0;
   size_t stage_offset = 0, smem_total = 0;
+  int grid_cycle_eager = 148; size_t smem_eager = 0;
   // staging
   void* d_stage = nullptr; size_t stage_bytes = 0;
   // profiling
   bool profile = false; std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events; double prof_ms = 0.0; uint64_t prof_n = 0;
+  // step-stamped ages (bmc_kernels.cuh): valid while d_t / outlet configuration stay constant and
+  // every age started at zero; otherwise the columns hold floats updated every step ("eager")
+  bool lazy_ages = true; bool epoch_set = false; double epoch_dt = 0.0; bool epoch_leave = false;
+  float *d_tab_div = nullptr, *d_tab_hyd = nullptr; size_t tab_cap = 0;
   // nccl
   void* nccl_comm = nullptr; int nccl_ranks = 0;
   std::string err;
@@ -193,18 +198,24 @@ static int configure_launch(bmc_ctx* ctx) {
   ctx->stage_offset = (ctx->smem_bins + 15) / 16 * 16;
   ctx->smem_total = ctx->stage_offset + ctx->vt.stage_bytes;
   if (ctx->smem_total > smem_budget) { ctx->err = "shared memory budget exceeded"; return BMC_ERR_UNSUPPORTED; }
-  if (ctx->smem_total > 48 * 1024)
-    CK(cudaFuncSetAttribute(ctx->vt.cycle_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_total));
-  int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ctx->vt.cycle_fn, kBlock, ctx->smem_total) != cudaSuccess) {
-    (void)cudaGetLastError();
-    occ = ctx->vt.minb;  // JIT kernel handle not accepted by the occupancy query: trust __launch_bounds__
-  }
-  if (occ < 1) occ = 1;
+  ctx->smem_eager = ctx->stage_offset;  // the eager-age variant loads directly: bins only
   const char* env = getenv("BMC_BLOCKS_PER_SM");
-  if (env && atoi(env) > 0) occ = std::min(occ, atoi(env));
-  ctx->blocks_per_sm = occ;
-  ctx->grid_cycle = std::min(ctx->n_sm * occ, kMaxGrid);
+  auto grid_of = [&](const void* fn, size_t smem, int& grid, int* occ_out) -> int {
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kBlock, smem) != cudaSuccess) {
+      (void)cudaGetLastError();
+      occ = ctx->vt.minb;  // JIT kernel handle not accepted by the occupancy query: trust __launch_bounds__
+    }
+    if (occ < 1) occ = 1;
+    if (env && atoi(env) > 0) occ = std::min(occ, atoi(env));
+    grid = std::min(ctx->n_sm * occ, kMaxGrid);
+    if (occ_out) *occ_out = occ;
+    return BMC_OK;
+  };
+  int rc;
+  if ((rc = grid_of(ctx->vt.cycle_fn, ctx->smem_total, ctx->grid_cycle, &ctx->blocks_per_sm))) return rc;
+  if ((rc = grid_of(ctx->vt.cycle_eager_fn, ctx->smem_eager, ctx->grid_cycle_eager, nullptr))) return rc;
   return BMC_OK;
 }
 
@@ -248,6 +259,55 @@ static int grow_if_needed(bmc_ctx* ctx) {
   if (s.n_used + margin <= ctx->cap) return BMC_OK;
   const size_t new_cap = (size_t)std::ceil((double)(s.n_used + margin) * ctx->allocation_factor);
   return resize_container(ctx, new_cap, (size_t)s.n_used);
+}
+
+// ---- step-stamped ages: host side ---------------------------------------------------------
+static bool force_eager_ages() { const char* e = getenv("BMC_EAGER_AGES"); return e && atoi(e) != 0; }
+
+// table entries [0, need) must exist; tab[0] = 0
+static int ensure_age_tables(bmc_ctx* ctx, size_t need) {
+  if (need <= ctx->tab_cap) return BMC_OK;
+  const size_t new_cap = std::max<size_t>(std::max<size_t>(2 * ctx->tab_cap, need), 1u << 16);
+  float *nd = nullptr, *nh = nullptr;
+  int rc;
+  if ((rc = dev_alloc(ctx, &nd, new_cap)) || (rc = dev_alloc(ctx, &nh, new_cap))) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemset(nd, 0, new_cap * 4)); CK(cudaMemset(nh, 0, new_cap * 4));
+  if (ctx->tab_cap) {
+    CK(cudaMemcpy(nd, ctx->d_tab_div, ctx->tab_cap * 4, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(nh, ctx->d_tab_hyd, ctx->tab_cap * 4, cudaMemcpyDeviceToDevice));
+  }
+  dev_free(ctx->d_tab_div); dev_free(ctx->d_tab_hyd);
+  ctx->d_tab_div = nd; ctx->d_tab_hyd = nh; ctx->tab_cap = new_cap;
+  return BMC_OK;
+}
+
+// start of an epoch (particles (re)loaded): stamps if every age is zero, floats otherwise
+static int begin_age_epoch(bmc_ctx* ctx, bool lazy) {
+  ctx->lazy_ages = lazy && !force_eager_ages();
+  ctx->epoch_set = false;
+  if (!ctx->lazy_ages) return BMC_OK;
+  int rc;
+  if ((rc = ensure_age_tables(ctx, 2))) return rc;
+  CK(cudaMemsetAsync(ctx->d_tab_div, 0, 8, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_tab_hyd, 0, 8, ctx->stream));
+  return BMC_OK;
+}
+
+// d_t / outlets changed (or the caller asked for it): turn the stamps into the floats they stand
+// for, in place, and continue with the eager kernel
+static int make_ages_eager(bmc_ctx* ctx) {
+  if (!ctx->lazy_ages) return BMC_OK;
+  if (ctx->cap) {
+    const unsigned grid = (unsigned)((ctx->cap + 255) / 256);
+    ages_to_eager_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->age_div, ctx->d_tab_div, (uint32_t)ctx->host_step, ctx->cap);
+    int rc;
+    if ((rc = check_launch(ctx, "ages_to_eager"))) return rc;
+    ages_to_eager_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->age_hyd, ctx->d_tab_hyd, (uint32_t)ctx->host_step, ctx->cap);
+    if ((rc = check_launch(ctx, "ages_to_eager"))) return rc;
+  }
+  ctx->lazy_ages = false;
+  return BMC_OK;
 }
 
 }  // namespace
@@ -323,6 +383,7 @@ int bmc_destroy(bmc_ctx** h) {
   dev_free(c->d_vol); dev_free(c->d_diag); dev_free(c->d_cdf);
   dev_free(c->d_ctab); dev_free(c->d_cdf_f); dev_free(c->d_neigh);
   dev_free(c->blk_total); dev_free(c->blk_gap); dev_free(c->blk_idle);
+  dev_free(c->d_tab_div); dev_free(c->d_tab_hyd);
   dev_free(c->st);
   if (c->d_stage) cudaFree(c->d_stage);
   for (int i = 0; i < 2; ++i) { if (c->h_st[i]) cudaFreeHost(c->h_st[i]); if (c->ev_mirror[i]) cudaEventDestroy(c->ev_mirror[i]); }
@@ -379,10 +440,21 @@ int bmc_set_particles(bmc_ctx* ctx, uint64_t n, const float* props, const uint64
     CK(cudaMemsetAsync(ctx->pos, 0, n * 4, s));
   }
   if (status) CK(cudaMemcpyAsync(ctx->status, status, n, cudaMemcpyHostToDevice, s)); else CK(cudaMemsetAsync(ctx->status, 0, n, s));
-  if (age_h) CK(cudaMemcpyAsync(ctx->age_hyd, age_h, n * 4, cudaMemcpyHostToDevice, s)); else CK(cudaMemsetAsync(ctx->age_hyd, 0, n * 4, s));
-  if (age_d) CK(cudaMemcpyAsync(ctx->age_div, age_d, n * 4, cudaMemcpyHostToDevice, s)); else CK(cudaMemsetAsync(ctx->age_div, 0, n * 4, s));
   // slots beyond n must be Idle (appended newborns rely on it)
   if (ctx->cap > n) CK(cudaMemsetAsync(ctx->status + n, 0, ctx->cap - n, s));
+  {
+    auto all_zero = [n](const float* a) { if (a) for (uint64_t i = 0; i < n; ++i) if (a[i] != 0.0f) return false; return true; };
+    if ((rc = begin_age_epoch(ctx, all_zero(age_h) && all_zero(age_d)))) return rc;
+    if (ctx->lazy_ages) {  // every age is zero: step stamps (0 for idle particles, frozen for the others)
+      if (n) {
+        ages_init_stamps_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ctx->status, ctx->age_hyd, ctx->age_div, n);
+        if ((rc = check_launch(ctx, "ages_init_stamps"))) return rc;
+      }
+    } else {
+      if (age_h) CK(cudaMemcpyAsync(ctx->age_hyd, age_h, n * 4, cudaMemcpyHostToDevice, s)); else CK(cudaMemsetAsync(ctx->age_hyd, 0, n * 4, s));
+      if (age_d) CK(cudaMemcpyAsync(ctx->age_div, age_d, n * 4, cudaMemcpyHostToDevice, s)); else CK(cudaMemsetAsync(ctx->age_div, 0, n * 4, s));
+    }
+  }
   if (status && n) {
     count_inactive_kernel<<<std::min<unsigned>(1024, (unsigned)((n + 255) / 256)), 256, 0, s>>>(ctx->status, n, ctx->st);
     if ((rc = check_launch(ctx, "count_inactive"))) return rc;
@@ -418,8 +490,22 @@ int bmc_get_particles(bmc_ctx* ctx, uint64_t n, float* props, uint64_t* position
     }
   }
   if (status) CK(cudaMemcpyAsync(status, ctx->status, n, cudaMemcpyDeviceToHost, s));
-  if (age_h) CK(cudaMemcpyAsync(age_h, ctx->age_hyd, n * 4, cudaMemcpyDeviceToHost, s));
-  if (age_d) CK(cudaMemcpyAsync(age_d, ctx->age_div, n * 4, cudaMemcpyDeviceToHost, s));
+  for (int a = 0; a < 2; ++a) {
+    float* out = a ? age_d : age_h;
+    const float* col = a ? ctx->age_div : ctx->age_hyd;
+    if (!out) continue;
+    if (!ctx->lazy_ages) { CK(cudaMemcpyAsync(out, col, n * 4, cudaMemcpyDeviceToHost, s)); continue; }
+    const size_t chunk = 1u << 23;  // stamps -> floats through the staging buffer
+    if ((rc = ensure_stage(ctx, std::min<size_t>(chunk, std::max<uint64_t>(n, 1)) * 4))) return rc;
+    for (size_t o = 0; o < n; o += chunk) {
+      const size_t c = std::min<size_t>(chunk, n - o);
+      ages_read_kernel<<<(unsigned)((c + 255) / 256), 256, 0, s>>>(col + o, a ? ctx->d_tab_div : ctx->d_tab_hyd, (uint32_t)ctx->host_step,
+                                                                  (float*)ctx->d_stage, c);
+      if ((rc = check_launch(ctx, "ages_read"))) return rc;
+      CK(cudaMemcpyAsync(out + o, ctx->d_stage, c * 4, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+    }
+  }
   CK(cudaStreamSynchronize(s));
   return BMC_OK;
 }
@@ -440,6 +526,7 @@ int bmc_init_particles(bmc_ctx* ctx, uint64_t n, int uniform_position, const flo
   }
   CK(cudaMemsetAsync(ctx->st, 0, sizeof(DevState), s));
   CK(cudaMemsetAsync(ctx->status, 0, ctx->cap, s));
+  if ((rc = begin_age_epoch(ctx, true))) return rc;  // init writes zero ages = stamp 0
   const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->n_sm * 8);
   InitParams ipar{ctx->props, ctx->cap, ctx->pos, ctx->status, ctx->age_hyd, ctx->age_div, n,
                   uniform_position ? (uint32_t)ctx->n_comp : 1u, d_linit, (uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32), ctx->rank, ctx->st};
@@ -611,9 +698,16 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   const uint32_t n_bins = (uint32_t)(ctx->n_species * ctx->n_comp);
   const bool enable_move = ctx->n_comp > 1;        // kernels.hpp:53-55
   const bool enable_leave = !ctx->flows.empty();   // kernels.hpp:56
+  if (ctx->lazy_ages) {
+    if (!ctx->epoch_set) { ctx->epoch_set = true; ctx->epoch_dt = d_t; ctx->epoch_leave = enable_leave; }
+    if (ctx->epoch_dt != d_t || ctx->epoch_leave != enable_leave || ctx->host_step >= 0x7ffffff0ull) {
+      if ((rc = make_ages_eager(ctx))) return rc;  // the stamps assume a constant increment per step
+    } else if ((rc = ensure_age_tables(ctx, ctx->host_step + 2))) return rc;
+  }
   PreParams pp;
   pp.st = ctx->st; pp.sources = ctx->d_sources; pp.n_bins = n_bins; pp.cap = ctx->cap; pp.buf_cap = ctx->buf_cap;
-  pp.grid_cycle = (unsigned)ctx->grid_cycle;
+  const int grid_cycle = ctx->lazy_ages ? ctx->grid_cycle : ctx->grid_cycle_eager;
+  pp.grid_cycle = (unsigned)grid_cycle;
   pp.diag = ctx->d_diag; pp.vol = ctx->d_vol; pp.dt = d_t; pp.conc = ctx->d_conc; pp.n_species = (uint32_t)ctx->n_species;
   pp.ctab = ctx->d_ctab; pp.n_comp = (uint32_t)ctx->n_comp; pp.enable_move = enable_move ? 1 : 0;
   pp.buf_mother = ctx->buf_mother; pp.div_mask = ctx->div_mask; pp.tile_div = ctx->tile_div;
@@ -652,7 +746,8 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
     CK(cudaEventRecord(e0, s));
   }
   void* cargs[] = {&p};
-  CK(cudaLaunchKernel(ctx->vt.cycle_fn, dim3(ctx->grid_cycle), dim3(kBlock), cargs, ctx->smem_total, s));
+  if (ctx->lazy_ages) CK(cudaLaunchKernel(ctx->vt.cycle_fn, dim3(grid_cycle), dim3(kBlock), cargs, ctx->smem_total, s));
+  else CK(cudaLaunchKernel(ctx->vt.cycle_eager_fn, dim3(grid_cycle), dim3(kBlock), cargs, ctx->smem_eager, s));
   if ((rc = check_launch(ctx, "cycle_kernel"))) return rc;
   if (ctx->profile) { CK(cudaEventRecord(e1, s)); ctx->prof_events.emplace_back(e0, e1); }
 
@@ -679,6 +774,9 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   ip.buf_props = ctx->buf_props; ip.buf_stride = ctx->buf_cap; ip.buf_pos = ctx->buf_pos; ip.buf_mother = ctx->buf_mother;
   ip.div_mask = ctx->div_mask; ip.tile_div = ctx->tile_div; ip.tile_off = ctx->tile_off; ip.blk_total = ctx->blk_total;
   ip.count_step = 1;
+  ip.newborn_stamp = ctx->lazy_ages ? (uint32_t)ctx->host_step + 1u : 0u;
+  ip.tab_div = ctx->d_tab_div; ip.tab_hyd = ctx->d_tab_hyd; ip.tab_idx = (uint32_t)ctx->host_step;
+  ip.tab_extend = ctx->lazy_ages ? 1 : 0; ip.enable_leave = enable_leave ? 1 : 0; ip.dt_f = (float)d_t; ip.dt = d_t;
   post_kernel<<<ctx->n_sm, 256, 0, s>>>(ip);
   if ((rc = check_launch(ctx, "post"))) return rc;
 

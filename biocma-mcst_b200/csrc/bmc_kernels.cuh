@@ -84,6 +84,24 @@ struct DevState {
 
 struct Outlet { uint32_t index; uint32_t pad; double flow; double dt_flow; double volume; };
 
+// -----------------------------------------------------------------------------
+// Step-stamped ages.  The reference adds d_t to both ages of every idle particle on every
+// step (ages(i,1) += float(d_t) model_kernel.hpp:191; ages(i,0) += d_t move_kernel.hpp:596) —
+// 16 bytes of HBM traffic per particle-step for values no kernel ever reads.  While d_t and
+// the outlet configuration are constant and every age started at zero, the age of a particle
+// is a pure function of the number of steps since it was last reset, BITWISE: the k-fold
+// floating-point accumulation A[k] = fl(A[k-1] + d_t) is the same for every particle.  The age
+// columns then hold 32-bit step stamps
+//     idle particle :  s            age = A[now - s]   (s = first step that ages the particle)
+//     frozen        :  kFrozen | k  age = A[k]         (exited particle: no longer updated)
+// which are written only when an age is reset (division, birth, exit).  A_div / A_hyd are
+// extended by one entry per step on the device (post_kernel) and applied when ages are read
+// (bmc_get_particles) — bit-identical to the eager accumulation.  If d_t or the outlet
+// configuration changes, or the caller supplies non-zero ages, the columns are converted to
+// floats in place and the eager kernel variant (LAZY = false) takes over.
+// -----------------------------------------------------------------------------
+constexpr uint32_t kFrozen = 0x80000000u;
+
 struct CycleParams {
   // particle SoA columns (ParticlesContainer views, particles_container.hpp:82-88)
   float* props; size_t cap;
@@ -142,6 +160,7 @@ template <> struct VecIO<4> {
     const uint4 t = BMC_LD(reinterpret_cast<const uint4*>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
   static __device__ __forceinline__ uint32_t ldb(const uint8_t* p) { return BMC_LD(reinterpret_cast<const unsigned int*>(p)); }
+  static __device__ __forceinline__ uint32_t ldb_plain(const uint8_t* p) { return *reinterpret_cast<const unsigned int*>(p); }
   static __device__ __forceinline__ void ldf_plain(const float* p, float (&v)[4]) {
     const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
@@ -158,6 +177,7 @@ template <> struct VecIO<2> {
     const uint2 t = BMC_LD(reinterpret_cast<const uint2*>(p)); v[0] = t.x; v[1] = t.y;
   }
   static __device__ __forceinline__ uint32_t ldb(const uint8_t* p) { return BMC_LD(reinterpret_cast<const unsigned short*>(p)); }
+  static __device__ __forceinline__ uint32_t ldb_plain(const uint8_t* p) { return *reinterpret_cast<const unsigned short*>(p); }
   static __device__ __forceinline__ void ldf_plain(const float* p, float (&v)[2]) {
     const float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y;
   }
@@ -170,6 +190,7 @@ template <> struct VecIO<1> {
   static __device__ __forceinline__ void stf(float* p, const float (&v)[1]) { BMC_ST(p, v[0]); }
   static __device__ __forceinline__ void ldu(const uint32_t* p, uint32_t (&v)[1]) { v[0] = BMC_LD(p); }
   static __device__ __forceinline__ uint32_t ldb(const uint8_t* p) { return BMC_LD(p); }
+  static __device__ __forceinline__ uint32_t ldb_plain(const uint8_t* p) { return *p; }
   static __device__ __forceinline__ void ldf_plain(const float* p, float (&v)[1]) { v[0] = *p; }
   static __device__ __forceinline__ void ldu_plain(const uint32_t* p, uint32_t (&v)[1]) { v[0] = *p; }
 };
@@ -274,28 +295,58 @@ __device__ __forceinline__ void make_plan(DevState* st, unsigned long long min_r
 // chains interleave; everything rare (division, the neighbour pick of a mover,
 // the outlet exit draw, partially idle groups) sits behind warp-level votes.
 // -----------------------------------------------------------------------------
-__host__ __device__ constexpr int popcount_c(uint32_t x) { return x == 0u ? 0 : (int)(x & 1u) + popcount_c(x >> 1); }
+__host__ __device__ constexpr int popcount_c(uint64_t x) { return x == 0u ? 0 : (int)(x & 1u) + popcount_c(x >> 1); }
+__host__ __device__ constexpr bool col_flag(uint64_t mask, int k) { return ((mask >> k) & 1ull) != 0ull; }  // k < 64
 // columns actually loaded per slot: every property that is not write-only
 template <class M> struct ReadCols {
-  static constexpr uint32_t all = M::n_var >= 32 ? 0xffffffffu : ((1u << M::n_var) - 1u);
-  static constexpr int value = M::n_var - popcount_c(M::write_only_mask & all);
+  static_assert(M::n_var <= 64, "at most 64 properties per particle");
+  static constexpr uint64_t all = M::n_var >= 64 ? ~0ull : ((1ull << M::n_var) - 1ull);
+  static constexpr int value = M::n_var - popcount_c((uint64_t)M::write_only_mask & all);
 };
-// bytes of one staging buffer of the software pipeline: pos, age_div, age_hyd + the read columns
-template <class M, int VEC> struct StageBytes { static constexpr size_t value = (size_t)(3 + ReadCols<M>::value) * kBlock * 4 * VEC; };
+// One staging buffer of the bulk-copy pipeline holds one GROUP = kBlock*VEC consecutive slots:
+// pos and the read columns (kBlock*VEC*4 bytes each), then the status bytes.  (The pipeline is
+// built for step-stamped ages only, so no age column is staged.)
+template <class M, int VEC> struct StageBytes {
+  static constexpr size_t col = (size_t)kBlock * 4 * VEC;
+  static constexpr size_t value = (size_t)(1 + ReadCols<M>::value) * col + (size_t)kBlock * VEC;
+};
+constexpr int kStages = 2;
 
-template <int BYTES> __device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
+// ---- mbarrier + TMA bulk copy (cp.async.bulk, 1-D; SASS: UBLKCP) --------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(a), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
 
-template <class M, int VEC, bool PIPE> __device__ __forceinline__ void cycle_body(const CycleParams& p) {
+template <class M, int VEC, bool PIPE, bool LAZY> __device__ __forceinline__ void cycle_body(const CycleParams& p) {
+  static_assert(!PIPE || LAZY, "the bulk-copy pipeline is built for step-stamped ages only");
   constexpr int NV = M::n_var, NC = M::n_c, CT = 1 + M::n_pre;
   constexpr int SUB = kTile / (kBlock * VEC);  // sub-iterations per tile
   constexpr int kColStride = kBlock * 4 * VEC;  // bytes between staged columns
   constexpr size_t kStage = StageBytes<M, VEC>::value;
-  extern __shared__ double s_bins[];           // [n_species * n_comp] when bins_in_smem, then 2 staging buffers
+  extern __shared__ __align__(128) double s_bins[];  // [n_species * n_comp] when bins_in_smem, then kStages staging buffers
   __shared__ unsigned long long s_cnt[4];      // move, exit, new, overflow
 
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -319,31 +370,36 @@ template <class M, int VEC, bool PIPE> __device__ __forceinline__ void cycle_bod
   for (int j = 0; j < NC; ++j) acc0d[j] = 0.0;
   const double w = (double)p.weight;  // `const double weight = get_weight(p)` contribution_kernel.hpp:179
   const BufRows bufrows{p.buf_props, p.buf_stride};
+  // LAZY: the age columns hold step stamps instead of floats (see "Step-stamped ages" below)
+  uint32_t* const stamps_hyd = reinterpret_cast<uint32_t*>(p.age_hyd);
+  uint32_t* const stamps_div = reinterpret_cast<uint32_t*>(p.age_div);
+  (void)stamps_hyd; (void)stamps_div;
   const uint32_t outlet0 = p.n_flows > 0 ? p.outlets[0].index : 0xffffffffu;
   const bool outlet0_live = p.n_flows > 0 && p.outlets[0].flow != 0.;
 
-  // PIPE: two-stage software pipeline.  Each thread copies ITS OWN next group of slots
-  // global -> shared with cp.async (LDGSTS: no registers held while the bytes are in flight),
-  // then computes the current group out of shared memory.  A thread only ever reads what it
-  // copied itself, so cp.async.wait_group is the only synchronisation needed.
+  // PIPE: two-stage bulk-copy pipeline.  One elected thread arms the stage's mbarrier with the byte
+  // count and issues one cp.async.bulk (TMA, 1-D) per column for the NEXT group of kBlock*VEC
+  // slots; the bytes land in shared memory while the block computes the current group, so the
+  // HBM latency is off the critical path and no registers are held by loads in flight.  Thread t
+  // then reads bytes [t*4*VEC, (t+1)*4*VEC) of every staged column (conflict-free LDS.128).
   unsigned char* const s_stage = reinterpret_cast<unsigned char*>(s_bins) + p.stage_offset;
+  __shared__ __align__(8) unsigned long long s_bar[kStages];
   const uint32_t n_used32 = (uint32_t)n_used;
   auto slot_base = [&](uint32_t tile, int sub) -> uint32_t {
     return tile * (uint32_t)kTile + ((uint32_t)sub * (kBlock / 32) + warp) * (32 * VEC) + lane * VEC;
   };
-  auto issue = [&](uint32_t it, int buf) -> uint32_t {  // returns the status bytes of that group
-    const uint32_t i_raw = slot_base(t0 + it / SUB, (int)(it % SUB));
-    const size_t i0 = i_raw < n_used32 ? i_raw : 0u;
-    unsigned char* dst = s_stage + (size_t)buf * kStage + threadIdx.x * (4 * VEC);
-    cp_async<4 * VEC>(dst, p.pos + i0);
-    cp_async<4 * VEC>(dst + kColStride, p.age_div + i0);
-    if (p.enable_leave) cp_async<4 * VEC>(dst + 2 * kColStride, p.age_hyd + i0);
-    int c = 3;
+  constexpr unsigned kColBytes = (unsigned)kColStride;
+  auto issue = [&](uint32_t it, int buf) {  // executed by thread 0 only
+    const size_t g0 = (size_t)(t0 * SUB + it) * (kBlock * VEC);  // first slot of the group (whole group < capacity)
+    unsigned char* dst = s_stage + (size_t)buf * kStage;
+    unsigned long long* bar = &s_bar[buf];
+    mbar_expect_tx(bar, (unsigned)kStage);
+    bulk_g2s(dst, p.pos + g0, kColBytes, bar);
+    int c = 1;
 #pragma unroll
     for (int k = 0; k < NV; ++k)
-      if (!((M::write_only_mask >> k) & 1u)) { cp_async<4 * VEC>(dst + c * kColStride, p.props + (size_t)k * p.cap + i0); ++c; }
-    cp_async_commit();
-    return VecIO<VEC>::ldb(p.status + i0);
+      if (!col_flag(M::write_only_mask, k)) { bulk_g2s(dst + c * kColStride, p.props + (size_t)k * p.cap + g0, kColBytes, bar); ++c; }
+    bulk_g2s(dst + (size_t)(1 + ReadCols<M>::value) * kColStride, p.status + g0, (unsigned)(kBlock * VEC), bar);
   };
 
   {
@@ -358,21 +414,16 @@ template <class M, int VEC, bool PIPE> __device__ __forceinline__ void cycle_bod
       uint32_t pos[VEC]; float adiv[VEC], ahyd[VEC]; float v[VEC][NV], old[VEC][NV];
       uint32_t stw;
       if constexpr (PIPE) {
-        // ---- operands were staged in shared memory by this thread one iteration ago ----
-        const unsigned char* src = s_stage + (size_t)buf * kStage + threadIdx.x * (4 * VEC);
-        stw = stw_in;
+        // ---- operands were staged in shared memory by the bulk copies issued one iteration ago ----
+        const unsigned char* stage = s_stage + (size_t)buf * kStage;
+        const unsigned char* src = stage + threadIdx.x * (4 * VEC);
+        stw = VecIO<VEC>::ldb_plain(stage + (size_t)(1 + ReadCols<M>::value) * kColStride + threadIdx.x * VEC);
         VecIO<VEC>::ldu_plain(reinterpret_cast<const uint32_t*>(src), pos);
-        VecIO<VEC>::ldf_plain(reinterpret_cast<const float*>(src + kColStride), adiv);
-        if (p.enable_leave) VecIO<VEC>::ldf_plain(reinterpret_cast<const float*>(src + 2 * kColStride), ahyd);
-        else {
-#pragma unroll
-          for (int q = 0; q < VEC; ++q) ahyd[q] = 0.f;
-        }
-        int c = 3;
+        int c = 1;
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
           float col[VEC];
-          if ((M::write_only_mask >> k) & 1u) {
+          if (col_flag(M::write_only_mask, k)) {
 #pragma unroll
             for (int q = 0; q < VEC; ++q) col[q] = 0.f;
           } else {
@@ -383,19 +434,17 @@ template <class M, int VEC, bool PIPE> __device__ __forceinline__ void cycle_bod
           for (int q = 0; q < VEC; ++q) { v[q][k] = col[q]; old[q][k] = col[q]; }
         }
       } else {
-        // ---- front-batched global loads (all independent; MLP = 4 + #columns read) ----
+        // ---- front-batched global loads (all independent) ----
         stw = VecIO<VEC>::ldb(p.status + i0);
         VecIO<VEC>::ldu(p.pos + i0, pos);
-        VecIO<VEC>::ldf(p.age_div + i0, adiv);
-        if (p.enable_leave) VecIO<VEC>::ldf(p.age_hyd + i0, ahyd);
-        else {
-#pragma unroll
-          for (int q = 0; q < VEC; ++q) ahyd[q] = 0.f;
+        if constexpr (!LAZY) {
+          VecIO<VEC>::ldf(p.age_div + i0, adiv);
+          if (p.enable_leave) VecIO<VEC>::ldf(p.age_hyd + i0, ahyd);
         }
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
           float col[VEC];
-          if ((M::write_only_mask >> k) & 1u) {
+          if (col_flag(M::write_only_mask, k)) {
 #pragma unroll
             for (int q = 0; q < VEC; ++q) col[q] = 0.f;
           } else {
@@ -405,12 +454,18 @@ template <class M, int VEC, bool PIPE> __device__ __forceinline__ void cycle_bod
           for (int q = 0; q < VEC; ++q) { v[q][k] = col[q]; old[q][k] = col[q]; }
         }
       }
-      uint32_t pos_old[VEC]; float adiv_old[VEC], ahyd_old[VEC];
+      if (LAZY || !p.enable_leave) {
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) ahyd[q] = 0.f;
+      }
+      if constexpr (LAZY) {
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) adiv[q] = 0.f;
+      }
       bool idle[VEC];
       unsigned valid_m = 0, idle_m = 0;
 #pragma unroll
       for (int q = 0; q < VEC; ++q) {
-        pos_old[q] = pos[q]; adiv_old[q] = adiv[q]; ahyd_old[q] = ahyd[q];
         const bool valid = FULL || (live && (i0 + q) < n_used);
         idle[q] = valid && (((stw >> (8 * q)) & 0xffu) == (unsigned)Idle);
         valid_m |= (unsigned)valid << q; idle_m |= (unsigned)idle[q] << q;
@@ -441,7 +496,7 @@ template <class M, int VEC, bool PIPE> __device__ __forceinline__ void cycle_bod
       unsigned div_nib = 0;
 #pragma unroll
       for (int q = 0; q < VEC; ++q) {
-        adiv[q] = idle[q] ? adiv[q] + p.dt_f : adiv[q];  // ages(i,1) += _d_t  (model_kernel.hpp:191)
+        if constexpr (!LAZY) adiv[q] = idle[q] ? adiv[q] + p.dt_f : adiv[q];  // ages(i,1) += _d_t  (model_kernel.hpp:191)
         Gen gen(p.seed_lo, p.seed_hi, p.rank, (uint32_t)(i0 + q), p.step, 2u);
         const ConcView conc{p.conc, p.n_species, &ctab[q][1]};
         const Status s = M::update(gen, p.dt_f, i0 + q, RegRow{v[q]}, RegRow{contrib[q]}, (size_t)pos[q], conc);
@@ -495,7 +550,8 @@ template <class M, int VEC, bool PIPE> __device__ __forceinline__ void cycle_bod
               M::division(gen, i0 + q, (size_t)j, RegRow{v[q]}, bufrows);
               p.buf_pos[j] = pos[q];               // buffer_position(idx2) = position(idx1): pre-move
               p.buf_mother[j] = (uint32_t)(i0 + q);
-              adiv[q] = 0.f;                       // ages(idx1,1) = 0
+              if constexpr (LAZY) stamps_div[i0 + q] = p.step + 1u;  // ages(idx1,1) = 0: counts from the next step
+              else adiv[q] = 0.f;                                    // ages(idx1,1) = 0
               ok_nib |= 1u << q;
             } else {
               ++c_over;  // waiting_allocation_particle / Overflow (model_kernel.hpp:253-258)
@@ -513,6 +569,7 @@ template <class M, int VEC, bool PIPE> __device__ __forceinline__ void cycle_bod
       }
 
       // ---- move (all slots, no status check: move_kernel.hpp:392-437) --------
+      unsigned moved = 0;
       if (p.enable_move) {
         unsigned mv = 0;
 #pragma unroll
@@ -521,6 +578,7 @@ template <class M, int VEC, bool PIPE> __device__ __forceinline__ void cycle_bod
           mv |= (unsigned)(u1 < ctab[q][0]) << q;  // (dt*flow/volume) > rng1
         }
         mv &= valid_m;
+        moved = mv;
         // movers are rare (dt*F/V ~ 1e-2): their neighbour pick draws its own block
         while (mv) {
           const int q = __ffs(mv) - 1;
@@ -550,7 +608,7 @@ template <class M, int VEC, bool PIPE> __device__ __forceinline__ void cycle_bod
         unsigned in_outlet = 0; int fsel[VEC];
 #pragma unroll
         for (int q = 0; q < VEC; ++q) {
-          ahyd[q] = idle[q] ? (float)((double)ahyd[q] + p.dt) : ahyd[q];  // ages(idx,0) += d_t (double)
+          if constexpr (!LAZY) ahyd[q] = idle[q] ? (float)((double)ahyd[q] + p.dt) : ahyd[q];  // ages(idx,0) += d_t (double)
           fsel[q] = 0;
         }
         if (p.n_flows == 1) {  // the usual case (0D reactor or a single outlet, move_kernel.hpp:113)
@@ -573,7 +631,14 @@ template <class M, int VEC, bool PIPE> __device__ __forceinline__ void cycle_bod
               const float lnu = (float)log((double)u3);  // Kokkos::log(float), see oracle ln_f32
               const Outlet& o = p.outlets[fsel[q]];
               if (o.dt_flow > (double)(-lnu) * o.volume) {  // probability_leaving<precision_tag>
-                ahyd[q] = ahyd[q] * 0.0f;                   // ages(idx,0) *= (1 - leave_mask)
+                if constexpr (LAZY) {
+                  // the particle stops ageing: freeze the step counts (age_hyd = 0, age_div as of this step)
+                  stamps_hyd[i0 + q] = kFrozen;
+                  const uint32_t sd = stamps_div[i0 + q];
+                  stamps_div[i0 + q] = (sd & kFrozen) ? sd : (kFrozen | (p.step + 1u - sd));
+                } else {
+                  ahyd[q] = ahyd[q] * 0.0f;                 // ages(idx,0) *= (1 - leave_mask)
+                }
                 exit_nib |= 1u << q;
                 ++c_exit;
               }
@@ -582,7 +647,10 @@ template <class M, int VEC, bool PIPE> __device__ __forceinline__ void cycle_bod
         }
       }
 
-      // ---- write back only what changed -------------------------------------
+      // ---- write back ---------------------------------------------------------
+      // Columns the model assigns on every update (always_written_mask, which includes the
+      // write-only ones) are stored whenever the thread has an idle slot; the others only if a
+      // value changed bitwise (the comparison folds away for columns the hooks never assign).
       const bool all_idle = (idle_m == kAll);
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
@@ -591,7 +659,7 @@ template <class M, int VEC, bool PIPE> __device__ __forceinline__ void cycle_bod
         for (int q = 0; q < VEC; ++q) col[q] = v[q][k];
         float* dst = p.props + (size_t)k * p.cap + i0;
         bool ch = false;
-        if ((M::write_only_mask >> k) & 1u) ch = idle_m != 0u;
+        if (col_flag(M::write_only_mask | M::always_written_mask, k)) ch = idle_m != 0u;
         else {
 #pragma unroll
           for (int q = 0; q < VEC; ++q) ch = ch || (idle[q] && __float_as_uint(v[q][k]) != __float_as_uint(old[q][k]));
@@ -604,18 +672,16 @@ template <class M, int VEC, bool PIPE> __device__ __forceinline__ void cycle_bod
           }
         }
       }
-      bool ch_ad = false, ch_ah = false, ch_pos = false;
-#pragma unroll
-      for (int q = 0; q < VEC; ++q) {
-        ch_ad = ch_ad || (__float_as_uint(adiv[q]) != __float_as_uint(adiv_old[q]));
-        ch_ah = ch_ah || (__float_as_uint(ahyd[q]) != __float_as_uint(ahyd_old[q]));
-        ch_pos = ch_pos || (pos[q] != pos_old[q]);
+      if constexpr (!LAZY) {
+        // eager ages change for every idle particle; non-idle lanes rewrite the value they loaded
+        if (idle_m) {
+          VecIO<VEC>::stf(p.age_div + i0, adiv);
+          if (p.enable_leave) VecIO<VEC>::stf(p.age_hyd + i0, ahyd);
+        }
       }
-      if (ch_ad) VecIO<VEC>::stf(p.age_div + i0, adiv);  // unchanged lanes rewrite their own value
-      if (ch_ah) VecIO<VEC>::stf(p.age_hyd + i0, ahyd);
-      if (ch_pos) {  // Q14: position written only when it changed (never for slots >= n_used: mv is masked)
+      if (moved) {  // Q14: position written only for movers (never for slots >= n_used: mv is masked)
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) if (pos[q] != pos_old[q] && ((valid_m >> q) & 1u)) p.pos[i0 + q] = pos[q];
+        for (int q = 0; q < VEC; ++q) if ((moved >> q) & 1u) p.pos[i0 + q] = pos[q];
       }
       if (exit_nib) {
 #pragma unroll
@@ -624,15 +690,23 @@ template <class M, int VEC, bool PIPE> __device__ __forceinline__ void cycle_bod
     };
     if constexpr (PIPE) {
       const uint32_t n_it = (t1 - t0) * SUB;
-      uint32_t stw_next = n_it ? issue(0, 0) : 0u;
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int b = 0; b < kStages; ++b) mbar_init(&s_bar[b], 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+      __syncthreads();
+      if (threadIdx.x == 0 && n_it) issue(0, 0);
 #pragma unroll 1
       for (uint32_t it = 0; it < n_it; ++it) {
-        const uint32_t stw_cur = stw_next;
-        if (it + 1 < n_it) { stw_next = issue(it + 1, (int)((it + 1) & 1u)); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
+        const int buf = (int)(it & 1u);
+        // every thread is done reading the other buffer (iteration it-1): it may be refilled
+        __syncthreads();
+        if (threadIdx.x == 0 && it + 1 < n_it) issue(it + 1, buf ^ 1);
+        mbar_wait(&s_bar[buf], (it >> 1) & 1u);
         const uint32_t tile = t0 + it / SUB;
-        if ((unsigned long long)(tile + 1) * kTile <= n_used) body(FullTile{}, tile, (int)(it % SUB), (int)(it & 1u), stw_cur);
-        else body(RaggedTile{}, tile, (int)(it % SUB), (int)(it & 1u), stw_cur);
+        if ((unsigned long long)(tile + 1) * kTile <= n_used) body(FullTile{}, tile, (int)(it % SUB), buf, 0u);
+        else body(RaggedTile{}, tile, (int)(it % SUB), buf, 0u);
       }
     } else {
 #pragma unroll 1
@@ -737,8 +811,8 @@ template <class M> __device__ __forceinline__ void init_body(const InitParams& p
 // __global__ entry points of the built-in models (the NVRTC path of user models wraps the same
 // bodies in extern "C" kernels, see bmc_udf.cu)
 template <class M> __global__ void __launch_bounds__(256) pre_step_kernel(const __grid_constant__ PreParams p) { pre_step_body<M>(p); }
-template <class M, int VEC, int MINB, bool PIPE>
-__global__ void __launch_bounds__(kBlock, MINB) cycle_kernel(const __grid_constant__ CycleParams p) { cycle_body<M, VEC, PIPE>(p); }
+template <class M, int VEC, int MINB, bool PIPE, bool LAZY>
+__global__ void __launch_bounds__(kBlock, MINB) cycle_kernel(const __grid_constant__ CycleParams p) { cycle_body<M, VEC, PIPE, LAZY>(p); }
 template <class M> __global__ void __launch_bounds__(256) init_kernel(const __grid_constant__ InitParams p) { init_body<M>(p); }
 
 }  // namespace bmc

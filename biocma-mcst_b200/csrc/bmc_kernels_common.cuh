@@ -174,6 +174,10 @@ struct InsertParams {
   const float* buf_props; size_t buf_stride; const uint32_t* buf_pos; const uint32_t* buf_mother;
   uint32_t* div_mask; uint32_t* tile_div; const uint32_t* tile_off; const uint32_t* blk_total;
   int count_step;  // 1 when called from a cycle, 0 from force_remove_dead
+  // step-stamped ages (bmc_kernels.cuh): stamp given to newborns (0 = eager float ages, bits of 0.f)
+  // and the per-step extension of the age tables A_div / A_hyd
+  uint32_t newborn_stamp;
+  float* tab_div; float* tab_hyd; uint32_t tab_idx; int tab_extend; int enable_leave; float dt_f; double dt;
 };
 
 __global__ void __launch_bounds__(256) post_kernel(const __grid_constant__ InsertParams p) {
@@ -207,7 +211,9 @@ __global__ void __launch_bounds__(256) post_kernel(const __grid_constant__ Inser
       const unsigned long long dst = base + s_pref[b] + p.tile_off[tile] + rank;
       for (int c = 0; c < p.n_var; ++c) p.props[(size_t)c * p.cap + dst] = p.buf_props[(size_t)c * p.buf_stride + j];
       p.pos[dst] = p.buf_pos[j];
-      p.age_hyd[dst] = 0.f; p.age_div[dst] = 0.f;  // InsertFunctor: both ages reset
+      // InsertFunctor: both ages reset (eager: 0.f; stamped: the newborn ages from the next step on)
+      reinterpret_cast<uint32_t*>(p.age_hyd)[dst] = p.newborn_stamp;
+      reinterpret_cast<uint32_t*>(p.age_div)[dst] = p.newborn_stamp;
       p.status[dst] = (uint8_t)Idle;
     }
   }
@@ -219,6 +225,34 @@ __global__ void __launch_bounds__(256) post_kernel(const __grid_constant__ Inser
     st->total_new += n_add;
     if (n_add > st->clear_n) st->clear_n = n_add;  // bits cleared by the next pre_step
     st->step += (unsigned long long)p.count_step;
+    if (p.tab_extend) {  // A[k+1] = fl(A[k] + d_t): exactly the accumulation an eagerly updated age goes through
+      p.tab_div[p.tab_idx + 1] = p.tab_div[p.tab_idx] + p.dt_f;                       // model_kernel.hpp:191 (float d_t)
+      p.tab_hyd[p.tab_idx + 1] = p.enable_leave ? (float)((double)p.tab_hyd[p.tab_idx] + p.dt)  // move_kernel.hpp:596 (double d_t)
+                                                : p.tab_hyd[p.tab_idx];
+    }
+  }
+}
+
+// ---- step-stamped ages -> floats -------------------------------------------------
+__device__ __forceinline__ float age_from_stamp(uint32_t s, const float* tab, uint32_t now) {
+  uint32_t k = (s & kFrozen) ? (s & ~kFrozen) : now - s;
+  if (k > now) k = now;  // slots beyond n_used hold unspecified stamps: stay inside the table
+  return tab[k];
+}
+__global__ void ages_read_kernel(const float* col, const float* tab, uint32_t now, float* out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = age_from_stamp(reinterpret_cast<const uint32_t*>(col)[i], tab, now);
+}
+__global__ void ages_to_eager_kernel(float* col, const float* tab, uint32_t now, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) col[i] = age_from_stamp(reinterpret_cast<const uint32_t*>(col)[i], tab, now);
+}
+__global__ void ages_init_stamps_kernel(const uint8_t* status, float* age_hyd, float* age_div, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const uint32_t s = status[i] == (uint8_t)Idle ? 0u : kFrozen;  // non-idle particles never age
+    reinterpret_cast<uint32_t*>(age_hyd)[i] = s;
+    reinterpret_cast<uint32_t*>(age_div)[i] = s;
   }
 }
 

@@ -10,10 +10,11 @@ namespace bmc {
 struct ModelVT {
   int n_var, n_c, vec, minb;
   int ct;              // floats per compartment-table row
-  size_t stage_bytes;  // dynamic shared memory of the cp.async pipeline (0 = direct loads)
+  size_t stage_bytes;  // dynamic shared memory of the bulk-copy pipeline (0 = direct loads)
   // kernel handles: addresses of __global__ instantiations, or cudaKernel_t of a JIT-compiled
   // user model; all launched with cudaLaunchKernel(handle, grid, block, {&params}, smem, stream)
-  const void* cycle_fn;   // (CycleParams)  block = kBlock
+  const void* cycle_fn;   // (CycleParams)  block = kBlock; step-stamped ages (bmc_kernels.cuh)
+  const void* cycle_eager_fn;  // same with float ages updated every step (direct loads, no staging)
   const void* pre_fn;     // (PreParams)    block = 256
   const void* init_fn;    // (InitParams)   block = 256
   void* jit_library;      // cudaLibrary_t of a user model (unloaded with the context), else nullptr
@@ -23,24 +24,32 @@ template <class M, int VEC, int MINB = 1, bool PIPE = false> static ModelVT make
   ModelVT v;
   v.n_var = M::n_var; v.n_c = M::n_c; v.vec = VEC; v.minb = MINB;
   v.ct = 1 + M::n_pre;
-  v.stage_bytes = PIPE ? 2 * StageBytes<M, VEC>::value : 0;
-  v.cycle_fn = (const void*)cycle_kernel<M, VEC, MINB, PIPE>;
+  v.stage_bytes = PIPE ? kStages * StageBytes<M, VEC>::value : 0;
+  v.cycle_fn = (const void*)cycle_kernel<M, VEC, MINB, PIPE, true>;
+  v.cycle_eager_fn = (const void*)cycle_kernel<M, VEC, (MINB > 3 ? 3 : MINB), false, false>;
   v.pre_fn = (const void*)pre_step_kernel<M>;
   v.init_fn = (const void*)init_kernel<M>;
   v.jit_library = nullptr;
   return v;
 }
 
-// Kernel variant = (slots per thread, min resident blocks per SM[, cp.async pipeline]).  Defaults
-// were picked from sweeps on a B200 (tools/sweep.py); BMC_VARIANT="v<VEC>b<MINB>"
-// overrides MINB for tuning runs ("p<VEC>b3" selects the cp.async pipeline where it is built).
-template <class M, int VEC, bool WITH_PIPE = false> static bool pick_variant(const std::string& var, int def_minb, ModelVT& vt) {
-  int minb = def_minb; bool pipe = false;
+// Kernel variant = (slots per thread, min resident blocks per SM, load path).  Defaults were
+// picked from sweeps on a B200 (tools/sweep.py).  BMC_VARIANT="v<VEC>b<MINB>" selects
+// direct global loads, "p<VEC>b<MINB>" the TMA bulk-copy pipeline (where it is built).
+template <class M, int VEC, bool WITH_PIPE = false> static bool pick_variant(const std::string& var, int def_minb, ModelVT& vt,
+                                                                            bool def_pipe = false) {
+  int minb = def_minb; bool pipe = def_pipe && WITH_PIPE;
   if (var.size() == 4 && (var[0] == 'v' || var[0] == 'p') && var[2] == 'b' && var[1] - '0' == VEC) {
     minb = var[3] - '0'; pipe = var[0] == 'p';
   }
   if constexpr (WITH_PIPE) {
-    if (pipe) { vt = make_vt<M, VEC, 3, true>(); return true; }
+    if (pipe) {
+      switch (minb) {
+        case 1: case 2: vt = make_vt<M, VEC, 2, true>(); return true;
+        case 3: vt = make_vt<M, VEC, 3, true>(); return true;
+        default: vt = make_vt<M, VEC, 4, true>(); return true;
+      }
+    }
   }
   switch (minb) {
     case 1: case 2: vt = make_vt<M, VEC, 2>(); return true;

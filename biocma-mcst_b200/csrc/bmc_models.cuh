@@ -19,6 +19,9 @@
 //   write_only_mask : bit k set => property k is never read by update/division
 //                     before being written; the kernel then skips loading that
 //                     column (SURVEY.md §8d algorithmic bytes).
+//   always_written_mask : bit k set => update assigns property k on every call; the
+//                     kernel then stores the column without comparing old and new
+//                     values (fewer registers and instructions).  0 is always valid.
 //   n_pre + compartment_terms(c, position, out[n_pre]) : sub-expressions of update
 //                     that depend on the local concentration only; evaluated once
 //                     per compartment per step and handed back through c.term(k).
@@ -101,8 +104,8 @@ __device__ __forceinline__ double lognormal(Gen& g, double mu, double sigma) { r
 // =============================================================================
 struct FixedLength {
   static constexpr int n_var = 2, n_c = 1, n_pre = 1;
-  static constexpr uint32_t write_only_mask = 0u;
   enum particle_var { length = 0, l_max = 1 };
+  static constexpr uint64_t write_only_mask = 0u, always_written_mask = 1u << length;
   static constexpr float l_dot_max = (float)(2e-6 / 3600.);
   static constexpr float l_max_m = (float)2e-6;
   static constexpr float k = (float)1e-3;
@@ -151,7 +154,8 @@ struct FixedLength {
 struct Monod {
   static constexpr int n_var = 6, n_c = 1, n_pre = 1;
   enum particle_var { l = 0, l_max, mu_p, mue, cell_lenghtening, phi_s_c };
-  static constexpr uint32_t write_only_mask = (1u << mue) | (1u << phi_s_c);
+  static constexpr uint64_t write_only_mask = (1u << mue) | (1u << phi_s_c);
+  static constexpr uint64_t always_written_mask = (1u << l) | (1u << mu_p) | write_only_mask;
   static constexpr float y_s_x = 2.0f;
   static constexpr float mu_max = (float)(0.77 / 3600.);
   static constexpr float tau_meta = (float)(1. / mu_max);
@@ -211,7 +215,8 @@ struct SimpleAcetate {
   static constexpr int n_var = 9, n_c = 2, n_pre = 0;
   enum particle_var { length = 0, l_max, a_p, a_max, a_e, a_e_s, a_e_a, phi_s, phi_a };
   // a_e is read by division AFTER update wrote it in the same cycle -> still write-only for loading
-  static constexpr uint32_t write_only_mask = (1u << a_e) | (1u << a_e_s) | (1u << a_e_a) | (1u << phi_s) | (1u << phi_a);
+  static constexpr uint64_t write_only_mask = (1u << a_e) | (1u << a_e_s) | (1u << a_e_a) | (1u << phi_s) | (1u << phi_a);
+  static constexpr uint64_t always_written_mask = (1u << length) | write_only_mask;
   static constexpr float a_max_m = (float)(2e-6 / 3600.);
   static constexpr float l_max_m = (float)2e-6;
   static constexpr float l_min_m = (float)(l_max_m / 2.);
@@ -296,7 +301,8 @@ struct SimpleAcetate {
 // =============================================================================
 template <int P> struct WideUdf {
   static constexpr int n_var = P, n_c = 4, n_pre = 4;
-  static constexpr uint32_t write_only_mask = 0u;
+  static constexpr uint64_t write_only_mask = 0u;
+  static constexpr uint64_t always_written_mask = (P >= 64 ? ~0ull : ((1ull << P) - 1ull)) & ~2ull;  // all but l_max
   enum { length = 0, l_max = 1, first_pool = 2 };
   static constexpr float l_dot_max = (float)(2e-6 / 3600.);
   static constexpr float lin_density = c_linear_density(1000.0f, (float)0.6e-6);

@@ -35,8 +35,11 @@
 // normal), obtained as in the reference: `auto gen = random_pool.get_state();
 // ... random_pool.free_state(gen);`.
 //
-// Optional hints (extensions): BMC_UDF_WRITE_ONLY_MASK (bit k = property k is never
-// read before being written, so its column is not loaded).
+// Optional hints (extensions, #define before including this header):
+//   BMC_UDF_WRITE_ONLY_MASK      bit k = property k is never read before being written, so its
+//                                column is not loaded
+//   BMC_UDF_ALWAYS_WRITTEN_MASK  bit k = update assigns property k on every call, so the column
+//                                is stored without an old/new comparison
 #pragma once
 #include "bmc_kernels.cuh"
 
@@ -106,6 +109,9 @@ template <class F> __device__ __forceinline__ MC::Status check_div(F l, F lc) { 
 #ifndef BMC_UDF_WRITE_ONLY_MASK
 #define BMC_UDF_WRITE_ONLY_MASK 0u
 #endif
+#ifndef BMC_UDF_ALWAYS_WRITTEN_MASK
+#define BMC_UDF_ALWAYS_WRITTEN_MASK 0u
+#endif
 
 // EXPORT_MODULE (apps/libs/dynlib macro used at apps/udf_model/minimal.cpp:146-155):
 // binds the free hooks to the static model concept the cycle kernel is instantiated on.
@@ -119,7 +125,8 @@ template <class F> __device__ __forceinline__ MC::Status check_div(F l, F lc) { 
     static constexpr int n_var = (int)(*(nvar_f))();                                                                  \
     static constexpr int n_c = (int)(*(nc_f))();                                                                      \
     static constexpr int n_pre = 0;                                                                                   \
-    static constexpr uint32_t write_only_mask = (BMC_UDF_WRITE_ONLY_MASK);                                            \
+    static constexpr uint64_t write_only_mask = (BMC_UDF_WRITE_ONLY_MASK);                                            \
+    static constexpr uint64_t always_written_mask = (BMC_UDF_ALWAYS_WRITTEN_MASK);                                    \
     using Row = MC::DynParticlesModel<float>;                                                                         \
     template <class A, class Cfg> __device__ static void init(bmc::Gen& g, size_t idx, const A& arr, const Cfg& cfg) { \
       (*f_init)(MC::pool_type{&g}, idx, Row{arr.v, 1, 0}, Models::UdfModel::Config{cfg.base});                      \
