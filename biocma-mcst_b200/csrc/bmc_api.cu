@@ -51,7 +51,7 @@ struct bmc_ctx {
   size_t cap = 0, buf_cap = 0;
   float* props = nullptr; uint32_t* pos = nullptr; uint8_t* status = nullptr; float* age_hyd = nullptr; float* age_div = nullptr;
   float* buf_props = nullptr; uint32_t* buf_pos = nullptr; uint32_t* buf_mother = nullptr;
-  uint32_t *div_mask = nullptr, *tile_div = nullptr, *tile_off = nullptr, *blk_total = nullptr;
+  uint32_t *div_mask = nullptr, *tile_off = nullptr, *blk_total = nullptr;
   uint32_t *tile_gap_off = nullptr, *tile_idle_off = nullptr, *blk_gap = nullptr, *blk_idle = nullptr, *src = nullptr;
   // domain
   int m = 0; bool domain_set = false; double table_dt = -1.0;
@@ -59,7 +59,7 @@ struct bmc_ctx {
   float *d_ctab = nullptr, *d_cdf_f = nullptr; uint32_t* d_neigh = nullptr;
   std::vector<bmc_leaving_flow> flows;
   // liquid
-  double *d_conc = nullptr, *d_sources = nullptr;
+  double *d_conc = nullptr, *d_sources = nullptr, *d_acc = nullptr;
   double *d_conc_next = nullptr, *d_mass = nullptr; bool mass_dirty = true;
   uint32_t *d_csc_ptr = nullptr, *d_csc_row = nullptr; double* d_csc_val = nullptr; bool transition_set = false;
   std::vector<bmc_feed> feeds; std::vector<double> h_vol;
@@ -74,7 +74,7 @@ struct bmc_ctx {
   // launch config
   int n_sm = 148, grid_cycle = 148, blocks_per_sm = 1; size_t smem_bins = 0; int bins_in_smem = 0;
   uint64_t launches = 0;
-  size_t stage_offset = 0, smem_total = 0;
+  size_t stage_offset = 0, smem_total = 0; int ctab_in_smem = 0; size_t ctab_offset = 0; int grid_post = 148;
   int grid_cycle_eager = 148; size_t smem_eager = 0;
   // staging
   void* d_stage = nullptr; size_t stage_bytes = 0;
@@ -120,7 +120,7 @@ static int check_launch(bmc_ctx* ctx, const char* what) {
 static void free_container(bmc_ctx* c) {
   dev_free(c->props); dev_free(c->pos); dev_free(c->status); dev_free(c->age_hyd); dev_free(c->age_div);
   dev_free(c->buf_props); dev_free(c->buf_pos); dev_free(c->buf_mother);
-  dev_free(c->div_mask); dev_free(c->tile_div); dev_free(c->tile_off);
+  dev_free(c->div_mask); dev_free(c->tile_off);
   dev_free(c->tile_gap_off); dev_free(c->tile_idle_off); dev_free(c->src);
   c->cap = 0; c->buf_cap = 0;
 }
@@ -163,15 +163,14 @@ static int resize_container(bmc_ctx* ctx, size_t new_cap, size_t keep) {
   if ((rc = dev_alloc(ctx, &ctx->buf_mother, ctx->buf_cap))) return rc;
   const size_t n_tiles = new_cap / kTile;
   if ((rc = dev_alloc(ctx, &ctx->div_mask, new_cap / 32))) return rc;
-  if ((rc = dev_alloc(ctx, &ctx->tile_div, n_tiles))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->tile_off, n_tiles))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->tile_gap_off, n_tiles))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->tile_idle_off, n_tiles))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->src, new_cap))) return rc;
   CK(cudaMemsetAsync(ctx->div_mask, 0, new_cap / 32 * 4, s));
-  CK(cudaMemsetAsync(ctx->tile_div, 0, n_tiles * 4, s));
   CK(cudaMemsetAsync(ctx->tile_off, 0, n_tiles * 4, s));
-  CK(cudaMemsetAsync(&ctx->st->clear_n, 0, sizeof(unsigned long long), s));  // bitmask arrays are fresh
+  prepare_kernel<<<1, 32, 0, s>>>(ctx->st, (unsigned long long)ctx->cap, (unsigned long long)ctx->buf_cap);  // room of the new capacity
+  if ((rc = check_launch(ctx, "prepare"))) return rc;
   CK(cudaStreamSynchronize(s));
   return BMC_OK;
 }
@@ -195,10 +194,16 @@ static int configure_launch(bmc_ctx* ctx) {
   const size_t smem_budget = (size_t)prop.sharedMemPerBlockOptin;
   ctx->bins_in_smem = (ctx->n_comp > 1 && bins_bytes <= std::min<size_t>(smem_budget, 100 * 1024)) ? 1 : 0;
   ctx->smem_bins = ctx->bins_in_smem ? bins_bytes : 0;
-  ctx->stage_offset = (ctx->smem_bins + 15) / 16 * 16;
+  // small compartment tables are rebuilt by every cycle block in shared memory (no pre_step launch)
+  const size_t ctab_bytes = ctx->n_comp * (size_t)ctx->vt.ct * sizeof(float);
+  ctx->ctab_in_smem = (ctx->n_comp > 1 && ctab_bytes <= 16 * 1024) ? 1 : 0;
+  if (const char* e = getenv("BMC_CTAB_SMEM")) ctx->ctab_in_smem = (ctx->ctab_in_smem && atoi(e) != 0) ? 1 : 0;  // tuning runs
+  ctx->ctab_offset = (ctx->smem_bins + 15) / 16 * 16;
+  ctx->stage_offset = (ctx->ctab_offset + (ctx->ctab_in_smem ? ctab_bytes : 0) + 127) / 128 * 128;
   ctx->smem_total = ctx->stage_offset + ctx->vt.stage_bytes;
   if (ctx->smem_total > smem_budget) { ctx->err = "shared memory budget exceeded"; return BMC_ERR_UNSUPPORTED; }
-  ctx->smem_eager = ctx->stage_offset;  // the eager-age variant loads directly: bins only
+  ctx->smem_eager = ctx->stage_offset;  // the eager-age variant loads directly: bins + table only
+  ctx->grid_post = ctx->n_sm;           // cooperative launch: one block per SM is always co-resident
   const char* env = getenv("BMC_BLOCKS_PER_SM");
   auto grid_of = [&](const void* fn, size_t smem, int& grid, int* occ_out) -> int {
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -259,6 +264,18 @@ static int grow_if_needed(bmc_ctx* ctx) {
   if (s.n_used + margin <= ctx->cap) return BMC_OK;
   const size_t new_cap = (size_t)std::ceil((double)(s.n_used + margin) * ctx->allocation_factor);
   return resize_container(ctx, new_cap, (size_t)s.n_used);
+}
+
+static void fill_post_params(bmc_ctx* ctx, PostParams& ip) {
+  memset(&ip, 0, sizeof(ip));
+  ip.props = ctx->props; ip.cap = ctx->cap; ip.n_var = ctx->vt.n_var; ip.pos = ctx->pos; ip.status = ctx->status;
+  ip.age_hyd = ctx->age_hyd; ip.age_div = ctx->age_div; ip.st = ctx->st;
+  ip.tile_gap_off = ctx->tile_gap_off; ip.tile_idle_off = ctx->tile_idle_off; ip.blk_gap = ctx->blk_gap; ip.blk_idle = ctx->blk_idle;
+  ip.src = ctx->src;
+  ip.buf_props = ctx->buf_props; ip.buf_stride = ctx->buf_cap; ip.buf_pos = ctx->buf_pos; ip.buf_mother = ctx->buf_mother;
+  ip.div_mask = ctx->div_mask; ip.tile_off = ctx->tile_off; ip.blk_total = ctx->blk_total;
+  ip.buf_cap = ctx->buf_cap;
+  ip.tab_div = ctx->d_tab_div; ip.tab_hyd = ctx->d_tab_hyd;
 }
 
 // ---- step-stamped ages: host side ---------------------------------------------------------
@@ -352,13 +369,13 @@ int bmc_create(bmc_ctx** out, const bmc_config* cfg) {
   }
   const size_t nb = ctx->n_species * ctx->n_comp;
   int rc;
-  if ((rc = dev_alloc(ctx, &ctx->d_conc, nb)) || (rc = dev_alloc(ctx, &ctx->d_sources, nb)) ||
+  if ((rc = dev_alloc(ctx, &ctx->d_conc, nb)) || (rc = dev_alloc(ctx, &ctx->d_sources, nb)) || (rc = dev_alloc(ctx, &ctx->d_acc, nb)) ||
       (rc = dev_alloc(ctx, &ctx->d_conc_next, nb)) || (rc = dev_alloc(ctx, &ctx->d_mass, nb)) || (rc = dev_alloc(ctx, &ctx->d_csc_ptr, ctx->n_comp + 1)) ||
       (rc = dev_alloc(ctx, &ctx->d_vol, ctx->n_comp)) || (rc = dev_alloc(ctx, &ctx->d_diag, ctx->n_comp)) ||
       (rc = dev_alloc(ctx, &ctx->d_ctab, ctx->n_comp * (size_t)ctx->vt.ct)) || (rc = dev_alloc(ctx, &ctx->blk_total, kMaxGrid + 1)) ||
       (rc = dev_alloc(ctx, &ctx->blk_gap, kMaxGrid + 1)) || (rc = dev_alloc(ctx, &ctx->blk_idle, kMaxGrid + 1)))
     return fail(rc);
-  cudaMemset(ctx->d_conc, 0, nb * 8); cudaMemset(ctx->d_sources, 0, nb * 8);
+  cudaMemset(ctx->d_conc, 0, nb * 8); cudaMemset(ctx->d_sources, 0, nb * 8); cudaMemset(ctx->d_acc, 0, nb * 8);
   cudaMemset(ctx->d_mass, 0, nb * 8); cudaMemset(ctx->d_csc_ptr, 0, (ctx->n_comp + 1) * 4);
   ctx->h_vol.assign(ctx->n_comp, 1.0);
   cudaMemset(ctx->d_ctab, 0, ctx->n_comp * (size_t)ctx->vt.ct * 4);
@@ -378,7 +395,7 @@ int bmc_destroy(bmc_ctx** h) {
   if (c->nccl_comm && g_nccl_destroy) g_nccl_destroy(c->nccl_comm);
   unload_udf_model(c->vt);
   free_container(c);
-  dev_free(c->d_conc); dev_free(c->d_sources); dev_free(c->d_conc_next); dev_free(c->d_mass);
+  dev_free(c->d_conc); dev_free(c->d_sources); dev_free(c->d_acc); dev_free(c->d_conc_next); dev_free(c->d_mass);
   dev_free(c->d_csc_ptr); dev_free(c->d_csc_row); dev_free(c->d_csc_val);
   dev_free(c->d_vol); dev_free(c->d_diag); dev_free(c->d_cdf);
   dev_free(c->d_ctab); dev_free(c->d_cdf_f); dev_free(c->d_neigh);
@@ -460,6 +477,8 @@ int bmc_set_particles(bmc_ctx* ctx, uint64_t n, const float* props, const uint64
     if ((rc = check_launch(ctx, "count_inactive"))) return rc;
   }
   CK(cudaMemcpyAsync(&ctx->st->n_used, &n, 8, cudaMemcpyHostToDevice, s));
+  prepare_kernel<<<1, 32, 0, s>>>(ctx->st, (unsigned long long)ctx->cap, (unsigned long long)ctx->buf_cap);
+  if ((rc = check_launch(ctx, "prepare"))) return rc;
   DevState hs;
   if ((rc = sync_state(ctx, &hs))) return rc;
   if (hs.error & 1u) { ctx->err = "particle position out of range"; return BMC_ERR_RANGE; }
@@ -534,6 +553,8 @@ int bmc_init_particles(bmc_ctx* ctx, uint64_t n, int uniform_position, const flo
   CK(cudaLaunchKernel(ctx->vt.init_fn, dim3(grid), dim3(256), iargs, 0, s));
   if ((rc = check_launch(ctx, "init_kernel"))) return rc;
   CK(cudaMemcpyAsync(&ctx->st->n_used, &n, 8, cudaMemcpyHostToDevice, s));
+  prepare_kernel<<<1, 32, 0, s>>>(ctx->st, (unsigned long long)ctx->cap, (unsigned long long)ctx->buf_cap);
+  if ((rc = check_launch(ctx, "prepare"))) return rc;
   DevState hs;
   if ((rc = sync_state(ctx, &hs))) return rc;
   if (total_mass) *total_mass = hs.init_mass;
@@ -704,16 +725,12 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
       if ((rc = make_ages_eager(ctx))) return rc;  // the stamps assume a constant increment per step
     } else if ((rc = ensure_age_tables(ctx, ctx->host_step + 2))) return rc;
   }
-  PreParams pp;
-  pp.st = ctx->st; pp.sources = ctx->d_sources; pp.n_bins = n_bins; pp.cap = ctx->cap; pp.buf_cap = ctx->buf_cap;
   const int grid_cycle = ctx->lazy_ages ? ctx->grid_cycle : ctx->grid_cycle_eager;
-  pp.grid_cycle = (unsigned)grid_cycle;
-  pp.diag = ctx->d_diag; pp.vol = ctx->d_vol; pp.dt = d_t; pp.conc = ctx->d_conc; pp.n_species = (uint32_t)ctx->n_species;
-  pp.ctab = ctx->d_ctab; pp.n_comp = (uint32_t)ctx->n_comp; pp.enable_move = enable_move ? 1 : 0;
-  pp.buf_mother = ctx->buf_mother; pp.div_mask = ctx->div_mask; pp.tile_div = ctx->tile_div;
-  {
-    const uint32_t work = std::max<uint32_t>(std::max<uint32_t>(n_bins, (uint32_t)ctx->n_comp), 256u);
-    const int grid = (int)std::min<uint32_t>((work + 255) / 256, (uint32_t)ctx->n_sm * 2);
+  if (!ctx->ctab_in_smem) {  // large compartment table: built once per step in global memory
+    PreParams pp;
+    pp.diag = ctx->d_diag; pp.vol = ctx->d_vol; pp.dt = d_t; pp.conc = ctx->d_conc; pp.n_species = (uint32_t)ctx->n_species;
+    pp.ctab = ctx->d_ctab; pp.n_comp = (uint32_t)ctx->n_comp; pp.enable_move = enable_move ? 1 : 0;
+    const int grid = (int)std::min<uint32_t>(((uint32_t)ctx->n_comp + 255) / 256, (uint32_t)ctx->n_sm * 2);
     void* pargs[] = {&pp};
     CK(cudaLaunchKernel(ctx->vt.pre_fn, dim3(grid), dim3(256), pargs, 0, s));
     if ((rc = check_launch(ctx, "pre_step"))) return rc;
@@ -724,7 +741,7 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   p.props = ctx->props; p.cap = ctx->cap; p.pos = ctx->pos; p.status = ctx->status; p.age_hyd = ctx->age_hyd; p.age_div = ctx->age_div;
   p.st = ctx->st;
   p.buf_props = ctx->buf_props; p.buf_stride = ctx->buf_cap; p.buf_pos = ctx->buf_pos; p.buf_mother = ctx->buf_mother;
-  p.div_mask = ctx->div_mask; p.tile_div = ctx->tile_div; p.tile_off = ctx->tile_off; p.blk_total = ctx->blk_total;
+  p.div_mask = ctx->div_mask; p.tile_off = ctx->tile_off; p.blk_total = ctx->blk_total;
   p.ctab = ctx->d_ctab; p.cdf = ctx->d_cdf_f; p.neigh = ctx->d_neigh; p.m = ctx->m; p.n_comp = (uint32_t)ctx->n_comp;
   p.n_flows = (int)ctx->flows.size();
   for (int i = 0; i < p.n_flows; ++i) {
@@ -733,7 +750,8 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
     p.outlets[i].dt_flow = d_t * ctx->flows[i].flow;  // (dt * flow), probability_leaving.hpp:28
     p.outlets[i].volume = ctx->flows[i].volume;
   }
-  p.conc = ctx->d_conc; p.n_species = (uint32_t)ctx->n_species; p.sources = ctx->d_sources;
+  p.conc = ctx->d_conc; p.n_species = (uint32_t)ctx->n_species; p.sources = ctx->d_sources; p.acc = ctx->d_acc;
+  p.diag = ctx->d_diag; p.vol = ctx->d_vol; p.ctab_in_smem = ctx->ctab_in_smem; p.ctab_offset = (uint32_t)ctx->ctab_offset;
   p.weight = ctx->weight; p.dt = d_t; p.dt_f = (float)d_t;
   p.step = (uint32_t)ctx->host_step; p.rank = ctx->rank; p.seed_lo = (uint32_t)ctx->seed; p.seed_hi = (uint32_t)(ctx->seed >> 32);
   p.enable_move = enable_move; p.enable_leave = enable_leave; p.bins_in_smem = ctx->bins_in_smem;
@@ -751,34 +769,19 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   if ((rc = check_launch(ctx, "cycle_kernel"))) return rc;
   if (ctx->profile) { CK(cudaEventRecord(e1, s)); ctx->prof_events.emplace_back(e0, e1); }
 
-  if (enable_leave) ctx->maybe_inactive = true;  // exits may happen from now on
-  if (ctx->maybe_inactive) {
-    // The trigger is evaluated on the device (cycle kernel's last block); these kernels return
-    // immediately unless it fired.  They are skipped entirely only when the host knows that no
-    // inactive slot can exist (no outlet so far and none in the initial statuses).
-    CompactParams cp;
-    cp.props = ctx->props; cp.cap = ctx->cap; cp.n_var = ctx->vt.n_var; cp.pos = ctx->pos; cp.status = ctx->status;
-    cp.age_hyd = ctx->age_hyd; cp.age_div = ctx->age_div; cp.st = ctx->st;
-    cp.tile_gap_off = ctx->tile_gap_off; cp.tile_idle_off = ctx->tile_idle_off; cp.blk_gap = ctx->blk_gap; cp.blk_idle = ctx->blk_idle; cp.src = ctx->src;
-    const int gc = std::min(ctx->n_sm * 2, kMaxGrid);
-    compact_count_kernel<<<gc, 1024, 0, s>>>(cp);
-    if ((rc = check_launch(ctx, "compact_count"))) return rc;
-    compact_src_kernel<<<gc, 1024, 0, s>>>(cp);
-    if ((rc = check_launch(ctx, "compact_src"))) return rc;
-    compact_move_kernel<<<gc, 1024, 0, s>>>(cp);
-    if ((rc = check_launch(ctx, "compact_move"))) return rc;
+  {
+    // post_cycle: compaction (when the plan of the cycle kernel's last block says so), newborn
+    // insertion and commit in one cooperative launch (grid barriers only on the compaction path)
+    PostParams ip;
+    fill_post_params(ctx, ip);
+    ip.count_step = 1;
+    ip.newborn_stamp = ctx->lazy_ages ? (uint32_t)ctx->host_step + 1u : 0u;
+    ip.tab_idx = (uint32_t)ctx->host_step;
+    ip.tab_extend = ctx->lazy_ages ? 1 : 0; ip.enable_leave = enable_leave ? 1 : 0; ip.dt_f = (float)d_t; ip.dt = d_t;
+    void* pargs[] = {&ip};
+    CK(cudaLaunchCooperativeKernel((const void*)post_cycle_kernel, dim3(ctx->grid_post), dim3(256), pargs, 0, s));
+    if ((rc = check_launch(ctx, "post_cycle"))) return rc;
   }
-  InsertParams ip;
-  ip.props = ctx->props; ip.cap = ctx->cap; ip.n_var = ctx->vt.n_var; ip.pos = ctx->pos; ip.status = ctx->status;
-  ip.age_hyd = ctx->age_hyd; ip.age_div = ctx->age_div; ip.st = ctx->st;
-  ip.buf_props = ctx->buf_props; ip.buf_stride = ctx->buf_cap; ip.buf_pos = ctx->buf_pos; ip.buf_mother = ctx->buf_mother;
-  ip.div_mask = ctx->div_mask; ip.tile_div = ctx->tile_div; ip.tile_off = ctx->tile_off; ip.blk_total = ctx->blk_total;
-  ip.count_step = 1;
-  ip.newborn_stamp = ctx->lazy_ages ? (uint32_t)ctx->host_step + 1u : 0u;
-  ip.tab_div = ctx->d_tab_div; ip.tab_hyd = ctx->d_tab_hyd; ip.tab_idx = (uint32_t)ctx->host_step;
-  ip.tab_extend = ctx->lazy_ages ? 1 : 0; ip.enable_leave = enable_leave ? 1 : 0; ip.dt_f = (float)d_t; ip.dt = d_t;
-  post_kernel<<<ctx->n_sm, 256, 0, s>>>(ip);
-  if ((rc = check_launch(ctx, "post"))) return rc;
 
   // asynchronous mirror of the device bookkeeping (never waited on here)
   if (ctx->host_step % (uint64_t)ctx->mirror_period == 0) {
@@ -837,20 +840,13 @@ int bmc_compact(bmc_ctx* ctx) {
   CK(cudaMemcpyAsync(&ctx->st->force_compact, &one, 4, cudaMemcpyHostToDevice, s));
   plan_kernel<<<1, 32, 0, s>>>(ctx->st, ctx->min_removal, ctx->dead_ratio);
   if ((rc = check_launch(ctx, "plan"))) return rc;
-  CompactParams cp;
-  cp.props = ctx->props; cp.cap = ctx->cap; cp.n_var = ctx->vt.n_var; cp.pos = ctx->pos; cp.status = ctx->status;
-  cp.age_hyd = ctx->age_hyd; cp.age_div = ctx->age_div; cp.st = ctx->st;
-  cp.tile_gap_off = ctx->tile_gap_off; cp.tile_idle_off = ctx->tile_idle_off; cp.blk_gap = ctx->blk_gap; cp.blk_idle = ctx->blk_idle; cp.src = ctx->src;
-  const int gc = std::min(ctx->n_sm * 2, kMaxGrid);
-  compact_count_kernel<<<gc, 1024, 0, s>>>(cp); if ((rc = check_launch(ctx, "compact_count"))) return rc;
-  compact_src_kernel<<<gc, 1024, 0, s>>>(cp); if ((rc = check_launch(ctx, "compact_src"))) return rc;
-  compact_move_kernel<<<gc, 1024, 0, s>>>(cp); if ((rc = check_launch(ctx, "compact_move"))) return rc;
-  InsertParams ip;
-  memset(&ip, 0, sizeof(ip));
-  ip.status = ctx->status; ip.st = ctx->st; ip.buf_mother = ctx->buf_mother; ip.div_mask = ctx->div_mask; ip.tile_div = ctx->tile_div;
-  ip.blk_total = ctx->blk_total;
-  ip.count_step = 0;  // n_add is 0 here (the plan cleared buffer_index): post only commits n_used / inactive
-  post_kernel<<<ctx->n_sm, 256, 0, s>>>(ip); if ((rc = check_launch(ctx, "post"))) return rc;
+  PostParams ip;
+  fill_post_params(ctx, ip);
+  ip.count_step = 0;  // n_add is 0 here (the plan cleared buffer_index): post only compacts and commits n_used / inactive
+  ip.newborn_stamp = 0; ip.tab_idx = 0; ip.tab_extend = 0; ip.enable_leave = 0; ip.dt_f = 0.f; ip.dt = 0.0;
+  void* pargs[] = {&ip};
+  CK(cudaLaunchCooperativeKernel((const void*)post_cycle_kernel, dim3(ctx->grid_post), dim3(256), pargs, 0, s));
+  if ((rc = check_launch(ctx, "post_cycle"))) return rc;
   DevState hs;
   return sync_state(ctx, &hs);
 }

@@ -79,7 +79,7 @@ struct DevState {
   double init_mass;                 // total mass reduce of mc_init_first
   unsigned int done_blocks;         // ticket counter: the last cycle block to finish writes the plan
   unsigned int pad0;
-  unsigned long long clear_n;       // division records whose bitmask bits the next pre_step clears
+  unsigned long long pad1;
 };
 
 struct Outlet { uint32_t index; uint32_t pad; double flow; double dt_flow; double volume; };
@@ -109,9 +109,8 @@ struct CycleParams {
   DevState* st;
   // division buffer (particles_container.hpp:222-227)
   float* buf_props; size_t buf_stride; uint32_t* buf_pos; uint32_t* buf_mother;
-  uint32_t* div_mask;   // 1 bit / slot: mother divided this step (allocated a buffer row)
-  uint32_t* tile_div;   // per tile: number of such mothers
-  uint32_t* tile_off;   // per tile: exclusive prefix inside the owning block
+  uint32_t* div_mask;   // 1 bit / slot: mother divided this step (allocated a buffer row); rewritten every step
+  uint32_t* tile_off;   // per tile: exclusive prefix of the division counts inside the owning block
   uint32_t* blk_total;  // per block: divisions in its range
   // domain (DomainState, domain.hpp:28-35) in derived single-precision form
   const float* ctab;       // compartment table rows {leave threshold, model terms...}
@@ -120,7 +119,11 @@ struct CycleParams {
   int m; uint32_t n_comp;
   int n_flows; Outlet outlets[kMaxFlows];
   // liquid coupling
-  const double* conc; uint32_t n_species; double* sources;
+  const double* conc; uint32_t n_species;
+  double* acc;       // accumulator of the source terms (zero between steps)
+  double* sources;   // published by the last block: sources = acc, acc = 0
+  // compartment table built by every block in shared memory (small n_comp) instead of pre_step
+  const double* diag; const double* vol; int ctab_in_smem; uint32_t ctab_offset;
   float weight;
   double dt; float dt_f;
   uint32_t step, rank, seed_lo, seed_hi;
@@ -197,52 +200,35 @@ template <> struct VecIO<1> {
 
 
 // -----------------------------------------------------------------------------
-// pre_step: everything that must happen before the particle pass, in one launch:
-//   * contribs_scatter.reset() (simulation.hpp:201): zero the source accumulators
-//   * compartment table, one row per compartment (n_comp rows — 500 .. 10k — not N):
-//       col 0        ceil_f32(dt * diag_transition / liquid_volume)   leave threshold
-//       col 1..n_pre M::compartment_terms(c, compartment)             optional model hook
-//     A model whose update starts with a function of the local concentration only
-//     (Monod: mu = mu_max*s/(k_s+s)) hoists it here: the IEEE division then runs once
-//     per compartment instead of once per particle, with bit-identical results.
-//   * clear the division bitmask bits of the previous step's newborn records
-//   * this step's usable buffer capacity and the per-step counters
+// Compartment table, one row per compartment (n_comp rows — 500 .. 10k — not N):
+//     col 0        ceil_f32(dt * diag_transition / liquid_volume)   leave threshold
+//     col 1..n_pre M::compartment_terms(c, compartment)             optional model hook
+// A model whose update starts with a function of the local concentration only
+// (Monod: mu = mu_max*s/(k_s+s)) hoists it here: the IEEE division then runs once
+// per compartment instead of once per particle, with bit-identical results.
+// Small tables are built by every cycle block in shared memory (no extra launch);
+// pre_step builds large ones in global memory.
 // -----------------------------------------------------------------------------
 struct PreParams {
-  DevState* st; double* sources; uint32_t n_bins;
-  unsigned long long cap, buf_cap; unsigned int grid_cycle;
   const double* diag; const double* vol; double dt; const double* conc; uint32_t n_species; float* ctab; uint32_t n_comp;
   int enable_move;
-  const uint32_t* buf_mother; uint32_t* div_mask; uint32_t* tile_div;
 };
+
+template <class M> __device__ __forceinline__ void compartment_row(const double* diag, const double* vol, double dt, const double* conc,
+                                                                   uint32_t n_species, int enable_move, uint32_t c, float* row) {
+  row[0] = enable_move ? __double2float_ru(dt * diag[c] / vol[c]) : 0.0f;
+  if constexpr (M::n_pre > 0) M::compartment_terms(ConcView{conc, n_species, nullptr}, (size_t)c, row + 1);
+}
 
 template <class M> __device__ __forceinline__ void pre_step_body(const PreParams& p) {
   constexpr int CT = 1 + M::n_pre;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t nthreads = gridDim.x * blockDim.x;
-  for (uint32_t k = i; k < p.n_bins; k += nthreads) p.sources[k] = 0.0;
   for (uint32_t c = i; c < p.n_comp; c += nthreads) {
     float row[CT];
-    row[0] = p.enable_move ? __double2float_ru(p.dt * p.diag[c] / p.vol[c]) : 0.0f;
-    if constexpr (M::n_pre > 0) M::compartment_terms(ConcView{p.conc, p.n_species, nullptr}, (size_t)c, row + 1);
+    compartment_row<M>(p.diag, p.vol, p.dt, p.conc, p.n_species, p.enable_move, c, row);
 #pragma unroll
     for (int k = 0; k < CT; ++k) p.ctab[(size_t)c * CT + k] = row[k];
-  }
-  const unsigned long long n_clear = p.st->clear_n;
-  for (unsigned long long j = i; j < n_clear; j += nthreads) {
-    const uint32_t mother = p.buf_mother[j];
-    p.div_mask[mother >> 5] = 0u;
-    p.tile_div[mother >> 10] = 0u;
-  }
-  if (i == 0) {
-    DevState* st = p.st;
-    const unsigned long long n = st->n_used;
-    const unsigned long long room = p.cap > n ? p.cap - n : 0ull;
-    st->buf_cap_eff = p.buf_cap < room ? p.buf_cap : room;
-    st->buf_index = 0; st->step_exit = 0; st->step_waiting = 0;
-    st->cyc_n_used = n;
-    st->cyc_tiles = (unsigned int)((n + kTile - 1) / kTile);
-    st->cyc_grid = p.grid_cycle;
   }
 }
 
@@ -251,6 +237,7 @@ template <class M> __device__ __forceinline__ void pre_step_body(const PreParams
 __device__ __forceinline__ void make_plan(DevState* st, unsigned long long min_removal, double dead_ratio) {
   const unsigned long long out = st->step_exit;
   st->last_out = out; st->last_dead = 0; st->last_waiting = st->step_waiting;
+  st->step_waiting = 0;
   st->total_out += out;
   st->inactive += out;  // inactive_counter += out; += dead (always 0, Q3)
   st->step_exit = 0;
@@ -362,6 +349,15 @@ template <class M, int VEC, bool PIPE, bool LAZY> __device__ __forceinline__ voi
   if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0ull;
   if (smem_bins)
     for (uint32_t k = threadIdx.x; k < n_bins; k += kBlock) s_bins[k] = 0.0;
+  float* const s_ctab = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_bins) + p.ctab_offset);
+  if (p.ctab_in_smem) {
+    for (uint32_t c = threadIdx.x; c < p.n_comp; c += kBlock) {
+      float row[CT];
+      compartment_row<M>(p.diag, p.vol, p.dt, p.conc, p.n_species, p.enable_move, c, row);
+#pragma unroll
+      for (int k = 0; k < CT; ++k) s_ctab[c * CT + k] = row[k];
+    }
+  }
   __syncthreads();
 
   unsigned c_move = 0, c_exit = 0, c_new = 0, c_over = 0;
@@ -477,12 +473,21 @@ template <class M, int VEC, bool PIPE, bool LAZY> __device__ __forceinline__ voi
       float ctab[VEC][CT];
 #pragma unroll
       for (int q = 0; q < VEC; ++q) {
-        const float* row = p.ctab + (size_t)pos[q] * CT;
-        if constexpr (CT == 2) { const float2 t = __ldg(reinterpret_cast<const float2*>(row)); ctab[q][0] = t.x; ctab[q][1] = t.y; }
-        else if constexpr (CT == 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(row)); ctab[q][0] = t.x; ctab[q][1] = t.y; ctab[q][2] = t.z; ctab[q][3] = t.w; }
-        else {
+        if (p.ctab_in_smem) {
+          const float* row = s_ctab + pos[q] * CT;
+          if constexpr (CT == 2) { const float2 t = *reinterpret_cast<const float2*>(row); ctab[q][0] = t.x; ctab[q][1] = t.y; }
+          else {
 #pragma unroll
-          for (int k = 0; k < CT; ++k) ctab[q][k] = __ldg(row + k);
+            for (int k = 0; k < CT; ++k) ctab[q][k] = row[k];
+          }
+        } else {
+          const float* row = p.ctab + (size_t)pos[q] * CT;
+          if constexpr (CT == 2) { const float2 t = __ldg(reinterpret_cast<const float2*>(row)); ctab[q][0] = t.x; ctab[q][1] = t.y; }
+          else if constexpr (CT == 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(row)); ctab[q][0] = t.x; ctab[q][1] = t.y; ctab[q][2] = t.z; ctab[q][3] = t.w; }
+          else {
+#pragma unroll
+            for (int k = 0; k < CT; ++k) ctab[q][k] = __ldg(row + k);
+          }
         }
       }
 
@@ -521,7 +526,7 @@ template <class M, int VEC, bool PIPE, bool LAZY> __device__ __forceinline__ voi
         for (int q = 0; q < VEC; ++q)
           if (idle[q]) {
 #pragma unroll
-            for (int j = 0; j < NC; ++j) atomicAdd(p.sources + (size_t)j + (size_t)p.n_species * pos[q], w * (double)contrib[q][j]);
+            for (int j = 0; j < NC; ++j) atomicAdd(p.acc + (size_t)j + (size_t)p.n_species * pos[q], w * (double)contrib[q][j]);
           }
       }
 
@@ -531,6 +536,7 @@ template <class M, int VEC, bool PIPE, bool LAZY> __device__ __forceinline__ voi
       // particle order inside the warp; final newborn placement is re-ranked by
       // mother index in insert_kernel, so the result does not depend on the
       // order warps hit the atomic.
+      unsigned ok_nib = 0;
       if (__any_sync(0xffffffffu, div_nib != 0u)) {
         const unsigned cnt = __popc(div_nib);
         unsigned total;
@@ -538,7 +544,7 @@ template <class M, int VEC, bool PIPE, bool LAZY> __device__ __forceinline__ voi
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(&p.st->buf_index, (unsigned long long)total);
         base = __shfl_sync(0xffffffffu, base, 0);
-        unsigned ok_nib = 0, r = 0;
+        unsigned r = 0;
 #pragma unroll
         for (int q = 0; q < VEC; ++q) {
           if ((div_nib >> q) & 1u) {
@@ -558,14 +564,19 @@ template <class M, int VEC, bool PIPE, bool LAZY> __device__ __forceinline__ voi
             }
           }
         }
-        // division bitmask: bit (slot & 31) of word (slot >> 5); a word is owned by 32/VEC lanes
+      }
+      {
+        // division bitmask: bit (slot & 31) of word (slot >> 5); a word is owned by 32/VEC lanes.
+        // Written for EVERY group of every step (0.125 B/slot), so no bit ever needs clearing.
         constexpr int LPW = 32 / VEC;
         unsigned word = ok_nib << (VEC * (lane % LPW));
 #pragma unroll
         for (int o = 1; o < LPW; o <<= 1) word |= __shfl_xor_sync(0xffffffffu, word, o);
-        const unsigned n_ok = __reduce_add_sync(0xffffffffu, __popc(ok_nib));
-        if (live && (lane % LPW) == 0 && word != 0u) p.div_mask[(i0 >> 5)] = word;
-        if (lane == 0 && n_ok) atomicAdd(&p.tile_div[tile], n_ok);
+#if !defined(BMC_EXP_NO_MASKSTORE)
+        if ((lane % LPW) == 0) p.div_mask[i_raw >> 5] = word;  // i_raw: also the ragged end of the last tile (zeros)
+#else
+        if ((lane % LPW) == 0 && word) p.div_mask[i_raw >> 5] = word;
+#endif
       }
 
       // ---- move (all slots, no status check: move_kernel.hpp:392-437) --------
@@ -737,7 +748,7 @@ template <class M, int VEC, bool PIPE, bool LAZY> __device__ __forceinline__ voi
       double a = acc0d[j];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      if (lane == 0 && a != 0.0) atomicAdd(p.sources + j, a);
+      if (lane == 0 && a != 0.0) atomicAdd(p.acc + j, a);
     }
   }
   __threadfence();
@@ -751,15 +762,21 @@ template <class M, int VEC, bool PIPE, bool LAZY> __device__ __forceinline__ voi
   if (smem_bins) {
     for (uint32_t k = threadIdx.x; k < n_bins; k += kBlock) {
       const double a = s_bins[k];
-      if (a != 0.0) atomicAdd(p.sources + k, a);
+      if (a != 0.0) atomicAdd(p.acc + k, a);
     }
   }
-  // block-local exclusive prefix of tile_div over [t0,t1) -> tile_off, blk_total
+  // per-tile division counts = popcount of the tile's 32 mask words (written above by this block,
+  // visible after the barrier), then their block-local exclusive prefix -> tile_off, blk_total
+  for (uint32_t t = t0 + warp; t < t1; t += kBlock / 32) {
+    const unsigned c = __reduce_add_sync(0xffffffffu, (unsigned)__popc(__ldcg(p.div_mask + (size_t)t * (kTile / 32) + lane)));
+    if (lane == 0) p.tile_off[t] = c;
+  }
+  __syncthreads();
   if (warp == 0) {
     unsigned run = 0;
     for (uint32_t base = t0; base < t1; base += 32) {
       const uint32_t t = base + lane;
-      const unsigned cnt = (t < t1) ? __ldcg(p.tile_div + t) : 0u;
+      const unsigned cnt = (t < t1) ? __ldcg(p.tile_off + t) : 0u;
       unsigned tot;
       const unsigned ex = warp_excl_scan(cnt, tot);
       if (t < t1) p.tile_off[t] = run + ex;
@@ -771,12 +788,20 @@ template <class M, int VEC, bool PIPE, bool LAZY> __device__ __forceinline__ voi
   // post-cycle plan (compaction trigger, newborn count) for the kernels that follow
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned ticket = atomicAdd(&p.st->done_blocks, 1u);
-    if (ticket == gridDim.x - 1) {
-      __threadfence();
+  __shared__ unsigned s_last;
+  if (threadIdx.x == 0) s_last = (atomicAdd(&p.st->done_blocks, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    // scatter_contribute + synchro_sources (simulation.cpp:143-151, implScalar.cpp:194-205): publish the
+    // source terms of this step and leave the accumulator zeroed for the next one
+    for (uint32_t k = threadIdx.x; k < n_bins; k += kBlock) {
+      p.sources[k] = __ldcg(p.acc + k);
+      p.acc[k] = 0.0;
+    }
+    if (threadIdx.x == 0) {
       p.st->done_blocks = 0;
-      p.st->clear_n = 0;
+      p.st->cyc_n_used = n_used; p.st->cyc_tiles = n_tiles; p.st->cyc_grid = gridDim.x;
       make_plan(p.st, p.min_removal, p.dead_ratio);
     }
   }
