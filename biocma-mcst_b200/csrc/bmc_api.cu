@@ -76,6 +76,7 @@ struct bmc_ctx {
   uint64_t launches = 0;
   size_t stage_offset = 0, smem_total = 0; int ctab_in_smem = 0; size_t ctab_offset = 0; int grid_post = 148;
   int grid_cycle_eager = 148; size_t smem_eager = 0;
+  bool fuse_post = true;  // whole step in one cooperative launch (BMC_FUSE_POST=0: particle pass + post_only_kernel)
   // staging
   void* d_stage = nullptr; size_t stage_bytes = 0;
   // profiling
@@ -204,6 +205,7 @@ static int configure_launch(bmc_ctx* ctx) {
   if (ctx->smem_total > smem_budget) { ctx->err = "shared memory budget exceeded"; return BMC_ERR_UNSUPPORTED; }
   ctx->smem_eager = ctx->stage_offset;  // the eager-age variant loads directly: bins + table only
   ctx->grid_post = ctx->n_sm;           // cooperative launch: one block per SM is always co-resident
+  if (const char* e = getenv("BMC_FUSE_POST")) ctx->fuse_post = atoi(e) != 0;
   const char* env = getenv("BMC_BLOCKS_PER_SM");
   auto grid_of = [&](const void* fn, size_t smem, int& grid, int* occ_out) -> int {
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -221,6 +223,13 @@ static int configure_launch(bmc_ctx* ctx) {
   int rc;
   if ((rc = grid_of(ctx->vt.cycle_fn, ctx->smem_total, ctx->grid_cycle, &ctx->blocks_per_sm))) return rc;
   if ((rc = grid_of(ctx->vt.cycle_eager_fn, ctx->smem_eager, ctx->grid_cycle_eager, nullptr))) return rc;
+  if (getenv("BMC_VERBOSE")) {
+    cudaFuncAttributes fa{};
+    cudaFuncGetAttributes(&fa, ctx->vt.cycle_fn);
+    fprintf(stderr, "[bmc] step kernel: grid %d (%d blocks/SM x %d SMs), %d regs, smem static %zu + dynamic %zu B (bins %zu, table %s, staging %zu), eager grid %d\n",
+            ctx->grid_cycle, ctx->blocks_per_sm, ctx->n_sm, fa.numRegs, fa.sharedSizeBytes, ctx->smem_total, ctx->smem_bins,
+            ctx->ctab_in_smem ? "smem" : "global", ctx->vt.stage_bytes, ctx->grid_cycle_eager);
+  }
   return BMC_OK;
 }
 
@@ -276,6 +285,8 @@ static void fill_post_params(bmc_ctx* ctx, PostParams& ip) {
   ip.div_mask = ctx->div_mask; ip.tile_off = ctx->tile_off; ip.blk_total = ctx->blk_total;
   ip.buf_cap = ctx->buf_cap;
   ip.tab_div = ctx->d_tab_div; ip.tab_hyd = ctx->d_tab_hyd;
+  ip.acc = ctx->d_acc; ip.sources = ctx->d_sources; ip.n_bins = (uint32_t)(ctx->n_species * ctx->n_comp);
+  ip.min_removal = ctx->min_removal; ip.dead_ratio = ctx->dead_ratio;
 }
 
 // ---- step-stamped ages: host side ---------------------------------------------------------
@@ -756,32 +767,37 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   p.step = (uint32_t)ctx->host_step; p.rank = ctx->rank; p.seed_lo = (uint32_t)ctx->seed; p.seed_hi = (uint32_t)(ctx->seed >> 32);
   p.enable_move = enable_move; p.enable_leave = enable_leave; p.bins_in_smem = ctx->bins_in_smem;
   p.stage_offset = (uint32_t)ctx->stage_offset;
-  p.min_removal = ctx->min_removal; p.dead_ratio = ctx->dead_ratio;
+
+  // second phase of the step kernel: compaction (when triggered), newborn insertion, commit
+  fill_post_params(ctx, p.post);
+  p.post.count_step = 1;
+  p.post.newborn_stamp = ctx->lazy_ages ? (uint32_t)ctx->host_step + 1u : 0u;
+  p.post.tab_idx = (uint32_t)ctx->host_step;
+  p.post.tab_extend = ctx->lazy_ages ? 1 : 0; p.post.enable_leave = enable_leave ? 1 : 0; p.post.dt_f = (float)d_t; p.post.dt = d_t;
 
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx->profile) {
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, s));
   }
+  // ONE cooperative launch per time step (grid = resident blocks: the grid barrier between the
+  // particle pass and the post-cycle phase needs every block on the device)
   void* cargs[] = {&p};
-  if (ctx->lazy_ages) CK(cudaLaunchKernel(ctx->vt.cycle_fn, dim3(grid_cycle), dim3(kBlock), cargs, ctx->smem_total, s));
-  else CK(cudaLaunchKernel(ctx->vt.cycle_eager_fn, dim3(grid_cycle), dim3(kBlock), cargs, ctx->smem_eager, s));
-  if ((rc = check_launch(ctx, "cycle_kernel"))) return rc;
-  if (ctx->profile) { CK(cudaEventRecord(e1, s)); ctx->prof_events.emplace_back(e0, e1); }
-
-  {
-    // post_cycle: compaction (when the plan of the cycle kernel's last block says so), newborn
-    // insertion and commit in one cooperative launch (grid barriers only on the compaction path)
-    PostParams ip;
-    fill_post_params(ctx, ip);
-    ip.count_step = 1;
-    ip.newborn_stamp = ctx->lazy_ages ? (uint32_t)ctx->host_step + 1u : 0u;
-    ip.tab_idx = (uint32_t)ctx->host_step;
-    ip.tab_extend = ctx->lazy_ages ? 1 : 0; ip.enable_leave = enable_leave ? 1 : 0; ip.dt_f = (float)d_t; ip.dt = d_t;
-    void* pargs[] = {&ip};
-    CK(cudaLaunchCooperativeKernel((const void*)post_cycle_kernel, dim3(ctx->grid_post), dim3(256), pargs, 0, s));
-    if ((rc = check_launch(ctx, "post_cycle"))) return rc;
+  p.fuse_post = ctx->fuse_post ? 1 : 0;
+  const void* fn = ctx->lazy_ages ? ctx->vt.cycle_fn : ctx->vt.cycle_eager_fn;
+  const size_t smem = ctx->lazy_ages ? ctx->smem_total : ctx->smem_eager;
+  if (ctx->fuse_post) {
+    CK(cudaLaunchCooperativeKernel(fn, dim3(grid_cycle), dim3(kBlock), cargs, smem, s));
+    if ((rc = check_launch(ctx, "cycle_kernel"))) return rc;
+  } else {
+    CK(cudaLaunchKernel(fn, dim3(grid_cycle), dim3(kBlock), cargs, smem, s));
+    if ((rc = check_launch(ctx, "cycle_kernel"))) return rc;
+    void* pargs[] = {&p.post};
+    CK(cudaLaunchCooperativeKernel((const void*)post_only_kernel, dim3(ctx->grid_post), dim3(kBlock), pargs, 0, s));
+    if ((rc = check_launch(ctx, "post_only"))) return rc;
   }
+  if (ctx->profile) { CK(cudaEventRecord(e1, s)); ctx->prof_events.emplace_back(e0, e1); }
+  if (enable_leave) ctx->maybe_inactive = true;  // exits may happen from now on
 
   // asynchronous mirror of the device bookkeeping (never waited on here)
   if (ctx->host_step % (uint64_t)ctx->mirror_period == 0) {
@@ -838,15 +854,13 @@ int bmc_compact(bmc_ctx* ctx) {
   int rc;
   const unsigned int one = 1;
   CK(cudaMemcpyAsync(&ctx->st->force_compact, &one, 4, cudaMemcpyHostToDevice, s));
-  plan_kernel<<<1, 32, 0, s>>>(ctx->st, ctx->min_removal, ctx->dead_ratio);
-  if ((rc = check_launch(ctx, "plan"))) return rc;
   PostParams ip;
   fill_post_params(ctx, ip);
-  ip.count_step = 0;  // n_add is 0 here (the plan cleared buffer_index): post only compacts and commits n_used / inactive
+  ip.count_step = 0;  // no newborn is waiting (the buffer index is reset by every commit): compaction + commit only
   ip.newborn_stamp = 0; ip.tab_idx = 0; ip.tab_extend = 0; ip.enable_leave = 0; ip.dt_f = 0.f; ip.dt = 0.0;
   void* pargs[] = {&ip};
-  CK(cudaLaunchCooperativeKernel((const void*)post_cycle_kernel, dim3(ctx->grid_post), dim3(256), pargs, 0, s));
-  if ((rc = check_launch(ctx, "post_cycle"))) return rc;
+  CK(cudaLaunchCooperativeKernel((const void*)post_only_kernel, dim3(ctx->grid_post), dim3(kBlock), pargs, 0, s));
+  if ((rc = check_launch(ctx, "post_only"))) return rc;
   DevState hs;
   return sync_state(ctx, &hs);
 }
@@ -874,6 +888,20 @@ int bmc_launch_count(const bmc_ctx* ctx, uint64_t* n) {
 int bmc_profile_enable(bmc_ctx* ctx, int on) {
   if (!ctx) return BMC_ERR_INVALID;
   ctx->profile = on != 0;
+  return BMC_OK;
+}
+// tuning aid (not declared in bmc.h): %globaltimer stamps of block 0 of the last step kernel; only
+// BMC_TIMELINE builds write them
+int bmc_debug_timeline(bmc_ctx* ctx, unsigned long long* out16) {
+  if (!ctx || !out16) return BMC_ERR_INVALID;
+  DevState s; int rc;
+  if ((rc = sync_state(ctx, &s))) return rc;
+  memcpy(out16, s.dbg, sizeof(s.dbg));
+  return BMC_OK;
+}
+int bmc_debug_blocks(bmc_ctx* ctx, uint32_t* out, uint64_t n_words) {  // per-block stamps of BMC_TIMELINE builds
+  if (!ctx || !out) return BMC_ERR_INVALID;
+  CK(cudaMemcpy(out, ctx->src, n_words * 4, cudaMemcpyDeviceToHost));
   return BMC_OK;
 }
 int bmc_profile_read(bmc_ctx* ctx, double* ms_total, uint64_t* n) {

@@ -79,7 +79,9 @@ struct DevState {
   double init_mass;                 // total mass reduce of mc_init_first
   unsigned int done_blocks;         // ticket counter: the last cycle block to finish writes the plan
   unsigned int pad0;
-  unsigned long long pad1;
+  unsigned int bar_count, bar_gen;  // grid barrier of the cooperatively launched step kernel
+  unsigned int next_group, pad2;    // work counter of the particle pass (groups drawn beyond each warp's first)
+  unsigned long long dbg[16];       // BMC_TIMELINE builds: %globaltimer stamps of block 0 (tuning only)
 };
 
 struct Outlet { uint32_t index; uint32_t pad; double flow; double dt_flow; double volume; };
@@ -101,6 +103,31 @@ struct Outlet { uint32_t index; uint32_t pad; double flow; double dt_flow; doubl
 // floats in place and the eager kernel variant (LAZY = false) takes over.
 // -----------------------------------------------------------------------------
 constexpr uint32_t kFrozen = 0x80000000u;
+
+#if defined(BMC_TIMELINE)
+#define BMC_STAMP(st, i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); (st)->dbg[i] = t_; } } while (0)
+#else
+#define BMC_STAMP(st, i) do { } while (0)
+#endif
+
+struct PostParams {
+  float* props; size_t cap; int n_var;
+  uint32_t* pos; uint8_t* status; float* age_hyd; float* age_div;
+  DevState* st;
+  // compaction scratch
+  uint32_t* tile_gap_off; uint32_t* tile_idle_off; uint32_t* blk_gap; uint32_t* blk_idle; uint32_t* src;
+  // division buffer + ranking data written by the cycle kernel
+  const float* buf_props; size_t buf_stride; const uint32_t* buf_pos; const uint32_t* buf_mother;
+  const uint32_t* div_mask; uint32_t* tile_off; uint32_t* blk_total;
+  unsigned long long buf_cap;
+  double* acc; double* sources; uint32_t n_bins;
+  unsigned long long min_removal; double dead_ratio;  // RuntimeParameters of update_and_remove_inactive
+  int count_step;  // 1 when called from a cycle, 0 from force_remove_dead
+  // step-stamped ages (bmc_kernels.cuh): stamp given to newborns (0 = eager float ages, bits of 0.f)
+  // and the per-step extension of the age tables A_div / A_hyd
+  uint32_t newborn_stamp;
+  float* tab_div; float* tab_hyd; uint32_t tab_idx; int tab_extend; int enable_leave; float dt_f; double dt;
+};
 
 struct CycleParams {
   // particle SoA columns (ParticlesContainer views, particles_container.hpp:82-88)
@@ -129,7 +156,8 @@ struct CycleParams {
   uint32_t step, rank, seed_lo, seed_hi;
   int enable_move, enable_leave, bins_in_smem;
   uint32_t stage_offset;  // byte offset of the cp.async staging buffers inside dynamic shared memory
-  unsigned long long min_removal; double dead_ratio;  // RuntimeParameters used by the post-cycle plan
+  PostParams post;   // second phase of the step (post_cycle_body)
+  int fuse_post;     // 1 = run it in this launch behind a grid barrier (cooperative launch), 0 = post_only_kernel follows
 };
 
 __device__ __forceinline__ unsigned warp_excl_scan(unsigned v, unsigned& total) {
@@ -232,31 +260,334 @@ template <class M> __device__ __forceinline__ void pre_step_body(const PreParams
   }
 }
 
-// update_and_remove_inactive (particles_container.hpp:539-557) and the merge_buffer size
-// (:575-581), decided on the device by ONE thread once every particle has been processed.
-__device__ __forceinline__ void make_plan(DevState* st, unsigned long long min_removal, double dead_ratio) {
-  const unsigned long long out = st->step_exit;
-  st->last_out = out; st->last_dead = 0; st->last_waiting = st->step_waiting;
-  st->step_waiting = 0;
-  st->total_out += out;
-  st->inactive += out;  // inactive_counter += out; += dead (always 0, Q3)
-  st->step_exit = 0;
-  const unsigned long long n = st->n_used;
-  unsigned long long thr = (unsigned long long)((double)n * dead_ratio);
-  if (min_removal > thr) thr = min_removal;
-  const bool trig = (st->inactive > thr) || (st->force_compact && st->inactive > 0);
-  st->force_compact = 0;
-  st->cmp_old_n = n;
-  if (trig) {
-    st->do_compact = 1;
-    st->cmp_new_n = n - st->inactive;
-    st->cmp_tiles = (unsigned int)((n + kTile - 1) / kTile);
-  } else {
-    st->do_compact = 0; st->cmp_new_n = n;
+// -----------------------------------------------------------------------------
+// post_cycle: everything of SimulationUnit::post_cycle (simulation.hpp:213-239) after the
+// particle pass.  It is the SECOND PHASE OF THE STEP KERNEL (cooperative launch: every block is
+// resident, a grid barrier separates it from the particle pass), so a whole time step is one
+// launch:
+//
+//   publish: scatter_contribute + synchro_sources (simulation.cpp:143-151, implScalar.cpp:194-205):
+//     sources = accumulator, accumulator = 0
+//   plan: update_and_remove_inactive (particles_container.hpp:539-557) and the merge_buffer size
+//     (:575-581) — a pure function of the device counters, evaluated redundantly by every block
+//   [only when the plan says so]
+//   compaction: remove_inactive_particles + CompactParticlesFunctor
+//     (particles_container.hpp:735-796, 292-385), made exact and deterministic: the
+//     k-th non-idle slot below new_n (ascending) receives the k-th idle particle of the tail
+//     [new_n, old_n) counted from the end — the pairing a serial execution of the reference
+//     functor produces.  Three phases separated by grid barriers:
+//       count : per-tile counts (gaps below new_n, idle in the tail) + block-local prefixes
+//       src   : tail tiles -> src[k] = slot of the k-th idle from the end
+//       move  : low tiles  -> the gap with rank k pulls src[k]
+//   insert: merge_buffer + InsertFunctor (particles_container.hpp:575-599, 403-443).  The newborn of
+//     mother i goes to new_n + (number of dividing mothers with a smaller slot index) — the order
+//     the reference's buffer has under serial execution.
+//   commit: container counters, the next step's buffer room, one more entry of the age tables;
+//     done by the last block to finish (ticket), when no block reads the counters any more.
+//
+// Blocks of 256 threads own contiguous ranges of 1024-slot tiles; thread t handles slots
+// t, t+256, t+512, t+768 of a tile ("virtual warp" vw = 8*r + warp covers 32 consecutive slots).
+// -----------------------------------------------------------------------------
+
+// exclusive prefix of per-block totals in shared memory (n <= kMaxGrid): warp 0 scans 32
+// entries per step with shuffles; executed by the whole block
+__device__ __forceinline__ unsigned block_prefix_of(const uint32_t* blk_tot, unsigned nblk, unsigned b, unsigned* s_tmp,
+                                                    unsigned& grand_total) {
+  __syncthreads();  // s_tmp may still be read from a previous use
+  for (unsigned k = threadIdx.x; k < nblk; k += blockDim.x) s_tmp[k] = __ldcg(blk_tot + k);  // one parallel pass
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const unsigned lane = threadIdx.x;
+    unsigned run = 0;
+    for (unsigned base = 0; base < nblk; base += 32) {
+      const unsigned k = base + lane;
+      const unsigned v = k < nblk ? s_tmp[k] : 0u;
+      unsigned tot;
+      const unsigned ex = warp_excl_scan(v, tot);
+      if (k < nblk) s_tmp[k] = run + ex;
+      run += tot;
+    }
+    if (lane == 0) s_tmp[nblk] = run;
   }
-  const unsigned long long bi = st->buf_index;
-  st->n_add = bi < st->buf_cap_eff ? bi : st->buf_cap_eff;
-  st->buf_index = 0;
+  __syncthreads();
+  grand_total = s_tmp[nblk];
+  return s_tmp[b];
+}
+
+// flags of the four slots a thread owns in `tile` + per-virtual-warp counts in s_w[32];
+// returns (by reference) the ballots; ends with a barrier so that s_w is complete
+template <bool WANT_GAP>
+__device__ __forceinline__ void tile_flags(const PostParams& p, uint32_t tile, unsigned long long old_n, unsigned long long new_n,
+                                           unsigned (&bal)[4], bool (&flag)[4], unsigned* s_w) {
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const unsigned long long i = (unsigned long long)tile * kTile + (unsigned)r * 256u + threadIdx.x;
+    bool f = false;
+    if (i < old_n) {
+      const bool is_idle = p.status[i] == (uint8_t)Idle;
+      f = WANT_GAP ? (i < new_n && !is_idle) : (i >= new_n && is_idle);
+    }
+    flag[r] = f;
+    bal[r] = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) s_w[r * 8 + warp] = __popc(bal[r]);
+  }
+  __syncthreads();
+}
+
+// Grid-wide barrier for cooperatively launched kernels (all blocks resident): arrive counter +
+// generation word in DevState.
+__device__ __forceinline__ void grid_barrier(DevState* st) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned gen = *reinterpret_cast<volatile unsigned*>(&st->bar_gen);
+    if (atomicAdd(&st->bar_count, 1u) == gridDim.x - 1) {
+      st->bar_count = 0;
+      __threadfence();
+      atomicAdd(&st->bar_gen, 1u);
+    } else {
+      while (*reinterpret_cast<volatile unsigned*>(&st->bar_gen) == gen) __nanosleep(20);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// InsertFunctor (particles_container.hpp:403-443): buffer row j -> container slot dst
+__device__ __forceinline__ void insert_newborn(const PostParams& p, unsigned long long j, unsigned long long dst, uint32_t npos) {
+  for (int c0 = 0; c0 < p.n_var; c0 += 8) {  // loads first, then stores: one round trip per 8 columns
+    float t[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) if (c0 + c < p.n_var) t[c] = __ldcg(p.buf_props + (size_t)(c0 + c) * p.buf_stride + j);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) if (c0 + c < p.n_var) p.props[(size_t)(c0 + c) * p.cap + dst] = t[c];
+  }
+  p.pos[dst] = npos;
+  // both ages reset (eager: 0.f; stamped: the newborn ages from the next step on)
+  reinterpret_cast<uint32_t*>(p.age_hyd)[dst] = p.newborn_stamp;
+  reinterpret_cast<uint32_t*>(p.age_div)[dst] = p.newborn_stamp;
+  p.status[dst] = (uint8_t)Idle;
+}
+
+// must be entered by every block of a cooperative launch, after a grid barrier that follows the
+// last write to the particle state, the division buffer and the device counters
+static __device__ __forceinline__ void post_cycle_body(const PostParams& p) {
+  __shared__ unsigned s_pref[kMaxGrid + 1];
+  __shared__ unsigned s_w[32];
+  DevState* const st = p.st;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned long long gtid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long gstride = (unsigned long long)gridDim.x * blockDim.x;
+  // ---- publish the source terms of this step; the accumulator is left zeroed for the next one
+  for (unsigned long long k = gtid; k < p.n_bins; k += gstride) {
+    p.sources[k] = __ldcg(p.acc + k);
+    p.acc[k] = 0.0;
+  }
+  BMC_STAMP(st, 5);
+  // ---- plan (read-only on the counters: every block derives the same values; one warp per block
+  // reads them, so that the few counter lines are not hammered by every thread of the grid)
+  __shared__ unsigned long long s_plan[6];
+  if (threadIdx.x < 6) {
+    const unsigned long long* src = threadIdx.x == 0 ? &st->step_exit : threadIdx.x == 1 ? &st->n_used : threadIdx.x == 2 ? &st->inactive
+                                  : threadIdx.x == 3 ? &st->buf_index : threadIdx.x == 4 ? &st->buf_cap_eff : nullptr;
+    s_plan[threadIdx.x] = src ? __ldcg(src) : (unsigned long long)__ldcg(&st->force_compact);
+  }
+  __syncthreads();
+  const unsigned long long out = s_plan[0];
+  const unsigned long long n_before = s_plan[1];
+  const unsigned long long inactive = s_plan[2] + out;  // inactive_counter += out; += dead (always 0, Q3)
+  unsigned long long thr = (unsigned long long)((double)n_before * p.dead_ratio);
+  if (p.min_removal > thr) thr = p.min_removal;
+  const bool do_compact = (inactive > thr) || (s_plan[5] && inactive > 0);
+  const unsigned long long old_n = n_before, new_n = do_compact ? n_before - inactive : n_before;
+  const unsigned long long n_add = s_plan[3] < s_plan[4] ? s_plan[3] : s_plan[4];
+
+  if (do_compact) {  // uniform across the grid
+    const uint32_t n_tiles = (uint32_t)((old_n + kTile - 1) / kTile);
+    const uint32_t t0 = (uint32_t)(((unsigned long long)blockIdx.x * n_tiles) / gridDim.x);
+    const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
+    // ---- count ----
+    {
+      unsigned run_g = 0, run_i = 0;
+      for (uint32_t tile = t0; tile < t1; ++tile) {
+        unsigned bal[4]; bool fl[4];
+        tile_flags<true>(p, tile, old_n, new_n, bal, fl, s_w);
+        unsigned tg = 0;
+        if (warp == 0) tg = __reduce_add_sync(0xffffffffu, s_w[lane]);
+        __syncthreads();
+        tile_flags<false>(p, tile, old_n, new_n, bal, fl, s_w);
+        if (warp == 0) {
+          const unsigned ti = __reduce_add_sync(0xffffffffu, s_w[lane]);
+          if (lane == 0) { p.tile_gap_off[tile] = run_g; p.tile_idle_off[tile] = run_i; }
+          run_g += tg; run_i += ti;
+        }
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) { p.blk_gap[blockIdx.x] = run_g; p.blk_idle[blockIdx.x] = run_i; }
+    }
+    grid_barrier(st);
+    // ---- src: k-th idle tail particle counted from the end ----
+    unsigned total_idle;
+    {
+      const unsigned blk_off = block_prefix_of(p.blk_idle, gridDim.x, blockIdx.x, s_pref, total_idle);
+      const uint32_t first_tail_tile = (uint32_t)(new_n / kTile);
+      for (uint32_t tile = (t0 > first_tail_tile ? t0 : first_tail_tile); tile < t1; ++tile) {
+        unsigned bal[4]; bool fl[4];
+        tile_flags<false>(p, tile, old_n, new_n, bal, fl, s_w);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          if (fl[r]) {
+            unsigned woff = 0;
+            for (unsigned k = 0; k < (unsigned)r * 8u + warp; ++k) woff += s_w[k];
+            const unsigned asc = blk_off + p.tile_idle_off[tile] + woff + __popc(bal[r] & ((1u << lane) - 1u));
+            p.src[total_idle - 1u - asc] = (uint32_t)((unsigned long long)tile * kTile + (unsigned)r * 256u + threadIdx.x);
+          }
+        }
+        __syncthreads();
+      }
+    }
+    grid_barrier(st);
+    // ---- move: gaps below new_n pull their replacement ----
+    {
+      unsigned total_gap;
+      const unsigned blk_off = block_prefix_of(p.blk_gap, gridDim.x, blockIdx.x, s_pref, total_gap);
+      const uint32_t last_low_tile = (uint32_t)((new_n + kTile - 1) / kTile);  // exclusive
+      for (uint32_t tile = t0; tile < t1 && tile < last_low_tile; ++tile) {
+        unsigned bal[4]; bool fl[4];
+        tile_flags<true>(p, tile, old_n, new_n, bal, fl, s_w);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          if (fl[r]) {
+            unsigned woff = 0;
+            for (unsigned k = 0; k < (unsigned)r * 8u + warp; ++k) woff += s_w[k];
+            const unsigned k = blk_off + p.tile_gap_off[tile] + woff + __popc(bal[r] & ((1u << lane) - 1u));
+            if (k >= total_idle) {
+              atomicOr(&st->error, 2u);  // inactive counter inconsistent with the status column
+            } else {
+              const size_t i = (size_t)tile * kTile + (unsigned)r * 256u + threadIdx.x;
+              const size_t s2 = p.src[k];
+              p.status[i] = (uint8_t)Idle;
+              p.pos[i] = p.pos[s2];
+              for (int c = 0; c < p.n_var; ++c) p.props[(size_t)c * p.cap + i] = p.props[(size_t)c * p.cap + s2];
+              p.age_hyd[i] = p.age_hyd[s2];
+              p.age_div[i] = p.age_div[s2];
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    grid_barrier(st);
+    // slots [new_n, old_n) left the container: mark them Idle so that appended newborns never inherit
+    // a stale status (the reference relies on zero-initialised storage, particles_container.hpp:403-443).
+    // Newborn slots below are written Idle as well, so the two writers agree where they overlap.
+    for (unsigned long long i = new_n + gtid; i < old_n; i += gstride) p.status[i] = (uint8_t)Idle;
+  }
+
+  BMC_STAMP(st, 6);
+  // Newborn of mother i goes to new_n + (number of dividing mothers with a smaller slot index).
+  constexpr unsigned kSmallAdd = kMaxGrid;  // records that fit the shared scratch: ranked by direct comparison
+  if (n_add && n_add <= kSmallAdd) {  // uniform across the grid; the usual case (a few hundred divisions per step)
+    if ((unsigned long long)blockIdx.x * blockDim.x < n_add) {  // blocks that have a newborn to place
+      for (unsigned j = threadIdx.x; j < (unsigned)n_add; j += blockDim.x) s_pref[j] = __ldcg(p.buf_mother + j);
+      __syncthreads();
+      const unsigned long long j = gtid;
+      if (j < n_add) {
+        const uint32_t mother = s_pref[j];
+        const uint32_t npos = __ldcg(p.buf_pos + j);
+        unsigned rank = 0;
+        for (unsigned q = 0; q < (unsigned)n_add; ++q) rank += (s_pref[q] < mother) ? 1u : 0u;
+        insert_newborn(p, j, new_n + rank, npos);
+      }
+    }
+  } else if (n_add) {
+    // Many divisions: counts per tile = popcount of the tile's 32 mask words (rewritten by the particle
+    // pass for every group below n_used); block-local exclusive prefix over this block's contiguous tile
+    // range -> tile_off, range total -> blk_total.  Then, behind a barrier, the global offsets.
+    const unsigned G = gridDim.x;
+    const uint32_t T = (uint32_t)((old_n + kTile - 1) / kTile);
+    const uint32_t t0 = (uint32_t)(((unsigned long long)blockIdx.x * T) / G);
+    const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * T) / G);
+    const unsigned long long words_valid = (old_n + 31ull) / 32ull;  // words beyond the last slot are stale
+#pragma unroll 4
+    for (uint32_t t = t0 + warp; t < t1; t += kBlock / 32) {
+      const unsigned long long wi = (unsigned long long)t * (kTile / 32) + lane;
+      const unsigned wv = wi < words_valid ? __ldcg(p.div_mask + wi) : 0u;
+      const unsigned c = __reduce_add_sync(0xffffffffu, (unsigned)__popc(wv));
+      if (lane == 0) p.tile_off[t] = c;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      unsigned run = 0;
+      for (uint32_t base = t0; base < t1; base += 32) {
+        const uint32_t t = base + lane;
+        const unsigned cnt = (t < t1) ? __ldcg(p.tile_off + t) : 0u;
+        unsigned tot;
+        const unsigned ex = warp_excl_scan(cnt, tot);
+        if (t < t1) p.tile_off[t] = run + ex;
+        run += tot;
+      }
+      if (lane == 0) p.blk_total[blockIdx.x] = run;
+    }
+    grid_barrier(st);
+    if ((unsigned long long)blockIdx.x * blockDim.x < n_add) {  // blocks that have a newborn to place
+      unsigned total;
+      block_prefix_of(p.blk_total, G, 0, s_pref, total);
+    }
+    for (unsigned long long j = gtid; j < n_add; j += gstride) {
+      const uint32_t mother = __ldcg(p.buf_mother + j);
+      const uint32_t tile = mother >> 10;
+      const unsigned b = (unsigned)((((unsigned long long)tile + 1ull) * G - 1ull) / T);  // owner block of the tile
+      // rank of the mother among the dividing mothers of its tile: all 32 mask words in one round trip
+      const uint4* w4 = reinterpret_cast<const uint4*>(p.div_mask + (size_t)tile * (kTile / 32));
+      const unsigned wi = (mother & (kTile - 1)) >> 5, bit = mother & 31u;
+      uint4 w[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) w[q] = __ldcg(w4 + q);
+      const unsigned toff = __ldcg(p.tile_off + tile);
+      const uint32_t npos = __ldcg(p.buf_pos + j);
+      unsigned rank = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const unsigned ww[4] = {w[q].x, w[q].y, w[q].z, w[q].w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const unsigned idx = (unsigned)(4 * q + c);
+          const unsigned m = idx < wi ? 0xffffffffu : (idx == wi ? ((1u << bit) - 1u) : 0u);
+          rank += __popc(ww[c] & m);
+        }
+      }
+      insert_newborn(p, j, new_n + s_pref[b] + toff + rank, npos);
+    }
+  }
+  BMC_STAMP(st, 7);
+  // commit: the last block to get here (every other block is done reading the counters)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(&st->done_blocks, 1u) == gridDim.x - 1) {
+    __threadfence();
+    st->done_blocks = 0; st->next_group = 0;
+    st->last_out = out; st->last_dead = 0; st->last_waiting = st->step_waiting;
+    st->total_out += out;
+    st->step_exit = 0; st->step_waiting = 0; st->buf_index = 0; st->force_compact = 0;
+    st->inactive = do_compact ? 0ull : inactive;
+    if (do_compact) st->n_compactions += 1;
+    st->do_compact = do_compact ? 1u : 0u; st->cmp_old_n = old_n; st->cmp_new_n = new_n; st->n_add = n_add;  // for inspection
+    const unsigned long long n = new_n + n_add;
+    st->n_used = n;
+    st->total_new += n_add;
+    st->step += (unsigned long long)p.count_step;
+    // room of the next step's division buffer: min(B, capacity - n_used); the device can never write
+    // past the capacity, growth is done lazily by the host
+    const unsigned long long room = p.cap > n ? p.cap - n : 0ull;
+    st->buf_cap_eff = p.buf_cap < room ? p.buf_cap : room;
+    if (p.tab_extend) {  // A[k+1] = fl(A[k] + d_t): exactly the accumulation an eagerly updated age goes through
+      p.tab_div[p.tab_idx + 1] = p.tab_div[p.tab_idx] + p.dt_f;                       // model_kernel.hpp:191 (float d_t)
+      p.tab_hyd[p.tab_idx + 1] = p.enable_leave ? (float)((double)p.tab_hyd[p.tab_idx] + p.dt)  // move_kernel.hpp:596 (double d_t)
+                                                : p.tab_hyd[p.tab_idx];
+    }
+  }
 }
 
 // -----------------------------------------------------------------------------
@@ -290,12 +621,13 @@ template <class M> struct ReadCols {
   static constexpr uint64_t all = M::n_var >= 64 ? ~0ull : ((1ull << M::n_var) - 1ull);
   static constexpr int value = M::n_var - popcount_c((uint64_t)M::write_only_mask & all);
 };
-// One staging buffer of the bulk-copy pipeline holds one GROUP = kBlock*VEC consecutive slots:
-// pos and the read columns (kBlock*VEC*4 bytes each), then the status bytes.  (The pipeline is
-// built for step-stamped ages only, so no age column is staged.)
+// One staging buffer of the bulk-copy pipeline holds one GROUP = 32*VEC consecutive slots (the work
+// unit of a warp): pos and the read columns (32*VEC*4 bytes each), then the status bytes.  Every warp
+// has kStages private buffers.  (The pipeline is built for step-stamped ages only: no age column.)
 template <class M, int VEC> struct StageBytes {
-  static constexpr size_t col = (size_t)kBlock * 4 * VEC;
-  static constexpr size_t value = (size_t)(1 + ReadCols<M>::value) * col + (size_t)kBlock * VEC;
+  static constexpr size_t col = (size_t)32 * 4 * VEC;
+  static constexpr size_t warp_stage = (size_t)(1 + ReadCols<M>::value) * col + (size_t)32 * VEC;
+  static constexpr size_t value = warp_stage * (kBlock / 32);  // one stage of a whole block
 };
 constexpr int kStages = 2;
 
@@ -330,22 +662,26 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 template <class M, int VEC, bool PIPE, bool LAZY> __device__ __forceinline__ void cycle_body(const CycleParams& p) {
   static_assert(!PIPE || LAZY, "the bulk-copy pipeline is built for step-stamped ages only");
   constexpr int NV = M::n_var, NC = M::n_c, CT = 1 + M::n_pre;
-  constexpr int SUB = kTile / (kBlock * VEC);  // sub-iterations per tile
-  constexpr int kColStride = kBlock * 4 * VEC;  // bytes between staged columns
-  constexpr size_t kStage = StageBytes<M, VEC>::value;
+  constexpr uint32_t kGroup = 32 * VEC;         // slots per group: the work unit of one warp
+  constexpr int kColStride = 32 * 4 * VEC;      // bytes between staged columns of a warp's buffer
+  constexpr size_t kWarpStage = StageBytes<M, VEC>::warp_stage;
   extern __shared__ __align__(128) double s_bins[];  // [n_species * n_comp] when bins_in_smem, then kStages staging buffers
   __shared__ unsigned long long s_cnt[4];      // move, exit, new, overflow
 
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned long long n_used = p.st->n_used;
   const unsigned long long buf_cap = p.st->buf_cap_eff;
-  const uint32_t n_tiles = (uint32_t)((n_used + kTile - 1) / kTile);
-  const uint32_t t0 = (uint32_t)(((unsigned long long)blockIdx.x * n_tiles) / gridDim.x);
-  const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
+  // Work distribution: the slots are cut into groups of 32*VEC; every warp of the (persistent,
+  // fully resident) grid starts with the group of its own index and then draws further groups from
+  // a device-wide counter — one L2 atomic per group, issued one group ahead so that its latency is
+  // hidden.  Blocks that start late or run on a slower SM simply process fewer groups.
+  const uint32_t n_groups = (uint32_t)((n_used + kGroup - 1) / kGroup);
+  const uint32_t total_warps = gridDim.x * (kBlock / 32);
   const uint32_t n_bins = p.n_species * p.n_comp;
   const bool single_comp = (p.n_comp == 1);
   const bool smem_bins = p.bins_in_smem && !single_comp;
 
+  BMC_STAMP(p.st, 0);
   if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0ull;
   if (smem_bins)
     for (uint32_t k = threadIdx.x; k < n_bins; k += kBlock) s_bins[k] = 0.0;
@@ -360,6 +696,7 @@ template <class M, int VEC, bool PIPE, bool LAZY> __device__ __forceinline__ voi
   }
   __syncthreads();
 
+  BMC_STAMP(p.st, 1);
   unsigned c_move = 0, c_exit = 0, c_new = 0, c_over = 0;
   double acc0d[NC];  // single-compartment accumulation lives in registers
 #pragma unroll
@@ -373,47 +710,43 @@ template <class M, int VEC, bool PIPE, bool LAZY> __device__ __forceinline__ voi
   const uint32_t outlet0 = p.n_flows > 0 ? p.outlets[0].index : 0xffffffffu;
   const bool outlet0_live = p.n_flows > 0 && p.outlets[0].flow != 0.;
 
-  // PIPE: two-stage bulk-copy pipeline.  One elected thread arms the stage's mbarrier with the byte
-  // count and issues one cp.async.bulk (TMA, 1-D) per column for the NEXT group of kBlock*VEC
-  // slots; the bytes land in shared memory while the block computes the current group, so the
-  // HBM latency is off the critical path and no registers are held by loads in flight.  Thread t
-  // then reads bytes [t*4*VEC, (t+1)*4*VEC) of every staged column (conflict-free LDS.128).
+  // PIPE: two-stage bulk-copy pipeline, private to each warp.  Lane 0 arms the stage's mbarrier with
+  // the byte count and issues one cp.async.bulk (TMA, 1-D) per column for the warp's NEXT group; the
+  // bytes land in shared memory while the warp computes its current group, so the HBM latency is off
+  // the critical path and no registers are held by loads in flight.  Lane l then reads bytes
+  // [l*4*VEC, (l+1)*4*VEC) of every staged column (conflict-free LDS.128).  No block-wide barrier.
   unsigned char* const s_stage = reinterpret_cast<unsigned char*>(s_bins) + p.stage_offset;
-  __shared__ __align__(8) unsigned long long s_bar[kStages];
-  const uint32_t n_used32 = (uint32_t)n_used;
-  auto slot_base = [&](uint32_t tile, int sub) -> uint32_t {
-    return tile * (uint32_t)kTile + ((uint32_t)sub * (kBlock / 32) + warp) * (32 * VEC) + lane * VEC;
-  };
+  __shared__ __align__(8) unsigned long long s_bar[kStages][kBlock / 32];
   constexpr unsigned kColBytes = (unsigned)kColStride;
-  auto issue = [&](uint32_t it, int buf) {  // executed by thread 0 only
-    const size_t g0 = (size_t)(t0 * SUB + it) * (kBlock * VEC);  // first slot of the group (whole group < capacity)
-    unsigned char* dst = s_stage + (size_t)buf * kStage;
-    unsigned long long* bar = &s_bar[buf];
-    mbar_expect_tx(bar, (unsigned)kStage);
+  auto issue = [&](uint32_t g, int buf) {  // executed by lane 0 of the warp
+    const size_t g0 = (size_t)g * kGroup;  // first slot of the group (the whole group is below the capacity)
+    unsigned char* dst = s_stage + ((size_t)buf * (kBlock / 32) + warp) * kWarpStage;
+    unsigned long long* bar = &s_bar[buf][warp];
+    mbar_expect_tx(bar, (unsigned)kWarpStage);
     bulk_g2s(dst, p.pos + g0, kColBytes, bar);
     int c = 1;
 #pragma unroll
     for (int k = 0; k < NV; ++k)
       if (!col_flag(M::write_only_mask, k)) { bulk_g2s(dst + c * kColStride, p.props + (size_t)k * p.cap + g0, kColBytes, bar); ++c; }
-    bulk_g2s(dst + (size_t)(1 + ReadCols<M>::value) * kColStride, p.status + g0, (unsigned)(kBlock * VEC), bar);
+    bulk_g2s(dst + (size_t)(1 + ReadCols<M>::value) * kColStride, p.status + g0, (unsigned)kGroup, bar);
   };
 
   {
-    // Every tile but the last is entirely below n_used: the body is instantiated twice so that the
+    // Every group but the last is entirely below n_used: the body is instantiated twice so that the
     // common case carries no per-slot range checks (FULL), the ragged tail keeps them.
-    auto body = [&](auto full_tag, const uint32_t tile, const int sub, const int buf, const uint32_t stw_in) {
+    auto body = [&](auto full_tag, const uint32_t g, const int buf) {
       constexpr bool FULL = decltype(full_tag)::value;
-      const uint32_t i_raw = slot_base(tile, sub);
-      const bool live = FULL || i_raw < n_used32;  // false only in the ragged end of the last tile
+      const uint32_t i_raw = g * kGroup + lane * VEC;
+      const bool live = FULL || i_raw < n_used;    // false only in the ragged end of the last group
       const size_t i0 = live ? i_raw : 0u;         // dead lanes shadow slot 0 (loads stay in range, nothing is stored)
 
       uint32_t pos[VEC]; float adiv[VEC], ahyd[VEC]; float v[VEC][NV], old[VEC][NV];
       uint32_t stw;
       if constexpr (PIPE) {
         // ---- operands were staged in shared memory by the bulk copies issued one iteration ago ----
-        const unsigned char* stage = s_stage + (size_t)buf * kStage;
-        const unsigned char* src = stage + threadIdx.x * (4 * VEC);
-        stw = VecIO<VEC>::ldb_plain(stage + (size_t)(1 + ReadCols<M>::value) * kColStride + threadIdx.x * VEC);
+        const unsigned char* stage = s_stage + ((size_t)buf * (kBlock / 32) + warp) * kWarpStage;
+        const unsigned char* src = stage + lane * (4 * VEC);
+        stw = VecIO<VEC>::ldb_plain(stage + (size_t)(1 + ReadCols<M>::value) * kColStride + lane * VEC);
         VecIO<VEC>::ldu_plain(reinterpret_cast<const uint32_t*>(src), pos);
         int c = 1;
 #pragma unroll
@@ -699,40 +1032,54 @@ template <class M, int VEC, bool PIPE, bool LAZY> __device__ __forceinline__ voi
         for (int q = 0; q < VEC; ++q) if ((exit_nib >> q) & 1u) p.status[i0 + q] = (uint8_t)Exit;
       }
     };
+    uint32_t g = blockIdx.x * (kBlock / 32) + warp;  // first group: the warp's own index
     if constexpr (PIPE) {
-      const uint32_t n_it = (t1 - t0) * SUB;
-      if (threadIdx.x == 0) {
+      if (lane == 0) {
 #pragma unroll
-        for (int b = 0; b < kStages; ++b) mbar_init(&s_bar[b], 1u);
+        for (int b = 0; b < kStages; ++b) mbar_init(&s_bar[b][warp], 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       }
-      __syncthreads();
-      if (threadIdx.x == 0 && n_it) issue(0, 0);
+      __syncwarp();
+      uint32_t nxt = 0;
+      if (lane == 0) {
+        if (g < n_groups) issue(g, 0);
+        nxt = atomicAdd(&p.st->next_group, 1u);  // the pipeline needs the next group one iteration ahead
+      }
 #pragma unroll 1
-      for (uint32_t it = 0; it < n_it; ++it) {
+      for (uint32_t it = 0; g < n_groups; ++it) {
         const int buf = (int)(it & 1u);
-        // every thread is done reading the other buffer (iteration it-1): it may be refilled
-        __syncthreads();
-        if (threadIdx.x == 0 && it + 1 < n_it) issue(it + 1, buf ^ 1);
-        mbar_wait(&s_bar[buf], (it >> 1) & 1u);
-        const uint32_t tile = t0 + it / SUB;
-        if ((unsigned long long)(tile + 1) * kTile <= n_used) body(FullTile{}, tile, (int)(it % SUB), buf, 0u);
-        else body(RaggedTile{}, tile, (int)(it % SUB), buf, 0u);
+        const uint32_t g_next = total_warps + __shfl_sync(0xffffffffu, nxt, 0);
+        __syncwarp();  // every lane is done reading the other buffer (previous iteration): it may be refilled
+        if (lane == 0) {
+          if (g_next < n_groups) issue(g_next, buf ^ 1);
+          nxt = atomicAdd(&p.st->next_group, 1u);
+        }
+        mbar_wait(&s_bar[buf][warp], (it >> 1) & 1u);
+        if ((unsigned long long)(g + 1) * kGroup <= n_used) body(FullTile{}, g, buf);
+        else body(RaggedTile{}, g, buf);
+        g = g_next;
       }
     } else {
 #pragma unroll 1
-      for (uint32_t tile = t0; tile < t1; ++tile) {
-        if ((unsigned long long)(tile + 1) * kTile <= n_used) {
-#pragma unroll 1
-          for (int sub = 0; sub < SUB; ++sub) body(FullTile{}, tile, sub, 0, 0u);
-        } else {
-#pragma unroll 1
-          for (int sub = 0; sub < SUB; ++sub) body(RaggedTile{}, tile, sub, 0, 0u);
-        }
+      while (g < n_groups) {
+        uint32_t nxt = 0;
+        if (lane == 0) nxt = atomicAdd(&p.st->next_group, 1u);  // consumed after this group: latency hidden
+        if ((unsigned long long)(g + 1) * kGroup <= n_used) body(FullTile{}, g, 0);
+        else body(RaggedTile{}, g, 0);
+        g = total_warps + __shfl_sync(0xffffffffu, nxt, 0);
       }
     }
   }
 
+  BMC_STAMP(p.st, 2);
+#if defined(BMC_TIMELINE)
+  if (threadIdx.x == 0) {  // per-block end of the particle pass + number of tiles, into the (idle) compaction scratch
+    unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+    unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.post.src[4 * blockIdx.x] = (uint32_t)t_; p.post.src[4 * blockIdx.x + 1] = (uint32_t)(t_ >> 32);
+    p.post.src[4 * blockIdx.x + 2] = 0u; p.post.src[4 * blockIdx.x + 3] = smid;
+  }
+#endif
   // ---- block epilogue: counters, source flush, block-local tile prefix -------
   const unsigned cm = __reduce_add_sync(0xffffffffu, c_move), ce = __reduce_add_sync(0xffffffffu, c_exit);
   const unsigned cn = __reduce_add_sync(0xffffffffu, c_new), co = __reduce_add_sync(0xffffffffu, c_over);
@@ -760,50 +1107,22 @@ template <class M, int VEC, bool PIPE, bool LAZY> __device__ __forceinline__ voi
     if (s_cnt[3]) { atomicAdd(&p.st->events[4], s_cnt[3]); atomicAdd(&p.st->step_waiting, s_cnt[3]); }  // Overflow
   }
   if (smem_bins) {
-    for (uint32_t k = threadIdx.x; k < n_bins; k += kBlock) {
+    // every block starts at a different bin, so that the blocks (which finish together) do not hit
+    // the same L2 addresses at the same time
+    const uint32_t rot = (uint32_t)(((unsigned long long)blockIdx.x * n_bins) / gridDim.x);
+    for (uint32_t k0 = threadIdx.x; k0 < n_bins; k0 += kBlock) {
+      uint32_t k = k0 + rot; if (k >= n_bins) k -= n_bins;
       const double a = s_bins[k];
       if (a != 0.0) atomicAdd(p.acc + k, a);
     }
   }
-  // per-tile division counts = popcount of the tile's 32 mask words (written above by this block,
-  // visible after the barrier), then their block-local exclusive prefix -> tile_off, blk_total
-  for (uint32_t t = t0 + warp; t < t1; t += kBlock / 32) {
-    const unsigned c = __reduce_add_sync(0xffffffffu, (unsigned)__popc(__ldcg(p.div_mask + (size_t)t * (kTile / 32) + lane)));
-    if (lane == 0) p.tile_off[t] = c;
-  }
-  __syncthreads();
-  if (warp == 0) {
-    unsigned run = 0;
-    for (uint32_t base = t0; base < t1; base += 32) {
-      const uint32_t t = base + lane;
-      const unsigned cnt = (t < t1) ? __ldcg(p.tile_off + t) : 0u;
-      unsigned tot;
-      const unsigned ex = warp_excl_scan(cnt, tot);
-      if (t < t1) p.tile_off[t] = run + ex;
-      run += tot;
-    }
-    if (lane == 0) p.blk_total[blockIdx.x] = run;
-  }
-  // last block to finish: every block's counters are visible (fence + ticket) -> write the
-  // post-cycle plan (compaction trigger, newborn count) for the kernels that follow
-  __threadfence();
-  __syncthreads();
-  __shared__ unsigned s_last;
-  if (threadIdx.x == 0) s_last = (atomicAdd(&p.st->done_blocks, 1u) == gridDim.x - 1) ? 1u : 0u;
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    // scatter_contribute + synchro_sources (simulation.cpp:143-151, implScalar.cpp:194-205): publish the
-    // source terms of this step and leave the accumulator zeroed for the next one
-    for (uint32_t k = threadIdx.x; k < n_bins; k += kBlock) {
-      p.sources[k] = __ldcg(p.acc + k);
-      p.acc[k] = 0.0;
-    }
-    if (threadIdx.x == 0) {
-      p.st->done_blocks = 0;
-      p.st->cyc_n_used = n_used; p.st->cyc_tiles = n_tiles; p.st->cyc_grid = gridDim.x;
-      make_plan(p.st, p.min_removal, p.dead_ratio);
-    }
+  // ---- second phase of the step: every block's state, buffer rows and counters are complete
+  BMC_STAMP(p.st, 3);
+  if (p.fuse_post) {
+    grid_barrier(p.st);
+    BMC_STAMP(p.st, 4);
+    post_cycle_body(p.post);
+    BMC_STAMP(p.st, 8);
   }
 }
 
