@@ -190,14 +190,19 @@ static int configure_launch(bmc_ctx* ctx) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, ctx->device));
   ctx->n_sm = prop.multiProcessorCount;
-  const size_t bins_bytes = ctx->n_species * ctx->n_comp * sizeof(double);
-  // Keep >= 2 resident blocks per SM when the bins live in shared memory.
+  // One block per SM: its dynamic shared memory holds the fp64 source bins (shared by all its warps),
+  // the compartment table when it is small, and the staging buffers of the bulk-copy pipeline.
   const size_t smem_budget = (size_t)prop.sharedMemPerBlockOptin;
-  ctx->bins_in_smem = (ctx->n_comp > 1 && bins_bytes <= std::min<size_t>(smem_budget, 100 * 1024)) ? 1 : 0;
-  ctx->smem_bins = ctx->bins_in_smem ? bins_bytes : 0;
-  // small compartment tables are rebuilt by every cycle block in shared memory (no pre_step launch)
+  const size_t static_reserve = 12 * 1024;  // static shared memory of the step kernel (post-cycle scratch, barriers)
   const size_t ctab_bytes = ctx->n_comp * (size_t)ctx->vt.ct * sizeof(float);
-  ctx->ctab_in_smem = (ctx->n_comp > 1 && ctab_bytes <= 16 * 1024) ? 1 : 0;
+  const size_t bins_bytes = ctx->n_species * ctx->n_comp * sizeof(double);
+  size_t room = smem_budget > static_reserve + ctx->vt.stage_bytes + 1024 ? smem_budget - static_reserve - ctx->vt.stage_bytes - 1024 : 0;
+  // first the bins (block-private accumulation instead of L2 atomics per particle), then the table
+  // (rebuilt by every block: no pre_step launch, gathers served from shared memory instead of L1/L2)
+  ctx->bins_in_smem = (ctx->n_comp > 1 && bins_bytes <= room) ? 1 : 0;
+  ctx->smem_bins = ctx->bins_in_smem ? bins_bytes : 0;
+  room -= ctx->smem_bins;
+  ctx->ctab_in_smem = (ctx->n_comp > 1 && ctab_bytes + 256 <= room) ? 1 : 0;
   if (const char* e = getenv("BMC_CTAB_SMEM")) ctx->ctab_in_smem = (ctx->ctab_in_smem && atoi(e) != 0) ? 1 : 0;  // tuning runs
   ctx->ctab_offset = (ctx->smem_bins + 15) / 16 * 16;
   ctx->stage_offset = (ctx->ctab_offset + (ctx->ctab_in_smem ? ctab_bytes : 0) + 127) / 128 * 128;
@@ -207,12 +212,12 @@ static int configure_launch(bmc_ctx* ctx) {
   ctx->grid_post = ctx->n_sm;           // cooperative launch: one block per SM is always co-resident
   if (const char* e = getenv("BMC_FUSE_POST")) ctx->fuse_post = atoi(e) != 0;
   const char* env = getenv("BMC_BLOCKS_PER_SM");
-  auto grid_of = [&](const void* fn, size_t smem, int& grid, int* occ_out) -> int {
+  auto grid_of = [&](const void* fn, int block, size_t smem, int& grid, int* occ_out) -> int {
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kBlock, smem) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, block, smem) != cudaSuccess) {
       (void)cudaGetLastError();
-      occ = ctx->vt.minb;  // JIT kernel handle not accepted by the occupancy query: trust __launch_bounds__
+      occ = 1;  // JIT kernel handle not accepted by the occupancy query: trust __launch_bounds__(block, 1)
     }
     if (occ < 1) occ = 1;
     if (env && atoi(env) > 0) occ = std::min(occ, atoi(env));
@@ -221,13 +226,13 @@ static int configure_launch(bmc_ctx* ctx) {
     return BMC_OK;
   };
   int rc;
-  if ((rc = grid_of(ctx->vt.cycle_fn, ctx->smem_total, ctx->grid_cycle, &ctx->blocks_per_sm))) return rc;
-  if ((rc = grid_of(ctx->vt.cycle_eager_fn, ctx->smem_eager, ctx->grid_cycle_eager, nullptr))) return rc;
+  if ((rc = grid_of(ctx->vt.cycle_fn, ctx->vt.block, ctx->smem_total, ctx->grid_cycle, &ctx->blocks_per_sm))) return rc;
+  if ((rc = grid_of(ctx->vt.cycle_eager_fn, ctx->vt.block_eager, ctx->smem_eager, ctx->grid_cycle_eager, nullptr))) return rc;
   if (getenv("BMC_VERBOSE")) {
     cudaFuncAttributes fa{};
     cudaFuncGetAttributes(&fa, ctx->vt.cycle_fn);
-    fprintf(stderr, "[bmc] step kernel: grid %d (%d blocks/SM x %d SMs), %d regs, smem static %zu + dynamic %zu B (bins %zu, table %s, staging %zu), eager grid %d\n",
-            ctx->grid_cycle, ctx->blocks_per_sm, ctx->n_sm, fa.numRegs, fa.sharedSizeBytes, ctx->smem_total, ctx->smem_bins,
+    fprintf(stderr, "[bmc] step kernel: grid %d (%d blocks/SM x %d SMs) x %d threads, %d regs, smem static %zu + dynamic %zu B (bins %zu, table %s, staging %zu), eager grid %d\n",
+            ctx->grid_cycle, ctx->blocks_per_sm, ctx->n_sm, ctx->vt.block, fa.numRegs, fa.sharedSizeBytes, ctx->smem_total, ctx->smem_bins,
             ctx->ctab_in_smem ? "smem" : "global", ctx->vt.stage_bytes, ctx->grid_cycle_eager);
   }
   return BMC_OK;
@@ -785,12 +790,13 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   void* cargs[] = {&p};
   p.fuse_post = ctx->fuse_post ? 1 : 0;
   const void* fn = ctx->lazy_ages ? ctx->vt.cycle_fn : ctx->vt.cycle_eager_fn;
+  const int block = ctx->lazy_ages ? ctx->vt.block : ctx->vt.block_eager;
   const size_t smem = ctx->lazy_ages ? ctx->smem_total : ctx->smem_eager;
   if (ctx->fuse_post) {
-    CK(cudaLaunchCooperativeKernel(fn, dim3(grid_cycle), dim3(kBlock), cargs, smem, s));
+    CK(cudaLaunchCooperativeKernel(fn, dim3(grid_cycle), dim3(block), cargs, smem, s));
     if ((rc = check_launch(ctx, "cycle_kernel"))) return rc;
   } else {
-    CK(cudaLaunchKernel(fn, dim3(grid_cycle), dim3(kBlock), cargs, smem, s));
+    CK(cudaLaunchKernel(fn, dim3(grid_cycle), dim3(block), cargs, smem, s));
     if ((rc = check_launch(ctx, "cycle_kernel"))) return rc;
     void* pargs[] = {&p.post};
     CK(cudaLaunchCooperativeKernel((const void*)post_only_kernel, dim3(ctx->grid_post), dim3(kBlock), pargs, 0, s));

@@ -47,7 +47,7 @@ struct FullTile { static constexpr bool value = true; };
 struct RaggedTile { static constexpr bool value = false; };
 
 constexpr int kTile = 1024;         // particles per rank-tile (bitmask / prefix granularity)
-constexpr int kBlock = 256;         // threads per block
+constexpr int kBlock = 256;         // thread-count unit: the step kernel runs ONE block of 256*WB threads per SM; post_only uses 256
 constexpr int kMaxFlows = 16;       // outlets (reference: n_flows <= ~10)
 constexpr int kMaxGrid = 2048;      // upper bound of the persistent grid
 
@@ -314,23 +314,28 @@ __device__ __forceinline__ unsigned block_prefix_of(const uint32_t* blk_tot, uns
   return s_tmp[b];
 }
 
-// flags of the four slots a thread owns in `tile` + per-virtual-warp counts in s_w[32];
-// returns (by reference) the ballots; ends with a barrier so that s_w is complete
+// flags of the slots a thread owns in `tile` (slot = r*blockDim + thread, r < 4: blocks of 256..1024
+// threads) + per-virtual-warp counts in s_w[32] (virtual warp = 32 consecutive slots); returns the
+// ballots; ends with a barrier so that s_w is complete
 template <bool WANT_GAP>
 __device__ __forceinline__ void tile_flags(const PostParams& p, uint32_t tile, unsigned long long old_n, unsigned long long new_n,
                                            unsigned (&bal)[4], bool (&flag)[4], unsigned* s_w) {
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lane = threadIdx.x & 31;
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
-    const unsigned long long i = (unsigned long long)tile * kTile + (unsigned)r * 256u + threadIdx.x;
-    bool f = false;
-    if (i < old_n) {
-      const bool is_idle = p.status[i] == (uint8_t)Idle;
-      f = WANT_GAP ? (i < new_n && !is_idle) : (i >= new_n && is_idle);
+    const unsigned slot = (unsigned)r * blockDim.x + threadIdx.x;  // uniform per warp: blockDim is a multiple of 32
+    flag[r] = false; bal[r] = 0u;
+    if (slot < (unsigned)kTile) {
+      const unsigned long long i = (unsigned long long)tile * kTile + slot;
+      bool f = false;
+      if (i < old_n) {
+        const bool is_idle = p.status[i] == (uint8_t)Idle;
+        f = WANT_GAP ? (i < new_n && !is_idle) : (i >= new_n && is_idle);
+      }
+      flag[r] = f;
+      bal[r] = __ballot_sync(0xffffffffu, f);
+      if (lane == 0) s_w[slot >> 5] = __popc(bal[r]);
     }
-    flag[r] = f;
-    bal[r] = __ballot_sync(0xffffffffu, f);
-    if (lane == 0) s_w[r * 8 + warp] = __popc(bal[r]);
   }
   __syncthreads();
 }
@@ -439,9 +444,10 @@ static __device__ __forceinline__ void post_cycle_body(const PostParams& p) {
         for (int r = 0; r < 4; ++r) {
           if (fl[r]) {
             unsigned woff = 0;
-            for (unsigned k = 0; k < (unsigned)r * 8u + warp; ++k) woff += s_w[k];
+            const unsigned slot = (unsigned)r * blockDim.x + threadIdx.x;
+            for (unsigned k = 0; k < (slot >> 5); ++k) woff += s_w[k];
             const unsigned asc = blk_off + p.tile_idle_off[tile] + woff + __popc(bal[r] & ((1u << lane) - 1u));
-            p.src[total_idle - 1u - asc] = (uint32_t)((unsigned long long)tile * kTile + (unsigned)r * 256u + threadIdx.x);
+            p.src[total_idle - 1u - asc] = (uint32_t)((unsigned long long)tile * kTile + slot);
           }
         }
         __syncthreads();
@@ -460,12 +466,13 @@ static __device__ __forceinline__ void post_cycle_body(const PostParams& p) {
         for (int r = 0; r < 4; ++r) {
           if (fl[r]) {
             unsigned woff = 0;
-            for (unsigned k = 0; k < (unsigned)r * 8u + warp; ++k) woff += s_w[k];
+            const unsigned slot = (unsigned)r * blockDim.x + threadIdx.x;
+            for (unsigned k = 0; k < (slot >> 5); ++k) woff += s_w[k];
             const unsigned k = blk_off + p.tile_gap_off[tile] + woff + __popc(bal[r] & ((1u << lane) - 1u));
             if (k >= total_idle) {
               atomicOr(&st->error, 2u);  // inactive counter inconsistent with the status column
             } else {
-              const size_t i = (size_t)tile * kTile + (unsigned)r * 256u + threadIdx.x;
+              const size_t i = (size_t)tile * kTile + slot;
               const size_t s2 = p.src[k];
               p.status[i] = (uint8_t)Idle;
               p.pos[i] = p.pos[s2];
@@ -511,7 +518,7 @@ static __device__ __forceinline__ void post_cycle_body(const PostParams& p) {
     const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * T) / G);
     const unsigned long long words_valid = (old_n + 31ull) / 32ull;  // words beyond the last slot are stale
 #pragma unroll 4
-    for (uint32_t t = t0 + warp; t < t1; t += kBlock / 32) {
+    for (uint32_t t = t0 + warp; t < t1; t += blockDim.x / 32) {
       const unsigned long long wi = (unsigned long long)t * (kTile / 32) + lane;
       const unsigned wv = wi < words_valid ? __ldcg(p.div_mask + wi) : 0u;
       const unsigned c = __reduce_add_sync(0xffffffffu, (unsigned)__popc(wv));
@@ -627,7 +634,6 @@ template <class M> struct ReadCols {
 template <class M, int VEC> struct StageBytes {
   static constexpr size_t col = (size_t)32 * 4 * VEC;
   static constexpr size_t warp_stage = (size_t)(1 + ReadCols<M>::value) * col + (size_t)32 * VEC;
-  static constexpr size_t value = warp_stage * (kBlock / 32);  // one stage of a whole block
 };
 constexpr int kStages = 2;
 
@@ -659,7 +665,8 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                : "memory");
 }
 
-template <class M, int VEC, bool PIPE, bool LAZY> __device__ __forceinline__ void cycle_body(const CycleParams& p) {
+template <class M, int VEC, bool PIPE, bool LAZY, int BLOCK> __device__ __forceinline__ void cycle_body(const CycleParams& p) {
+  constexpr int kWarps = BLOCK / 32;
   static_assert(!PIPE || LAZY, "the bulk-copy pipeline is built for step-stamped ages only");
   constexpr int NV = M::n_var, NC = M::n_c, CT = 1 + M::n_pre;
   constexpr uint32_t kGroup = 32 * VEC;         // slots per group: the work unit of one warp
@@ -676,7 +683,7 @@ template <class M, int VEC, bool PIPE, bool LAZY> __device__ __forceinline__ voi
   // a device-wide counter — one L2 atomic per group, issued one group ahead so that its latency is
   // hidden.  Blocks that start late or run on a slower SM simply process fewer groups.
   const uint32_t n_groups = (uint32_t)((n_used + kGroup - 1) / kGroup);
-  const uint32_t total_warps = gridDim.x * (kBlock / 32);
+  const uint32_t total_warps = gridDim.x * kWarps;
   const uint32_t n_bins = p.n_species * p.n_comp;
   const bool single_comp = (p.n_comp == 1);
   const bool smem_bins = p.bins_in_smem && !single_comp;
@@ -684,10 +691,10 @@ template <class M, int VEC, bool PIPE, bool LAZY> __device__ __forceinline__ voi
   BMC_STAMP(p.st, 0);
   if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0ull;
   if (smem_bins)
-    for (uint32_t k = threadIdx.x; k < n_bins; k += kBlock) s_bins[k] = 0.0;
+    for (uint32_t k = threadIdx.x; k < n_bins; k += BLOCK) s_bins[k] = 0.0;
   float* const s_ctab = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_bins) + p.ctab_offset);
   if (p.ctab_in_smem) {
-    for (uint32_t c = threadIdx.x; c < p.n_comp; c += kBlock) {
+    for (uint32_t c = threadIdx.x; c < p.n_comp; c += BLOCK) {
       float row[CT];
       compartment_row<M>(p.diag, p.vol, p.dt, p.conc, p.n_species, p.enable_move, c, row);
 #pragma unroll
@@ -716,11 +723,11 @@ template <class M, int VEC, bool PIPE, bool LAZY> __device__ __forceinline__ voi
   // the critical path and no registers are held by loads in flight.  Lane l then reads bytes
   // [l*4*VEC, (l+1)*4*VEC) of every staged column (conflict-free LDS.128).  No block-wide barrier.
   unsigned char* const s_stage = reinterpret_cast<unsigned char*>(s_bins) + p.stage_offset;
-  __shared__ __align__(8) unsigned long long s_bar[kStages][kBlock / 32];
+  __shared__ __align__(8) unsigned long long s_bar[kStages][kWarps];
   constexpr unsigned kColBytes = (unsigned)kColStride;
   auto issue = [&](uint32_t g, int buf) {  // executed by lane 0 of the warp
     const size_t g0 = (size_t)g * kGroup;  // first slot of the group (the whole group is below the capacity)
-    unsigned char* dst = s_stage + ((size_t)buf * (kBlock / 32) + warp) * kWarpStage;
+    unsigned char* dst = s_stage + ((size_t)buf * kWarps + warp) * kWarpStage;
     unsigned long long* bar = &s_bar[buf][warp];
     mbar_expect_tx(bar, (unsigned)kWarpStage);
     bulk_g2s(dst, p.pos + g0, kColBytes, bar);
@@ -744,7 +751,7 @@ template <class M, int VEC, bool PIPE, bool LAZY> __device__ __forceinline__ voi
       uint32_t stw;
       if constexpr (PIPE) {
         // ---- operands were staged in shared memory by the bulk copies issued one iteration ago ----
-        const unsigned char* stage = s_stage + ((size_t)buf * (kBlock / 32) + warp) * kWarpStage;
+        const unsigned char* stage = s_stage + ((size_t)buf * kWarps + warp) * kWarpStage;
         const unsigned char* src = stage + lane * (4 * VEC);
         stw = VecIO<VEC>::ldb_plain(stage + (size_t)(1 + ReadCols<M>::value) * kColStride + lane * VEC);
         VecIO<VEC>::ldu_plain(reinterpret_cast<const uint32_t*>(src), pos);
@@ -1032,7 +1039,7 @@ template <class M, int VEC, bool PIPE, bool LAZY> __device__ __forceinline__ voi
         for (int q = 0; q < VEC; ++q) if ((exit_nib >> q) & 1u) p.status[i0 + q] = (uint8_t)Exit;
       }
     };
-    uint32_t g = blockIdx.x * (kBlock / 32) + warp;  // first group: the warp's own index
+    uint32_t g = blockIdx.x * kWarps + warp;  // first group: the warp's own index
     if constexpr (PIPE) {
       if (lane == 0) {
 #pragma unroll
@@ -1110,7 +1117,7 @@ template <class M, int VEC, bool PIPE, bool LAZY> __device__ __forceinline__ voi
     // every block starts at a different bin, so that the blocks (which finish together) do not hit
     // the same L2 addresses at the same time
     const uint32_t rot = (uint32_t)(((unsigned long long)blockIdx.x * n_bins) / gridDim.x);
-    for (uint32_t k0 = threadIdx.x; k0 < n_bins; k0 += kBlock) {
+    for (uint32_t k0 = threadIdx.x; k0 < n_bins; k0 += BLOCK) {
       uint32_t k = k0 + rot; if (k >= n_bins) k -= n_bins;
       const double a = s_bins[k];
       if (a != 0.0) atomicAdd(p.acc + k, a);
@@ -1155,8 +1162,12 @@ template <class M> __device__ __forceinline__ void init_body(const InitParams& p
 // __global__ entry points of the built-in models (the NVRTC path of user models wraps the same
 // bodies in extern "C" kernels, see bmc_udf.cu)
 template <class M> __global__ void __launch_bounds__(256) pre_step_kernel(const __grid_constant__ PreParams p) { pre_step_body<M>(p); }
-template <class M, int VEC, int MINB, bool PIPE, bool LAZY>
-__global__ void __launch_bounds__(kBlock, MINB) cycle_kernel(const __grid_constant__ CycleParams p) { cycle_body<M, VEC, PIPE, LAZY>(p); }
+// WB = 256-thread units per block (one block per SM): 4 -> 1024 threads x <=64 registers, 3 -> 768 x <=80,
+// 2 -> 512 x <=128.  One big block per SM shares one set of shared-memory source bins among all its warps.
+template <class M, int VEC, int WB, bool PIPE, bool LAZY>
+__global__ void __launch_bounds__(kBlock * WB, 1) cycle_kernel(const __grid_constant__ CycleParams p) {
+  cycle_body<M, VEC, PIPE, LAZY, kBlock * WB>(p);
+}
 template <class M> __global__ void __launch_bounds__(256) init_kernel(const __grid_constant__ InitParams p) { init_body<M>(p); }
 
 }  // namespace bmc

@@ -9,11 +9,12 @@ namespace bmc {
 
 struct ModelVT {
   int n_var, n_c, vec, minb;
+  int block, block_eager;  // threads per block of cycle_fn / cycle_eager_fn (one block per SM)
   int ct;              // floats per compartment-table row
   size_t stage_bytes;  // dynamic shared memory of the bulk-copy pipeline (0 = direct loads)
   // kernel handles: addresses of __global__ instantiations, or cudaKernel_t of a JIT-compiled
   // user model; all launched with cudaLaunchKernel(handle, grid, block, {&params}, smem, stream)
-  const void* cycle_fn;   // (CycleParams)  block = kBlock; step-stamped ages (bmc_kernels.cuh)
+  const void* cycle_fn;   // (CycleParams)  block = 256*minb threads, one block per SM; step-stamped ages (bmc_kernels.cuh)
   const void* cycle_eager_fn;  // same with float ages updated every step (direct loads, no staging)
   const void* pre_fn;     // (PreParams)    block = 256
   const void* init_fn;    // (InitParams)   block = 256
@@ -23,8 +24,9 @@ struct ModelVT {
 template <class M, int VEC, int MINB = 1, bool PIPE = false> static ModelVT make_vt() {
   ModelVT v;
   v.n_var = M::n_var; v.n_c = M::n_c; v.vec = VEC; v.minb = MINB;
+  v.block = kBlock * MINB; v.block_eager = kBlock * (MINB > 3 ? 3 : MINB);
   v.ct = 1 + M::n_pre;
-  v.stage_bytes = PIPE ? kStages * StageBytes<M, VEC>::value : 0;
+  v.stage_bytes = PIPE ? kStages * StageBytes<M, VEC>::warp_stage * (size_t)(kBlock * MINB / 32) : 0;
   v.cycle_fn = (const void*)cycle_kernel<M, VEC, MINB, PIPE, true>;
   v.cycle_eager_fn = (const void*)cycle_kernel<M, VEC, (MINB > 3 ? 3 : MINB), false, false>;
   v.pre_fn = (const void*)pre_step_kernel<M>;

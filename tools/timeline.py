@@ -16,7 +16,7 @@ buf = (ctypes.c_ulonglong * 16)()
 rc = lib.bmc_debug_timeline(g.h, buf)
 t = np.array(list(buf), dtype=np.int64)
 print("rc", rc); print("block 0 stamps [us]:", np.round((t[:9] - t[0]) / 1000.0, 1))
-G = 592
+G = 148
 raw = np.zeros(4 * G, np.uint32)
 lib.bmc_debug_blocks(g.h, raw.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(raw.size))
 raw = raw.reshape(G, 4)
