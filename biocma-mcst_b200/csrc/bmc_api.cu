@@ -22,14 +22,15 @@ using namespace bmc;
 
 namespace {
 
-static bool pick_model(int model, int n_var_udf, ModelVT& vt) {
+static bool pick_model(int model, int n_var_udf, bool large, ModelVT& vt) {
   const char* v = getenv("BMC_VARIANT");
   const std::string var = v ? v : "";
   switch (model) {
-    case BMC_MODEL_FIXED_LENGTH: return pick_fixed_length(var, vt);
-    case BMC_MODEL_MONOD: return pick_monod(var, vt);
-    case BMC_MODEL_SIMPLE_ACETATE: return pick_simple_acetate(var, vt);
-    case BMC_MODEL_WIDE_UDF: return n_var_udf <= 16 ? pick_wide_udf_small(var, n_var_udf, vt) : pick_wide_udf_large(var, n_var_udf, vt);
+    case BMC_MODEL_FIXED_LENGTH: return pick_fixed_length(var, large, vt);
+    case BMC_MODEL_MONOD: return pick_monod(var, large, vt);
+    case BMC_MODEL_SIMPLE_ACETATE: return pick_simple_acetate(var, large, vt);
+    case BMC_MODEL_WIDE_UDF:
+      return n_var_udf <= 16 ? pick_wide_udf_small(var, large, n_var_udf, vt) : pick_wide_udf_large(var, large, n_var_udf, vt);
     default: return false;
   }
 }
@@ -41,7 +42,7 @@ static int (*g_nccl_destroy)(void*) = nullptr;
 struct bmc_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  int model = 0;
+  int model = 0, n_var_udf = 0; bool large = false;  // large: kernel variant chosen for > kLargePopulation slots
   ModelVT vt{};
   uint64_t n_species = 1, n_comp = 1;
   uint64_t seed = 0; uint32_t rank = 0;
@@ -76,6 +77,7 @@ struct bmc_ctx {
   uint64_t launches = 0;
   size_t stage_offset = 0, smem_total = 0; int ctab_in_smem = 0; size_t ctab_offset = 0; int grid_post = 148;
   int grid_cycle_eager = 148; size_t smem_eager = 0;
+  int n_streams = 1;
   bool fuse_post = true;  // whole step in one cooperative launch (BMC_FUSE_POST=0: particle pass + post_only_kernel)
   // staging
   void* d_stage = nullptr; size_t stage_bytes = 0;
@@ -128,9 +130,16 @@ static void free_container(bmc_ctx* c) {
 
 // ParticlesContainer::_resize + __allocate_buffer__ (particles_container.hpp:601-643, 669-685):
 // (re)allocate every column for `new_cap` slots, keeping the first `keep` slots.
+static int configure_launch(bmc_ctx* ctx);
 static int resize_container(bmc_ctx* ctx, size_t new_cap, size_t keep) {
   new_cap = round_up(std::max<size_t>(new_cap, kTile), kTile);
   if (new_cap > 0xFFFFFFF0ull) { ctx->err = "capacity exceeds 2^32 slots per context"; return BMC_ERR_RANGE; }
+  if (ctx->model != BMC_MODEL_UDF && (new_cap > kLargePopulation) != ctx->large) {  // population class changed: other block size
+    ctx->large = new_cap > kLargePopulation;
+    if (!pick_model(ctx->model, ctx->n_var_udf, ctx->large, ctx->vt)) { ctx->err = "kernel variant selection failed"; return BMC_ERR_INVALID; }
+    int rc0 = configure_launch(ctx);
+    if (rc0) return rc0;
+  }
   const int nv = ctx->vt.n_var;
   float* props = nullptr; uint32_t* pos = nullptr; uint8_t* status = nullptr; float *ah = nullptr, *ad = nullptr;
   int rc;
@@ -211,6 +220,7 @@ static int configure_launch(bmc_ctx* ctx) {
   ctx->smem_eager = ctx->stage_offset;  // the eager-age variant loads directly: bins + table only
   ctx->grid_post = ctx->n_sm;           // cooperative launch: one block per SM is always co-resident
   if (const char* e = getenv("BMC_FUSE_POST")) ctx->fuse_post = atoi(e) != 0;
+  if (const char* e = getenv("BMC_STREAMS")) ctx->n_streams = std::max(1, atoi(e));
   const char* env = getenv("BMC_BLOCKS_PER_SM");
   auto grid_of = [&](const void* fn, int block, size_t smem, int& grid, int* occ_out) -> int {
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -364,9 +374,9 @@ int bmc_create(bmc_ctx** out, const bmc_config* cfg) {
     const char* path = cfg->udf_source_path ? cfg->udf_source_path : getenv("BIOMC_LIB_UDF");
     if (!path) { ctx->err = "BMC_MODEL_UDF needs udf_source_path or BIOMC_LIB_UDF"; return fail(BMC_ERR_INVALID); }
     if (!load_udf_model(path, ctx->vt, ctx->err)) return fail(BMC_ERR_UNSUPPORTED);
-  } else if (!pick_model(cfg->model, cfg->n_var_udf, ctx->vt)) { ctx->err = "unknown model / unsupported n_var_udf"; return fail(BMC_ERR_INVALID); }
+  } else if (!pick_model(cfg->model, cfg->n_var_udf, cfg->capacity > kLargePopulation, ctx->vt)) { ctx->err = "unknown model / unsupported n_var_udf"; return fail(BMC_ERR_INVALID); }
   if ((uint64_t)ctx->vt.n_c > cfg->n_species) { ctx->err = "model n_c exceeds n_species"; return fail(BMC_ERR_INVALID); }
-  ctx->device = cfg->device; ctx->model = cfg->model;
+  ctx->device = cfg->device; ctx->model = cfg->model; ctx->n_var_udf = cfg->n_var_udf; ctx->large = cfg->capacity > kLargePopulation;
   ctx->n_species = cfg->n_species; ctx->n_comp = cfg->n_compartments;
   ctx->seed = cfg->seed; ctx->rank = cfg->rank;
   if (cfg->allocation_factor > 0) ctx->allocation_factor = std::max(1.0, cfg->allocation_factor);
@@ -789,6 +799,7 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   // particle pass and the post-cycle phase needs every block on the device)
   void* cargs[] = {&p};
   p.fuse_post = ctx->fuse_post ? 1 : 0;
+  p.n_streams = (uint32_t)ctx->n_streams;
   const void* fn = ctx->lazy_ages ? ctx->vt.cycle_fn : ctx->vt.cycle_eager_fn;
   const int block = ctx->lazy_ages ? ctx->vt.block : ctx->vt.block_eager;
   const size_t smem = ctx->lazy_ages ? ctx->smem_total : ctx->smem_eager;

@@ -2,8 +2,8 @@
 #include "bmc_model_vt.cuh"
 
 namespace bmc {
-bool pick_wide_udf_small(const std::string& var, int n_var, ModelVT& vt) {
-  if (n_var == 8) return pick_variant<WideUdf<8>, 4, true>(var, 3, vt);
+bool pick_wide_udf_small(const std::string& var, bool large, int n_var, ModelVT& vt) {
+  if (n_var == 8) return pick_variant<WideUdf<8>, 4, true>(var, large ? 3 : 4, vt);
   if (n_var == 16) return pick_variant<WideUdf<16>, 2, true>(var, 3, vt);
   return false;
 }

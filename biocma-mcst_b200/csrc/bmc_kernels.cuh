@@ -32,8 +32,11 @@ namespace bmc {
 #ifndef BMC_SCATTER_MODE
 #define BMC_SCATTER_MODE 1  // 1 = shared-memory fp64 bins (product); others are timing experiments
 #endif
+// Cache-streaming ld/st hints (ld.global.cs / st.global.cs) on the particle columns were measured to
+// HURT: with 32 resident warps per SM and more than ~3e7 particles the step becomes 60-90 % slower
+// (1e8 particles, monod: 1620 us with the hints, 855 us without), so plain accesses are the default.
 #ifndef BMC_STREAM_HINTS
-#define BMC_STREAM_HINTS 1
+#define BMC_STREAM_HINTS 0
 #endif
 #if BMC_STREAM_HINTS
 #define BMC_LD(p) __ldcs(p)
@@ -157,6 +160,7 @@ struct CycleParams {
   int enable_move, enable_leave, bins_in_smem;
   uint32_t stage_offset;  // byte offset of the cp.async staging buffers inside dynamic shared memory
   PostParams post;   // second phase of the step (post_cycle_body)
+  uint32_t n_streams; // interleaved address streams of the work distribution (>= 1)
   int fuse_post;     // 1 = run it in this launch behind a grid barrier (cooperative launch), 0 = post_only_kernel follows
 };
 
@@ -1039,7 +1043,17 @@ template <class M, int VEC, bool PIPE, bool LAZY, int BLOCK> __device__ __forcei
         for (int q = 0; q < VEC; ++q) if ((exit_nib >> q) & 1u) p.status[i0 + q] = (uint8_t)Exit;
       }
     };
-    uint32_t g = blockIdx.x * kWarps + warp;  // first group: the warp's own index
+    // Draw number s -> group: the groups form n_streams interleaved streams of stream_len consecutive
+    // groups; consecutive draws go to consecutive streams, so the warps that run at the same time
+    // read/write n_streams separate address windows per column (one window thrashes DRAM banks against
+    // the L2 write-backs of the lines written shortly before).  Draws that map beyond the last group
+    // of the last stream carry no work.
+    const uint32_t n_streams = p.n_streams, stream_len = (n_groups + n_streams - 1) / n_streams;
+    const unsigned long long n_draws = (unsigned long long)n_streams * stream_len;
+    auto group_of = [&](unsigned long long s) -> uint32_t {
+      return (uint32_t)(s % n_streams) * stream_len + (uint32_t)(s / n_streams);
+    };
+    unsigned long long s = (unsigned long long)blockIdx.x * kWarps + warp;  // first draw: the warp's own index
     if constexpr (PIPE) {
       if (lane == 0) {
 #pragma unroll
@@ -1048,32 +1062,42 @@ template <class M, int VEC, bool PIPE, bool LAZY, int BLOCK> __device__ __forcei
       }
       __syncwarp();
       uint32_t nxt = 0;
+      uint32_t g = s < n_draws ? group_of(s) : n_groups;
       if (lane == 0) {
         if (g < n_groups) issue(g, 0);
         nxt = atomicAdd(&p.st->next_group, 1u);  // the pipeline needs the next group one iteration ahead
       }
+      uint32_t it = 0;  // counts the groups that were staged (buffer / barrier phase)
 #pragma unroll 1
-      for (uint32_t it = 0; g < n_groups; ++it) {
+      while (s < n_draws) {
         const int buf = (int)(it & 1u);
-        const uint32_t g_next = total_warps + __shfl_sync(0xffffffffu, nxt, 0);
+        const unsigned long long s_next = (unsigned long long)total_warps + __shfl_sync(0xffffffffu, nxt, 0);
+        const uint32_t g_next = s_next < n_draws ? group_of(s_next) : n_groups;
+        const bool have = g < n_groups, have_next = g_next < n_groups;
         __syncwarp();  // every lane is done reading the other buffer (previous iteration): it may be refilled
         if (lane == 0) {
-          if (g_next < n_groups) issue(g_next, buf ^ 1);
+          if (have_next) issue(g_next, have ? buf ^ 1 : buf);
           nxt = atomicAdd(&p.st->next_group, 1u);
         }
-        mbar_wait(&s_bar[buf][warp], (it >> 1) & 1u);
-        if ((unsigned long long)(g + 1) * kGroup <= n_used) body(FullTile{}, g, buf);
-        else body(RaggedTile{}, g, buf);
-        g = g_next;
+        if (have) {
+          mbar_wait(&s_bar[buf][warp], (it >> 1) & 1u);
+          if ((unsigned long long)(g + 1) * kGroup <= n_used) body(FullTile{}, g, buf);
+          else body(RaggedTile{}, g, buf);
+          ++it;
+        }
+        g = g_next; s = s_next;
       }
     } else {
 #pragma unroll 1
-      while (g < n_groups) {
+      while (s < n_draws) {
         uint32_t nxt = 0;
         if (lane == 0) nxt = atomicAdd(&p.st->next_group, 1u);  // consumed after this group: latency hidden
-        if ((unsigned long long)(g + 1) * kGroup <= n_used) body(FullTile{}, g, 0);
-        else body(RaggedTile{}, g, 0);
-        g = total_warps + __shfl_sync(0xffffffffu, nxt, 0);
+        const uint32_t g = group_of(s);
+        if (g < n_groups) {
+          if ((unsigned long long)(g + 1) * kGroup <= n_used) body(FullTile{}, g, 0);
+          else body(RaggedTile{}, g, 0);
+        }
+        s = (unsigned long long)total_warps + __shfl_sync(0xffffffffu, nxt, 0);
       }
     }
   }

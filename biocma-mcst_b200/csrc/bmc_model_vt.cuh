@@ -60,11 +60,16 @@ template <class M, int VEC, bool WITH_PIPE = false> static bool pick_variant(con
   }
 }
 
-bool pick_fixed_length(const std::string& var, ModelVT& vt);
-bool pick_monod(const std::string& var, ModelVT& vt);
-bool pick_simple_acetate(const std::string& var, ModelVT& vt);
-bool pick_wide_udf_small(const std::string& var, int n_var, ModelVT& vt);   // P = 8, 16
-bool pick_wide_udf_large(const std::string& var, int n_var, ModelVT& vt);   // P = 32, 64
+// `large`: more than kLargePopulation slots.  With 1024-thread blocks (WB 4) the particle pass was
+// measured to fall into a ~1.9x slower mode on large populations (1e8 particles: 1620-1750 us per step
+// against 990-1050 us with 768 threads), while it is the fastest choice at 1e7 (104 vs 117 us); the
+// 768-thread variant never showed that mode, so it is the default above the threshold.
+constexpr size_t kLargePopulation = 24u * 1000u * 1000u;
+bool pick_fixed_length(const std::string& var, bool large, ModelVT& vt);
+bool pick_monod(const std::string& var, bool large, ModelVT& vt);
+bool pick_simple_acetate(const std::string& var, bool large, ModelVT& vt);
+bool pick_wide_udf_small(const std::string& var, bool large, int n_var, ModelVT& vt);   // P = 8, 16
+bool pick_wide_udf_large(const std::string& var, bool large, int n_var, ModelVT& vt);   // P = 32, 64
 // BMC_MODEL_UDF: NVRTC-compile a user model source against these headers (bmc_udf.cu)
 bool load_udf_model(const char* source_path, ModelVT& vt, std::string& err);
 void unload_udf_model(ModelVT& vt);

@@ -4,7 +4,8 @@ os.environ["BMC_LIB"] = os.path.join(os.getcwd(), "biocma-mcst_b200", "lib_tl.so
 from _bmc_loader import load_pkg, load_synth
 import util, torch
 pkg, synth = load_pkg(), load_synth()
-case = util.make_case(synth, "monod", 10_000_000, 500, dt=0.1)
+N = int(os.environ.get("TL_N", "10000000"))
+case = util.make_case(synth, "monod", N, 500, dt=0.1)
 g = pkg.ParticleLoop("monod", 1, 500)
 util.load_case(g, case)
 for _ in range(20): g.cycle(0.1)
