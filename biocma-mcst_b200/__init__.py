@@ -240,13 +240,15 @@ class ParticleLoop:
 
     # ---- liquid coupling -----------------------------------------------------
     def set_concentrations(self, c):
-        c = np.ascontiguousarray(c, dtype=np.float64)
+        if not (isinstance(c, np.ndarray) and c.dtype == np.float64 and c.flags.c_contiguous):
+            c = np.ascontiguousarray(c, dtype=np.float64)
         assert c.size == self.n_species * self.n_compartments
-        self._ck(self.lib.bmc_set_concentrations(self.h, _ptr(c)))
+        self._ck(self.lib.bmc_set_concentrations(self.h, c.ctypes.data))
 
-    def get_sources(self):
-        out = np.empty(self.n_species * self.n_compartments, np.float64)
-        self._ck(self.lib.bmc_get_sources(self.h, _ptr(out)))
+    def get_sources(self, out=None):
+        if out is None:
+            out = np.empty(self.n_species * self.n_compartments, np.float64)
+        self._ck(self.lib.bmc_get_sources(self.h, out.ctypes.data))
         return out
 
     # ---- liquid phase on the device ---------------------------------------------

@@ -87,6 +87,10 @@ struct bmc_ctx {
   // every age started at zero; otherwise the columns hold floats updated every step ("eager")
   bool lazy_ages = true; bool epoch_set = false; double epoch_dt = 0.0; bool epoch_leave = false;
   float *d_tab_div = nullptr, *d_tab_hyd = nullptr; size_t tab_cap = 0;
+  // pinned staging of the per-step host buffers (concentrations in, sources out)
+  static constexpr int kPinRing = 4;
+  double* h_pin_in[kPinRing] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t ev_pin_in[kPinRing] = {nullptr, nullptr, nullptr, nullptr};
+  int pin_next = 0; double* h_pin_out = nullptr;
   // nccl
   void* nccl_comm = nullptr; int nccl_ranks = 0;
   std::string err;
@@ -402,6 +406,11 @@ int bmc_create(bmc_ctx** out, const bmc_config* cfg) {
       (rc = dev_alloc(ctx, &ctx->blk_gap, kMaxGrid + 1)) || (rc = dev_alloc(ctx, &ctx->blk_idle, kMaxGrid + 1)))
     return fail(rc);
   cudaMemset(ctx->d_conc, 0, nb * 8); cudaMemset(ctx->d_sources, 0, nb * 8); cudaMemset(ctx->d_acc, 0, nb * 8);
+  for (int i = 0; i < bmc_ctx::kPinRing; ++i) {
+    if (!ck(cudaMallocHost((void**)&ctx->h_pin_in[i], nb * 8), "cudaMallocHost")) return fail(BMC_ERR_NOMEM);
+    if (!ck(cudaEventCreateWithFlags(&ctx->ev_pin_in[i], cudaEventDisableTiming), "cudaEventCreate")) return fail(BMC_ERR_CUDA);
+  }
+  if (!ck(cudaMallocHost((void**)&ctx->h_pin_out, nb * 8), "cudaMallocHost")) return fail(BMC_ERR_NOMEM);
   cudaMemset(ctx->d_mass, 0, nb * 8); cudaMemset(ctx->d_csc_ptr, 0, (ctx->n_comp + 1) * 4);
   ctx->h_vol.assign(ctx->n_comp, 1.0);
   cudaMemset(ctx->d_ctab, 0, ctx->n_comp * (size_t)ctx->vt.ct * 4);
@@ -430,6 +439,8 @@ int bmc_destroy(bmc_ctx** h) {
   dev_free(c->st);
   if (c->d_stage) cudaFree(c->d_stage);
   for (int i = 0; i < 2; ++i) { if (c->h_st[i]) cudaFreeHost(c->h_st[i]); if (c->ev_mirror[i]) cudaEventDestroy(c->ev_mirror[i]); }
+  for (int i = 0; i < bmc_ctx::kPinRing; ++i) { if (c->h_pin_in[i]) cudaFreeHost(c->h_pin_in[i]); if (c->ev_pin_in[i]) cudaEventDestroy(c->ev_pin_in[i]); }
+  if (c->h_pin_out) cudaFreeHost(c->h_pin_out);
   for (auto& pr : c->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -641,9 +652,14 @@ int bmc_set_leaving_flows(bmc_ctx* ctx, uint64_t n, const bmc_leaving_flow* f) {
 int bmc_set_concentrations(bmc_ctx* ctx, const double* c) {
   if (!ctx || !c) return BMC_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
-  // pageable source: the runtime stages the bytes before returning, so the caller's
-  // buffer is free on return; ordering with enqueued cycles is by stream order.
-  CK(cudaMemcpyAsync(ctx->d_conc, c, ctx->n_species * ctx->n_comp * 8, cudaMemcpyHostToDevice, ctx->stream));
+  // The caller's buffer is copied into a pinned ring slot (free on return, api_raw.cpp:328-379 convention);
+  // the H2D copy is then truly asynchronous and ordered with the enqueued cycles by the stream.
+  const size_t bytes = ctx->n_species * ctx->n_comp * 8;
+  const int slot = ctx->pin_next; ctx->pin_next = (ctx->pin_next + 1) % bmc_ctx::kPinRing;
+  CK(cudaEventSynchronize(ctx->ev_pin_in[slot]));  // the copy that last used this slot has executed
+  memcpy(ctx->h_pin_in[slot], c, bytes);
+  CK(cudaMemcpyAsync(ctx->d_conc, ctx->h_pin_in[slot], bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaEventRecord(ctx->ev_pin_in[slot], ctx->stream));
   ctx->mass_dirty = true;  // total_mass = C * V is rebuilt by the next bmc_liquid_step
   return BMC_OK;
 }
@@ -729,8 +745,10 @@ int bmc_liquid_step(bmc_ctx* ctx, double d_t) {
 int bmc_get_sources(bmc_ctx* ctx, double* out) {
   if (!ctx || !out) return BMC_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
-  CK(cudaMemcpyAsync(out, ctx->d_sources, ctx->n_species * ctx->n_comp * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  const size_t bytes = ctx->n_species * ctx->n_comp * 8;
+  CK(cudaMemcpyAsync(ctx->h_pin_out, ctx->d_sources, bytes, cudaMemcpyDeviceToHost, ctx->stream));  // pinned: one DMA, no staging
   CK(cudaStreamSynchronize(ctx->stream));
+  memcpy(out, ctx->h_pin_out, bytes);
   return BMC_OK;
 }
 
