@@ -77,7 +77,6 @@ struct bmc_ctx {
   uint64_t launches = 0;
   size_t stage_offset = 0, smem_total = 0; int ctab_in_smem = 0; size_t ctab_offset = 0; int grid_post = 148;
   int grid_cycle_eager = 148; size_t smem_eager = 0;
-  int n_streams = 1;
   bool fuse_post = true;  // whole step in one cooperative launch (BMC_FUSE_POST=0: particle pass + post_only_kernel)
   // staging
   void* d_stage = nullptr; size_t stage_bytes = 0;
@@ -224,7 +223,6 @@ static int configure_launch(bmc_ctx* ctx) {
   ctx->smem_eager = ctx->stage_offset;  // the eager-age variant loads directly: bins + table only
   ctx->grid_post = ctx->n_sm;           // cooperative launch: one block per SM is always co-resident
   if (const char* e = getenv("BMC_FUSE_POST")) ctx->fuse_post = atoi(e) != 0;
-  if (const char* e = getenv("BMC_STREAMS")) ctx->n_streams = std::max(1, atoi(e));
   const char* env = getenv("BMC_BLOCKS_PER_SM");
   auto grid_of = [&](const void* fn, int block, size_t smem, int& grid, int* occ_out) -> int {
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -817,7 +815,6 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   // particle pass and the post-cycle phase needs every block on the device)
   void* cargs[] = {&p};
   p.fuse_post = ctx->fuse_post ? 1 : 0;
-  p.n_streams = (uint32_t)ctx->n_streams;
   const void* fn = ctx->lazy_ages ? ctx->vt.cycle_fn : ctx->vt.cycle_eager_fn;
   const int block = ctx->lazy_ages ? ctx->vt.block : ctx->vt.block_eager;
   const size_t smem = ctx->lazy_ages ? ctx->smem_total : ctx->smem_eager;

@@ -160,7 +160,6 @@ struct CycleParams {
   int enable_move, enable_leave, bins_in_smem;
   uint32_t stage_offset;  // byte offset of the cp.async staging buffers inside dynamic shared memory
   PostParams post;   // second phase of the step (post_cycle_body)
-  uint32_t n_streams; // interleaved address streams of the work distribution (>= 1)
   int fuse_post;     // 1 = run it in this launch behind a grid barrier (cooperative launch), 0 = post_only_kernel follows
 };
 
@@ -1043,16 +1042,11 @@ template <class M, int VEC, bool PIPE, bool LAZY, int BLOCK> __device__ __forcei
         for (int q = 0; q < VEC; ++q) if ((exit_nib >> q) & 1u) p.status[i0 + q] = (uint8_t)Exit;
       }
     };
-    // Draw number s -> group: the groups form n_streams interleaved streams of stream_len consecutive
-    // groups; consecutive draws go to consecutive streams, so the warps that run at the same time
-    // read/write n_streams separate address windows per column (one window thrashes DRAM banks against
-    // the L2 write-backs of the lines written shortly before).  Draws that map beyond the last group
-    // of the last stream carry no work.
-    const uint32_t n_streams = p.n_streams, stream_len = (n_groups + n_streams - 1) / n_streams;
-    const unsigned long long n_draws = (unsigned long long)n_streams * stream_len;
-    auto group_of = [&](unsigned long long s) -> uint32_t {
-      return (uint32_t)(s % n_streams) * stream_len + (uint32_t)(s / n_streams);
-    };
+    // Draw number s -> group s: the warps that run at the same time work on adjacent groups, i.e. the
+    // whole grid streams through ONE moving window of every column.  (Spreading the draws over many
+    // interleaved address streams was measured to make no difference.)
+    const unsigned long long n_draws = n_groups;
+    auto group_of = [&](unsigned long long s) -> uint32_t { return (uint32_t)s; };
     unsigned long long s = (unsigned long long)blockIdx.x * kWarps + warp;  // first draw: the warp's own index
     if constexpr (PIPE) {
       if (lane == 0) {
