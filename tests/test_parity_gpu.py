@@ -265,3 +265,44 @@ def test_capacity_growth_is_transparent(bmc, orc, synth):
     assert co["n_used"] > 4 * case["n"] and cg["capacity"] > 2.5 * case["n"] * 2 and cg["events"]["Overflow"] == 0
     util.assert_counters_equal(cg, co)
     util.assert_state_equal(g.get_particles(co["n_used"]), o.get_particles(co["n_used"]), co["n_used"])
+
+
+def test_synchronised_population_many_divisions_in_one_step(bmc, orc, synth):
+    """> 2048 divisions in one step: newborn placement goes through the per-tile prefix path (mask popcounts +
+    block prefix behind a grid barrier) instead of the direct ranking used for small batches; both must give
+    ascending-mother order.  Then more steps with exits and compaction on the grown population."""
+    n = 70_000
+    case = util.make_case(synth, "fixed_length", n, 64, dt=600.0, p_move=0.3, p_exit=0.2)
+    rng = np.random.default_rng(9)
+    case["props"][0] = (1.9e-6 + 0.1e-6 * rng.random(n)).astype(np.float32)   # all close to l_max: about half divide at once
+    g, o = _pair(bmc, orc, case, dead_ratio=0.002, allocation_factor=4.0)
+    util.load_case(g, case); util.load_case(o, case)
+    sg = util.run_steps(g, case, 1, collect=True); so = util.run_steps(o, case, 1, collect=True)
+    _compare_sources(sg, so)
+    _compare(g, o)
+    assert g.counters()["total_new"] > 4096
+    # the whole population divides again two steps later (139k -> 278k); stop before the third doubling, which
+    # exceeds the division buffer of the fixed 4x allocation (an overflow, handled differently by design)
+    sg = util.run_steps(g, case, 4, collect=True); so = util.run_steps(o, case, 4, collect=True)
+    _compare_sources(sg, so)
+    _compare(g, o)
+    assert g.counters()["total_new"] > 200_000 and g.counters()["n_compactions"] >= 3
+
+
+def test_small_and_large_insert_paths_agree_on_order(bmc, synth):
+    """the same population stepped with 1500 and with 5000 simultaneous divisions keeps newborns in ascending-mother order"""
+    for n_div in (1500, 5000):
+        n = 40_000
+        case = util.make_case(synth, "fixed_length", n, 8, dt=1.0, outlet=False)
+        case["props"][0][:] = 1.0e-6
+        idx = np.sort(np.random.default_rng(n_div).choice(n, n_div, replace=False))
+        case["props"][0][idx] = 2.5e-6                                         # exactly these divide in step 1
+        g = bmc.ParticleLoop("fixed_length", 1, 8, allocation_factor=3.0)
+        util.load_case(g, case)
+        g.cycle(1.0)
+        c = g.counters()
+        assert c["total_new"] == n_div and c["n_used"] == n + n_div
+        p = g.get_particles()
+        # newborn k (slot n+k) is the daughter of the k-th dividing mother: same halved length, same compartment
+        assert np.array_equal(p["props"][0][n:], p["props"][0][idx])
+        assert np.array_equal(p["position"][n:], case["pos"][idx]) or case["n_comp"] > 1

@@ -164,3 +164,16 @@ def test_udf_device_init_matches_oracle(bmc, orc):
     mg = g.init_particles(n, True, linit); mo = o.init_particles(n, True, linit)
     assert abs(mg - mo) <= 1e-12 * abs(mo)
     util.assert_state_equal(g.get_particles(n), o.get_particles(n), n)
+
+
+@pytest.mark.gpu
+def test_udf_eager_ages_path(bmc, orc, synth):
+    """non-zero initial ages select the eager kernel variant of the JIT-compiled model"""
+    case = util.make_case(synth, "udf_model", 30_000, 40, dt=20.0, near_division=0.8, p_move=0.3, p_exit=0.2)
+    rng = np.random.default_rng(4)
+    ah = (10.0 * rng.random(case["n"])).astype(np.float32); ad = (5.0 * rng.random(case["n"])).astype(np.float32)
+    g, o = _pair(bmc, orc, case, dead_ratio=0.002)
+    util.load_case(g, case); util.load_case(o, case)
+    g.set_particles(case["props"], case["pos"], None, ah, ad); o.set_particles(case["props"], case["pos"], None, ah, ad)
+    util.run_steps(g, case, 8); util.run_steps(o, case, 8)
+    _compare(g, o)
