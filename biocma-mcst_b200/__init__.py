@@ -31,7 +31,7 @@ ABI_SYMBOLS = (
     "bmc_sources_device", "bmc_concentrations_device", "bmc_stream", "bmc_launch_count", "bmc_profile_enable",
     "bmc_profile_read", "bmc_nccl_unique_id", "bmc_comm_init", "bmc_allreduce_sources",
     "bmc_liquid_set_transition", "bmc_liquid_set_feeds", "bmc_liquid_step", "bmc_get_concentrations",
-    "bmc_udf_check",
+    "bmc_udf_check", "bmc_get_properties", "bmc_cma_build",
 )
 
 
@@ -121,6 +121,8 @@ def load_library(path=None):
     lib.bmc_liquid_step.argtypes = [vp, dbl]
     lib.bmc_get_concentrations.argtypes = [vp, vp]
     lib.bmc_udf_check.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
+    lib.bmc_get_properties.argtypes = [vp, vp, u64, vp, vp, vp, P(u64)]
+    lib.bmc_cma_build.argtypes = [u64, u64, vp, vp, vp, u64, P(u64), vp, vp, vp, vp, vp, vp]
     for name in ABI_SYMBOLS:
         if name != "bmc_last_error":
             getattr(lib, name).restype = ctypes.c_int
@@ -131,6 +133,25 @@ def load_library(path=None):
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def cma_build(n, src, dst, flow, n_cols=0):
+    """Flow matrix triplets -> dict(m, neighbors (n, m), cdf (n, m), out_flows (n), coo=(rows, cols, vals)) (host only)."""
+    lib = load_library()
+    src = np.ascontiguousarray(src, np.uint64); dst = np.ascontiguousarray(dst, np.uint64); flow = np.ascontiguousarray(flow, np.float64)
+    m = ctypes.c_uint64()
+    rc = lib.bmc_cma_build(n, flow.size, _ptr(src), _ptr(dst), _ptr(flow), n_cols, ctypes.byref(m), None, None, None, None, None, None)
+    if rc != 0:
+        raise BmcError(rc, "bmc_cma_build: invalid flow matrix")
+    mm = m.value
+    nb = np.zeros((n, mm), np.uint64); cdf = np.zeros((n, mm), np.float64); out = np.zeros(n, np.float64)
+    nz = int(np.count_nonzero((src != dst) & (flow > 0))) + n
+    tr, tc, tv = np.zeros(nz, np.uint64), np.zeros(nz, np.uint64), np.zeros(nz, np.float64)
+    rc = lib.bmc_cma_build(n, flow.size, _ptr(src), _ptr(dst), _ptr(flow), mm, ctypes.byref(m), _ptr(nb), _ptr(cdf), _ptr(out),
+                           _ptr(tr), _ptr(tc), _ptr(tv))
+    if rc != 0:
+        raise BmcError(rc, "bmc_cma_build failed")
+    return dict(n=n, m=mm, neighbors=nb, cdf=cdf, out_flows=out, coo=(tr, tc, tv))
 
 
 def udf_check(source_path):
@@ -298,6 +319,18 @@ class ParticleLoop:
 
     def compact(self):
         self._ck(self.lib.bmc_compact(self.h))
+
+    def get_properties(self, indices=None, with_age=True):
+        """PostProcessing::get_properties: dict(particle_values (n_exp+1, n_p), spatial_values (n_exp+1, n_comp), ages (2, n_p))"""
+        idx = None if indices is None else np.ascontiguousarray(indices, np.uint64)
+        n_exp = self.n_var if idx is None else idx.size
+        n = ctypes.c_uint64()
+        self._ck(self.lib.bmc_get_properties(self.h, _ptr(idx), 0 if idx is None else idx.size, None, None, None, ctypes.byref(n)))
+        n_p = n.value
+        pv = np.zeros((n_exp + 1, n_p), np.float64); sv = np.zeros((n_exp + 1, self.n_compartments), np.float64)
+        ag = np.zeros((2, n_p), np.float64) if with_age else None
+        self._ck(self.lib.bmc_get_properties(self.h, _ptr(idx), 0 if idx is None else idx.size, _ptr(pv), _ptr(sv), _ptr(ag), ctypes.byref(n)))
+        return dict(particle_values=pv, spatial_values=sv, ages=ag)
 
     # ---- device-side handles -------------------------------------------------
     def sources_device_ptr(self):

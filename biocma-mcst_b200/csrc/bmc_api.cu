@@ -879,6 +879,53 @@ int bmc_repartition(bmc_ctx* ctx, uint64_t* out) {
   return BMC_OK;
 }
 
+int bmc_get_properties(bmc_ctx* ctx, const uint64_t* indices, uint64_t n_indices, double* particle_values, double* spatial_values,
+                       double* ages, uint64_t* n_particles) {
+  if (!ctx || ctx->cap == 0) return BMC_ERR_INVALID;
+  const int nv = ctx->vt.n_var;
+  const uint32_t n_exp = indices ? (uint32_t)n_indices : (uint32_t)nv;
+  if (indices) for (uint64_t e = 0; e < n_indices; ++e) if (indices[e] >= (uint64_t)nv) { ctx->err = "exported property index out of range"; return BMC_ERR_RANGE; }
+  int rc;
+  if ((rc = bmc_compact(ctx))) return rc;  // container.force_remove_dead() (post_process.hpp:181)
+  DevState hs;
+  if ((rc = sync_state(ctx, &hs))) return rc;
+  const uint64_t n_p = hs.n_used;
+  if (n_particles) *n_particles = n_p;
+  if (!particle_values && !spatial_values && !ages) return BMC_OK;  // size query
+  cudaStream_t s = ctx->stream;
+  const size_t rows = (size_t)n_exp + 1, chunk = 1u << 21;
+  double* d_spatial = nullptr; uint32_t* d_idx = nullptr;
+  if ((rc = dev_alloc(ctx, &d_spatial, rows * ctx->n_comp))) return rc;
+  CK(cudaMemsetAsync(d_spatial, 0, rows * ctx->n_comp * 8, s));
+  if (indices) {
+    std::vector<uint32_t> idx(indices, indices + n_indices);
+    if ((rc = dev_alloc(ctx, &d_idx, n_exp))) { dev_free(d_spatial); return rc; }
+    CK(cudaMemcpyAsync(d_idx, idx.data(), n_exp * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  if ((rc = ensure_stage(ctx, rows * std::min<size_t>(chunk, std::max<uint64_t>(n_p, 1)) * 8))) { dev_free(d_spatial); dev_free(d_idx); return rc; }
+  for (uint64_t o = 0; o < n_p; o += chunk) {
+    const uint64_t c = std::min<uint64_t>(chunk, n_p - o);
+    ExportParams ep{ctx->props, ctx->cap, ctx->pos, ctx->status, o, c, d_idx, n_exp, (double*)ctx->d_stage, d_spatial, (uint32_t)ctx->n_comp};
+    void* args[] = {&ep};
+    CK(cudaLaunchKernel(ctx->vt.export_fn, dim3((unsigned)std::min<uint64_t>((c + 255) / 256, (uint64_t)ctx->n_sm * 8)), dim3(256), args, 0, s));
+    if ((rc = check_launch(ctx, "export_kernel"))) { dev_free(d_spatial); dev_free(d_idx); return rc; }
+    if (particle_values)  // (n_exp + 1, n_p) LayoutRight like ParticlePropertyViewType
+      for (size_t r = 0; r < rows; ++r)
+        CK(cudaMemcpyAsync(particle_values + r * n_p + o, (double*)ctx->d_stage + r * c, c * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  if (spatial_values) CK(cudaMemcpyAsync(spatial_values, d_spatial, rows * ctx->n_comp * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  dev_free(d_spatial); dev_free(d_idx);
+  if (ages && n_p) {  // ages_value(0,i) = hydraulic, (1,i) = since division; doubles; zero for non-idle (none after the compaction)
+    std::vector<float> ah(n_p), ad(n_p);
+    if ((rc = bmc_get_particles(ctx, n_p, nullptr, nullptr, nullptr, ah.data(), ad.data()))) return rc;
+    for (uint64_t i = 0; i < n_p; ++i) { ages[i] = (double)ah[i]; ages[n_p + i] = (double)ad[i]; }
+  }
+  return BMC_OK;
+}
+
 int bmc_compact(bmc_ctx* ctx) {
   if (!ctx || ctx->cap == 0) return BMC_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));

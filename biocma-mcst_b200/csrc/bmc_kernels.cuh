@@ -1177,6 +1177,43 @@ template <class M> __device__ __forceinline__ void init_body(const InitParams& p
   if ((threadIdx.x & 31) == 0 && m != 0.0) atomicAdd(&p.st->init_mass, m);
 }
 
+// -----------------------------------------------------------------------------
+// get_properties: GetPropertiesFunctor (apps/core/public/core/post_process.hpp:33-118, 173-250).  For every
+// Idle particle i of the chunk [first, first+count): particle_values(k, i) = property (double), row n_exp =
+// M::mass; spatial_values(k, position) += value (per-compartment sums); ages.  `indices` selects the exported
+// properties (HasExportPropertiesPartial, get_number()), nullptr = all (HasExportPropertiesFull).
+// Non-idle particles keep zeros (the reference's views are zero-initialised and the functor returns early).
+// -----------------------------------------------------------------------------
+struct ExportParams {
+  const float* props; size_t cap; const uint32_t* pos; const uint8_t* status;
+  unsigned long long first, count;
+  const uint32_t* indices; uint32_t n_exp;   // exported property columns (n_exp <= n_var)
+  double* particle_values;                   // device chunk buffer, (n_exp + 1) rows of `count`
+  double* spatial_values; uint32_t n_comp;   // (n_exp + 1) x n_comp, accumulated over chunks
+};
+template <class M> __device__ __forceinline__ void export_body(const ExportParams& p) {
+  for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < p.count;
+       j += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long i = p.first + j;
+    const bool idle = p.status[i] == (uint8_t)Idle;
+    float v[M::n_var];
+#pragma unroll
+    for (int k = 0; k < M::n_var; ++k) v[k] = p.props[(size_t)k * p.cap + i];
+    const uint32_t c = p.pos[i];
+    for (uint32_t e = 0; e < p.n_exp; ++e) {
+      const uint32_t k = p.indices ? p.indices[e] : e;
+      float cur = 0.f;
+#pragma unroll
+      for (int q = 0; q < M::n_var; ++q) if ((uint32_t)q == k) cur = v[q];
+      p.particle_values[(size_t)e * p.count + j] = idle ? (double)cur : 0.0;
+      if (idle) atomicAdd(p.spatial_values + (size_t)e * p.n_comp + c, (double)cur);
+    }
+    const double m = M::mass((size_t)i, RegRow{v});
+    p.particle_values[(size_t)p.n_exp * p.count + j] = idle ? m : 0.0;
+    if (idle) atomicAdd(p.spatial_values + (size_t)p.n_exp * p.n_comp + c, m);
+  }
+}
+
 // __global__ entry points of the built-in models (the NVRTC path of user models wraps the same
 // bodies in extern "C" kernels, see bmc_udf.cu)
 template <class M> __global__ void __launch_bounds__(256) pre_step_kernel(const __grid_constant__ PreParams p) { pre_step_body<M>(p); }
@@ -1187,5 +1224,6 @@ __global__ void __launch_bounds__(kBlock * WB, 1) cycle_kernel(const __grid_cons
   cycle_body<M, VEC, PIPE, LAZY, kBlock * WB>(p);
 }
 template <class M> __global__ void __launch_bounds__(256) init_kernel(const __grid_constant__ InitParams p) { init_body<M>(p); }
+template <class M> __global__ void __launch_bounds__(256) export_kernel(const __grid_constant__ ExportParams p) { export_body<M>(p); }
 
 }  // namespace bmc

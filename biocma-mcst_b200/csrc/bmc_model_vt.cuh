@@ -18,6 +18,7 @@ struct ModelVT {
   const void* cycle_eager_fn;  // same with float ages updated every step (direct loads, no staging)
   const void* pre_fn;     // (PreParams)    block = 256
   const void* init_fn;    // (InitParams)   block = 256
+  const void* export_fn;  // (ExportParams) block = 256
   void* jit_library;      // cudaLibrary_t of a user model (unloaded with the context), else nullptr
 };
 
@@ -31,6 +32,7 @@ template <class M, int VEC, int MINB = 1, bool PIPE = false> static ModelVT make
   v.cycle_eager_fn = (const void*)cycle_kernel<M, VEC, (MINB > 3 ? 3 : MINB), false, false>;
   v.pre_fn = (const void*)pre_step_kernel<M>;
   v.init_fn = (const void*)init_kernel<M>;
+  v.export_fn = (const void*)export_kernel<M>;
   v.jit_library = nullptr;
   return v;
 }

@@ -908,6 +908,35 @@ int orc_repartition(void* h, uint64_t* out) {
   for (uint64_t i = 0; i < c.n_used; ++i) if (c.status[i] == Idle) out[c.position[i]]++;
   return 0;
 }
+// PostProcessing::get_properties post_process.hpp:33-118, 173-250: force_remove_dead, then per Idle particle the
+// exported properties + mass as doubles, their per-compartment sums, and both ages.
+static double model_mass(const Ctx& c, size_t i) {
+  const float lin = c_linear_density(1000.0f, (float)0.6e-6);
+  return c.model_v[i * (size_t)c.n_var + 0] * lin;  // every model here: mass = length * lin_density (property 0)
+}
+int orc_get_properties(void* h, const uint64_t* indices, uint64_t n_indices, double* pv, double* sv, double* ages, uint64_t* n_out) {
+  Ctx& c = *(Ctx*)h;
+  remove_inactive(c, c.inactive_counter);
+  const uint64_t n_p = c.n_used;
+  if (n_out) *n_out = n_p;
+  if (!pv && !sv && !ages) return 0;
+  const size_t n_exp = indices ? n_indices : (size_t)c.n_var;
+  if (sv) std::fill(sv, sv + (n_exp + 1) * c.n_comp, 0.0);
+  for (uint64_t i = 0; i < n_p; ++i) {
+    if (c.status[i] != Idle) continue;
+    for (size_t e = 0; e < n_exp; ++e) {
+      const size_t k = indices ? indices[e] : e;
+      const double cur = c.model_v[i * (size_t)c.n_var + k];
+      if (sv) sv[e * c.n_comp + c.position[i]] += cur;
+      if (pv) pv[e * n_p + i] = cur;
+    }
+    const double m = model_mass(c, i);
+    if (sv) sv[n_exp * c.n_comp + c.position[i]] += m;
+    if (pv) pv[n_exp * n_p + i] = m;
+    if (ages) { ages[i] = c.age_hyd[i]; ages[n_p + i] = c.age_div[i]; }
+  }
+  return 0;
+}
 // force_remove_dead particles_container.hpp:463-468
 int orc_compact(void* h) { Ctx& c = *(Ctx*)h; remove_inactive(c, c.inactive_counter); return c.err.empty() ? 0 : -1; }
 // test_container.cpp:62-148 drives handle_division / merge_buffer directly

@@ -54,6 +54,7 @@ def lib():
         L.orc_get_counters.argtypes = [vp, vp]
         L.orc_repartition.argtypes = [vp, vp]
         L.orc_compact.argtypes = [vp]
+        L.orc_get_properties.argtypes = [vp, vp, u64, vp, vp, vp, ctypes.POINTER(u64)]
         L.orc_handle_division.argtypes = [vp, u64]
         L.orc_merge_buffer.argtypes = [vp]
         L.orc_set_status.argtypes = [vp, u64, ctypes.c_uint8]
@@ -200,6 +201,17 @@ class OracleLoop:
 
     def compact(self):
         self._ck(self.L.orc_compact(self.h))
+
+    def get_properties(self, indices=None, with_age=True):
+        idx = None if indices is None else np.ascontiguousarray(indices, np.uint64)
+        n_exp = self.n_var if idx is None else idx.size
+        n = ctypes.c_uint64()
+        self._ck(self.L.orc_get_properties(self.h, _ptr(idx), 0 if idx is None else idx.size, None, None, None, ctypes.byref(n)))
+        n_p = n.value
+        pv = np.zeros((n_exp + 1, n_p), np.float64); sv = np.zeros((n_exp + 1, self.n_compartments), np.float64)
+        ag = np.zeros((2, n_p), np.float64) if with_age else None
+        self._ck(self.L.orc_get_properties(self.h, _ptr(idx), 0 if idx is None else idx.size, _ptr(pv), _ptr(sv), _ptr(ag), ctypes.byref(n)))
+        return dict(particle_values=pv, spatial_values=sv, ages=ag)
 
     # hooks used by the container tests (test_container.cpp)
     def handle_division(self, idx):
