@@ -561,6 +561,9 @@ static void contributions(Ctx& c) {
   const int nc = c.n_c;
   const double w = (double)c.weight;  // const double weight = get_weight(p)  (:179)
   const int T = std::max(1, c.n_threads);
+  // Q2 belongs to the Tag3D functor only; single-compartment cases run Tag0D (kernels.hpp:200-222), whose
+  // lambda skips a non-idle particle and stays inside n_particle (contribution_kernel.hpp:70-88)
+  const bool quirk = c.quirk_contrib_return && c.n_comp > 1;
   std::vector<double> part((size_t)T * nb, 0.0);
   const size_t chunk = 1024, n_chunks = (n + chunk - 1) / chunk;
 #pragma omp parallel num_threads(T)
@@ -573,10 +576,15 @@ static void contributions(Ctx& c) {
     double* acc = part.data() + (size_t)t * nb;
 #pragma omp for schedule(static)
     for (long ch = 0; ch < (long)n_chunks; ++ch) {
-      const size_t p0 = ch * chunk, p1 = std::min(n, p0 + chunk);
+      const size_t p0 = ch * chunk;
+      size_t p1 = std::min(n, p0 + chunk);
+      // Q2, second half: the reference bounds the 32-particle runs by `i >= n_particle` with i the RUN index, not
+      // the particle (:172-175), so the last run reads up to 31 slots past n_used — stale rows left behind by a
+      // compaction still count.  Reproduced only in quirk mode (used to compare with the reference sources).
+      if (quirk) p1 = std::min<size_t>(c.n_allocated, p0 + ((p1 - p0 + 31) / 32) * 32);
       for (size_t i0 = p0; i0 < p1; i0 += 32) {  // work_per_thread = 32 (:156)
         for (size_t p = i0; p < std::min(p1, i0 + 32); ++p) {
-          if (c.status[p] != Idle) { if (c.quirk_contrib_return) break; else continue; }
+          if (c.status[p] != Idle) { if (quirk) break; else continue; }
           const size_t pos = c.position[p];
           for (int j = 0; j < nc; ++j) acc[(size_t)j + ns * pos] += w * (double)c.contribs[p * nc + j];
         }

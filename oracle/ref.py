@@ -1,0 +1,167 @@
+"""ctypes binding of oracle/_ref/libbmc_ref.so: the REFERENCE'S OWN hot-path sources compiled from
+/root/reference over oracle/kokkos_shim (see oracle/ref_driver.cpp).
+
+TEST INFRASTRUCTURE ONLY.  Same method names as oracle.OracleLoop / biocma_mcst_b200.ParticleLoop so one
+test body drives all three.  The library can only be (re)built where /root/reference exists; elsewhere the
+prebuilt file that travelled with the snapshot is used, and `available()` says whether there is one.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libbmc_ref.so")
+REFERENCE_ROOT = os.environ.get("BMC_REFERENCE_ROOT", "/root/reference")
+EVENTS = ("NewParticle", "Exit", "Move", "Death", "Overflow", "ChangeWeight")
+MODEL_IDS = {"fixed_length": 0, "monod": 1, "simple_acetate": 2}
+_lib = None
+
+
+def can_build():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "apps", "libs", "simulation"))
+
+
+def build(force=False):
+    """compile the reference sources where they lie (oracle/Makefile target `ref`); no-op without them"""
+    if not can_build():
+        return LIB_PATH if os.path.exists(LIB_PATH) else None
+    cmd = ["make", "-C", _HERE, "REF=" + REFERENCE_ROOT, "ref"] + (["-B"] if force else [])
+    subprocess.run(cmd, check=True, capture_output=True)
+    return LIB_PATH
+
+
+def available():
+    return os.path.exists(LIB_PATH) or can_build()
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if can_build():
+            build()
+        L = ctypes.CDLL(LIB_PATH)
+        vp, u64, dbl, u32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_double, ctypes.c_uint32
+        L.ref_create.restype = vp
+        L.ref_create.argtypes = [ctypes.c_int, u64, u64, u64, u32, u64]
+        L.ref_destroy.argtypes = [vp]; L.ref_destroy.restype = None
+        L.ref_last_error.argtypes = [vp]; L.ref_last_error.restype = ctypes.c_char_p
+        L.ref_n_var.argtypes = [vp]; L.ref_n_c.argtypes = [vp]
+        L.ref_set_runtime.argtypes = [vp, u64, dbl, dbl, dbl, dbl]; L.ref_set_runtime.restype = None
+        L.ref_set_step.argtypes = [vp, u32]; L.ref_set_step.restype = None
+        L.ref_set_particles.argtypes = [vp, u64, vp, vp, vp, vp, vp]
+        L.ref_get_particles.argtypes = [vp, u64, vp, vp, vp, vp, vp]
+        L.ref_get_contribs.argtypes = [vp, u64, vp]
+        L.ref_set_weight.argtypes = [vp, dbl]; L.ref_set_weight.restype = None
+        L.ref_domain_update.argtypes = [vp, vp, vp, vp, vp, u64]
+        L.ref_set_leaving_flows.argtypes = [vp, u64, vp, vp, vp]
+        L.ref_set_concentrations.argtypes = [vp, vp]
+        L.ref_cycle.argtypes = [vp, dbl]
+        L.ref_get_sources.argtypes = [vp, vp]
+        L.ref_get_counters.argtypes = [vp, vp]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class RefLoop:
+    """The reference's cycleProcess on the CPU (serial).  The reference refuses N <= particles_per_team
+    (kernels.hpp:130-134,163-167); `particles_per_team` (a power of two, multiple of 32) lowers the
+    KernelDispatchOptions so that small cases run."""
+
+    def __init__(self, model, n_species=1, n_compartments=1, *, seed=2024, rank=0, particles_per_team=1024,
+                 allocation_factor=1.5, buffer_ratio=0.6, dead_ratio=0.01, min_removal=0, shrink_ratio=0.0, **_):
+        self.L = lib()
+        self.model = MODEL_IDS[model]
+        self.h = self.L.ref_create(self.model, n_species, n_compartments, seed, rank, particles_per_team)
+        assert self.h, "ref_create failed"
+        self.n_var, self.n_c = self.L.ref_n_var(self.h), self.L.ref_n_c(self.h)
+        self.n_species, self.n_compartments = int(n_species), int(n_compartments)
+        self.L.ref_set_runtime(self.h, min_removal, buffer_ratio, allocation_factor, shrink_ratio, dead_ratio)
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"reference error {rc}: {self.L.ref_last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h:
+            self.L.ref_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_particles(self, props, position=None, status=None, age_hyd=None, age_div=None):
+        props = np.ascontiguousarray(props, np.float32)
+        n = props.shape[1]
+        position = None if position is None else np.ascontiguousarray(position, np.uint64)
+        status = None if status is None else np.ascontiguousarray(status, np.uint8)
+        age_hyd = None if age_hyd is None else np.ascontiguousarray(age_hyd, np.float32)
+        age_div = None if age_div is None else np.ascontiguousarray(age_div, np.float32)
+        self._ck(self.L.ref_set_particles(self.h, n, _ptr(props), _ptr(position), _ptr(status), _ptr(age_hyd), _ptr(age_div)))
+
+    def n_used(self):
+        return self.counters()["n_used"]
+
+    def get_particles(self, n=None):
+        n = self.n_used() if n is None else int(n)
+        props = np.empty((self.n_var, n), np.float32); pos = np.empty(n, np.uint64); st = np.empty(n, np.uint8)
+        ah = np.empty(n, np.float32); ad = np.empty(n, np.float32)
+        self._ck(self.L.ref_get_particles(self.h, n, _ptr(props), _ptr(pos), _ptr(st), _ptr(ah), _ptr(ad)))
+        return dict(props=props, position=pos, status=st, age_hyd=ah, age_div=ad)
+
+    def get_contribs(self, n=None):
+        n = self.n_used() if n is None else int(n)
+        out = np.empty((self.n_c, n), np.float32)
+        self._ck(self.L.ref_get_contribs(self.h, n, _ptr(out)))
+        return out
+
+    def set_weight(self, w):
+        self.L.ref_set_weight(self.h, float(w))
+
+    def domain_update(self, volumes, neighbors_flat, out_flows, proba_flat):
+        vol = np.ascontiguousarray(volumes, np.float64); of = np.ascontiguousarray(out_flows, np.float64)
+        if neighbors_flat is None:
+            nb = np.zeros((self.n_compartments, 1), np.uint64); pr = np.ones((self.n_compartments, 1))
+        else:
+            nb = np.ascontiguousarray(neighbors_flat, np.uint64).reshape(self.n_compartments, -1)
+            pr = np.ascontiguousarray(proba_flat, np.float64).reshape(self.n_compartments, -1)
+        self._ck(self.L.ref_domain_update(self.h, _ptr(vol), _ptr(nb), _ptr(of), _ptr(pr), nb.shape[1]))
+
+    def set_leaving_flows(self, flows):
+        flows = list(flows)
+        idx = np.array([f[0] for f in flows], np.uint64); q = np.array([f[1] for f in flows], np.float64)
+        v = np.array([f[2] for f in flows], np.float64)
+        self._ck(self.L.ref_set_leaving_flows(self.h, len(flows), _ptr(idx), _ptr(q), _ptr(v)))
+
+    def set_concentrations(self, c):
+        c = np.ascontiguousarray(c, np.float64)
+        self._ck(self.L.ref_set_concentrations(self.h, _ptr(c)))
+
+    def get_sources(self):
+        out = np.empty(self.n_species * self.n_compartments, np.float64)
+        self._ck(self.L.ref_get_sources(self.h, _ptr(out)))
+        return out
+
+    def cycle(self, d_t):
+        self._ck(self.L.ref_cycle(self.h, float(d_t)))
+
+    cycle_process = cycle
+
+    def sync(self):
+        pass
+
+    def counters(self):
+        c = np.zeros(16, np.uint64)
+        self._ck(self.L.ref_get_counters(self.h, _ptr(c)))
+        c = [int(x) for x in c]
+        return dict(events={EVENTS[i]: c[i] for i in range(6)}, n_used=c[6], n_inactive=c[7], last_out=c[8],
+                    last_dead=c[9], last_waiting_allocation=c[10], buffer_index=c[11], capacity=c[12], total_out=c[13],
+                    total_new=c[14], n_compactions=c[15])

@@ -1,0 +1,295 @@
+// =============================================================================
+// oracle/ref_driver.cpp — TEST INFRASTRUCTURE, NOT THE PRODUCT.
+//
+// Drives the REFERENCE'S OWN hot-path sources, compiled from /root/reference where
+// they lie (never copied), on the CPU through oracle/kokkos_shim (a serial stand-in
+// for Kokkos).  Built by `make -C oracle ref` into oracle/_ref/libbmc_ref.so.  Used
+// only by tests/ and by tools that generate tests/golden/ fixtures, to pin
+// oracle/bmc_oracle.cpp (and through it the CUDA path) to the reference:
+//
+//   reference code that runs here, unmodified
+//     Simulation::KernelInline::CycleFunctors<Space,Model>::update / launch_model / launch_move
+//                                   simulation/kernels/kernels.hpp:49-224
+//     CycleFunctor<M>               simulation/kernels/model_kernel.hpp:163-268
+//     ContributionFunctor<M>        simulation/kernels/contribution_kernel.hpp:48-186
+//     MoveFunctor (move + leave)    simulation/kernels/move_kernel.hpp:140-669
+//     probability_leaving<>         simulation/probability_leaving.hpp:16-46
+//     MC::ParticlesContainer<M>     mc/particles_container.hpp (handle_division, merge_buffer,
+//                                   update_and_remove_inactive, CompactParticlesFunctor, InsertFunctor)
+//     MC::ReactorDomain             mc/domain.hpp + mc/src/domain.cpp
+//     MC::EventContainer            mc/events.hpp
+//     Models::FixedLength, Models::Monod, Models::SimpleAcetate   models/*.hpp
+//     Common::c_league_size         common/src/common.cpp
+//   what this file adds
+//     the body of SimulationUnit::cycleProcess / post_cycle (simulation/simulation.hpp:183-239), which
+//     cannot be instantiated here (SimulationUnit needs Eigen + rcmtool): the same calls in the same order;
+//     Tap<M>: forwards every model hook unchanged after telling the shim's random generator which particle
+//     it serves (the reference's pool is not indexable by particle; DESIGN.md §4 defines the streams);
+//     MonodQ1: SURVEY.md Q1 — monod.hpp predates the 7-argument hook concept and has no n_c; the wrapper
+//     calls Models::Monod::{init,update,division,mass} as they are and mirrors phi_s_c into contribs(.,0).
+//
+// Not reproduced (shim limits, stated in DESIGN.md): parallel execution order, the XorShift1024 pool,
+// ScatterView duplication (float sums are accumulated in particle order).
+// =============================================================================
+#include <Kokkos_Core.hpp>
+
+#include <mc/macros.hpp>
+// monod.hpp ends with CHECK_MODEL(Monod), which cannot hold: check the models we wrap ourselves
+#undef CHECK_MODEL
+#define CHECK_MODEL(name)
+#include <models/monod.hpp>
+#undef CHECK_MODEL
+#define CHECK_MODEL(name) static_assert(ModelType<name>, #name);
+#include <models/fixed_length.hpp>
+#include <models/simple_acetate.hpp>
+#include <simulation/kernels/kernels.hpp>
+
+#include <memory>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------ shim hooks
+namespace {
+Kokkos::shim::RngState g_rng;
+size_t g_team_move = 1024;
+}  // namespace
+namespace Kokkos::shim {
+RngState& rng() { return g_rng; }
+void kernel_begin(const std::string& label) {
+  if (label == "cycle_move") { g_rng.mode = Mode::MoveTape; g_rng.per_team = g_team_move; g_rng.tape = 0; }
+  else if (label == "cycle_move_leave") { g_rng.mode = Mode::Leave; }
+  else { g_rng.mode = Mode::Sequential; }
+}
+void kernel_end() { g_rng.mode = Mode::Sequential; }
+void team_begin(size_t league_rank) { g_rng.league = league_rank; g_rng.tape = 0; }
+void range_index(size_t i) { g_rng.index = i; }
+}  // namespace Kokkos::shim
+
+// ------------------------------------------------------------------ model wrappers
+namespace {
+// draw blocks of the model hooks' generator: update/init 3.., division 0x40000001..
+constexpr uint32_t kBaseUpdate = 2u, kBaseDivision = 0x40000000u;
+
+template <class M> struct Tap : M {
+  using Self = Tap;
+  KOKKOS_INLINE_FUNCTION static MC::Status update(const MC::pool_type& pool, typename M::FloatType d_t, std::size_t idx,
+                                                  const typename M::SelfParticle& arr, const typename M::SelfContribs& contribs,
+                                                  std::size_t position, const MC::LocalConcentration& c) {
+    g_rng.start_sequence((uint32_t)idx, kBaseUpdate);
+    return M::update(pool, d_t, idx, arr, contribs, position, c);
+  }
+  KOKKOS_INLINE_FUNCTION static void division(const MC::pool_type& pool, std::size_t idx, std::size_t idx2,
+                                              const typename M::SelfParticle& arr, const typename M::SelfParticle& buf) {
+    g_rng.start_sequence((uint32_t)idx, kBaseDivision);
+    M::division(pool, idx, idx2, arr, buf);
+  }
+};
+
+struct MonodQ1 {
+  using Base = Models::Monod;
+  using Self = MonodQ1;
+  using FloatType = Base::FloatType;
+  using uniform_weight = std::true_type;
+  using Config = std::nullopt_t;
+  static constexpr std::size_t n_var = Base::n_var;
+  static constexpr std::size_t n_c = 1;
+  using SelfParticle = Base::SelfParticle;
+  using SelfContribs = MC::ParticlesContribs<n_c, FloatType>;
+  KOKKOS_INLINE_FUNCTION static void init(const MC::pool_type& pool, std::size_t idx, const SelfParticle& arr) { Base::init(pool, idx, arr); }
+  KOKKOS_INLINE_FUNCTION static double mass(std::size_t idx, const SelfParticle& arr) { return Base::mass(idx, arr); }
+  KOKKOS_INLINE_FUNCTION static MC::Status update(const MC::pool_type& pool, FloatType d_t, std::size_t idx, const SelfParticle& arr,
+                                                  const SelfContribs& contribs, std::size_t position, const MC::LocalConcentration& c) {
+    const MC::Status s = Base::update(pool, d_t, idx, arr, position, c);
+    contribs(idx, 0) = arr(idx, INDEX_FROM_ENUM(Base::particle_var::phi_s_c));
+    return s;
+  }
+  KOKKOS_INLINE_FUNCTION static void division(const MC::pool_type& pool, std::size_t idx, std::size_t idx2, const SelfParticle& arr,
+                                              const SelfParticle& buf) { Base::division(pool, idx, idx2, arr, buf); }
+};
+static_assert(ModelType<MonodQ1>);
+static_assert(ModelType<Tap<Models::FixedLength>>);
+static_assert(ModelType<Tap<Models::SimpleAcetate>>);
+static_assert(ModelType<Tap<MonodQ1>>);
+static_assert(ConstWeightModelType<Tap<MonodQ1>>);
+
+// ------------------------------------------------------------------ one simulation unit's worth of state
+struct IRef {
+  virtual ~IRef() = default;
+  std::string err;
+  uint64_t seed = 2024; uint32_t rank = 0, step = 0;
+  size_t n_species = 1, n_comp = 1;
+  MC::RuntimeParameters rt{0, 0.6, 1.5, 0.0, 0.01};
+  KernelDispatchOptions opts{};
+  // domain inputs (applied lazily: init_inner reallocates every view)
+  std::vector<double> vol, out_flows, proba; std::vector<size_t> neigh; size_t m = 1;
+  std::vector<size_t> lf_index; std::vector<double> lf_flow, lf_vol;
+  bool domain_dirty = true;
+  unsigned long long last_out = 0, last_dead = 0, last_waiting = 0, total_out = 0, total_new = 0, n_compactions = 0;
+  virtual int n_var() const = 0;
+  virtual int n_c() const = 0;
+  virtual void set_particles(size_t n, const float* props, const uint64_t* pos, const uint8_t* st, const float* ah, const float* ad) = 0;
+  virtual void get_particles(size_t n, float* props, uint64_t* pos, uint8_t* st, float* ah, float* ad) = 0;
+  virtual void get_contribs(size_t n, float* out) = 0;
+  virtual void set_weight(double w) = 0;
+  virtual void set_conc(const double* c) = 0;
+  virtual void cycle(double dt) = 0;
+  virtual void get_sources(double* out) = 0;
+  virtual void counters(unsigned long long* c) = 0;
+};
+
+template <class M> struct Ref final : IRef {
+  using Container = MC::ParticlesContainer<M>;
+  using Functors = Simulation::KernelInline::CycleFunctors<ComputeSpace, M>;
+  Container container;
+  MC::ReactorDomain domain;
+  MC::EventContainer events;
+  MC::pool_type pool;
+  Kokkos::View<double**, Kokkos::LayoutLeft, ComputeSpace> conc;  // (n_species, n_comp): scalar_simulation.hpp:116-119
+  MC::kernelContribution contribs;                                  // float (n_species, n_comp)
+  MC::ContributionView scatter;
+  Simulation::ProbeAutogeneratedBuffer probe_leave, probe_div;
+  std::unique_ptr<Functors> functors;
+  double weight = 1.0;
+
+  int n_var() const override { return (int)M::n_var; }
+  int n_c() const override { return (int)M::n_c; }
+
+  void set_particles(size_t n, const float* props, const uint64_t* pos, const uint8_t* st, const float* ah, const float* ad) override {
+    container = Container(rt, n, 0);  // particles_container.hpp:670-697
+    for (size_t i = 0; i < n; ++i) {
+      for (size_t k = 0; k < M::n_var; ++k) container.model(i, k) = props[k * n + i];
+      container.position(i) = pos ? pos[i] : 0;
+      container.status(i) = st ? static_cast<MC::Status>(st[i]) : MC::Status::Idle;
+      container.ages(i, 0) = ah ? ah[i] : 0.f;
+      container.ages(i, 1) = ad ? ad[i] : 0.f;
+    }
+    container.weights(0) = (typename M::FloatType)weight;
+    functors.reset();
+  }
+  void get_particles(size_t n, float* props, uint64_t* pos, uint8_t* st, float* ah, float* ad) override {
+    for (size_t i = 0; i < n; ++i) {
+      for (size_t k = 0; k < M::n_var; ++k) props[k * n + i] = container.model(i, k);
+      pos[i] = container.position(i); st[i] = (uint8_t)container.status(i);
+      ah[i] = container.ages(i, 0); ad[i] = container.ages(i, 1);
+    }
+  }
+  void get_contribs(size_t n, float* out) override {
+    for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < M::n_c; ++j) out[j * n + i] = container.contribs(i, j);
+  }
+  void set_weight(double w) override { weight = w; if (container.weights.extent(0)) container.weights(0) = (typename M::FloatType)w; }
+  void set_conc(const double* c) override {
+    if (conc.extent(0) != n_species || conc.extent(1) != n_comp) { conc = decltype(conc)("conc", n_species, n_comp); functors.reset(); }
+    for (size_t j = 0; j < n_comp; ++j) for (size_t s = 0; s < n_species; ++s) conc(s, j) = c[s + n_species * j];
+  }
+  void apply_domain() {
+    if (!domain_dirty) return;
+    domain = MC::ReactorDomain(std::span<double>(vol));          // mcinit.hpp:83
+    domain.init_inner(lf_index.size());                          // simulation.cpp:74
+    domain.update(vol, neigh, out_flows, proba);                 // simulation.cpp:112-120
+    for (size_t i = 0; i < lf_index.size(); ++i)                 // simulation.model.cpp:101-110 (update_feed)
+      if (lf_flow[i] > 0.) domain.set_leaving_flow(i, lf_index[i], lf_flow[i], lf_vol[i]);
+    domain_dirty = false;
+    functors.reset();
+  }
+
+  // SimulationUnit::cycleProcess + post_cycle (simulation/simulation.hpp:183-239), call for call
+  void cycle(double d_t) override {
+    const size_t n_particle = container.n_particles();
+    if (n_particle == 0) return;
+    apply_domain();
+    if (conc.extent(0) != n_species) throw std::runtime_error("concentrations not set");
+    if (contribs.extent(0) != n_species || contribs.extent(1) != n_comp) {
+      contribs = MC::kernelContribution("contribs", n_species, n_comp);
+      scatter = Kokkos::Experimental::create_scatter_view(contribs);  // simulation.cpp:76-77
+      functors.reset();
+    }
+    g_rng.key[0] = (uint32_t)seed; g_rng.key[1] = (uint32_t)(seed >> 32); g_rng.rank = rank; g_rng.step = step;
+    g_team_move = opts.m_p_p_team_move;
+    if (!functors)  // init_functors (simulation.hpp:165-181)
+      functors = std::make_unique<Functors>(opts, container, pool, MC::KernelConcentrationType(conc), scatter, events,
+                                            domain.get_const_inner(), probe_leave, probe_div);
+    functors->update(d_t, container, domain.get_const_inner());  // pre_cycle (simulation.hpp:154-162)
+    // the concentrations view is captured by value in the cycle functor: same allocation, refreshed in place above
+    scatter.reset();                                             // :201
+    Kokkos::deep_copy(contribs, 0.f);  // shim ScatterView writes through; the reference's target is empty here (simulation.cpp:147-150)
+    functors->launch_model(n_particle);                          // :202
+    if (functors->move_kernel.need_launch()) functors->launch_move(n_particle);  // :205-208
+    // post_cycle
+    Kokkos::fence();
+    Kokkos::Experimental::contribute(contribs, scatter);         // scatter_contribute, simulation.cpp:143-151
+    const auto [host_red, host_out_counter] = functors->get_host_reduction();
+    const size_t before = container.n_particles(), inactive_before = container.get_inactive();
+    container.update_and_remove_inactive(host_out_counter, host_red.dead_total);
+    if (container.n_particles() != before || (container.get_inactive() == 0 && inactive_before + host_out_counter > 0)) ++n_compactions;
+    const size_t pre_merge = container.n_particles();
+    container.merge_buffer();
+    total_new += container.n_particles() - pre_merge;
+    last_out = host_out_counter; last_dead = host_red.dead_total; last_waiting = host_red.waiting_allocation_particle;
+    total_out += host_out_counter;
+    ++step;
+  }
+  void get_sources(double* out) override {
+    for (size_t j = 0; j < n_comp; ++j) for (size_t s = 0; s < n_species; ++s)
+      out[s + n_species * j] = contribs.extent(0) ? (double)contribs(s, j) : 0.0;
+  }
+  void counters(unsigned long long* c) override {
+    const auto ev = events.get_span();
+    for (int k = 0; k < 6; ++k) c[k] = ev[k];
+    c[6] = container.n_particles(); c[7] = container.get_inactive(); c[8] = last_out; c[9] = last_dead; c[10] = last_waiting;
+    c[11] = 0; c[12] = container.capacity(); c[13] = total_out; c[14] = total_new; c[15] = n_compactions;
+  }
+};
+}  // namespace
+
+#define REF_TRY(h, ...) try { __VA_ARGS__; return 0; } catch (const std::exception& e) { (h)->err = e.what(); return -1; }
+
+extern "C" {
+// model ids as in oracle/oracle.py: 0 fixed_length, 1 monod, 2 simple_acetate
+void* ref_create(int model, uint64_t n_species, uint64_t n_comp, uint64_t seed, uint32_t rank, uint64_t particles_per_team) {
+  IRef* r = nullptr;
+  try {
+    if (model == 0) r = new Ref<Tap<Models::FixedLength>>();
+    else if (model == 1) r = new Ref<Tap<MonodQ1>>();
+    else if (model == 2) r = new Ref<Tap<Models::SimpleAcetate>>();
+    else return nullptr;
+  } catch (...) { return nullptr; }
+  r->n_species = n_species; r->n_comp = n_comp; r->seed = seed; r->rank = rank;
+  if (particles_per_team) {  // KernelDispatchOptions (execinfo.hpp:11-17); default = the generated 1024
+    r->opts.m_p_p_team_model = r->opts.m_p_p_team_move = r->opts.m_p_p_team_contribs = particles_per_team;
+  }
+  r->vol.assign(n_comp, 1.0); r->out_flows.assign(n_comp, 0.0); r->neigh.assign(n_comp, 0); r->proba.assign(n_comp, 1.0);
+  for (size_t i = 0; i < n_comp; ++i) r->neigh[i] = i;
+  return r;
+}
+void ref_destroy(void* h) { delete static_cast<IRef*>(h); }
+const char* ref_last_error(void* h) { return static_cast<IRef*>(h)->err.c_str(); }
+int ref_n_var(void* h) { return static_cast<IRef*>(h)->n_var(); }
+int ref_n_c(void* h) { return static_cast<IRef*>(h)->n_c(); }
+void ref_set_runtime(void* h, uint64_t min_removal, double buffer_ratio, double allocation_factor, double shrink_ratio, double dead_ratio) {
+  static_cast<IRef*>(h)->rt = MC::RuntimeParameters{min_removal, buffer_ratio, allocation_factor, shrink_ratio, dead_ratio};
+}
+void ref_set_step(void* h, uint32_t s) { static_cast<IRef*>(h)->step = s; }
+int ref_set_particles(void* h, uint64_t n, const float* props, const uint64_t* pos, const uint8_t* st, const float* ah, const float* ad) {
+  auto* r = static_cast<IRef*>(h); REF_TRY(r, r->set_particles(n, props, pos, st, ah, ad));
+}
+int ref_get_particles(void* h, uint64_t n, float* props, uint64_t* pos, uint8_t* st, float* ah, float* ad) {
+  auto* r = static_cast<IRef*>(h); REF_TRY(r, r->get_particles(n, props, pos, st, ah, ad));
+}
+int ref_get_contribs(void* h, uint64_t n, float* out) { auto* r = static_cast<IRef*>(h); REF_TRY(r, r->get_contribs(n, out)); }
+void ref_set_weight(void* h, double w) { static_cast<IRef*>(h)->set_weight(w); }
+int ref_domain_update(void* h, const double* vol, const uint64_t* neigh, const double* out_flows, const double* proba, uint64_t m) {
+  auto* r = static_cast<IRef*>(h);
+  REF_TRY(r, {
+    r->vol.assign(vol, vol + r->n_comp); r->out_flows.assign(out_flows, out_flows + r->n_comp);
+    r->neigh.assign(neigh, neigh + r->n_comp * m); r->proba.assign(proba, proba + r->n_comp * m); r->m = m; r->domain_dirty = true;
+  });
+}
+int ref_set_leaving_flows(void* h, uint64_t k, const uint64_t* idx, const double* flow, const double* vol) {
+  auto* r = static_cast<IRef*>(h);
+  REF_TRY(r, { r->lf_index.assign(idx, idx + k); r->lf_flow.assign(flow, flow + k); r->lf_vol.assign(vol, vol + k); r->domain_dirty = true; });
+}
+int ref_set_concentrations(void* h, const double* c) { auto* r = static_cast<IRef*>(h); REF_TRY(r, r->set_conc(c)); }
+int ref_cycle(void* h, double dt) { auto* r = static_cast<IRef*>(h); REF_TRY(r, r->cycle(dt)); }
+int ref_get_sources(void* h, double* out) { auto* r = static_cast<IRef*>(h); REF_TRY(r, r->get_sources(out)); }
+int ref_get_counters(void* h, unsigned long long* c) { auto* r = static_cast<IRef*>(h); REF_TRY(r, r->counters(c)); }
+}

@@ -1,0 +1,191 @@
+"""Parity against the REFERENCE'S OWN SOURCES.
+
+oracle/_ref/libbmc_ref.so is the reference's hot path — CycleFunctors / CycleFunctor / ContributionFunctor /
+MoveFunctor, ParticlesContainer, ReactorDomain, EventContainer and the model headers — compiled from
+/root/reference where it lies, over oracle/kokkos_shim (serial stand-in for Kokkos; random streams as
+DESIGN.md §4).  tests/golden/ref_*.npz hold its inputs and per-step outputs on seeded cases
+(tools/make_golden.py).  Here:
+
+  CPU suite   the oracle reproduces every fixture: compartment indices, statuses, counters, event tallies,
+              float properties and both ages BIT-EXACT on every snapshot; source terms to 2e-5 relative
+              (the reference sums them in float, the oracle in double: SURVEY Q7/Q19);
+              where /root/reference exists the library is rebuilt and compared live on other seeds/sizes,
+              and the committed fixtures are checked to be reproducible.
+  -m gpu      the CUDA path (through the C ABI) reproduces the same fixtures.
+
+SURVEY Q2 (contribution_kernel.hpp:172-178): the reference's Tag3D contribution loop stops a 32-particle run
+at its first non-idle particle and bounds the runs by the run index, so exited particles suppress their
+neighbours' uptake and up to 31 stale rows past n_used still count.  The oracle reproduces both only in its
+`quirk_contrib_return` mode, which is how the fixtures' source terms are matched on every step; the default
+(physically meant) mode and the CUDA path agree with the reference wherever no particle is inactive.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import util
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_*.npz")))
+NAMES = [os.path.basename(p)[4:-4] for p in GOLDEN]
+SRC_RTOL = 2e-5  # float accumulation over <= 2.8e3 particles in the reference vs fp64 here
+
+
+def _load(name):
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"ref_{name}.npz"))
+    g = {k: z[k] for k in z.files}
+    for k in ("model",):
+        g[k] = str(g[k])
+    for k in ("n", "n_comp", "steps", "particles_per_team", "seed", "n_species"):
+        g[k] = int(g[k])
+    for k in ("dt", "weight"):
+        g[k] = float(g[k])
+    return g
+
+
+def _feed(loop, g):
+    loop.set_particles(g["props0"], g["pos0"].astype(np.uint64), None)
+    loop.set_weight(g["weight"])
+    if g["n_comp"] > 1:
+        loop.domain_update(g["volumes"], g["neighbors"].astype(np.uint64), g["out_flows"], g["cdf"])
+    else:
+        loop.domain_update(g["volumes"], None, g["out_flows"], None)
+    loop.set_leaving_flows([(int(f[0]), float(f[1]), float(f[2])) for f in g["flows"]])
+    loop.set_concentrations(g["conc0"])
+
+
+def _conc(g, step):
+    return util.conc_at(dict(conc=g["conc0"]), step)
+
+
+def _counters_row(c):
+    from ref import EVENTS
+    return [c["events"][e] for e in EVENTS] + [c[k] for k in util.COUNTER_KEYS]
+
+
+def _check_against_golden(loop, g, *, exact_props=True, sources="all", prop_rtol=1e-6):
+    """drives `loop` through the fixture; sources: 'all' | 'quirk_free' (steps before any particle is inactive)"""
+    snaps = set(int(s) for s in g["snap_steps"])
+    quirk_free = True
+    for s in range(g["steps"]):
+        quirk_free = quirk_free and int(g["inactive_before"][s]) == 0
+        loop.set_concentrations(_conc(g, s))
+        loop.cycle(g["dt"])
+        got = _counters_row(loop.counters())
+        want = [int(x) for x in g["counters"][s]]
+        assert got == want, (s, got, want)
+        if sources == "all" or quirk_free:
+            a, b = loop.get_sources(), g["sources"][s]
+            scale = np.max(np.abs(b)) + 1e-300
+            assert np.max(np.abs(a - b)) <= SRC_RTOL * scale, (s, np.max(np.abs(a - b)) / scale)
+        if s in snaps:
+            n = want[6]
+            st = loop.get_particles(n)
+            assert np.array_equal(st["position"][:n].astype(np.uint32), g[f"pos_{s}"]), (s, "compartment indices differ")
+            assert np.array_equal(st["status"][:n], g[f"status_{s}"]), (s, "statuses differ")
+            if exact_props:
+                assert np.array_equal(st["props"][:, :n].view(np.uint32), g[f"props_{s}"].view(np.uint32)), (s, "properties not bit-identical")
+                assert np.array_equal(st["age_div"][:n].view(np.uint32), g[f"age_div_{s}"].view(np.uint32)), (s, "age_div")
+                assert np.array_equal(st["age_hyd"][:n].view(np.uint32), g[f"age_hyd_{s}"].view(np.uint32)), (s, "age_hyd")
+            else:
+                np.testing.assert_allclose(st["props"][:, :n], g[f"props_{s}"], rtol=prop_rtol, atol=0)
+                np.testing.assert_allclose(st["age_div"][:n], g[f"age_div_{s}"], rtol=1e-6, atol=0)
+                np.testing.assert_allclose(st["age_hyd"][:n], g[f"age_hyd_{s}"], rtol=1e-6, atol=0)
+
+
+def test_fixtures_present():
+    assert len(NAMES) >= 8, NAMES
+    g = _load("monod_cma")
+    last = g["counters"][-1]
+    # the fixture exercises the whole path: divisions, outlet exits, moves, >= 2 compactions
+    assert last[0] > 0 and last[1] > 0 and last[2] > 0 and last[-1] >= 2, last
+
+
+# ----------------------------------------------------------------------------- CPU: oracle vs reference outputs
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_reproduces_reference_fixture(orc, name):
+    g = _load(name)
+    o = orc.OracleLoop(g["model"], g["n_species"], g["n_comp"], seed=g["seed"])
+    _feed(o, g)
+    o.set_quirk_contrib_return(True)   # the reference's contribution loop, bug for bug (Q2): sources match on EVERY step
+    _check_against_golden(o, g, sources="all")
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_default_mode_reproduces_reference_state(orc, name):
+    # default (physically meant) contribution loop: particle state, counters and tallies are unaffected by Q2;
+    # the source terms agree with the reference as long as no particle is inactive
+    g = _load(name)
+    o = orc.OracleLoop(g["model"], g["n_species"], g["n_comp"], seed=g["seed"], n_threads=2)
+    _feed(o, g)
+    _check_against_golden(o, g, sources="quirk_free")
+
+
+def _ref_or_skip():
+    import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref/libbmc_ref.so absent and /root/reference not mounted")
+    return ref
+
+
+@pytest.mark.parametrize("model,n,n_comp,ppt,kw", [
+    ("monod", 5000, 20, 1024, dict(near_division=0.5, p_exit=0.2, p_move=0.05, dt=20.0, seed=7)),
+    ("fixed_length", 4100, 37, 1024, dict(near_division=0.6, p_exit=0.3, p_move=0.2, dt=20.0, seed=11)),
+    ("simple_acetate", 3000, 8, 512, dict(near_division=0.5, p_exit=0.1, p_move=0.1, dt=20.0, seed=13)),
+    ("monod", 2300, 1, 256, dict(near_division=0.5, p_exit=0.05, dt=20.0, seed=17)),
+])
+def test_live_reference_equals_oracle(orc, synth, model, n, n_comp, ppt, kw):
+    ref = _ref_or_skip()
+    case = util.make_case(synth, model, n, n_comp, **kw)
+    o = orc.OracleLoop(model, case["n_species"], n_comp, seed=case["seed"])
+    r = ref.RefLoop(model, case["n_species"], n_comp, seed=case["seed"], particles_per_team=ppt)
+    util.load_case(o, case); util.load_case(r, case)
+    o.set_quirk_contrib_return(True)
+    for s in range(10):
+        c = util.conc_at(case, s)
+        o.set_concentrations(c); r.set_concentrations(c)
+        o.cycle(case["dt"]); r.cycle(case["dt"])
+        co, cr = o.counters(), r.counters()
+        util.assert_counters_equal(co, cr)
+        n_u = co["n_used"]
+        util.assert_state_equal(o.get_particles(n_u), r.get_particles(n_u), n_u, exact_props=True)
+        a, b = o.get_sources(), r.get_sources()
+        assert np.max(np.abs(a - b)) <= SRC_RTOL * (np.max(np.abs(b)) + 1e-300)
+    assert cr["total_new"] > 0 and (n_comp == 1 or cr["events"]["Move"] > 0)
+
+
+def test_fixture_is_reproducible(synth):
+    # the committed fixtures are what the reference sources produce today
+    ref = _ref_or_skip()
+    import importlib.util as iu
+    spec = iu.spec_from_file_location("make_golden", os.path.join(os.path.dirname(GOLDEN[0]), "..", "..", "tools", "make_golden.py"))
+    mg = iu.module_from_spec(spec); spec.loader.exec_module(mg)
+    for name in ("monod_cma", "fixed_length_0d_batch"):
+        fresh, g = mg.run_case(name, synth), _load(name)
+        for k in ("counters", "sources", "pos_0", "props_0") + tuple(f"props_{int(s)}" for s in g["snap_steps"]):
+            assert np.array_equal(np.asarray(fresh[k]), g[k]), (name, k)
+
+
+def test_reference_refuses_small_populations():
+    # kernels.hpp:130-134,163-167: N <= particles per team throws "Nparticle<n per team" 
+    ref = _ref_or_skip()
+    r = ref.RefLoop("fixed_length", 1, 1, particles_per_team=1024)
+    props = np.stack([np.full(1000, 1.5e-6, np.float32), np.full(1000, 2e-6, np.float32)])
+    r.set_particles(props); r.domain_update(np.array([0.02]), None, np.array([0.0]), None)
+    r.set_leaving_flows([]); r.set_concentrations(np.array([1.0]))
+    with pytest.raises(RuntimeError, match="Nparticle<n per team"):
+        r.cycle(0.1)
+
+
+# ----------------------------------------------------------------------------- GPU: CUDA path vs reference outputs
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_cuda_reproduces_reference_fixture(bmc, name):
+    g = _load(name)
+    loop = bmc.ParticleLoop(g["model"], g["n_species"], g["n_comp"], seed=g["seed"])
+    _feed(loop, g)
+    # simple_acetate::division evaluates exp/log/erfc (CUDA libdevice vs glibc: last-bit differences in the
+    # newborn's drawn properties); everything else is bit-exact
+    exact = g["model"] != "simple_acetate"
+    _check_against_golden(loop, g, exact_props=exact, sources="quirk_free", prop_rtol=1e-5)

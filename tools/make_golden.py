@@ -1,0 +1,78 @@
+"""Generates tests/golden/ref_*.npz: inputs and per-step outputs of the REFERENCE'S OWN hot-path sources
+(oracle/_ref/libbmc_ref.so = /root/reference compiled over oracle/kokkos_shim, see oracle/ref_driver.cpp)
+on small seeded cases.  Runs only where /root/reference exists; the fixtures are committed so that the
+oracle (CPU suite) and the CUDA path (-m gpu suite) are checked against reference outputs everywhere.
+
+    python tools/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+import ref  # noqa: E402
+import util  # noqa: E402
+from _bmc_loader import load_synth  # noqa: E402
+
+# name -> (model, n, n_comp, steps, particles_per_team, make_case kwargs)
+CASES = {
+    # stirred-tank lattice, one outlet with a high exit probability: movement, exits, >= 2 compactions, divisions
+    "fixed_length_cma": ("fixed_length", 2500, 20, 12, 1024, dict(near_division=0.5, p_exit=0.2, p_move=0.05, dt=20.0)),
+    "monod_cma": ("monod", 2500, 20, 12, 1024, dict(near_division=0.5, p_exit=0.2, p_move=0.05, dt=20.0)),
+    "simple_acetate_cma": ("simple_acetate", 2500, 20, 12, 1024, dict(near_division=0.5, p_exit=0.2, p_move=0.05, dt=20.0)),
+    # no outlet: nothing ever leaves, so the reference's contribution quirk never fires and the
+    # source terms are comparable on every step
+    "monod_closed": ("monod", 1500, 12, 8, 256, dict(near_division=0.5, outlet=False, p_move=0.1, dt=20.0)),
+    "fixed_length_closed": ("fixed_length", 1500, 12, 8, 256, dict(near_division=0.5, outlet=False, p_move=0.1, dt=20.0)),
+    "simple_acetate_closed": ("simple_acetate", 1500, 12, 8, 256, dict(near_division=0.5, outlet=False, p_move=0.1, dt=20.0)),
+    # 0D: one compartment (Tag0D contribution kernel, no move), chemostat outlet
+    "monod_0d": ("monod", 2048 + 77, 1, 10, 1024, dict(near_division=0.5, p_exit=0.05, dt=20.0)),
+    "fixed_length_0d_batch": ("fixed_length", 1300, 1, 6, 256, dict(near_division=0.5, outlet=False, dt=20.0)),
+}
+
+
+def run_case(name, synth):
+    model, n, n_comp, steps, ppt, kw = CASES[name]
+    case = util.make_case(synth, model, n, n_comp, **kw)
+    loop = ref.RefLoop(model, case["n_species"], n_comp, seed=case["seed"], particles_per_team=ppt)
+    util.load_case(loop, case)
+    out = dict(model=model, n=n, n_comp=n_comp, steps=steps, particles_per_team=ppt, dt=case["dt"], seed=case["seed"],
+               n_species=case["n_species"], weight=case["weight"], props0=case["props"], pos0=case["pos"].astype(np.uint32),
+               conc0=case["conc"], volumes=case["fm"]["volumes"], out_flows=case["fm"]["out_flows"],
+               neighbors=np.asarray(case["fm"]["neighbors"], np.uint32), cdf=case["fm"]["cdf"],
+               flows=np.array(case["flows"], np.float64).reshape(-1, 3))
+    srcs, counters, inactive_before = [], [], []
+    for s in range(steps):
+        inactive_before.append(loop.counters()["n_inactive"])
+        loop.set_concentrations(util.conc_at(case, s))
+        loop.cycle(case["dt"])
+        srcs.append(loop.get_sources())
+        c = loop.counters()
+        counters.append([c["events"][e] for e in ref.EVENTS] + [c[k] for k in util.COUNTER_KEYS])
+        if s in (0, steps // 2, steps - 1):
+            st = loop.get_particles()
+            out[f"props_{s}"] = st["props"]; out[f"pos_{s}"] = st["position"].astype(np.uint32); out[f"status_{s}"] = st["status"]
+            out[f"age_hyd_{s}"] = st["age_hyd"]; out[f"age_div_{s}"] = st["age_div"]
+    out["snap_steps"] = np.array(sorted({0, steps // 2, steps - 1}))
+    out["sources"] = np.array(srcs); out["counters"] = np.array(counters, np.uint64)
+    out["inactive_before"] = np.array(inactive_before, np.uint64)
+    return out
+
+
+def main():
+    assert ref.can_build(), "needs /root/reference (the fixtures are generated in the build container)"
+    ref.build()
+    synth = load_synth()
+    os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    for name in CASES:
+        out = run_case(name, synth)
+        path = os.path.join(ROOT, "tests", "golden", f"ref_{name}.npz")
+        np.savez_compressed(path, **out)
+        c = out["counters"][-1]
+        print(f"{name}: n_used {c[6]}, events {c[:6].tolist()}, compactions {c[-1]}, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()
