@@ -8,12 +8,19 @@
 // legs may load it.  The product (biocma-mcst_b200/) never links, imports or
 // calls anything in this directory.
 //
-// PARITY STATUS: "parity unpinned" for the per-particle numerics.  The
-// reference cannot be compiled here (Kokkos 5.1.1, rcmtool (Rust), Eigen, MPI,
-// HDF5, meson are un-vendored and absent; no network) and its own tests hold no
-// golden vectors for cycle/move/contribution/compaction.
-// What the reference's tests DO pin for this path is restated against this
-// oracle in tests/test_oracle_reference_invariants.py:
+// PARITY STATUS: PINNED against outputs of the reference itself run here.  The reference's
+// own hot-path sources (CycleFunctors, CycleFunctor, ContributionFunctor, MoveFunctor,
+// ParticlesContainer, ReactorDomain, EventContainer, models/*.hpp, prng_extension.hpp) are
+// compiled where they lie under /root/reference over oracle/kokkos_shim (a serial stand-in
+// for Kokkos, which is not installed) into oracle/_ref/libbmc_ref.so (oracle/ref_driver.cpp,
+// `make -C oracle ref`).  tests/test_reference_sources.py compares this restatement with
+// it, live and through the committed fixtures tests/golden/ref*.npz: compartment indices,
+// statuses, counters, event tallies, float properties, both ages, MC::init and every
+// distribution BIT-EXACT; source terms to 2e-5 relative (the reference sums in float).
+// What the shim cannot pin (not in the reference tree): the XorShift1024 pool's bit
+// streams, Kokkos' parallel execution order, ScatterView summation order, Kokkos::log(float).
+// In addition, what the reference's own tests pin for this path is restated in
+// tests/test_oracle_reference_invariants.py:
 //   * container counts       apps/libs/mc/tests/test_container.cpp:62-148
 //   * distribution moments   apps/libs/mc/tests/test_rng_2.cpp:61-107,190-283
 //   * CDF-row invariants     apps/libs/cma_utils/tests/test_transport.cpp:42-79

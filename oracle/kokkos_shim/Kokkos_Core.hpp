@@ -622,7 +622,7 @@ template <class Device = Serial> class Random_XorShift1024_Pool {
   using generator_type = Random_XorShift1024<Device>;
   using device_type = Device;
   Random_XorShift1024_Pool() = default;
-  explicit Random_XorShift1024_Pool(uint64_t) {}
+  Random_XorShift1024_Pool(uint64_t) {}  // implicit: `return (seed);` in mc/src/prng.cpp
   void init(uint64_t, int) {}
   generator_type get_state() const { return {}; }
   generator_type get_state(int) const { return {}; }

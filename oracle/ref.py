@@ -60,12 +60,26 @@ def lib():
         L.ref_cycle.argtypes = [vp, dbl]
         L.ref_get_sources.argtypes = [vp, vp]
         L.ref_get_counters.argtypes = [vp, vp]
+        L.ref_init_particles.argtypes = [vp, u64, ctypes.c_int, vp, ctypes.POINTER(dbl)]
+        L.ref_sample.argtypes = [ctypes.c_int, u64, u64, dbl, dbl, dbl, dbl, vp]
         _lib = L
     return _lib
 
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+SAMPLE_KINDS = {"normal": 0, "lognormal": 1, "truncated_normal": 2, "truncated_normal_f32": 3, "exponential_f32": 4,
+                "drand": 5, "frand": 6, "norminv": 7}
+
+
+def sample(kind, seed, n, p0=0.0, p1=0.0, p2=0.0, p3=0.0):
+    """n draws of a distribution of mc/prng/prng_extension.hpp (same signature as oracle.sample)"""
+    out = np.empty(n, np.float64)
+    rc = lib().ref_sample(SAMPLE_KINDS[kind], seed, n, p0, p1, p2, p3, _ptr(out))
+    assert rc == 0
+    return out
 
 
 class RefLoop:
@@ -106,6 +120,12 @@ class RefLoop:
         age_hyd = None if age_hyd is None else np.ascontiguousarray(age_hyd, np.float32)
         age_div = None if age_div is None else np.ascontiguousarray(age_div, np.float32)
         self._ck(self.L.ref_set_particles(self.h, n, _ptr(props), _ptr(position), _ptr(status), _ptr(age_hyd), _ptr(age_div)))
+
+    def init_particles(self, n, uniform_position=True, linit=None):
+        linit = None if linit is None else np.ascontiguousarray(linit, np.float32)
+        m = ctypes.c_double()
+        self._ck(self.L.ref_init_particles(self.h, int(n), int(bool(uniform_position)), _ptr(linit), ctypes.byref(m)))
+        return m.value
 
     def n_used(self):
         return self.counters()["n_used"]

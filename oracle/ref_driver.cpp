@@ -130,6 +130,7 @@ struct IRef {
   virtual void set_particles(size_t n, const float* props, const uint64_t* pos, const uint8_t* st, const float* ah, const float* ad) = 0;
   virtual void get_particles(size_t n, float* props, uint64_t* pos, uint8_t* st, float* ah, float* ad) = 0;
   virtual void get_contribs(size_t n, float* out) = 0;
+  virtual double init_particles(size_t n, bool uniform_pos, const float* linit) = 0;
   virtual void set_weight(double w) = 0;
   virtual void set_conc(const double* c) = 0;
   virtual void cycle(double dt) = 0;
@@ -172,6 +173,29 @@ template <class M> struct Ref final : IRef {
       pos[i] = container.position(i); st[i] = (uint8_t)container.status(i);
       ah[i] = container.ages(i, 0); ad[i] = container.ages(i, 1);
     }
+  }
+  // MC::init<M> + impl_init + initialize_model (mc/public/mc/mcinit.hpp:67-105, mc/src/unit.cpp:146-163,258-300).
+  // InitFunctor itself (unit.cpp:102-144) sits in an anonymous namespace of a translation unit that also pulls in
+  // the generated model loader, so its three statements are issued here over the reference's own Model::init,
+  // MC::KPRNG::uniform_u and Model::mass; step id 0xFFFFFFFF is the stream reserved for initialisation.
+  double init_particles(size_t n, bool uniform_pos, const float* linit) override {
+    container = Container(rt, n, 0);
+    functors.reset();
+    g_rng.key[0] = (uint32_t)seed; g_rng.key[1] = (uint32_t)(seed >> 32); g_rng.rank = rank; g_rng.step = 0xFFFFFFFFu;
+    MC::KPRNG kprng(seed ? seed : 1);
+    const uint64_t min_c = 0, max_c = uniform_pos ? n_comp : 1;  // select_bounds_compartment
+    Kokkos::View<float*, ComputeSpace> lin("linit", n);
+    for (size_t i = 0; i < n; ++i) lin(i) = linit ? linit[i] : 1.5e-6f;
+    double total_mass = 0.;
+    for (size_t i = 0; i < n; ++i) {
+      g_rng.start_sequence((uint32_t)i, kBaseUpdate);
+      if constexpr (ConfigurableModel<M>) M::init(kprng.random_pool, i, container.model, typename M::Config(lin));
+      else M::init(kprng.random_pool, i, container.model);
+      container.position(i) = kprng.uniform_u(min_c, max_c);
+      total_mass += M::mass(i, container.model);
+    }
+    container.weights(0) = (typename M::FloatType)weight;
+    return total_mass;
   }
   void get_contribs(size_t n, float* out) override {
     for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < M::n_c; ++j) out[j * n + i] = container.contribs(i, j);
@@ -274,6 +298,34 @@ int ref_set_particles(void* h, uint64_t n, const float* props, const uint64_t* p
 }
 int ref_get_particles(void* h, uint64_t n, float* props, uint64_t* pos, uint8_t* st, float* ah, float* ad) {
   auto* r = static_cast<IRef*>(h); REF_TRY(r, r->get_particles(n, props, pos, st, ah, ad));
+}
+int ref_init_particles(void* h, uint64_t n, int uniform_pos, const float* linit, double* total_mass) {
+  auto* r = static_cast<IRef*>(h);
+  REF_TRY(r, { const double m = r->init_particles(n, uniform_pos != 0, linit); if (total_mass) *total_mass = m; });
+}
+// distributions of mc/prng/prng_extension.hpp on the streams orc_sample uses: counter {i, i>>32, 3.., 0}, key = seed
+int ref_sample(int kind, uint64_t seed, uint64_t n, double p0, double p1, double p2, double p3, double* out) {
+  using namespace MC::Distributions;
+  g_rng.key[0] = (uint32_t)seed; g_rng.key[1] = (uint32_t)(seed >> 32); g_rng.rank = 0;
+  MC::pool_type pool;
+  for (uint64_t i = 0; i < n; ++i) {
+    g_rng.step = (uint32_t)(i >> 32);
+    g_rng.start_sequence((uint32_t)i, kBaseUpdate);
+    auto gen = pool.get_state();
+    switch (kind) {
+      case 0: out[i] = gen.normal(p0, p1); break;
+      case 1: out[i] = LogNormal<double>{p0, p1}.draw(gen); break;
+      case 2: out[i] = TruncatedNormal<double>(p0, p1, p2, p3).draw(gen); break;
+      case 3: out[i] = (double)TruncatedNormal<float>((float)p0, (float)p1, (float)p2, (float)p3).draw(gen); break;
+      case 4: out[i] = (double)Exponential<float>{(float)p0}.draw(gen); break;
+      case 5: out[i] = gen.drand(); break;
+      case 6: out[i] = (double)gen.frand(); break;
+      case 7: out[i] = norminv<double>(gen.drand(), p0, p1); break;
+      default: return -1;
+    }
+    pool.free_state(gen);
+  }
+  return 0;
 }
 int ref_get_contribs(void* h, uint64_t n, float* out) { auto* r = static_cast<IRef*>(h); REF_TRY(r, r->get_contribs(n, out)); }
 void ref_set_weight(void* h, double w) { static_cast<IRef*>(h)->set_weight(w); }

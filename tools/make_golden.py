@@ -61,6 +61,29 @@ def run_case(name, synth):
     return out
 
 
+# kind -> parameters (the sets of apps/libs/mc/tests/test_rng_2.cpp where it has one)
+DISTRIBUTIONS = {
+    "normal": (1.0, 2.0, 0.0, 0.0), "lognormal": (0.5, 0.3, 0.0, 0.0), "truncated_normal": (1.5e-6, 0.375e-6, 1e-6, 2e-6),
+    "truncated_normal_f32": (1.5e-6, 0.375e-6, 1e-6, 2e-6), "exponential_f32": (2.5, 0.0, 0.0, 0.0), "drand": (0.0,) * 4,
+    "frand": (0.0,) * 4, "norminv": (0.2, 1.5, 0.0, 0.0),
+}
+INIT = dict(n=3000, n_comp=37, seed=99)
+
+
+def run_init(model):
+    """MC::init on the reference's model headers: M::init, position = uniform_u(0, n_comp), total mass"""
+    ns = 2 if model == "simple_acetate" else 1
+    r = ref.RefLoop(model, ns, INIT["n_comp"], seed=INIT["seed"])
+    linit = (1e-6 + np.random.default_rng(5).random(INIT["n"]) * 1e-6).astype(np.float32)
+    mass = r.init_particles(INIT["n"], True, linit)
+    st = r.get_particles(INIT["n"])
+    return dict(model=model, linit=linit, mass=mass, props=st["props"], pos=st["position"].astype(np.uint32), **INIT)
+
+
+def run_distributions():
+    return {k: ref.sample(k, 1407, 4096, *p) for k, p in DISTRIBUTIONS.items()}
+
+
 def main():
     assert ref.can_build(), "needs /root/reference (the fixtures are generated in the build container)"
     ref.build()
@@ -72,6 +95,10 @@ def main():
         np.savez_compressed(path, **out)
         c = out["counters"][-1]
         print(f"{name}: n_used {c[6]}, events {c[:6].tolist()}, compactions {c[-1]}, {os.path.getsize(path) / 1024:.0f} KiB")
+    for model in ("fixed_length", "monod", "simple_acetate"):
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"refinit_{model}.npz"), **run_init(model))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "refdist.npz"), **run_distributions())
+    print("init + distributions written")
 
 
 if __name__ == "__main__":
