@@ -15,9 +15,12 @@ growth so division/removal/compaction are exercised every step).
   e2e       : same metric through the host-buffer C ABI a reference caller would
               use each step: concentrations H2D -> bmc_cycle -> sources D2H.
   roofline  : dominant kernel (fused cycle) algorithmic bytes / CUDA-event time.
-  cpu_baseline / --impl reference : the oracle's OpenMP restatement of the
-              reference path on the host cores (the Kokkos build cannot be
-              produced here), on a bounded sample.
+  cpu_baseline / --impl reference : the REFERENCE'S OWN kernels on the host cores, on a bounded
+              sample: oracle/_ref/libbmc_ref_release.so = the reference's hot-path sources
+              compiled with its release flags over oracle/kokkos_shim, leagues and ranges spread
+              over all host threads like the Kokkos OpenMP backend (kind "reference").  Where
+              that library is absent, or for models the reference does not have, the oracle's
+              OpenMP restatement (kind "port").  See DESIGN.md §2/§6.
 """
 import argparse
 import json
@@ -154,25 +157,50 @@ def setup_loop(loop, fm, flows, conc, n_comp):
     loop.set_concentrations(conc)
 
 
+def make_cpu_loop(model, n_species, n_comp, threads):
+    """(loop, kind, label): the reference's own kernels when oracle/_ref holds the timing build, else the port"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    if os.environ.get("BMC_CPU_BASELINE", "reference") == "reference":
+        try:
+            import ref
+            if model in ref.MODEL_IDS and (os.path.exists(ref.RELEASE_LIB_PATH) or ref.can_build()):
+                return (ref.RefLoop(model, n_species, n_comp, release=True, n_threads=threads), "reference",
+                        "reference kernels (oracle/_ref, release flags, Kokkos shim with OpenMP leagues)")
+        except Exception as e:  # noqa: BLE001 - fall back to the port, say why
+            print(f"[bench] reference build unavailable ({e}); timing the oracle port", file=sys.stderr)
+    import oracle
+    return oracle.OracleLoop(model, n_species, n_comp, n_threads=threads), "port", "oracle OpenMP restatement"
+
+
 def run_reference(args, wl):
     """Reference arm: the reference path's CPU implementation (oracle restatement, OpenMP,
     all host threads) on the same config; each step is a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle
     from _bmc_loader import load_synth
     synth = load_synth()
     model, n_comp, n_full, dt, near, p_exit = WORKLOADS[wl]
     threads = host_threads()
     n = min(n_full, args.cpu_sample)
     fm, flows, conc = build_case(synth, model, n_comp, dt, p_exit)
-    props, pos = synth.make_population(model, n, n_comp, seed=11, near_division=near)
-    o = oracle.OracleLoop(model, N_SPECIES[model], n_comp, n_threads=threads)
-    o.set_particles(props, pos)
-    o.set_weight(synth.initial_weight(props, 0.5, float(fm["volumes"].sum())))
-    setup_loop(o, fm, flows, conc, n_comp)
+
+    def make(n):
+        props, pos = synth.make_population(model, n, n_comp, seed=11, near_division=near)
+        o, kind, label = make_cpu_loop(model, N_SPECIES[model], n_comp, threads)
+        o.set_particles(props, pos)
+        o.set_weight(synth.initial_weight(props, 0.5, float(fm["volumes"].sum())))
+        setup_loop(o, fm, flows, conc, n_comp)
+        return o, kind, label
+    o, kind, label = make(n)
+    # bound the whole --steps/--warmup run to a few minutes: calibrate on two steps, shrink the sample if needed
+    o.cycle(dt)
+    t0 = time.perf_counter(); o.cycle(dt); t_step = time.perf_counter() - t0
+    budget = float(os.environ.get("BMC_REF_BUDGET_S", "120"))
+    if t_step * (args.steps + args.warmup) > budget:
+        n = max(65_536, int(n * budget / (t_step * (args.steps + args.warmup))))
+        o.close()
+        o, kind, label = make(n)
     for _ in range(args.warmup):
         o.cycle(dt)
     live = 0
@@ -183,12 +211,12 @@ def run_reference(args, wl):
         o.cycle(dt)
     el = time.perf_counter() - t0
     v = live / el
-    sample = f"{n} of {n_full} particles/GPU x {args.steps} steps, {threads} OpenMP threads"
+    sample = f"{n} of {n_full} particles/GPU x {args.steps} steps, {threads} OpenMP threads, {label}"
     line = {"metric": "particle-steps/sec", "value": v, "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": {"workload": f"{wl}: {n_comp}-compartment stirred-tank CMA, {model}, {n_full} particles/GPU, dt={dt}"},
-            "cpu_baseline": {"value": v, "unit": "particle-steps/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "particle-steps/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -359,12 +387,10 @@ def main():
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            sys.path.insert(0, os.path.join(ROOT, "oracle"))
-            import oracle
             threads = host_threads()
             n = min(n_per_gpu, args.cpu_sample)
             props, pos = synth.make_population(model, n, n_comp, seed=11, near_division=near)
-            o = oracle.OracleLoop(model, N_SPECIES[model], n_comp, n_threads=threads)
+            o, kind, label = make_cpu_loop(model, N_SPECIES[model], n_comp, threads)
             o.set_particles(props, pos)
             o.set_weight(1.0)
             setup_loop(o, fm, flows, conc, n_comp)
@@ -373,8 +399,8 @@ def main():
             while time.perf_counter() - t0 < 10.0 and steps_cpu < 400:
                 done += o.counters()["n_used"]; o.cycle(dt); steps_cpu += 1
             el = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": done / el, "unit": "particle-steps/s", "cores": threads, "kind": "port",
-                                    "sample": f"{n} of {n_per_gpu} particles x {steps_cpu} steps, oracle OpenMP restatement"}
+            line["cpu_baseline"] = {"value": done / el, "unit": "particle-steps/s", "cores": threads, "kind": kind,
+                                    "sample": f"{n} of {n_per_gpu} particles x {steps_cpu} steps, {label}"}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

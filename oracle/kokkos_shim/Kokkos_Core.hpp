@@ -8,8 +8,12 @@
 // run on the CPU so that oracle/bmc_oracle.cpp and the CUDA path can be checked
 // against them (oracle/ref_driver.cpp, oracle/Makefile target `ref`).
 //
-// What it is NOT: Kokkos.  Everything executes serially, in ascending index order,
-// teams of one thread; memory spaces are all host; ScatterView writes through.
+// What it is NOT: Kokkos.  Teams have one thread; memory spaces are all host; ScatterView is
+// duplicated per thread.  By default everything executes serially, in ascending
+// index order (the mode every parity test uses: deterministic).  shim::set_threads(n > 1)
+// distributes the leagues of a TeamPolicy and the indices of a RangePolicy over n OpenMP
+// threads, as the Kokkos OpenMP backend does with team_size 1 — used only to TIME the
+// reference's kernels on all host cores (bench.py --impl reference); parallel_scan stays serial.
 // Two pieces of Kokkos arithmetic are not reproduced and are re-specified exactly as
 // DESIGN.md §2/§4 states for the oracle:
 //   * Random_XorShift1024_Pool -> Philox4x32-10 streams selected by shim::rng() (the
@@ -34,6 +38,9 @@
 #include <type_traits>
 #include <utility>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define KOKKOS_INLINE_FUNCTION inline
 #define KOKKOS_FORCEINLINE_FUNCTION inline
@@ -44,6 +51,17 @@
 #define KOKKOS_ENABLE_SERIAL 1
 
 namespace Kokkos {
+namespace shim {
+int n_threads();            // defined by the driver; 1 = serial (deterministic)
+void set_threads(int n);
+inline bool in_parallel() {
+#ifdef _OPENMP
+  return omp_in_parallel();
+#else
+  return false;
+#endif
+}
+}  // namespace shim
 
 // ---------------------------------------------------------------- spaces, layouts, traits
 struct LayoutLeft {
@@ -186,7 +204,17 @@ template <class DataT, class... Props> class View {
   template <class, class...> friend class View;
 
  public:
-  View() { const size_t z[4] = {0, 0, 0, 0}; set_extents(z); if (rank == 0 || DTA::n_dyn == 0) { /* unallocated */ } }
+  View() { const size_t z[4] = {0, 0, 0, 0}; set_extents(z); }
+  // copies made inside a parallel region do not share ownership (Kokkos disables reference counting there too)
+  View(const View& o) : own_(shim::in_parallel() ? nullptr : o.own_), p_(o.p_), label_(shim::in_parallel() ? std::string() : o.label_) {
+    for (int k = 0; k < 4; ++k) e_[k] = o.e_[k];
+  }
+  View(View&&) = default;
+  View& operator=(const View& o) {
+    if (this != &o) { own_ = shim::in_parallel() ? nullptr : o.own_; p_ = o.p_; if (!shim::in_parallel()) label_ = o.label_; for (int k = 0; k < 4; ++k) e_[k] = o.e_[k]; }
+    return *this;
+  }
+  View& operator=(View&&) = default;
   // allocating constructors
   explicit View(const std::string& label, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0) : label_(label) {
     const size_t d[4] = {n0, n1, n2, 0}; set_extents(d); allocate(true);
@@ -208,7 +236,7 @@ template <class DataT, class... Props> class View {
   template <class D2, class... P2>
     requires(View<D2, P2...>::rank == rank && std::is_same_v<std::remove_const_t<typename View<D2, P2...>::value_type>, non_const_value_type> &&
              (std::is_const_v<value_type> || !std::is_const_v<typename View<D2, P2...>::value_type>))
-  View(const View<D2, P2...>& o) : own_(o.own_), p_(o.p_), label_(o.label_) {
+  View(const View<D2, P2...>& o) : own_(shim::in_parallel() ? nullptr : o.own_), p_(o.p_), label_(shim::in_parallel() ? std::string() : o.label_) {
     static_assert(rank <= 1 || View<D2, P2...>::is_left == is_left, "kokkos_shim: layout mismatch in View assignment");
     for (int k = 0; k < 4; ++k) e_[k] = o.e_[k];
   }
@@ -313,12 +341,32 @@ template <class D, class... P, class A, class B> auto subview(const View<D, P...
 template <class V, class... Args> using Subview = decltype(subview(std::declval<V>(), std::declval<Args>()...));
 
 // ---------------------------------------------------------------- atomics, math, misc
-template <class T, class U> T atomic_fetch_add(T* p, U v) { T o = *p; *p = (T)(o + (T)v); return o; }
-template <class T> T atomic_fetch_inc(T* p) { T o = *p; *p = o + 1; return o; }
-template <class T, class U> void atomic_add(T* p, U v) { *p = (T)(*p + v); }
-template <class T> T atomic_load(const T* p) { return *p; }
-template <class T, class U> T atomic_exchange(T* p, U v) { T o = *p; *p = (T)v; return o; }
-template <class T, class U> void atomic_store(T* p, U v) { *p = (T)v; }
+namespace Impl {
+template <class T, class Op> T atomic_rmw(T* p, Op op) {  // returns the old value
+  if constexpr (std::is_integral_v<T> || std::is_enum_v<T>) {
+    T o = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (!__atomic_compare_exchange_n(p, &o, op(o), true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return o;
+  } else {
+    using I = std::conditional_t<sizeof(T) == 4, uint32_t, uint64_t>;
+    static_assert(sizeof(T) == sizeof(I));
+    I* q = reinterpret_cast<I*>(p);
+    I o = __atomic_load_n(q, __ATOMIC_RELAXED);
+    for (;;) {
+      T ov; std::memcpy(&ov, &o, sizeof(T));
+      const T nv = op(ov);
+      I ni; std::memcpy(&ni, &nv, sizeof(T));
+      if (__atomic_compare_exchange_n(q, &o, ni, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) return ov;
+    }
+  }
+}
+}  // namespace Impl
+template <class T, class U> T atomic_fetch_add(T* p, U v) { return Impl::atomic_rmw(p, [v](T o) { return (T)(o + (T)v); }); }
+template <class T> T atomic_fetch_inc(T* p) { return Impl::atomic_rmw(p, [](T o) { return (T)(o + 1); }); }
+template <class T, class U> void atomic_add(T* p, U v) { Impl::atomic_rmw(p, [v](T o) { return (T)(o + v); }); }
+template <class T> T atomic_load(const T* p) { return Impl::atomic_rmw(const_cast<T*>(p), [](T o) { return o; }); }
+template <class T, class U> T atomic_exchange(T* p, U v) { return Impl::atomic_rmw(p, [v](T) { return (T)v; }); }
+template <class T, class U> void atomic_store(T* p, U v) { Impl::atomic_rmw(p, [v](T) { return (T)v; }); }
 inline void fence() {}
 inline void fence(const std::string&) {}
 template <class... A> int printf(const char* fmt, A... a) { if constexpr (sizeof...(A) == 0) return std::fputs(fmt, stderr); else return std::fprintf(stderr, fmt, a...); }
@@ -444,12 +492,36 @@ namespace Impl {
 template <class Tag, class F, class... A> void call(const F& f, A&&... a) {
   if constexpr (std::is_void_v<Tag>) f(std::forward<A>(a)...); else f(Tag{}, std::forward<A>(a)...);
 }
-template <class Policy, class Body> void for_each_team(const Policy& pol, const Body& body) {
-  std::vector<char> scratch(pol.scratch_size() + 64);
-  for (size_t l = 0; l < pol.league_size(); ++l) {
-    shim::team_begin(l);
-    HostTeamMember m(l, pol.league_size(), scratch.data(), scratch.data() + scratch.size());
-    body(m);
+template <class Policy, class Body> void for_each_team(const Policy& pol, const Body& body) {  // body(member, thread)
+  const int nt = shim::in_parallel() ? 1 : shim::n_threads();
+  const long n = (long)pol.league_size();
+#pragma omp parallel num_threads(nt) if (nt > 1)
+  {
+#ifdef _OPENMP
+    const int t = omp_get_thread_num();
+#else
+    const int t = 0;
+#endif
+    std::vector<char> scratch(pol.scratch_size() + 64);
+#pragma omp for schedule(static)
+    for (long l = 0; l < n; ++l) {
+      shim::team_begin((size_t)l);
+      HostTeamMember m((size_t)l, (size_t)n, scratch.data(), scratch.data() + scratch.size());
+      body(m, t);
+    }
+  }
+}
+template <class Body> void for_each_index(size_t b, size_t e, const Body& body) {  // body(i, thread)
+  const int nt = shim::in_parallel() ? 1 : shim::n_threads();
+#pragma omp parallel num_threads(nt) if (nt > 1)
+  {
+#ifdef _OPENMP
+    const int t = omp_get_thread_num();
+#else
+    const int t = 0;
+#endif
+#pragma omp for schedule(static)
+    for (long i = (long)b; i < (long)e; ++i) { shim::range_index((size_t)i); body((size_t)i, t); }
   }
 }
 template <class R> concept ReducerLike = requires(const R& r) { typename R::value_type; r.reference(); };
@@ -458,12 +530,12 @@ template <class R> concept ReducerLike = requires(const R& r) { typename R::valu
 // parallel_for
 template <class F, class... P> void parallel_for(const std::string& label, const TeamPolicy<P...>& pol, const F& f) {
   shim::kernel_begin(label);
-  Impl::for_each_team(pol, [&](const HostTeamMember& m) { Impl::call<typename TeamPolicy<P...>::work_tag>(f, m); });
+  Impl::for_each_team(pol, [&](const HostTeamMember& m, int) { Impl::call<typename TeamPolicy<P...>::work_tag>(f, m); });
   shim::kernel_end();
 }
 template <class F, class... P> void parallel_for(const std::string& label, const RangePolicy<P...>& pol, const F& f) {
   shim::kernel_begin(label);
-  for (size_t i = pol.begin(); i < pol.end(); ++i) { shim::range_index(i); Impl::call<typename RangePolicy<P...>::work_tag>(f, i); }
+  Impl::for_each_index(pol.begin(), pol.end(), [&](size_t i, int) { Impl::call<typename RangePolicy<P...>::work_tag>(f, i); });
   shim::kernel_end();
 }
 template <class F, class I> requires std::is_integral_v<I> void parallel_for(const std::string& label, I n, const F& f) {
@@ -475,27 +547,33 @@ template <class F, class I> requires std::is_integral_v<I> void parallel_for(I n
 
 // parallel_reduce: the result is a reducer object, a rank-0 View or a scalar reference
 namespace Impl {
-template <class Policy, class F, class V> void reduce_loop(const Policy& pol, const F& f, V& v) {
+// per-thread partial values (each starts from `init`), joined in thread order afterwards
+template <class Policy, class F, class V, class Join> void reduce_loop(const Policy& pol, const F& f, V& v, const V& init, const Join& join) {
   using Tag = typename Policy::work_tag;
+  const int nt = std::max(1, shim::n_threads());
+  std::vector<V> part((size_t)nt, init);
   if constexpr (requires { pol.league_size(); }) {
-    for_each_team(pol, [&](const HostTeamMember& m) { call<Tag>(f, m, v); });
+    for_each_team(pol, [&](const HostTeamMember& m, int t) { call<Tag>(f, m, part[(size_t)t]); });
   } else {
-    for (size_t i = pol.begin(); i < pol.end(); ++i) { shim::range_index(i); call<Tag>(f, i, v); }
+    for_each_index(pol.begin(), pol.end(), [&](size_t i, int t) { call<Tag>(f, i, part[(size_t)t]); });
   }
+  v = part[0];
+  for (int t = 1; t < nt; ++t) join(v, part[(size_t)t]);
 }
 }  // namespace Impl
 template <class Policy, class F, class R> requires Impl::ReducerLike<R>
 void parallel_reduce(const std::string& label, const Policy& pol, const F& f, const R& red) {
   shim::kernel_begin(label);
-  typename R::value_type v; red.init(v);
-  Impl::reduce_loop(pol, f, v);
+  typename R::value_type v, init; red.init(v); red.init(init);
+  Impl::reduce_loop(pol, f, v, init, [&](typename R::value_type& d, const typename R::value_type& s2) { red.join(d, s2); });
   red.reference() = v;
   shim::kernel_end();
 }
 template <class Policy, class F, class D, class... P> void parallel_reduce(const std::string& label, const Policy& pol, const F& f, const View<D, P...>& res) {
   shim::kernel_begin(label);
-  typename View<D, P...>::non_const_value_type v{};
-  Impl::reduce_loop(pol, f, v);
+  using V = typename View<D, P...>::non_const_value_type;
+  V v{};
+  Impl::reduce_loop(pol, f, v, V{}, [](V& d, const V& s2) { d += s2; });
   res() = v;
   shim::kernel_end();
 }
@@ -503,7 +581,7 @@ template <class Policy, class F, class T> requires(!Impl::ReducerLike<T> && !is_
 void parallel_reduce(const std::string& label, const Policy& pol, const F& f, T& res) {
   shim::kernel_begin(label);
   T v{};
-  Impl::reduce_loop(pol, f, v);
+  Impl::reduce_loop(pol, f, v, T{}, [](T& d, const T& s2) { d += s2; });
   res = v;
   shim::kernel_end();
 }
@@ -520,23 +598,49 @@ template <class F, class... P> void parallel_scan(const std::string& label, cons
   shim::kernel_end();
 }
 
-// ---------------------------------------------------------------- ScatterView (serial: writes through)
+// ---------------------------------------------------------------- ScatterView
+// Duplicated per thread like Kokkos' host default (ScatterDuplicated, ScatterNonAtomic): access() hands out the
+// calling thread's private copy, contribute() adds the copies into the target in thread order, reset() zeroes them.
 namespace Experimental {
 template <class V> class ScatterView {
+  using T = typename V::non_const_value_type;
   V target_;
+  std::shared_ptr<std::vector<T>> dup_;
+  size_t n_ = 0; int nt_ = 1;
+  static int max_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+  }
  public:
   ScatterView() = default;
-  explicit ScatterView(const V& v) : target_(v) {}
+  explicit ScatterView(const V& v) : target_(v), n_(v.span()), nt_(max_threads()) { dup_ = std::make_shared<std::vector<T>>(n_ * (size_t)nt_, T{}); }
+  struct Ref {
+    T* p;
+    void operator+=(T v) const { *p += v; }  // the right-hand side is converted to the value type first, like ScatterValue::operator+=(value_type const&)
+    void operator-=(T v) const { *p -= v; }
+  };
   struct Access {
     V t;
-    template <class... I> auto& operator()(I... i) const { return t(i...); }
+    template <class... I> Ref operator()(I... i) const { return Ref{&t(i...)}; }
   };
-  Access access() const { return Access{target_}; }
-  void reset() const {}  // duplicates are the target itself: the owner of the target clears it (see ref_driver.cpp)
-  const V& shim_target() const { return target_; }
+  Access access() const {
+#ifdef _OPENMP
+    const int th = omp_in_parallel() ? omp_get_thread_num() : 0;
+#else
+    const int th = 0;
+#endif
+    return Access{V(dup_->data() + (size_t)th * n_, target_.extent(0), target_.extent(1), target_.extent(2))};
+  }
+  void reset() const { if (dup_) std::fill(dup_->begin(), dup_->end(), T{}); }
+  void shim_contribute_into(const V& dst) const {
+    for (int th = 0; th < nt_; ++th) for (size_t k = 0; k < n_; ++k) dst.data()[k] += (*dup_)[(size_t)th * n_ + k];
+  }
 };
 template <class D, class... P> ScatterView<View<D, P...>> create_scatter_view(const View<D, P...>& v) { return ScatterView<View<D, P...>>(v); }
-template <class V, class S> void contribute(const V&, const S&) {}
+template <class V, class S> void contribute(const V& dst, const S& scatter) { scatter.shim_contribute_into(dst); }
 }  // namespace Experimental
 
 // ---------------------------------------------------------------- sorting API named by ParticlesContainer::_sort (never called)
@@ -591,11 +695,45 @@ struct RngState {
 RngState& rng();
 }  // namespace shim
 
+#ifdef KOKKOS_SHIM_XORSHIFT
+// Timing build only (libbmc_ref_release.so): a generator of the cost class of the reference's, so that the
+// CPU baseline is not charged for Philox.  xorshift1024* (S. Vigna, 2014, public domain), one state per
+// thread — the design of a Kokkos random pool.  Streams are NOT comparable with the checker build.
+namespace shim {
+struct XsState {
+  uint64_t s[16]; int p = 0; bool seeded = false;
+  void seed(uint64_t x) { for (auto& w : s) { x += 0x9E3779B97F4A7C15ull; uint64_t z = x; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; w = z ^ (z >> 31); } seeded = true; }
+  uint64_t next() {
+    const uint64_t s0 = s[p]; uint64_t s1 = s[p = (p + 1) & 15];
+    s1 ^= s1 << 31; s[p] = s1 ^ s0 ^ (s1 >> 11) ^ (s0 >> 30);
+    return s[p] * 1181783497276652981ull;
+  }
+};
+inline XsState& xs() {
+  thread_local XsState st;
+  if (!st.seeded) {
+#ifdef _OPENMP
+    st.seed(0x2024ull + 0x1000ull * (uint64_t)omp_get_thread_num());
+#else
+    st.seed(0x2024ull);
+#endif
+  }
+  return st;
+}
+}  // namespace shim
+#endif
+
 template <class Device = Serial> class Random_XorShift1024 {
  public:
   static constexpr uint64_t MAX_URAND64 = ~0ull;
+#ifdef KOKKOS_SHIM_XORSHIFT
+  shim::XsState* st_ = &shim::xs();
+  uint64_t urand64() { return st_->next(); }
+  uint32_t urand() { return (uint32_t)(st_->next() >> 32); }
+#else
   uint32_t urand() { return shim::rng().next32(); }
   uint64_t urand64() { const uint64_t hi = urand(); return (hi << 32) | urand(); }
+#endif
   uint64_t urand64(uint64_t range) { return urand64() % range; }
   uint64_t urand64(uint64_t lo, uint64_t hi) { return lo + urand64() % (hi - lo); }
   uint32_t urand(uint32_t range) { return urand() % range; }

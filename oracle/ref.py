@@ -13,6 +13,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libbmc_ref.so")
+RELEASE_LIB_PATH = os.path.join(_HERE, "_ref", "libbmc_ref_release.so")  # -O3 -DNDEBUG -ffast-math: timing only
 REFERENCE_ROOT = os.environ.get("BMC_REFERENCE_ROOT", "/root/reference")
 EVENTS = ("NewParticle", "Exit", "Move", "Death", "Overflow", "ChangeWeight")
 MODEL_IDS = {"fixed_length": 0, "monod": 1, "simple_acetate": 2}
@@ -36,34 +37,53 @@ def available():
     return os.path.exists(LIB_PATH) or can_build()
 
 
+def _declare(L):
+    vp, u64, dbl, u32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_double, ctypes.c_uint32
+    L.ref_create.restype = vp
+    L.ref_create.argtypes = [ctypes.c_int, u64, u64, u64, u32, u64]
+    L.ref_destroy.argtypes = [vp]; L.ref_destroy.restype = None
+    L.ref_last_error.argtypes = [vp]; L.ref_last_error.restype = ctypes.c_char_p
+    L.ref_n_var.argtypes = [vp]; L.ref_n_c.argtypes = [vp]
+    L.ref_set_runtime.argtypes = [vp, u64, dbl, dbl, dbl, dbl]; L.ref_set_runtime.restype = None
+    L.ref_set_step.argtypes = [vp, u32]; L.ref_set_step.restype = None
+    L.ref_set_particles.argtypes = [vp, u64, vp, vp, vp, vp, vp]
+    L.ref_get_particles.argtypes = [vp, u64, vp, vp, vp, vp, vp]
+    L.ref_get_contribs.argtypes = [vp, u64, vp]
+    L.ref_set_weight.argtypes = [vp, dbl]; L.ref_set_weight.restype = None
+    L.ref_domain_update.argtypes = [vp, vp, vp, vp, vp, u64]
+    L.ref_set_leaving_flows.argtypes = [vp, u64, vp, vp, vp]
+    L.ref_set_concentrations.argtypes = [vp, vp]
+    L.ref_cycle.argtypes = [vp, dbl]
+    L.ref_get_sources.argtypes = [vp, vp]
+    L.ref_get_counters.argtypes = [vp, vp]
+    L.ref_init_particles.argtypes = [vp, u64, ctypes.c_int, vp, ctypes.POINTER(dbl)]
+    L.ref_sample.argtypes = [ctypes.c_int, u64, u64, dbl, dbl, dbl, dbl, vp]
+    L.ref_set_threads.argtypes = [ctypes.c_int]; L.ref_set_threads.restype = None
+    L.ref_max_threads.restype = ctypes.c_int
+    return L
+
+
 def lib():
+    """the checker build (assertions, IEEE arithmetic, serial unless set_threads is called)"""
     global _lib
     if _lib is None:
         if can_build():
             build()
-        L = ctypes.CDLL(LIB_PATH)
-        vp, u64, dbl, u32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_double, ctypes.c_uint32
-        L.ref_create.restype = vp
-        L.ref_create.argtypes = [ctypes.c_int, u64, u64, u64, u32, u64]
-        L.ref_destroy.argtypes = [vp]; L.ref_destroy.restype = None
-        L.ref_last_error.argtypes = [vp]; L.ref_last_error.restype = ctypes.c_char_p
-        L.ref_n_var.argtypes = [vp]; L.ref_n_c.argtypes = [vp]
-        L.ref_set_runtime.argtypes = [vp, u64, dbl, dbl, dbl, dbl]; L.ref_set_runtime.restype = None
-        L.ref_set_step.argtypes = [vp, u32]; L.ref_set_step.restype = None
-        L.ref_set_particles.argtypes = [vp, u64, vp, vp, vp, vp, vp]
-        L.ref_get_particles.argtypes = [vp, u64, vp, vp, vp, vp, vp]
-        L.ref_get_contribs.argtypes = [vp, u64, vp]
-        L.ref_set_weight.argtypes = [vp, dbl]; L.ref_set_weight.restype = None
-        L.ref_domain_update.argtypes = [vp, vp, vp, vp, vp, u64]
-        L.ref_set_leaving_flows.argtypes = [vp, u64, vp, vp, vp]
-        L.ref_set_concentrations.argtypes = [vp, vp]
-        L.ref_cycle.argtypes = [vp, dbl]
-        L.ref_get_sources.argtypes = [vp, vp]
-        L.ref_get_counters.argtypes = [vp, vp]
-        L.ref_init_particles.argtypes = [vp, u64, ctypes.c_int, vp, ctypes.POINTER(dbl)]
-        L.ref_sample.argtypes = [ctypes.c_int, u64, u64, dbl, dbl, dbl, dbl, vp]
-        _lib = L
+        _lib = _declare(ctypes.CDLL(LIB_PATH))
     return _lib
+
+
+_release = None
+
+
+def release_lib():
+    """the timing build: the reference's release flags (meson.build:98-105)"""
+    global _release
+    if _release is None:
+        if can_build():
+            build()
+        _release = _declare(ctypes.CDLL(RELEASE_LIB_PATH))
+    return _release
 
 
 def _ptr(a):
@@ -88,8 +108,10 @@ class RefLoop:
     KernelDispatchOptions so that small cases run."""
 
     def __init__(self, model, n_species=1, n_compartments=1, *, seed=2024, rank=0, particles_per_team=1024,
-                 allocation_factor=1.5, buffer_ratio=0.6, dead_ratio=0.01, min_removal=0, shrink_ratio=0.0, **_):
-        self.L = lib()
+                 allocation_factor=1.5, buffer_ratio=0.6, dead_ratio=0.01, min_removal=0, shrink_ratio=0.0,
+                 release=False, n_threads=1, **_):
+        self.L = release_lib() if release else lib()
+        self.L.ref_set_threads(int(n_threads))  # process-wide in that library: leagues / ranges over OpenMP threads
         self.model = MODEL_IDS[model]
         self.h = self.L.ref_create(self.model, n_species, n_compartments, seed, rank, particles_per_team)
         assert self.h, "ref_create failed"

@@ -44,25 +44,49 @@
 #include <models/simple_acetate.hpp>
 #include <simulation/kernels/kernels.hpp>
 
+#include <chrono>
+#include <cstdlib>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
 
 // ------------------------------------------------------------------ shim hooks
+// Stream selection state: the configuration of the running kernel is shared (written by the launching thread
+// before the parallel region), the position inside a stream is per thread.
 namespace {
-Kokkos::shim::RngState g_rng;
-size_t g_team_move = 1024;
+struct RngConfig { uint32_t key[2] = {0, 0}; uint32_t rank = 0, step = 0; Kokkos::shim::Mode mode = Kokkos::shim::Mode::Sequential; size_t per_team = 1024; };
+RngConfig g_cfg;
+thread_local Kokkos::shim::RngState t_rng;
+int g_threads = 1;
+// BMC_REF_PROFILE=1: seconds per kernel label, printed by ref_destroy (tuning aid)
+const bool g_profile = std::getenv("BMC_REF_PROFILE") != nullptr;
+std::map<std::string, double> g_times; std::string g_label; std::chrono::steady_clock::time_point g_t0;
+inline Kokkos::shim::RngState& synced() {
+  Kokkos::shim::RngState& r = t_rng;
+  r.key[0] = g_cfg.key[0]; r.key[1] = g_cfg.key[1]; r.rank = g_cfg.rank; r.step = g_cfg.step; r.mode = g_cfg.mode; r.per_team = g_cfg.per_team;
+  return r;
+}
+inline void set_streams(uint64_t seed, uint32_t rank, uint32_t step) {
+  g_cfg.key[0] = (uint32_t)seed; g_cfg.key[1] = (uint32_t)(seed >> 32); g_cfg.rank = rank; g_cfg.step = step;
+}
 }  // namespace
 namespace Kokkos::shim {
-RngState& rng() { return g_rng; }
+RngState& rng() { return t_rng; }
+int n_threads() { return g_threads; }
+void set_threads(int n) { g_threads = n < 1 ? 1 : n; }
 void kernel_begin(const std::string& label) {
-  if (label == "cycle_move") { g_rng.mode = Mode::MoveTape; g_rng.per_team = g_team_move; g_rng.tape = 0; }
-  else if (label == "cycle_move_leave") { g_rng.mode = Mode::Leave; }
-  else { g_rng.mode = Mode::Sequential; }
+  if (g_profile) { g_label = label; g_t0 = std::chrono::steady_clock::now(); }
+  if (label == "cycle_move") g_cfg.mode = Mode::MoveTape;
+  else if (label == "cycle_move_leave") g_cfg.mode = Mode::Leave;
+  else g_cfg.mode = Mode::Sequential;
 }
-void kernel_end() { g_rng.mode = Mode::Sequential; }
-void team_begin(size_t league_rank) { g_rng.league = league_rank; g_rng.tape = 0; }
-void range_index(size_t i) { g_rng.index = i; }
+void kernel_end() {
+  g_cfg.mode = Mode::Sequential;
+  if (g_profile) g_times[g_label] += std::chrono::duration<double>(std::chrono::steady_clock::now() - g_t0).count();
+}
+void team_begin(size_t league_rank) { RngState& r = synced(); r.league = league_rank; r.tape = 0; }
+void range_index(size_t i) { RngState& r = synced(); r.index = i; }
 }  // namespace Kokkos::shim
 
 // ------------------------------------------------------------------ model wrappers
@@ -75,12 +99,12 @@ template <class M> struct Tap : M {
   KOKKOS_INLINE_FUNCTION static MC::Status update(const MC::pool_type& pool, typename M::FloatType d_t, std::size_t idx,
                                                   const typename M::SelfParticle& arr, const typename M::SelfContribs& contribs,
                                                   std::size_t position, const MC::LocalConcentration& c) {
-    g_rng.start_sequence((uint32_t)idx, kBaseUpdate);
+    synced().start_sequence((uint32_t)idx, kBaseUpdate);
     return M::update(pool, d_t, idx, arr, contribs, position, c);
   }
   KOKKOS_INLINE_FUNCTION static void division(const MC::pool_type& pool, std::size_t idx, std::size_t idx2,
                                               const typename M::SelfParticle& arr, const typename M::SelfParticle& buf) {
-    g_rng.start_sequence((uint32_t)idx, kBaseDivision);
+    synced().start_sequence((uint32_t)idx, kBaseDivision);
     M::division(pool, idx, idx2, arr, buf);
   }
 };
@@ -181,14 +205,14 @@ template <class M> struct Ref final : IRef {
   double init_particles(size_t n, bool uniform_pos, const float* linit) override {
     container = Container(rt, n, 0);
     functors.reset();
-    g_rng.key[0] = (uint32_t)seed; g_rng.key[1] = (uint32_t)(seed >> 32); g_rng.rank = rank; g_rng.step = 0xFFFFFFFFu;
+    set_streams(seed, rank, 0xFFFFFFFFu);
     MC::KPRNG kprng(seed ? seed : 1);
     const uint64_t min_c = 0, max_c = uniform_pos ? n_comp : 1;  // select_bounds_compartment
     Kokkos::View<float*, ComputeSpace> lin("linit", n);
     for (size_t i = 0; i < n; ++i) lin(i) = linit ? linit[i] : 1.5e-6f;
     double total_mass = 0.;
     for (size_t i = 0; i < n; ++i) {
-      g_rng.start_sequence((uint32_t)i, kBaseUpdate);
+      synced().start_sequence((uint32_t)i, kBaseUpdate);
       if constexpr (ConfigurableModel<M>) M::init(kprng.random_pool, i, container.model, typename M::Config(lin));
       else M::init(kprng.random_pool, i, container.model);
       container.position(i) = kprng.uniform_u(min_c, max_c);
@@ -227,19 +251,19 @@ template <class M> struct Ref final : IRef {
       scatter = Kokkos::Experimental::create_scatter_view(contribs);  // simulation.cpp:76-77
       functors.reset();
     }
-    g_rng.key[0] = (uint32_t)seed; g_rng.key[1] = (uint32_t)(seed >> 32); g_rng.rank = rank; g_rng.step = step;
-    g_team_move = opts.m_p_p_team_move;
+    set_streams(seed, rank, step);
+    g_cfg.per_team = opts.m_p_p_team_move;
     if (!functors)  // init_functors (simulation.hpp:165-181)
       functors = std::make_unique<Functors>(opts, container, pool, MC::KernelConcentrationType(conc), scatter, events,
                                             domain.get_const_inner(), probe_leave, probe_div);
     functors->update(d_t, container, domain.get_const_inner());  // pre_cycle (simulation.hpp:154-162)
     // the concentrations view is captured by value in the cycle functor: same allocation, refreshed in place above
     scatter.reset();                                             // :201
-    Kokkos::deep_copy(contribs, 0.f);  // shim ScatterView writes through; the reference's target is empty here (simulation.cpp:147-150)
     functors->launch_model(n_particle);                          // :202
     if (functors->move_kernel.need_launch()) functors->launch_move(n_particle);  // :205-208
     // post_cycle
     Kokkos::fence();
+    Kokkos::deep_copy(contribs, 0.f);  // "scatter_contribute is called ... when contribs is empty" (simulation.cpp:147-150)
     Kokkos::Experimental::contribute(contribs, scatter);         // scatter_contribute, simulation.cpp:143-151
     const auto [host_red, host_out_counter] = functors->get_host_reduction();
     const size_t before = container.n_particles(), inactive_before = container.get_inactive();
@@ -285,12 +309,24 @@ void* ref_create(int model, uint64_t n_species, uint64_t n_comp, uint64_t seed, 
   for (size_t i = 0; i < n_comp; ++i) r->neigh[i] = i;
   return r;
 }
-void ref_destroy(void* h) { delete static_cast<IRef*>(h); }
+void ref_destroy(void* h) {
+  if (g_profile) { for (auto& [k, v] : g_times) std::fprintf(stderr, "[ref] %-28s %.3f s\n", k.c_str(), v); g_times.clear(); }
+  delete static_cast<IRef*>(h);
+}
 const char* ref_last_error(void* h) { return static_cast<IRef*>(h)->err.c_str(); }
 int ref_n_var(void* h) { return static_cast<IRef*>(h)->n_var(); }
 int ref_n_c(void* h) { return static_cast<IRef*>(h)->n_c(); }
 void ref_set_runtime(void* h, uint64_t min_removal, double buffer_ratio, double allocation_factor, double shrink_ratio, double dead_ratio) {
   static_cast<IRef*>(h)->rt = MC::RuntimeParameters{min_removal, buffer_ratio, allocation_factor, shrink_ratio, dead_ratio};
+}
+// number of OpenMP threads the shim runs leagues / ranges on (1 = serial and deterministic, the default)
+void ref_set_threads(int n) { Kokkos::shim::set_threads(n); }
+int ref_max_threads() {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
 }
 void ref_set_step(void* h, uint32_t s) { static_cast<IRef*>(h)->step = s; }
 int ref_set_particles(void* h, uint64_t n, const float* props, const uint64_t* pos, const uint8_t* st, const float* ah, const float* ad) {
@@ -306,11 +342,10 @@ int ref_init_particles(void* h, uint64_t n, int uniform_pos, const float* linit,
 // distributions of mc/prng/prng_extension.hpp on the streams orc_sample uses: counter {i, i>>32, 3.., 0}, key = seed
 int ref_sample(int kind, uint64_t seed, uint64_t n, double p0, double p1, double p2, double p3, double* out) {
   using namespace MC::Distributions;
-  g_rng.key[0] = (uint32_t)seed; g_rng.key[1] = (uint32_t)(seed >> 32); g_rng.rank = 0;
   MC::pool_type pool;
   for (uint64_t i = 0; i < n; ++i) {
-    g_rng.step = (uint32_t)(i >> 32);
-    g_rng.start_sequence((uint32_t)i, kBaseUpdate);
+    set_streams(seed, 0, (uint32_t)(i >> 32));
+    synced().start_sequence((uint32_t)i, kBaseUpdate);
     auto gen = pool.get_state();
     switch (kind) {
       case 0: out[i] = gen.normal(p0, p1); break;
