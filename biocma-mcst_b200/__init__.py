@@ -31,7 +31,7 @@ ABI_SYMBOLS = (
     "bmc_sources_device", "bmc_concentrations_device", "bmc_stream", "bmc_launch_count", "bmc_profile_enable",
     "bmc_profile_read", "bmc_nccl_unique_id", "bmc_comm_init", "bmc_allreduce_sources",
     "bmc_liquid_set_transition", "bmc_liquid_set_feeds", "bmc_liquid_step", "bmc_get_concentrations",
-    "bmc_udf_check", "bmc_get_properties", "bmc_cma_build",
+    "bmc_udf_check", "bmc_get_properties", "bmc_cma_build", "bmc_checkpoint_size", "bmc_checkpoint_save", "bmc_checkpoint_load",
 )
 
 
@@ -107,6 +107,9 @@ def load_library(path=None):
     lib.bmc_repartition.argtypes = [vp, vp]
     lib.bmc_compact.argtypes = [vp]
     lib.bmc_reserve.argtypes = [vp, u64]
+    lib.bmc_checkpoint_size.argtypes = [vp, ctypes.POINTER(u64)]
+    lib.bmc_checkpoint_save.argtypes = [vp, vp, u64]
+    lib.bmc_checkpoint_load.argtypes = [vp, vp, u64]
     lib.bmc_sources_device.argtypes = [vp, P(vp), P(u64)]
     lib.bmc_concentrations_device.argtypes = [vp, P(vp), P(u64)]
     lib.bmc_stream.argtypes = [vp, P(vp)]
@@ -316,6 +319,19 @@ class ParticleLoop:
         out = np.empty(self.n_compartments, np.uint64)
         self._ck(self.lib.bmc_repartition(self.h, _ptr(out)))
         return out
+
+    def checkpoint(self):
+        """SerDe::save_simulation: the Monte-Carlo unit + concentrations + step counter as bytes"""
+        n = ctypes.c_uint64()
+        self._ck(self.lib.bmc_checkpoint_size(self.h, ctypes.byref(n)))
+        buf = np.empty(n.value, np.uint8)
+        self._ck(self.lib.bmc_checkpoint_save(self.h, _ptr(buf), ctypes.c_uint64(buf.size)))
+        return buf.tobytes()
+
+    def restore(self, blob):
+        """SerDe::load_simulation into a context of the same model and dimensions"""
+        buf = np.frombuffer(blob, np.uint8)
+        self._ck(self.lib.bmc_checkpoint_load(self.h, _ptr(buf), ctypes.c_uint64(buf.size)))
 
     def compact(self):
         self._ck(self.lib.bmc_compact(self.h))

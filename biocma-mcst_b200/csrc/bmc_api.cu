@@ -926,6 +926,136 @@ int bmc_get_properties(bmc_ctx* ctx, const uint64_t* indices, uint64_t n_indices
   return BMC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Checkpoint / resume of the Monte-Carlo unit.  Reference: SerDe::save_simulation /
+// load_simulation (apps/core/src/serde.cpp:64-219) archive {version, number_particle, dimensions, liquid
+// concentrations, time, MonteCarloUnit{init_weight, events, domain ids, container{n_allocated, n_used,
+// rt_params, weights, position, status, model, ages}}} with cereal.  cereal is not available and its byte
+// layout is not part of the reference tree, so the same content is written in a self-described
+// little-endian layout (include/bmc.h).  The domain (flow map) is NOT part of it, as in the reference: the
+// caller re-applies bmc_domain_update / bmc_set_leaving_flows from its case before resuming.
+// Counter-based RNG: restoring `step` resumes every random stream exactly, so a resumed run is bit-identical
+// to an uninterrupted one.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct CkptHeader {
+  char magic[8];            // "BMCCKPT1"
+  uint32_t header_bytes, model, n_var, lazy_ages;
+  uint64_t n_species, n_comp, seed, rank, step, n_used, capacity_hint;
+  uint64_t inactive, total_out, total_new, n_compactions, last_out, last_dead, last_waiting;
+  uint64_t events[6];
+  double weight, allocation_factor, buffer_ratio, dead_ratio, epoch_dt;
+  uint64_t min_removal;
+  uint32_t epoch_set, epoch_leave;
+  uint64_t tab_entries;     // lazy ages: entries of each age table that follow
+};
+}  // namespace
+
+static uint64_t ckpt_bytes(const bmc_ctx* ctx, uint64_t n, uint64_t tab_entries) {
+  const uint64_t nb = ctx->n_species * ctx->n_comp;
+  return sizeof(CkptHeader) + 2 * nb * 8 + (uint64_t)ctx->vt.n_var * n * 4 + n * 4 + n + 2 * n * 4 + 2 * tab_entries * 4;
+}
+
+int bmc_checkpoint_size(bmc_ctx* ctx, uint64_t* bytes) {
+  if (!ctx || !bytes) return BMC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  DevState hs; int rc;
+  if ((rc = sync_state(ctx, &hs))) return rc;
+  *bytes = ckpt_bytes(ctx, hs.n_used, ctx->lazy_ages ? ctx->host_step + 2 : 0);
+  return BMC_OK;
+}
+
+int bmc_checkpoint_save(bmc_ctx* ctx, void* buffer, uint64_t bytes) {
+  if (!ctx || !buffer) return BMC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  DevState hs; int rc;
+  if ((rc = sync_state(ctx, &hs))) return rc;
+  const uint64_t n = hs.n_used, tab = ctx->lazy_ages ? ctx->host_step + 2 : 0;
+  if (bytes < ckpt_bytes(ctx, n, tab)) { ctx->err = "bmc_checkpoint_save: buffer too small (see bmc_checkpoint_size)"; return BMC_ERR_RANGE; }
+  CkptHeader h;
+  memset(&h, 0, sizeof(h));
+  memcpy(h.magic, "BMCCKPT1", 8);
+  h.header_bytes = (uint32_t)sizeof(h); h.model = (uint32_t)ctx->model; h.n_var = (uint32_t)ctx->vt.n_var; h.lazy_ages = ctx->lazy_ages ? 1u : 0u;
+  h.n_species = ctx->n_species; h.n_comp = ctx->n_comp; h.seed = ctx->seed; h.rank = ctx->rank; h.step = ctx->host_step; h.n_used = n;
+  h.capacity_hint = ctx->cap;
+  h.inactive = hs.inactive; h.total_out = hs.total_out; h.total_new = hs.total_new; h.n_compactions = hs.n_compactions;
+  h.last_out = hs.last_out; h.last_dead = hs.last_dead; h.last_waiting = hs.last_waiting;
+  for (int i = 0; i < 6; ++i) h.events[i] = hs.events[i];
+  h.weight = (double)ctx->weight; h.allocation_factor = ctx->allocation_factor; h.buffer_ratio = ctx->buffer_ratio; h.dead_ratio = ctx->dead_ratio;
+  h.epoch_dt = ctx->epoch_dt; h.min_removal = ctx->min_removal; h.epoch_set = ctx->epoch_set ? 1u : 0u; h.epoch_leave = ctx->epoch_leave ? 1u : 0u;
+  h.tab_entries = tab;
+  unsigned char* o = (unsigned char*)buffer;
+  memcpy(o, &h, sizeof(h)); o += sizeof(h);
+  cudaStream_t s = ctx->stream;
+  const uint64_t nb = ctx->n_species * ctx->n_comp;
+  CK(cudaMemcpyAsync(o, ctx->d_conc, nb * 8, cudaMemcpyDeviceToHost, s)); o += nb * 8;
+  CK(cudaMemcpyAsync(o, ctx->d_sources, nb * 8, cudaMemcpyDeviceToHost, s)); o += nb * 8;
+  for (int k = 0; k < ctx->vt.n_var; ++k) { CK(cudaMemcpyAsync(o, ctx->props + (size_t)k * ctx->cap, n * 4, cudaMemcpyDeviceToHost, s)); o += n * 4; }
+  CK(cudaMemcpyAsync(o, ctx->pos, n * 4, cudaMemcpyDeviceToHost, s)); o += n * 4;
+  CK(cudaMemcpyAsync(o, ctx->status, n, cudaMemcpyDeviceToHost, s)); o += n;
+  CK(cudaMemcpyAsync(o, ctx->age_hyd, n * 4, cudaMemcpyDeviceToHost, s)); o += n * 4;  // raw columns: step stamps or floats
+  CK(cudaMemcpyAsync(o, ctx->age_div, n * 4, cudaMemcpyDeviceToHost, s)); o += n * 4;
+  if (tab) {
+    CK(cudaMemcpyAsync(o, ctx->d_tab_hyd, tab * 4, cudaMemcpyDeviceToHost, s)); o += tab * 4;
+    CK(cudaMemcpyAsync(o, ctx->d_tab_div, tab * 4, cudaMemcpyDeviceToHost, s)); o += tab * 4;
+  }
+  CK(cudaStreamSynchronize(s));
+  return BMC_OK;
+}
+
+int bmc_checkpoint_load(bmc_ctx* ctx, const void* buffer, uint64_t bytes) {
+  if (!ctx || !buffer || bytes < sizeof(CkptHeader)) return BMC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CkptHeader h;
+  memcpy(&h, buffer, sizeof(h));
+  if (memcmp(h.magic, "BMCCKPT1", 8) != 0 || h.header_bytes != sizeof(h)) { ctx->err = "bmc_checkpoint_load: not a checkpoint of this version"; return BMC_ERR_INVALID; }
+  if (h.model != (uint32_t)ctx->model || h.n_var != (uint32_t)ctx->vt.n_var || h.n_species != ctx->n_species || h.n_comp != ctx->n_comp) {
+    ctx->err = "bmc_checkpoint_load: model / dimensions differ from this context (serde.cpp: \"model number of property mismatch\")";
+    return BMC_ERR_INVALID;
+  }
+  const uint64_t n = h.n_used, tab = h.tab_entries;
+  if (h.lazy_ages ? (tab != h.step + 2) : (tab != 0)) { ctx->err = "bmc_checkpoint_load: inconsistent age tables"; return BMC_ERR_INVALID; }
+  if (bytes < ckpt_bytes(ctx, n, tab)) { ctx->err = "bmc_checkpoint_load: truncated buffer"; return BMC_ERR_RANGE; }
+  CK(cudaStreamSynchronize(ctx->stream));
+  int rc;
+  ctx->seed = h.seed; ctx->rank = (uint32_t)h.rank; ctx->weight = (float)h.weight;
+  ctx->allocation_factor = h.allocation_factor; ctx->buffer_ratio = h.buffer_ratio; ctx->dead_ratio = h.dead_ratio; ctx->min_removal = h.min_removal;
+  const size_t want = std::max<size_t>((size_t)std::ceil((double)n * ctx->allocation_factor), std::max<size_t>((size_t)n, 1));
+  if (want > ctx->cap || ctx->cap == 0) { if ((rc = resize_container(ctx, want, 0))) return rc; }
+  cudaStream_t s = ctx->stream;
+  const unsigned char* in = (const unsigned char*)buffer + sizeof(h);
+  const uint64_t nb = ctx->n_species * ctx->n_comp;
+  CK(cudaMemcpyAsync(ctx->d_conc, in, nb * 8, cudaMemcpyHostToDevice, s)); in += nb * 8;
+  CK(cudaMemcpyAsync(ctx->d_sources, in, nb * 8, cudaMemcpyHostToDevice, s)); in += nb * 8;
+  ctx->mass_dirty = true;
+  for (int k = 0; k < ctx->vt.n_var; ++k) { CK(cudaMemcpyAsync(ctx->props + (size_t)k * ctx->cap, in, n * 4, cudaMemcpyHostToDevice, s)); in += n * 4; }
+  CK(cudaMemcpyAsync(ctx->pos, in, n * 4, cudaMemcpyHostToDevice, s)); in += n * 4;
+  CK(cudaMemcpyAsync(ctx->status, in, n, cudaMemcpyHostToDevice, s)); in += n;
+  if (ctx->cap > n) CK(cudaMemsetAsync(ctx->status + n, 0, ctx->cap - n, s));  // slots beyond n_used are Idle
+  CK(cudaMemcpyAsync(ctx->age_hyd, in, n * 4, cudaMemcpyHostToDevice, s)); in += n * 4;
+  CK(cudaMemcpyAsync(ctx->age_div, in, n * 4, cudaMemcpyHostToDevice, s)); in += n * 4;
+  ctx->lazy_ages = h.lazy_ages != 0; ctx->epoch_set = h.epoch_set != 0; ctx->epoch_dt = h.epoch_dt; ctx->epoch_leave = h.epoch_leave != 0;
+  if (ctx->lazy_ages) {
+    if ((rc = ensure_age_tables(ctx, tab))) return rc;
+    CK(cudaMemcpyAsync(ctx->d_tab_hyd, in, tab * 4, cudaMemcpyHostToDevice, s)); in += tab * 4;
+    CK(cudaMemcpyAsync(ctx->d_tab_div, in, tab * 4, cudaMemcpyHostToDevice, s)); in += tab * 4;
+    if (force_eager_ages()) { ctx->host_step = h.step; if ((rc = make_ages_eager(ctx))) return rc; }
+  }
+  DevState ds;
+  memset(&ds, 0, sizeof(ds));
+  ds.n_used = n; ds.inactive = h.inactive; ds.total_out = h.total_out; ds.total_new = h.total_new; ds.n_compactions = h.n_compactions;
+  ds.last_out = h.last_out; ds.last_dead = h.last_dead; ds.last_waiting = h.last_waiting; ds.step = h.step;
+  for (int i = 0; i < 6; ++i) ds.events[i] = h.events[i];
+  CK(cudaMemcpyAsync(ctx->st, &ds, sizeof(ds), cudaMemcpyHostToDevice, s));
+  prepare_kernel<<<1, 32, 0, s>>>(ctx->st, (unsigned long long)ctx->cap, (unsigned long long)ctx->buf_cap);
+  if ((rc = check_launch(ctx, "prepare"))) return rc;
+  DevState hs;
+  if ((rc = sync_state(ctx, &hs))) return rc;  // also waits for the copies out of the caller's buffer
+  ctx->maybe_inactive = h.inactive != 0 || !ctx->flows.empty();
+  ctx->host_step = h.step; ctx->known_max_add = 0;
+  return BMC_OK;
+}
+
 int bmc_compact(bmc_ctx* ctx) {
   if (!ctx || ctx->cap == 0) return BMC_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
