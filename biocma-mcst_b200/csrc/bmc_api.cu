@@ -316,12 +316,15 @@ static int ensure_age_tables(bmc_ctx* ctx, size_t need) {
   float *nd = nullptr, *nh = nullptr;
   int rc;
   if ((rc = dev_alloc(ctx, &nd, new_cap)) || (rc = dev_alloc(ctx, &nh, new_cap))) return rc;
-  CK(cudaStreamSynchronize(ctx->stream));
-  CK(cudaMemset(nd, 0, new_cap * 4)); CK(cudaMemset(nh, 0, new_cap * 4));
+  // everything on the context's stream: it is a non-blocking stream, so work issued on the legacy default stream
+  // (cudaMemset is asynchronous for device memory) would not be ordered with what the caller enqueues next
+  cudaStream_t s = ctx->stream;
+  CK(cudaMemsetAsync(nd, 0, new_cap * 4, s)); CK(cudaMemsetAsync(nh, 0, new_cap * 4, s));
   if (ctx->tab_cap) {
-    CK(cudaMemcpy(nd, ctx->d_tab_div, ctx->tab_cap * 4, cudaMemcpyDeviceToDevice));
-    CK(cudaMemcpy(nh, ctx->d_tab_hyd, ctx->tab_cap * 4, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpyAsync(nd, ctx->d_tab_div, ctx->tab_cap * 4, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(nh, ctx->d_tab_hyd, ctx->tab_cap * 4, cudaMemcpyDeviceToDevice, s));
   }
+  CK(cudaStreamSynchronize(s));  // the old tables are freed next
   dev_free(ctx->d_tab_div); dev_free(ctx->d_tab_hyd);
   ctx->d_tab_div = nd; ctx->d_tab_hyd = nh; ctx->tab_cap = new_cap;
   return BMC_OK;
@@ -416,6 +419,9 @@ int bmc_create(bmc_ctx** out, const bmc_config* cfg) {
   cudaMemset(ctx->blk_total, 0, (kMaxGrid + 1) * 4);
   if ((rc = configure_launch(ctx))) return fail(rc);
   if (cfg->capacity) { if ((rc = resize_container(ctx, cfg->capacity, 0))) return fail(rc); }
+  // the clears above went to the legacy default stream and are asynchronous for device memory; the context's stream
+  // is non-blocking, so they must have completed before the caller's first enqueue (e.g. bmc_set_concentrations)
+  if (!ck(cudaDeviceSynchronize(), "cudaDeviceSynchronize")) return fail(BMC_ERR_CUDA);
   *out = ctx;
   return BMC_OK;
 }

@@ -388,9 +388,12 @@ static __device__ __forceinline__ void post_cycle_body(const PostParams& p) {
   const unsigned long long gtid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned long long gstride = (unsigned long long)gridDim.x * blockDim.x;
   // ---- publish the source terms of this step; the accumulator is left zeroed for the next one
-  for (unsigned long long k = gtid; k < p.n_bins; k += gstride) {
-    p.sources[k] = __ldcg(p.acc + k);
-    p.acc[k] = 0.0;
+  // (not from force_remove_dead: the sources of the last cycle stay what they are)
+  if (p.count_step) {
+    for (unsigned long long k = gtid; k < p.n_bins; k += gstride) {
+      p.sources[k] = __ldcg(p.acc + k);
+      p.acc[k] = 0.0;
+    }
   }
   BMC_STAMP(st, 5);
   // ---- plan (read-only on the counters: every block derives the same values; one warp per block

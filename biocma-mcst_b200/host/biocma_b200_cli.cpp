@@ -2,7 +2,8 @@
 // takes a value, parsed pairwise (:40-70).
 //   -np particles  -d final time [s]  -dt step [s] (<= 0: auto for multi-compartment cases)
 //   -mn model (fixed_length | monod | simple_acetate)  -f case directory | ring:<n> | 0d
-//   -er result stem  -nex number of exports  -nt/-force/-r/-fi/-serde accepted (ignored here)
+//   -er result stem  -nex number of exports  -serde checkpoint to resume the MC unit from (cli_parser.cpp:147-151)
+//   -nt/-force/-r/-fi accepted (ignored here).  `<stem>_serde_0.raw` is written at the end (serde.cpp:64-70).
 // Flow maps: raw flat arrays written by biocma_mcst_b200.synth.write_case (the reference's on-disk
 // format is owned by the un-vendored rcmtool crate), or the built-in ring / 0D cases.
 #include <cstring>
@@ -18,6 +19,7 @@ struct UserControlParameters {
   double delta_time = 0., final_time = 0.;
   double feed_flow = 0., feed_concentration = 0.;
   uint64_t seed = 2024;
+  bool load_serde = false; std::string serde_file;
 };
 int model_id(const std::string& n) {
   if (n == "fixed_length") return BMC_MODEL_FIXED_LENGTH;
@@ -46,7 +48,8 @@ int main(int argc, char** argv) {
       else if (k == "feed") uc.feed_flow = std::stod(v);      // extension: constant chemostat feed [m3/s]
       else if (k == "feedc") uc.feed_concentration = std::stod(v);
       else if (k == "seed") uc.seed = std::stoull(v);
-      else if (k == "nt" || k == "force" || k == "r" || k == "fi" || k == "serde") {}
+      else if (k == "serde") { uc.load_serde = true; uc.serde_file = v; }
+      else if (k == "nt" || k == "force" || k == "r" || k == "fi") {}
       else throw std::invalid_argument("bad argument -" + k);
     }
     // sanitise_check_cli (cli_parser.cpp:267-289)
@@ -69,6 +72,7 @@ int main(int argc, char** argv) {
     const double m_tot = unit->init(params.number_particle, params.uniform_mc_init, params.biomass_initial_concentration, fm.total_volume());
     std::vector<double> c0(n_species * fm.n, 1.0);  // uniform 1.0 without an initialiser file (global_initaliser.cpp:42-49)
     Simulation::SimulationUnit simulation(std::move(unit), fm, n_species, c0);
+    if (uc.load_serde) simulation.load_serde(uc.serde_file);  // particles, tallies, step counter and concentrations of the saved run
     if (uc.feed_flow > 0) simulation.add_feed(Simulation::Feed::FeedFactory::constant(uc.feed_flow, uc.feed_concentration, 0, 0));
 
     const Core::Records rec = Core::main_loop(params, simulation);
@@ -82,6 +86,7 @@ int main(int argc, char** argv) {
     write_raw(stem + "_concentration_liquid.raw", rec.concentration_liquid.data(), rec.concentration_liquid.size() * 8);
     write_raw(stem + "_number_particle.raw", rec.number_particle.data(), rec.number_particle.size() * 8);
     write_raw(stem + "_tallies.raw", rec.tallies.data(), rec.tallies.size() * 8);
+    simulation.save_serde(stem + "_serde_0.raw");
     std::printf("{\"n_compartments\": %zu, \"n_species\": %zu, \"d_t\": %.17g, \"n_records\": %zu, \"initial_mass\": %.17g, "
                 "\"n_particles\": %llu, \"new\": %llu, \"out\": %llu, \"compactions\": %llu, \"steps\": %llu, \"balance_ok\": %s}\n",
                 fm.n, n_species, uc.delta_time, rec.time.size(), m_tot, (unsigned long long)total, (unsigned long long)c.total_new,

@@ -224,6 +224,25 @@ class MonteCarloUnit {
     return r;
   }
   bmc_counters counters() const { bmc_counters c{}; check(bmc_get_counters(ctx, &c)); return c; }
+  // SerDe::save_simulation / load_simulation (apps/core/src/serde.cpp:64-219): `<results>_serde_<rank>.raw`
+  void save(const std::string& path) const {
+    uint64_t bytes = 0;
+    check(bmc_checkpoint_size(ctx, &bytes));
+    std::vector<char> buf(bytes);
+    check(bmc_checkpoint_save(ctx, buf.data(), bytes));
+    std::ofstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("Error opening file: " + path);
+    f.write(buf.data(), static_cast<std::streamsize>(bytes));
+  }
+  void load(const std::string& path) {
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f) throw std::runtime_error("cannot read file");  // serde.cpp:52
+    std::vector<char> buf(static_cast<std::size_t>(f.tellg()));
+    f.seekg(0);
+    f.read(buf.data(), static_cast<std::streamsize>(buf.size()));
+    check(bmc_checkpoint_load(ctx, buf.data(), buf.size()));
+    bmc_counters c{}; check(bmc_get_counters(ctx, &c));
+  }
   bmc_ctx* handle() const { return ctx; }
   double init_weight = 0;
 
@@ -276,6 +295,20 @@ class SimulationUnit {
     mc_unit->check(bmc_set_concentrations(h, liquid_scalar.getConcentrationData().data()));
     mc_unit->check(bmc_cycle(h, d_t));
     mc_unit->check(bmc_get_sources(h, liquid_scalar.getContributionData().data()));  // scatter_contribute + synchro_sources
+  }
+  // SerDe::load_simulation (serde.cpp:139-219): MC unit + liquid concentrations of the saved run
+  void load_serde(const std::string& path) {
+    mc_unit->load(path);
+    std::vector<double> c(dims.n_species * dims.n_compartment);
+    mc_unit->check(bmc_get_concentrations(mc_unit->handle(), c.data()));
+    liquid_scalar.set_concentration(c);  // total mass = C * V is rebuilt from the archived concentrations, as the reference does
+    // the source terms of the last cycle are still to be applied by the next ODE step (main_loop order): restored too
+    // (the reference's archive drops them, so its resumed liquid lags the uninterrupted one by one step of uptake)
+    mc_unit->check(bmc_get_sources(mc_unit->handle(), liquid_scalar.getContributionData().data()));
+  }
+  void save_serde(const std::string& path) {
+    mc_unit->check(bmc_set_concentrations(mc_unit->handle(), liquid_scalar.getConcentrationData().data()));
+    mc_unit->save(path);
   }
   Dimensions getDimensions() const { return dims; }
   double absolute() const { return absolute_time; }

@@ -98,3 +98,16 @@ def test_checkpoint_rejects_other_model_and_garbage(bmc, synth):
         a.restore(blob[: len(blob) // 2])
     a.restore(blob)  # still usable
     a.cycle(case["dt"])
+
+
+def test_force_remove_dead_keeps_last_sources(bmc, synth):
+    # ParticlesContainer::force_remove_dead touches the container only: the source terms of the last cycle
+    # (still to be consumed by the next ODE step, host_specific.cpp:257-313) must survive it
+    case = util.make_case(synth, "monod", 20_000, 50, dt=20.0, near_division=0.5, p_move=0.2, p_exit=0.3)
+    g = _mk(bmc, case)
+    util.load_case(g, case)
+    util.run_steps(g, case, 3)
+    before = g.get_sources().copy()
+    assert np.any(before != 0)
+    g.compact()
+    assert np.array_equal(g.get_sources(), before)

@@ -91,3 +91,36 @@ def test_cli_full_loop_matches_oracle_loop(orc, synth, tmp_path, n_comp, feed):
     assert info["out"] == co["total_out"] and info["new"] == co["total_new"]
     if feed > 0:
         assert info["out"] > 0
+
+
+def test_cli_serde_resume(synth, tmp_path):
+    # -serde (cli_parser.cpp:147-151, serde.cpp:64-219): a run resumed from `<stem>_serde_0.raw` ends where the
+    # uninterrupted run of the same number of steps ends.  Batch case (nothing leaves), so that the compactions
+    # the exporter forces at dump times — which fall on different steps in the two runs — have nothing to move.
+    # The liquid restarts from the archived CONCENTRATIONS (mass = C*V is recomputed, as in the reference).
+    d_t, n, n_comp = 20.0, 30_000, 16
+    fm = synth.make_flowmap(n_comp, d_t, p_move=0.05)
+    case_dir = str(tmp_path / "case")
+    synth.write_case(case_dir, fm)
+    exe = os.path.join(HOST, "biocma_b200")
+
+    def run(stem, final_time, extra=()):
+        args = [exe, "-np", str(n), "-d", str(final_time), "-dt", str(d_t), "-mn", "monod", "-f", case_dir,
+                "-er", stem, "-nex", "3"] + list(extra)
+        r = subprocess.run(args, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    a1 = run(str(tmp_path / "a1"), 400.0)                                   # 21 steps, writes a1_serde_0.raw
+    assert os.path.getsize(str(tmp_path / "a1_serde_0.raw")) > n * 10
+    a2 = run(str(tmp_path / "a2"), 400.0, ["-serde", str(tmp_path / "a1_serde_0.raw")])  # 21 more
+    b = run(str(tmp_path / "b"), 820.0)                                    # 42 steps in one go
+    assert a1["steps"] == 21 and a2["steps"] == 42 and b["steps"] == 42
+    assert b["new"] > 1000 and a1["new"] > 0
+    for k in ("n_particles", "new", "out"):
+        assert a2[k] == b[k], (k, a2[k], b[k])
+    ca = np.fromfile(str(tmp_path / "a2") + "_concentration_liquid.raw", np.float64).reshape(-1, n_comp)[-1]
+    cb = np.fromfile(str(tmp_path / "b") + "_concentration_liquid.raw", np.float64).reshape(-1, n_comp)[-1]
+    np.testing.assert_allclose(ca, cb, rtol=1e-9, atol=0)
+    na = np.fromfile(str(tmp_path / "a2") + "_number_particle.raw", np.uint64).reshape(-1, n_comp)[-1]
+    nb = np.fromfile(str(tmp_path / "b") + "_number_particle.raw", np.uint64).reshape(-1, n_comp)[-1]
+    assert np.array_equal(na, nb)
