@@ -178,10 +178,14 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    threads = host_threads()
+    # torchrun exports OMP_NUM_THREADS=1; libgomp reads it when it is loaded (nothing has loaded it yet in this
+    # process: torch is only imported by the GPU arm) and runs oversized teams badly when it says 1
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    # (no OMP_PROC_BIND/OMP_PLACES: binding as tools/exec.py:47-49 does measured 20 % SLOWER on the GPU boxes' cgroups)
     from _bmc_loader import load_synth
     synth = load_synth()
     model, n_comp, n_full, dt, near, p_exit = WORKLOADS[wl]
-    threads = host_threads()
     n = min(n_full, args.cpu_sample)
     fm, flows, conc = build_case(synth, model, n_comp, dt, p_exit)
 

@@ -607,9 +607,9 @@ template <class V> class ScatterView {
   V target_;
   std::shared_ptr<std::vector<T>> dup_;
   size_t n_ = 0; int nt_ = 1;
-  static int max_threads() {
+  static int max_threads() {  // OMP_NUM_THREADS may say 1 (torchrun exports it) while shim::set_threads asks for more
 #ifdef _OPENMP
-    return omp_get_max_threads();
+    return std::max(omp_get_max_threads(), shim::n_threads());
 #else
     return 1;
 #endif
@@ -634,7 +634,11 @@ template <class V> class ScatterView {
 #endif
     return Access{V(dup_->data() + (size_t)th * n_, target_.extent(0), target_.extent(1), target_.extent(2))};
   }
-  void reset() const { if (dup_) std::fill(dup_->begin(), dup_->end(), T{}); }
+  void reset() {  // called between kernels (serial): also the place to follow a change of the thread count
+    if (!dup_) return;
+    if (max_threads() > nt_) { nt_ = max_threads(); dup_->assign(n_ * (size_t)nt_, T{}); }
+    else std::fill(dup_->begin(), dup_->end(), T{});
+  }
   void shim_contribute_into(const V& dst) const {
     for (int th = 0; th < nt_; ++th) for (size_t k = 0; k < n_; ++k) dst.data()[k] += (*dup_)[(size_t)th * n_ + k];
   }
