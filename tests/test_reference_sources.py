@@ -248,3 +248,31 @@ def test_cuda_reproduces_reference_fixture(bmc, name):
     # newborn's drawn properties); everything else is bit-exact
     exact = g["model"] != "simple_acetate"
     _check_against_golden(loop, g, exact_props=exact, sources="quirk_free", prop_rtol=1e-5)
+
+
+def test_timing_build_runs_threaded_under_omp_num_threads_1(synth):
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm of bench.py still asks the shim for all
+    # host threads (per-thread ScatterView duplicates must follow).  The timing build draws from one xorshift1024*
+    # generator per thread, so the two runs are different realisations: counts agree statistically only.
+    ref = _ref_or_skip()
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys
+        sys.path[:0] = [%r, %r, %r]
+        import util, ref
+        from _bmc_loader import load_synth
+        case = util.make_case(load_synth(), "monod", 20000, 50, dt=20.0, near_division=0.5, p_move=0.1, p_exit=0.1)
+        out = []
+        for nt in (1, 4):
+            r = ref.RefLoop("monod", 1, 50, release=True, n_threads=nt)
+            util.load_case(r, case)
+            for s in range(3):
+                r.cycle(case["dt"])
+            c = r.counters(); out.append((c["n_used"], c["events"]["NewParticle"], round(float(r.get_sources().sum()), 9)))
+        print(out)
+        assert abs(out[0][1] - out[1][1]) <= 0.1 * out[0][1] + 5 and abs(out[0][2] - out[1][2]) <= 0.05 * abs(out[0][2])
+    """) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"),
+            os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
