@@ -163,7 +163,7 @@ def make_cpu_loop(model, n_species, n_comp, threads):
     if os.environ.get("BMC_CPU_BASELINE", "reference") == "reference":
         try:
             import ref
-            if model in ref.MODEL_IDS and (os.path.exists(ref.RELEASE_LIB_PATH) or ref.can_build()):
+            if model in ref.RELEASE_MODELS and (os.path.exists(ref.RELEASE_LIB_PATH) or ref.can_build()):
                 return (ref.RefLoop(model, n_species, n_comp, release=True, n_threads=threads), "reference",
                         "reference kernels (oracle/_ref, release flags, Kokkos shim with OpenMP leagues)")
         except Exception as e:  # noqa: BLE001 - fall back to the port, say why

@@ -16,7 +16,9 @@ LIB_PATH = os.path.join(_HERE, "_ref", "libbmc_ref.so")
 RELEASE_LIB_PATH = os.path.join(_HERE, "_ref", "libbmc_ref_release.so")  # -O3 -DNDEBUG -ffast-math: timing only
 REFERENCE_ROOT = os.environ.get("BMC_REFERENCE_ROOT", "/root/reference")
 EVENTS = ("NewParticle", "Exit", "Move", "Death", "Overflow", "ChangeWeight")
-MODEL_IDS = {"fixed_length": 0, "monod": 1, "simple_acetate": 2}
+MODEL_IDS = {"fixed_length": 0, "monod": 1, "simple_acetate": 2,
+             "udf_model": 4}  # the reference's example UDF apps/udf_model/minimal.cpp (checker build only)
+RELEASE_MODELS = ("fixed_length", "monod", "simple_acetate")
 _lib = None
 
 

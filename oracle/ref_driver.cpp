@@ -43,6 +43,9 @@
 #include <models/fixed_length.hpp>
 #include <models/simple_acetate.hpp>
 #include <simulation/kernels/kernels.hpp>
+#ifdef BMC_REF_WITH_UDF
+#include <models/udf_model.hpp>  // hooks: apps/udf_model/minimal.cpp through UnsafeUDF::Loader (oracle/ref_udf.cpp)
+#endif
 
 #include <chrono>
 #include <cstdlib>
@@ -135,6 +138,9 @@ static_assert(ModelType<Tap<Models::FixedLength>>);
 static_assert(ModelType<Tap<Models::SimpleAcetate>>);
 static_assert(ModelType<Tap<MonodQ1>>);
 static_assert(ConstWeightModelType<Tap<MonodQ1>>);
+#ifdef BMC_REF_WITH_UDF
+static_assert(ModelType<Tap<Models::UdfModel>>);
+#endif
 
 // ------------------------------------------------------------------ one simulation unit's worth of state
 struct IRef {
@@ -209,11 +215,13 @@ template <class M> struct Ref final : IRef {
     MC::KPRNG kprng(seed ? seed : 1);
     const uint64_t min_c = 0, max_c = uniform_pos ? n_comp : 1;  // select_bounds_compartment
     Kokkos::View<float*, ComputeSpace> lin("linit", n);
-    for (size_t i = 0; i < n; ++i) lin(i) = linit ? linit[i] : 1.5e-6f;
+    Kokkos::View<float**> lin2("linit2", n, 1);
+    for (size_t i = 0; i < n; ++i) lin(i) = lin2(i, 0) = linit ? linit[i] : 1.5e-6f;
     double total_mass = 0.;
     for (size_t i = 0; i < n; ++i) {
       synced().start_sequence((uint32_t)i, kBaseUpdate);
-      if constexpr (ConfigurableModel<M>) M::init(kprng.random_pool, i, container.model, typename M::Config(lin));
+      if constexpr (std::is_same_v<typename M::Config, Kokkos::View<float**>>) M::init(kprng.random_pool, i, container.model, lin2);  // UdfModel: config(idx, 0)
+      else if constexpr (ConfigurableModel<M>) M::init(kprng.random_pool, i, container.model, typename M::Config(lin));
       else M::init(kprng.random_pool, i, container.model);
       container.position(i) = kprng.uniform_u(min_c, max_c);
       total_mass += M::mass(i, container.model);
@@ -292,13 +300,16 @@ template <class M> struct Ref final : IRef {
 #define REF_TRY(h, ...) try { __VA_ARGS__; return 0; } catch (const std::exception& e) { (h)->err = e.what(); return -1; }
 
 extern "C" {
-// model ids as in oracle/oracle.py: 0 fixed_length, 1 monod, 2 simple_acetate
+// model ids as in oracle/oracle.py: 0 fixed_length, 1 monod, 2 simple_acetate, 4 udf_model (checker build only)
 void* ref_create(int model, uint64_t n_species, uint64_t n_comp, uint64_t seed, uint32_t rank, uint64_t particles_per_team) {
   IRef* r = nullptr;
   try {
     if (model == 0) r = new Ref<Tap<Models::FixedLength>>();
     else if (model == 1) r = new Ref<Tap<MonodQ1>>();
     else if (model == 2) r = new Ref<Tap<Models::SimpleAcetate>>();
+#ifdef BMC_REF_WITH_UDF
+    else if (model == 4) { Models::UdfModel::set_nvar(); r = new Ref<Tap<Models::UdfModel>>(); }  // udfmodel_user.cpp:51-56
+#endif
     else return nullptr;
   } catch (...) { return nullptr; }
   r->n_species = n_species; r->n_comp = n_comp; r->seed = seed; r->rank = rank;

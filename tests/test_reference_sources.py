@@ -95,7 +95,7 @@ def _check_against_golden(loop, g, *, exact_props=True, sources="all", prop_rtol
 
 
 def test_fixtures_present():
-    assert len(NAMES) >= 8, NAMES
+    assert len(NAMES) >= 9, NAMES
     g = _load("monod_cma")
     last = g["counters"][-1]
     # the fixture exercises the whole path: divisions, outlet exits, moves, >= 2 compactions
@@ -134,6 +134,7 @@ def _ref_or_skip():
     ("fixed_length", 4100, 37, 1024, dict(near_division=0.6, p_exit=0.3, p_move=0.2, dt=20.0, seed=11)),
     ("simple_acetate", 3000, 8, 512, dict(near_division=0.5, p_exit=0.1, p_move=0.1, dt=20.0, seed=13)),
     ("monod", 2300, 1, 256, dict(near_division=0.5, p_exit=0.05, dt=20.0, seed=17)),
+    ("udf_model", 2600, 12, 512, dict(near_division=0.5, p_exit=0.2, p_move=0.1, dt=20.0, seed=19)),
 ])
 def test_live_reference_equals_oracle(orc, synth, model, n, n_comp, ppt, kw):
     ref = _ref_or_skip()
@@ -197,7 +198,7 @@ def _ref_available():
     return ref.available()
 
 
-@pytest.mark.parametrize("model", ["fixed_length", "monod", "simple_acetate"])
+@pytest.mark.parametrize("model", ["fixed_length", "monod", "simple_acetate", "udf_model"])
 def test_oracle_init_reproduces_reference_fixture(orc, model):
     # MC::init (mcinit.hpp:67-105, unit.cpp:102-163): M::init + uniform compartment + total mass
     z = np.load(os.path.join(_gdir(), f"refinit_{model}.npz"))
@@ -210,17 +211,25 @@ def test_oracle_init_reproduces_reference_fixture(orc, model):
     assert np.array_equal(st["position"].astype(np.uint32), z["pos"])
 
 
+UDF_SRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "biocma-mcst_b200", "udf", "minimal_udf.cu")
+
+
+def _cuda_loop(bmc, model, n_species, n_comp, seed):
+    kw = dict(udf_source=UDF_SRC) if model == "udf_model" else {}  # the same model in bmc_udf.cuh form, NVRTC-compiled
+    return bmc.ParticleLoop(model, n_species, n_comp, seed=seed, **kw)
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("model", ["fixed_length", "monod", "simple_acetate"])
+@pytest.mark.parametrize("model", ["fixed_length", "monod", "simple_acetate", "udf_model"])
 def test_cuda_init_reproduces_reference_fixture(bmc, model):
     z = np.load(os.path.join(_gdir(), f"refinit_{model}.npz"))
     n, nc = int(z["n"]), int(z["n_comp"])
-    g = bmc.ParticleLoop(model, 2 if model == "simple_acetate" else 1, nc, seed=int(z["seed"]))
+    g = _cuda_loop(bmc, model, 2 if model == "simple_acetate" else 1, nc, int(z["seed"]))
     m = g.init_particles(n, True, z["linit"])
     st = g.get_particles(n)
     assert abs(m - float(z["mass"])) <= 1e-12 * float(z["mass"])  # device reduction order
     assert np.array_equal(st["position"][:n].astype(np.uint32), z["pos"])
-    if model == "fixed_length":  # configurable init: lengths are given, nothing is drawn
+    if model in ("fixed_length", "udf_model"):  # configurable init: lengths are given, nothing is drawn
         assert np.array_equal(st["props"][:, :n].view(np.uint32), z["props"].view(np.uint32))
     else:  # TruncatedNormal through erfc/log/sqrt: libdevice vs glibc differ in the last bits
         np.testing.assert_allclose(st["props"][:, :n], z["props"], rtol=2e-6, atol=0)
@@ -242,7 +251,7 @@ def test_reference_refuses_small_populations():
 @pytest.mark.parametrize("name", NAMES)
 def test_cuda_reproduces_reference_fixture(bmc, name):
     g = _load(name)
-    loop = bmc.ParticleLoop(g["model"], g["n_species"], g["n_comp"], seed=g["seed"])
+    loop = _cuda_loop(bmc, g["model"], g["n_species"], g["n_comp"], g["seed"])
     _feed(loop, g)
     # simple_acetate::division evaluates exp/log/erfc (CUDA libdevice vs glibc: last-bit differences in the
     # newborn's drawn properties); everything else is bit-exact

@@ -29,6 +29,8 @@ CASES = {
     "simple_acetate_closed": ("simple_acetate", 1500, 12, 8, 256, dict(near_division=0.5, outlet=False, p_move=0.1, dt=20.0)),
     # 0D: one compartment (Tag0D contribution kernel, no move), chemostat outlet
     "monod_0d": ("monod", 2048 + 77, 1, 10, 1024, dict(near_division=0.5, p_exit=0.05, dt=20.0)),
+    # the reference's example user-defined model (apps/udf_model/minimal.cpp behind Models::UdfModel)
+    "udf_model_cma": ("udf_model", 2500, 20, 12, 1024, dict(near_division=0.5, p_exit=0.2, p_move=0.05, dt=20.0)),
     "fixed_length_0d_batch": ("fixed_length", 1300, 1, 6, 256, dict(near_division=0.5, outlet=False, dt=20.0)),
 }
 
@@ -95,7 +97,7 @@ def main():
         np.savez_compressed(path, **out)
         c = out["counters"][-1]
         print(f"{name}: n_used {c[6]}, events {c[:6].tolist()}, compactions {c[-1]}, {os.path.getsize(path) / 1024:.0f} KiB")
-    for model in ("fixed_length", "monod", "simple_acetate"):
+    for model in ("fixed_length", "monod", "simple_acetate", "udf_model"):
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"refinit_{model}.npz"), **run_init(model))
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "refdist.npz"), **run_distributions())
     print("init + distributions written")
