@@ -275,6 +275,7 @@ def main():
         total_mass = float(np.sum(props[0].astype(np.float64))) * 2.8274e-10
     loop.set_weight(0.5 * float(fm["volumes"].sum()) / (total_mass * world))
     setup_loop(loop, fm, flows, conc, n_comp)
+    collective = ""
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8)
         if rank == 0:
@@ -282,6 +283,33 @@ def main():
         uid = uid.cuda()
         dist.broadcast(uid, 0)
         loop.comm_init(world, rank, uid.cpu().numpy())
+        # one-shot all-reduce over NVLink peer mappings (bmc_p2p_*): the 64-byte IPC handles are gathered here; if any
+        # rank cannot attach, every rank stays on the NCCL communicator.  BMC_P2P=0 forces NCCL, BMC_P2P=1 forces the
+        # peer-memory path; by default it is used from BMC_P2P_MIN_RANKS ranks on (see DESIGN.md §7 for the measurements).
+        collective = "1 NCCL all-reduce/step"
+        want_p2p = os.environ.get("BMC_P2P", "auto")
+        use_p2p = want_p2p == "1" or (want_p2p == "auto" and world >= int(os.environ.get("BMC_P2P_MIN_RANKS", "4")))
+        if use_p2p and world <= 16:
+            ok = 1
+            try:
+                mine = torch.from_numpy(loop.p2p_export().copy()).cuda()
+            except RuntimeError:
+                ok, mine = 0, torch.zeros(64, dtype=torch.uint8, device="cuda")
+            gathered = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(gathered, mine)
+            if ok:
+                try:
+                    loop.p2p_attach(world, rank, torch.stack(gathered).cpu().numpy())
+                except RuntimeError as e:
+                    print(f"[bench] rank {rank}: peer attach failed ({e}); NCCL", file=sys.stderr)
+                    ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 1:
+                collective = "1 peer-memory all-reduce/step (one-shot over NVLink, NCCL only for set-up)"
+            else:
+                loop.p2p_disable()
+            dist.barrier()
     stream = torch.cuda.ExternalStream(loop.stream_handle(), device=torch.device("cuda", local))
 
     def barrier():
@@ -378,7 +406,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{wl}: {n_comp}-compartment stirred-tank CMA, {model}, {n_per_gpu} particles/GPU, dt={dt}",
-                       "parallelism": f"particle-sharded x{world}, replicated liquid state, 1 NCCL all-reduce/step" if world > 1 else "single GPU",
+                       "parallelism": f"particle-sharded x{world}, replicated liquid state, {collective}" if world > 1 else "single GPU",
                        "l2_policy": f"inputs larger than L2 ({n_per_gpu * (loop.n_var * 4 + 13) / 1e6:.0f} MB of particle state per GPU)"},
             "e2e": {"value": e2e_v, "unit": "particle-steps/s", "h2d_bytes_per_step": nb, "d2h_bytes_per_step": nb,
                     "ms_per_step": ms_e2e / e2e_steps},

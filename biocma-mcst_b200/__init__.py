@@ -31,6 +31,7 @@ ABI_SYMBOLS = (
     "bmc_sources_device", "bmc_concentrations_device", "bmc_stream", "bmc_launch_count", "bmc_profile_enable",
     "bmc_profile_read", "bmc_nccl_unique_id", "bmc_comm_init", "bmc_allreduce_sources",
     "bmc_liquid_set_transition", "bmc_liquid_set_feeds", "bmc_liquid_step", "bmc_get_concentrations",
+    "bmc_p2p_export", "bmc_p2p_attach", "bmc_p2p_region", "bmc_p2p_attach_local", "bmc_p2p_disable",
     "bmc_udf_check", "bmc_get_properties", "bmc_cma_build", "bmc_checkpoint_size", "bmc_checkpoint_save", "bmc_checkpoint_load",
 )
 
@@ -119,6 +120,11 @@ def load_library(path=None):
     lib.bmc_nccl_unique_id.argtypes = [vp]
     lib.bmc_comm_init.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
     lib.bmc_allreduce_sources.argtypes = [vp]
+    lib.bmc_p2p_export.argtypes = [vp, vp]
+    lib.bmc_p2p_attach.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
+    lib.bmc_p2p_region.argtypes = [vp, P(vp)]
+    lib.bmc_p2p_disable.argtypes = [vp]
+    lib.bmc_p2p_attach_local.argtypes = [vp, ctypes.c_int, ctypes.c_int, P(vp)]
     lib.bmc_liquid_set_transition.argtypes = [vp, u64, vp, vp, vp]
     lib.bmc_liquid_set_feeds.argtypes = [vp, u64, P(BmcFeed)]
     lib.bmc_liquid_step.argtypes = [vp, dbl]
@@ -386,6 +392,28 @@ class ParticleLoop:
     def comm_init(self, n_ranks, rank, unique_id):
         uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
         self._ck(self.lib.bmc_comm_init(self.h, int(n_ranks), int(rank), _ptr(uid)))
+
+    def p2p_export(self):
+        """64-byte IPC handle of this rank's exchange region (gather them, then p2p_attach)"""
+        buf = np.zeros(64, np.uint8)
+        self._ck(self.lib.bmc_p2p_export(self.h, _ptr(buf)))
+        return buf
+
+    def p2p_attach(self, n_ranks, rank, handles):
+        hs = np.ascontiguousarray(handles, np.uint8).reshape(n_ranks * 64)
+        self._ck(self.lib.bmc_p2p_attach(self.h, int(n_ranks), int(rank), _ptr(hs)))
+
+    def p2p_disable(self):
+        self._ck(self.lib.bmc_p2p_disable(self.h))
+
+    def p2p_region(self):
+        base = ctypes.c_void_p()
+        self._ck(self.lib.bmc_p2p_region(self.h, ctypes.byref(base)))
+        return base.value
+
+    def p2p_attach_local(self, n_ranks, rank, bases):
+        arr = (ctypes.c_void_p * n_ranks)(*bases)
+        self._ck(self.lib.bmc_p2p_attach_local(self.h, int(n_ranks), int(rank), arr))
 
     def allreduce_sources(self):
         self._ck(self.lib.bmc_allreduce_sources(self.h))

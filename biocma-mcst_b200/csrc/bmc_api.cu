@@ -92,6 +92,9 @@ struct bmc_ctx {
   int pin_next = 0; double* h_pin_out = nullptr;
   // nccl
   void* nccl_comm = nullptr; int nccl_ranks = 0;
+  // peer-memory all-reduce (bmc_p2p_*)
+  unsigned char* p2p_region = nullptr; size_t p2p_bytes = 0; int p2p_world = 0, p2p_rank = 0; bool p2p_on = false, p2p_ipc = false;
+  unsigned char* p2p_base[kMaxPeers] = {}; unsigned long long p2p_epoch = 0;
   std::string err;
 };
 
@@ -275,6 +278,7 @@ static int sync_state(bmc_ctx* ctx, DevState* out) {
   ctx->known_max_add = std::max<uint64_t>(ctx->known_max_add, out->n_add);
   if (out->inactive == 0 && ctx->flows.empty()) ctx->maybe_inactive = false;
   if (out->error & 2u) { ctx->err = "compaction found fewer idle tail particles than gaps (inactive counter inconsistent)"; return BMC_ERR_INVALID; }
+  if (out->error & 4u) { ctx->err = "peer-memory all-reduce: a peer did not publish its sources in time"; return BMC_ERR_NCCL; }
   return BMC_OK;
 }
 
@@ -432,6 +436,8 @@ int bmc_destroy(bmc_ctx** h) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->nccl_comm && g_nccl_destroy) g_nccl_destroy(c->nccl_comm);
+  if (c->p2p_ipc) for (int r = 0; r < c->p2p_world; ++r) if (r != c->p2p_rank && c->p2p_base[r]) cudaIpcCloseMemHandle(c->p2p_base[r]);
+  if (c->p2p_region) cudaFree(c->p2p_region);
   unload_udf_model(c->vt);
   free_container(c);
   dev_free(c->d_conc); dev_free(c->d_sources); dev_free(c->d_acc); dev_free(c->d_conc_next); dev_free(c->d_mass);
@@ -1178,9 +1184,83 @@ int bmc_comm_init(bmc_ctx* ctx, int n_ranks, int rank, const uint8_t* id128) {
   ctx->nccl_ranks = n_ranks;
   return BMC_OK;
 }
+// ---- peer-memory all-reduce ------------------------------------------------------------------
+static int p2p_alloc_region(bmc_ctx* ctx) {
+  if (ctx->p2p_region) return BMC_OK;
+  CK(cudaSetDevice(ctx->device));
+  ctx->p2p_bytes = 128 + 2 * ctx->n_species * ctx->n_comp * sizeof(double);
+  CK(cudaMalloc((void**)&ctx->p2p_region, ctx->p2p_bytes));  // plain cudaMalloc: exportable with cudaIpcGetMemHandle
+  CK(cudaMemset(ctx->p2p_region, 0, ctx->p2p_bytes));
+  CK(cudaDeviceSynchronize());
+  return BMC_OK;
+}
+int bmc_p2p_export(bmc_ctx* ctx, uint8_t* handle64) {
+  if (!ctx || !handle64) return BMC_ERR_INVALID;
+  int rc = p2p_alloc_region(ctx);
+  if (rc) return rc;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, ctx->p2p_region));
+  memcpy(handle64, &h, 64);
+  return BMC_OK;
+}
+int bmc_p2p_region(bmc_ctx* ctx, void** base) {
+  if (!ctx || !base) return BMC_ERR_INVALID;
+  int rc = p2p_alloc_region(ctx);
+  if (rc) return rc;
+  *base = ctx->p2p_region;
+  return BMC_OK;
+}
+static int p2p_finish_attach(bmc_ctx* ctx, int n_ranks, int rank, bool ipc) {
+  ctx->p2p_world = n_ranks; ctx->p2p_rank = rank; ctx->p2p_ipc = ipc; ctx->p2p_epoch = 0; ctx->p2p_on = true;
+  return BMC_OK;
+}
+int bmc_p2p_attach(bmc_ctx* ctx, int n_ranks, int rank, const uint8_t* handles64) {
+  if (!ctx || !handles64 || n_ranks < 1 || n_ranks > kMaxPeers || rank < 0 || rank >= n_ranks) return BMC_ERR_INVALID;
+  if (!ctx->p2p_region) { ctx->err = "bmc_p2p_export not called"; return BMC_ERR_INVALID; }
+  CK(cudaSetDevice(ctx->device));
+  for (int r = 0; r < n_ranks; ++r) {
+    if (r == rank) { ctx->p2p_base[r] = ctx->p2p_region; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles64 + 64 * (size_t)r, 64);
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      ctx->err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);
+      for (int q = 0; q < r; ++q) if (q != rank && ctx->p2p_base[q]) { cudaIpcCloseMemHandle(ctx->p2p_base[q]); ctx->p2p_base[q] = nullptr; }
+      return BMC_ERR_CUDA;
+    }
+    ctx->p2p_base[r] = (unsigned char*)ptr;
+  }
+  return p2p_finish_attach(ctx, n_ranks, rank, true);
+}
+int bmc_p2p_attach_local(bmc_ctx* ctx, int n_ranks, int rank, void* const* bases) {
+  if (!ctx || !bases || n_ranks < 1 || n_ranks > kMaxPeers || rank < 0 || rank >= n_ranks) return BMC_ERR_INVALID;
+  if (!ctx->p2p_region || bases[rank] != ctx->p2p_region) { ctx->err = "bmc_p2p_attach_local: bases[rank] must be this context's region"; return BMC_ERR_INVALID; }
+  for (int r = 0; r < n_ranks; ++r) ctx->p2p_base[r] = (unsigned char*)bases[r];
+  return p2p_finish_attach(ctx, n_ranks, rank, false);
+}
+
+int bmc_p2p_disable(bmc_ctx* ctx) {
+  if (!ctx) return BMC_ERR_INVALID;
+  ctx->p2p_on = false;  // bmc_allreduce_sources goes back to the NCCL communicator
+  return BMC_OK;
+}
+
 int bmc_allreduce_sources(bmc_ctx* ctx) {
   if (!ctx) return BMC_ERR_INVALID;
-  if (!ctx->nccl_comm) { ctx->err = "bmc_comm_init not called"; return BMC_ERR_INVALID; }
+  if (ctx->p2p_on) {  // one-shot reduction over peer mappings (bmc_kernels_common.cuh)
+    CK(cudaSetDevice(ctx->device));
+    P2PParams pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.sources = ctx->d_sources; pp.n = (uint32_t)(ctx->n_species * ctx->n_comp); pp.world = ctx->p2p_world; pp.rank = ctx->p2p_rank;
+    pp.epoch = ++ctx->p2p_epoch; pp.st = ctx->st; pp.spin_limit = 20000000000ll;  // ~10 s at 2 GHz
+    for (int r = 0; r < ctx->p2p_world; ++r) pp.base[r] = ctx->p2p_base[r];
+    p2p_allreduce_kernel<<<1, 1024, 0, ctx->stream>>>(pp);
+    return check_launch(ctx, "p2p_allreduce");
+  }
+  if (!ctx->nccl_comm) { ctx->err = "bmc_comm_init / bmc_p2p_attach not called"; return BMC_ERR_INVALID; }
   CK(cudaSetDevice(ctx->device));
   // ncclFloat64 = 8, ncclSum = 0
   const int r = g_nccl.AllReduce(ctx->d_sources, ctx->d_sources, ctx->n_species * ctx->n_comp, 8, 0, ctx->nccl_comm, ctx->stream);
