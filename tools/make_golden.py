@@ -32,19 +32,39 @@ CASES = {
     # the reference's example user-defined model (apps/udf_model/minimal.cpp behind Models::UdfModel)
     "udf_model_cma": ("udf_model", 2500, 20, 12, 1024, dict(near_division=0.5, p_exit=0.2, p_move=0.05, dt=20.0)),
     "fixed_length_0d_batch": ("fixed_length", 1300, 1, 6, 256, dict(near_division=0.5, outlet=False, dt=20.0)),
+    # two outlets (find_flow with n_flows > 1, move_kernel.hpp:105-127)
+    "monod_two_outlets": ("monod", 2600, 20, 10, 1024, dict(near_division=0.5, p_exit=0.15, p_move=0.1, dt=20.0, two_outlets=True)),
+    # the caller supplies non-zero ages (the CUDA path then keeps them as floats, updated every step)
+    "fixed_length_aged": ("fixed_length", 2200, 16, 10, 1024, dict(near_division=0.5, p_exit=0.2, p_move=0.1, dt=20.0, initial_ages=True)),
+    # RuntimeParameters: compaction only above 5 % inactive and at least 64 particles (particles_container.hpp:539-557)
+    "monod_late_compaction": ("monod", 2400, 20, 14, 1024, dict(near_division=0.5, p_exit=0.3, p_move=0.1, dt=20.0,
+                                                               runtime=dict(dead_ratio=0.05, min_removal=64))),
 }
 
 
 def run_case(name, synth):
     model, n, n_comp, steps, ppt, kw = CASES[name]
+    kw = dict(kw)
+    two_outlets, initial_ages, runtime = kw.pop("two_outlets", False), kw.pop("initial_ages", False), kw.pop("runtime", {})
     case = util.make_case(synth, model, n, n_comp, **kw)
-    loop = ref.RefLoop(model, case["n_species"], n_comp, seed=case["seed"], particles_per_team=ppt)
+    if two_outlets:  # a second outlet in the middle of the lattice, twice the flow
+        o2 = n_comp // 2
+        q2 = 2.0 * case["flows"][0][1] * case["fm"]["volumes"][o2] / case["fm"]["volumes"][case["flows"][0][0]]
+        case["flows"] = case["flows"] + [(o2, q2, case["fm"]["volumes"][o2])]
+    rng = np.random.default_rng(77)
+    age_hyd0 = (rng.random(n) * 500.0).astype(np.float32) if initial_ages else np.zeros(n, np.float32)
+    age_div0 = (rng.random(n) * 300.0).astype(np.float32) if initial_ages else np.zeros(n, np.float32)
+    loop = ref.RefLoop(model, case["n_species"], n_comp, seed=case["seed"], particles_per_team=ppt, **runtime)
     util.load_case(loop, case)
+    if initial_ages:
+        loop.set_particles(case["props"], case["pos"], None, age_hyd0, age_div0)
+        loop.set_weight(case["weight"])
     out = dict(model=model, n=n, n_comp=n_comp, steps=steps, particles_per_team=ppt, dt=case["dt"], seed=case["seed"],
                n_species=case["n_species"], weight=case["weight"], props0=case["props"], pos0=case["pos"].astype(np.uint32),
                conc0=case["conc"], volumes=case["fm"]["volumes"], out_flows=case["fm"]["out_flows"],
                neighbors=np.asarray(case["fm"]["neighbors"], np.uint32), cdf=case["fm"]["cdf"],
-               flows=np.array(case["flows"], np.float64).reshape(-1, 3))
+               flows=np.array(case["flows"], np.float64).reshape(-1, 3), age_hyd0=age_hyd0, age_div0=age_div0,
+               dead_ratio=runtime.get("dead_ratio", 0.01), min_removal=runtime.get("min_removal", 0))
     srcs, counters, inactive_before = [], [], []
     for s in range(steps):
         inactive_before.append(loop.counters()["n_inactive"])
