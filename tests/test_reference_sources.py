@@ -289,3 +289,26 @@ def test_timing_build_runs_threaded_under_omp_num_threads_1(synth):
     env = dict(os.environ, OMP_NUM_THREADS="1")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_live_division_buffer_overflow(orc, synth):
+    # Q6 (model_kernel.hpp:253-259): with a division buffer that is too small the overflowing mothers keep their length,
+    # NewParticle is counted anyway, Overflow / waiting_allocation_particle are reported, and they retry next step.
+    # Under serial execution the mothers that get a row are the lowest indices: reference and oracle agree exactly.
+    ref = _ref_or_skip()
+    case = util.make_case(synth, "fixed_length", 3000, 10, near_division=0.5, p_move=0.1, outlet=False, dt=60.0, seed=23)
+    kw = dict(buffer_ratio=0.01, allocation_factor=1.5)   # 45 rows for ~100 divisions per step
+    o = orc.OracleLoop("fixed_length", 1, 10, seed=case["seed"], **kw)
+    r = ref.RefLoop("fixed_length", 1, 10, seed=case["seed"], **kw)
+    util.load_case(o, case); util.load_case(r, case)
+    waited = 0
+    for s in range(8):
+        c = util.conc_at(case, s)
+        o.set_concentrations(c); r.set_concentrations(c)
+        o.cycle(case["dt"]); r.cycle(case["dt"])
+        co, cr = o.counters(), r.counters()
+        util.assert_counters_equal(co, cr)
+        waited += cr["last_waiting_allocation"]
+        n_u = co["n_used"]
+        util.assert_state_equal(o.get_particles(n_u), r.get_particles(n_u), n_u, exact_props=True)
+    assert waited > 0 and cr["events"]["Overflow"] == waited and cr["events"]["NewParticle"] > cr["total_new"]
