@@ -602,7 +602,8 @@ template <class F, class... P> void parallel_scan(const std::string& label, cons
 // Duplicated per thread like Kokkos' host default (ScatterDuplicated, ScatterNonAtomic): access() hands out the
 // calling thread's private copy, contribute() adds the copies into the target in thread order, reset() zeroes them.
 namespace Experimental {
-template <class V> class ScatterView {
+template <class DataT, class... Props> class ScatterView {
+  using V = View<DataT, Props...>;
   using T = typename V::non_const_value_type;
   V target_;
   std::shared_ptr<std::vector<T>> dup_;
@@ -639,11 +640,11 @@ template <class V> class ScatterView {
     if (max_threads() > nt_) { nt_ = max_threads(); dup_->assign(n_ * (size_t)nt_, T{}); }
     else std::fill(dup_->begin(), dup_->end(), T{});
   }
-  void shim_contribute_into(const V& dst) const {
+  template <class W> void shim_contribute_into(const W& dst) const {
     for (int th = 0; th < nt_; ++th) for (size_t k = 0; k < n_; ++k) dst.data()[k] += (*dup_)[(size_t)th * n_ + k];
   }
 };
-template <class D, class... P> ScatterView<View<D, P...>> create_scatter_view(const View<D, P...>& v) { return ScatterView<View<D, P...>>(v); }
+template <class D, class... P> ScatterView<D, P...> create_scatter_view(const View<D, P...>& v) { return ScatterView<D, P...>(v); }
 template <class V, class S> void contribute(const V& dst, const S& scatter) { scatter.shim_contribute_into(dst); }
 }  // namespace Experimental
 

@@ -60,6 +60,7 @@ def _declare(L):
     L.ref_get_counters.argtypes = [vp, vp]
     L.ref_init_particles.argtypes = [vp, u64, ctypes.c_int, vp, ctypes.POINTER(dbl)]
     L.ref_sample.argtypes = [ctypes.c_int, u64, u64, dbl, dbl, dbl, dbl, vp]
+    L.ref_get_properties.argtypes = [vp, vp, vp, vp, ctypes.POINTER(u64), ctypes.POINTER(u64)]
     L.ref_set_threads.argtypes = [ctypes.c_int]; L.ref_set_threads.restype = None
     L.ref_max_threads.restype = ctypes.c_int
     return L
@@ -160,6 +161,15 @@ class RefLoop:
         ah = np.empty(n, np.float32); ad = np.empty(n, np.float32)
         self._ck(self.L.ref_get_particles(self.h, n, _ptr(props), _ptr(pos), _ptr(st), _ptr(ah), _ptr(ad)))
         return dict(props=props, position=pos, status=st, age_hyd=ah, age_div=ad)
+
+    def get_properties(self, indices=None, with_age=True):
+        """PostProcessing::get_properties; `indices` is ignored: the model's own get_number() decides (as in the reference)"""
+        n, rows = ctypes.c_uint64(), ctypes.c_uint64()
+        self._ck(self.L.ref_get_properties(self.h, None, None, None, ctypes.byref(n), ctypes.byref(rows)))
+        pv = np.zeros((rows.value, n.value), np.float64); sv = np.zeros((rows.value, self.n_compartments), np.float64)
+        ag = np.zeros((2, n.value), np.float64)
+        self._ck(self.L.ref_get_properties(self.h, _ptr(pv), _ptr(sv), _ptr(ag), ctypes.byref(n), ctypes.byref(rows)))
+        return dict(particle_values=pv, spatial_values=sv, ages=ag if with_age else None)
 
     def get_contribs(self, n=None):
         n = self.n_used() if n is None else int(n)

@@ -20,6 +20,7 @@
 //     MC::EventContainer            mc/events.hpp
 //     Models::FixedLength, Models::Monod, Models::SimpleAcetate   models/*.hpp
 //     Common::c_league_size         common/src/common.cpp
+//     PostProcessing::get_properties core/post_process.hpp:173-250 (+ GetPropertiesFunctor :33-147)
 //   what this file adds
 //     the body of SimulationUnit::cycleProcess / post_cycle (simulation/simulation.hpp:183-239), which
 //     cannot be instantiated here (SimulationUnit needs Eigen + rcmtool): the same calls in the same order;
@@ -43,6 +44,7 @@
 #include <models/fixed_length.hpp>
 #include <models/simple_acetate.hpp>
 #include <simulation/kernels/kernels.hpp>
+#include <core/post_process.hpp>  // PostProcessing::get_properties / GetPropertiesFunctor (apps/core/public/core/post_process.hpp:33-250)
 #ifdef BMC_REF_WITH_UDF
 #include <models/udf_model.hpp>  // hooks: apps/udf_model/minimal.cpp through UnsafeUDF::Loader (oracle/ref_udf.cpp)
 #endif
@@ -132,6 +134,8 @@ struct MonodQ1 {
   }
   KOKKOS_INLINE_FUNCTION static void division(const MC::pool_type& pool, std::size_t idx, std::size_t idx2, const SelfParticle& arr,
                                               const SelfParticle& buf) { Base::division(pool, idx, idx2, arr, buf); }
+  static std::vector<std::string_view> names() { return Base::names(); }        // partial export: length, mu, mu_eff
+  static std::vector<std::size_t> get_number() { return Base::get_number(); }
 };
 static_assert(ModelType<MonodQ1>);
 static_assert(ModelType<Tap<Models::FixedLength>>);
@@ -160,6 +164,7 @@ struct IRef {
   virtual void set_particles(size_t n, const float* props, const uint64_t* pos, const uint8_t* st, const float* ah, const float* ad) = 0;
   virtual void get_particles(size_t n, float* props, uint64_t* pos, uint8_t* st, float* ah, float* ad) = 0;
   virtual void get_contribs(size_t n, float* out) = 0;
+  virtual void get_properties(double* pv, double* sv, double* ages, uint64_t* n_p, uint64_t* n_rows) = 0;
   virtual double init_particles(size_t n, bool uniform_pos, const float* linit) = 0;
   virtual void set_weight(double w) = 0;
   virtual void set_conc(const double* c) = 0;
@@ -228,6 +233,18 @@ template <class M> struct Ref final : IRef {
     }
     container.weights(0) = (typename M::FloatType)weight;
     return total_mass;
+  }
+  // PostProcessing::get_properties (post_process.hpp:173-250): force_remove_dead, then exported properties + mass per
+  // particle (rows x n_p), their per-compartment sums (rows x n_comp) and both ages (2 x n_p), all LayoutRight doubles
+  void get_properties(double* pv, double* sv, double* ages, uint64_t* n_p, uint64_t* n_rows) override {
+    auto res = PostProcessing::get_properties<M>(container, n_comp, true);
+    if (!res.has_value() || !res->particle_values.has_value()) throw std::runtime_error("model has no export properties");
+    const auto& P = *res->particle_values; const auto& S = *res->spatial_values; const auto& A = *res->ages;
+    if (n_p) *n_p = P.extent(1);
+    if (n_rows) *n_rows = P.extent(0);
+    if (pv) for (size_t r = 0; r < P.extent(0); ++r) for (size_t i = 0; i < P.extent(1); ++i) pv[r * P.extent(1) + i] = P(r, i);
+    if (sv) for (size_t r = 0; r < S.extent(0); ++r) for (size_t j = 0; j < S.extent(1); ++j) sv[r * S.extent(1) + j] = S(r, j);
+    if (ages) for (size_t r = 0; r < 2; ++r) for (size_t i = 0; i < A.extent(1); ++i) ages[r * A.extent(1) + i] = A(r, i);
   }
   void get_contribs(size_t n, float* out) override {
     for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < M::n_c; ++j) out[j * n + i] = container.contribs(i, j);
@@ -372,6 +389,9 @@ int ref_sample(int kind, uint64_t seed, uint64_t n, double p0, double p1, double
     pool.free_state(gen);
   }
   return 0;
+}
+int ref_get_properties(void* h, double* pv, double* sv, double* ages, uint64_t* n_p, uint64_t* n_rows) {
+  auto* r = static_cast<IRef*>(h); REF_TRY(r, r->get_properties(pv, sv, ages, n_p, n_rows));
 }
 int ref_get_contribs(void* h, uint64_t n, float* out) { auto* r = static_cast<IRef*>(h); REF_TRY(r, r->get_contribs(n, out)); }
 void ref_set_weight(void* h, double w) { static_cast<IRef*>(h)->set_weight(w); }

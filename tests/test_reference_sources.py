@@ -98,6 +98,19 @@ def _check_against_golden(loop, g, *, exact_props=True, sources="all", prop_rtol
                 np.testing.assert_allclose(st["age_hyd"][:n], g[f"age_hyd_{s}"], rtol=1e-6, atol=0)
 
 
+def _check_export(loop, g, sv_rtol=0.0):
+    """PostProcessing::get_properties (post_process.hpp:173-250) after the last step of the fixture"""
+    idx = None if int(g["export_indices"][0]) < 0 else g["export_indices"].astype(np.uint64)
+    ex = loop.get_properties(idx)
+    assert ex["particle_values"].shape == g["export_pv"].shape
+    assert np.array_equal(ex["particle_values"], g["export_pv"]), "exported particle properties"
+    assert np.array_equal(ex["ages"], g["export_ages"]), "exported ages"
+    if sv_rtol == 0.0:
+        assert np.array_equal(ex["spatial_values"], g["export_sv"]), "per-compartment sums"
+    else:
+        np.testing.assert_allclose(ex["spatial_values"], g["export_sv"], rtol=sv_rtol, atol=0)
+
+
 def test_fixtures_present():
     assert len(NAMES) >= 12, NAMES
     g = _load("monod_cma")
@@ -114,6 +127,7 @@ def test_oracle_reproduces_reference_fixture(orc, name):
     _feed(o, g)
     o.set_quirk_contrib_return(True)   # the reference's contribution loop, bug for bug (Q2): sources match on EVERY step
     _check_against_golden(o, g, sources="all")
+    _check_export(o, g)
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -261,6 +275,8 @@ def test_cuda_reproduces_reference_fixture(bmc, name):
     # newborn's drawn properties); everything else is bit-exact
     exact = g["model"] != "simple_acetate"
     _check_against_golden(loop, g, exact_props=exact, sources="quirk_free", prop_rtol=1e-5)
+    if exact:
+        _check_export(loop, g, sv_rtol=1e-12)   # the device sums the per-compartment values with fp64 atomics: order differs
 
 
 def test_timing_build_runs_threaded_under_omp_num_threads_1(synth):

@@ -42,6 +42,10 @@ CASES = {
 }
 
 
+# the models' get_number() (partial exports) — None = HasExportPropertiesFull (all properties)
+EXPORT_INDICES = {"fixed_length": [0], "monod": [0, 2, 3], "simple_acetate": None, "udf_model": [0]}
+
+
 def run_case(name, synth):
     model, n, n_comp, steps, ppt, kw = CASES[name]
     kw = dict(kw)
@@ -77,6 +81,10 @@ def run_case(name, synth):
             st = loop.get_particles()
             out[f"props_{s}"] = st["props"]; out[f"pos_{s}"] = st["position"].astype(np.uint32); out[f"status_{s}"] = st["status"]
             out[f"age_hyd_{s}"] = st["age_hyd"]; out[f"age_div_{s}"] = st["age_div"]
+    # PostProcessing::get_properties at the end of the run (forces a compaction): what the exporters write
+    ex = loop.get_properties()
+    out["export_pv"] = ex["particle_values"]; out["export_sv"] = ex["spatial_values"]; out["export_ages"] = ex["ages"]
+    out["export_indices"] = np.array(EXPORT_INDICES[model] if EXPORT_INDICES[model] is not None else [-1], np.int64)
     out["snap_steps"] = np.array(sorted({0, steps // 2, steps - 1}))
     out["sources"] = np.array(srcs); out["counters"] = np.array(counters, np.uint64)
     out["inactive_before"] = np.array(inactive_before, np.uint64)
