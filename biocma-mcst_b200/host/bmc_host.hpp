@@ -185,8 +185,15 @@ class MonteCarloUnit {
     bmc_config cfg{};
     cfg.device = device; cfg.model = model; cfg.n_var_udf = n_var_udf; cfg.n_species = n_species;
     cfg.n_compartments = n_compartments; cfg.seed = seed; cfg.rank = rank;
-    if (const char* e = std::getenv("BIOMC_MC_ALLOC_FACTOR")) cfg.allocation_factor = std::atof(e);          // unit.cpp:313-337
-    if (const char* e = std::getenv("BIOMC_MC_BUFFER_RATIO")) cfg.buffer_ratio = std::atof(e);
+    // load_tuning_constant (mc/src/unit.cpp:302-343): a value outside (min, max] is ignored (read_env_valid_or, :28-41)
+    auto valid_or = [](const char* name, double vdefault, double lo, double hi) {
+      const char* e = std::getenv(name);
+      if (!e) return vdefault;
+      const double v = std::atof(e);
+      return (v > lo && v <= hi) ? v : vdefault;
+    };
+    cfg.allocation_factor = valid_or("BIOMC_MC_ALLOC_FACTOR", 0.0, 0., 5.);   // 0 = the library's default
+    cfg.buffer_ratio = valid_or("BIOMC_MC_BUFFER_RATIO", 0.0, 0., 1.);
     if (const char* e = std::getenv("BIOMC_MC_REMOVE_RATIO_THRESHOLD")) cfg.dead_particle_ratio_threshold = std::atof(e);
     if (const char* e = std::getenv("BIOMC_MC_MINIMUM_REMOVAL")) cfg.minimum_dead_particle_removal = std::strtoull(e, nullptr, 10);
     if (bmc_create(&ctx, &cfg) != BMC_OK) throw std::runtime_error("bmc_create failed");
