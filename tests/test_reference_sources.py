@@ -153,6 +153,8 @@ def _ref_or_skip():
     ("simple_acetate", 3000, 8, 512, dict(near_division=0.5, p_exit=0.1, p_move=0.1, dt=20.0, seed=13)),
     ("monod", 2300, 1, 256, dict(near_division=0.5, p_exit=0.05, dt=20.0, seed=17)),
     ("udf_model", 2600, 12, 512, dict(near_division=0.5, p_exit=0.2, p_move=0.1, dt=20.0, seed=19)),
+    # BASELINE configs[1] shape: 500 compartments, monod, the reference's default 1024 particles per team
+    ("monod", 60_000, 500, 1024, dict(near_division=0.5, p_exit=0.3, p_move=0.05, dt=20.0, seed=29)),
 ])
 def test_live_reference_equals_oracle(orc, synth, model, n, n_comp, ppt, kw):
     ref = _ref_or_skip()
