@@ -61,6 +61,16 @@ def _declare(L):
     L.ref_init_particles.argtypes = [vp, u64, ctypes.c_int, vp, ctypes.POINTER(dbl)]
     L.ref_sample.argtypes = [ctypes.c_int, u64, u64, dbl, dbl, dbl, dbl, vp]
     L.ref_get_properties.argtypes = [vp, vp, vp, vp, ctypes.POINTER(u64), ctypes.POINTER(u64)]
+    if hasattr(L, "ref_unit_init"):  # checker build only
+        L.ref_unit_init.restype = vp
+        L.ref_unit_init.argtypes = [ctypes.c_int, u64, vp, u64, ctypes.c_int, u64, u32, vp, dbl]
+        L.ref_unit_destroy.argtypes = [vp]; L.ref_unit_destroy.restype = None
+        L.ref_unit_total_mass.argtypes = [vp]; L.ref_unit_total_mass.restype = dbl
+        L.ref_unit_weight.argtypes = [vp]; L.ref_unit_weight.restype = dbl
+        L.ref_unit_n_particle.argtypes = [vp]; L.ref_unit_n_particle.restype = u64
+        L.ref_unit_get.argtypes = [vp, ctypes.c_int, u64, vp, vp, vp]
+        L.ref_unit_repartition.argtypes = [vp, vp, u64]
+        L.ref_load_tuning_constant.argtypes = [vp]; L.ref_load_tuning_constant.restype = None
     L.ref_set_threads.argtypes = [ctypes.c_int]; L.ref_set_threads.restype = None
     L.ref_max_threads.restype = ctypes.c_int
     return L
@@ -103,6 +113,36 @@ def sample(kind, seed, n, p0=0.0, p1=0.0, p2=0.0, p3=0.0):
     rc = lib().ref_sample(SAMPLE_KINDS[kind], seed, n, p0, p1, p2, p3, _ptr(out))
     assert rc == 0
     return out
+
+
+def unit_init(model, n, volumes, *, uniform=True, seed=2024, rank=0, linit=None, x0=0.5):
+    """The reference's own MC::init<Model> + post_init_weight + getRepartition (mcinit.hpp, mc/src/unit.cpp), for the
+    models of its container variant (fixed_length, simple_acetate).  Returns the initialised unit's content."""
+    L = lib()
+    mid = MODEL_IDS[model]
+    n_var = {0: 2, 2: 9}[mid]
+    vol = np.ascontiguousarray(volumes, np.float64)
+    lin = None if linit is None else np.ascontiguousarray(linit, np.float32)
+    h = L.ref_unit_init(mid, int(n), _ptr(vol), vol.size, int(bool(uniform)), int(seed), int(rank), _ptr(lin), float(x0))
+    if not h:
+        raise RuntimeError("MC::init failed")
+    try:
+        props = np.empty((n_var, n), np.float32); pos = np.empty(n, np.uint64); w = ctypes.c_float()
+        assert L.ref_unit_get(h, mid, int(n), _ptr(props), _ptr(pos), ctypes.byref(w)) == 0
+        rep = np.zeros(vol.size, np.uint64)
+        assert L.ref_unit_repartition(h, _ptr(rep), vol.size) == 0
+        return dict(props=props, position=pos, total_mass=L.ref_unit_total_mass(h), init_weight=L.ref_unit_weight(h),
+                    weight_f32=w.value, repartition=rep, n_particle=int(L.ref_unit_n_particle(h)))
+    finally:
+        L.ref_unit_destroy(h)
+
+
+def load_tuning_constant():
+    """MC::load_tuning_constant (mc/src/unit.cpp:302-343) with the current environment"""
+    out = np.zeros(5)
+    lib().ref_load_tuning_constant(_ptr(out))
+    return dict(minimum_dead_particle_removal=int(out[0]), buffer_ratio=out[1], allocation_factor=out[2], shrink_ratio=out[3],
+                dead_particle_ratio_threshold=out[4])
 
 
 class RefLoop:

@@ -64,6 +64,7 @@ struct RngConfig { uint32_t key[2] = {0, 0}; uint32_t rank = 0, step = 0; Kokkos
 RngConfig g_cfg;
 thread_local Kokkos::shim::RngState t_rng;
 int g_threads = 1;
+bool g_init_kernel = false;
 // BMC_REF_PROFILE=1: seconds per kernel label, printed by ref_destroy (tuning aid)
 const bool g_profile = std::getenv("BMC_REF_PROFILE") != nullptr;
 std::map<std::string, double> g_times; std::string g_label; std::chrono::steady_clock::time_point g_t0;
@@ -82,17 +83,24 @@ int n_threads() { return g_threads; }
 void set_threads(int n) { g_threads = n < 1 ? 1 : n; }
 void kernel_begin(const std::string& label) {
   if (g_profile) { g_label = label; g_t0 = std::chrono::steady_clock::now(); }
+  g_init_kernel = label == "mc_init_first";  // InitFunctor (mc/src/unit.cpp:102-144): one stream per visited particle
   if (label == "cycle_move") g_cfg.mode = Mode::MoveTape;
   else if (label == "cycle_move_leave") g_cfg.mode = Mode::Leave;
   else g_cfg.mode = Mode::Sequential;
 }
 void kernel_end() {
-  g_cfg.mode = Mode::Sequential;
+  g_cfg.mode = Mode::Sequential; g_init_kernel = false;
   if (g_profile) g_times[g_label] += std::chrono::duration<double>(std::chrono::steady_clock::now() - g_t0).count();
 }
 void team_begin(size_t league_rank) { RngState& r = synced(); r.league = league_rank; r.tape = 0; }
-void range_index(size_t i) { RngState& r = synced(); r.index = i; }
+void range_index(size_t i) {
+  RngState& r = synced(); r.index = i;
+  if (g_init_kernel) r.start_sequence((uint32_t)i, 2u);  // M::init, then KPRNG::uniform_u, continue this stream
+}
 }  // namespace Kokkos::shim
+
+// oracle/ref_unit.cpp: streams of the reference's own MC::init (step id 0xFFFFFFFF is reserved for initialisation)
+void ref_unit_stream_setup(uint64_t seed, uint32_t rank) { set_streams(seed, rank, 0xFFFFFFFFu); }
 
 // ------------------------------------------------------------------ model wrappers
 namespace {

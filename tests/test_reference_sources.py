@@ -400,3 +400,42 @@ def test_stochastic_mode_cuda_vs_reference_kernels(bmc, synth, model):
         g = bmc.ParticleLoop(model, case["n_species"], case["n_comp"], seed=case["seed"])
         util.load_case(r, case); util.load_case(g, case)
         _assert_same_distribution(_run_traj(g, case, 25), _run_traj(r, case, 25), case["n_comp"], check_traj=not outlet)
+
+
+# ----------------------------------------------------------------------------- the unit: MC::init, weight, repartition
+@pytest.mark.parametrize("model", ["fixed_length", "simple_acetate"])
+def test_live_reference_unit_init(orc, model):
+    # the reference's own MC::init<Model> -> impl_init -> initialize_model -> InitFunctor, post_init_weight and
+    # MonteCarloUnit::getRepartition (mcinit.hpp:67-105, mc/src/unit.cpp:102-300), compiled from where they lie
+    ref = _ref_or_skip()
+    n, nc = 3000, 37
+    vol = 0.02 / nc * (0.8 + 0.4 * np.random.default_rng(1).random(nc))
+    lin = (1e-6 + np.random.default_rng(0).random(n) * 1e-6).astype(np.float32)
+    u = ref.unit_init(model, n, vol, seed=99, linit=lin, x0=0.5)
+    o = orc.OracleLoop(model, 2 if model == "simple_acetate" else 1, nc, seed=99)
+    m = o.init_particles(n, True, lin)
+    st = o.get_particles(n)
+    assert m == u["total_mass"]
+    assert np.array_equal(st["props"].view(np.uint32), u["props"].view(np.uint32))
+    assert np.array_equal(st["position"], u["position"])
+    assert np.array_equal(o.repartition(), u["repartition"]) and u["n_particle"] == n
+    # post_init_weight: w = X0 * V_tot / m_tot, stored in a float view (mc/src/unit.cpp:232-257)
+    assert abs(u["init_weight"] - 0.5 * float(np.sum(vol)) / m) <= 1e-15 * u["init_weight"]
+    assert u["weight_f32"] == np.float32(u["init_weight"])
+
+
+def test_live_reference_tuning_constants(monkeypatch):
+    # load_tuning_constant (mc/src/unit.cpp:302-343): a BIOMC_MC_* value outside (min, max] is ignored — the rule the
+    # host layer (biocma-mcst_b200/host/bmc_host.hpp) applies to the same variables
+    ref = _ref_or_skip()
+    for k in ("BIOMC_MC_BUFFER_RATIO", "BIOMC_MC_ALLOC_FACTOR", "BIOMC_MC_MINIMUM_REMOVAL", "BIOMC_MC_SHRINK_RATIO", "BIOMC_MC_REMOVE_RATIO_THRESHOLD"):
+        monkeypatch.delenv(k, raising=False)
+    d = ref.load_tuning_constant()
+    assert d == dict(minimum_dead_particle_removal=0, buffer_ratio=1.0, allocation_factor=2.5, shrink_ratio=0.1, dead_particle_ratio_threshold=0.01)
+    monkeypatch.setenv("BIOMC_MC_BUFFER_RATIO", "1.5")      # > 1: ignored
+    monkeypatch.setenv("BIOMC_MC_ALLOC_FACTOR", "3.0")      # in (0, 5]: taken
+    monkeypatch.setenv("BIOMC_MC_MINIMUM_REMOVAL", "77")
+    d = ref.load_tuning_constant()
+    assert d["buffer_ratio"] == 1.0 and d["allocation_factor"] == 3.0 and d["minimum_dead_particle_removal"] == 77
+    monkeypatch.setenv("BIOMC_MC_ALLOC_FACTOR", "7.0")      # > 5: ignored
+    assert ref.load_tuning_constant()["allocation_factor"] == 2.5
