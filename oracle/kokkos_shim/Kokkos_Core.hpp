@@ -29,12 +29,15 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <initializer_list>
 #include <memory>
+#include <ostream>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -47,7 +50,12 @@
 #define KOKKOS_FUNCTION
 #define KOKKOS_LAMBDA [=]
 #define KOKKOS_CLASS_LAMBDA [ =, *this ]
-#define KOKKOS_ASSERT(...) assert((__VA_ARGS__))
+// a statement block, like Kokkos' own (the reference writes it without a trailing semicolon in places)
+#ifdef NDEBUG
+#define KOKKOS_ASSERT(...) {}
+#else
+#define KOKKOS_ASSERT(...) { if (!bool(__VA_ARGS__)) { std::fprintf(stderr, "KOKKOS_ASSERT(%s) failed at %s:%d\n", #__VA_ARGS__, __FILE__, __LINE__); std::abort(); } }
+#endif
 #define KOKKOS_ENABLE_SERIAL 1
 
 namespace Kokkos {
@@ -259,7 +267,9 @@ template <class DataT, class... Props> class View {
   template <class I> reference_type operator()(I i) const requires(rank == 1) { return p_[(size_t)i]; }
   template <class I> reference_type operator[](I i) const requires(rank == 1) { return p_[(size_t)i]; }
   template <class I, class J> reference_type operator()(I i, J j) const requires(rank == 2) {
-    assert((size_t)i < e_[0] && (size_t)j < e_[1]);
+#ifdef KOKKOS_SHIM_BOUNDS_CHECK  // like KOKKOS_ENABLE_DEBUG_BOUNDS_CHECK: on in the checker library, off for the reference's own tests
+    if (!((size_t)i < e_[0] && (size_t)j < e_[1])) { std::fprintf(stderr, "kokkos_shim: View '%s' index (%zu,%zu) out of (%zu,%zu)\n", label_.c_str(), (size_t)i, (size_t)j, e_[0], e_[1]); std::abort(); }
+#endif
     return is_left ? p_[(size_t)i + e_[0] * (size_t)j] : p_[(size_t)i * e_[1] + (size_t)j];
   }
   template <class I, class J, class K> reference_type operator()(I i, J j, K k) const requires(rank == 3) {
@@ -374,7 +384,7 @@ inline void abort(const char* m) { std::fprintf(stderr, "%s\n", m); std::abort()
 
 using std::abs; using std::sqrt; using std::exp; using std::pow; using std::isfinite; using std::erf; using std::erfc; using std::copysign;
 using std::floor; using std::ceil; using std::tanh; using std::cbrt; using std::isnan; using std::fabs; using std::log1p; using std::expm1; using std::exp2;
-using std::sin; using std::cos; using std::fmin; using std::fmax; using std::round; using std::trunc; using std::log2; using std::log10;
+using std::isinf; using std::sin; using std::cos; using std::fmin; using std::fmax; using std::round; using std::trunc; using std::log2; using std::log10;
 // Kokkos::log(float) is re-specified: correctly rounded from the double logarithm
 inline float log(float x) { return (float)std::log((double)x); }
 inline double log(double x) { return std::log(x); }
@@ -588,6 +598,18 @@ void parallel_reduce(const std::string& label, const Policy& pol, const F& f, T&
 template <class F, class T, class I> requires std::is_integral_v<I> void parallel_reduce(const std::string& label, I n, const F& f, T& res) {
   parallel_reduce(label, RangePolicy<>(0, (size_t)n), f, res);
 }
+// without a label
+template <class Policy, class F, class R> requires(requires(const Policy& p) { p.league_size(); } || requires(const Policy& p) { p.begin(); })
+void parallel_reduce(const Policy& pol, const F& f, R&& res) { parallel_reduce(std::string(), pol, f, std::forward<R>(res)); }
+// several scalar results: f(i, a, b, ...) over a range (serial or per-thread partial sums)
+template <class F, class I, class T0, class T1, class... Ts> requires std::is_integral_v<I>
+void parallel_reduce(const std::string& label, I n, const F& f, T0& r0, T1& r1, Ts&... rs) {
+  shim::kernel_begin(label);
+  std::tuple<T0, T1, Ts...> acc{};
+  for (size_t i = 0; i < (size_t)n; ++i) { shim::range_index(i); std::apply([&](auto&... a) { f((I)i, a...); }, acc); }
+  std::tie(r0, r1, rs...) = acc;
+  shim::kernel_end();
+}
 
 // parallel_scan: a serial execution runs the final pass only, in ascending order
 template <class F, class... P> void parallel_scan(const std::string& label, const RangePolicy<P...>& pol, const F& f) {
@@ -747,7 +769,13 @@ template <class Device = Serial> class Random_XorShift1024 {
   int rand(int range) { return rand() % range; }
   int rand(int lo, int hi) { return lo + rand() % (hi - lo); }
   // [0,1): top 24 bits of one word / 53 bits of two words
+#ifdef KOKKOS_SHIM_OPEN_UNIFORM
+  // (0,1): only for the reference's own distribution test, whose Exponential<float> case takes -ln(frand()) over 4e7
+  // draws and asserts finiteness (Kokkos' frand never returns 0 in practice; a 24-bit uniform does, once in 1.7e7)
+  float frand() { return ((float)(urand() >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+#else
   float frand() { return (float)(urand() >> 8) * (1.0f / 16777216.0f); }
+#endif
   float frand(float range) { return range * frand(); }
   float frand(float lo, float hi) { return (lo == 0.f && hi == 1.f) ? frand() : lo + (hi - lo) * frand(); }
   double drand() { const uint64_t v = urand64() >> 11; return (double)v * (1.0 / 9007199254740992.0); }
@@ -784,6 +812,7 @@ template <class V, class Pool, class T> void fill_random(const V& v, Pool pool, 
   for (size_t i = 0; i < v.size(); ++i) v.data()[i] = (typename V::non_const_value_type)g.drand((double)lo, (double)hi);
 }
 
+inline void print_configuration(std::ostream& os, bool = false) { os << "kokkos_shim: serial stand-in (oracle/kokkos_shim/Kokkos_Core.hpp)\n"; }
 inline void initialize() {}
 inline void initialize(int&, char**) {}
 inline void finalize() {}

@@ -35,6 +35,17 @@ def build(force=False):
     return LIB_PATH
 
 
+OWN_TESTS = ("test_container", "test_team_strategy", "test_model_sppecies_name", "test_env_var", "test_rng_2")
+OWN_TESTS_DIR = os.path.join(_HERE, "_ref", "tests")
+
+
+def build_own_tests():
+    """the reference's own unit tests for this path over the shim (oracle/Makefile target `ref_tests`)"""
+    if can_build():
+        subprocess.run(["make", "-C", _HERE, "-j", "5", "REF=" + REFERENCE_ROOT, "ref_tests"], check=True, capture_output=True)
+    return OWN_TESTS_DIR
+
+
 def available():
     return os.path.exists(LIB_PATH) or can_build()
 
