@@ -35,14 +35,15 @@ def build(force=False):
     return LIB_PATH
 
 
-OWN_TESTS = ("test_container", "test_team_strategy", "test_model_sppecies_name", "test_env_var", "test_rng_2")
+OWN_TESTS = ("test_container", "test_team_strategy", "test_model_sppecies_name", "test_env_var", "test_rng_2", "test_utils_1", "test_feed",
+             "test_load_balancing")
 OWN_TESTS_DIR = os.path.join(_HERE, "_ref", "tests")
 
 
 def build_own_tests():
     """the reference's own unit tests for this path over the shim (oracle/Makefile target `ref_tests`)"""
     if can_build():
-        subprocess.run(["make", "-C", _HERE, "-j", "5", "REF=" + REFERENCE_ROOT, "ref_tests"], check=True, capture_output=True)
+        subprocess.run(["make", "-C", _HERE, "-j", "8", "REF=" + REFERENCE_ROOT, "ref_tests"], check=True, capture_output=True)
     return OWN_TESTS_DIR
 
 
@@ -82,6 +83,7 @@ def _declare(L):
         L.ref_unit_get.argtypes = [vp, ctypes.c_int, u64, vp, vp, vp]
         L.ref_unit_repartition.argtypes = [vp, vp, u64]
         L.ref_load_tuning_constant.argtypes = [vp]; L.ref_load_tuning_constant.restype = None
+        L.ref_uniform_balance.argtypes = [u32, u32, u64]; L.ref_uniform_balance.restype = u64
     L.ref_set_threads.argtypes = [ctypes.c_int]; L.ref_set_threads.restype = None
     L.ref_max_threads.restype = ctypes.c_int
     return L
@@ -146,6 +148,11 @@ def unit_init(model, n, volumes, *, uniform=True, seed=2024, rank=0, linit=None,
                     weight_f32=w.value, repartition=rep, n_particle=int(L.ref_unit_n_particle(h)))
     finally:
         L.ref_unit_destroy(h)
+
+
+def uniform_balance(n_ranks, rank, n):
+    """UniformLoadBalancer(n_ranks).balance(rank, n) — apps/core/src/load_balancing"""
+    return int(lib().ref_uniform_balance(int(n_ranks), int(rank), int(n)))
 
 
 def load_tuning_constant():

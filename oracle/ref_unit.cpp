@@ -16,6 +16,7 @@
 // =============================================================================
 #include <Kokkos_Core.hpp>
 #include <Kokkos_sampling/metropolis.hpp>
+#include <load_balancing/impl_lb.hpp>  // UniformLoadBalancer (apps/core/src/load_balancing/impl_lb.cpp, iload_balancer.cpp:26-49)
 #include <mc/mcinit.hpp>
 #include <models/fixed_length.hpp>
 #include <models/simple_acetate.hpp>
@@ -86,6 +87,11 @@ int ref_unit_repartition(void* p, uint64_t* out, uint64_t n_comp) {
     std::memcpy(out, r.data(), n_comp * 8);
   } catch (const std::exception& e) { h->err = e.what(); return -1; }
   return 0;
+}
+// ILoadBalancer::balance with the uniform strategy: particles of `rank` out of n over n_ranks (global_initaliser.cpp:275-279)
+uint64_t ref_uniform_balance(uint32_t n_ranks, uint32_t rank, uint64_t n) {
+  UniformLoadBalancer lb(n_ranks);
+  return lb.balance(rank, n);
 }
 // {minimum_dead_particle_removal, buffer_ratio, allocation_factor, shrink_ratio, dead_particle_ratio_threshold}
 void ref_load_tuning_constant(double* out5) {

@@ -6,6 +6,9 @@ hold; these are those tests themselves, executed against the reference's code on
   apps/libs/mc/tests/test_team_strategy.cpp        every particle visited exactly once for the team / chunk strategies
   apps/libs/mc/tests/test_model_sppecies_name.cpp  species-name extraction of the model concept
   apps/libs/common/tests/test_env_var.cpp          read_env / read_env_or / set_local_env
+  apps/libs/models/tests/test_utils_1.cpp          helpers of models/utils.hpp
+  apps/libs/simulation/tests/test_feed.cpp         feed laws (constant, step, pulse, exponential) of feed_descriptor.cpp
+  apps/core/tests/test_load_balancing.cpp          particle shares of the load balancers (the rule sharding.py restates)
   apps/libs/mc/tests/test_rng_2.cpp                moments (mean, variance, skewness) of Normal, LogNormal, SkewNormal,
                                                    TruncatedNormal (several), Exponential<float>, norminv: 4e7 samples per law,
                                                    5 % tolerance, drawn from the generator the parity tests use (Philox streams
@@ -30,7 +33,8 @@ def _exe(name):
     return path
 
 
-@pytest.mark.parametrize("name", ["test_container", "test_team_strategy", "test_model_sppecies_name", "test_env_var"])
+@pytest.mark.parametrize("name", ["test_container", "test_team_strategy", "test_model_sppecies_name", "test_env_var", "test_utils_1",
+                                  "test_feed", "test_load_balancing"])
 def test_reference_unit_test_passes_on_the_shim(name, tmp_path):
     r = subprocess.run([_exe(name)], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
@@ -42,3 +46,16 @@ def test_reference_distribution_moments_pass_on_the_shim(tmp_path):
     r = subprocess.run([_exe("test_rng_2")], cwd=str(tmp_path), capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
     assert r.stderr.count("Test  ") >= 60 and "Failed" not in r.stderr
+
+
+def test_sharding_rule_equals_the_reference_load_balancer(bmc):
+    # biocma-mcst_b200/sharding.py against UniformLoadBalancer::balance itself (iload_balancer.cpp:26-49)
+    if not ref.available():
+        pytest.skip("oracle/_ref/libbmc_ref.so absent and /root/reference not mounted")
+    import importlib
+    sharding = importlib.import_module("biocma_mcst_b200.sharding")
+    for n in (1, 7, 1000, 10**7 + 3, 10**9 + 1, 2 * 10**9 + 5):
+        for world in (1, 2, 3, 4, 8):
+            got = [sharding.shard_count(n, r, world) for r in range(world)]
+            want = [ref.uniform_balance(world, r, n) for r in range(world)]
+            assert got == want and sum(got) == n, (n, world, got, want)
