@@ -38,3 +38,40 @@ def allreduce_sources_torch(sources, group=None):
     t = torch.from_numpy(np.ascontiguousarray(sources, np.float64))
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t.numpy()
+
+
+def setup_peer_allreduce(loop, world, rank, device=None, group=None, log=None):
+    """Collective set-up of the peer-memory all-reduce (bmc_p2p_export / bmc_p2p_attach) over torch.distributed: every
+    rank exports its 64-byte IPC handle, the handles are all-gathered, every rank attaches.  The decision is collective:
+    if ANY rank fails to export or attach, every rank calls p2p_disable() and stays on the NCCL communicator.
+    Returns True when the peer path is active on all ranks.  `device`: where the exchanged tensors live (cuda for NCCL
+    groups, None/cpu for gloo)."""
+    import torch
+    import torch.distributed as dist
+    ok = 1
+    try:
+        mine = torch.from_numpy(np.ascontiguousarray(loop.p2p_export(), np.uint8).copy())
+    except RuntimeError as e:
+        if log:
+            log(f"rank {rank}: peer export failed ({e})")
+        ok, mine = 0, torch.zeros(64, dtype=torch.uint8)
+    if device is not None:
+        mine = mine.to(device)
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=group)
+    if ok:
+        try:
+            loop.p2p_attach(world, rank, torch.stack(gathered).cpu().numpy())
+        except RuntimeError as e:
+            if log:
+                log(f"rank {rank}: peer attach failed ({e})")
+            ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32)
+    if device is not None:
+        flag = flag.to(device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    active = int(flag.item()) == 1
+    if not active:
+        loop.p2p_disable()
+    dist.barrier(group=group)
+    return active

@@ -71,3 +71,56 @@ def test_two_rank_source_allreduce_matches_single_rank(orc, synth):
     assert counts == [30_001, 30_000]
     assert np.allclose(total, ref, rtol=1e-12, atol=0)
     assert n_tot == o.counters()["n_used"]  # same number of divisions in total
+
+
+# ---- collective set-up of the peer-memory all-reduce (sharding.setup_peer_allreduce): handle exchange and the
+# all-or-nothing fallback, with a stand-in for the context (the real one needs a GPU: tests/test_p2p_allreduce_gpu.py)
+class _FakeLoop:
+    def __init__(self, rank, fail_attach):
+        self.rank, self.fail_attach, self.attached, self.disabled = rank, fail_attach, None, False
+
+    def p2p_export(self):
+        return np.full(64, 17 + self.rank, np.uint8)
+
+    def p2p_attach(self, world, rank, handles):
+        if self.fail_attach:
+            raise RuntimeError("cudaIpcOpenMemHandle: simulated failure")
+        self.attached = np.asarray(handles).reshape(world, 64).copy()
+
+    def p2p_disable(self):
+        self.disabled = True
+
+
+def _peer_worker(rank, world, port, fail_rank, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from _bmc_loader import load_pkg
+    load_pkg()
+    from biocma_mcst_b200 import sharding
+    loop = _FakeLoop(rank, fail_attach=(rank == fail_rank))
+    active = sharding.setup_peer_allreduce(loop, world, rank)
+    rows = None if loop.attached is None else loop.attached[:, 0].tolist()
+    q.put((rank, active, loop.disabled, rows))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_rank", [-1, 1])
+def test_peer_allreduce_setup_is_all_or_nothing(fail_rank):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31000 + (os.getpid() + 7 * (fail_rank + 2)) % 2000
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, fail_rank, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, active, disabled, rows in got:
+        if fail_rank < 0:   # every rank sees every handle, in rank order, and keeps the peer path
+            assert active and not disabled and rows == [17, 18]
+        else:               # one rank could not attach: nobody uses the peer path
+            assert not active and disabled
