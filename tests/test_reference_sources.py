@@ -159,8 +159,9 @@ def _ref_or_skip():
 def test_live_reference_equals_oracle(orc, synth, model, n, n_comp, ppt, kw):
     ref = _ref_or_skip()
     case = util.make_case(synth, model, n, n_comp, **kw)
-    o = orc.OracleLoop(model, case["n_species"], n_comp, seed=case["seed"])
-    r = ref.RefLoop(model, case["n_species"], n_comp, seed=case["seed"], particles_per_team=ppt)
+    shard = case["seed"] % 4   # the rank word of the stream counters (one shard of a multi-GPU run)
+    o = orc.OracleLoop(model, case["n_species"], n_comp, seed=case["seed"], rank=shard)
+    r = ref.RefLoop(model, case["n_species"], n_comp, seed=case["seed"], rank=shard, particles_per_team=ppt)
     util.load_case(o, case); util.load_case(r, case)
     o.set_quirk_contrib_return(True)
     for s in range(10):
