@@ -290,26 +290,10 @@ def main():
         want_p2p = os.environ.get("BMC_P2P", "auto")
         use_p2p = want_p2p == "1" or (want_p2p == "auto" and world >= int(os.environ.get("BMC_P2P_MIN_RANKS", "4")))
         if use_p2p and world <= 16:
-            ok = 1
-            try:
-                mine = torch.from_numpy(loop.p2p_export().copy()).cuda()
-            except RuntimeError:
-                ok, mine = 0, torch.zeros(64, dtype=torch.uint8, device="cuda")
-            gathered = [torch.empty_like(mine) for _ in range(world)]
-            dist.all_gather(gathered, mine)
-            if ok:
-                try:
-                    loop.p2p_attach(world, rank, torch.stack(gathered).cpu().numpy())
-                except RuntimeError as e:
-                    print(f"[bench] rank {rank}: peer attach failed ({e}); NCCL", file=sys.stderr)
-                    ok = 0
-            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            if int(flag.item()) == 1:
+            from biocma_mcst_b200 import sharding
+            if sharding.setup_peer_allreduce(loop, world, rank, device=torch.device("cuda", local),
+                                             log=lambda m: print(f"[bench] {m}; NCCL", file=sys.stderr)):
                 collective = "1 peer-memory all-reduce/step (one-shot over NVLink, NCCL only for set-up)"
-            else:
-                loop.p2p_disable()
-            dist.barrier()
     stream = torch.cuda.ExternalStream(loop.stream_handle(), device=torch.device("cuda", local))
 
     def barrier():
