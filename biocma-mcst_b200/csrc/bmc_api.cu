@@ -1027,7 +1027,8 @@ int bmc_checkpoint_load(bmc_ctx* ctx, const void* buffer, uint64_t bytes) {
   }
   const uint64_t n = h.n_used, tab = h.tab_entries;
   if (h.lazy_ages ? (tab != h.step + 2) : (tab != 0)) { ctx->err = "bmc_checkpoint_load: inconsistent age tables"; return BMC_ERR_INVALID; }
-  if (bytes < ckpt_bytes(ctx, n, tab)) { ctx->err = "bmc_checkpoint_load: truncated buffer"; return BMC_ERR_RANGE; }
+  // (n, tab <= bytes first: a corrupt header must not wrap the size computation)
+  if (n > bytes || tab > bytes || bytes < ckpt_bytes(ctx, n, tab)) { ctx->err = "bmc_checkpoint_load: truncated buffer"; return BMC_ERR_RANGE; }
   CK(cudaStreamSynchronize(ctx->stream));
   int rc;
   ctx->seed = h.seed; ctx->rank = (uint32_t)h.rank; ctx->weight = (float)h.weight;
