@@ -1,0 +1,50 @@
+"""Compile-time resource budget of the step kernel (no GPU needed: cuobjdump reads the built library).
+
+The 1024-thread variant only fits one block per SM with 64 registers per thread; an innocent-looking edit that pushes
+live state into local memory costs real time (a multi-step outer loop tried in session 3 took the kernel from an
+8-byte to a 168-byte stack frame and the step from 108 to 118 us).  This test makes such a change visible
+before it reaches a GPU."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "biocma-mcst_b200", "libbmc_b200.so")
+
+
+def _usage():
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe) or not os.path.exists(LIB):
+        pytest.skip("cuobjdump or the built library not available")
+    out = subprocess.run([exe, "-res-usage", LIB], capture_output=True, text=True, timeout=300).stdout
+    res = {}
+    for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", out):
+        res[m.group(1)] = dict(reg=int(m.group(2)), stack=int(m.group(3)), shared=int(m.group(4)), local=int(m.group(5)))
+    return res
+
+
+def test_wide_models_have_a_spill_free_variant():
+    # simple_acetate (9 properties, 2 source terms) does not fit 64 registers: its 512-thread variant (<= 128) must be clean
+    res = _usage()
+    hits = {k: v for k, v in res.items() if "cycle_kernelINS_13SimpleAcetateELi4ELi2ELb0ELb1" in k}
+    assert hits
+    for k, v in hits.items():
+        assert v["reg"] <= 128 and v["stack"] == 0 and v["local"] == 0, (k, v)
+
+
+@pytest.mark.parametrize("model", ["Monod", "FixedLength"])
+def test_step_kernel_register_and_stack_budget(model):
+    res = _usage()
+    # cycle_kernel<Model, VEC=4, WB, PIPE=false, LAZY=true>: WB 4 -> 1024 threads x <= 64 registers, WB 3 -> 768 x <= 80
+    for wb, max_reg in ((4, 64), (3, 80)):
+        hits = {k: v for k, v in res.items() if f"cycle_kernelINS_{len(model)}{model}ELi4ELi{wb}ELb0ELb1" in k}
+        if not hits:
+            continue   # variant not instantiated for this model
+        for k, v in hits.items():
+            assert v["reg"] <= max_reg, (k, v)
+            assert v["stack"] <= 16 and v["local"] == 0, (k, v)          # a handful of spilled invariants at most
+            assert v["shared"] <= 14 * 1024, (k, v)                      # static shared memory reserve of configure_launch
+    assert any(f"{model}ELi4ELi4ELb0ELb1" in k for k in res), "default variant missing"
