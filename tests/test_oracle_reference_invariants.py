@@ -250,3 +250,19 @@ def test_ode_step_mass_conservation(orc, synth):
     Cu = np.full(64, 2.0); mu_ = Cu * vol
     orc.ode_step(Cu, mu_, vol, z, z, fm["coo"], 0.1)
     assert np.allclose(Cu, 2.0, rtol=1e-12)
+
+
+def test_zero_d_case_matches_the_reference_fixture(synth):
+    # apps/api/tests/data/0d/: the reference's own 0D case (rcmtool raw files: u32 count + f64 values).  Its liquid volume,
+    # 0.02 m3, is what the synthetic 0D flow map uses; its single flow entry is zero (batch).
+    import os
+    import struct
+    d = "/root/reference/apps/api/tests/data/0d"
+    if not os.path.isdir(d):
+        pytest.skip("/root/reference not mounted")
+    n, v = struct.unpack("<Id", open(os.path.join(d, "vofL.raw"), "rb").read())
+    assert n == 1 and v == 0.02
+    fm = synth.make_flowmap(1, 0.1)
+    assert fm["volumes"].shape == (1,) and fm["volumes"][0] == v and float(fm["out_flows"][0]) == 0.0
+    nr, ncol = struct.unpack("<II", open(os.path.join(d, "flowL.raw"), "rb").read()[:8])
+    assert (nr, ncol) == (1, 1)
