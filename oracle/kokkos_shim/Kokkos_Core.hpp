@@ -19,6 +19,9 @@
 //   * Random_XorShift1024_Pool -> Philox4x32-10 streams selected by shim::rng() (the
 //     driver tells the generator which particle / draw block it is serving);
 //   * Kokkos::log(float) -> (float)std::log((double)x).
+// Build switches: KOKKOS_SHIM_BOUNDS_CHECK (View index checks; ON in the parity library, OFF for the reference's own
+// unit tests, like Kokkos' default), KOKKOS_SHIM_XORSHIFT (timing build: an xorshift1024* state per thread instead of
+// the Philox streams), KOKKOS_SHIM_OPEN_UNIFORM (frand in (0,1) for the reference's 4e7-sample distribution test).
 // Written from the public Kokkos API documentation; contains no Kokkos source.
 // =============================================================================
 #pragma once
