@@ -75,3 +75,26 @@ def setup_peer_allreduce(loop, world, rank, device=None, group=None, log=None):
         loop.p2p_disable()
     dist.barrier(group=group)
     return active
+
+
+def global_init_weight(local_total_mass, x0, total_volume, device=None, group=None):
+    """post_init_weight on a sharded population: every rank initialises its shard, the total masses are summed
+    (MPI all-reduce in global_initaliser.cpp:311) and every rank uses w = X0 * V_tot / m_tot (mc/src/unit.cpp:232-257)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(local_total_mass)], dtype=torch.float64)
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return x0 * float(total_volume) / float(t.item())
+
+
+def global_repartition(local_repartition, device=None, group=None):
+    """records/number_particle of the whole job: the per-rank getRepartition() vectors summed"""
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(local_repartition, np.int64).copy())
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy().astype(np.uint64)

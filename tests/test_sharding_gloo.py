@@ -43,8 +43,13 @@ def _worker(rank, world, port, q):
     total = sharding.allreduce_sources_torch(o.get_sources())
     n_tot = np.array([o.counters()["n_used"]], np.float64)
     n_tot = sharding.allreduce_sources_torch(n_tot)
+    # job-wide weight and repartition (global_initaliser.cpp:311)
+    lin_density = np.float32(1000.0) * np.float32(np.pi) * np.float32(0.6e-6) * np.float32(0.6e-6) / np.float32(4.0)
+    local_mass = float(np.sum(case["props"][0, lo:hi].astype(np.float64) * float(lin_density)))
+    w = sharding.global_init_weight(local_mass, 0.5, float(np.sum(fm["volumes"])))
+    rep = sharding.global_repartition(o.repartition())
     if rank == 0:
-        q.put((total, float(n_tot[0]), counts))
+        q.put((total, float(n_tot[0]), counts, w, rep))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -57,7 +62,7 @@ def test_two_rank_source_allreduce_matches_single_rank(orc, synth):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    total, n_tot, counts = q.get(timeout=120)
+    total, n_tot, counts, w, rep = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -71,6 +76,11 @@ def test_two_rank_source_allreduce_matches_single_rank(orc, synth):
     assert counts == [30_001, 30_000]
     assert np.allclose(total, ref, rtol=1e-12, atol=0)
     assert n_tot == o.counters()["n_used"]  # same number of divisions in total
+    # the job-wide weight is the single-rank one (post_init_weight on the summed mass), and so is the repartition: the
+    # set of particles per compartment does not depend on the sharding (moves draw from (seed, rank, slot, step), so the
+    # two runs are different realisations — only the totals are comparable after a step)
+    assert abs(w - case["weight"]) <= 1e-12 * case["weight"]
+    assert int(rep.sum()) == o.counters()["n_used"] - o.counters()["n_inactive"] and rep.shape == (100,)
 
 
 # ---- collective set-up of the peer-memory all-reduce (sharding.setup_peer_allreduce): handle exchange and the
