@@ -61,6 +61,7 @@ struct bmc_ctx {
   std::vector<bmc_leaving_flow> flows;
   // liquid
   double *d_conc = nullptr, *d_sources = nullptr, *d_acc = nullptr;
+  unsigned long long* d_acc_fix = nullptr;  // fixed-point source accumulator (bmc_kernels.cuh, "Scatter")
   double *d_conc_next = nullptr, *d_mass = nullptr; bool mass_dirty = true;
   uint32_t *d_csc_ptr = nullptr, *d_csc_row = nullptr; double* d_csc_val = nullptr; bool transition_set = false;
   std::vector<bmc_feed> feeds; std::vector<double> h_vol;
@@ -75,13 +76,14 @@ struct bmc_ctx {
   // launch config
   int n_sm = 148, grid_cycle = 148, blocks_per_sm = 1; size_t smem_bins = 0; int bins_in_smem = 0;
   uint64_t launches = 0;
-  size_t stage_offset = 0, smem_total = 0; int ctab_in_smem = 0; size_t ctab_offset = 0; int grid_post = 148;
+  size_t queue_offset = 0, smem_total = 0; int ctab_in_smem = 0; size_t ctab_offset = 0; int grid_post = 148;
   int grid_cycle_eager = 148; size_t smem_eager = 0;
   bool fuse_post = true;  // whole step in one cooperative launch (BMC_FUSE_POST=0: particle pass + post_only_kernel)
   // staging
   void* d_stage = nullptr; size_t stage_bytes = 0;
   // profiling
-  bool profile = false; std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events; double prof_ms = 0.0; uint64_t prof_n = 0;
+  bool profile = false; std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events; size_t prof_used = 0;  // pool, reused after bmc_profile_read
+  double prof_ms = 0.0; uint64_t prof_n = 0;
   // step-stamped ages (bmc_kernels.cuh): valid while d_t / outlet configuration stay constant and
   // every age started at zero; otherwise the columns hold floats updated every step ("eager")
   bool lazy_ages = true; bool epoch_set = false; double epoch_dt = 0.0; bool epoch_leave = false;
@@ -210,8 +212,10 @@ static int configure_launch(bmc_ctx* ctx) {
   const size_t smem_budget = (size_t)prop.sharedMemPerBlockOptin;
   const size_t static_reserve = 12 * 1024;  // static shared memory of the step kernel (post-cycle scratch, barriers)
   const size_t ctab_bytes = ctx->n_comp * (size_t)ctx->vt.ct * sizeof(float);
-  const size_t bins_bytes = ctx->n_species * ctx->n_comp * sizeof(double);
-  size_t room = smem_budget > static_reserve + ctx->vt.stage_bytes + 1024 ? smem_budget - static_reserve - ctx->vt.stage_bytes - 1024 : 0;
+  const size_t bins_bytes = ctx->n_species * ctx->n_comp * sizeof(unsigned long long);
+  // one deferred queue per warp (movers / outlet candidates waiting to be handled 32 at a time)
+  const size_t queue_bytes = (size_t)(std::max(ctx->vt.block, ctx->vt.block_eager) / 32) * queue_entries(ctx->vt.vec) * sizeof(uint32_t);
+  size_t room = smem_budget > static_reserve + queue_bytes + 1024 ? smem_budget - static_reserve - queue_bytes - 1024 : 0;
   // first the bins (block-private accumulation instead of L2 atomics per particle), then the table
   // (rebuilt by every block: no pre_step launch, gathers served from shared memory instead of L1/L2)
   ctx->bins_in_smem = (ctx->n_comp > 1 && bins_bytes <= room) ? 1 : 0;
@@ -220,21 +224,23 @@ static int configure_launch(bmc_ctx* ctx) {
   ctx->ctab_in_smem = (ctx->n_comp > 1 && ctab_bytes + 256 <= room) ? 1 : 0;
   if (const char* e = getenv("BMC_CTAB_SMEM")) ctx->ctab_in_smem = (ctx->ctab_in_smem && atoi(e) != 0) ? 1 : 0;  // tuning runs
   ctx->ctab_offset = (ctx->smem_bins + 15) / 16 * 16;
-  ctx->stage_offset = (ctx->ctab_offset + (ctx->ctab_in_smem ? ctab_bytes : 0) + 127) / 128 * 128;
-  ctx->smem_total = ctx->stage_offset + ctx->vt.stage_bytes;
+  ctx->queue_offset = (ctx->ctab_offset + (ctx->ctab_in_smem ? ctab_bytes : 0) + 127) / 128 * 128;
+  ctx->smem_total = ctx->queue_offset + queue_bytes;
   if (ctx->smem_total > smem_budget) { ctx->err = "shared memory budget exceeded"; return BMC_ERR_UNSUPPORTED; }
-  ctx->smem_eager = ctx->stage_offset;  // the eager-age variant loads directly: bins + table only
+  ctx->smem_eager = ctx->smem_total;
   ctx->grid_post = ctx->n_sm;           // cooperative launch: one block per SM is always co-resident
   if (const char* e = getenv("BMC_FUSE_POST")) ctx->fuse_post = atoi(e) != 0;
   const char* env = getenv("BMC_BLOCKS_PER_SM");
   auto grid_of = [&](const void* fn, int block, size_t smem, int& grid, int* occ_out) -> int {
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // always: static shared memory of the kernel counts against the 48 KB default as well
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, block, smem) != cudaSuccess) {
       (void)cudaGetLastError();
       occ = 1;  // JIT kernel handle not accepted by the occupancy query: trust __launch_bounds__(block, 1)
+    } else if (occ < 1) {
+      ctx->err = "step kernel does not fit on an SM (registers / shared memory)"; return BMC_ERR_UNSUPPORTED;
     }
-    if (occ < 1) occ = 1;
     if (env && atoi(env) > 0) occ = std::min(occ, atoi(env));
     grid = std::min(ctx->n_sm * occ, kMaxGrid);
     if (occ_out) *occ_out = occ;
@@ -246,9 +252,9 @@ static int configure_launch(bmc_ctx* ctx) {
   if (getenv("BMC_VERBOSE")) {
     cudaFuncAttributes fa{};
     cudaFuncGetAttributes(&fa, ctx->vt.cycle_fn);
-    fprintf(stderr, "[bmc] step kernel: grid %d (%d blocks/SM x %d SMs) x %d threads, %d regs, smem static %zu + dynamic %zu B (bins %zu, table %s, staging %zu), eager grid %d\n",
+    fprintf(stderr, "[bmc] step kernel: grid %d (%d blocks/SM x %d SMs) x %d threads, %d regs, smem static %zu + dynamic %zu B (bins %zu, table %s, queues %zu), eager grid %d\n",
             ctx->grid_cycle, ctx->blocks_per_sm, ctx->n_sm, ctx->vt.block, fa.numRegs, fa.sharedSizeBytes, ctx->smem_total, ctx->smem_bins,
-            ctx->ctab_in_smem ? "smem" : "global", ctx->vt.stage_bytes, ctx->grid_cycle_eager);
+            ctx->ctab_in_smem ? "smem" : "global", queue_bytes, ctx->grid_cycle_eager);
   }
   return BMC_OK;
 }
@@ -307,6 +313,8 @@ static void fill_post_params(bmc_ctx* ctx, PostParams& ip) {
   ip.buf_cap = ctx->buf_cap;
   ip.tab_div = ctx->d_tab_div; ip.tab_hyd = ctx->d_tab_hyd;
   ip.acc = ctx->d_acc; ip.sources = ctx->d_sources; ip.n_bins = (uint32_t)(ctx->n_species * ctx->n_comp);
+  ip.acc_fix = ctx->d_acc_fix; ip.weight = (double)ctx->weight; ip.n_species = (uint32_t)ctx->n_species; ip.n_c = ctx->vt.n_c;
+  ip.vec = ctx->vt.vec;
   ip.min_removal = ctx->min_removal; ip.dead_ratio = ctx->dead_ratio;
 }
 
@@ -405,12 +413,14 @@ int bmc_create(bmc_ctx** out, const bmc_config* cfg) {
   const size_t nb = ctx->n_species * ctx->n_comp;
   int rc;
   if ((rc = dev_alloc(ctx, &ctx->d_conc, nb)) || (rc = dev_alloc(ctx, &ctx->d_sources, nb)) || (rc = dev_alloc(ctx, &ctx->d_acc, nb)) ||
+      (rc = dev_alloc(ctx, &ctx->d_acc_fix, nb)) ||
       (rc = dev_alloc(ctx, &ctx->d_conc_next, nb)) || (rc = dev_alloc(ctx, &ctx->d_mass, nb)) || (rc = dev_alloc(ctx, &ctx->d_csc_ptr, ctx->n_comp + 1)) ||
       (rc = dev_alloc(ctx, &ctx->d_vol, ctx->n_comp)) || (rc = dev_alloc(ctx, &ctx->d_diag, ctx->n_comp)) ||
       (rc = dev_alloc(ctx, &ctx->d_ctab, ctx->n_comp * (size_t)ctx->vt.ct)) || (rc = dev_alloc(ctx, &ctx->blk_total, kMaxGrid + 1)) ||
       (rc = dev_alloc(ctx, &ctx->blk_gap, kMaxGrid + 1)) || (rc = dev_alloc(ctx, &ctx->blk_idle, kMaxGrid + 1)))
     return fail(rc);
   cudaMemset(ctx->d_conc, 0, nb * 8); cudaMemset(ctx->d_sources, 0, nb * 8); cudaMemset(ctx->d_acc, 0, nb * 8);
+  cudaMemset(ctx->d_acc_fix, 0, nb * 8);
   for (int i = 0; i < bmc_ctx::kPinRing; ++i) {
     if (!ck(cudaMallocHost((void**)&ctx->h_pin_in[i], nb * 8), "cudaMallocHost")) return fail(BMC_ERR_NOMEM);
     if (!ck(cudaEventCreateWithFlags(&ctx->ev_pin_in[i], cudaEventDisableTiming), "cudaEventCreate")) return fail(BMC_ERR_CUDA);
@@ -440,7 +450,7 @@ int bmc_destroy(bmc_ctx** h) {
   if (c->p2p_region) cudaFree(c->p2p_region);
   unload_udf_model(c->vt);
   free_container(c);
-  dev_free(c->d_conc); dev_free(c->d_sources); dev_free(c->d_acc); dev_free(c->d_conc_next); dev_free(c->d_mass);
+  dev_free(c->d_conc); dev_free(c->d_sources); dev_free(c->d_acc); dev_free(c->d_acc_fix); dev_free(c->d_conc_next); dev_free(c->d_mass);
   dev_free(c->d_csc_ptr); dev_free(c->d_csc_row); dev_free(c->d_csc_val);
   dev_free(c->d_vol); dev_free(c->d_diag); dev_free(c->d_cdf);
   dev_free(c->d_ctab); dev_free(c->d_cdf_f); dev_free(c->d_neigh);
@@ -770,7 +780,6 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   int rc;
   if ((rc = grow_if_needed(ctx))) return rc;
   cudaStream_t s = ctx->stream;
-  const uint32_t n_bins = (uint32_t)(ctx->n_species * ctx->n_comp);
   const bool enable_move = ctx->n_comp > 1;        // kernels.hpp:53-55
   const bool enable_leave = !ctx->flows.empty();   // kernels.hpp:56
   if (ctx->lazy_ages) {
@@ -784,6 +793,8 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
     PreParams pp;
     pp.diag = ctx->d_diag; pp.vol = ctx->d_vol; pp.dt = d_t; pp.conc = ctx->d_conc; pp.n_species = (uint32_t)ctx->n_species;
     pp.ctab = ctx->d_ctab; pp.n_comp = (uint32_t)ctx->n_comp; pp.enable_move = enable_move ? 1 : 0;
+    pp.n_flows = (int)ctx->flows.size();
+    for (int i = 0; i < pp.n_flows; ++i) { memset(&pp.outlets[i], 0, sizeof(Outlet)); pp.outlets[i].index = (uint32_t)ctx->flows[i].index; pp.outlets[i].flow = ctx->flows[i].flow; }
     const int grid = (int)std::min<uint32_t>(((uint32_t)ctx->n_comp + 255) / 256, (uint32_t)ctx->n_sm * 2);
     void* pargs[] = {&pp};
     CK(cudaLaunchKernel(ctx->vt.pre_fn, dim3(grid), dim3(256), pargs, 0, s));
@@ -804,12 +815,16 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
     p.outlets[i].dt_flow = d_t * ctx->flows[i].flow;  // (dt * flow), probability_leaving.hpp:28
     p.outlets[i].volume = ctx->flows[i].volume;
   }
-  p.conc = ctx->d_conc; p.n_species = (uint32_t)ctx->n_species; p.sources = ctx->d_sources; p.acc = ctx->d_acc;
+  p.conc = ctx->d_conc; p.n_species = (uint32_t)ctx->n_species; p.sources = ctx->d_sources; p.acc = ctx->d_acc; p.acc_fix = ctx->d_acc_fix;
   p.diag = ctx->d_diag; p.vol = ctx->d_vol; p.ctab_in_smem = ctx->ctab_in_smem; p.ctab_offset = (uint32_t)ctx->ctab_offset;
   p.weight = ctx->weight; p.dt = d_t; p.dt_f = (float)d_t;
   p.step = (uint32_t)ctx->host_step; p.rank = ctx->rank; p.seed_lo = (uint32_t)ctx->seed; p.seed_hi = (uint32_t)(ctx->seed >> 32);
   p.enable_move = enable_move; p.enable_leave = enable_leave; p.bins_in_smem = ctx->bins_in_smem;
-  p.stage_offset = (uint32_t)ctx->stage_offset;
+  p.queue_offset = (uint32_t)ctx->queue_offset;
+  // Philox constants of this step's three draw blocks, folded on the host (bmc_rng.cuh)
+  p.ph0 = philox_pre(p.step, 0u, p.rank, p.seed_lo, p.seed_hi);  // u1: leaves its compartment
+  p.ph1 = philox_pre(p.step, 1u, p.rank, p.seed_lo, p.seed_hi);  // u3: outlet test
+  p.ph2 = philox_pre(p.step, 2u, p.rank, p.seed_lo, p.seed_hi);  // u2: neighbour pick
 
   // second phase of the step kernel: compaction (when triggered), newborn insertion, commit
   fill_post_params(ctx, p.post);
@@ -819,8 +834,12 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   p.post.tab_extend = ctx->lazy_ages ? 1 : 0; p.post.enable_leave = enable_leave ? 1 : 0; p.post.dt_f = (float)d_t; p.post.dt = d_t;
 
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (ctx->profile) {
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  if (ctx->profile) {  // event pairs come from a pool that bmc_profile_read recycles: nothing is created in steady state
+    if (ctx->prof_used == ctx->prof_events.size()) {
+      CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+      ctx->prof_events.emplace_back(e0, e1);
+    }
+    e0 = ctx->prof_events[ctx->prof_used].first; e1 = ctx->prof_events[ctx->prof_used].second;
     CK(cudaEventRecord(e0, s));
   }
   // ONE cooperative launch per time step (grid = resident blocks: the grid barrier between the
@@ -840,7 +859,7 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
     CK(cudaLaunchCooperativeKernel((const void*)post_only_kernel, dim3(ctx->grid_post), dim3(kBlock), pargs, 0, s));
     if ((rc = check_launch(ctx, "post_only"))) return rc;
   }
-  if (ctx->profile) { CK(cudaEventRecord(e1, s)); ctx->prof_events.emplace_back(e0, e1); }
+  if (ctx->profile) { CK(cudaEventRecord(e1, s)); ctx->prof_used++; }
   if (enable_leave) ctx->maybe_inactive = true;  // exits may happen from now on
 
   // asynchronous mirror of the device bookkeeping (never waited on here)
@@ -951,7 +970,7 @@ int bmc_get_properties(bmc_ctx* ctx, const uint64_t* indices, uint64_t n_indices
 // ---------------------------------------------------------------------------------------------
 namespace {
 struct CkptHeader {
-  char magic[8];            // "BMCCKPT1"
+  char magic[8];            // "BMCCKPT2"
   uint32_t header_bytes, model, n_var, lazy_ages;
   uint64_t n_species, n_comp, seed, rank, step, n_used, capacity_hint;
   uint64_t inactive, total_out, total_new, n_compactions, last_out, last_dead, last_waiting;
@@ -960,6 +979,7 @@ struct CkptHeader {
   uint64_t min_removal;
   uint32_t epoch_set, epoch_leave;
   uint64_t tab_entries;     // lazy ages: entries of each age table that follow
+  float src_bound[8], src_scale[8];  // fixed-point scatter state (DevState): a resumed run adds up the very same integers
 };
 }  // namespace
 
@@ -973,7 +993,7 @@ int bmc_checkpoint_size(bmc_ctx* ctx, uint64_t* bytes) {
   CK(cudaSetDevice(ctx->device));
   DevState hs; int rc;
   if ((rc = sync_state(ctx, &hs))) return rc;
-  *bytes = ckpt_bytes(ctx, hs.n_used, ctx->lazy_ages ? ctx->host_step + 2 : 0);
+  *bytes = ckpt_bytes(ctx, hs.n_used, ctx->lazy_ages ? ctx->host_step + 1 : 0);
   return BMC_OK;
 }
 
@@ -982,11 +1002,12 @@ int bmc_checkpoint_save(bmc_ctx* ctx, void* buffer, uint64_t bytes) {
   CK(cudaSetDevice(ctx->device));
   DevState hs; int rc;
   if ((rc = sync_state(ctx, &hs))) return rc;
-  const uint64_t n = hs.n_used, tab = ctx->lazy_ages ? ctx->host_step + 2 : 0;
+  // entries [0, host_step] of the age tables are written (bmc_cycle guarantees host_step + 1 allocated entries)
+  const uint64_t n = hs.n_used, tab = ctx->lazy_ages ? ctx->host_step + 1 : 0;
   if (bytes < ckpt_bytes(ctx, n, tab)) { ctx->err = "bmc_checkpoint_save: buffer too small (see bmc_checkpoint_size)"; return BMC_ERR_RANGE; }
   CkptHeader h;
   memset(&h, 0, sizeof(h));
-  memcpy(h.magic, "BMCCKPT1", 8);
+  memcpy(h.magic, "BMCCKPT2", 8);
   h.header_bytes = (uint32_t)sizeof(h); h.model = (uint32_t)ctx->model; h.n_var = (uint32_t)ctx->vt.n_var; h.lazy_ages = ctx->lazy_ages ? 1u : 0u;
   h.n_species = ctx->n_species; h.n_comp = ctx->n_comp; h.seed = ctx->seed; h.rank = ctx->rank; h.step = ctx->host_step; h.n_used = n;
   h.capacity_hint = ctx->cap;
@@ -996,6 +1017,7 @@ int bmc_checkpoint_save(bmc_ctx* ctx, void* buffer, uint64_t bytes) {
   h.weight = (double)ctx->weight; h.allocation_factor = ctx->allocation_factor; h.buffer_ratio = ctx->buffer_ratio; h.dead_ratio = ctx->dead_ratio;
   h.epoch_dt = ctx->epoch_dt; h.min_removal = ctx->min_removal; h.epoch_set = ctx->epoch_set ? 1u : 0u; h.epoch_leave = ctx->epoch_leave ? 1u : 0u;
   h.tab_entries = tab;
+  for (int i = 0; i < 8; ++i) { h.src_bound[i] = hs.src_bound[i]; h.src_scale[i] = hs.src_scale[i]; }
   unsigned char* o = (unsigned char*)buffer;
   memcpy(o, &h, sizeof(h)); o += sizeof(h);
   cudaStream_t s = ctx->stream;
@@ -1020,13 +1042,13 @@ int bmc_checkpoint_load(bmc_ctx* ctx, const void* buffer, uint64_t bytes) {
   CK(cudaSetDevice(ctx->device));
   CkptHeader h;
   memcpy(&h, buffer, sizeof(h));
-  if (memcmp(h.magic, "BMCCKPT1", 8) != 0 || h.header_bytes != sizeof(h)) { ctx->err = "bmc_checkpoint_load: not a checkpoint of this version"; return BMC_ERR_INVALID; }
+  if (memcmp(h.magic, "BMCCKPT2", 8) != 0 || h.header_bytes != sizeof(h)) { ctx->err = "bmc_checkpoint_load: not a checkpoint of this version"; return BMC_ERR_INVALID; }
   if (h.model != (uint32_t)ctx->model || h.n_var != (uint32_t)ctx->vt.n_var || h.n_species != ctx->n_species || h.n_comp != ctx->n_comp) {
     ctx->err = "bmc_checkpoint_load: model / dimensions differ from this context (serde.cpp: \"model number of property mismatch\")";
     return BMC_ERR_INVALID;
   }
   const uint64_t n = h.n_used, tab = h.tab_entries;
-  if (h.lazy_ages ? (tab != h.step + 2) : (tab != 0)) { ctx->err = "bmc_checkpoint_load: inconsistent age tables"; return BMC_ERR_INVALID; }
+  if (h.lazy_ages ? (tab != h.step + 1) : (tab != 0)) { ctx->err = "bmc_checkpoint_load: inconsistent age tables"; return BMC_ERR_INVALID; }
   // (n, tab <= bytes first: a corrupt header must not wrap the size computation)
   if (n > bytes || tab > bytes || bytes < ckpt_bytes(ctx, n, tab)) { ctx->err = "bmc_checkpoint_load: truncated buffer"; return BMC_ERR_RANGE; }
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1049,7 +1071,7 @@ int bmc_checkpoint_load(bmc_ctx* ctx, const void* buffer, uint64_t bytes) {
   CK(cudaMemcpyAsync(ctx->age_div, in, n * 4, cudaMemcpyHostToDevice, s)); in += n * 4;
   ctx->lazy_ages = h.lazy_ages != 0; ctx->epoch_set = h.epoch_set != 0; ctx->epoch_dt = h.epoch_dt; ctx->epoch_leave = h.epoch_leave != 0;
   if (ctx->lazy_ages) {
-    if ((rc = ensure_age_tables(ctx, tab))) return rc;
+    if ((rc = ensure_age_tables(ctx, tab + 1))) return rc;  // zero-extended: the next cycle writes entry `tab`
     CK(cudaMemcpyAsync(ctx->d_tab_hyd, in, tab * 4, cudaMemcpyHostToDevice, s)); in += tab * 4;
     CK(cudaMemcpyAsync(ctx->d_tab_div, in, tab * 4, cudaMemcpyHostToDevice, s)); in += tab * 4;
     if (force_eager_ages()) { ctx->host_step = h.step; if ((rc = make_ages_eager(ctx))) return rc; }
@@ -1059,6 +1081,7 @@ int bmc_checkpoint_load(bmc_ctx* ctx, const void* buffer, uint64_t bytes) {
   ds.n_used = n; ds.inactive = h.inactive; ds.total_out = h.total_out; ds.total_new = h.total_new; ds.n_compactions = h.n_compactions;
   ds.last_out = h.last_out; ds.last_dead = h.last_dead; ds.last_waiting = h.last_waiting; ds.step = h.step;
   for (int i = 0; i < 6; ++i) ds.events[i] = h.events[i];
+  for (int i = 0; i < 8; ++i) { ds.src_bound[i] = h.src_bound[i]; ds.src_scale[i] = h.src_scale[i]; }
   CK(cudaMemcpyAsync(ctx->st, &ds, sizeof(ds), cudaMemcpyHostToDevice, s));
   prepare_kernel<<<1, 32, 0, s>>>(ctx->st, (unsigned long long)ctx->cap, (unsigned long long)ctx->buf_cap);
   if ((rc = check_launch(ctx, "prepare"))) return rc;
@@ -1130,12 +1153,11 @@ int bmc_profile_read(bmc_ctx* ctx, double* ms_total, uint64_t* n) {
   if (!ctx) return BMC_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
-  for (auto& pr : ctx->prof_events) {
+  for (size_t i = 0; i < ctx->prof_used; ++i) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) { ctx->prof_ms += ms; ctx->prof_n++; }
-    cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+    if (cudaEventElapsedTime(&ms, ctx->prof_events[i].first, ctx->prof_events[i].second) == cudaSuccess) { ctx->prof_ms += ms; ctx->prof_n++; }
   }
-  ctx->prof_events.clear();
+  ctx->prof_used = 0;
   if (ms_total) *ms_total = ctx->prof_ms;
   if (n) *n = ctx->prof_n;
   ctx->prof_ms = 0.0; ctx->prof_n = 0;

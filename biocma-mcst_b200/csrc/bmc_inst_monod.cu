@@ -3,7 +3,6 @@
 
 namespace bmc {
 bool pick_monod(const std::string& var, bool large, ModelVT& vt) {
-  if (var.size() == 4 && var[1] == '2') return pick_variant<Monod, 2, true>(var, 4, vt);
-  return pick_variant<Monod, 4, true>(var, large ? 3 : 4, vt);  // 1024 threads x 64 registers / 768 x 80 (see kLargePopulation)
+  return pick_variant<Monod, 4>(var, large ? 3 : 4, vt);  // 1024 threads x 64 registers / 768 x 80 (see kLargePopulation)
 }
 }  // namespace bmc

@@ -4,34 +4,23 @@
 // (apps/libs/simulation/public/simulation/simulation.hpp:183-239) is, on the
 // reference, four full passes over the particle arrays (cycle_model,
 // cycle_model_contribs, cycle_move, cycle_move_leave: kernels.hpp:123-224) plus a
-// host synchronisation.  Here it is ONE streaming pass (`cycle_kernel`) over
-// structure-of-arrays state followed by O(events) bookkeeping kernels, with no
-// host synchronisation:
+// host synchronisation.  Here it is ONE cooperative launch (`cycle_kernel`) with no host
+// synchronisation:
 //
-//   pre_step     zero the source accumulators, build the per-compartment table,
-//                clear last step's division bits, fix this step's buffer capacity
-//   cycle        fused model update + division + contribution scatter + move +
-//                outlet exit                      [HBM-bound, dominant kernel];
-//                its last block decides update_and_remove_inactive (the "plan")
-//   compact_*    deterministic stream compaction of exited particles (launched only
-//                when inactive particles can exist; early-exit when not triggered)
-//   post         merge_buffer: append newborns in ascending-mother order, commit
+//   particle pass   one streaming pass over structure-of-arrays state: fused model update +
+//                   division + contribution scatter + move + outlet exit   [HBM-bound, dominant]
+//   grid barrier
+//   post-cycle      publish the source terms, update_and_remove_inactive (deterministic stream
+//                   compaction, only when triggered), merge_buffer (newborns appended in
+//                   ascending-mother order), commit of the device-resident counters
 //
-// Work distribution: a persistent grid (multiple of the SM count); block b owns
-// the contiguous 1024-particle tiles [b*T/G, (b+1)*T/G).  Contiguous ownership
-// lets the block (i) accumulate the per-compartment source terms in shared
-// memory for its whole range and flush once, and (ii) produce block-local
-// prefix sums of division counts so that newborn placement is deterministic
-// without a global scan.
+// Only compartment tables too large for shared memory add a second launch (`pre_step`).
 #pragma once
 #include "bmc_models.cuh"
 #include "bmc_rng.cuh"
 
 namespace bmc {
 
-#ifndef BMC_SCATTER_MODE
-#define BMC_SCATTER_MODE 1  // 1 = shared-memory fp64 bins (product); others are timing experiments
-#endif
 // Cache-streaming ld/st hints (ld.global.cs / st.global.cs) on the particle columns were measured to
 // HURT: with 32 resident warps per SM and more than ~3e7 particles the step becomes 60-90 % slower
 // (1e8 particles, monod: 1620 us with the hints, 855 us without), so plain accesses are the default.
@@ -83,7 +72,11 @@ struct DevState {
   unsigned int done_blocks;         // ticket counter: the last cycle block to finish writes the plan
   unsigned int pad0;
   unsigned int bar_count, bar_gen;  // grid barrier of the cooperatively launched step kernel
-  unsigned int next_group, pad2;    // work counter of the particle pass (groups drawn beyond each warp's first)
+  unsigned int next_group, pad2;    // work counter of the particle pass (groups drawn dynamically)
+  // fixed-point source accumulation of the step kernel (see "Scatter" in cycle_body): per species the
+  // largest |contribution| admitted to the integer bins this step, the power-of-two scale applied to it, and the
+  // running maximum observed this step (float bits; the commit thread derives the next step's bound/scale from it)
+  float src_bound[8]; float src_scale[8]; unsigned int src_max[8];
   unsigned long long dbg[16];       // BMC_TIMELINE builds: %globaltimer stamps of block 0 (tuning only)
 };
 
@@ -124,6 +117,8 @@ struct PostParams {
   const uint32_t* div_mask; uint32_t* tile_off; uint32_t* blk_total;
   unsigned long long buf_cap;
   double* acc; double* sources; uint32_t n_bins;
+  unsigned long long* acc_fix; double weight; uint32_t n_species; int n_c;  // fixed-point bins of the step kernel (publish: sources = w * fix / scale + acc)
+  int vec;  // slots per thread of the step kernel: layout of div_mask (VEC ballot words per group of 32*VEC slots)
   unsigned long long min_removal; double dead_ratio;  // RuntimeParameters of update_and_remove_inactive
   int count_step;  // 1 when called from a cycle, 0 from force_remove_dead
   // step-stamped ages (bmc_kernels.cuh): stamp given to newborns (0 = eager float ages, bits of 0.f)
@@ -151,14 +146,16 @@ struct CycleParams {
   // liquid coupling
   const double* conc; uint32_t n_species;
   double* acc;       // accumulator of the source terms (zero between steps)
+  unsigned long long* acc_fix;  // 64-bit fixed-point accumulator (two's complement, zero between steps)
   double* sources;   // published by the last block: sources = acc, acc = 0
   // compartment table built by every block in shared memory (small n_comp) instead of pre_step
   const double* diag; const double* vol; int ctab_in_smem; uint32_t ctab_offset;
   float weight;
   double dt; float dt_f;
   uint32_t step, rank, seed_lo, seed_hi;
+  PhiloxPre ph0, ph1, ph2;  // host-folded Philox constants of draw blocks 0 (u1), 1 (u3), 2 (u2) for this step (bmc_rng.cuh)
   int enable_move, enable_leave, bins_in_smem;
-  uint32_t stage_offset;  // byte offset of the cp.async staging buffers inside dynamic shared memory
+  uint32_t queue_offset;  // byte offset of the per-warp deferred queues inside dynamic shared memory
   PostParams post;   // second phase of the step (post_cycle_body)
   int fuse_post;     // 1 = run it in this launch behind a grid barrier (cooperative launch), 0 = post_only_kernel follows
 };
@@ -231,23 +228,45 @@ template <> struct VecIO<1> {
 
 
 // -----------------------------------------------------------------------------
-// Compartment table, one row per compartment (n_comp rows — 500 .. 10k — not N):
-//     col 0        ceil_f32(dt * diag_transition / liquid_volume)   leave threshold
-//     col 1..n_pre M::compartment_terms(c, compartment)             optional model hook
+// Compartment table, one row per compartment (n_comp rows — 500 .. 10k — not N), 32-bit words:
+//     col 0        leave threshold as an INTEGER (below)
+//     col 1..n_pre M::compartment_terms(c, compartment)             optional model hook (floats)
 // A model whose update starts with a function of the local concentration only
 // (Monod: mu = mu_max*s/(k_s+s)) hoists it here: the IEEE division then runs once
 // per compartment instead of once per particle, with bit-identical results.
 // Small tables are built by every cycle block in shared memory (no extra launch);
 // pre_step builds large ones in global memory.
+//
+// Leave threshold.  The reference tests (dt*flow/volume) > (double)u1 with a float uniform u1
+// (move_kernel.hpp:407-411).  u1 = n * 2^-24 with n = the top 24 bits of a random word, so
+//     (dt*F/V) > (double)u1  <=>  u1 < ceil_f32(dt*F/V) =: t  <=>  n < t * 2^24  <=>  n < ceil(t * 2^24)
+// (t * 2^24 is exact in single precision).  The table holds that integer, clamped to [0, 2^24], in
+// bits 0..24: the per-particle test is a shift and an integer compare, no conversion.  Bit 31
+// (kOutletBit) marks a compartment whose first matching outlet (find_flow, move_kernel.hpp:113-127)
+// has a non-zero flow, so the particle pass needs no loop over the outlet list either.
 // -----------------------------------------------------------------------------
+constexpr uint32_t kThrMask = 0x01ffffffu;
+constexpr uint32_t kOutletBit = 0x80000000u;
 struct PreParams {
   const double* diag; const double* vol; double dt; const double* conc; uint32_t n_species; float* ctab; uint32_t n_comp;
   int enable_move;
+  int n_flows; Outlet outlets[kMaxFlows];
 };
 
+__device__ __forceinline__ uint32_t leave_threshold(double dt, double diag, double vol) {
+  const float t = __double2float_ru(dt * diag / vol);
+  if (!(t > 0.0f)) return 0u;          // also NaN (0/0): the comparison with a NaN is false for every particle
+  if (t >= 1.0f) return 1u << 24;      // every n < 2^24 passes
+  return (uint32_t)ceilf(t * 16777216.0f);
+}
+
 template <class M> __device__ __forceinline__ void compartment_row(const double* diag, const double* vol, double dt, const double* conc,
-                                                                   uint32_t n_species, int enable_move, uint32_t c, float* row) {
-  row[0] = enable_move ? __double2float_ru(dt * diag[c] / vol[c]) : 0.0f;
+                                                                   uint32_t n_species, int enable_move, const Outlet* outlets, int n_flows,
+                                                                   uint32_t c, float* row) {
+  uint32_t w0 = enable_move ? leave_threshold(dt, diag[c], vol[c]) : 0u;
+  for (int f = 0; f < n_flows; ++f)
+    if (outlets[f].index == c) { if (outlets[f].flow != 0.) w0 |= kOutletBit; break; }
+  row[0] = __uint_as_float(w0);
   if constexpr (M::n_pre > 0) M::compartment_terms(ConcView{conc, n_species, nullptr}, (size_t)c, row + 1);
 }
 
@@ -257,7 +276,7 @@ template <class M> __device__ __forceinline__ void pre_step_body(const PreParams
   const uint32_t nthreads = gridDim.x * blockDim.x;
   for (uint32_t c = i; c < p.n_comp; c += nthreads) {
     float row[CT];
-    compartment_row<M>(p.diag, p.vol, p.dt, p.conc, p.n_species, p.enable_move, c, row);
+    compartment_row<M>(p.diag, p.vol, p.dt, p.conc, p.n_species, p.enable_move, p.outlets, p.n_flows, c, row);
 #pragma unroll
     for (int k = 0; k < CT; ++k) p.ctab[(size_t)c * CT + k] = row[k];
   }
@@ -391,7 +410,15 @@ static __device__ __forceinline__ void post_cycle_body(const PostParams& p) {
   // (not from force_remove_dead: the sources of the last cycle stay what they are)
   if (p.count_step) {
     for (unsigned long long k = gtid; k < p.n_bins; k += gstride) {
-      p.sources[k] = __ldcg(p.acc + k);
+      // fast kernel: integer bins hold sum(c_i * scale) exactly; the fp64 accumulator holds what did not go through them
+      const long long fix = (long long)__ldcg(p.acc_fix + k);
+      double s = __ldcg(p.acc + k);
+      if (fix != 0) {
+        const uint32_t j = (uint32_t)(k % p.n_species);
+        s += (double)fix * (p.weight / (double)__ldcg(&st->src_scale[j < 8u ? j : 7u]));  // scale is a power of two: exact
+        p.acc_fix[k] = 0ull;
+      }
+      p.sources[k] = s;
       p.acc[k] = 0.0;
     }
   }
@@ -522,7 +549,8 @@ static __device__ __forceinline__ void post_cycle_body(const PostParams& p) {
     const uint32_t T = (uint32_t)((old_n + kTile - 1) / kTile);
     const uint32_t t0 = (uint32_t)(((unsigned long long)blockIdx.x * T) / G);
     const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * T) / G);
-    const unsigned long long words_valid = (old_n + 31ull) / 32ull;  // words beyond the last slot are stale
+    const unsigned long long gslots = 32ull * (unsigned long long)p.vec;
+    const unsigned long long words_valid = ((old_n + gslots - 1ull) / gslots) * (unsigned long long)p.vec;  // words of groups beyond the last slot are stale
 #pragma unroll 4
     for (uint32_t t = t0 + warp; t < t1; t += blockDim.x / 32) {
       const unsigned long long wi = (unsigned long long)t * (kTile / 32) + lane;
@@ -552,9 +580,13 @@ static __device__ __forceinline__ void post_cycle_body(const PostParams& p) {
       const uint32_t mother = __ldcg(p.buf_mother + j);
       const uint32_t tile = mother >> 10;
       const unsigned b = (unsigned)((((unsigned long long)tile + 1ull) * G - 1ull) / T);  // owner block of the tile
-      // rank of the mother among the dividing mothers of its tile: all 32 mask words in one round trip
+      // rank of the mother among the dividing mothers of its tile: all 32 mask words in one round trip.
+      // Layout (written by the particle pass): per group of 32*VEC slots VEC ballot words, word q bit l <-> slot
+      // group*32*VEC + l*VEC + q.
       const uint4* w4 = reinterpret_cast<const uint4*>(p.div_mask + (size_t)tile * (kTile / 32));
-      const unsigned wi = (mother & (kTile - 1)) >> 5, bit = mother & 31u;
+      const unsigned in_tile = mother & (kTile - 1);
+      const unsigned vec = (unsigned)p.vec, gsz = 32u * vec;
+      const unsigned gi = in_tile / gsz, l = (in_tile % gsz) / vec, qm = in_tile % vec;
       uint4 w[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) w[q] = __ldcg(w4 + q);
@@ -566,8 +598,11 @@ static __device__ __forceinline__ void post_cycle_body(const PostParams& p) {
         const unsigned ww[4] = {w[q].x, w[q].y, w[q].z, w[q].w};
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const unsigned idx = (unsigned)(4 * q + c);
-          const unsigned m = idx < wi ? 0xffffffffu : (idx == wi ? ((1u << bit) - 1u) : 0u);
+          const unsigned idx = (unsigned)(4 * q + c);       // word index inside the tile
+          const unsigned wg = idx / vec, wq = idx % vec;    // its group and slot-in-thread
+          // slots of word (wg, wq) below the mother: whole word for earlier groups; in the mother's group the lanes
+          // l' < l, plus lane l itself when wq < qm
+          const unsigned m = wg < gi ? 0xffffffffu : (wg == gi ? (((1u << l) - 1u) | (wq < qm ? (1u << l) : 0u)) : 0u);
           rank += __popc(ww[c] & m);
         }
       }
@@ -581,7 +616,7 @@ static __device__ __forceinline__ void post_cycle_body(const PostParams& p) {
   if (threadIdx.x == 0 && atomicAdd(&st->done_blocks, 1u) == gridDim.x - 1) {
     __threadfence();
     st->done_blocks = 0; st->next_group = 0;
-    st->last_out = out; st->last_dead = 0; st->last_waiting = st->step_waiting;
+    if (p.count_step) { st->last_out = out; st->last_dead = 0; st->last_waiting = st->step_waiting; }  // a forced compaction is not a step
     st->total_out += out;
     st->step_exit = 0; st->step_waiting = 0; st->buf_index = 0; st->force_compact = 0;
     st->inactive = do_compact ? 0ull : inactive;
@@ -595,6 +630,25 @@ static __device__ __forceinline__ void post_cycle_body(const PostParams& p) {
     // past the capacity, growth is done lazily by the host
     const unsigned long long room = p.cap > n ? p.cap - n : 0ull;
     st->buf_cap_eff = p.buf_cap < room ? p.buf_cap : room;
+    if (p.count_step) {
+      // Fixed-point scatter of the particle pass: next step's admission bound and scale per species from this step's
+      // largest |contribution| m, with m < 2^e_m and n <= 2^e_n particles:
+      //   bound = 2^(e_m + 2)   a contribution may grow 4x from one step to the next before it takes the fp64 path
+      //   scale = 2^(62 - e_n - e_m - 2)   so that n contributions at the bound stay below 2^62
+      const int e_n = n > 1ull ? 64 - __clzll((long long)(n - 1ull)) : 0;
+      for (int j = 0; j < 8; ++j) {
+        const float m = __uint_as_float(st->src_max[j]);
+        st->src_max[j] = 0u;
+        float bound = 0.0f, scale = 1.0f;  // nothing seen: only exact zeros are admitted (they add nothing)
+        if (j < p.n_c && m > 0.0f && m < 3.0e38f) {
+          int e_m;
+          (void)frexpf(m, &e_m);  // m = f * 2^e_m, 0.5 <= f < 1
+          const int kexp = 62 - e_n - e_m - 2;
+          if (kexp >= -120 && kexp <= 120 && e_m + 2 <= 120 && e_m >= -120) { bound = ldexpf(1.0f, e_m + 2); scale = ldexpf(1.0f, kexp); }
+        }
+        st->src_bound[j] = bound; st->src_scale[j] = scale;
+      }
+    }
     if (p.tab_extend) {  // A[k+1] = fl(A[k] + d_t): exactly the accumulation an eagerly updated age goes through
       p.tab_div[p.tab_idx + 1] = p.tab_div[p.tab_idx] + p.dt_f;                       // model_kernel.hpp:191 (float d_t)
       p.tab_hyd[p.tab_idx + 1] = p.enable_leave ? (float)((double)p.tab_hyd[p.tab_idx] + p.dt)  // move_kernel.hpp:596 (double d_t)
@@ -620,11 +674,20 @@ static __device__ __forceinline__ void post_cycle_body(const PostParams& p) {
 // particles only interact through the atomically allocated division buffer and
 // the additive source terms.
 //
-// Structure of the per-thread body (VEC particles per thread, 128-bit column
-// accesses): the common path — load, model update, age updates, leave/outlet
-// tests — is straight-line code over the VEC particles so that their dependency
-// chains interleave; everything rare (division, the neighbour pick of a mover,
-// the outlet exit draw, partially idle groups) sits behind warp-level votes.
+// Structure.  A warp works on a GROUP of 32*VEC consecutive slots (lane l owns slots
+// l*VEC .. l*VEC+VEC-1: 128-bit column accesses).  The per-group body is straight-line code
+// over the VEC particles of a thread — load, model update, fixed-point scatter, division vote,
+// the two integer tests "leaves its compartment" / "sits in a compartment with an outlet",
+// write-back — so that the dependency chains of the VEC particles interleave.  Everything a
+// particle does RARELY is taken out of that body:
+//   * division (a warp vote guards it; a few groups per thousand);
+//   * move + leave.  About 1 % of the particles change compartment in a step and 1/n_comp of them
+//     sit in an outlet compartment, but with 128 slots per warp three groups out of four contain at
+//     least one such particle, and a divergent branch costs the whole warp.  The body therefore only
+//     QUEUES the slot index of a candidate (warp-private queue in shared memory, ballot + popcount);
+//     whenever 32 candidates are waiting the warp handles them one per lane (`deferred`): Philox
+//     draws, CDF search, outlet test, position / status / age-stamp updates — everything recomputed
+//     from the slot index, because every random draw is a pure function of (slot, step).
 // -----------------------------------------------------------------------------
 __host__ __device__ constexpr int popcount_c(uint64_t x) { return x == 0u ? 0 : (int)(x & 1u) + popcount_c(x >> 1); }
 __host__ __device__ constexpr bool col_flag(uint64_t mask, int k) { return ((mask >> k) & 1ull) != 0ull; }  // k < 64
@@ -634,469 +697,429 @@ template <class M> struct ReadCols {
   static constexpr uint64_t all = M::n_var >= 64 ? ~0ull : ((1ull << M::n_var) - 1ull);
   static constexpr int value = M::n_var - popcount_c((uint64_t)M::write_only_mask & all);
 };
-// One staging buffer of the bulk-copy pipeline holds one GROUP = 32*VEC consecutive slots (the work
-// unit of a warp): pos and the read columns (32*VEC*4 bytes each), then the status bytes.  Every warp
-// has kStages private buffers.  (The pipeline is built for step-stamped ages only: no age column.)
-template <class M, int VEC> struct StageBytes {
-  static constexpr size_t col = (size_t)32 * 4 * VEC;
-  static constexpr size_t warp_stage = (size_t)(1 + ReadCols<M>::value) * col + (size_t)32 * VEC;
-};
-constexpr int kStages = 2;
+// entries of a warp's deferred queue: one group can add 32*VEC candidates to at most 31 waiting ones
+__host__ __device__ constexpr uint32_t queue_entries(int vec) { return 32u * (uint32_t)vec + 32u; }
 
-// ---- mbarrier + TMA bulk copy (cp.async.bulk, 1-D; SASS: UBLKCP) --------------------------------
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(a), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   (unsigned)__cvta_generic_to_shared(smem_dst)),
-               "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
-               : "memory");
-}
+template <int VEC> struct MaskIO;
+template <> struct MaskIO<4> { static __device__ __forceinline__ void st(uint32_t* p, const unsigned (&w)[4]) { *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]); } };
+template <> struct MaskIO<2> { static __device__ __forceinline__ void st(uint32_t* p, const unsigned (&w)[2]) { *reinterpret_cast<uint2*>(p) = make_uint2(w[0], w[1]); } };
+template <> struct MaskIO<1> { static __device__ __forceinline__ void st(uint32_t* p, const unsigned (&w)[1]) { *p = w[0]; } };
 
-template <class M, int VEC, bool PIPE, bool LAZY, int BLOCK> __device__ __forceinline__ void cycle_body(const CycleParams& p) {
+template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ void cycle_body(const CycleParams& p) {
   constexpr int kWarps = BLOCK / 32;
-  static_assert(!PIPE || LAZY, "the bulk-copy pipeline is built for step-stamped ages only");
   constexpr int NV = M::n_var, NC = M::n_c, CT = 1 + M::n_pre;
   constexpr uint32_t kGroup = 32 * VEC;         // slots per group: the work unit of one warp
-  constexpr int kColStride = 32 * 4 * VEC;      // bytes between staged columns of a warp's buffer
-  constexpr size_t kWarpStage = StageBytes<M, VEC>::warp_stage;
-  extern __shared__ __align__(128) double s_bins[];  // [n_species * n_comp] when bins_in_smem, then kStages staging buffers
-  __shared__ unsigned long long s_cnt[4];      // move, exit, new, overflow
+  constexpr unsigned kFull = 0xffffffffu;
+  // dynamic shared memory: [n_species * n_comp] 64-bit source bins when bins_in_smem, the compartment table when
+  // ctab_in_smem, one deferred queue per warp
+  extern __shared__ __align__(128) unsigned long long s_dyn[];
+  __shared__ unsigned s_cnt[4];                // move, exit, new, overflow of this block (rare events: counted with shared atomics)
+  __shared__ unsigned s_fxmax[8];              // largest |contribution| per species seen by this block (float bits)
+  // work distribution (see below): ticket counter + a ring of chunk descriptors
+  constexpr unsigned kRing = 8;
+  __shared__ unsigned s_ticket;
+  __shared__ unsigned s_chunk_base[kRing];     // first group of chunk c (slot c % kRing) ...
+  __shared__ unsigned s_chunk_seq[kRing];      // ... valid when == c + 1
+  __shared__ unsigned s_chunk_left[kRing];     // tickets of the slot's chunk not yet resolved (0 = slot free)
 
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned long long n_used = p.st->n_used;
-  const unsigned long long buf_cap = p.st->buf_cap_eff;
-  // Work distribution: the slots are cut into groups of 32*VEC; every warp of the (persistent,
-  // fully resident) grid starts with the group of its own index and then draws further groups from
-  // a device-wide counter — one L2 atomic per group, issued one group ahead so that its latency is
-  // hidden.  Blocks that start late or run on a slower SM simply process fewer groups.
-  const uint32_t n_groups = (uint32_t)((n_used + kGroup - 1) / kGroup);
+  const uint32_t n_used = (uint32_t)p.st->n_used;  // a context holds fewer than 2^32 slots
+  // Work distribution: the slots are cut into groups of 32*VEC; every warp of the (persistent, fully
+  // resident) grid starts with the group of its own index and then draws further groups dynamically, so
+  // that blocks which start late or run on a slower SM simply process fewer groups.  Two levels: a
+  // BLOCK draws chunks of kWarps consecutive groups from the device-wide counter, its warps draw
+  // single groups of the chunk with a shared-memory ticket.  (One L2 atomic per GROUP on one address
+  // was the limiter of the whole pass: same-address atomics retire at ~0.8 per ns on a B200, i.e.
+  // 78 125 groups of a 1e7-particle step could not be handed out in less than ~95 us — the time per
+  // step divided by the number of groups was the same 1.2 ns for 1e7 and for 1.25e8 particles.)
+  const uint32_t n_groups = (uint32_t)(((unsigned long long)n_used + kGroup - 1) / kGroup);
   const uint32_t total_warps = gridDim.x * kWarps;
   const uint32_t n_bins = p.n_species * p.n_comp;
   const bool single_comp = (p.n_comp == 1);
   const bool smem_bins = p.bins_in_smem && !single_comp;
+  unsigned int* const s_bins = reinterpret_cast<unsigned int*>(s_dyn);  // bin k = words (2k: low, 2k+1: high)
+  uint32_t* const s_ctab = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(s_dyn) + p.ctab_offset);
+  uint32_t* const s_queue = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(s_dyn) + p.queue_offset) + warp * queue_entries(VEC);
 
   BMC_STAMP(p.st, 0);
-  if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0ull;
+  if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
+  if (threadIdx.x < 8) s_fxmax[threadIdx.x] = 0u;
+  if (threadIdx.x < kRing) { s_chunk_seq[threadIdx.x] = 0u; s_chunk_left[threadIdx.x] = 0u; s_chunk_base[threadIdx.x] = 0u; }
+  if (threadIdx.x == 0) s_ticket = 0u;
   if (smem_bins)
-    for (uint32_t k = threadIdx.x; k < n_bins; k += BLOCK) s_bins[k] = 0.0;
-  float* const s_ctab = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_bins) + p.ctab_offset);
+    for (uint32_t k = threadIdx.x; k < n_bins; k += BLOCK) s_dyn[k] = 0ull;
   if (p.ctab_in_smem) {
     for (uint32_t c = threadIdx.x; c < p.n_comp; c += BLOCK) {
       float row[CT];
-      compartment_row<M>(p.diag, p.vol, p.dt, p.conc, p.n_species, p.enable_move, c, row);
+      compartment_row<M>(p.diag, p.vol, p.dt, p.conc, p.n_species, p.enable_move, p.outlets, p.n_flows, c, row);
 #pragma unroll
-      for (int k = 0; k < CT; ++k) s_ctab[c * CT + k] = row[k];
+      for (int k = 0; k < CT; ++k) s_ctab[c * CT + k] = __float_as_uint(row[k]);
     }
+  }
+  // Scatter (c): fixed-point accumulation.  sm_100a has a native shared-memory atomic for 32-bit integers only
+  // (ATOMS.ADD; fp32/fp64/u64 adds are LDS + ATOMS.CAST.SPIN retry loops), so a contribution c enters its bin as the
+  // 64-bit integer rn(c * 2^k): ATOMS.ADD on the low word, the carry out of it (from the value the atomic returns)
+  // added with the high word by a second ATOMS.ADD.  Integer sums do not depend on the order of the additions: the
+  // source terms are bit-identical from run to run and for any grid size.  Scale 2^k and admission bound per species
+  // come from the previous step (commit thread of post_cycle_body): the bound is 4x the largest |contribution| seen
+  // and k is chosen so that n_used contributions at the bound cannot overflow 2^62; a contribution at the bound keeps
+  // >= 60 - log2(n_used) bits, i.e. more than its 24-bit mantissa for any population a GPU can hold, smaller ones are
+  // rounded to 2^-k.  A contribution above the bound (first step, or a 4x jump from one step to the next) goes to the
+  // fp64 accumulator with an L2 atomic instead; the published value is the sum of the two accumulators.
+  float fx_bound[NC], fx_scale[NC], fx_max[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    fx_bound[j] = (smem_bins && j < 8) ? __ldcg(&p.st->src_bound[j < 8 ? j : 7]) : -1.0f;  // -1: nothing is admitted
+    fx_scale[j] = j < 8 ? __ldcg(&p.st->src_scale[j < 8 ? j : 7]) : 1.0f;
+    fx_max[j] = 0.0f;
   }
   __syncthreads();
 
   BMC_STAMP(p.st, 1);
-  unsigned c_move = 0, c_exit = 0, c_new = 0, c_over = 0;
   double acc0d[NC];  // single-compartment accumulation lives in registers
 #pragma unroll
   for (int j = 0; j < NC; ++j) acc0d[j] = 0.0;
   const double w = (double)p.weight;  // `const double weight = get_weight(p)` contribution_kernel.hpp:179
   const BufRows bufrows{p.buf_props, p.buf_stride};
-  // LAZY: the age columns hold step stamps instead of floats (see "Step-stamped ages" below)
+  // LAZY: the age columns hold step stamps instead of floats (see "Step-stamped ages" above)
   uint32_t* const stamps_hyd = reinterpret_cast<uint32_t*>(p.age_hyd);
   uint32_t* const stamps_div = reinterpret_cast<uint32_t*>(p.age_div);
   (void)stamps_hyd; (void)stamps_div;
-  const uint32_t outlet0 = p.n_flows > 0 ? p.outlets[0].index : 0xffffffffu;
-  const bool outlet0_live = p.n_flows > 0 && p.outlets[0].flow != 0.;
 
-  // PIPE: two-stage bulk-copy pipeline, private to each warp.  Lane 0 arms the stage's mbarrier with
-  // the byte count and issues one cp.async.bulk (TMA, 1-D) per column for the warp's NEXT group; the
-  // bytes land in shared memory while the warp computes its current group, so the HBM latency is off
-  // the critical path and no registers are held by loads in flight.  Lane l then reads bytes
-  // [l*4*VEC, (l+1)*4*VEC) of every staged column (conflict-free LDS.128).  No block-wide barrier.
-  unsigned char* const s_stage = reinterpret_cast<unsigned char*>(s_bins) + p.stage_offset;
-  __shared__ __align__(8) unsigned long long s_bar[kStages][kWarps];
-  constexpr unsigned kColBytes = (unsigned)kColStride;
-  auto issue = [&](uint32_t g, int buf) {  // executed by lane 0 of the warp
-    const size_t g0 = (size_t)g * kGroup;  // first slot of the group (the whole group is below the capacity)
-    unsigned char* dst = s_stage + ((size_t)buf * kWarps + warp) * kWarpStage;
-    unsigned long long* bar = &s_bar[buf][warp];
-    mbar_expect_tx(bar, (unsigned)kWarpStage);
-    bulk_g2s(dst, p.pos + g0, kColBytes, bar);
-    int c = 1;
+  auto ctab_word0 = [&](uint32_t c) -> uint32_t {
+    return p.ctab_in_smem ? s_ctab[c * CT] : __ldg(reinterpret_cast<const uint32_t*>(p.ctab) + (size_t)c * CT);
+  };
+
+  // ---- move + leave of one queued slot (one per lane) ------------------------------------------------
+  auto deferred = [&](const uint32_t slot) {
+    uint32_t c = p.pos[slot];
+    if (p.enable_move) {  // handle_move (all slots, no status check: move_kernel.hpp:392-437)
+      uint32_t r[4];
+      philox4x32_10_idx(slot >> 2, p.ph0, r);
+      const uint32_t n1 = pick4(r, slot & 3u) >> 8;
+      if (n1 < (ctab_word0(c) & kThrMask)) {  // (dt*flow/volume) > rng1
+        philox4x32_10_idx(slot, p.ph2, r);   // the neighbour pick draws its own block
+        const float u2 = u01f(r[0]);
+        const float* row = p.cdf + (size_t)c * p.m;
+        int left = 0, right = p.m - 1;
+        while (left < right) {  // __find_next_compartment, move_kernel.hpp:87-95
+          const int mid = (left + right) >> 1;
+          if (u2 > __ldg(row + mid)) left = mid + 1; else right = mid;
+        }
+        c = __ldg(p.neigh + (size_t)c * p.m + left);
+        p.pos[slot] = c;
+        atomicAdd(&s_cnt[0], 1u);  // events.wrap_incr<Move>() (Q20: aggregated per block)
+      }
+    }
+    // leave (Idle only, post-move position: move_kernel.hpp:347-359)
+    if (p.enable_leave && p.status[slot] == (uint8_t)Idle) {
+      int f = -1;
+      for (int k = 0; k < p.n_flows; ++k)  // find_flow: first match wins
+        if (p.outlets[k].index == c) { if (p.outlets[k].flow != 0.) f = k; break; }
+      if (f >= 0) {
+        uint32_t r[4];
+        philox4x32_10_idx(slot >> 2, p.ph1, r);
+        const float u3 = u01f(pick4(r, slot & 3u));
+        const float lnu = (float)log((double)u3);  // Kokkos::log(float), see oracle ln_f32
+        if (p.outlets[f].dt_flow > (double)(-lnu) * p.outlets[f].volume) {  // probability_leaving<precision_tag>
+          if constexpr (LAZY) {
+            // the particle stops ageing: freeze the step counts (age_hyd = 0, age_div as of this step)
+            stamps_hyd[slot] = kFrozen;
+            const uint32_t sd = stamps_div[slot];
+            stamps_div[slot] = (sd & kFrozen) ? sd : (kFrozen | (p.step + 1u - sd));
+          } else {
+            p.age_hyd[slot] = p.age_hyd[slot] * 0.0f;  // ages(idx,0) *= (1 - leave_mask), after this step's increment
+          }
+          p.status[slot] = (uint8_t)Exit;
+          atomicAdd(&s_cnt[1], 1u);
+        }
+      }
+    }
+  };
+  uint32_t qn = 0;  // entries waiting in this warp's queue (warp-uniform)
+
+  // Every group but the last is entirely below n_used: the body is instantiated twice so that the
+  // common case carries no per-slot range checks (FULL), the ragged tail keeps them.
+  auto body = [&](auto full_tag, const uint32_t g) {
+    constexpr bool FULL = decltype(full_tag)::value;
+    const uint32_t i_raw = g * kGroup + lane * VEC;
+    const bool live = FULL || i_raw < n_used;    // false only in the ragged end of the last group
+    const uint32_t i0 = live ? i_raw : 0u;       // dead lanes shadow slot 0 (loads stay in range, nothing is stored)
+
+    // ---- front-batched global loads (all independent) ----
+    uint32_t pos[VEC]; float adiv[VEC], ahyd[VEC]; float v[VEC][NV], old[VEC][NV];
+    const uint32_t stw = VecIO<VEC>::ldb(p.status + i0);
+    VecIO<VEC>::ldu(p.pos + i0, pos);
+    if constexpr (!LAZY) {
+      VecIO<VEC>::ldf(p.age_div + i0, adiv);
+      if (p.enable_leave) VecIO<VEC>::ldf(p.age_hyd + i0, ahyd);
+    }
 #pragma unroll
-    for (int k = 0; k < NV; ++k)
-      if (!col_flag(M::write_only_mask, k)) { bulk_g2s(dst + c * kColStride, p.props + (size_t)k * p.cap + g0, kColBytes, bar); ++c; }
-    bulk_g2s(dst + (size_t)(1 + ReadCols<M>::value) * kColStride, p.status + g0, (unsigned)kGroup, bar);
+    for (int k = 0; k < NV; ++k) {
+      float col[VEC];
+      if (col_flag(M::write_only_mask, k)) {
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) col[q] = 0.f;
+      } else {
+        VecIO<VEC>::ldf(p.props + (size_t)k * p.cap + i0, col);
+      }
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) { v[q][k] = col[q]; old[q][k] = col[q]; }
+    }
+    if (LAZY || !p.enable_leave) {
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) ahyd[q] = 0.f;
+    }
+    if constexpr (LAZY) {
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) adiv[q] = 0.f;
+    }
+    bool idle[VEC];
+    unsigned valid_m = 0, idle_m = 0;
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+      const bool valid = FULL || (live && (i0 + q) < n_used);
+      idle[q] = valid && (((stw >> (8 * q)) & 0xffu) == (unsigned)Idle);
+      valid_m |= (unsigned)valid << q; idle_m |= (unsigned)idle[q] << q;
+      if (!FULL && !valid) pos[q] = 0;  // slots past n_used hold unspecified bytes: keep the gathers in range
+    }
+    constexpr unsigned kAll = (1u << VEC) - 1u;
+
+    // ---- compartment rows: leave threshold / outlet flag + model terms, one gather per particle
+    uint32_t cw0[VEC]; float cterm[VEC][CT];  // cterm[q][1..] = compartment_terms (index 0 unused)
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+      if (p.ctab_in_smem) {
+        const uint32_t* row = s_ctab + pos[q] * CT;
+        if constexpr (CT == 2) { const uint2 t = *reinterpret_cast<const uint2*>(row); cw0[q] = t.x; cterm[q][1] = __uint_as_float(t.y); }
+        else {
+          cw0[q] = row[0];
+#pragma unroll
+          for (int k = 1; k < CT; ++k) cterm[q][k] = __uint_as_float(row[k]);
+        }
+      } else {
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(p.ctab) + (size_t)pos[q] * CT;
+        if constexpr (CT == 2) { const uint2 t = __ldg(reinterpret_cast<const uint2*>(row)); cw0[q] = t.x; cterm[q][1] = __uint_as_float(t.y); }
+        else if constexpr (CT == 4) {
+          const uint4 t = __ldg(reinterpret_cast<const uint4*>(row));
+          cw0[q] = t.x; cterm[q][1] = __uint_as_float(t.y); cterm[q][2] = __uint_as_float(t.z); cterm[q][3] = __uint_as_float(t.w);
+        } else {
+          cw0[q] = __ldg(row);
+#pragma unroll
+          for (int k = 1; k < CT; ++k) cterm[q][k] = __uint_as_float(__ldg(row + k));
+        }
+      }
+    }
+
+    // ---- u1: ONE Philox block per group of four slots (draw_block 0) ---------
+    uint32_t rw1[4] = {0u, 0u, 0u, 0u};
+    if (p.enable_move) philox4x32_10_idx((uint32_t)(i0 >> 2), p.ph0, rw1);
+
+    // ---- move / leave candidates: two integer tests per slot, the work itself is deferred ----
+    //   word 0 of the compartment row = leave threshold (bits 0..24) | kOutletBit
+    unsigned cand = 0;
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+      const uint32_t n1 = (VEC == 4 ? rw1[q] : pick4(rw1, (unsigned)((i0 + q) & 3))) >> 8;
+      const bool leaves = n1 < (cw0[q] & kThrMask);                 // (dt*flow/volume) > rng1, all slots
+      const bool in_outlet = (cw0[q] & kOutletBit) != 0u && idle[q];  // leave test applies to Idle particles only
+      cand |= (unsigned)(leaves || in_outlet) << q;
+    }
+    cand &= valid_m;
+
+    // ---- model update: unconditional straight-line code over the VEC particles;
+    // results of non-idle slots are never stored (model_kernel.hpp:186-196)
+    float contrib[VEC][NC];
+    unsigned div_nib = 0;
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+      if constexpr (!LAZY) adiv[q] = idle[q] ? adiv[q] + p.dt_f : adiv[q];  // ages(i,1) += _d_t  (model_kernel.hpp:191)
+      Gen gen(p.seed_lo, p.seed_hi, p.rank, (uint32_t)(i0 + q), p.step, 2u);
+      const ConcView conc{p.conc, p.n_species, &cterm[q][1]};
+      const Status s = M::update(gen, p.dt_f, i0 + q, RegRow{v[q]}, RegRow{contrib[q]}, (size_t)pos[q], conc);
+      div_nib |= (unsigned)(idle[q] && s == Division) << q;
+    }
+
+    // ---- contribution scatter at the PRE-move position (Q15) -----------------
+    if (single_comp) {
+#pragma unroll
+      for (int q = 0; q < VEC; ++q)
+#pragma unroll
+        for (int j = 0; j < NC; ++j) acc0d[j] += idle[q] ? w * (double)contrib[q][j] : 0.0;
+    } else {
+      unsigned slow = 0;  // slots with a contribution that was not admitted to the integer bins (rare)
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+          const float c = contrib[q][j];
+          const float a = idle[q] ? fabsf(c) : 0.0f;
+          fx_max[j] = fmaxf(fx_max[j], a);
+          const bool adm = idle[q] && a <= fx_bound[j];
+          if (adm) {
+            const long long fix = __float2ll_rn(c * fx_scale[j]);
+            const uint32_t lo = (uint32_t)fix, hi = (uint32_t)((unsigned long long)fix >> 32);
+            unsigned int* bin = s_bins + 2u * ((uint32_t)j + p.n_species * pos[q]);
+            const uint32_t was = atomicAdd(bin, lo);
+            atomicAdd(bin + 1, hi + (uint32_t)((uint32_t)(was + lo) < lo));
+          }
+          slow |= (unsigned)(idle[q] && !adm) << q;
+        }
+      }
+      if (slow) {  // first step, a 4x jump, NaN, or bins too large for shared memory: fp64 accumulator in L2 (RED.F64)
+#pragma unroll
+        for (int q = 0; q < VEC; ++q)
+          if ((slow >> q) & 1u) {
+#pragma unroll
+            for (int j = 0; j < NC; ++j)
+              if (!(fabsf(contrib[q][j]) <= fx_bound[j]))
+                atomicAdd(p.acc + (size_t)j + (size_t)p.n_species * pos[q], w * (double)contrib[q][j]);
+          }
+      }
+    }
+
+    // ---- division: handle_division (particles_container.hpp:559-573) -------
+    // warp-aggregated slot allocation: ONE atomic per warp that has a dividing
+    // mother (reference: one per mother, a6).  Rows are allocated in ascending
+    // particle order inside the warp; final newborn placement is re-ranked by
+    // mother index in the post-cycle phase, so the result does not depend on the
+    // order warps hit the atomic.
+    // Division mask: VEC ballot words per group (word q, bit l <-> slot g*32*VEC + l*VEC + q), written for EVERY
+    // group of every step by lane 0 (0.125 B/slot), so no bit ever needs clearing.
+    unsigned mask_w[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) mask_w[q] = 0u;
+    if (__any_sync(kFull, div_nib != 0u)) {
+      unsigned ok_nib = 0;
+      const unsigned long long buf_cap = __ldcg(&p.st->buf_cap_eff);
+      const unsigned cnt = __popc(div_nib);
+      unsigned total;
+      const unsigned excl = warp_excl_scan(cnt, total);
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(&p.st->buf_index, (unsigned long long)total);
+      base = __shfl_sync(kFull, base, 0);
+      unsigned r = 0;
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) {
+        if ((div_nib >> q) & 1u) {
+          const unsigned long long j = base + excl + r;
+          ++r;
+          atomicAdd(&s_cnt[2], 1u);  // NewParticle++ even on overflow (model_kernel.hpp:259, Q6)
+          if (j < buf_cap) {
+            Gen gen(p.seed_lo, p.seed_hi, p.rank, (uint32_t)(i0 + q), p.step, 0x40000000u);
+            M::division(gen, i0 + q, (size_t)j, RegRow{v[q]}, bufrows);
+            p.buf_pos[j] = pos[q];               // buffer_position(idx2) = position(idx1): pre-move
+            p.buf_mother[j] = (uint32_t)(i0 + q);
+            if constexpr (LAZY) stamps_div[i0 + q] = p.step + 1u;  // ages(idx1,1) = 0: counts from the next step
+            else adiv[q] = 0.f;                                    // ages(idx1,1) = 0
+            ok_nib |= 1u << q;
+          } else {
+            atomicAdd(&s_cnt[3], 1u);  // waiting_allocation_particle / Overflow (model_kernel.hpp:253-258)
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) mask_w[q] = __ballot_sync(kFull, (ok_nib >> q) & 1u);
+    }
+    if (lane == 0) MaskIO<VEC>::st(p.div_mask + (size_t)g * VEC, mask_w);
+
+    // ---- write back ---------------------------------------------------------
+    // Columns the model assigns on every update (always_written_mask, which includes the
+    // write-only ones) are stored whenever the thread has an idle slot; the others only if a
+    // value changed bitwise (the comparison folds away for columns the hooks never assign).
+    // Position, status and (stamped) ages are written by `deferred` / the division branch only.
+    const bool all_idle = (idle_m == kAll);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      float col[VEC];
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) col[q] = v[q][k];
+      float* dst = p.props + (size_t)k * p.cap + i0;
+      bool ch = false;
+      if (col_flag(M::write_only_mask | M::always_written_mask, k)) ch = idle_m != 0u;
+      else {
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) ch = ch || (idle[q] && __float_as_uint(v[q][k]) != __float_as_uint(old[q][k]));
+      }
+      if (ch) {
+        if (all_idle) VecIO<VEC>::stf(dst, col);
+        else {  // group with exited / out-of-range slots: their columns stay untouched
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) if (idle[q]) dst[q] = col[q];
+        }
+      }
+    }
+    if constexpr (!LAZY) {
+      // eager ages change for every idle particle; non-idle lanes rewrite the value they loaded
+      if (p.enable_leave) {
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) ahyd[q] = idle[q] ? (float)((double)ahyd[q] + p.dt) : ahyd[q];  // ages(idx,0) += d_t (double)
+      }
+      if (idle_m) {
+        VecIO<VEC>::stf(p.age_div + i0, adiv);
+        if (p.enable_leave) VecIO<VEC>::stf(p.age_hyd + i0, ahyd);
+      }
+    }
+
+    // ---- queue the candidates; handle 32 at a time ----------------------------
+    if (__any_sync(kFull, cand != 0u)) {
+      const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) {
+        const bool mine = (cand >> q) & 1u;
+        const unsigned b = __ballot_sync(kFull, mine);
+        if (mine) s_queue[qn + __popc(b & lt)] = (uint32_t)(i0 + q);
+        qn += __popc(b);
+      }
+      __syncwarp();  // queue entries and this group's age / stamp stores are visible to the whole warp
+      while (qn >= 32u) {
+        qn -= 32u;
+        const uint32_t slot = s_queue[qn + lane];
+        __syncwarp();
+        deferred(slot);
+      }
+    }
   };
 
   {
-    // Every group but the last is entirely below n_used: the body is instantiated twice so that the
-    // common case carries no per-slot range checks (FULL), the ragged tail keeps them.
-    auto body = [&](auto full_tag, const uint32_t g, const int buf) {
-      constexpr bool FULL = decltype(full_tag)::value;
-      const uint32_t i_raw = g * kGroup + lane * VEC;
-      const bool live = FULL || i_raw < n_used;    // false only in the ragged end of the last group
-      const size_t i0 = live ? i_raw : 0u;         // dead lanes shadow slot 0 (loads stay in range, nothing is stored)
-
-      uint32_t pos[VEC]; float adiv[VEC], ahyd[VEC]; float v[VEC][NV], old[VEC][NV];
-      uint32_t stw;
-      if constexpr (PIPE) {
-        // ---- operands were staged in shared memory by the bulk copies issued one iteration ago ----
-        const unsigned char* stage = s_stage + ((size_t)buf * kWarps + warp) * kWarpStage;
-        const unsigned char* src = stage + lane * (4 * VEC);
-        stw = VecIO<VEC>::ldb_plain(stage + (size_t)(1 + ReadCols<M>::value) * kColStride + lane * VEC);
-        VecIO<VEC>::ldu_plain(reinterpret_cast<const uint32_t*>(src), pos);
-        int c = 1;
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-          float col[VEC];
-          if (col_flag(M::write_only_mask, k)) {
-#pragma unroll
-            for (int q = 0; q < VEC; ++q) col[q] = 0.f;
-          } else {
-            VecIO<VEC>::ldf_plain(reinterpret_cast<const float*>(src + c * kColStride), col);
-            ++c;
-          }
-#pragma unroll
-          for (int q = 0; q < VEC; ++q) { v[q][k] = col[q]; old[q][k] = col[q]; }
-        }
-      } else {
-        // ---- front-batched global loads (all independent) ----
-        stw = VecIO<VEC>::ldb(p.status + i0);
-        VecIO<VEC>::ldu(p.pos + i0, pos);
-        if constexpr (!LAZY) {
-          VecIO<VEC>::ldf(p.age_div + i0, adiv);
-          if (p.enable_leave) VecIO<VEC>::ldf(p.age_hyd + i0, ahyd);
-        }
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-          float col[VEC];
-          if (col_flag(M::write_only_mask, k)) {
-#pragma unroll
-            for (int q = 0; q < VEC; ++q) col[q] = 0.f;
-          } else {
-            VecIO<VEC>::ldf(p.props + (size_t)k * p.cap + i0, col);
-          }
-#pragma unroll
-          for (int q = 0; q < VEC; ++q) { v[q][k] = col[q]; old[q][k] = col[q]; }
-        }
-      }
-      if (LAZY || !p.enable_leave) {
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) ahyd[q] = 0.f;
-      }
-      if constexpr (LAZY) {
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) adiv[q] = 0.f;
-      }
-      bool idle[VEC];
-      unsigned valid_m = 0, idle_m = 0;
-#pragma unroll
-      for (int q = 0; q < VEC; ++q) {
-        const bool valid = FULL || (live && (i0 + q) < n_used);
-        idle[q] = valid && (((stw >> (8 * q)) & 0xffu) == (unsigned)Idle);
-        valid_m |= (unsigned)valid << q; idle_m |= (unsigned)idle[q] << q;
-        if (!FULL && !valid) pos[q] = 0;  // slots past n_used hold unspecified bytes: keep the gathers in range
-      }
-      constexpr unsigned kAll = (1u << VEC) - 1u;
-
-      // ---- compartment rows: leave threshold + model terms, one gather per particle
-      float ctab[VEC][CT];
-#pragma unroll
-      for (int q = 0; q < VEC; ++q) {
-        if (p.ctab_in_smem) {
-          const float* row = s_ctab + pos[q] * CT;
-          if constexpr (CT == 2) { const float2 t = *reinterpret_cast<const float2*>(row); ctab[q][0] = t.x; ctab[q][1] = t.y; }
-          else {
-#pragma unroll
-            for (int k = 0; k < CT; ++k) ctab[q][k] = row[k];
-          }
-        } else {
-          const float* row = p.ctab + (size_t)pos[q] * CT;
-          if constexpr (CT == 2) { const float2 t = __ldg(reinterpret_cast<const float2*>(row)); ctab[q][0] = t.x; ctab[q][1] = t.y; }
-          else if constexpr (CT == 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(row)); ctab[q][0] = t.x; ctab[q][1] = t.y; ctab[q][2] = t.z; ctab[q][3] = t.w; }
-          else {
-#pragma unroll
-            for (int k = 0; k < CT; ++k) ctab[q][k] = __ldg(row + k);
-          }
-        }
-      }
-
-      // ---- u1: ONE Philox block per group of four slots (draw_block 0) ---------
-      uint32_t rw1[4] = {0u, 0u, 0u, 0u};
-      if (p.enable_move) philox4x32_10((uint32_t)(i0 >> 2), p.step, 0u, p.rank, p.seed_lo, p.seed_hi, rw1);
-
-      // ---- model update: unconditional straight-line code over the VEC particles;
-      // results of non-idle slots are never stored (model_kernel.hpp:186-196)
-      float contrib[VEC][NC];
-      unsigned div_nib = 0;
-#pragma unroll
-      for (int q = 0; q < VEC; ++q) {
-        if constexpr (!LAZY) adiv[q] = idle[q] ? adiv[q] + p.dt_f : adiv[q];  // ages(i,1) += _d_t  (model_kernel.hpp:191)
-        Gen gen(p.seed_lo, p.seed_hi, p.rank, (uint32_t)(i0 + q), p.step, 2u);
-        const ConcView conc{p.conc, p.n_species, &ctab[q][1]};
-        const Status s = M::update(gen, p.dt_f, i0 + q, RegRow{v[q]}, RegRow{contrib[q]}, (size_t)pos[q], conc);
-        div_nib |= (unsigned)(idle[q] && s == Division) << q;
-      }
-
-      // ---- contribution scatter at the PRE-move position (Q15) -----------------
-      if (single_comp) {
-#pragma unroll
-        for (int q = 0; q < VEC; ++q)
-#pragma unroll
-          for (int j = 0; j < NC; ++j) acc0d[j] += idle[q] ? w * (double)contrib[q][j] : 0.0;
-      } else if (smem_bins) {  // block-private fp64 bins (LDS/DADD/ATOMS.CAST.SPIN), flushed once per block
-#pragma unroll
-        for (int q = 0; q < VEC; ++q)
-          if (idle[q]) {
-#pragma unroll
-            for (int j = 0; j < NC; ++j) atomicAdd(&s_bins[(uint32_t)j + p.n_species * pos[q]], w * (double)contrib[q][j]);
-          }
-      } else {  // table too large for shared memory: L2 atomics (RED.F64)
-#pragma unroll
-        for (int q = 0; q < VEC; ++q)
-          if (idle[q]) {
-#pragma unroll
-            for (int j = 0; j < NC; ++j) atomicAdd(p.acc + (size_t)j + (size_t)p.n_species * pos[q], w * (double)contrib[q][j]);
-          }
-      }
-
-      // ---- division: handle_division (particles_container.hpp:559-573) -------
-      // warp-aggregated slot allocation: ONE atomic per warp that has a dividing
-      // mother (reference: one per mother, a6).  Rows are allocated in ascending
-      // particle order inside the warp; final newborn placement is re-ranked by
-      // mother index in insert_kernel, so the result does not depend on the
-      // order warps hit the atomic.
-      unsigned ok_nib = 0;
-      if (__any_sync(0xffffffffu, div_nib != 0u)) {
-        const unsigned cnt = __popc(div_nib);
-        unsigned total;
-        const unsigned excl = warp_excl_scan(cnt, total);
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&p.st->buf_index, (unsigned long long)total);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        unsigned r = 0;
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) {
-          if ((div_nib >> q) & 1u) {
-            const unsigned long long j = base + excl + r;
-            ++r;
-            ++c_new;  // NewParticle++ even on overflow (model_kernel.hpp:259, Q6)
-            if (j < buf_cap) {
-              Gen gen(p.seed_lo, p.seed_hi, p.rank, (uint32_t)(i0 + q), p.step, 0x40000000u);
-              M::division(gen, i0 + q, (size_t)j, RegRow{v[q]}, bufrows);
-              p.buf_pos[j] = pos[q];               // buffer_position(idx2) = position(idx1): pre-move
-              p.buf_mother[j] = (uint32_t)(i0 + q);
-              if constexpr (LAZY) stamps_div[i0 + q] = p.step + 1u;  // ages(idx1,1) = 0: counts from the next step
-              else adiv[q] = 0.f;                                    // ages(idx1,1) = 0
-              ok_nib |= 1u << q;
-            } else {
-              ++c_over;  // waiting_allocation_particle / Overflow (model_kernel.hpp:253-258)
-            }
-          }
-        }
-      }
-      {
-        // division bitmask: bit (slot & 31) of word (slot >> 5); a word is owned by 32/VEC lanes.
-        // Written for EVERY group of every step (0.125 B/slot), so no bit ever needs clearing.
-        constexpr int LPW = 32 / VEC;
-        unsigned word = ok_nib << (VEC * (lane % LPW));
-#pragma unroll
-        for (int o = 1; o < LPW; o <<= 1) word |= __shfl_xor_sync(0xffffffffu, word, o);
-#if !defined(BMC_EXP_NO_MASKSTORE)
-        if ((lane % LPW) == 0) p.div_mask[i_raw >> 5] = word;  // i_raw: also the ragged end of the last tile (zeros)
-#else
-        if ((lane % LPW) == 0 && word) p.div_mask[i_raw >> 5] = word;
-#endif
-      }
-
-      // ---- move (all slots, no status check: move_kernel.hpp:392-437) --------
-      unsigned moved = 0;
-      if (p.enable_move) {
-        unsigned mv = 0;
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) {
-          const float u1 = u01f(pick4(rw1, (unsigned)((i0 + q) & 3)));
-          mv |= (unsigned)(u1 < ctab[q][0]) << q;  // (dt*flow/volume) > rng1
-        }
-        mv &= valid_m;
-        moved = mv;
-        // movers are rare (dt*F/V ~ 1e-2): their neighbour pick draws its own block
-        while (mv) {
-          const int q = __ffs(mv) - 1;
-          mv &= mv - 1;
-          uint32_t c = pos[0];
-#pragma unroll
-          for (int qq = 1; qq < VEC; ++qq) if (qq == q) c = pos[qq];
-          uint32_t r2[4];
-          philox4x32_10((uint32_t)(i0 + q), p.step, 2u, p.rank, p.seed_lo, p.seed_hi, r2);
-          const float u2 = u01f(r2[0]);
-          const float* row = p.cdf + (size_t)c * p.m;
-          int left = 0, right = p.m - 1;
-          while (left < right) {  // __find_next_compartment, move_kernel.hpp:87-95
-            const int mid = (left + right) >> 1;
-            if (u2 > __ldg(row + mid)) left = mid + 1; else right = mid;
-          }
-          const uint32_t np = __ldg(p.neigh + (size_t)c * p.m + left);
-#pragma unroll
-          for (int qq = 0; qq < VEC; ++qq) if (qq == q) pos[qq] = np;
-          ++c_move;  // events.wrap_incr<Move>() (Q20: aggregated)
-        }
-      }
-
-      // ---- leave (Idle only, post-move position: move_kernel.hpp:347-359) ----
-      unsigned exit_nib = 0;
-      if (p.enable_leave) {
-        unsigned in_outlet = 0; int fsel[VEC];
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) {
-          if constexpr (!LAZY) ahyd[q] = idle[q] ? (float)((double)ahyd[q] + p.dt) : ahyd[q];  // ages(idx,0) += d_t (double)
-          fsel[q] = 0;
-        }
-        if (p.n_flows == 1) {  // the usual case (0D reactor or a single outlet, move_kernel.hpp:113)
-#pragma unroll
-          for (int q = 0; q < VEC; ++q) in_outlet |= (unsigned)(outlet0_live && pos[q] == outlet0) << q;
-        } else {
-#pragma unroll
-          for (int q = 0; q < VEC; ++q)
-            for (int f = 0; f < p.n_flows; ++f)  // find_flow: first match wins
-              if (p.outlets[f].index == pos[q]) { if (p.outlets[f].flow != 0.) { in_outlet |= 1u << q; fsel[q] = f; } break; }
-        }
-        in_outlet &= idle_m;
-        if (in_outlet) {  // u3: draw_block 1 of the group of four
-          uint32_t rw3[4];
-          philox4x32_10((uint32_t)(i0 >> 2), p.step, 1u, p.rank, p.seed_lo, p.seed_hi, rw3);
-#pragma unroll
-          for (int q = 0; q < VEC; ++q) {
-            if ((in_outlet >> q) & 1u) {
-              const float u3 = u01f(pick4(rw3, (unsigned)((i0 + q) & 3)));
-              const float lnu = (float)log((double)u3);  // Kokkos::log(float), see oracle ln_f32
-              const Outlet& o = p.outlets[fsel[q]];
-              if (o.dt_flow > (double)(-lnu) * o.volume) {  // probability_leaving<precision_tag>
-                if constexpr (LAZY) {
-                  // the particle stops ageing: freeze the step counts (age_hyd = 0, age_div as of this step)
-                  stamps_hyd[i0 + q] = kFrozen;
-                  const uint32_t sd = stamps_div[i0 + q];
-                  stamps_div[i0 + q] = (sd & kFrozen) ? sd : (kFrozen | (p.step + 1u - sd));
-                } else {
-                  ahyd[q] = ahyd[q] * 0.0f;                 // ages(idx,0) *= (1 - leave_mask)
-                }
-                exit_nib |= 1u << q;
-                ++c_exit;
-              }
-            }
-          }
-        }
-      }
-
-      // ---- write back ---------------------------------------------------------
-      // Columns the model assigns on every update (always_written_mask, which includes the
-      // write-only ones) are stored whenever the thread has an idle slot; the others only if a
-      // value changed bitwise (the comparison folds away for columns the hooks never assign).
-      const bool all_idle = (idle_m == kAll);
-#pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        float col[VEC];
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) col[q] = v[q][k];
-        float* dst = p.props + (size_t)k * p.cap + i0;
-        bool ch = false;
-        if (col_flag(M::write_only_mask | M::always_written_mask, k)) ch = idle_m != 0u;
-        else {
-#pragma unroll
-          for (int q = 0; q < VEC; ++q) ch = ch || (idle[q] && __float_as_uint(v[q][k]) != __float_as_uint(old[q][k]));
-        }
-        if (ch) {
-          if (all_idle) VecIO<VEC>::stf(dst, col);
-          else {  // group with exited / out-of-range slots: their columns stay untouched
-#pragma unroll
-            for (int q = 0; q < VEC; ++q) if (idle[q]) dst[q] = col[q];
-          }
-        }
-      }
-      if constexpr (!LAZY) {
-        // eager ages change for every idle particle; non-idle lanes rewrite the value they loaded
-        if (idle_m) {
-          VecIO<VEC>::stf(p.age_div + i0, adiv);
-          if (p.enable_leave) VecIO<VEC>::stf(p.age_hyd + i0, ahyd);
-        }
-      }
-      if (moved) {  // Q14: position written only for movers (never for slots >= n_used: mv is masked)
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) if ((moved >> q) & 1u) p.pos[i0 + q] = pos[q];
-      }
-      if (exit_nib) {
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) if ((exit_nib >> q) & 1u) p.status[i0 + q] = (uint8_t)Exit;
-      }
-    };
-    // Draw number s -> group s: the warps that run at the same time work on adjacent groups, i.e. the
-    // whole grid streams through ONE moving window of every column.  (Spreading the draws over many
-    // interleaved address streams was measured to make no difference.)
-    const unsigned long long n_draws = n_groups;
-    auto group_of = [&](unsigned long long s) -> uint32_t { return (uint32_t)s; };
-    unsigned long long s = (unsigned long long)blockIdx.x * kWarps + warp;  // first draw: the warp's own index
-    if constexpr (PIPE) {
-      if (lane == 0) {
-#pragma unroll
-        for (int b = 0; b < kStages; ++b) mbar_init(&s_bar[b][warp], 1u);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      }
-      __syncwarp();
-      uint32_t nxt = 0;
-      uint32_t g = s < n_draws ? group_of(s) : n_groups;
-      if (lane == 0) {
-        if (g < n_groups) issue(g, 0);
-        nxt = atomicAdd(&p.st->next_group, 1u);  // the pipeline needs the next group one iteration ahead
-      }
-      uint32_t it = 0;  // counts the groups that were staged (buffer / barrier phase)
+    // Ticket t of a block -> chunk c = t / kWarps, offset o = t % kWarps.  The warp that draws o == 0 fetches the
+    // chunk from the device-wide counter (the only L2 atomic: one per kWarps groups) and publishes its first group
+    // in ring slot c % kRing; the other warps of the chunk read it when they need their group (normally long after).
+    // A slot is reused only when every ticket of its previous chunk has been resolved (s_chunk_left), so a warp can
+    // never read the base of a later chunk.  Every warp holds at most one unresolved ticket and resolves it before
+    // it draws again or leaves the loop, which makes the scheme deadlock-free.
+    volatile unsigned* const v_seq = s_chunk_seq;
+    volatile unsigned* const v_left = s_chunk_left;
+    volatile unsigned* const v_base = s_chunk_base;
+    uint32_t s = blockIdx.x * kWarps + warp;  // first group: the warp's own index
 #pragma unroll 1
-      while (s < n_draws) {
-        const int buf = (int)(it & 1u);
-        const unsigned long long s_next = (unsigned long long)total_warps + __shfl_sync(0xffffffffu, nxt, 0);
-        const uint32_t g_next = s_next < n_draws ? group_of(s_next) : n_groups;
-        const bool have = g < n_groups, have_next = g_next < n_groups;
-        __syncwarp();  // every lane is done reading the other buffer (previous iteration): it may be refilled
-        if (lane == 0) {
-          if (have_next) issue(g_next, have ? buf ^ 1 : buf);
-          nxt = atomicAdd(&p.st->next_group, 1u);
+    while (s < n_groups) {
+      unsigned t = 0;
+      if (lane == 0) {  // draw the ticket of the NEXT group now, resolve it after this group
+        t = atomicAdd(&s_ticket, 1u);
+        const unsigned c = t / kWarps, o = t - c * kWarps, slot = c % kRing;
+        if (o == 0u) {
+          while (v_left[slot] != 0u) { }  // previous chunk of this slot still has unresolved tickets (practically never)
+          const unsigned base = total_warps + atomicAdd(&p.st->next_group, (unsigned)kWarps);
+          v_base[slot] = base;
+          v_left[slot] = (unsigned)kWarps;
+          __threadfence_block();
+          v_seq[slot] = c + 1u;
         }
-        if (have) {
-          mbar_wait(&s_bar[buf][warp], (it >> 1) & 1u);
-          if ((unsigned long long)(g + 1) * kGroup <= n_used) body(FullTile{}, g, buf);
-          else body(RaggedTile{}, g, buf);
-          ++it;
-        }
-        g = g_next; s = s_next;
       }
-    } else {
-#pragma unroll 1
-      while (s < n_draws) {
-        uint32_t nxt = 0;
-        if (lane == 0) nxt = atomicAdd(&p.st->next_group, 1u);  // consumed after this group: latency hidden
-        const uint32_t g = group_of(s);
-        if (g < n_groups) {
-          if ((unsigned long long)(g + 1) * kGroup <= n_used) body(FullTile{}, g, 0);
-          else body(RaggedTile{}, g, 0);
-        }
-        s = (unsigned long long)total_warps + __shfl_sync(0xffffffffu, nxt, 0);
+      if ((unsigned long long)(s + 1u) * kGroup <= n_used) body(FullTile{}, s);
+      else body(RaggedTile{}, s);
+      if (lane == 0) {
+        const unsigned c = t / kWarps, o = t - c * kWarps, slot = c % kRing;
+        while (v_seq[slot] != c + 1u) { }
+        __threadfence_block();
+        s = v_base[slot] + o;
+        atomicSub(&s_chunk_left[slot], 1u);
       }
+      s = __shfl_sync(kFull, s, 0);
     }
+    __syncwarp();
+    if (lane < qn) deferred(s_queue[lane]);  // what is left in the queue (< 32 entries)
   }
 
   BMC_STAMP(p.st, 2);
@@ -1108,40 +1131,39 @@ template <class M, int VEC, bool PIPE, bool LAZY, int BLOCK> __device__ __forcei
     p.post.src[4 * blockIdx.x + 2] = 0u; p.post.src[4 * blockIdx.x + 3] = smid;
   }
 #endif
-  // ---- block epilogue: counters, source flush, block-local tile prefix -------
-  const unsigned cm = __reduce_add_sync(0xffffffffu, c_move), ce = __reduce_add_sync(0xffffffffu, c_exit);
-  const unsigned cn = __reduce_add_sync(0xffffffffu, c_new), co = __reduce_add_sync(0xffffffffu, c_over);
-  if (lane == 0) {
-    if (cm) atomicAdd(&s_cnt[0], (unsigned long long)cm);
-    if (ce) atomicAdd(&s_cnt[1], (unsigned long long)ce);
-    if (cn) atomicAdd(&s_cnt[2], (unsigned long long)cn);
-    if (co) atomicAdd(&s_cnt[3], (unsigned long long)co);
+  // ---- block epilogue: counters, source flush ---------------------------------
+#pragma unroll
+  for (int j = 0; j < NC && j < 8; ++j) {  // non-negative floats order like their bit patterns
+    const unsigned m = __reduce_max_sync(kFull, __float_as_uint(fx_max[j]));
+    if (lane == 0 && m) atomicMax(&s_fxmax[j], m);
   }
   if (single_comp) {
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
       double a = acc0d[j];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(kFull, a, o);
       if (lane == 0 && a != 0.0) atomicAdd(p.acc + j, a);
     }
   }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    if (s_cnt[0]) atomicAdd(&p.st->events[2], s_cnt[0]);                                               // Move
-    if (s_cnt[1]) { atomicAdd(&p.st->events[1], s_cnt[1]); atomicAdd(&p.st->step_exit, s_cnt[1]); }     // Exit
-    if (s_cnt[2]) atomicAdd(&p.st->events[0], s_cnt[2]);                                               // NewParticle
-    if (s_cnt[3]) { atomicAdd(&p.st->events[4], s_cnt[3]); atomicAdd(&p.st->step_waiting, s_cnt[3]); }  // Overflow
+    const unsigned long long cm = s_cnt[0], ce = s_cnt[1], cn = s_cnt[2], co = s_cnt[3];
+    if (cm) atomicAdd(&p.st->events[2], cm);                                             // Move
+    if (ce) { atomicAdd(&p.st->events[1], ce); atomicAdd(&p.st->step_exit, ce); }        // Exit
+    if (cn) atomicAdd(&p.st->events[0], cn);                                             // NewParticle
+    if (co) { atomicAdd(&p.st->events[4], co); atomicAdd(&p.st->step_waiting, co); }     // Overflow
   }
+  if (threadIdx.x < 8 && s_fxmax[threadIdx.x]) atomicMax(&p.st->src_max[threadIdx.x], s_fxmax[threadIdx.x]);
   if (smem_bins) {
     // every block starts at a different bin, so that the blocks (which finish together) do not hit
-    // the same L2 addresses at the same time
+    // the same L2 addresses at the same time; integer adds (RED.ADD.64): order-independent
     const uint32_t rot = (uint32_t)(((unsigned long long)blockIdx.x * n_bins) / gridDim.x);
     for (uint32_t k0 = threadIdx.x; k0 < n_bins; k0 += BLOCK) {
       uint32_t k = k0 + rot; if (k >= n_bins) k -= n_bins;
-      const double a = s_bins[k];
-      if (a != 0.0) atomicAdd(p.acc + k, a);
+      const unsigned long long a = s_dyn[k];
+      if (a != 0ull) atomicAdd(p.acc_fix + k, a);
     }
   }
   // ---- second phase of the step: every block's state, buffer rows and counters are complete
@@ -1222,9 +1244,9 @@ template <class M> __device__ __forceinline__ void export_body(const ExportParam
 template <class M> __global__ void __launch_bounds__(256) pre_step_kernel(const __grid_constant__ PreParams p) { pre_step_body<M>(p); }
 // WB = 256-thread units per block (one block per SM): 4 -> 1024 threads x <=64 registers, 3 -> 768 x <=80,
 // 2 -> 512 x <=128.  One big block per SM shares one set of shared-memory source bins among all its warps.
-template <class M, int VEC, int WB, bool PIPE, bool LAZY>
+template <class M, int VEC, int WB, bool LAZY>
 __global__ void __launch_bounds__(kBlock * WB, 1) cycle_kernel(const __grid_constant__ CycleParams p) {
-  cycle_body<M, VEC, PIPE, LAZY, kBlock * WB>(p);
+  cycle_body<M, VEC, LAZY, kBlock * WB>(p);
 }
 template <class M> __global__ void __launch_bounds__(256) init_kernel(const __grid_constant__ InitParams p) { init_body<M>(p); }
 template <class M> __global__ void __launch_bounds__(256) export_kernel(const __grid_constant__ ExportParams p) { export_body<M>(p); }

@@ -10,26 +10,26 @@ namespace bmc {
 struct ModelVT {
   int n_var, n_c, vec, minb;
   int block, block_eager;  // threads per block of cycle_fn / cycle_eager_fn (one block per SM)
-  int ct;              // floats per compartment-table row
-  size_t stage_bytes;  // dynamic shared memory of the bulk-copy pipeline (0 = direct loads)
+  int ct;              // 32-bit words per compartment-table row
   // kernel handles: addresses of __global__ instantiations, or cudaKernel_t of a JIT-compiled
   // user model; all launched with cudaLaunchKernel(handle, grid, block, {&params}, smem, stream)
   const void* cycle_fn;   // (CycleParams)  block = 256*minb threads, one block per SM; step-stamped ages (bmc_kernels.cuh)
-  const void* cycle_eager_fn;  // same with float ages updated every step (direct loads, no staging)
+  const void* cycle_eager_fn;  // same with float ages loaded, incremented and stored every step
   const void* pre_fn;     // (PreParams)    block = 256
   const void* init_fn;    // (InitParams)   block = 256
   const void* export_fn;  // (ExportParams) block = 256
   void* jit_library;      // cudaLibrary_t of a user model (unloaded with the context), else nullptr
 };
 
-template <class M, int VEC, int MINB = 1, bool PIPE = false> static ModelVT make_vt() {
+// MINB = 256-thread units per block of the stamped-age kernel, MINB_E of the eager-age kernel (two more
+// columns in flight per slot: more registers per thread, fewer threads)
+template <class M, int VEC, int MINB, int MINB_E> static ModelVT make_vt() {
   ModelVT v;
   v.n_var = M::n_var; v.n_c = M::n_c; v.vec = VEC; v.minb = MINB;
-  v.block = kBlock * MINB; v.block_eager = kBlock * (MINB > 3 ? 3 : MINB);
+  v.block = kBlock * MINB; v.block_eager = kBlock * MINB_E;
   v.ct = 1 + M::n_pre;
-  v.stage_bytes = PIPE ? kStages * StageBytes<M, VEC>::warp_stage * (size_t)(kBlock * MINB / 32) : 0;
-  v.cycle_fn = (const void*)cycle_kernel<M, VEC, MINB, PIPE, true>;
-  v.cycle_eager_fn = (const void*)cycle_kernel<M, VEC, (MINB > 3 ? 3 : MINB), false, false>;
+  v.cycle_fn = (const void*)cycle_kernel<M, VEC, MINB, true>;
+  v.cycle_eager_fn = (const void*)cycle_kernel<M, VEC, MINB_E, false>;
   v.pre_fn = (const void*)pre_step_kernel<M>;
   v.init_fn = (const void*)init_kernel<M>;
   v.export_fn = (const void*)export_kernel<M>;
@@ -37,28 +37,16 @@ template <class M, int VEC, int MINB = 1, bool PIPE = false> static ModelVT make
   return v;
 }
 
-// Kernel variant = (slots per thread, min resident blocks per SM, load path).  Defaults were
-// picked from sweeps on a B200 (tools/sweep.py).  BMC_VARIANT="v<VEC>b<MINB>" selects
-// direct global loads, "p<VEC>b<MINB>" the TMA bulk-copy pipeline (where it is built).
-template <class M, int VEC, bool WITH_PIPE = false> static bool pick_variant(const std::string& var, int def_minb, ModelVT& vt,
-                                                                            bool def_pipe = false) {
-  int minb = def_minb; bool pipe = def_pipe && WITH_PIPE;
-  if (var.size() == 4 && (var[0] == 'v' || var[0] == 'p') && var[2] == 'b' && var[1] - '0' == VEC) {
-    minb = var[3] - '0'; pipe = var[0] == 'p';
-  }
-  if constexpr (WITH_PIPE) {
-    if (pipe) {
-      switch (minb) {
-        case 1: case 2: vt = make_vt<M, VEC, 2, true>(); return true;
-        case 3: vt = make_vt<M, VEC, 3, true>(); return true;
-        default: vt = make_vt<M, VEC, 4, true>(); return true;
-      }
-    }
-  }
+// Kernel variant = (slots per thread VEC, 256-thread units per block).  BMC_VARIANT="v<VEC>b<MINB>" overrides the
+// block size of a model's default among the instantiations that are built (tuning / parity tests of every shipped
+// instantiation); anything else is ignored.
+template <class M, int VEC> static bool pick_variant(const std::string& var, int def_minb, ModelVT& vt) {
+  int minb = def_minb;
+  if (var.size() == 4 && var[0] == 'v' && var[2] == 'b' && var[1] - '0' == VEC && var[3] >= '2' && var[3] <= '4') minb = var[3] - '0';
   switch (minb) {
-    case 1: case 2: vt = make_vt<M, VEC, 2>(); return true;
-    case 3: vt = make_vt<M, VEC, 3>(); return true;
-    default: vt = make_vt<M, VEC, 4>(); return true;
+    case 2: vt = make_vt<M, VEC, 2, 2>(); return true;
+    case 3: vt = make_vt<M, VEC, 3, 3>(); return true;
+    default: vt = make_vt<M, VEC, 4, 3>(); return true;
   }
 }
 

@@ -46,6 +46,60 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// -----------------------------------------------------------------------------
+// The same function with everything that does not depend on the particle hoisted to the host.
+// In the step kernel only counter word 0 (the slot index) differs between threads; step, draw
+// block and rank are launch constants.  Following the rounds with (T)hread / (U)niform values:
+//   round 0:  c0' = hi(M1*blk) ^ step ^ k0[0]   (U)        c1' = lo(M1*blk)            (U)
+//             c2' = hi(M0*c0) ^ (rank ^ k1[0])  (T)        c3' = lo(M0*c0)             (T)
+//   round 1:  c0" = hi(M1*c2') ^ (c1' ^ k0[1])  (T)        c1" = lo(M1*c2')            (T)
+//             c2" = c3' ^ (hi(M0*c0') ^ k1[1])  (T)        c3" = lo(M0*c0')            (U)
+//   round 2:  the only uniform input left is c3", folded into the key: hi(M0*c0") ^ (c3" ^ k1[2])
+// so rounds 0 and 1 cost one multiplication each instead of two, and the round keys (k + r*W)
+// come from the constant bank instead of being re-derived by every thread: 37 instructions per
+// block instead of ~66.  philox_pre() is evaluated by the host once per launch and draw block.
+// -----------------------------------------------------------------------------
+struct PhiloxPre {
+  uint32_t n2x;           // rank ^ k1[0]
+  uint32_t x2, y2, z3;    // folded uniform terms of rounds 1 and 2
+  uint32_t k0[10], k1[10];  // round keys (entries 0..1 of k0 and 0..2 of k1 are folded above)
+};
+__host__ __device__ inline PhiloxPre philox_pre(uint32_t step, uint32_t blk, uint32_t rank, uint32_t key0, uint32_t key1) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  PhiloxPre p;
+  for (int r = 0; r < 10; ++r) { p.k0[r] = key0 + (uint32_t)r * W0; p.k1[r] = key1 + (uint32_t)r * W1; }
+  const uint64_t pb = (uint64_t)M1 * blk;
+  const uint32_t a = (uint32_t)(pb >> 32) ^ step ^ p.k0[0];  // c0 after round 0
+  const uint32_t b = (uint32_t)pb;                           // c1 after round 0
+  const uint64_t pa = (uint64_t)M0 * a;
+  p.n2x = rank ^ p.k1[0];
+  p.x2 = b ^ p.k0[1];
+  p.y2 = (uint32_t)(pa >> 32) ^ p.k1[1];
+  p.z3 = (uint32_t)pa ^ p.k1[2];
+  return p;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void philox4x32_10_idx(uint32_t c0, const PhiloxPre& P, uint32_t out[4]) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  // round 0
+  uint32_t c2 = __umulhi(M0, c0) ^ P.n2x, c3 = M0 * c0;
+  // round 1
+  uint32_t n0 = __umulhi(M1, c2) ^ P.x2, c1 = M1 * c2;
+  c2 = c3 ^ P.y2; c0 = n0;
+  // round 2
+  {
+    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0, hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    c0 = hi1 ^ c1 ^ P.k0[2]; c1 = lo1; c2 = hi0 ^ P.z3; c3 = lo0;
+  }
+#pragma unroll
+  for (int r = 3; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0, hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    c0 = hi1 ^ c1 ^ P.k0[r]; c1 = lo1; c2 = hi0 ^ c3 ^ P.k1[r]; c3 = lo0;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+#endif
+
 // gen.frand(0.,1.): 24-bit uniform in [0,1)
 __host__ __device__ __forceinline__ float u01f(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 // gen.drand(): 53-bit uniform in [0,1)
