@@ -28,7 +28,7 @@ ABI_SYMBOLS = (
     "bmc_create", "bmc_destroy", "bmc_last_error", "bmc_model_dims", "bmc_set_particles", "bmc_get_particles",
     "bmc_init_particles", "bmc_set_weight", "bmc_domain_update", "bmc_set_leaving_flows", "bmc_set_concentrations",
     "bmc_get_sources", "bmc_cycle", "bmc_sync", "bmc_get_counters", "bmc_repartition", "bmc_compact", "bmc_reserve",
-    "bmc_sources_device", "bmc_concentrations_device", "bmc_stream", "bmc_launch_count", "bmc_profile_enable",
+    "bmc_sources_device", "bmc_concentrations_device", "bmc_stream", "bmc_launch_count", "bmc_kernel_config", "bmc_profile_enable",
     "bmc_profile_read", "bmc_nccl_unique_id", "bmc_comm_init", "bmc_allreduce_sources",
     "bmc_liquid_set_transition", "bmc_liquid_set_feeds", "bmc_liquid_step", "bmc_get_concentrations",
     "bmc_p2p_export", "bmc_p2p_attach", "bmc_p2p_region", "bmc_p2p_attach_local", "bmc_p2p_disable",
@@ -63,7 +63,8 @@ class BmcCounters(ctypes.Structure):
         ("last_out", ctypes.c_uint64), ("last_dead", ctypes.c_uint64), ("last_waiting_allocation", ctypes.c_uint64),
         ("buffer_index", ctypes.c_uint64), ("capacity", ctypes.c_uint64), ("total_out", ctypes.c_uint64),
         ("total_new", ctypes.c_uint64), ("n_compactions", ctypes.c_uint64), ("step", ctypes.c_uint64),
-        ("buffer_capacity", ctypes.c_uint64),
+        ("buffer_capacity", ctypes.c_uint64), ("physical_capacity", ctypes.c_uint64),
+        ("physical_buffer_capacity", ctypes.c_uint64), ("n_reallocations", ctypes.c_uint64),
     ]
 
 
@@ -180,7 +181,8 @@ class ParticleLoop:
     """
 
     def __init__(self, model, n_species=1, n_compartments=1, *, device=0, seed=2024, rank=0, capacity=0,
-                 n_var_udf=32, allocation_factor=0.0, buffer_ratio=0.0, dead_ratio=0.0, min_removal=0, udf_source=None):
+                 n_var_udf=32, allocation_factor=0.0, buffer_ratio=0.0, dead_ratio=0.0, min_removal=0, udf_source=None,
+                 shrink_ratio=0.0):
         self.lib = load_library()
         self.model = MODEL_IDS[model] if isinstance(model, str) else int(model)
         # `-mn udf_model`: source path from the argument, else env BIOMC_LIB_UDF (read by the library)
@@ -188,7 +190,7 @@ class ParticleLoop:
         cfg = BmcConfig(device=device, model=self.model, n_var_udf=n_var_udf, n_species=n_species,
                         n_compartments=n_compartments, capacity=capacity, seed=seed, rank=rank,
                         allocation_factor=allocation_factor, buffer_ratio=buffer_ratio,
-                        dead_particle_ratio_threshold=dead_ratio, shrink_ratio=0.0,
+                        dead_particle_ratio_threshold=dead_ratio, shrink_ratio=shrink_ratio,
                         minimum_dead_particle_removal=min_removal, udf_source_path=self._udf)
         self.h = ctypes.c_void_p()
         rc = self.lib.bmc_create(ctypes.byref(self.h), ctypes.byref(cfg))
@@ -320,6 +322,12 @@ class ParticleLoop:
         d = {k: int(getattr(c, k)) for k, _ in BmcCounters._fields_ if k != "events"}
         d["events"] = {EVENTS[i]: int(c.events[i]) for i in range(6)}
         return d
+
+    def kernel_config(self):
+        """launch configuration of the step kernel: which instantiation this context runs"""
+        a = (ctypes.c_int32 * 6)()
+        self._ck(self.lib.bmc_kernel_config(self.h, a))
+        return dict(vec=a[0], block=a[1], block_eager=a[2], grid=a[3], stamped_ages=bool(a[4]), smem_bytes=a[5])
 
     def repartition(self):
         out = np.empty(self.n_compartments, np.uint64)

@@ -3,11 +3,13 @@
 // No CPU fallback exists: every entry point that computes runs CUDA kernels and
 // reports BMC_ERR_CUDA if the device is unavailable.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <sched.h>
 #include <new>
 #include <string>
 #include <vector>
@@ -22,15 +24,15 @@ using namespace bmc;
 
 namespace {
 
-static bool pick_model(int model, int n_var_udf, bool large, ModelVT& vt) {
+static bool pick_model(int model, int n_var_udf, ModelVT& vt) {
   const char* v = getenv("BMC_VARIANT");
   const std::string var = v ? v : "";
   switch (model) {
-    case BMC_MODEL_FIXED_LENGTH: return pick_fixed_length(var, large, vt);
-    case BMC_MODEL_MONOD: return pick_monod(var, large, vt);
-    case BMC_MODEL_SIMPLE_ACETATE: return pick_simple_acetate(var, large, vt);
+    case BMC_MODEL_FIXED_LENGTH: return pick_fixed_length(var, vt);
+    case BMC_MODEL_MONOD: return pick_monod(var, vt);
+    case BMC_MODEL_SIMPLE_ACETATE: return pick_simple_acetate(var, vt);
     case BMC_MODEL_WIDE_UDF:
-      return n_var_udf <= 16 ? pick_wide_udf_small(var, large, n_var_udf, vt) : pick_wide_udf_large(var, large, n_var_udf, vt);
+      return n_var_udf <= 16 ? pick_wide_udf_small(var, n_var_udf, vt) : pick_wide_udf_large(var, n_var_udf, vt);
     default: return false;
   }
 }
@@ -42,7 +44,7 @@ static int (*g_nccl_destroy)(void*) = nullptr;
 struct bmc_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  int model = 0, n_var_udf = 0; bool large = false;  // large: kernel variant chosen for > kLargePopulation slots
+  int model = 0, n_var_udf = 0;
   ModelVT vt{};
   uint64_t n_species = 1, n_comp = 1;
   uint64_t seed = 0; uint32_t rank = 0;
@@ -68,11 +70,14 @@ struct bmc_ctx {
   float weight = 1.0f;
   // state
   DevState* st = nullptr;
-  DevState* h_st[2] = {nullptr, nullptr}; cudaEvent_t ev_mirror[2] = {nullptr, nullptr}; int mirror_next = 0; bool mirror_valid[2] = {false, false};
-  uint64_t host_step = 0;
-  uint64_t known_n_used = 0, known_max_add = 0;
+  DevState* h_st = nullptr;     // pinned landing buffer of sync_state
+  // capacity policy (ensure_room): zero-copy mirror written by the commit thread of every step
+  PinState* h_pin = nullptr; PinState* d_pin = nullptr;
+  uint64_t host_step = 0;       // cycles enqueued since the particles were (re)loaded
+  uint64_t recent_max_add = 0;  // decaying maximum of the newborns per step seen in the mirror
+  uint64_t pin_seen_step = ~0ull, pin_history = 0;  // last mirrored step looked at, number of distinct ones since the (re)load
+  double shrink_ratio = 0.0; bool exact_capacity = false; uint64_t n_regrow = 0;
   bool maybe_inactive = false;  // false only when the host KNOWS no slot is inactive (compaction kernels skipped)
-  int mirror_period = 8;        // asynchronous DevState mirror every this many cycles
   // launch config
   int n_sm = 148, grid_cycle = 148, blocks_per_sm = 1; size_t smem_bins = 0; int bins_in_smem = 0;
   uint64_t launches = 0;
@@ -138,16 +143,9 @@ static void free_container(bmc_ctx* c) {
 
 // ParticlesContainer::_resize + __allocate_buffer__ (particles_container.hpp:601-643, 669-685):
 // (re)allocate every column for `new_cap` slots, keeping the first `keep` slots.
-static int configure_launch(bmc_ctx* ctx);
 static int resize_container(bmc_ctx* ctx, size_t new_cap, size_t keep) {
   new_cap = round_up(std::max<size_t>(new_cap, kTile), kTile);
   if (new_cap > 0xFFFFFFF0ull) { ctx->err = "capacity exceeds 2^32 slots per context"; return BMC_ERR_RANGE; }
-  if (ctx->model != BMC_MODEL_UDF && (new_cap > kLargePopulation) != ctx->large) {  // population class changed: other block size
-    ctx->large = new_cap > kLargePopulation;
-    if (!pick_model(ctx->model, ctx->n_var_udf, ctx->large, ctx->vt)) { ctx->err = "kernel variant selection failed"; return BMC_ERR_INVALID; }
-    int rc0 = configure_launch(ctx);
-    if (rc0) return rc0;
-  }
   const int nv = ctx->vt.n_var;
   float* props = nullptr; uint32_t* pos = nullptr; uint8_t* status = nullptr; float *ah = nullptr, *ad = nullptr;
   int rc;
@@ -187,7 +185,8 @@ static int resize_container(bmc_ctx* ctx, size_t new_cap, size_t keep) {
   if ((rc = dev_alloc(ctx, &ctx->src, new_cap))) return rc;
   CK(cudaMemsetAsync(ctx->div_mask, 0, new_cap / 32 * 4, s));
   CK(cudaMemsetAsync(ctx->tile_off, 0, n_tiles * 4, s));
-  prepare_kernel<<<1, 32, 0, s>>>(ctx->st, (unsigned long long)ctx->cap, (unsigned long long)ctx->buf_cap);  // room of the new capacity
+  prepare_kernel<<<1, 32, 0, s>>>(ctx->st, (unsigned long long)ctx->cap, (unsigned long long)ctx->buf_cap, 0, ctx->allocation_factor,
+                                  ctx->buffer_ratio, ctx->d_pin);  // room of the new capacity
   if ((rc = check_launch(ctx, "prepare"))) return rc;
   CK(cudaStreamSynchronize(s));
   return BMC_OK;
@@ -259,47 +258,130 @@ static int configure_launch(bmc_ctx* ctx) {
   return BMC_OK;
 }
 
-static int refresh_mirror(bmc_ctx* ctx, bool block) {
-  // read the most recent completed asynchronous copy of DevState
-  for (int t = 0; t < 2; ++t) {
-    const int i = (ctx->mirror_next + 1 - t) & 1;  // most recent first
-    if (!ctx->mirror_valid[i]) continue;
-    cudaError_t q = block ? cudaEventSynchronize(ctx->ev_mirror[i]) : cudaEventQuery(ctx->ev_mirror[i]);
-    if (q == cudaSuccess) {
-      ctx->known_n_used = ctx->h_st[i]->n_used;
-      ctx->known_max_add = std::max<uint64_t>(ctx->known_max_add, ctx->h_st[i]->n_add);
-      return BMC_OK;
-    }
-    if (q != cudaErrorNotReady) { ctx->err = std::string("mirror: ") + cudaGetErrorString(q); return BMC_ERR_CUDA; }
+static int sync_state(bmc_ctx* ctx, DevState* out) {
+  CK(cudaMemcpyAsync(ctx->h_st, ctx->st, sizeof(DevState), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *out = *ctx->h_st;
+  if (out->inactive == 0 && ctx->flows.empty()) ctx->maybe_inactive = false;
+  if (out->error & 2u) { ctx->err = "compaction found fewer idle tail particles than gaps (inactive counter inconsistent)"; return BMC_ERR_INVALID; }
+  if (out->error & 4u) { ctx->err = "peer-memory all-reduce: a peer did not publish its sources in time"; return BMC_ERR_NCCL; }
+  if (out->error & kErrCapacity) {
+    ctx->err = "capacity exhausted: a division was refused for lack of physical room, results differ from the reference from that step on "
+               "(reserve more with bmc_reserve, or run with BMC_CAPACITY_MODE=exact)";
+    return BMC_ERR_RANGE;
   }
   return BMC_OK;
 }
 
-static int sync_state(bmc_ctx* ctx, DevState* out) {
-  CK(cudaMemcpyAsync(ctx->h_st[0], ctx->st, sizeof(DevState), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  ctx->mirror_valid[0] = ctx->mirror_valid[1] = false;
-  *out = *ctx->h_st[0];
-  ctx->known_n_used = out->n_used;
-  ctx->known_max_add = std::max<uint64_t>(ctx->known_max_add, out->n_add);
-  if (out->inactive == 0 && ctx->flows.empty()) ctx->maybe_inactive = false;
-  if (out->error & 2u) { ctx->err = "compaction found fewer idle tail particles than gaps (inactive counter inconsistent)"; return BMC_ERR_INVALID; }
-  if (out->error & 4u) { ctx->err = "peer-memory all-reduce: a peer did not publish its sources in time"; return BMC_ERR_NCCL; }
+// -----------------------------------------------------------------------------
+// Capacity policy.  The reference resizes the container inside merge_buffer (particles_container.hpp:575-643):
+// births are only ever limited by the division buffer, never by the capacity.  Here a step is enqueued without
+// waiting for the previous one, so the arrays must already be large enough when the step runs.
+//   * The device follows the reference's extents (n_allocated_elements, buffer extent) exactly in DevState
+//     (logical_alloc / logical_buf) and limits the births of a step by the LOGICAL buffer, like the reference.
+//   * The commit thread of every step writes {step, n_used, n_add, logical extents, error} into pinned host memory;
+//     the host reads that mirror before every launch without any CUDA call.
+//   * With no cycle in flight the counters are exact and one step can never add more than min(buffer, n_used)
+//     particles: the arrays are always kept large enough for that, so a launch onto an idle stream is PROVABLY safe.
+//   * Running ahead (at most kMaxAhead cycles) is allowed while the free room covers every cycle in flight at twice
+//     the largest number of newborns seen recently; otherwise the host waits on the mirror (no CUDA call) until
+//     enough cycles have committed — in the limit until the stream is idle, where it reallocates if it must.
+//   * Should the physical room bind nevertheless (births more than doubled from one step to the next while the host
+//     was ahead), the device sets kErrCapacity and every following call FAILS instead of silently counting an
+//     Overflow the reference would not have had.  BMC_CAPACITY_MODE=exact never runs ahead: it cannot fail, at the
+//     price of one launch latency per step.
+// -----------------------------------------------------------------------------
+constexpr uint64_t kMaxAhead = 4;
+
+struct PinSnap { uint64_t step, n_used, n_add, la, lb; uint32_t error; };
+// The mirror carries the low 32 bits of the step counter; the host knows the full value to within kMaxAhead + 1.
+static uint64_t widen_step(const bmc_ctx* ctx, uint32_t low) {
+  const uint64_t hs = ctx->host_step;
+  uint64_t v = (hs & ~0xffffffffull) | low;
+  if (v > hs) v -= 0x100000000ull;  // the device is never ahead of the host
+  return v;
+}
+static PinSnap read_pin(const bmc_ctx* ctx) {
+  const volatile unsigned* a = reinterpret_cast<const volatile unsigned*>(&ctx->h_pin->a);
+  const volatile unsigned* b = reinterpret_cast<const volatile unsigned*>(&ctx->h_pin->b);
+  for (;;) {  // each record arrives whole (one 16-byte write); a snapshot is consistent when both carry the same step
+    unsigned ra[4], rb[4];
+    for (int i = 0; i < 4; ++i) ra[i] = a[i];
+    std::atomic_thread_fence(std::memory_order_acquire);
+    for (int i = 0; i < 4; ++i) rb[i] = b[i];
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (ra[0] != rb[0] || a[0] != ra[0]) continue;
+    PinSnap sn;
+    sn.step = widen_step(ctx, ra[0]); sn.n_used = ra[1]; sn.n_add = ra[2]; sn.error = ra[3];
+    sn.la = ((uint64_t)(rb[1] & 0xffffu) << 32) | rb[2]; sn.lb = ((uint64_t)(rb[1] >> 16) << 32) | rb[3];
+    return sn;
+  }
+}
+static uint64_t pin_step(const bmc_ctx* ctx) {
+  return widen_step(ctx, reinterpret_cast<const volatile unsigned*>(&ctx->h_pin->a)[0]);
+}
+
+// wait on the pinned mirror (no CUDA synchronisation) until the device has committed a cycle beyond `seen`
+static int wait_commit_beyond(bmc_ctx* ctx, uint64_t seen) {
+  unsigned spins = 0;
+  while (pin_step(ctx) <= seen) {
+    if ((++spins & 0x3ffu) == 0u) {  // a fault on the device must not hang the host
+      const cudaError_t q = cudaStreamQuery(ctx->stream);
+      if (q == cudaSuccess) { if (pin_step(ctx) <= seen) { ctx->err = "device finished without committing the enqueued cycles"; return BMC_ERR_CUDA; } break; }
+      if (q != cudaErrorNotReady) { ctx->err = std::string("cudaStreamQuery: ") + cudaGetErrorString(q); return BMC_ERR_CUDA; }
+      sched_yield();
+    }
+  }
   return BMC_OK;
 }
 
-static int grow_if_needed(bmc_ctx* ctx) {
-  // Lazy capacity growth (ParticlesContainer::_resize on merge): the device clamps
-  // newborns to the free room, so this only has to run before the room runs out.
-  int rc = refresh_mirror(ctx, false);
-  if (rc) return rc;
-  const uint64_t margin = std::max<uint64_t>(4 * ctx->known_max_add, ctx->cap / 16);
-  if (ctx->known_n_used + margin <= ctx->cap) return BMC_OK;
-  DevState s;
-  if ((rc = sync_state(ctx, &s))) return rc;
-  if (s.n_used + margin <= ctx->cap) return BMC_OK;
-  const size_t new_cap = (size_t)std::ceil((double)(s.n_used + margin) * ctx->allocation_factor);
-  return resize_container(ctx, new_cap, (size_t)s.n_used);
+static uint64_t logical_alloc_after(const bmc_ctx* ctx, uint64_t la, uint64_t n) {  // _resize(n) on the logical extent
+  return n > la ? (uint64_t)std::ceil((double)n * ctx->allocation_factor) : la;
+}
+static uint64_t worst_case_births(uint64_t n, uint64_t lb) { return std::min<uint64_t>(n, lb); }  // one division per particle, up to the buffer
+static uint64_t predicted_births(uint64_t n, uint64_t recent) { return 2 * recent + n / 1024 + 64; }
+
+// slots to allocate for a container (re)constructed with n particles: the reference's ceil(n * factor), and room for
+// the worst case of one step
+static size_t initial_capacity(const bmc_ctx* ctx, uint64_t n) {
+  unsigned long long la = 0, lb = 0;
+  if (n) logical_grow(n, ctx->allocation_factor, ctx->buffer_ratio, la, lb);
+  return (size_t)std::max<uint64_t>(std::max<uint64_t>(la, n + worst_case_births(n, lb) + n / 64 + 1024), 1);
+}
+
+static int ensure_room(bmc_ctx* ctx) {
+  int rc;
+  for (;;) {
+    const PinSnap sn = read_pin(ctx);
+    if (sn.error & kErrCapacity) { DevState s; return sync_state(ctx, &s); }  // reports it
+    if (sn.step != ctx->pin_seen_step) {  // history of the newborns per step (decaying maximum)
+      ctx->recent_max_add = std::max<uint64_t>(sn.n_add, ctx->recent_max_add - ctx->recent_max_add / 8);
+      ctx->pin_seen_step = sn.step; ctx->pin_history++;
+    }
+    const uint64_t d = ctx->host_step - sn.step;  // cycles in flight
+    const uint64_t room = ctx->cap > sn.n_used ? ctx->cap - sn.n_used : 0;
+    if (d == 0) {
+      // idle stream: exact counters, provable bound
+      if (room >= worst_case_births(sn.n_used, sn.lb) && sn.lb <= ctx->buf_cap && sn.la <= ctx->cap) return BMC_OK;
+      DevState s;
+      if ((rc = sync_state(ctx, &s))) return rc;
+      const uint64_t n = s.n_used, pred = predicted_births(n, std::max<uint64_t>(s.n_add, ctx->recent_max_add));
+      uint64_t want = n + worst_case_births(n, s.logical_buf) + n / 64 + 1024;
+      want = std::max<uint64_t>(want, (uint64_t)std::ceil((double)(n + (kMaxAhead + 1) * pred) * ctx->allocation_factor));
+      want = std::max<uint64_t>(want, s.logical_alloc);
+      want = std::max<uint64_t>(want, (uint64_t)std::ceil((double)s.logical_buf / ctx->buffer_ratio));
+      if (want <= ctx->cap) return BMC_OK;  // (only the pinned mirror was behind)
+      ctx->n_regrow++;
+      return resize_container(ctx, (size_t)want, (size_t)n);
+    }
+    if (!ctx->exact_capacity && d <= kMaxAhead && ctx->pin_history >= 2) {
+      const uint64_t pred = predicted_births(sn.n_used, std::max<uint64_t>(sn.n_add, ctx->recent_max_add));
+      const uint64_t la_next = logical_alloc_after(ctx, sn.la, sn.n_used + d * pred);  // a logical resize enlarges the logical buffer
+      const uint64_t lb_next = std::max<uint64_t>(sn.lb, (uint64_t)std::ceil(ctx->buffer_ratio * (double)la_next));
+      if (room >= (d + 1) * pred && lb_next <= ctx->buf_cap && la_next <= ctx->cap) return BMC_OK;
+    }
+    if ((rc = wait_commit_beyond(ctx, sn.step))) return rc;  // not covered: let the device catch up, then look again
+  }
 }
 
 static void fill_post_params(bmc_ctx* ctx, PostParams& ip) {
@@ -316,6 +398,7 @@ static void fill_post_params(bmc_ctx* ctx, PostParams& ip) {
   ip.acc_fix = ctx->d_acc_fix; ip.weight = (double)ctx->weight; ip.n_species = (uint32_t)ctx->n_species; ip.n_c = ctx->vt.n_c;
   ip.vec = ctx->vt.vec;
   ip.min_removal = ctx->min_removal; ip.dead_ratio = ctx->dead_ratio;
+  ip.allocation_factor = ctx->allocation_factor; ip.buffer_ratio = ctx->buffer_ratio; ip.shrink_ratio = ctx->shrink_ratio; ip.pin = ctx->d_pin;
 }
 
 // ---- step-stamped ages: host side ---------------------------------------------------------
@@ -391,25 +474,27 @@ int bmc_create(bmc_ctx** out, const bmc_config* cfg) {
     const char* path = cfg->udf_source_path ? cfg->udf_source_path : getenv("BIOMC_LIB_UDF");
     if (!path) { ctx->err = "BMC_MODEL_UDF needs udf_source_path or BIOMC_LIB_UDF"; return fail(BMC_ERR_INVALID); }
     if (!load_udf_model(path, ctx->vt, ctx->err)) return fail(BMC_ERR_UNSUPPORTED);
-  } else if (!pick_model(cfg->model, cfg->n_var_udf, cfg->capacity > kLargePopulation, ctx->vt)) { ctx->err = "unknown model / unsupported n_var_udf"; return fail(BMC_ERR_INVALID); }
+  } else if (!pick_model(cfg->model, cfg->n_var_udf, ctx->vt)) { ctx->err = "unknown model / unsupported n_var_udf"; return fail(BMC_ERR_INVALID); }
   if ((uint64_t)ctx->vt.n_c > cfg->n_species) { ctx->err = "model n_c exceeds n_species"; return fail(BMC_ERR_INVALID); }
-  ctx->device = cfg->device; ctx->model = cfg->model; ctx->n_var_udf = cfg->n_var_udf; ctx->large = cfg->capacity > kLargePopulation;
+  ctx->device = cfg->device; ctx->model = cfg->model; ctx->n_var_udf = cfg->n_var_udf;
   ctx->n_species = cfg->n_species; ctx->n_comp = cfg->n_compartments;
   ctx->seed = cfg->seed; ctx->rank = cfg->rank;
   if (cfg->allocation_factor > 0) ctx->allocation_factor = std::max(1.0, cfg->allocation_factor);
   if (cfg->buffer_ratio > 0) ctx->buffer_ratio = std::min(1.0, cfg->buffer_ratio);
   if (cfg->dead_particle_ratio_threshold > 0) ctx->dead_ratio = cfg->dead_particle_ratio_threshold;
   ctx->min_removal = cfg->minimum_dead_particle_removal;
+  if (cfg->shrink_ratio > 0) ctx->shrink_ratio = cfg->shrink_ratio;
   cudaError_t e = cudaSetDevice(ctx->device);
   if (e != cudaSuccess) { ctx->err = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return fail(BMC_ERR_CUDA); }
   auto ck = [&](cudaError_t e2, const char* w) { if (e2 != cudaSuccess) { ctx->err = std::string(w) + ": " + cudaGetErrorString(e2); return false; } return true; };
   if (!ck(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return fail(BMC_ERR_CUDA);
   if (!ck(cudaMalloc((void**)&ctx->st, sizeof(DevState)), "cudaMalloc state")) return fail(BMC_ERR_NOMEM);
   if (!ck(cudaMemset(ctx->st, 0, sizeof(DevState)), "memset state")) return fail(BMC_ERR_CUDA);
-  for (int i = 0; i < 2; ++i) {
-    if (!ck(cudaMallocHost((void**)&ctx->h_st[i], sizeof(DevState)), "cudaMallocHost")) return fail(BMC_ERR_NOMEM);
-    if (!ck(cudaEventCreateWithFlags(&ctx->ev_mirror[i], cudaEventDisableTiming), "cudaEventCreate")) return fail(BMC_ERR_CUDA);
-  }
+  if (!ck(cudaMallocHost((void**)&ctx->h_st, sizeof(DevState)), "cudaMallocHost")) return fail(BMC_ERR_NOMEM);
+  if (!ck(cudaHostAlloc((void**)&ctx->h_pin, sizeof(PinState), cudaHostAllocMapped), "cudaHostAlloc")) return fail(BMC_ERR_NOMEM);
+  memset(ctx->h_pin, 0, sizeof(PinState));
+  if (!ck(cudaHostGetDevicePointer((void**)&ctx->d_pin, ctx->h_pin, 0), "cudaHostGetDevicePointer")) return fail(BMC_ERR_CUDA);
+  if (const char* e = getenv("BMC_CAPACITY_MODE")) ctx->exact_capacity = std::string(e) == "exact";
   const size_t nb = ctx->n_species * ctx->n_comp;
   int rc;
   if ((rc = dev_alloc(ctx, &ctx->d_conc, nb)) || (rc = dev_alloc(ctx, &ctx->d_sources, nb)) || (rc = dev_alloc(ctx, &ctx->d_acc, nb)) ||
@@ -458,7 +543,8 @@ int bmc_destroy(bmc_ctx** h) {
   dev_free(c->d_tab_div); dev_free(c->d_tab_hyd);
   dev_free(c->st);
   if (c->d_stage) cudaFree(c->d_stage);
-  for (int i = 0; i < 2; ++i) { if (c->h_st[i]) cudaFreeHost(c->h_st[i]); if (c->ev_mirror[i]) cudaEventDestroy(c->ev_mirror[i]); }
+  if (c->h_st) cudaFreeHost(c->h_st);
+  if (c->h_pin) cudaFreeHost(c->h_pin);
   for (int i = 0; i < bmc_ctx::kPinRing; ++i) { if (c->h_pin_in[i]) cudaFreeHost(c->h_pin_in[i]); if (c->ev_pin_in[i]) cudaEventDestroy(c->ev_pin_in[i]); }
   if (c->h_pin_out) cudaFreeHost(c->h_pin_out);
   for (auto& pr : c->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -492,8 +578,8 @@ int bmc_set_particles(bmc_ctx* ctx, uint64_t n, const float* props, const uint64
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   int rc;
-  const size_t want = (size_t)std::ceil((double)n * ctx->allocation_factor);
-  if (want > ctx->cap || ctx->cap == 0) { if ((rc = resize_container(ctx, std::max<size_t>(want, n), 0))) return rc; }
+  const size_t want = initial_capacity(ctx, n);
+  if (want > ctx->cap || ctx->cap == 0) { if ((rc = resize_container(ctx, want, 0))) return rc; }
   cudaStream_t s = ctx->stream;
   const int nv = ctx->vt.n_var;
   for (int k = 0; k < nv; ++k)
@@ -534,13 +620,14 @@ int bmc_set_particles(bmc_ctx* ctx, uint64_t n, const float* props, const uint64
     if ((rc = check_launch(ctx, "count_inactive"))) return rc;
   }
   CK(cudaMemcpyAsync(&ctx->st->n_used, &n, 8, cudaMemcpyHostToDevice, s));
-  prepare_kernel<<<1, 32, 0, s>>>(ctx->st, (unsigned long long)ctx->cap, (unsigned long long)ctx->buf_cap);
+  prepare_kernel<<<1, 32, 0, s>>>(ctx->st, (unsigned long long)ctx->cap, (unsigned long long)ctx->buf_cap, 1, ctx->allocation_factor,
+                                  ctx->buffer_ratio, ctx->d_pin);
   if ((rc = check_launch(ctx, "prepare"))) return rc;
   DevState hs;
   if ((rc = sync_state(ctx, &hs))) return rc;
   if (hs.error & 1u) { ctx->err = "particle position out of range"; return BMC_ERR_RANGE; }
   ctx->maybe_inactive = hs.inactive != 0;
-  ctx->host_step = 0; ctx->known_max_add = 0;
+  ctx->host_step = 0; ctx->recent_max_add = 0; ctx->pin_seen_step = ~0ull; ctx->pin_history = 0;
   return BMC_OK;
 }
 
@@ -591,7 +678,7 @@ int bmc_init_particles(bmc_ctx* ctx, uint64_t n, int uniform_position, const flo
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   int rc;
-  const size_t want = (size_t)std::ceil((double)n * ctx->allocation_factor);
+  const size_t want = initial_capacity(ctx, n);
   if (want > ctx->cap || ctx->cap == 0) { if ((rc = resize_container(ctx, want, 0))) return rc; }
   cudaStream_t s = ctx->stream;
   float* d_linit = nullptr;
@@ -610,13 +697,14 @@ int bmc_init_particles(bmc_ctx* ctx, uint64_t n, int uniform_position, const flo
   CK(cudaLaunchKernel(ctx->vt.init_fn, dim3(grid), dim3(256), iargs, 0, s));
   if ((rc = check_launch(ctx, "init_kernel"))) return rc;
   CK(cudaMemcpyAsync(&ctx->st->n_used, &n, 8, cudaMemcpyHostToDevice, s));
-  prepare_kernel<<<1, 32, 0, s>>>(ctx->st, (unsigned long long)ctx->cap, (unsigned long long)ctx->buf_cap);
+  prepare_kernel<<<1, 32, 0, s>>>(ctx->st, (unsigned long long)ctx->cap, (unsigned long long)ctx->buf_cap, 1, ctx->allocation_factor,
+                                  ctx->buffer_ratio, ctx->d_pin);
   if ((rc = check_launch(ctx, "prepare"))) return rc;
   DevState hs;
   if ((rc = sync_state(ctx, &hs))) return rc;
   if (total_mass) *total_mass = hs.init_mass;
   ctx->maybe_inactive = false;
-  ctx->host_step = 0; ctx->known_max_add = 0;
+  ctx->host_step = 0; ctx->recent_max_add = 0; ctx->pin_seen_step = ~0ull; ctx->pin_history = 0;
   return BMC_OK;
 }
 
@@ -778,7 +866,7 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   if (ctx->n_comp > 1 && !ctx->domain_set) { ctx->err = "multi-compartment case without bmc_domain_update"; return BMC_ERR_INVALID; }
   CK(cudaSetDevice(ctx->device));
   int rc;
-  if ((rc = grow_if_needed(ctx))) return rc;
+  if ((rc = ensure_room(ctx))) return rc;
   cudaStream_t s = ctx->stream;
   const bool enable_move = ctx->n_comp > 1;        // kernels.hpp:53-55
   const bool enable_leave = !ctx->flows.empty();   // kernels.hpp:56
@@ -862,14 +950,6 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   if (ctx->profile) { CK(cudaEventRecord(e1, s)); ctx->prof_used++; }
   if (enable_leave) ctx->maybe_inactive = true;  // exits may happen from now on
 
-  // asynchronous mirror of the device bookkeeping (never waited on here)
-  if (ctx->host_step % (uint64_t)ctx->mirror_period == 0) {
-    const int mi = ctx->mirror_next;
-    CK(cudaMemcpyAsync(ctx->h_st[mi], ctx->st, sizeof(DevState), cudaMemcpyDeviceToHost, s));
-    CK(cudaEventRecord(ctx->ev_mirror[mi], s));
-    ctx->mirror_valid[mi] = true;
-    ctx->mirror_next ^= 1;
-  }
   ctx->host_step++;
   return BMC_OK;
 }
@@ -888,9 +968,10 @@ int bmc_get_counters(bmc_ctx* ctx, bmc_counters* out) {
   if ((rc = sync_state(ctx, &s))) return rc;
   for (int i = 0; i < BMC_N_EVENTS; ++i) out->events[i] = s.events[i];
   out->n_used = s.n_used; out->n_inactive = s.inactive; out->last_out = s.last_out; out->last_dead = s.last_dead;
-  out->last_waiting_allocation = s.last_waiting; out->buffer_index = 0; out->capacity = ctx->cap;
+  out->last_waiting_allocation = s.last_waiting; out->buffer_index = 0; out->capacity = s.logical_alloc;
   out->total_out = s.total_out; out->total_new = s.total_new; out->n_compactions = s.n_compactions; out->step = s.step;
-  out->buffer_capacity = ctx->buf_cap;
+  out->buffer_capacity = s.logical_buf;
+  out->physical_capacity = ctx->cap; out->physical_buffer_capacity = ctx->buf_cap; out->n_reallocations = ctx->n_regrow;
   return BMC_OK;
 }
 
@@ -980,6 +1061,7 @@ struct CkptHeader {
   uint32_t epoch_set, epoch_leave;
   uint64_t tab_entries;     // lazy ages: entries of each age table that follow
   float src_bound[8], src_scale[8];  // fixed-point scatter state (DevState): a resumed run adds up the very same integers
+  uint64_t logical_alloc, logical_buf;  // n_allocated_elements / buffer extent of the reference's container (serde.cpp archives n_allocated)
 };
 }  // namespace
 
@@ -1018,6 +1100,7 @@ int bmc_checkpoint_save(bmc_ctx* ctx, void* buffer, uint64_t bytes) {
   h.epoch_dt = ctx->epoch_dt; h.min_removal = ctx->min_removal; h.epoch_set = ctx->epoch_set ? 1u : 0u; h.epoch_leave = ctx->epoch_leave ? 1u : 0u;
   h.tab_entries = tab;
   for (int i = 0; i < 8; ++i) { h.src_bound[i] = hs.src_bound[i]; h.src_scale[i] = hs.src_scale[i]; }
+  h.logical_alloc = hs.logical_alloc; h.logical_buf = hs.logical_buf;
   unsigned char* o = (unsigned char*)buffer;
   memcpy(o, &h, sizeof(h)); o += sizeof(h);
   cudaStream_t s = ctx->stream;
@@ -1055,7 +1138,7 @@ int bmc_checkpoint_load(bmc_ctx* ctx, const void* buffer, uint64_t bytes) {
   int rc;
   ctx->seed = h.seed; ctx->rank = (uint32_t)h.rank; ctx->weight = (float)h.weight;
   ctx->allocation_factor = h.allocation_factor; ctx->buffer_ratio = h.buffer_ratio; ctx->dead_ratio = h.dead_ratio; ctx->min_removal = h.min_removal;
-  const size_t want = std::max<size_t>((size_t)std::ceil((double)n * ctx->allocation_factor), std::max<size_t>((size_t)n, 1));
+  const size_t want = std::max<size_t>(initial_capacity(ctx, n), (size_t)h.logical_alloc);
   if (want > ctx->cap || ctx->cap == 0) { if ((rc = resize_container(ctx, want, 0))) return rc; }
   cudaStream_t s = ctx->stream;
   const unsigned char* in = (const unsigned char*)buffer + sizeof(h);
@@ -1082,13 +1165,15 @@ int bmc_checkpoint_load(bmc_ctx* ctx, const void* buffer, uint64_t bytes) {
   ds.last_out = h.last_out; ds.last_dead = h.last_dead; ds.last_waiting = h.last_waiting; ds.step = h.step;
   for (int i = 0; i < 6; ++i) ds.events[i] = h.events[i];
   for (int i = 0; i < 8; ++i) { ds.src_bound[i] = h.src_bound[i]; ds.src_scale[i] = h.src_scale[i]; }
+  ds.logical_alloc = h.logical_alloc; ds.logical_buf = h.logical_buf;
   CK(cudaMemcpyAsync(ctx->st, &ds, sizeof(ds), cudaMemcpyHostToDevice, s));
-  prepare_kernel<<<1, 32, 0, s>>>(ctx->st, (unsigned long long)ctx->cap, (unsigned long long)ctx->buf_cap);
+  prepare_kernel<<<1, 32, 0, s>>>(ctx->st, (unsigned long long)ctx->cap, (unsigned long long)ctx->buf_cap, 0, ctx->allocation_factor,
+                                  ctx->buffer_ratio, ctx->d_pin);
   if ((rc = check_launch(ctx, "prepare"))) return rc;
   DevState hs;
   if ((rc = sync_state(ctx, &hs))) return rc;  // also waits for the copies out of the caller's buffer
   ctx->maybe_inactive = h.inactive != 0 || !ctx->flows.empty();
-  ctx->host_step = h.step; ctx->known_max_add = 0;
+  ctx->host_step = h.step; ctx->recent_max_add = 0; ctx->pin_seen_step = ~0ull; ctx->pin_history = 0;
   return BMC_OK;
 }
 
@@ -1128,6 +1213,12 @@ int bmc_stream(bmc_ctx* ctx, void** s) {
 int bmc_launch_count(const bmc_ctx* ctx, uint64_t* n) {
   if (!ctx || !n) return BMC_ERR_INVALID;
   *n = ctx->launches;
+  return BMC_OK;
+}
+int bmc_kernel_config(const bmc_ctx* ctx, int32_t* out6) {
+  if (!ctx || !out6) return BMC_ERR_INVALID;
+  out6[0] = ctx->vt.vec; out6[1] = ctx->vt.block; out6[2] = ctx->vt.block_eager;
+  out6[3] = ctx->lazy_ages ? ctx->grid_cycle : ctx->grid_cycle_eager; out6[4] = ctx->lazy_ages ? 1 : 0; out6[5] = (int32_t)ctx->smem_total;
   return BMC_OK;
 }
 int bmc_profile_enable(bmc_ctx* ctx, int on) {

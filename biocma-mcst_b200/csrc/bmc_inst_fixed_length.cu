@@ -2,5 +2,5 @@
 #include "bmc_model_vt.cuh"
 
 namespace bmc {
-bool pick_fixed_length(const std::string& var, bool large, ModelVT& vt) { return pick_variant<FixedLength, 4>(var, large ? 3 : 4, vt); }
+bool pick_fixed_length(const std::string& var, ModelVT& vt) { return pick_variant<FixedLength, 4, 4, 3>(var, vt); }
 }  // namespace bmc

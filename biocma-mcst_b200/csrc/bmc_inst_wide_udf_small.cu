@@ -2,9 +2,9 @@
 #include "bmc_model_vt.cuh"
 
 namespace bmc {
-bool pick_wide_udf_small(const std::string& var, bool large, int n_var, ModelVT& vt) {
-  if (n_var == 8) return pick_variant<WideUdf<8>, 4>(var, large ? 3 : 4, vt);
-  if (n_var == 16) return pick_variant<WideUdf<16>, 2>(var, 3, vt);
+bool pick_wide_udf_small(const std::string& var, int n_var, ModelVT& vt) {
+  if (n_var == 8) return pick_variant<WideUdf<8>, 4, 4, 3>(var, vt);
+  if (n_var == 16) return pick_variant<WideUdf<16>, 2, 3>(var, vt);
   return false;
 }
 }  // namespace bmc

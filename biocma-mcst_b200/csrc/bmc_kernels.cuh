@@ -77,8 +77,38 @@ struct DevState {
   // largest |contribution| admitted to the integer bins this step, the power-of-two scale applied to it, and the
   // running maximum observed this step (float bits; the commit thread derives the next step's bound/scale from it)
   float src_bound[8]; float src_scale[8]; unsigned int src_max[8];
+  // the reference's container bookkeeping, followed exactly (particles_container.hpp:575-643, 669-685, 784-797):
+  // n_allocated_elements and the extent of the division buffer.  The buffer room of a step is the LOGICAL extent;
+  // the physical arrays (PostParams::cap / buf_cap) are kept ahead of it by the host (bmc_api.cu: ensure_room).
+  unsigned long long logical_alloc, logical_buf;
   unsigned long long dbg[16];       // BMC_TIMELINE builds: %globaltimer stamps of block 0 (tuning only)
 };
+
+// Host-visible mirror of the counters the capacity policy needs, written by the commit thread of every step into
+// pinned, device-mapped host memory: the host reads it without any CUDA call (bmc_api.cu: ensure_room).
+// Two 16-byte records, each written with ONE vector store (a single PCIe write: never torn), both tagged with the
+// step they belong to: the host takes a snapshot when the tags agree.  No fence, no dependent store — the commit
+// thread does not wait for host memory.
+struct PinState {
+  uint4 a;   // { step (low 32 bits), n_used, n_add (saturated), error }
+  uint4 b;   // { step (low 32 bits), logical_alloc >> 32 | (logical_buf >> 32) << 16, logical_alloc low, logical_buf low }
+};
+__device__ __forceinline__ void pin_write(PinState* pin, unsigned long long step, unsigned long long n_used, unsigned long long n_add,
+                                          unsigned long long la, unsigned long long lb, unsigned error) {
+  const unsigned add32 = n_add > 0xffffffffull ? 0xffffffffu : (unsigned)n_add;
+  const unsigned b1 = (unsigned)((la >> 32) & 0xffffu) | ((unsigned)((lb >> 32) & 0xffffu) << 16);
+  asm volatile("st.volatile.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(&pin->b), "r"((unsigned)step), "r"(b1), "r"((unsigned)la), "r"((unsigned)lb) : "memory");
+  asm volatile("st.volatile.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(&pin->a), "r"((unsigned)step), "r"((unsigned)n_used), "r"(add32), "r"(error) : "memory");
+}
+constexpr unsigned kErrCapacity = 8u;  // DevState::error: a division was refused for lack of PHYSICAL room (host policy failed)
+
+// merge_buffer's _resize + __allocate_buffer__ on the logical extents (particles_container.hpp:575-643, 669-685)
+__host__ __device__ inline void logical_grow(unsigned long long new_size, double allocation_factor, double buffer_ratio,
+                                             unsigned long long& la, unsigned long long& lb) {
+  if (new_size > 0ull && new_size > la) la = (unsigned long long)ceil((double)new_size * allocation_factor);
+  const unsigned long long req = (unsigned long long)ceil(buffer_ratio * (double)la);
+  if (lb < req) lb = req;
+}
 
 struct Outlet { uint32_t index; uint32_t pad; double flow; double dt_flow; double volume; };
 
@@ -120,6 +150,8 @@ struct PostParams {
   unsigned long long* acc_fix; double weight; uint32_t n_species; int n_c;  // fixed-point bins of the step kernel (publish: sources = w * fix / scale + acc)
   int vec;  // slots per thread of the step kernel: layout of div_mask (VEC ballot words per group of 32*VEC slots)
   unsigned long long min_removal; double dead_ratio;  // RuntimeParameters of update_and_remove_inactive
+  double allocation_factor, buffer_ratio, shrink_ratio;  // RuntimeParameters of _resize / __allocate_buffer__ / remove_inactive_particles
+  PinState* pin;                                         // device pointer of the pinned host mirror
   int count_step;  // 1 when called from a cycle, 0 from force_remove_dead
   // step-stamped ages (bmc_kernels.cuh): stamp given to newborns (0 = eager float ages, bits of 0.f)
   // and the per-step extension of the age tables A_div / A_hyd
@@ -626,10 +658,24 @@ static __device__ __forceinline__ void post_cycle_body(const PostParams& p) {
     st->n_used = n;
     st->total_new += n_add;
     st->step += (unsigned long long)p.count_step;
-    // room of the next step's division buffer: min(B, capacity - n_used); the device can never write
-    // past the capacity, growth is done lazily by the host
+    // the reference's extents after this post_cycle: shrink after a compaction (remove_inactive_particles,
+    // particles_container.hpp:784-797), _resize + __allocate_buffer__ in merge_buffer (:575-599, returns early
+    // without newborns)
+    unsigned long long la = st->logical_alloc, lb = st->logical_buf;
+    if (s_plan[3] > s_plan[4] && s_plan[4] < lb) atomicOr(&st->error, kErrCapacity);  // divisions refused by the PHYSICAL room
+    if (do_compact && new_n != 0ull && new_n <= (unsigned long long)(p.shrink_ratio * (double)la)) {
+      const unsigned long long ns = (unsigned long long)((double)new_n * p.allocation_factor);
+      if (ns > 0ull) la = (unsigned long long)ceil((double)ns * p.allocation_factor);  // _resize(n_used * factor, force)
+    }
+    if (n_add) logical_grow(n, p.allocation_factor, p.buffer_ratio, la, lb);
+    st->logical_alloc = la; st->logical_buf = lb;
+    // room of the next step's division buffer: the logical extent, bounded by the physical arrays (the device can
+    // never write past them; the host keeps them ahead, and kErrCapacity reports it if it did not)
     const unsigned long long room = p.cap > n ? p.cap - n : 0ull;
-    st->buf_cap_eff = p.buf_cap < room ? p.buf_cap : room;
+    unsigned long long eff = lb < p.buf_cap ? lb : p.buf_cap;
+    st->buf_cap_eff = eff < room ? eff : room;
+    // host mirror (zero-copy), as early as the values exist: the stores travel while the rest of the commit runs
+    if (p.pin) pin_write(p.pin, st->step, n, n_add, la, lb, *reinterpret_cast<volatile unsigned*>(&st->error));
     if (p.count_step) {
       // Fixed-point scatter of the particle pass: next step's admission bound and scale per species from this step's
       // largest |contribution| m, with m < 2^e_m and n <= 2^e_n particles:

@@ -10,13 +10,23 @@ namespace bmc {
 // without a particle pass: the second phase of the step kernel on its own (cooperative launch)
 __global__ void __launch_bounds__(kBlock) post_only_kernel(const __grid_constant__ PostParams p) { post_cycle_body(p); }
 
-// host events that change n_used or the capacity (set/init particles, resize): next step's buffer room
-__global__ void prepare_kernel(DevState* st, unsigned long long cap, unsigned long long buf_cap) {
+// host events that change n_used or the capacity (set/init/load particles, resize): next step's buffer room.
+// `reset_logical`: the container was (re)constructed with n_used particles -> the reference's constructor extents
+// (_resize(n_particle) + __allocate_buffer__ on an empty container, particles_container.hpp:692-727)
+__global__ void prepare_kernel(DevState* st, unsigned long long cap, unsigned long long buf_cap, int reset_logical,
+                               double allocation_factor, double buffer_ratio, PinState* pin) {
   if (blockIdx.x || threadIdx.x) return;
   const unsigned long long n = st->n_used;
+  if (reset_logical) {
+    unsigned long long la = 0ull, lb = 0ull;
+    if (n) logical_grow(n, allocation_factor, buffer_ratio, la, lb);
+    st->logical_alloc = la; st->logical_buf = lb;
+  }
   const unsigned long long room = cap > n ? cap - n : 0ull;
-  st->buf_cap_eff = buf_cap < room ? buf_cap : room;
+  const unsigned long long eff = st->logical_buf < buf_cap ? st->logical_buf : buf_cap;
+  st->buf_cap_eff = eff < room ? eff : room;
   st->buf_index = 0; st->step_exit = 0; st->step_waiting = 0;
+  if (pin) pin_write(pin, st->step, n, 0ull, st->logical_alloc, st->logical_buf, st->error);
 }
 
 // ---- step-stamped ages -> floats -------------------------------------------------

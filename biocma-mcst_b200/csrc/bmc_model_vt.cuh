@@ -37,29 +37,25 @@ template <class M, int VEC, int MINB, int MINB_E> static ModelVT make_vt() {
   return v;
 }
 
-// Kernel variant = (slots per thread VEC, 256-thread units per block).  BMC_VARIANT="v<VEC>b<MINB>" overrides the
-// block size of a model's default among the instantiations that are built (tuning / parity tests of every shipped
-// instantiation); anything else is ignored.
-template <class M, int VEC> static bool pick_variant(const std::string& var, int def_minb, ModelVT& vt) {
-  int minb = def_minb;
-  if (var.size() == 4 && var[0] == 'v' && var[2] == 'b' && var[1] - '0' == VEC && var[3] >= '2' && var[3] <= '4') minb = var[3] - '0';
-  switch (minb) {
-    case 2: vt = make_vt<M, VEC, 2, 2>(); return true;
-    case 3: vt = make_vt<M, VEC, 3, 3>(); return true;
-    default: vt = make_vt<M, VEC, 4, 3>(); return true;
+// Kernel variant = (slots per thread VEC, 256-thread units per block).  Every model ships its default and at most one
+// alternative block size; BMC_VARIANT="v<VEC>b<MINB>" selects the alternative (tuning runs, and the parity tests that
+// cover every instantiation in the library), anything else is ignored.
+//   DEF = 4: 1024 threads x <= 64 registers (eager ages: 768 x <= 80), ALT = 3: 768 x <= 80
+template <class M, int VEC, int DEF, int ALT = DEF> static bool pick_variant(const std::string& var, ModelVT& vt) {
+  constexpr int DEF_E = DEF > 3 ? 3 : DEF, ALT_E = ALT > 3 ? 3 : ALT;
+  if (ALT != DEF && var.size() == 4 && var[0] == 'v' && var[2] == 'b' && var[1] - '0' == VEC && var[3] - '0' == ALT) {
+    vt = make_vt<M, VEC, ALT, ALT_E>();
+    return true;
   }
+  vt = make_vt<M, VEC, DEF, DEF_E>();
+  return true;
 }
 
-// `large`: more than kLargePopulation slots.  With 1024-thread blocks (WB 4) the particle pass was
-// measured to fall into a ~1.9x slower mode on large populations (1e8 particles: 1620-1750 us per step
-// against 990-1050 us with 768 threads), while it is the fastest choice at 1e7 (104 vs 117 us); the
-// 768-thread variant never showed that mode, so it is the default above the threshold.
-constexpr size_t kLargePopulation = 24u * 1000u * 1000u;
-bool pick_fixed_length(const std::string& var, bool large, ModelVT& vt);
-bool pick_monod(const std::string& var, bool large, ModelVT& vt);
-bool pick_simple_acetate(const std::string& var, bool large, ModelVT& vt);
-bool pick_wide_udf_small(const std::string& var, bool large, int n_var, ModelVT& vt);   // P = 8, 16
-bool pick_wide_udf_large(const std::string& var, bool large, int n_var, ModelVT& vt);   // P = 32, 64
+bool pick_fixed_length(const std::string& var, ModelVT& vt);
+bool pick_monod(const std::string& var, ModelVT& vt);
+bool pick_simple_acetate(const std::string& var, ModelVT& vt);
+bool pick_wide_udf_small(const std::string& var, int n_var, ModelVT& vt);   // P = 8, 16
+bool pick_wide_udf_large(const std::string& var, int n_var, ModelVT& vt);   // P = 32, 64
 // BMC_MODEL_UDF: NVRTC-compile a user model source against these headers (bmc_udf.cu)
 bool load_udf_model(const char* source_path, ModelVT& vt, std::string& err);
 void unload_udf_model(ModelVT& vt);

@@ -16,7 +16,7 @@ int main() {
     std::vector<float> props(2 * size, 1.5e-6f);
     unit.check(bmc_set_particles(unit.handle(), size, props.data(), nullptr, nullptr, nullptr, nullptr));
     CHECK(unit.n_particles() == size);
-    CHECK(unit.capacity() >= size * 1.5 && unit.capacity() % 1024 == 0);  // capacity() == N*alloc_factor, rounded to whole tiles
+    CHECK(unit.capacity() == size * 3 / 2);  // capacity() == size * get_allocation_factor() (test_container.cpp:18-19): the LOGICAL extent
     CHECK(unit.get_inactive() == 0);
   }
   {  // div_test / merge_test :56-103 — ndiv mothers at l >= l_max divide in one cycle and are merged

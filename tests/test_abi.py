@@ -25,7 +25,7 @@ def test_header_symbols_exported(bmc):
 
 def test_struct_layouts_match_header(bmc):
     assert ctypes.sizeof(bmc.BmcLeavingFlow) == 24
-    assert ctypes.sizeof(bmc.BmcCounters) == 8 * (6 + 12)
+    assert ctypes.sizeof(bmc.BmcCounters) == 8 * (6 + 15)
     assert ctypes.sizeof(bmc.BmcConfig) == 16 + 8 * 4 + 8 + 8 * 4 + 8 + 8
 
 

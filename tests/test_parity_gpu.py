@@ -251,20 +251,71 @@ def test_large_compartment_tables(bmc, orc, synth):
 
 
 def test_capacity_growth_is_transparent(bmc, orc, synth):
-    # population doubles several times: the device container is grown by the host from its view of
-    # n_used (ParticlesContainer::_resize, particles_container.hpp:601-643) and the state survives
-    # every reallocation.  The device never writes past the capacity: newborns beyond the free room
-    # would be counted as Overflow (like a full buffer), so the case leaves room for a doubling.
-    case = util.make_case(synth, "fixed_length", 30_000, 16, dt=600.0, near_division=0.5, p_move=0.3, outlet=False)
-    g, o = _pair(bmc, orc, case, allocation_factor=2.5)
+    # The population grows 5x with the reference's DEFAULT runtime parameters (allocation factor 1.5, buffer ratio 0.6)
+    # and NO host synchronisation between the steps: the host follows the device through the pinned mirror, enlarges
+    # the arrays ahead of the population, and the device follows the reference's logical extents (capacity(), buffer
+    # extent: ParticlesContainer::_resize / __allocate_buffer__, particles_container.hpp:601-685) exactly.
+    case = util.make_case(synth, "fixed_length", 30_000, 16, dt=300.0, near_division=0.5, p_move=0.3, outlet=False)
+    g, o = _pair(bmc, orc, case, allocation_factor=1.5, buffer_ratio=0.6)
     util.load_case(g, case); util.load_case(o, case)
-    for s in range(14):
-        util.run_steps(g, case, 1); util.run_steps(o, case, 1)
-        g.counters()  # synchronous read refreshes the host's view -> growth happens before it is needed
+    util.run_steps(g, case, 40); util.run_steps(o, case, 40)
     cg, co = g.counters(), o.counters()
-    assert co["n_used"] > 4 * case["n"] and cg["capacity"] > 2.5 * case["n"] * 2 and cg["events"]["Overflow"] == 0
+    assert co["n_used"] > 4 * case["n"] and cg["n_reallocations"] >= 2 and cg["events"]["Overflow"] == co["events"]["Overflow"]
+    assert cg["capacity"] == co["capacity"] and cg["buffer_capacity"] == co["buffer_capacity"]   # the reference's extents, exactly
+    assert cg["physical_capacity"] >= cg["capacity"]
     util.assert_counters_equal(cg, co)
     util.assert_state_equal(g.get_particles(co["n_used"]), o.get_particles(co["n_used"]), co["n_used"])
+
+
+def _burst_case(synth, n=200_000):
+    # quiet for three steps, then EVERY cell divides in the same step (a synchronised culture)
+    case = util.make_case(synth, "fixed_length", n, 16, dt=100.0, p_move=0.3, outlet=False)
+    case["props"][0][:] = np.float32(1.9995e-6)
+    return case
+
+
+def test_capacity_exact_mode_survives_a_synchronised_burst(bmc, orc, synth, monkeypatch):
+    # BMC_CAPACITY_MODE=exact: lock-step with the device and worst-case room.  The reference's births are limited by the
+    # division buffer only (0.6 * 1.5 * n here): 180 000 of the 200 000 cells divide at once, 20 000 are counted as
+    # Overflow and divide one step later.  WHICH mothers overflow depends on the execution order in the reference too,
+    # so the comparison is on the tallies and the extents, not on the particle rows.
+    monkeypatch.setenv("BMC_CAPACITY_MODE", "exact")
+    case = _burst_case(synth)
+    g, o = _pair(bmc, orc, case, allocation_factor=1.5, buffer_ratio=0.6)
+    util.load_case(g, case); util.load_case(o, case)
+    for _ in range(6):
+        util.run_steps(g, case, 2); util.run_steps(o, case, 2)
+        cg, co = g.counters(), o.counters()
+        for k in ("n_used", "capacity", "buffer_capacity", "total_new", "last_waiting_allocation"):
+            assert cg[k] == co[k], (k, cg[k], co[k])
+        for k in ("NewParticle", "Overflow"):
+            assert cg["events"][k] == co["events"][k], (k, cg["events"], co["events"])
+    assert co["events"]["Overflow"] == 20_000 and co["n_used"] == 2 * case["n"]
+
+
+def test_burst_without_overflow_is_bit_exact_in_default_mode(bmc, orc, synth):
+    # the same synchronised burst with a buffer that holds it (allocation factor 4): every cell divides in the very
+    # first step, i.e. on an idle stream, where the room is provably sufficient -> bit-exact, no error, default mode
+    case = _burst_case(synth)
+    g, o = _pair(bmc, orc, case, allocation_factor=4.0, buffer_ratio=0.6)
+    util.load_case(g, case); util.load_case(o, case)
+    util.run_steps(g, case, 8); util.run_steps(o, case, 8)
+    _compare(g, o)
+    assert o.counters()["n_used"] == 2 * case["n"] and o.counters()["events"]["Overflow"] == 0
+
+
+def test_capacity_exhaustion_fails_loudly(bmc, synth):
+    # default mode: four quiet steps let the host run ahead, then every cell divides in the same step — births the
+    # history did not announce.  The device refuses divisions for lack of PHYSICAL room, which the reference would
+    # not have done: that must surface as an error, never as a silent Overflow.
+    n = 200_000
+    case = util.make_case(synth, "fixed_length", n, 16, dt=100.0, p_move=0.3, outlet=False)
+    case["props"][0][:] = np.float32(1.93e-6)   # l grows 2.8e-8 per step: l_max = 2e-6 is crossed in the third step
+    g = bmc.ParticleLoop("fixed_length", 1, 16, allocation_factor=1.5, buffer_ratio=0.6)
+    util.load_case(g, case)
+    with pytest.raises(bmc.BmcError, match="capacity exhausted"):
+        util.run_steps(g, case, 12)
+        g.counters()
 
 
 def test_synchronised_population_many_divisions_in_one_step(bmc, orc, synth):

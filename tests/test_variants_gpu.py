@@ -1,0 +1,82 @@
+"""Every instantiation of the step kernel that the library ships is run through the parity cases.
+
+Each model has its default block size and at most one alternative, selected by BMC_VARIANT (read at bmc_create);
+the eager-age kernel of a variant is a third instantiation (exercised by the cases with caller-supplied ages or a
+changing time step).  `kernel_config()` proves which instantiation ran."""
+import pytest
+
+import test_ages_gpu as ta
+import test_parity_gpu as tp
+import test_reference_sources as tr
+
+pytestmark = pytest.mark.gpu
+
+# model -> (default block, alternative variant, its block): bmc_inst_*.cu
+ALT = {"fixed_length": (1024, "v4b3", 768), "monod": (1024, "v4b3", 768), "simple_acetate": (1024, "v4b3", 768)}
+
+
+@pytest.mark.parametrize("model", sorted(ALT))
+def test_variant_selection(bmc, monkeypatch, model):
+    ns = 2 if model == "simple_acetate" else 1
+    assert bmc.ParticleLoop(model, ns, 8).kernel_config()["block"] == ALT[model][0]
+    monkeypatch.setenv("BMC_VARIANT", ALT[model][1])
+    k = bmc.ParticleLoop(model, ns, 8).kernel_config()
+    assert k["block"] == ALT[model][2] and k["vec"] == 4
+    assert bmc.ParticleLoop("wide_udf", 4, 8, n_var_udf=8).kernel_config()["block"] == 768
+    monkeypatch.setenv("BMC_VARIANT", "v9b9")   # unknown: ignored
+    assert bmc.ParticleLoop(model, ns, 8).kernel_config()["block"] == ALT[model][0]
+
+
+@pytest.mark.parametrize("model", ["fixed_length", "monod", "wide_udf"])
+def test_alt_many_steps_division_exit_compaction(bmc, orc, synth, monkeypatch, model):
+    monkeypatch.setenv("BMC_VARIANT", "v4b3")
+    tp.test_many_steps_division_exit_compaction(bmc, orc, synth, model)
+
+
+def test_alt_simple_acetate(bmc, orc, synth, monkeypatch):
+    monkeypatch.setenv("BMC_VARIANT", "v4b3")
+    tp.test_simple_acetate_deterministic_part(bmc, orc, synth)
+
+
+def test_alt_large_compartment_tables(bmc, orc, synth, monkeypatch):
+    monkeypatch.setenv("BMC_VARIANT", "v4b3")
+    tp.test_large_compartment_tables(bmc, orc, synth)
+
+
+def test_alt_synchronised_population(bmc, orc, synth, monkeypatch):
+    monkeypatch.setenv("BMC_VARIANT", "v4b3")
+    tp.test_synchronised_population_many_divisions_in_one_step(bmc, orc, synth)
+
+
+@pytest.mark.parametrize("name", tr.NAMES)
+def test_alt_reproduces_reference_fixture(bmc, monkeypatch, name):
+    monkeypatch.setenv("BMC_VARIANT", "v4b3")
+    tr.test_cuda_reproduces_reference_fixture(bmc, name)
+
+
+@pytest.mark.parametrize("model", ["fixed_length", "monod"])
+def test_alt_stamped_ages(bmc, orc, synth, monkeypatch, model):
+    monkeypatch.setenv("BMC_VARIANT", "v4b3")
+    ta.test_stamped_ages_many_steps(bmc, orc, synth, model)
+
+
+def test_alt_eager_ages(bmc, orc, synth, monkeypatch):
+    monkeypatch.setenv("BMC_VARIANT", "v4b3")
+    ta.test_nonzero_initial_ages_use_the_eager_kernel(bmc, orc, synth)
+    ta.test_time_step_change_switches_to_eager(bmc, orc, synth)
+    ta.test_outlet_switched_on_mid_run(bmc, orc, synth)
+
+
+def test_wide_models_default_instantiations(bmc, orc, synth):
+    # WideUdf<16> (VEC 2), <32> and <64> (VEC 1) ship one block size each: many steps with division, exits, compaction
+    import util
+    for nv in (8, 16, 32, 64):
+        case = util.make_case(synth, "wide_udf", 40_000, 100, dt=20.0, near_division=0.8, p_move=0.3, p_exit=0.3, n_var_udf=nv)
+        g, o = tp._pair(bmc, orc, case, dead_ratio=0.0005)
+        assert g.kernel_config()["vec"] == {8: 4, 16: 2, 32: 1, 64: 1}[nv]
+        util.load_case(g, case); util.load_case(o, case)
+        for _ in range(2):
+            sg = util.run_steps(g, case, 5, collect=True); so = util.run_steps(o, case, 5, collect=True)
+            tp._compare_sources(sg, so)
+            tp._compare(g, o)
+        assert o.counters()["total_new"] > 0 and o.counters()["n_compactions"] >= 1
