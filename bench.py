@@ -3,14 +3,19 @@
 
 A "step" is one cycleProcess (model update + division, contribution scatter,
 compartment move, outlet exit, compaction, spawn) over this rank's particles.
-Workload at any N: BASELINE.json configs[1] per GPU — stirred-tank CMA with 500
-compartments, Monod uptake model, 1e7 particles per GPU (weak scaling), fixed
-synthetic flow map, one outlet, dt = 0.1 s; synthetic population initialised on
-the device.  `--workload c3` is configs[2] (1e8 particles per GPU, faster
-growth so division/removal/compaction are exercised every step).
+
+Headline workload at every N ("ns", the north-star case of BASELINE.json): the stirred-tank
+CMA of configs[1] — 500 compartments, Monod uptake model, one outlet, dt = 0.1 s, fixed
+synthetic flow map — at 1.25e8 particles PER GPU (weak scaling), so that --gpus 8 IS the
+1e9-particle target case and the 1 -> 8 curve compares like with like.  At N = 1 the line also
+carries, under "configs", one sub-record per BASELINE configuration measured the same way in
+the same run: c2 (configs[1] at its own 1e7 particles), c2_eager (the same with ages updated
+eagerly, i.e. the 57 B/particle layout of SURVEY.md §8d), c3 (1e8 particles, division + outlet
++ compaction inside the timed region), c4 (10 000 compartments, 1.25e8 particles = the 8-GPU
+shard of configs[3]) and c5 (32-property UDF model, 2.5e8 particles = the shard of configs[4]).
 
   value     : whole-job particle-steps/s, state resident in HBM, no host sync
-              inside the timed region, one NCCL all-reduce of the source vector
+              inside the timed region, one all-reduce of the source vector
               per step when N > 1.
   e2e       : same metric through the host-buffer C ABI a reference caller would
               use each step: concentrations H2D -> bmc_cycle -> sources D2H.
@@ -37,7 +42,8 @@ sys.path.insert(0, ROOT)
 
 # Algorithmic bytes per particle-step of THIS design: 4*(R + W) property bytes + position
 # read+write (8) + status (1).  Ages cost nothing per step (step stamps), which is 16 B less
-# than the figure SURVEY.md §8d derives for an eagerly updated layout (kept below as B_SURVEY).
+# than the figure SURVEY.md §8d derives for an eagerly updated layout (kept below as B_SURVEY; it IS what the
+# eager-age kernel moves: 2 x 4 B read + 2 x 4 B written per particle on top).
 B_ALG = {"monod": 41, "fixed_length": 21, "simple_acetate": 49, "wide_udf": 8 * 32 + 9}      # multi-compartment
 B_ALG_0D = {"monod": 37, "fixed_length": 17, "simple_acetate": 45, "wide_udf": 8 * 32 + 5}  # 0D: position only read
 B_SURVEY = {"monod": 57, "fixed_length": 37, "simple_acetate": 65, "wide_udf": 8 * 32 + 25}
@@ -45,6 +51,8 @@ N_SPECIES = {"monod": 1, "fixed_length": 1, "simple_acetate": 2, "wide_udf": 4}
 
 WORKLOADS = {
     # name: (model, n_comp, particles per GPU, dt, near_division, p_exit)
+    # north-star target: 1e9 particles, 500 compartments, monod on 8 GPUs -> 1.25e8 per GPU
+    "ns": ("monod", 500, 125_000_000, 0.1, 0.0, 1e-3),
     "c2": ("monod", 500, 10_000_000, 0.1, 0.0, 1e-3),
     "c3": ("monod", 500, 100_000_000, 1.0, 0.5, 1e-3),
     "c1": ("monod", 1, 100_000, 0.1, 0.0, 1e-3),
@@ -56,6 +64,19 @@ WORKLOADS = {
     "fl": ("fixed_length", 500, 10_000_000, 0.1, 0.0, 1e-3),
     "sa": ("simple_acetate", 500, 10_000_000, 0.1, 0.0, 1e-3),
 }
+SUB_RECORDS = ("c2", "c2_eager", "c3", "c4", "c5")   # measured after the headline at N = 1 (each on a fresh context)
+
+
+def workload_label(wl, n_per_gpu=None):
+    model, n_comp, n_full, dt, _, _ = WORKLOADS[wl]
+    n = n_per_gpu or n_full
+    return f"{wl}: {n_comp}-compartment stirred-tank CMA, {model}, {n} particles/GPU, dt={dt}"
+
+
+def workload_config(wl, n_per_gpu, n_var):
+    """the `config` object, identical in both arms (it describes the workload, not the implementation)"""
+    return {"workload": workload_label(wl, n_per_gpu),
+            "l2_policy": f"inputs larger than L2 ({n_per_gpu * (n_var * 4 + 13) / 1e6:.0f} MB of particle state per GPU)"}
 
 
 def peaks():
@@ -172,9 +193,19 @@ def make_cpu_loop(model, n_species, n_comp, threads):
     return oracle.OracleLoop(model, n_species, n_comp, n_threads=threads), "port", "oracle OpenMP restatement"
 
 
+N_VAR = {"monod": 6, "fixed_length": 2, "simple_acetate": 9, "wide_udf": 32}
+# c3 exercises removal: exits at 5 % per step in the outlet compartment and a compaction threshold low enough that
+# several compactions fall inside the timed region
+LOOP_KW = {"c3": dict(dead_ratio=5e-4)}
+P_EXIT = {"c3": 0.05}
+# c3 grows by ~1 % per step: like a production run that knows its horizon, the arrays are reserved up front (bmc_reserve)
+# so that no reallocation (a one-off of tens of ms) lands inside a 30-step timed region
+RESERVE = {"c3": 2.4}
+
+
 def run_reference(args, wl):
-    """Reference arm: the reference path's CPU implementation (oracle restatement, OpenMP,
-    all host threads) on the same config; each step is a bounded sample of the workload."""
+    """Reference arm: the reference's own kernels on the host cores (oracle/_ref timing build, else the oracle port) on
+    the same config; each step is a bounded sample of the workload (--cpu-sample particles)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -186,6 +217,9 @@ def run_reference(args, wl):
     from _bmc_loader import load_synth
     synth = load_synth()
     model, n_comp, n_full, dt, near, p_exit = WORKLOADS[wl]
+    p_exit = P_EXIT.get(wl, p_exit)
+    if args.particles:
+        n_full = args.particles
     n = min(n_full, args.cpu_sample)
     fm, flows, conc = build_case(synth, model, n_comp, dt, p_exit)
 
@@ -219,63 +253,90 @@ def run_reference(args, wl):
     line = {"metric": "particle-steps/sec", "value": v, "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"{wl}: {n_comp}-compartment stirred-tank CMA, {model}, {n_full} particles/GPU, dt={dt}"},
+            "config": workload_config(wl, n_full, N_VAR[model]),
             "cpu_baseline": {"value": v, "unit": "particle-steps/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--particles", type=int, default=0, help="override particles per GPU")
-    ap.add_argument("--cpu-sample", type=int, default=2_000_000, help="particles in the bounded CPU sample")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the e2e leg (default: --steps)")
-    args = ap.parse_args()
-    if args.warmup < 3:
-        args.warmup = 3
-    wl = args.workload
-    if args.impl == "reference":
-        return run_reference(args, wl)
+def traffic_entry(wl, n_per_gpu, kcfg, eager):
+    """measured DRAM bytes per launch of the step kernel for this workload, from the committed ncu capture
+    (profiles/traffic.json: one entry per workload with the kernel instantiation and the commit it was taken on);
+    None when the entry does not describe the kernel that just ran"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(wl + ("_eager" if eager else ""))
+        if t and t["particles"] == n_per_gpu and t.get("block") == (kcfg["block_eager"] if eager else kcfg["block"]) and t.get("vec") == kcfg["vec"]:
+            return t["bytes_per_launch"], f"profiles/traffic.json ({t.get('kernel')}, commit {t.get('commit')}, {t.get('capture')})"
+    except Exception:
+        pass
+    return None, None
 
-    import torch
-    from _bmc_loader import load_pkg, load_synth
-    pkg, synth = load_pkg(), load_synth()
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the particle loop has no CPU fallback")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    model, n_comp, n_per_gpu, dt, near, p_exit = WORKLOADS[wl]
-    if args.particles:
-        n_per_gpu = args.particles
+class Dist:
+    """the torch.distributed plumbing of one bench process"""
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the particle loop has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+        self.device = torch.device("cuda", self.local)
+
+    def barrier(self, loop=None):
+        if loop is not None:
+            loop.sync()
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+
+def measure(D, pkg, synth, wl, n_per_gpu, steps, warmup, e2e_steps, eager=False, sampler=None):
+    """one workload on this job's GPUs: device-resident leg, end-to-end leg, roofline of the step kernel.
+    Returns the record on rank 0 (None elsewhere); the context is destroyed before returning."""
+    torch, dist, world, rank, local = D.torch, D.dist, D.world, D.rank, D.local
+    model, n_comp, _, dt, near, p_exit = WORKLOADS[wl]
+    p_exit = P_EXIT.get(wl, p_exit)
     fm, flows, conc = build_case(synth, model, n_comp, dt, p_exit)
-    loop = pkg.ParticleLoop(model, N_SPECIES[model], n_comp, device=local, seed=2024, rank=rank)
-    # population: device-side mc_init_first (monod draws its TruncatedNormal lengths on the GPU)
-    linit = None
-    if model in ("fixed_length", "wide_udf"):  # configurable models take their lengths from a Config view
-        linit = (1e-6 + 1e-6 * np.random.default_rng(3 + rank).random(n_per_gpu)).astype(np.float32)
-    total_mass = loop.init_particles(n_per_gpu, uniform_position=True, linit=linit)
-    del linit
-    if near > 0:  # c3: bring cells close to division through the host path once
-        props, pos = synth.make_population(model, n_per_gpu, n_comp, seed=11 + rank, near_division=near)
-        loop.set_particles(props, pos)
-        total_mass = float(np.sum(props[0].astype(np.float64))) * 2.8274e-10
-    loop.set_weight(0.5 * float(fm["volumes"].sum()) / (total_mass * world))
+    if eager:
+        os.environ["BMC_EAGER_AGES"] = "1"
+    try:
+        loop = pkg.ParticleLoop(model, N_SPECIES[model], n_comp, device=local, seed=2024, rank=rank, **LOOP_KW.get(wl, {}))
+        # population: device-side mc_init_first (monod draws its TruncatedNormal lengths on the GPU)
+        linit = None
+        if model in ("fixed_length", "wide_udf"):  # configurable models take their lengths from a Config view
+            linit = (1e-6 + 1e-6 * np.random.default_rng(3 + rank).random(n_per_gpu)).astype(np.float32)
+        total_mass = loop.init_particles(n_per_gpu, uniform_position=True, linit=linit)
+        del linit
+        if near > 0:  # c3: bring cells close to division through the host path once
+            props, pos = synth.make_population(model, n_per_gpu, n_comp, seed=11 + rank, near_division=near)
+            loop.set_particles(props, pos)
+            total_mass = float(np.sum(props[0].astype(np.float64))) * 2.8274e-10
+            del props, pos
+    finally:
+        os.environ.pop("BMC_EAGER_AGES", None)
+    if wl in RESERVE:
+        loop.reserve(int(RESERVE[wl] * n_per_gpu))
+    v_tot = float(fm["volumes"].sum())
+    if dist is not None:
+        # post_init_weight on a sharded population: the masses are all-reduced, every rank uses the same weight
+        # (global_initaliser.cpp:311, mc/src/unit.cpp:232-257)
+        from biocma_mcst_b200 import sharding
+        loop.set_weight(sharding.global_init_weight(total_mass, 0.5, v_tot, device=D.device))
+    else:
+        loop.set_weight(0.5 * v_tot / total_mass)
     setup_loop(loop, fm, flows, conc, n_comp)
-    collective = ""
+    collective, check = "", None
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8)
         if rank == 0:
@@ -288,58 +349,62 @@ def main():
         # peer-memory path; by default it is used from BMC_P2P_MIN_RANKS ranks on (see DESIGN.md §7 for the measurements).
         collective = "1 NCCL all-reduce/step"
         want_p2p = os.environ.get("BMC_P2P", "auto")
-        use_p2p = want_p2p == "1" or (want_p2p == "auto" and world >= int(os.environ.get("BMC_P2P_MIN_RANKS", "4")))
+        use_p2p = want_p2p == "1" or (want_p2p == "auto" and world >= int(os.environ.get("BMC_P2P_MIN_RANKS", "2")))
         if use_p2p and world <= 16:
             from biocma_mcst_b200 import sharding
-            if sharding.setup_peer_allreduce(loop, world, rank, device=torch.device("cuda", local),
+            if sharding.setup_peer_allreduce(loop, world, rank, device=D.device,
                                              log=lambda m: print(f"[bench] {m}; NCCL", file=sys.stderr)):
                 collective = "1 peer-memory all-reduce/step (one-shot over NVLink, NCCL only for set-up)"
-    stream = torch.cuda.ExternalStream(loop.stream_handle(), device=torch.device("cuda", local))
-
-    def barrier():
-        loop.sync()
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
+    stream = torch.cuda.ExternalStream(loop.stream_handle(), device=D.device)
 
     def step_resident():
         loop.cycle(dt)
         if world > 1:
             loop.allreduce_sources()
 
-    # ---------------- value: device-resident steps -----------------------------
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_resident()
-    barrier()
-    n_live0 = loop.counters()["n_used"]
+    D.barrier(loop)
+    if world > 1:
+        # one-time check on the real exchange path: the all-reduced vector equals the NCCL sum of the per-rank vectors
+        loop.cycle(dt)
+        mine = torch.from_numpy(loop.get_sources().copy()).to(D.device)
+        dist.all_reduce(mine, op=dist.ReduceOp.SUM)
+        loop.allreduce_sources()
+        got = loop.get_sources()
+        ref_sum = mine.cpu().numpy()
+        err = float(np.max(np.abs(got - ref_sum)) / (np.max(np.abs(ref_sum)) + 1e-300))
+        check = {"allreduce_matches_nccl_sum": bool(err <= 1e-12), "max_rel_err": err}
+        if err > 1e-12:
+            raise SystemExit(f"[bench] rank {rank}: all-reduced sources differ from the NCCL sum of the per-rank vectors ({err:.3e})")
+        D.barrier(loop)
+    # ---------------- value: device-resident steps -----------------------------
+    c0 = loop.counters()
     launches0 = loop.launch_count()
     loop.profile_enable(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    sampler.mark_begin()
+    D.barrier(loop)
+    if sampler is not None:
+        sampler.mark_begin()
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_resident()
     e1.record(stream)
-    barrier()
-    sampler.mark_end()
+    D.barrier(loop)
+    if sampler is not None:
+        sampler.mark_end()
     ms = e0.elapsed_time(e1)
     kernel_ms, kernel_n = loop.profile_read()
     loop.profile_enable(False)
     launches = loop.launch_count() - launches0
-    n_live1 = loop.counters()["n_used"]
-    live_avg = 0.5 * (n_live0 + n_live1)
+    c1 = loop.counters()
+    live_avg = 0.5 * (c0["n_used"] + c1["n_used"])
 
     # ---------------- e2e: host-buffer ABI every step ---------------------------
-    e2e_steps = args.e2e_steps or args.steps
     conc_host = np.ascontiguousarray(conc, np.float64)
     for _ in range(3):
         loop.set_concentrations(conc_host); step_resident(); loop.get_sources()
-    barrier()
+    D.barrier(loop)
     n_e0 = loop.counters()["n_used"]
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # per-step inputs prepared outside the timed region (the liquid solver of the caller owns them);
@@ -352,12 +417,12 @@ def main():
         step_resident()
         loop.get_sources(src)                        # D2H of this step's result (synchronises)
     f1.record(stream)
-    barrier()
+    D.barrier(loop)
     ms_e2e = f0.elapsed_time(f1)
-    n_e1 = loop.counters()["n_used"]
-    live_e2e = 0.5 * (n_e0 + n_e1)
-
-    clocks = sampler.stop() if rank == 0 else None
+    c2 = loop.counters()
+    live_e2e = 0.5 * (n_e0 + c2["n_used"])
+    kcfg = loop.kernel_config()
+    n_var = loop.n_var
 
     # ---------------- reduce over ranks (max time, sum particles) ---------------
     stats = torch.tensor([ms, ms_e2e, live_avg, live_e2e, kernel_ms / max(1, kernel_n), float(launches)], dtype=torch.float64,
@@ -369,58 +434,117 @@ def main():
         live_tot, live_e2e_tot, launches_tot = sm[2].item(), sm[3].item(), sm[5].item()
     else:
         k_ms = stats[4].item(); live_tot, live_e2e_tot, launches_tot = live_avg, live_e2e, float(launches)
+    loop.close()
+    del loop
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    peak, peak_src = peaks()
+    b_tab = B_SURVEY if eager else (B_ALG if n_comp > 1 else B_ALG_0D)
+    b_alg = b_tab[model]
+    achieved = (live_avg * b_alg) / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    nb = N_SPECIES[model] * n_comp * 8
+    traffic, traffic_src = traffic_entry(wl, n_per_gpu, kcfg, eager)
+    block = kcfg["block_eager"] if eager else kcfg["block"]
+    rec = {
+        "value": live_tot * steps / (ms * 1e-3), "unit": "particle-steps/s", "steps": steps, "warmup": warmup,
+        "ms_per_step": ms / steps, "config": workload_config(wl, n_per_gpu, n_var),
+        "parallelism": f"particle-sharded x{world}, replicated liquid state, {collective}" if world > 1 else "single GPU",
+        "e2e": {"value": live_e2e_tot * e2e_steps / (ms_e2e * 1e-3), "unit": "particle-steps/s", "h2d_bytes_per_step": nb,
+                "d2h_bytes_per_step": nb, "ms_per_step": ms_e2e / e2e_steps},
+        "gpu_launches": int(launches_tot),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "kernel": f"cycle_kernel<{model}, VEC={kcfg['vec']}, {block} threads, {'eager' if eager else 'stamped'} ages> "
+                               "(whole step: particle pass + post-cycle phase)",
+                     "kernel_ms": k_ms, "bytes_per_particle": b_alg,
+                     "bytes_per_particle_note": ("ages loaded and stored every step (the layout SURVEY.md 8d counts)" if eager else
+                                                 "4*(R+W) property bytes + position 8 + status 1; ages are step stamps, not rewritten"),
+                     "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", "kernel_share_of_step": k_ms * steps / ms},
+        "events_in_timed_region": {"divisions": c1["total_new"] - c0["total_new"], "exits": c1["total_out"] - c0["total_out"],
+                                   "compactions": c1["n_compactions"] - c0["n_compactions"], "reallocations": c1["n_reallocations"] - c0["n_reallocations"]},
+    }
+    if check is not None:
+        rec["collective_check"] = check
+    return rec
 
-    if rank == 0:
-        value = live_tot * args.steps / (ms * 1e-3)
-        e2e_v = live_e2e_tot * e2e_steps / (ms_e2e * 1e-3)
-        peak, peak_src = peaks()
-        b_alg = B_ALG[model] if n_comp > 1 else B_ALG_0D[model]
-        achieved = (live_avg * b_alg) / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-        nb = N_SPECIES[model] * n_comp * 8
-        traffic = None  # DRAM bytes per launch of the cycle kernel from the committed ncu capture of this workload
-        try:
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                t = json.load(f).get(wl)
-            if t and t["particles"] == n_per_gpu:
-                traffic = t["bytes_per_launch"]
-        except Exception:
-            pass
-        line = {
-            "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{wl}: {n_comp}-compartment stirred-tank CMA, {model}, {n_per_gpu} particles/GPU, dt={dt}",
-                       "parallelism": f"particle-sharded x{world}, replicated liquid state, {collective}" if world > 1 else "single GPU",
-                       "l2_policy": f"inputs larger than L2 ({n_per_gpu * (loop.n_var * 4 + 13) / 1e6:.0f} MB of particle state per GPU)"},
-            "e2e": {"value": e2e_v, "unit": "particle-steps/s", "h2d_bytes_per_step": nb, "d2h_bytes_per_step": nb,
-                    "ms_per_step": ms_e2e / e2e_steps},
-            "gpu_launches": int(launches_tot),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": f"cycle_kernel<{model}> (whole step: particle pass + post-cycle phase)", "kernel_ms": k_ms,
-                         "bytes_per_particle": b_alg, "bytes_per_particle_survey_8d": B_SURVEY[model],
-                         "frac_survey_8d": (live_avg * B_SURVEY[model]) / (k_ms * 1e-3) / 1e9 / peak if k_ms > 0 else 0.0,
-                         "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", "kernel_share_of_step": k_ms * args.steps / ms},
-            "clocks": clocks,
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            threads = host_threads()
-            n = min(n_per_gpu, args.cpu_sample)
-            props, pos = synth.make_population(model, n, n_comp, seed=11, near_division=near)
-            o, kind, label = make_cpu_loop(model, N_SPECIES[model], n_comp, threads)
-            o.set_particles(props, pos)
-            o.set_weight(1.0)
-            setup_loop(o, fm, flows, conc, n_comp)
-            o.cycle(dt)
-            steps_cpu, t0, done = 0, time.perf_counter(), 0
-            while time.perf_counter() - t0 < 10.0 and steps_cpu < 400:
-                done += o.counters()["n_used"]; o.cycle(dt); steps_cpu += 1
-            el = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": done / el, "unit": "particle-steps/s", "cores": threads, "kind": kind,
-                                    "sample": f"{n} of {n_per_gpu} particles x {steps_cpu} steps, {label}"}
+
+def cpu_baseline(synth, wl, n_per_gpu, cpu_sample):
+    model, n_comp, _, dt, near, p_exit = WORKLOADS[wl]
+    fm, flows, conc = build_case(synth, model, n_comp, dt, P_EXIT.get(wl, p_exit))
+    threads = host_threads()
+    n = min(n_per_gpu, cpu_sample)
+    props, pos = synth.make_population(model, n, n_comp, seed=11, near_division=near)
+    o, kind, label = make_cpu_loop(model, N_SPECIES[model], n_comp, threads)
+    o.set_particles(props, pos)
+    o.set_weight(1.0)
+    setup_loop(o, fm, flows, conc, n_comp)
+    o.cycle(dt)
+    steps_cpu, t0, done = 0, time.perf_counter(), 0
+    while time.perf_counter() - t0 < 10.0 and steps_cpu < 400:
+        done += o.counters()["n_used"]; o.cycle(dt); steps_cpu += 1
+    el = time.perf_counter() - t0
+    o.close()
+    return {"value": done / el, "unit": "particle-steps/s", "cores": threads, "kind": kind,
+            "sample": f"{n} of {n_per_gpu} particles x {steps_cpu} steps, {label}"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ns", choices=sorted(WORKLOADS))
+    ap.add_argument("--particles", type=int, default=0, help="override particles per GPU")
+    ap.add_argument("--eager", action="store_true", help="eager float ages (BMC_EAGER_AGES=1): the 57 B/particle kernel")
+    ap.add_argument("--cpu-sample", type=int, default=10_000_000, help="particles in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-configuration sub-records (N = 1)")
+    ap.add_argument("--configs-steps", type=int, default=30, help="timed steps of each sub-record")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the e2e leg (default: --steps)")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    wl = args.workload
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    from _bmc_loader import load_pkg, load_synth
+    pkg, synth = load_pkg(), load_synth()
+    D = Dist()
+    n_per_gpu = args.particles or WORKLOADS[wl][2]
+    sampler = ClockSampler(D.local)
+    if D.rank == 0:
+        sampler.start()
+    rec = measure(D, pkg, synth, wl, n_per_gpu, args.steps, args.warmup, args.e2e_steps or args.steps, eager=args.eager, sampler=sampler)
+    clocks = sampler.stop() if D.rank == 0 else None
+    if D.rank == 0:
+        line = {"metric": "particle-steps/sec", "value": rec["value"], "unit": rec["unit"], "n_gpus": D.world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": rec["config"], "parallelism": rec["parallelism"],
+                "e2e": rec["e2e"], "gpu_launches": rec["gpu_launches"], "roofline": rec["roofline"],
+                "events_in_timed_region": rec["events_in_timed_region"], "clocks": clocks}
+        if "collective_check" in rec:
+            line["collective_check"] = rec["collective_check"]
+    if D.world == 1 and wl == "ns" and not args.particles and not args.eager and not args.no_configs:
+        # one sub-record per BASELINE configuration, same measurement, fresh context each
+        subs = {}
+        for name in SUB_RECORDS:
+            swl, eager = (name[:-6], True) if name.endswith("_eager") else (name, False)
+            try:
+                r = measure(D, pkg, synth, swl, WORKLOADS[swl][2], args.configs_steps, max(3, min(args.warmup, 5)), args.configs_steps, eager=eager)
+                subs[name] = {k: r[k] for k in ("value", "unit", "steps", "ms_per_step", "config", "e2e", "roofline", "events_in_timed_region")}
+            except Exception as e:  # noqa: BLE001 - a sub-record must not take the headline down
+                subs[name] = {"error": f"{type(e).__name__}: {e}"}
+        line["configs"] = subs
+    if D.rank == 0:
+        if D.world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(synth, wl, n_per_gpu, args.cpu_sample)
         print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    if D.dist is not None:
+        D.dist.barrier()
+        D.dist.destroy_process_group()
 
 
 if __name__ == "__main__":
