@@ -102,6 +102,8 @@ struct bmc_ctx {
   // peer-memory all-reduce (bmc_p2p_*)
   unsigned char* p2p_region = nullptr; size_t p2p_bytes = 0; int p2p_world = 0, p2p_rank = 0; bool p2p_on = false, p2p_ipc = false;
   unsigned char* p2p_base[kMaxPeers] = {}; unsigned long long p2p_epoch = 0;
+  unsigned long long p2p_published = 0;  // epoch of the sources currently in d_sources if a cycle published them, else 0
+  unsigned long long p2p_pending = 0;    // epoch whose all-reduce was requested and not finished yet (bmc_allreduce_sources is lazy)
   std::string err;
 };
 
@@ -258,7 +260,27 @@ static int configure_launch(bmc_ctx* ctx) {
   return BMC_OK;
 }
 
+static void fill_peer_exchange(const bmc_ctx* ctx, PeerExchange& x, unsigned long long publish, unsigned long long consume) {
+  memset(&x, 0, sizeof(x));
+  if (!ctx->p2p_on) return;
+  x.world = ctx->p2p_world; x.rank = ctx->p2p_rank; x.publish_epoch = publish; x.consume_epoch = consume;
+  x.spin_limit = 20000000000ll;  // ~10 s at 2 GHz
+  for (int r = 0; r < ctx->p2p_world; ++r) x.base[r] = ctx->p2p_base[r];
+}
+
+// bmc_allreduce_sources is lazy on the peer-memory path: the sum is finished by the next step kernel (overlapped with
+// its particle pass) or, when anything else touches the sources or synchronises first, by this small kernel
+static int finish_pending_sum(bmc_ctx* ctx) {
+  if (!ctx->p2p_pending) return BMC_OK;
+  PeerExchange x;
+  fill_peer_exchange(ctx, x, 0, ctx->p2p_pending);
+  ctx->p2p_pending = 0; ctx->p2p_published = 0;  // d_sources now holds the global sum
+  p2p_exchange_kernel<<<1, 1024, 0, ctx->stream>>>(x, ctx->d_sources, (uint32_t)(ctx->n_species * ctx->n_comp), ctx->st);
+  return check_launch(ctx, "p2p_exchange");
+}
+
 static int sync_state(bmc_ctx* ctx, DevState* out) {
+  { int rc0 = finish_pending_sum(ctx); if (rc0) return rc0; }
   CK(cudaMemcpyAsync(ctx->h_st, ctx->st, sizeof(DevState), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   *out = *ctx->h_st;
@@ -830,6 +852,8 @@ int bmc_liquid_step(bmc_ctx* ctx, double d_t) {
   cudaStream_t s = ctx->stream;
   const uint32_t nb = (uint32_t)(ctx->n_species * ctx->n_comp);
   int rc;
+  if ((rc = finish_pending_sum(ctx))) return rc;
+  ctx->p2p_published = 0;  // the sources are consumed (cleared) by this step
   if (ctx->mass_dirty) {
     liquid_mass_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ctx->d_conc, ctx->d_vol, ctx->d_mass, (uint32_t)ctx->n_species, nb);
     if ((rc = check_launch(ctx, "liquid_mass"))) return rc;
@@ -854,6 +878,7 @@ int bmc_get_sources(bmc_ctx* ctx, double* out) {
   if (!ctx || !out) return BMC_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
   const size_t bytes = ctx->n_species * ctx->n_comp * 8;
+  { int rc = finish_pending_sum(ctx); if (rc) return rc; }
   CK(cudaMemcpyAsync(ctx->h_pin_out, ctx->d_sources, bytes, cudaMemcpyDeviceToHost, ctx->stream));  // pinned: one DMA, no staging
   CK(cudaStreamSynchronize(ctx->stream));
   memcpy(out, ctx->h_pin_out, bytes);
@@ -920,6 +945,13 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   p.post.newborn_stamp = ctx->lazy_ages ? (uint32_t)ctx->host_step + 1u : 0u;
   p.post.tab_idx = (uint32_t)ctx->host_step;
   p.post.tab_extend = ctx->lazy_ages ? 1 : 0; p.post.enable_leave = enable_leave ? 1 : 0; p.post.dt_f = (float)d_t; p.post.dt = d_t;
+  if (ctx->p2p_on) {  // this step publishes its sources to the peers and finishes the previous all-reduce, if one is pending
+    // (peers that are contexts on the SAME device — the test harness — cannot be waited for from inside a kernel that
+    // fills the device: their all-reduce is finished by the small kernel instead)
+    if (ctx->p2p_pending && !ctx->p2p_ipc && (rc = finish_pending_sum(ctx))) return rc;
+    fill_peer_exchange(ctx, p.post.px, ++ctx->p2p_epoch, ctx->p2p_pending);
+    ctx->p2p_pending = 0; ctx->p2p_published = ctx->p2p_epoch;
+  }
 
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx->profile) {  // event pairs come from a pool that bmc_profile_read recycles: nothing is created in steady state
@@ -957,6 +989,7 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
 int bmc_sync(bmc_ctx* ctx) {
   if (!ctx) return BMC_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
+  { int rc = finish_pending_sum(ctx); if (rc) return rc; }
   CK(cudaStreamSynchronize(ctx->stream));
   return BMC_OK;
 }
@@ -1197,6 +1230,7 @@ int bmc_compact(bmc_ctx* ctx) {
 
 int bmc_sources_device(bmc_ctx* ctx, double** ptr, uint64_t* n) {
   if (!ctx || !ptr) return BMC_ERR_INVALID;
+  { int rc = finish_pending_sum(ctx); if (rc) return rc; }
   *ptr = ctx->d_sources; if (n) *n = ctx->n_species * ctx->n_comp;
   return BMC_OK;
 }
@@ -1358,21 +1392,30 @@ int bmc_p2p_attach_local(bmc_ctx* ctx, int n_ranks, int rank, void* const* bases
 
 int bmc_p2p_disable(bmc_ctx* ctx) {
   if (!ctx) return BMC_ERR_INVALID;
+  { int rc = finish_pending_sum(ctx); if (rc) return rc; }
   ctx->p2p_on = false;  // bmc_allreduce_sources goes back to the NCCL communicator
   return BMC_OK;
 }
 
 int bmc_allreduce_sources(bmc_ctx* ctx) {
   if (!ctx) return BMC_ERR_INVALID;
-  if (ctx->p2p_on) {  // one-shot reduction over peer mappings (bmc_kernels_common.cuh)
+  if (ctx->p2p_on) {
+    // Peer-memory path (bmc_kernels.cuh: PeerExchange).  The last cycle's commit block has already written this rank's
+    // sources into its exchange buffer; the sum over the ranks is finished by whoever touches the sources next — the
+    // next step kernel does it in its first block while the particle pass runs, so the collective costs no launch and
+    // no time on the critical path.  Nothing is enqueued here.
     CK(cudaSetDevice(ctx->device));
-    P2PParams pp;
-    memset(&pp, 0, sizeof(pp));
-    pp.sources = ctx->d_sources; pp.n = (uint32_t)(ctx->n_species * ctx->n_comp); pp.world = ctx->p2p_world; pp.rank = ctx->p2p_rank;
-    pp.epoch = ++ctx->p2p_epoch; pp.st = ctx->st; pp.spin_limit = 20000000000ll;  // ~10 s at 2 GHz
-    for (int r = 0; r < ctx->p2p_world; ++r) pp.base[r] = ctx->p2p_base[r];
-    p2p_allreduce_kernel<<<1, 1024, 0, ctx->stream>>>(pp);
-    return check_launch(ctx, "p2p_allreduce");
+    int rc;
+    if ((rc = finish_pending_sum(ctx))) return rc;  // (two requests in a row)
+    if (!ctx->p2p_published) {  // the sources were not published by a cycle (first call after a load, liquid step in between, ...)
+      PeerExchange x;
+      fill_peer_exchange(ctx, x, ++ctx->p2p_epoch, 0);
+      p2p_exchange_kernel<<<1, 1024, 0, ctx->stream>>>(x, ctx->d_sources, (uint32_t)(ctx->n_species * ctx->n_comp), ctx->st);
+      if ((rc = check_launch(ctx, "p2p_exchange"))) return rc;
+      ctx->p2p_published = ctx->p2p_epoch;
+    }
+    ctx->p2p_pending = ctx->p2p_published;
+    return BMC_OK;
   }
   if (!ctx->nccl_comm) { ctx->err = "bmc_comm_init / bmc_p2p_attach not called"; return BMC_ERR_INVALID; }
   CK(cudaSetDevice(ctx->device));

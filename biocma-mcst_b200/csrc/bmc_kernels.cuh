@@ -136,6 +136,55 @@ constexpr uint32_t kFrozen = 0x80000000u;
 #define BMC_STAMP(st, i) do { } while (0)
 #endif
 
+// -----------------------------------------------------------------------------
+// Peer-memory exchange of the source vector (the one collective of the path: MPI_Reduce of the sources in
+// apps/core/src/sync.cpp:57-78), fused into the step kernel.  Every rank owns one small region that all ranks map
+// (NVLink / NVSwitch peer mappings): [flag, padded to 128 B][buffer 0][buffer 1].
+//   publish (commit block of step e): sources -> my buffer[e & 1], system-scope fence, flag = e
+//   consume (block 0 of the NEXT step kernel, concurrently with its particle pass; or consume_kernel when something
+//            else reads the sources first): wait for every peer's flag >= e, sources = sum over ranks IN RANK ORDER of
+//            buffer[e & 1] (bitwise the same vector on every rank)
+// Two buffers suffice: a rank publishes e + 2 at the end of its step e + 2, whose first block has consumed e + 1 from
+// every peer, i.e. every peer has finished step e + 1, whose first block consumed e.
+// A peer that never shows up trips a clock limit (error bit 4) instead of hanging the device.
+// -----------------------------------------------------------------------------
+constexpr int kMaxPeers = 16;
+struct PeerExchange {
+  int world, rank;                  // world == 0: no peer exchange
+  unsigned long long publish_epoch; // epoch this step publishes (0 = none)
+  unsigned long long consume_epoch; // epoch to sum before this step's particle pass (0 = none)
+  long long spin_limit;             // clock64 ticks before a missing peer is reported
+  unsigned char* base[kMaxPeers];   // exchange region of every rank (own entry = local pointer)
+};
+__device__ __forceinline__ volatile unsigned long long* p2p_flag(unsigned char* base) { return reinterpret_cast<volatile unsigned long long*>(base); }
+__device__ __forceinline__ double* p2p_buf(unsigned char* base, uint32_t n, unsigned par) { return reinterpret_cast<double*>(base + 128) + (size_t)par * n; }
+// executed by one whole block, after every block's publish of `sources` is visible
+__device__ __forceinline__ void p2p_publish(const PeerExchange& x, const double* sources, uint32_t n) {
+  double* mine = p2p_buf(x.base[x.rank], n, (unsigned)(x.publish_epoch & 1ull));
+  for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) mine[k] = __ldcg(sources + k);
+  __syncthreads();
+  // release: the block barrier orders every thread's stores before thread 0's system-scope fence (cumulative)
+  if (threadIdx.x == 0) { __threadfence_system(); *p2p_flag(x.base[x.rank]) = x.publish_epoch; }
+}
+// executed by one whole block
+__device__ __forceinline__ void p2p_consume(const PeerExchange& x, double* sources, uint32_t n, unsigned int* error) {
+  if ((int)threadIdx.x < x.world && (int)threadIdx.x != x.rank) {
+    volatile unsigned long long* f = p2p_flag(x.base[threadIdx.x]);
+    const long long t0 = clock64();
+    while (*f < x.consume_epoch) {
+      if (clock64() - t0 > x.spin_limit) { atomicOr(error, 4u); break; }
+    }
+    __threadfence_system();  // acquire, by the threads that observed the flags; the barrier passes it on
+  }
+  __syncthreads();
+  const unsigned par = (unsigned)(x.consume_epoch & 1ull);
+  for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+    double a = 0.0;
+    for (int r = 0; r < x.world; ++r) a += *reinterpret_cast<volatile double*>(p2p_buf(x.base[r], n, par) + k);
+    sources[k] = a;
+  }
+}
+
 struct PostParams {
   float* props; size_t cap; int n_var;
   uint32_t* pos; uint8_t* status; float* age_hyd; float* age_div;
@@ -152,6 +201,7 @@ struct PostParams {
   unsigned long long min_removal; double dead_ratio;  // RuntimeParameters of update_and_remove_inactive
   double allocation_factor, buffer_ratio, shrink_ratio;  // RuntimeParameters of _resize / __allocate_buffer__ / remove_inactive_particles
   PinState* pin;                                         // device pointer of the pinned host mirror
+  PeerExchange px;                                       // multi-GPU: publish this step's sources to the peers (commit block)
   int count_step;  // 1 when called from a cycle, 0 from force_remove_dead
   // step-stamped ages (bmc_kernels.cuh): stamp given to newborns (0 = eager float ages, bits of 0.f)
   // and the per-step extension of the age tables A_div / A_hyd
@@ -642,11 +692,16 @@ static __device__ __forceinline__ void post_cycle_body(const PostParams& p) {
     }
   }
   BMC_STAMP(st, 7);
-  // commit: the last block to get here (every other block is done reading the counters)
+  // commit: the last block to get here (every other block is done reading the counters and has published its bins)
+  __shared__ unsigned s_last;
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0 && atomicAdd(&st->done_blocks, 1u) == gridDim.x - 1) {
-    __threadfence();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&st->done_blocks, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (p.count_step && p.px.world > 1 && p.px.publish_epoch) p2p_publish(p.px, p.sources, p.n_bins);  // whole block
+  if (threadIdx.x == 0) {
     st->done_blocks = 0; st->next_group = 0;
     if (p.count_step) { st->last_out = out; st->last_dead = 0; st->last_waiting = st->step_waiting; }  // a forced compaction is not a step
     st->total_out += out;
@@ -820,6 +875,10 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
     fx_max[j] = 0.0f;
   }
   __syncthreads();
+
+  // multi-GPU: the all-reduce of the PREVIOUS step's sources is finished here, by block 0, while the other blocks are
+  // already streaming particles (the dynamic work distribution absorbs the few microseconds block 0 arrives late)
+  if (p.post.px.world > 1 && p.post.px.consume_epoch && blockIdx.x == 0) p2p_consume(p.post.px, p.sources, n_bins, &p.st->error);
 
   BMC_STAMP(p.st, 1);
   double acc0d[NC];  // single-compartment accumulation lives in registers

@@ -132,46 +132,11 @@ __global__ void fill_u8_kernel(uint8_t* p, size_t n, uint8_t v) {
 
 
 
-// -----------------------------------------------------------------------------
-// Peer-memory all-reduce of the source vector (bmc_p2p_*): the one exchange step of the path
-// (MPI_Reduce of the sources in apps/core/src/sync.cpp:57-78).  The vector is a few KB, so the
-// cost of a collective is pure latency; instead of a library ring/tree this is a ONE-SHOT reduction
-// over NVLink / NVSwitch peer mappings, one small kernel per rank:
-//   1. copy my sources into my exchange buffer [epoch & 1], fence (system scope), publish `epoch` in my flag
-//   2. poll every peer's flag (volatile loads through the peer mapping) until it reaches `epoch`
-//   3. every rank sums the peers' buffers IN RANK ORDER (bitwise identical results on all ranks) into its sources
-// Two buffers suffice: a rank can only start epoch e+2 (and overwrite buffer e & 1) after every peer has published
-// e+1, i.e. has finished reading epoch e.  Region layout: [flag, padded to 128 B][buffer 0][buffer 1].
-// -----------------------------------------------------------------------------
-constexpr int kMaxPeers = 16;
-struct P2PParams {
-  double* sources; uint32_t n; int world, rank; unsigned long long epoch;
-  unsigned char* base[kMaxPeers];  // exchange region of every rank (own entry = local pointer)
-  DevState* st; long long spin_limit;  // clock64 ticks before a missing peer is reported (error bit 4) instead of hanging
-};
-__device__ __forceinline__ volatile unsigned long long* p2p_flag(unsigned char* base) { return reinterpret_cast<volatile unsigned long long*>(base); }
-__device__ __forceinline__ double* p2p_buf(unsigned char* base, uint32_t n, unsigned par) { return reinterpret_cast<double*>(base + 128) + (size_t)par * n; }
-__global__ void __launch_bounds__(1024) p2p_allreduce_kernel(const __grid_constant__ P2PParams p) {
-  const unsigned par = (unsigned)(p.epoch & 1ull);
-  double* mine = p2p_buf(p.base[p.rank], p.n, par);
-  for (uint32_t k = threadIdx.x; k < p.n; k += blockDim.x) mine[k] = p.sources[k];
-  __syncthreads();
-  // release: the block barrier orders every thread's stores before thread 0's system-scope fence (cumulative)
-  if (threadIdx.x == 0) { __threadfence_system(); *p2p_flag(p.base[p.rank]) = p.epoch; }
-  if ((int)threadIdx.x < p.world && (int)threadIdx.x != p.rank) {
-    volatile unsigned long long* f = p2p_flag(p.base[threadIdx.x]);
-    const long long t0 = clock64();
-    while (*f < p.epoch) {
-      if (clock64() - t0 > p.spin_limit) { atomicOr(&p.st->error, 4u); break; }
-    }
-    __threadfence_system();  // acquire, by the threads that observed the flags; the barrier passes it on
-  }
-  __syncthreads();
-  for (uint32_t k = threadIdx.x; k < p.n; k += blockDim.x) {
-    double a = 0.0;
-    for (int r = 0; r < p.world; ++r) a += *reinterpret_cast<volatile double*>(p2p_buf(p.base[r], p.n, par) + k);
-    p.sources[k] = a;
-  }
+// Peer exchange outside the step kernel (bmc_kernels.cuh: PeerExchange): publish the current sources when no cycle
+// has published them, and/or finish the all-reduce when something other than the next cycle reads the sources first.
+__global__ void __launch_bounds__(1024) p2p_exchange_kernel(const __grid_constant__ PeerExchange x, double* sources, uint32_t n, DevState* st) {
+  if (x.publish_epoch) p2p_publish(x, sources, n);
+  if (x.consume_epoch) { __syncthreads(); p2p_consume(x, sources, n, &st->error); }
 }
 
 }  // namespace bmc
