@@ -91,12 +91,19 @@ struct bmc_ctx {
   double prof_ms = 0.0; uint64_t prof_n = 0;
   // step-stamped ages (bmc_kernels.cuh): valid while d_t / outlet configuration stay constant and
   // every age started at zero; otherwise the columns hold floats updated every step ("eager")
-  bool lazy_ages = true; bool epoch_set = false; double epoch_dt = 0.0; bool epoch_leave = false;
+  bool lazy_ages = true; bool epoch_set = false; double epoch_dt = 0.0;
+  uint64_t hyd_clock = 0;  // steps with an outlet so far: the clock of the hydraulic age (the division age ticks with host_step)
   float *d_tab_div = nullptr, *d_tab_hyd = nullptr; size_t tab_cap = 0;
   // pinned staging of the per-step host buffers (concentrations in, sources out)
   static constexpr int kPinRing = 4;
   double* h_pin_in[kPinRing] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t ev_pin_in[kPinRing] = {nullptr, nullptr, nullptr, nullptr};
   int pin_next = 0; double* h_pin_out = nullptr;
+  // pinned staging of flow-map updates (bmc_domain_update / bmc_liquid_set_transition): two slots, so that a new map
+  // can be staged while the copy of the previous one may still be in flight; nothing synchronises the stream
+  static constexpr int kMapRing = 2;
+  unsigned char* h_map[kMapRing] = {nullptr, nullptr}; size_t h_map_bytes[kMapRing] = {0, 0};
+  cudaEvent_t ev_map[kMapRing] = {nullptr, nullptr}; int map_next = 0;
+  size_t csc_cap = 0;
   // nccl
   void* nccl_comm = nullptr; int nccl_ranks = 0;
   // peer-memory all-reduce (bmc_p2p_*)
@@ -191,6 +198,21 @@ static int resize_container(bmc_ctx* ctx, size_t new_cap, size_t keep) {
                                   ctx->buffer_ratio, ctx->d_pin);  // room of the new capacity
   if ((rc = check_launch(ctx, "prepare"))) return rc;
   CK(cudaStreamSynchronize(s));
+  return BMC_OK;
+}
+
+// next pinned staging slot of at least `bytes` (waits only for the copy that last read the slot, two updates ago)
+static int map_stage(bmc_ctx* ctx, size_t bytes, unsigned char** out, int* slot_out) {
+  const int slot = ctx->map_next; ctx->map_next = (ctx->map_next + 1) % bmc_ctx::kMapRing;
+  if (!ctx->ev_map[slot]) CK(cudaEventCreateWithFlags(&ctx->ev_map[slot], cudaEventDisableTiming));
+  else CK(cudaEventSynchronize(ctx->ev_map[slot]));
+  if (ctx->h_map_bytes[slot] < bytes) {
+    if (ctx->h_map[slot]) cudaFreeHost(ctx->h_map[slot]);
+    ctx->h_map[slot] = nullptr; ctx->h_map_bytes[slot] = 0;
+    CK(cudaMallocHost((void**)&ctx->h_map[slot], bytes + bytes / 4));
+    ctx->h_map_bytes[slot] = bytes + bytes / 4;
+  }
+  *out = ctx->h_map[slot]; *slot_out = slot;
   return BMC_OK;
 }
 
@@ -450,7 +472,7 @@ static int ensure_age_tables(bmc_ctx* ctx, size_t need) {
 // start of an epoch (particles (re)loaded): stamps if every age is zero, floats otherwise
 static int begin_age_epoch(bmc_ctx* ctx, bool lazy) {
   ctx->lazy_ages = lazy && !force_eager_ages();
-  ctx->epoch_set = false;
+  ctx->epoch_set = false; ctx->hyd_clock = 0;
   if (!ctx->lazy_ages) return BMC_OK;
   int rc;
   if ((rc = ensure_age_tables(ctx, 2))) return rc;
@@ -468,7 +490,7 @@ static int make_ages_eager(bmc_ctx* ctx) {
     ages_to_eager_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->age_div, ctx->d_tab_div, (uint32_t)ctx->host_step, ctx->cap);
     int rc;
     if ((rc = check_launch(ctx, "ages_to_eager"))) return rc;
-    ages_to_eager_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->age_hyd, ctx->d_tab_hyd, (uint32_t)ctx->host_step, ctx->cap);
+    ages_to_eager_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->age_hyd, ctx->d_tab_hyd, (uint32_t)ctx->hyd_clock, ctx->cap);
     if ((rc = check_launch(ctx, "ages_to_eager"))) return rc;
   }
   ctx->lazy_ages = false;
@@ -569,6 +591,7 @@ int bmc_destroy(bmc_ctx** h) {
   if (c->h_pin) cudaFreeHost(c->h_pin);
   for (int i = 0; i < bmc_ctx::kPinRing; ++i) { if (c->h_pin_in[i]) cudaFreeHost(c->h_pin_in[i]); if (c->ev_pin_in[i]) cudaEventDestroy(c->ev_pin_in[i]); }
   if (c->h_pin_out) cudaFreeHost(c->h_pin_out);
+  for (int i = 0; i < bmc_ctx::kMapRing; ++i) { if (c->h_map[i]) cudaFreeHost(c->h_map[i]); if (c->ev_map[i]) cudaEventDestroy(c->ev_map[i]); }
   for (auto& pr : c->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -684,7 +707,7 @@ int bmc_get_particles(bmc_ctx* ctx, uint64_t n, float* props, uint64_t* position
     if ((rc = ensure_stage(ctx, std::min<size_t>(chunk, std::max<uint64_t>(n, 1)) * 4))) return rc;
     for (size_t o = 0; o < n; o += chunk) {
       const size_t c = std::min<size_t>(chunk, n - o);
-      ages_read_kernel<<<(unsigned)((c + 255) / 256), 256, 0, s>>>(col + o, a ? ctx->d_tab_div : ctx->d_tab_hyd, (uint32_t)ctx->host_step,
+      ages_read_kernel<<<(unsigned)((c + 255) / 256), 256, 0, s>>>(col + o, a ? ctx->d_tab_div : ctx->d_tab_hyd, (uint32_t)(a ? ctx->host_step : ctx->hyd_clock),
                                                                   (float*)ctx->d_stage, c);
       if ((rc = check_launch(ctx, "ages_read"))) return rc;
       CK(cudaMemcpyAsync(out + o, ctx->d_stage, c * 4, cudaMemcpyDeviceToHost, s));
@@ -742,32 +765,41 @@ int bmc_domain_update(bmc_ctx* ctx, const double* volumes, const uint64_t* neigh
   if (ctx->n_comp > 1 && (!neighbors_flat || !proba_flat || n_cols == 0)) return BMC_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
-  CK(cudaStreamSynchronize(s));  // tables may be in use by enqueued cycles
+  // Stream-ordered, no host synchronisation: the arrays are staged in pinned memory and copied on the context's
+  // stream, i.e. after the cycles already enqueued (which read the old tables) and before the ones that follow.
+  // A flow-map switch of a transitioner (host_specific.cpp:81-87, 263-266) therefore costs a few small copies.
   const size_t nc = ctx->n_comp, nn = nc * n_cols;
-  CK(cudaMemcpyAsync(ctx->d_vol, volumes, nc * 8, cudaMemcpyHostToDevice, s));
-  ctx->h_vol.assign(volumes, volumes + nc);
-  CK(cudaMemcpyAsync(ctx->d_diag, out_flows, nc * 8, cudaMemcpyHostToDevice, s));
-  if (nn) {
-    std::vector<uint32_t> nb(nn);
-    for (size_t i = 0; i < nn; ++i) {
-      if (neighbors_flat[i] >= nc) { ctx->err = "neighbor index out of range"; return BMC_ERR_RANGE; }
-      nb[i] = (uint32_t)neighbors_flat[i];
-    }
-    if ((int)n_cols != ctx->m) {
-      dev_free(ctx->d_cdf); dev_free(ctx->d_cdf_f); dev_free(ctx->d_neigh);
-      int rc;
-      if ((rc = dev_alloc(ctx, &ctx->d_cdf, nn)) || (rc = dev_alloc(ctx, &ctx->d_cdf_f, nn)) || (rc = dev_alloc(ctx, &ctx->d_neigh, nn))) return rc;
-      ctx->m = (int)n_cols;
-    }
-    CK(cudaMemcpyAsync(ctx->d_cdf, proba_flat, nn * 8, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->d_neigh, nb.data(), nn * 4, cudaMemcpyHostToDevice, s));
-    derive_cdf_table_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(ctx->d_cdf, ctx->d_cdf_f, nn);
-    int rc;
-    if ((rc = check_launch(ctx, "derive_cdf"))) return rc;
-    CK(cudaStreamSynchronize(s));  // nb goes out of scope
+  for (size_t i = 0; i < nn; ++i)
+    if (neighbors_flat[i] >= nc) { ctx->err = "neighbor index out of range"; return BMC_ERR_RANGE; }
+  int rc;
+  if (nn && (int)n_cols != ctx->m) {  // first map, or a map with another neighbour count: the tables change size
+    CK(cudaStreamSynchronize(s));
+    dev_free(ctx->d_cdf); dev_free(ctx->d_cdf_f); dev_free(ctx->d_neigh);
+    if ((rc = dev_alloc(ctx, &ctx->d_cdf, nn)) || (rc = dev_alloc(ctx, &ctx->d_cdf_f, nn)) || (rc = dev_alloc(ctx, &ctx->d_neigh, nn))) return rc;
+    ctx->m = (int)n_cols;
   }
+  const size_t o_vol = 0, o_diag = nc * 8, o_cdf = 2 * nc * 8, o_nb = o_cdf + nn * 8, bytes = o_nb + nn * 4;
+  unsigned char* h = nullptr; int slot = 0;
+  if ((rc = map_stage(ctx, bytes, &h, &slot))) return rc;
+  memcpy(h + o_vol, volumes, nc * 8);
+  memcpy(h + o_diag, out_flows, nc * 8);
+  if (nn) {
+    memcpy(h + o_cdf, proba_flat, nn * 8);
+    uint32_t* nb = reinterpret_cast<uint32_t*>(h + o_nb);
+    for (size_t i = 0; i < nn; ++i) nb[i] = (uint32_t)neighbors_flat[i];
+  }
+  ctx->h_vol.assign(volumes, volumes + nc);
+  CK(cudaMemcpyAsync(ctx->d_vol, h + o_vol, nc * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->d_diag, h + o_diag, nc * 8, cudaMemcpyHostToDevice, s));
+  if (nn) {
+    CK(cudaMemcpyAsync(ctx->d_cdf, h + o_cdf, nn * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_neigh, h + o_nb, nn * 4, cudaMemcpyHostToDevice, s));
+    derive_cdf_table_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(ctx->d_cdf, ctx->d_cdf_f, nn);
+    if ((rc = check_launch(ctx, "derive_cdf"))) return rc;
+  }
+  CK(cudaEventRecord(ctx->ev_map[slot], s));
   ctx->domain_set = true;
-  ctx->table_dt = -1.0;  // leave table depends on dt: rebuilt by the next cycle
+  ctx->table_dt = -1.0;    // leave table depends on dt: rebuilt by the next cycle
   return BMC_OK;
 }
 
@@ -806,24 +838,36 @@ int bmc_liquid_set_transition(bmc_ctx* ctx, uint64_t nnz, const uint64_t* rows, 
   if (!ctx || (nnz && (!rows || !cols || !vals))) return BMC_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
   const size_t nc = ctx->n_comp;
-  std::vector<uint32_t> ptr(nc + 1, 0), row(nnz);
-  std::vector<double> val(nnz);
-  for (uint64_t e = 0; e < nnz; ++e) {
+  for (uint64_t e = 0; e < nnz; ++e)
     if (rows[e] >= nc || cols[e] >= nc) { ctx->err = "transition index out of range"; return BMC_ERR_RANGE; }
-    ptr[cols[e] + 1]++;
-  }
-  for (size_t j = 0; j < nc; ++j) ptr[j + 1] += ptr[j];
-  std::vector<uint32_t> fill(ptr.begin(), ptr.end() - 1);
-  for (uint64_t e = 0; e < nnz; ++e) { const uint32_t d = fill[cols[e]]++; row[d] = (uint32_t)rows[e]; val[d] = vals[e]; }  // stable: COO order kept per column
-  CK(cudaStreamSynchronize(ctx->stream));
-  dev_free(ctx->d_csc_row); dev_free(ctx->d_csc_val);
+  cudaStream_t s = ctx->stream;
   int rc;
-  if ((rc = dev_alloc(ctx, &ctx->d_csc_row, nnz)) || (rc = dev_alloc(ctx, &ctx->d_csc_val, nnz))) return rc;
-  CK(cudaMemcpy(ctx->d_csc_ptr, ptr.data(), (nc + 1) * 4, cudaMemcpyHostToDevice));
-  if (nnz) {
-    CK(cudaMemcpy(ctx->d_csc_row, row.data(), nnz * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_csc_val, val.data(), nnz * 8, cudaMemcpyHostToDevice));
+  if (nnz > ctx->csc_cap) {  // more non-zeros than any map before: larger arrays (the only case that waits for the stream)
+    CK(cudaStreamSynchronize(s));
+    dev_free(ctx->d_csc_row); dev_free(ctx->d_csc_val);
+    const size_t cap = (size_t)nnz + (size_t)nnz / 4;
+    if ((rc = dev_alloc(ctx, &ctx->d_csc_row, cap)) || (rc = dev_alloc(ctx, &ctx->d_csc_val, cap))) return rc;
+    ctx->csc_cap = cap;
   }
+  // COO -> CSC in pinned staging (stable: COO order kept per column, so every element accumulates its inflow terms
+  // in the order a sequential COO sweep does), then stream-ordered copies: no host synchronisation
+  const size_t o_ptr = 0, o_val = ((nc + 1) * 4 + 7) / 8 * 8, o_row = o_val + nnz * 8, bytes = o_row + nnz * 4;
+  unsigned char* h = nullptr; int slot = 0;
+  if ((rc = map_stage(ctx, bytes, &h, &slot))) return rc;
+  uint32_t* ptr = reinterpret_cast<uint32_t*>(h + o_ptr);
+  double* val = reinterpret_cast<double*>(h + o_val);
+  uint32_t* row = reinterpret_cast<uint32_t*>(h + o_row);
+  for (size_t j = 0; j <= nc; ++j) ptr[j] = 0;
+  for (uint64_t e = 0; e < nnz; ++e) ptr[cols[e] + 1]++;
+  for (size_t j = 0; j < nc; ++j) ptr[j + 1] += ptr[j];
+  std::vector<uint32_t> fill(ptr, ptr + nc);
+  for (uint64_t e = 0; e < nnz; ++e) { const uint32_t d = fill[cols[e]]++; row[d] = (uint32_t)rows[e]; val[d] = vals[e]; }
+  CK(cudaMemcpyAsync(ctx->d_csc_ptr, ptr, (nc + 1) * 4, cudaMemcpyHostToDevice, s));
+  if (nnz) {
+    CK(cudaMemcpyAsync(ctx->d_csc_row, row, nnz * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_csc_val, val, nnz * 8, cudaMemcpyHostToDevice, s));
+  }
+  CK(cudaEventRecord(ctx->ev_map[slot], s));
   ctx->transition_set = true;
   return BMC_OK;
 }
@@ -896,8 +940,8 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   const bool enable_move = ctx->n_comp > 1;        // kernels.hpp:53-55
   const bool enable_leave = !ctx->flows.empty();   // kernels.hpp:56
   if (ctx->lazy_ages) {
-    if (!ctx->epoch_set) { ctx->epoch_set = true; ctx->epoch_dt = d_t; ctx->epoch_leave = enable_leave; }
-    if (ctx->epoch_dt != d_t || ctx->epoch_leave != enable_leave || ctx->host_step >= 0x7ffffff0ull) {
+    if (!ctx->epoch_set) { ctx->epoch_set = true; ctx->epoch_dt = d_t; }
+    if (ctx->epoch_dt != d_t || ctx->host_step >= 0x7ffffff0ull) {
       if ((rc = make_ages_eager(ctx))) return rc;  // the stamps assume a constant increment per step
     } else if ((rc = ensure_age_tables(ctx, ctx->host_step + 2))) return rc;
   }
@@ -942,8 +986,10 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   // second phase of the step kernel: compaction (when triggered), newborn insertion, commit
   fill_post_params(ctx, p.post);
   p.post.count_step = 1;
-  p.post.newborn_stamp = ctx->lazy_ages ? (uint32_t)ctx->host_step + 1u : 0u;
-  p.post.tab_idx = (uint32_t)ctx->host_step;
+  // newborns age from the next step on: their stamps are the clock values AFTER this step
+  p.post.newborn_stamp_div = ctx->lazy_ages ? (uint32_t)ctx->host_step + 1u : 0u;
+  p.post.newborn_stamp_hyd = ctx->lazy_ages ? (uint32_t)(ctx->hyd_clock + (enable_leave ? 1u : 0u)) : 0u;
+  p.post.tab_idx_div = (uint32_t)ctx->host_step; p.post.tab_idx_hyd = (uint32_t)ctx->hyd_clock;
   p.post.tab_extend = ctx->lazy_ages ? 1 : 0; p.post.enable_leave = enable_leave ? 1 : 0; p.post.dt_f = (float)d_t; p.post.dt = d_t;
   if (ctx->p2p_on) {  // this step publishes its sources to the peers and finishes the previous all-reduce, if one is pending
     // (peers that are contexts on the SAME device — the test harness — cannot be waited for from inside a kernel that
@@ -983,6 +1029,7 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   if (enable_leave) ctx->maybe_inactive = true;  // exits may happen from now on
 
   ctx->host_step++;
+  if (enable_leave) ctx->hyd_clock++;
   return BMC_OK;
 }
 
@@ -1091,7 +1138,8 @@ struct CkptHeader {
   uint64_t events[6];
   double weight, allocation_factor, buffer_ratio, dead_ratio, epoch_dt;
   uint64_t min_removal;
-  uint32_t epoch_set, epoch_leave;
+  uint32_t epoch_set, reserved_epoch;
+  uint64_t hyd_clock;
   uint64_t tab_entries;     // lazy ages: entries of each age table that follow
   float src_bound[8], src_scale[8];  // fixed-point scatter state (DevState): a resumed run adds up the very same integers
   uint64_t logical_alloc, logical_buf;  // n_allocated_elements / buffer extent of the reference's container (serde.cpp archives n_allocated)
@@ -1130,7 +1178,7 @@ int bmc_checkpoint_save(bmc_ctx* ctx, void* buffer, uint64_t bytes) {
   h.last_out = hs.last_out; h.last_dead = hs.last_dead; h.last_waiting = hs.last_waiting;
   for (int i = 0; i < 6; ++i) h.events[i] = hs.events[i];
   h.weight = (double)ctx->weight; h.allocation_factor = ctx->allocation_factor; h.buffer_ratio = ctx->buffer_ratio; h.dead_ratio = ctx->dead_ratio;
-  h.epoch_dt = ctx->epoch_dt; h.min_removal = ctx->min_removal; h.epoch_set = ctx->epoch_set ? 1u : 0u; h.epoch_leave = ctx->epoch_leave ? 1u : 0u;
+  h.epoch_dt = ctx->epoch_dt; h.min_removal = ctx->min_removal; h.epoch_set = ctx->epoch_set ? 1u : 0u; h.hyd_clock = ctx->hyd_clock;
   h.tab_entries = tab;
   for (int i = 0; i < 8; ++i) { h.src_bound[i] = hs.src_bound[i]; h.src_scale[i] = hs.src_scale[i]; }
   h.logical_alloc = hs.logical_alloc; h.logical_buf = hs.logical_buf;
@@ -1185,11 +1233,12 @@ int bmc_checkpoint_load(bmc_ctx* ctx, const void* buffer, uint64_t bytes) {
   if (ctx->cap > n) CK(cudaMemsetAsync(ctx->status + n, 0, ctx->cap - n, s));  // slots beyond n_used are Idle
   CK(cudaMemcpyAsync(ctx->age_hyd, in, n * 4, cudaMemcpyHostToDevice, s)); in += n * 4;
   CK(cudaMemcpyAsync(ctx->age_div, in, n * 4, cudaMemcpyHostToDevice, s)); in += n * 4;
-  ctx->lazy_ages = h.lazy_ages != 0; ctx->epoch_set = h.epoch_set != 0; ctx->epoch_dt = h.epoch_dt; ctx->epoch_leave = h.epoch_leave != 0;
+  ctx->lazy_ages = h.lazy_ages != 0; ctx->epoch_set = h.epoch_set != 0; ctx->epoch_dt = h.epoch_dt;
   if (ctx->lazy_ages) {
     if ((rc = ensure_age_tables(ctx, tab + 1))) return rc;  // zero-extended: the next cycle writes entry `tab`
     CK(cudaMemcpyAsync(ctx->d_tab_hyd, in, tab * 4, cudaMemcpyHostToDevice, s)); in += tab * 4;
     CK(cudaMemcpyAsync(ctx->d_tab_div, in, tab * 4, cudaMemcpyHostToDevice, s)); in += tab * 4;
+    ctx->hyd_clock = h.hyd_clock;
     if (force_eager_ages()) { ctx->host_step = h.step; if ((rc = make_ages_eager(ctx))) return rc; }
   }
   DevState ds;
@@ -1220,7 +1269,7 @@ int bmc_compact(bmc_ctx* ctx) {
   PostParams ip;
   fill_post_params(ctx, ip);
   ip.count_step = 0;  // no newborn is waiting (the buffer index is reset by every commit): compaction + commit only
-  ip.newborn_stamp = 0; ip.tab_idx = 0; ip.tab_extend = 0; ip.enable_leave = 0; ip.dt_f = 0.f; ip.dt = 0.0;
+  ip.newborn_stamp_div = 0; ip.newborn_stamp_hyd = 0; ip.tab_idx_div = 0; ip.tab_idx_hyd = 0; ip.tab_extend = 0; ip.enable_leave = 0; ip.dt_f = 0.f; ip.dt = 0.0;
   void* pargs[] = {&ip};
   CK(cudaLaunchCooperativeKernel((const void*)post_only_kernel, dim3(ctx->grid_post), dim3(kBlock), pargs, 0, s));
   if ((rc = check_launch(ctx, "post_only"))) return rc;

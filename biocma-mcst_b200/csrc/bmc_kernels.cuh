@@ -114,19 +114,22 @@ struct Outlet { uint32_t index; uint32_t pad; double flow; double dt_flow; doubl
 
 // -----------------------------------------------------------------------------
 // Step-stamped ages.  The reference adds d_t to both ages of every idle particle on every
-// step (ages(i,1) += float(d_t) model_kernel.hpp:191; ages(i,0) += d_t move_kernel.hpp:596) —
-// 16 bytes of HBM traffic per particle-step for values no kernel ever reads.  While d_t and
-// the outlet configuration are constant and every age started at zero, the age of a particle
-// is a pure function of the number of steps since it was last reset, BITWISE: the k-fold
-// floating-point accumulation A[k] = fl(A[k-1] + d_t) is the same for every particle.  The age
-// columns then hold 32-bit step stamps
-//     idle particle :  s            age = A[now - s]   (s = first step that ages the particle)
-//     frozen        :  kFrozen | k  age = A[k]         (exited particle: no longer updated)
+// step (ages(i,1) += float(d_t) model_kernel.hpp:191; ages(i,0) += d_t move_kernel.hpp:596, the
+// latter only in steps that run the leave kernel, i.e. while the domain has an outlet) —
+// 16 bytes of HBM traffic per particle-step for values no kernel ever reads.  While d_t is
+// constant and every age started at zero, an age is a pure function of the number of increments
+// since it was last reset, BITWISE: the k-fold floating-point accumulation A[k] = fl(A[k-1] + d_t)
+// is the same for every particle.  Each age has its own clock — the division age ticks every
+// step, the hydraulic age only in steps with an outlet (adding nothing is exact, so switching
+// outlets on and off, as a fed-batch run does, costs nothing) — and the age columns hold 32-bit
+// clock stamps
+//     idle particle :  s            age = A[clock - s]   (s = clock value at the reset)
+//     frozen        :  kFrozen | k  age = A[k]           (exited particle: no longer updated)
 // which are written only when an age is reset (division, birth, exit).  A_div / A_hyd are
-// extended by one entry per step on the device (post_kernel) and applied when ages are read
-// (bmc_get_particles) — bit-identical to the eager accumulation.  If d_t or the outlet
-// configuration changes, or the caller supplies non-zero ages, the columns are converted to
-// floats in place and the eager kernel variant (LAZY = false) takes over.
+// extended by one entry per tick on the device (commit thread) and applied when ages are read
+// (bmc_get_particles) — bit-identical to the eager accumulation.  If d_t changes, or the caller
+// supplies non-zero ages, the columns are converted to floats in place and the eager kernel
+// variant (LAZY = false) takes over.
 // -----------------------------------------------------------------------------
 constexpr uint32_t kFrozen = 0x80000000u;
 
@@ -205,8 +208,9 @@ struct PostParams {
   int count_step;  // 1 when called from a cycle, 0 from force_remove_dead
   // step-stamped ages (bmc_kernels.cuh): stamp given to newborns (0 = eager float ages, bits of 0.f)
   // and the per-step extension of the age tables A_div / A_hyd
-  uint32_t newborn_stamp;
-  float* tab_div; float* tab_hyd; uint32_t tab_idx; int tab_extend; int enable_leave; float dt_f; double dt;
+  uint32_t newborn_stamp_div, newborn_stamp_hyd;
+  float* tab_div; float* tab_hyd; uint32_t tab_idx_div, tab_idx_hyd;  // clock values before this step
+  int tab_extend; int enable_leave; float dt_f; double dt;
 };
 
 struct CycleParams {
@@ -474,8 +478,8 @@ __device__ __forceinline__ void insert_newborn(const PostParams& p, unsigned lon
   }
   p.pos[dst] = npos;
   // both ages reset (eager: 0.f; stamped: the newborn ages from the next step on)
-  reinterpret_cast<uint32_t*>(p.age_hyd)[dst] = p.newborn_stamp;
-  reinterpret_cast<uint32_t*>(p.age_div)[dst] = p.newborn_stamp;
+  reinterpret_cast<uint32_t*>(p.age_hyd)[dst] = p.newborn_stamp_hyd;
+  reinterpret_cast<uint32_t*>(p.age_div)[dst] = p.newborn_stamp_div;
   p.status[dst] = (uint8_t)Idle;
 }
 
@@ -751,9 +755,8 @@ static __device__ __forceinline__ void post_cycle_body(const PostParams& p) {
       }
     }
     if (p.tab_extend) {  // A[k+1] = fl(A[k] + d_t): exactly the accumulation an eagerly updated age goes through
-      p.tab_div[p.tab_idx + 1] = p.tab_div[p.tab_idx] + p.dt_f;                       // model_kernel.hpp:191 (float d_t)
-      p.tab_hyd[p.tab_idx + 1] = p.enable_leave ? (float)((double)p.tab_hyd[p.tab_idx] + p.dt)  // move_kernel.hpp:596 (double d_t)
-                                                : p.tab_hyd[p.tab_idx];
+      p.tab_div[p.tab_idx_div + 1] = p.tab_div[p.tab_idx_div] + p.dt_f;                                  // model_kernel.hpp:191 (float d_t)
+      if (p.enable_leave) p.tab_hyd[p.tab_idx_hyd + 1] = (float)((double)p.tab_hyd[p.tab_idx_hyd] + p.dt);  // move_kernel.hpp:596 (double d_t)
     }
   }
 }

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <fstream>
 #include <optional>
 #include <stdexcept>
@@ -62,6 +63,63 @@ struct FlowMap {
     fm.m = fm.neighbors.size() / fm.n;
     return fm;
   }
+  // Flow map from the triplets of a flow matrix (bmc_cma_build: what the reference gets from rcmtool's
+  // get_transition_matrix / get_cumulative_probabilities / get_diag_transition, 03_cma.md:26-63)
+  static FlowMap from_flows(const std::vector<double>& volumes, const std::vector<uint64_t>& from, const std::vector<uint64_t>& to,
+                            const std::vector<double>& flow) {
+    FlowMap fm; fm.n = volumes.size(); fm.volumes = volumes;
+    uint64_t m = 0;
+    if (bmc_cma_build(fm.n, flow.size(), from.data(), to.data(), flow.data(), 0, &m, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr) != BMC_OK)
+      throw std::invalid_argument("invalid flow matrix");
+    fm.m = m;
+    std::size_t nz = fm.n;
+    for (std::size_t e = 0; e < flow.size(); ++e) nz += (from[e] != to[e] && flow[e] > 0.) ? 1 : 0;
+    fm.neighbors.resize(fm.n * m); fm.cdf.resize(fm.n * m); fm.out_flows.resize(fm.n);
+    fm.rows.resize(nz); fm.cols.resize(nz); fm.vals.resize(nz);
+    if (bmc_cma_build(fm.n, flow.size(), from.data(), to.data(), flow.data(), m, &m, fm.neighbors.data(), fm.cdf.data(), fm.out_flows.data(),
+                      fm.rows.data(), fm.cols.data(), fm.vals.data()) != BMC_OK)
+      throw std::invalid_argument("invalid flow matrix");
+    return fm;
+  }
+  // One flow map of an rcmtool case directory, as far as the format can be read off the one case in the reference
+  // tree (apps/api/tests/data/0d/{cma_case, vofL.raw, flowL.raw}; the format itself belongs to the un-vendored
+  // rcmtool crate):  vofL.raw = u32 n, then n f64 liquid volumes;  flowL.raw = u32 rows, u32 cols, then triplets
+  // {u64 row, u64 col, f64 flow} up to the end of the file.  `cma_case` names the two files (length-prefixed strings).
+  struct CmaCase { std::vector<std::string> files; uint32_t header[3] = {0, 0, 0}; double t_per_flowmap = 0.; };
+  static CmaCase read_cma_case(const std::string& dir) {
+    const auto raw = read_raw<unsigned char>(dir + "/cma_case");
+    CmaCase c;
+    if (raw.size() < 20) throw std::runtime_error("cma_case: file too short");
+    std::memcpy(c.header, raw.data(), 12);
+    std::memcpy(&c.t_per_flowmap, raw.data() + 12, 8);
+    for (std::size_t o = 20; o + 4 < raw.size(); ++o) {  // length-prefixed ASCII strings ending in ".raw"
+      uint32_t len = 0; std::memcpy(&len, raw.data() + o, 4);
+      if (len < 5 || len > 4096 || o + 4 + len > raw.size()) continue;
+      const std::string name(reinterpret_cast<const char*>(raw.data() + o + 4), len);
+      bool ascii = true; for (char ch : name) ascii = ascii && ch >= 0x20 && ch < 0x7f;
+      if (ascii && name.size() > 4 && name.compare(name.size() - 4, 4, ".raw") == 0) { c.files.push_back(name); o += 3 + len; }
+    }
+    if (c.files.size() < 2) throw std::runtime_error("cma_case: volume / flow file names not found");
+    return c;
+  }
+  static FlowMap load_cma_case(const std::string& dir) {
+    const CmaCase c = read_cma_case(dir);
+    auto find = [&](const char* key) { for (const auto& f : c.files) if (f.find(key) != std::string::npos) return dir + "/" + f; throw std::runtime_error(std::string("cma_case: no ") + key); };
+    const auto vraw = read_raw<unsigned char>(find("vof"));
+    uint32_t n = 0; std::memcpy(&n, vraw.data(), 4);
+    if (vraw.size() != 4 + 8 * static_cast<std::size_t>(n) || n == 0) throw std::runtime_error("vofL.raw: size does not match its count");
+    std::vector<double> vol(n); std::memcpy(vol.data(), vraw.data() + 4, 8 * static_cast<std::size_t>(n));
+    const auto fraw = read_raw<unsigned char>(find("flow"));
+    uint32_t nr = 0, ncol = 0; std::memcpy(&nr, fraw.data(), 4); std::memcpy(&ncol, fraw.data() + 4, 4);
+    if (nr != n || ncol != n || (fraw.size() - 8) % 24) throw std::runtime_error("flowL.raw: shape does not match the volumes");
+    std::vector<uint64_t> from, to; std::vector<double> flow;
+    for (std::size_t o = 8; o + 24 <= fraw.size(); o += 24) {
+      uint64_t r, cc; double f; std::memcpy(&r, fraw.data() + o, 8); std::memcpy(&cc, fraw.data() + o + 8, 8); std::memcpy(&f, fraw.data() + o + 16, 8);
+      if (r != cc && f > 0.) { from.push_back(r); to.push_back(cc); flow.push_back(f); }
+    }
+    if (n == 1) return zero_d(vol[0]);
+    return from_flows(vol, from, to, flow);
+  }
   // 0D reactor (apps/api/tests/data/0d: one compartment of 0.02 m3)
   static FlowMap zero_d(double volume = 0.02) {
     FlowMap fm; fm.n = 1; fm.m = 1; fm.volumes = {volume}; fm.out_flows = {0.}; fm.cdf = {0.}; fm.neighbors = {0};
@@ -84,6 +142,35 @@ struct FlowMap {
     return fm;
   }
   double total_volume() const { double s = 0; for (double v : volumes) s += v; return s; }
+};
+// Flow-map schedule of a run (CmaUtils::TransitionnerPtrType, used by host_specific.cpp:81-87, 263-266; the class itself
+// lives in the un-vendored rcmtool crate): `size()` flow maps, each valid for t_per_flow_map seconds, visited in a
+// loop (the reference's "n14" case rotates 14 maps, tools/cases.xml:21-46).
+//   need_advance(t, d_t): true when the map that covers time t is not the current one
+//   advance(t, d_t):      makes it current and returns it (main_loop then calls simulation.updateHydro)
+class Transitioner {
+ public:
+  Transitioner(std::vector<FlowMap> maps, double t_per_flow_map) : maps_(std::move(maps)), t_per_(t_per_flow_map) {
+    if (maps_.empty()) throw std::invalid_argument("Transitioner: no flow map");
+    for (const auto& m : maps_) if (m.n != maps_[0].n) throw std::invalid_argument("Transitioner: flow maps of different size");
+  }
+  std::size_t size() const noexcept { return maps_.size(); }
+  std::size_t index_at(double t) const noexcept {
+    if (maps_.size() == 1 || !(t_per_ > 0.)) return 0;
+    return static_cast<std::size_t>(std::floor(t / t_per_)) % maps_.size();
+  }
+  bool need_advance(double t, double /*d_t*/) const noexcept { return index_at(t) != current_; }
+  const FlowMap& advance(double t, double /*d_t*/) noexcept { current_ = index_at(t); return maps_[current_]; }
+  const FlowMap& get_current() const noexcept { return maps_[current_]; }
+  std::size_t current_index() const noexcept { return current_; }
+  double t_per_flow_map() const noexcept { return t_per_; }
+  // compute_n_per_flowmap (global_initaliser.cpp:103-114)
+  std::size_t n_per_flowmap(double d_t) const noexcept {
+    return (t_per_ == 0. || maps_.size() == 1) ? 1 : static_cast<std::size_t>(t_per_ / d_t) + 1;
+  }
+
+ private:
+  std::vector<FlowMap> maps_; double t_per_; std::size_t current_ = 0;
 };
 // get_time_step: min(F/V)/100 although named residence time (utils.cpp:47-74, global_initaliser.cpp:65-72; Q10)
 inline double get_time_step(const FlowMap& fm) {
@@ -348,7 +435,8 @@ inline void get_n_interval(const SimulationParameters& p, std::size_t& n_iter, s
   dump_interval = (p.number_exported_result != 0 && dump_number != 0) ? n_iter / dump_number + 1 : n_iter + 1;
 }
 // main_loop, host_specific.cpp:215-330 (single rank; the ordering is the contract)
-inline Records main_loop(const SimulationParameters& params, Simulation::SimulationUnit& simulation) {
+inline Records main_loop(const SimulationParameters& params, Simulation::SimulationUnit& simulation,
+                         CmaUtils::Transitioner* d_transitionner = nullptr) {
   Records rec;
   std::size_t n_iter = 0, dump_interval = 0;
   get_n_interval(params, n_iter, dump_interval);
@@ -363,7 +451,10 @@ inline Records main_loop(const SimulationParameters& params, Simulation::Simulat
     rec.tallies.insert(rec.tallies.end(), ev.begin(), ev.end());
   };
   simulation.update_feed(d_t);  // :241 (before the loop: the first step sees the feed twice, as in the reference)
+  if (d_transitionner) simulation.updateHydro(d_transitionner->advance(simulation.absolute(), d_t));  // UPDATE_HYDRO_STEP, :257
   for (std::size_t it = 0; it < n_iter; ++it) {
+    if (d_transitionner && d_transitionner->need_advance(simulation.absolute(), d_t))  // :263-266
+      simulation.updateHydro(d_transitionner->advance(simulation.absolute(), d_t));
     if (params.number_exported_result != 0 && it % dump_interval == 0) dump();
     // sync_step: single rank -> nothing to reduce (multi-GPU: bmc_allreduce_sources inside cycleProcess)
     simulation.update_feed(d_t);

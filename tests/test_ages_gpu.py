@@ -81,8 +81,10 @@ def test_time_step_change_switches_to_eager(bmc, orc, synth):
 
 
 def test_outlet_switched_on_mid_run(bmc, orc, synth):
-    # age_hyd only advances while an outlet exists (cycle_move_leave runs only if enable_leave, kernels.hpp:142-157)
-    case = util.make_case(synth, "fixed_length", 20_000, 16, dt=5.0, p_move=0.3, p_exit=0.1)
+    # age_hyd only advances while an outlet exists (cycle_move_leave runs only if enable_leave, kernels.hpp:142-157).
+    # The hydraulic age has its own clock (steps WITH an outlet), so a fed-batch run that opens and closes its outlet
+    # stays on the stamped-age kernel — and stays bit-identical to the eager accumulation of the oracle.
+    case = util.make_case(synth, "fixed_length", 20_000, 16, dt=300.0, near_division=0.5, p_move=0.3, p_exit=0.1)
     flows = case["flows"]
     g, o = _pair(bmc, orc, case)
     _load(g, case); _load(o, case)
@@ -90,10 +92,14 @@ def test_outlet_switched_on_mid_run(bmc, orc, synth):
     util.run_steps(g, case, 5); util.run_steps(o, case, 5)
     _same(g, o)
     assert np.all(g.get_particles()["age_hyd"] == 0.0)
-    g.set_leaving_flows(flows); o.set_leaving_flows(flows)
-    util.run_steps(g, case, 5); util.run_steps(o, case, 5)
-    _same(g, o)
+    for k, fl in enumerate((flows, [], flows, [], flows)):   # open, close, open, ... with divisions and exits in between
+        g.set_leaving_flows(fl); o.set_leaving_flows(fl)
+        util.run_steps(g, case, 3 + k); util.run_steps(o, case, 3 + k)
+        _same(g, o)
     assert np.any(g.get_particles()["age_hyd"] > 0.0)
+    c = o.counters()
+    assert c["total_new"] > 0 and c["total_out"] > 0
+    assert g.kernel_config()["stamped_ages"], "an outlet toggle must not drop to the eager-age kernel"
 
 
 def test_eager_forced_by_environment_matches(bmc, orc, synth, monkeypatch):

@@ -124,3 +124,42 @@ def test_cli_serde_resume(synth, tmp_path):
     na = np.fromfile(str(tmp_path / "a2") + "_number_particle.raw", np.uint64).reshape(-1, n_comp)[-1]
     nb = np.fromfile(str(tmp_path / "b") + "_number_particle.raw", np.uint64).reshape(-1, n_comp)[-1]
     assert np.array_equal(na, nb)
+
+
+def test_cli_reads_the_reference_0d_case_and_initialiser(tmp_path):
+    # -f <directory with an rcmtool cma_case> (apps/api/tests/data/0d, written here byte for byte) and -fi <raw f64 file>
+    import test_transitioner as tt
+    case_dir = tmp_path / "0d"
+    case_dir.mkdir()
+    tt._write_case(str(case_dir), {"cma_case": tt.CMA_CASE_0D, "vofL.raw": tt.VOF_0D, "flowL.raw": tt.FLOW_0D})
+    fi = tmp_path / "c0.raw"
+    np.array([3.25]).tofile(str(fi))
+    exe = os.path.join(HOST, "biocma_b200")
+    stem = str(tmp_path / "res")
+    r = subprocess.run([exe, "-np", "20000", "-d", "1.0", "-dt", "0.05", "-mn", "monod", "-f", str(case_dir), "-fi", str(fi), "-er", stem,
+                        "-nex", "3"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    assert info["balance_ok"] and info["n_compartments"] == 1
+    C = np.fromfile(stem + "_concentration_liquid.raw", np.float64)
+    assert C[0] == 3.25 and C[-1] < 3.25            # starts from the initialiser, the cells take the substrate up
+    bad = tmp_path / "bad.raw"
+    np.array([1.0, 2.0]).tofile(str(bad))
+    r = subprocess.run([exe, "-np", "20000", "-d", "1.0", "-f", str(case_dir), "-fi", str(bad)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 2 and "-fi" in r.stderr
+
+
+def test_cli_rotating_flow_maps_and_default_model(tmp_path):
+    # rotate:<maps>:<n>:<t_per_flow_map>: the transitioner drives updateHydro inside main_loop (host_specific.cpp:263-266);
+    # an unknown model name falls back to the default model with an alert (global_initaliser.cpp:261-271)
+    exe = os.path.join(HOST, "biocma_b200")
+    stem = str(tmp_path / "rot")
+    r = subprocess.run([exe, "-np", "30000", "-d", "8.0", "-dt", "0.1", "-mn", "two_meta_div", "-f", "rotate:14:16:0.5", "-er", stem, "-nex", "4"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "using the default model" in r.stderr
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    assert info["balance_ok"] and info["n_compartments"] == 16 and info["steps"] == 81
+    # the exchange rate differs from map to map, so the occupancy keeps being redistributed: every compartment is visited
+    npart = np.fromfile(stem + "_number_particle.raw", np.uint64).reshape(-1, 16)
+    assert npart[-1].sum() == info["n_particles"] and np.all(npart[-1] > 0)
