@@ -201,6 +201,7 @@ P_EXIT = {"c3": 0.05}
 # c3 grows by ~1 % per step: like a production run that knows its horizon, the arrays are reserved up front (bmc_reserve)
 # so that no reallocation (a one-off of tens of ms) lands inside a 30-step timed region
 RESERVE = {"c3": 2.4}
+PROFILE_EVERY = 4
 
 
 def run_reference(args, wl):
@@ -381,7 +382,9 @@ def measure(D, pkg, synth, wl, n_per_gpu, steps, warmup, e2e_steps, eager=False,
     # ---------------- value: device-resident steps -----------------------------
     c0 = loop.counters()
     launches0 = loop.launch_count()
-    loop.profile_enable(True)
+    # CUDA events around every PROFILE_EVERY-th step kernel of the timed region (around every one they cost ~7 % of a
+    # 90 us step: two event records per launch on the launching stream)
+    loop.profile_enable(PROFILE_EVERY if steps >= 4 * PROFILE_EVERY else 1)  # at least 4 samples
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     D.barrier(loop)
     if sampler is not None:
@@ -395,7 +398,7 @@ def measure(D, pkg, synth, wl, n_per_gpu, steps, warmup, e2e_steps, eager=False,
         sampler.mark_end()
     ms = e0.elapsed_time(e1)
     kernel_ms, kernel_n = loop.profile_read()
-    loop.profile_enable(False)
+    loop.profile_enable(0)
     launches = loop.launch_count() - launches0
     c1 = loop.counters()
     live_avg = 0.5 * (c0["n_used"] + c1["n_used"])
@@ -457,7 +460,7 @@ def measure(D, pkg, synth, wl, n_per_gpu, steps, warmup, e2e_steps, eager=False,
                      "traffic": traffic, "traffic_source": traffic_src,
                      "kernel": f"cycle_kernel<{model}, VEC={kcfg['vec']}, {block} threads, {'eager' if eager else 'stamped'} ages> "
                                "(whole step: particle pass + post-cycle phase)",
-                     "kernel_ms": k_ms, "bytes_per_particle": b_alg,
+                     "kernel_ms": k_ms, "kernel_ms_samples": int(kernel_n), "bytes_per_particle": b_alg,
                      "bytes_per_particle_note": ("ages loaded and stored every step (the layout SURVEY.md 8d counts)" if eager else
                                                  "4*(R+W) property bytes + position 8 + status 1; ages are step stamps, not rewritten"),
                      "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", "kernel_share_of_step": k_ms * steps / ms},

@@ -87,7 +87,8 @@ struct bmc_ctx {
   // staging
   void* d_stage = nullptr; size_t stage_bytes = 0;
   // profiling
-  bool profile = false; std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events; size_t prof_used = 0;  // pool, reused after bmc_profile_read
+  int profile = 0;  // 0 = off, N = CUDA events around every N-th step kernel
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events; size_t prof_used = 0;  // pool, reused after bmc_profile_read
   double prof_ms = 0.0; uint64_t prof_n = 0;
   // step-stamped ages (bmc_kernels.cuh): valid while d_t / outlet configuration stay constant and
   // every age started at zero; otherwise the columns hold floats updated every step ("eager")
@@ -390,7 +391,7 @@ static uint64_t predicted_births(uint64_t n, uint64_t recent) { return 2 * recen
 static size_t initial_capacity(const bmc_ctx* ctx, uint64_t n) {
   unsigned long long la = 0, lb = 0;
   if (n) logical_grow(n, ctx->allocation_factor, ctx->buffer_ratio, la, lb);
-  return (size_t)std::max<uint64_t>(std::max<uint64_t>(la, n + worst_case_births(n, lb) + n / 64 + 1024), 1);
+  return (size_t)std::max<uint64_t>(std::max<uint64_t>(la, n + worst_case_births(n, lb) + n / 8 + 1024), 1);
 }
 
 static int ensure_room(bmc_ctx* ctx) {
@@ -410,11 +411,12 @@ static int ensure_room(bmc_ctx* ctx) {
       DevState s;
       if ((rc = sync_state(ctx, &s))) return rc;
       const uint64_t n = s.n_used, pred = predicted_births(n, std::max<uint64_t>(s.n_add, ctx->recent_max_add));
-      uint64_t want = n + worst_case_births(n, s.logical_buf) + n / 64 + 1024;
+      uint64_t want = n + worst_case_births(n, s.logical_buf) + n / 8 + 1024;
       want = std::max<uint64_t>(want, (uint64_t)std::ceil((double)(n + (kMaxAhead + 1) * pred) * ctx->allocation_factor));
       want = std::max<uint64_t>(want, s.logical_alloc);
       want = std::max<uint64_t>(want, (uint64_t)std::ceil((double)s.logical_buf / ctx->buffer_ratio));
       if (want <= ctx->cap) return BMC_OK;  // (only the pinned mirror was behind)
+      want = std::max<uint64_t>(want, ctx->cap + ctx->cap / 4);  // geometric: a reallocation copies every particle
       ctx->n_regrow++;
       return resize_container(ctx, (size_t)want, (size_t)n);
     }
@@ -1000,7 +1002,8 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   }
 
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (ctx->profile) {  // event pairs come from a pool that bmc_profile_read recycles: nothing is created in steady state
+  const bool prof_this = ctx->profile > 0 && ctx->host_step % (uint64_t)ctx->profile == 0;
+  if (prof_this) {  // event pairs come from a pool that bmc_profile_read recycles: nothing is created in steady state
     if (ctx->prof_used == ctx->prof_events.size()) {
       CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
       ctx->prof_events.emplace_back(e0, e1);
@@ -1025,7 +1028,7 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
     CK(cudaLaunchCooperativeKernel((const void*)post_only_kernel, dim3(ctx->grid_post), dim3(kBlock), pargs, 0, s));
     if ((rc = check_launch(ctx, "post_only"))) return rc;
   }
-  if (ctx->profile) { CK(cudaEventRecord(e1, s)); ctx->prof_used++; }
+  if (prof_this) { CK(cudaEventRecord(e1, s)); ctx->prof_used++; }
   if (enable_leave) ctx->maybe_inactive = true;  // exits may happen from now on
 
   ctx->host_step++;
@@ -1306,7 +1309,7 @@ int bmc_kernel_config(const bmc_ctx* ctx, int32_t* out6) {
 }
 int bmc_profile_enable(bmc_ctx* ctx, int on) {
   if (!ctx) return BMC_ERR_INVALID;
-  ctx->profile = on != 0;
+  ctx->profile = on < 0 ? 0 : on;  // 1 = every step kernel, N = every N-th (two event records cost a few microseconds each)
   return BMC_OK;
 }
 // tuning aid (not declared in bmc.h): %globaltimer stamps of block 0 of the last step kernel; only

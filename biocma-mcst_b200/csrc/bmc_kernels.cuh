@@ -492,6 +492,16 @@ static __device__ __forceinline__ void post_cycle_body(const PostParams& p) {
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned long long gtid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned long long gstride = (unsigned long long)gridDim.x * blockDim.x;
+  // plan inputs (read-only on the counters: every block derives the same values; six threads per block read them,
+  // so that the few counter lines are not hammered by every thread of the grid).  Issued before the publish loop:
+  // the round trip overlaps it.
+  __shared__ unsigned long long s_plan[6];
+  unsigned long long plan_v = 0ull;
+  if (threadIdx.x < 6) {
+    const unsigned long long* src = threadIdx.x == 0 ? &st->step_exit : threadIdx.x == 1 ? &st->n_used : threadIdx.x == 2 ? &st->inactive
+                                  : threadIdx.x == 3 ? &st->buf_index : threadIdx.x == 4 ? &st->buf_cap_eff : nullptr;
+    plan_v = src ? __ldcg(src) : (unsigned long long)__ldcg(&st->force_compact);
+  }
   // ---- publish the source terms of this step; the accumulator is left zeroed for the next one
   // (not from force_remove_dead: the sources of the last cycle stay what they are)
   if (p.count_step) {
@@ -509,14 +519,8 @@ static __device__ __forceinline__ void post_cycle_body(const PostParams& p) {
     }
   }
   BMC_STAMP(st, 5);
-  // ---- plan (read-only on the counters: every block derives the same values; one warp per block
-  // reads them, so that the few counter lines are not hammered by every thread of the grid)
-  __shared__ unsigned long long s_plan[6];
-  if (threadIdx.x < 6) {
-    const unsigned long long* src = threadIdx.x == 0 ? &st->step_exit : threadIdx.x == 1 ? &st->n_used : threadIdx.x == 2 ? &st->inactive
-                                  : threadIdx.x == 3 ? &st->buf_index : threadIdx.x == 4 ? &st->buf_cap_eff : nullptr;
-    s_plan[threadIdx.x] = src ? __ldcg(src) : (unsigned long long)__ldcg(&st->force_compact);
-  }
+  // ---- plan
+  if (threadIdx.x < 6) s_plan[threadIdx.x] = plan_v;
   __syncthreads();
   const unsigned long long out = s_plan[0];
   const unsigned long long n_before = s_plan[1];
@@ -846,6 +850,13 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
   uint32_t* const s_queue = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(s_dyn) + p.queue_offset) + warp * queue_entries(VEC);
 
   BMC_STAMP(p.st, 0);
+#if defined(BMC_TIMELINE)
+  if (threadIdx.x == 0) {  // per-block start of the kernel (step parity selects the half): words [4G + 8b + 4*(step&1) ..]
+    unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+    uint32_t* w = p.post.src + 4 * gridDim.x + 8 * blockIdx.x + 4 * (p.step & 1u);
+    w[0] = (uint32_t)t_; w[1] = (uint32_t)(t_ >> 32);
+  }
+#endif
   if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
   if (threadIdx.x < 8) s_fxmax[threadIdx.x] = 0u;
   if (threadIdx.x < kRing) { s_chunk_seq[threadIdx.x] = 0u; s_chunk_left[threadIdx.x] = 0u; s_chunk_base[threadIdx.x] = 0u; }
@@ -1254,8 +1265,7 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
       if (lane == 0 && a != 0.0) atomicAdd(p.acc + j, a);
     }
   }
-  __threadfence();
-  __syncthreads();
+  __syncthreads();  // s_cnt, s_fxmax and the bins of every warp are complete (shared memory: no device-wide fence needed)
   if (threadIdx.x == 0) {
     const unsigned long long cm = s_cnt[0], ce = s_cnt[1], cn = s_cnt[2], co = s_cnt[3];
     if (cm) atomicAdd(&p.st->events[2], cm);                                             // Move
@@ -1281,6 +1291,13 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
     BMC_STAMP(p.st, 4);
     post_cycle_body(p.post);
     BMC_STAMP(p.st, 8);
+#if defined(BMC_TIMELINE)
+    if (threadIdx.x == 0) {  // per-block end of the kernel
+      unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+      uint32_t* w = p.post.src + 4 * gridDim.x + 8 * blockIdx.x + 4 * (p.step & 1u);
+      w[2] = (uint32_t)t_; w[3] = (uint32_t)(t_ >> 32);
+    }
+#endif
   }
 }
 

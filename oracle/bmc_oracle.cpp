@@ -395,7 +395,7 @@ int WideUdf::n_var_rt = 32;
 
 // The reference's example user-defined model, apps/udf_model/minimal.cpp:24-121 (loaded through
 // `-mn udf_model` + BIOMC_LIB_UDF).  The CUDA path compiles its own source-level version of it
-// (biocma-mcst_b200/udf/minimal_udf.cu) with NVRTC; this is the independent CPU restatement.
+// (examples/minimal_udf.cu) with NVRTC; this is the independent CPU restatement.
 struct UdfMinimal {
   static constexpr int n_var = 2, n_c = 1;
   enum { length = 0, l_max = 1 };

@@ -232,7 +232,7 @@ def test_oracle_init_reproduces_reference_fixture(orc, model):
     assert np.array_equal(st["position"].astype(np.uint32), z["pos"])
 
 
-UDF_SRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "biocma-mcst_b200", "udf", "minimal_udf.cu")
+UDF_SRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "minimal_udf.cu")
 
 
 def _cuda_loop(bmc, model, n_species, n_comp, seed, **runtime):

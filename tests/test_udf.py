@@ -13,7 +13,7 @@ import pytest
 import util
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-UDF_SRC = os.path.join(ROOT, "biocma-mcst_b200", "udf", "minimal_udf.cu")
+UDF_SRC = os.path.join(ROOT, "examples", "minimal_udf.cu")
 
 
 def test_example_udf_compiles_without_device(bmc):

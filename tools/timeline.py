@@ -32,3 +32,15 @@ sm_mean = np.array([np.mean(v) for v in per_sm.values()]); sm_spread = np.array(
 print("per-SM mean end: min %.1f max %.1f ; within-SM spread mean %.1f max %.1f ; SMs %d" % (sm_mean.min(), sm_mean.max(), sm_spread.mean(), sm_spread.max(), len(per_sm)))
 order = np.argsort(us); print("slowest blocks:", [(int(b), int(smid[b]), int(tiles[b]), round(float(us[b]), 1)) for b in order[-8:]])
 print("fastest blocks:", [(int(b), int(smid[b]), int(tiles[b]), round(float(us[b]), 1)) for b in order[:8]])
+
+# per-block start / end of the last two kernels (step parity halves)
+raw2 = np.zeros(12 * G, np.uint32)
+lib.bmc_debug_blocks(g.h, raw2.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(raw2.size))
+w = raw2[4 * G:].reshape(G, 8).astype(np.int64)
+def u64(lo, hi): return lo | (hi << 32)
+st = [u64(w[:, 0], w[:, 1]), u64(w[:, 4], w[:, 5])]; en = [u64(w[:, 2], w[:, 3]), u64(w[:, 6], w[:, 7])]
+last = 0 if st[0].min() > st[1].min() else 1   # the later kernel
+prev = 1 - last
+print("previous kernel: first start 0, last start %.1f, first end %.1f, last end %.1f us" % tuple((x - st[prev].min()) / 1000.0 for x in (st[prev].max(), en[prev].min(), en[prev].max())))
+print("gap: last end of previous kernel -> first start of next %.1f us, -> last start of next %.1f us" % ((st[last].min() - en[prev].max()) / 1000.0, (st[last].max() - en[prev].max()) / 1000.0))
+print("next kernel: duration first start -> last end %.1f us ; period (start to start) %.1f us" % ((en[last].max() - st[last].min()) / 1000.0, (st[last].min() - st[prev].min()) / 1000.0))
