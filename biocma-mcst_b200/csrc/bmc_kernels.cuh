@@ -422,32 +422,6 @@ __device__ __forceinline__ unsigned block_prefix_of(const uint32_t* blk_tot, uns
   return s_tmp[b];
 }
 
-// flags of the slots a thread owns in `tile` (slot = r*blockDim + thread, r < 4: blocks of 256..1024
-// threads) + per-virtual-warp counts in s_w[32] (virtual warp = 32 consecutive slots); returns the
-// ballots; ends with a barrier so that s_w is complete
-template <bool WANT_GAP>
-__device__ __forceinline__ void tile_flags(const PostParams& p, uint32_t tile, unsigned long long old_n, unsigned long long new_n,
-                                           unsigned (&bal)[4], bool (&flag)[4], unsigned* s_w) {
-  const unsigned lane = threadIdx.x & 31;
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const unsigned slot = (unsigned)r * blockDim.x + threadIdx.x;  // uniform per warp: blockDim is a multiple of 32
-    flag[r] = false; bal[r] = 0u;
-    if (slot < (unsigned)kTile) {
-      const unsigned long long i = (unsigned long long)tile * kTile + slot;
-      bool f = false;
-      if (i < old_n) {
-        const bool is_idle = p.status[i] == (uint8_t)Idle;
-        f = WANT_GAP ? (i < new_n && !is_idle) : (i >= new_n && is_idle);
-      }
-      flag[r] = f;
-      bal[r] = __ballot_sync(0xffffffffu, f);
-      if (lane == 0) s_w[slot >> 5] = __popc(bal[r]);
-    }
-  }
-  __syncthreads();
-}
-
 // Grid-wide barrier for cooperatively launched kernels (all blocks resident): arrive counter +
 // generation word in DevState.
 __device__ __forceinline__ void grid_barrier(DevState* st) {
@@ -532,80 +506,104 @@ static __device__ __forceinline__ void post_cycle_body(const PostParams& p) {
   const unsigned long long n_add = s_plan[3] < s_plan[4] ? s_plan[3] : s_plan[4];
 
   if (do_compact) {  // uniform across the grid
+    // One WARP per 1024-slot tile: lane l owns slots [32 l, 32 l + 32) of the tile and reads their status bytes with two
+    // 128-bit loads (1 KB per warp, fully coalesced); flags live in one 32-bit word per lane, counts are popcounts, ranks
+    // inside a tile come from a warp scan.  No block-wide barrier per tile (the first version had two per tile and took
+    // 1.6 ms to remove 5e4 particles from 1e8: 660 serial tiles per block, and the ~1000 tail tiles all owned by the
+    // last two blocks).
     const uint32_t n_tiles = (uint32_t)((old_n + kTile - 1) / kTile);
-    const uint32_t t0 = (uint32_t)(((unsigned long long)blockIdx.x * n_tiles) / gridDim.x);
-    const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
-    // ---- count ----
-    {
+    const unsigned G = gridDim.x, nwarp = blockDim.x >> 5;
+    const uint32_t t0 = (uint32_t)(((unsigned long long)blockIdx.x * n_tiles) / G);
+    const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / G);
+    const unsigned lt = (1u << lane) - 1u;
+    // bit b of the result: slot (tile, 32*lane + b) is a GAP (not idle, below new_n) / an idle particle of the TAIL
+    auto lane_bits = [&](uint32_t tile, unsigned& gap, unsigned& tail) {
+      const unsigned long long base = (unsigned long long)tile * kTile + 32ull * lane;
+      const uint4* ptr = reinterpret_cast<const uint4*>(p.status + base);  // the capacity is a multiple of 1024: in range
+      const uint4 a = ptr[0], c = ptr[1];
+      const unsigned w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+      unsigned nonidle = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)  // one bit per status byte: 0xff where the byte differs from Idle (0)
+        nonidle |= ((((__vcmpne4(w[k], 0u)) & 0x01010101u) * 0x01020408u) >> 24) << (4 * k);
+      auto below = [&](unsigned long long lim) -> unsigned {  // bits of the slots < lim
+        return base + 32ull <= lim ? 0xffffffffu : (base >= lim ? 0u : ((1u << (unsigned)(lim - base)) - 1u));
+      };
+      const unsigned valid = below(old_n), low = below(new_n);
+      gap = nonidle & valid & low;
+      tail = ~nonidle & valid & ~low;
+    };
+    // ---- count: every block counts its own contiguous tile range (equal work per tile), then scans it ----
+    for (uint32_t tile = t0 + warp; tile < t1; tile += nwarp) {
+      unsigned gb, tb;
+      lane_bits(tile, gb, tb);
+      const unsigned g = __reduce_add_sync(0xffffffffu, (unsigned)__popc(gb)), i = __reduce_add_sync(0xffffffffu, (unsigned)__popc(tb));
+      if (lane == 0) { p.tile_gap_off[tile] = g; p.tile_idle_off[tile] = i; }
+    }
+    __syncthreads();
+    if (warp == 0) {  // counts -> block-local exclusive prefixes, block totals
       unsigned run_g = 0, run_i = 0;
-      for (uint32_t tile = t0; tile < t1; ++tile) {
-        unsigned bal[4]; bool fl[4];
-        tile_flags<true>(p, tile, old_n, new_n, bal, fl, s_w);
-        unsigned tg = 0;
-        if (warp == 0) tg = __reduce_add_sync(0xffffffffu, s_w[lane]);
-        __syncthreads();
-        tile_flags<false>(p, tile, old_n, new_n, bal, fl, s_w);
-        if (warp == 0) {
-          const unsigned ti = __reduce_add_sync(0xffffffffu, s_w[lane]);
-          if (lane == 0) { p.tile_gap_off[tile] = run_g; p.tile_idle_off[tile] = run_i; }
-          run_g += tg; run_i += ti;
-        }
-        __syncthreads();
+      for (uint32_t bt = t0; bt < t1; bt += 32) {
+        const uint32_t t = bt + lane;
+        const unsigned g = t < t1 ? p.tile_gap_off[t] : 0u, i = t < t1 ? p.tile_idle_off[t] : 0u;
+        unsigned tg, ti;
+        const unsigned eg = warp_excl_scan(g, tg), ei = warp_excl_scan(i, ti);
+        if (t < t1) { p.tile_gap_off[t] = run_g + eg; p.tile_idle_off[t] = run_i + ei; }
+        run_g += tg; run_i += ti;
       }
-      if (threadIdx.x == 0) { p.blk_gap[blockIdx.x] = run_g; p.blk_idle[blockIdx.x] = run_i; }
+      if (lane == 0) { p.blk_gap[blockIdx.x] = run_g; p.blk_idle[blockIdx.x] = run_i; }
     }
     grid_barrier(st);
-    // ---- src: k-th idle tail particle counted from the end ----
+    auto owner_of = [&](uint32_t tile) -> unsigned { return (unsigned)((((unsigned long long)tile + 1ull) * G - 1ull) / n_tiles); };
+    const unsigned gwarp = blockIdx.x * nwarp + warp, gwarps = G * nwarp;
+    // ---- src: k-th idle tail particle counted from the end; tail tiles spread over ALL warps of the grid ----
     unsigned total_idle;
     {
-      const unsigned blk_off = block_prefix_of(p.blk_idle, gridDim.x, blockIdx.x, s_pref, total_idle);
+      block_prefix_of(p.blk_idle, G, blockIdx.x, s_pref, total_idle);
       const uint32_t first_tail_tile = (uint32_t)(new_n / kTile);
-      for (uint32_t tile = (t0 > first_tail_tile ? t0 : first_tail_tile); tile < t1; ++tile) {
-        unsigned bal[4]; bool fl[4];
-        tile_flags<false>(p, tile, old_n, new_n, bal, fl, s_w);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          if (fl[r]) {
-            unsigned woff = 0;
-            const unsigned slot = (unsigned)r * blockDim.x + threadIdx.x;
-            for (unsigned k = 0; k < (slot >> 5); ++k) woff += s_w[k];
-            const unsigned asc = blk_off + p.tile_idle_off[tile] + woff + __popc(bal[r] & ((1u << lane) - 1u));
-            p.src[total_idle - 1u - asc] = (uint32_t)((unsigned long long)tile * kTile + slot);
-          }
+      for (uint32_t tile = first_tail_tile + gwarp; tile < n_tiles; tile += gwarps) {
+        unsigned gb, tb;
+        lane_bits(tile, gb, tb);
+        unsigned tot;
+        const unsigned ex = warp_excl_scan((unsigned)__popc(tb), tot);
+        unsigned asc = s_pref[owner_of(tile)] + p.tile_idle_off[tile] + ex;
+        while (tb) {
+          const unsigned bit = __ffs(tb) - 1u;
+          tb &= tb - 1u;
+          p.src[total_idle - 1u - asc] = (uint32_t)((unsigned long long)tile * kTile + 32u * lane + bit);
+          ++asc;
         }
-        __syncthreads();
       }
     }
     grid_barrier(st);
-    // ---- move: gaps below new_n pull their replacement ----
+    // ---- move: gaps below new_n pull their replacement; low tiles spread over all warps of the grid ----
     {
       unsigned total_gap;
-      const unsigned blk_off = block_prefix_of(p.blk_gap, gridDim.x, blockIdx.x, s_pref, total_gap);
+      block_prefix_of(p.blk_gap, G, blockIdx.x, s_pref, total_gap);
       const uint32_t last_low_tile = (uint32_t)((new_n + kTile - 1) / kTile);  // exclusive
-      for (uint32_t tile = t0; tile < t1 && tile < last_low_tile; ++tile) {
-        unsigned bal[4]; bool fl[4];
-        tile_flags<true>(p, tile, old_n, new_n, bal, fl, s_w);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          if (fl[r]) {
-            unsigned woff = 0;
-            const unsigned slot = (unsigned)r * blockDim.x + threadIdx.x;
-            for (unsigned k = 0; k < (slot >> 5); ++k) woff += s_w[k];
-            const unsigned k = blk_off + p.tile_gap_off[tile] + woff + __popc(bal[r] & ((1u << lane) - 1u));
-            if (k >= total_idle) {
-              atomicOr(&st->error, 2u);  // inactive counter inconsistent with the status column
-            } else {
-              const size_t i = (size_t)tile * kTile + slot;
-              const size_t s2 = p.src[k];
-              p.status[i] = (uint8_t)Idle;
-              p.pos[i] = p.pos[s2];
-              for (int c = 0; c < p.n_var; ++c) p.props[(size_t)c * p.cap + i] = p.props[(size_t)c * p.cap + s2];
-              p.age_hyd[i] = p.age_hyd[s2];
-              p.age_div[i] = p.age_div[s2];
-            }
+      for (uint32_t tile = gwarp; tile < last_low_tile; tile += gwarps) {
+        unsigned gb, tb;
+        lane_bits(tile, gb, tb);
+        if (!__any_sync(0xffffffffu, gb != 0u)) continue;  // most tiles have no gap
+        unsigned tot;
+        const unsigned ex = warp_excl_scan((unsigned)__popc(gb), tot);
+        unsigned k = s_pref[owner_of(tile)] + p.tile_gap_off[tile] + ex;
+        while (gb) {
+          const unsigned bit = __ffs(gb) - 1u;
+          gb &= gb - 1u;
+          if (k >= total_idle) {
+            atomicOr(&st->error, 2u);  // inactive counter inconsistent with the status column
+          } else {
+            const size_t i = (size_t)tile * kTile + 32u * lane + bit;
+            const size_t s2 = p.src[k];
+            p.status[i] = (uint8_t)Idle;
+            p.pos[i] = p.pos[s2];
+            for (int c = 0; c < p.n_var; ++c) p.props[(size_t)c * p.cap + i] = p.props[(size_t)c * p.cap + s2];
+            p.age_hyd[i] = p.age_hyd[s2];
+            p.age_div[i] = p.age_div[s2];
           }
+          ++k;
         }
-        __syncthreads();
       }
     }
     grid_barrier(st);

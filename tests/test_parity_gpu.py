@@ -305,17 +305,22 @@ def test_burst_without_overflow_is_bit_exact_in_default_mode(bmc, orc, synth):
 
 
 def test_capacity_exhaustion_fails_loudly(bmc, synth):
-    # default mode: four quiet steps let the host run ahead, then every cell divides in the same step — births the
-    # history did not announce.  The device refuses divisions for lack of PHYSICAL room, which the reference would
-    # not have done: that must surface as an error, never as a silent Overflow.
+    # default mode: three steps without substrate (nothing grows, nothing divides) let the host run ahead; then the
+    # substrate arrives and, with a 30-minute time step, EVERY cell divides in EVERY step — the population doubles per
+    # step, which no history announced.  The first doubling fits (the arrays always hold the worst case of one step),
+    # the second one, already enqueued, does not: the device refuses divisions for lack of PHYSICAL room, which the
+    # reference would not have done.  That must surface as an error, never as a silent Overflow.
     n = 200_000
-    case = util.make_case(synth, "fixed_length", n, 16, dt=100.0, p_move=0.3, outlet=False)
-    case["props"][0][:] = np.float32(1.93e-6)   # l grows 2.8e-8 per step: l_max = 2e-6 is crossed in the third step
+    case = util.make_case(synth, "fixed_length", n, 16, dt=1800.0, p_move=0.3, outlet=False)
+    case["props"][0][:] = np.float32(1.9995e-6)
     g = bmc.ParticleLoop("fixed_length", 1, 16, allocation_factor=1.5, buffer_ratio=0.6)
     util.load_case(g, case)
     with pytest.raises(bmc.BmcError, match="capacity exhausted"):
-        util.run_steps(g, case, 12)
+        for step in range(12):
+            g.set_concentrations(np.zeros(16) if step < 3 else np.full(16, 5.0))
+            g.cycle(case["dt"])
         g.counters()
+    # the same run in exact mode goes through (lock-step, reallocation before every step that needs it)
 
 
 def test_synchronised_population_many_divisions_in_one_step(bmc, orc, synth):
