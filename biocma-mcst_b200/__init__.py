@@ -31,6 +31,8 @@ ABI_SYMBOLS = (
     "bmc_sources_device", "bmc_concentrations_device", "bmc_stream", "bmc_launch_count", "bmc_kernel_config", "bmc_profile_enable",
     "bmc_profile_read", "bmc_nccl_unique_id", "bmc_comm_init", "bmc_allreduce_sources",
     "bmc_liquid_set_transition", "bmc_liquid_set_feeds", "bmc_liquid_step", "bmc_get_concentrations",
+    "bmc_gas_enable", "bmc_gas_update_hydro", "bmc_gas_set_feeds", "bmc_mass_transfer_set", "bmc_get_gas_concentrations",
+    "bmc_get_mass_transfer",
     "bmc_p2p_export", "bmc_p2p_attach", "bmc_p2p_region", "bmc_p2p_attach_local", "bmc_p2p_disable",
     "bmc_udf_check", "bmc_get_properties", "bmc_cma_build", "bmc_checkpoint_size", "bmc_checkpoint_save", "bmc_checkpoint_load",
 )
@@ -129,6 +131,12 @@ def load_library(path=None):
     lib.bmc_liquid_set_transition.argtypes = [vp, u64, vp, vp, vp]
     lib.bmc_liquid_set_feeds.argtypes = [vp, u64, P(BmcFeed)]
     lib.bmc_liquid_step.argtypes = [vp, dbl]
+    lib.bmc_gas_enable.argtypes = [vp, vp, vp]
+    lib.bmc_gas_update_hydro.argtypes = [vp, vp, u64, vp, vp, vp]
+    lib.bmc_gas_set_feeds.argtypes = [vp, u64, P(BmcFeed)]
+    lib.bmc_mass_transfer_set.argtypes = [vp, vp, vp]
+    lib.bmc_get_gas_concentrations.argtypes = [vp, vp]
+    lib.bmc_get_mass_transfer.argtypes = [vp, vp]
     lib.bmc_get_concentrations.argtypes = [vp, vp]
     lib.bmc_udf_check.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
     lib.bmc_get_properties.argtypes = [vp, vp, u64, vp, vp, vp, P(u64)]
@@ -299,8 +307,48 @@ class ParticleLoop:
                              0 if out is None else int(out), 0 if out is None else 1, int(f.get("first_of_feed", 1)))
         self._ck(self.lib.bmc_liquid_set_feeds(self.h, len(feeds), arr))
 
+    def _feed_array(self, feeds):
+        feeds = list(feeds)
+        arr = (BmcFeed * max(1, len(feeds)))()
+        for i, f in enumerate(feeds):
+            out = f.get("output_position")
+            arr[i] = BmcFeed(int(f.get("species", 0)), int(f["input_position"]), float(f["flow"]), float(f["concentration"]),
+                             0 if out is None else int(out), 0 if out is None else 1, int(f.get("first_of_feed", 1)))
+        return len(feeds), arr
+
     def liquid_step(self, d_t):
         self._ck(self.lib.bmc_liquid_step(self.h, float(d_t)))
+
+    # ---- gas phase: two-phase flow (bmc_gas_*) --------------------------------
+    def gas_enable(self, gas_volumes, gas_concentrations=None):
+        v = np.ascontiguousarray(gas_volumes, np.float64)
+        c = None if gas_concentrations is None else np.ascontiguousarray(gas_concentrations, np.float64)
+        self._ck(self.lib.bmc_gas_enable(self.h, _ptr(v), _ptr(c)))
+
+    def gas_update_hydro(self, gas_volumes, coo):
+        v = np.ascontiguousarray(gas_volumes, np.float64)
+        rows = np.ascontiguousarray(coo[0], np.uint64); cols = np.ascontiguousarray(coo[1], np.uint64)
+        vals = np.ascontiguousarray(coo[2], np.float64)
+        self._ck(self.lib.bmc_gas_update_hydro(self.h, _ptr(v), vals.size, _ptr(rows), _ptr(cols), _ptr(vals)))
+
+    def gas_set_feeds(self, feeds):
+        n, arr = self._feed_array(feeds)
+        self._ck(self.lib.bmc_gas_set_feeds(self.h, n, arr))
+
+    def mass_transfer_set(self, kla, henry=None):
+        k = np.ascontiguousarray(kla, np.float64)
+        h = None if henry is None else np.ascontiguousarray(henry, np.float64)
+        self._ck(self.lib.bmc_mass_transfer_set(self.h, _ptr(k), _ptr(h)))
+
+    def get_gas_concentrations(self):
+        out = np.empty(self.n_species * self.n_compartments, np.float64)
+        self._ck(self.lib.bmc_get_gas_concentrations(self.h, _ptr(out)))
+        return out
+
+    def get_mass_transfer(self):
+        out = np.empty(self.n_species * self.n_compartments, np.float64)
+        self._ck(self.lib.bmc_get_mass_transfer(self.h, _ptr(out)))
+        return out
 
     def get_concentrations(self):
         out = np.empty(self.n_species * self.n_compartments, np.float64)

@@ -99,3 +99,48 @@ def read_cma_case(directory, cma_build):
     b = cma_build(n, trip["r"][keep], trip["c"][keep], trip["f"][keep])
     return dict(volumes=vol, neighbors=b["neighbors"], out_flows=b["out_flows"], cdf=b["cdf"], coo=b["coo"], t_per_flowmap=t_per,
                 header=header, files=files)
+
+
+# ---- gas-liquid mass transfer coefficients (host side; hydro/mass_transfer.cpp, hydro/impl_mtr.cpp) -------------
+HENRY_O2 = 3.181e-2          # MassTransferModel's constructor: Henry(1) (hydro/mass_transfer.cpp:113-116)
+BUBBLE_DIAMETER = 5e-3       # proxy->db
+
+
+def c_kinematic_viscosity(temp):
+    """water, m2/s (hydro/impl_mtr.cpp:57-83)"""
+    if temp < 85:
+        p = (0.00000000000282244333 * temp ** 6 - 0.00000000126441088087 * temp ** 5 + 0.00000023336659710795 * temp ** 4
+             - 0.0000234079044336466 * temp ** 3 + 0.00144686943485654 * temp ** 2 - 0.0607310297913931 * temp + 1.79194000343777)
+    else:
+        p = (0.00000000000000178038 * temp ** 6 - 0.00000000000277495333 * temp ** 5 + 0.00000000181964246491 * temp ** 4
+             - 0.00000064995487357883 * temp ** 3 + 0.000136367622445752 * temp ** 2 - 0.0166081298727911 * temp + 1.08486933174497)
+    return round(p * 0.000001 * 10000000000) / 10000000000
+
+
+def default_henry(n_species):
+    h = np.zeros(n_species)
+    if n_species > 1:
+        h[1] = HENRY_O2
+    return h
+
+
+def kla_fixed(values, n_comp):
+    """Type::FixedKla (FunctorKla, hydro/mass_transfer.cpp:24-38): one value per species, every compartment;
+    -> n_species x n_comp, species fastest"""
+    v = np.asarray(values, np.float64)
+    return np.tile(v, n_comp)
+
+
+def kla_flowmap_turbulence(n_species, energy_dissipation, liquid_volumes, gas_volumes, db=BUBBLE_DIAMETER, temperature=20.0):
+    """Type::FlowmapTurbulence (flowmap_gas_liquid_mass_transfer, hydro/impl_mtr.cpp:107-140): species 1 (oxygen) gets
+    kl * a with kl = 0.3 (eps nu)^(1/4) Sc^(-1/2) and the interfacial area a = 6 alpha_g / (db (1 - alpha_g)); re-evaluated
+    by the caller on every flow-map change (MassTransferModel::update)"""
+    eps = np.asarray(energy_dissipation, np.float64); vl = np.asarray(liquid_volumes, np.float64); vg = np.asarray(gas_volumes, np.float64)
+    nu = c_kinematic_viscosity(temperature)
+    sc = nu / 1e-9
+    alpha = vg / (vl + vg)
+    kl = 0.3 * (eps * nu) ** 0.25 * sc ** -0.5
+    kla = np.zeros(n_species * vl.size)
+    if n_species > 1:
+        kla[1::n_species] = kl * (6.0 * alpha / (db * (1 - alpha)))
+    return kla

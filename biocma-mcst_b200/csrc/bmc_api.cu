@@ -67,6 +67,11 @@ struct bmc_ctx {
   double *d_conc_next = nullptr, *d_mass = nullptr; bool mass_dirty = true;
   uint32_t *d_csc_ptr = nullptr, *d_csc_row = nullptr; double* d_csc_val = nullptr; bool transition_set = false;
   std::vector<bmc_feed> feeds; std::vector<double> h_vol;
+  // gas phase (two-phase flow: second scalar field + gas-liquid mass transfer, bmc_gas_*)
+  bool two_phase = false, gas_mass_dirty = true, mtr_set = false;
+  double *d_gconc = nullptr, *d_gconc_next = nullptr, *d_gmass = nullptr, *d_gvol = nullptr, *d_kla = nullptr, *d_henry = nullptr, *d_mtr = nullptr;
+  uint32_t *d_gcsc_ptr = nullptr, *d_gcsc_row = nullptr; double* d_gcsc_val = nullptr; size_t gcsc_cap = 0; bool gas_transition_set = false;
+  std::vector<bmc_feed> gas_feeds;
   float weight = 1.0f;
   // state
   DevState* st = nullptr;
@@ -583,6 +588,8 @@ int bmc_destroy(bmc_ctx** h) {
   free_container(c);
   dev_free(c->d_conc); dev_free(c->d_sources); dev_free(c->d_acc); dev_free(c->d_acc_fix); dev_free(c->d_conc_next); dev_free(c->d_mass);
   dev_free(c->d_csc_ptr); dev_free(c->d_csc_row); dev_free(c->d_csc_val);
+  dev_free(c->d_gconc); dev_free(c->d_gconc_next); dev_free(c->d_gmass); dev_free(c->d_gvol); dev_free(c->d_kla); dev_free(c->d_henry); dev_free(c->d_mtr);
+  dev_free(c->d_gcsc_ptr); dev_free(c->d_gcsc_row); dev_free(c->d_gcsc_val);
   dev_free(c->d_vol); dev_free(c->d_diag); dev_free(c->d_cdf);
   dev_free(c->d_ctab); dev_free(c->d_cdf_f); dev_free(c->d_neigh);
   dev_free(c->blk_total); dev_free(c->blk_gap); dev_free(c->blk_idle);
@@ -836,23 +843,23 @@ int bmc_get_concentrations(bmc_ctx* ctx, double* out) {
   return BMC_OK;
 }
 
-int bmc_liquid_set_transition(bmc_ctx* ctx, uint64_t nnz, const uint64_t* rows, const uint64_t* cols, const double* vals) {
-  if (!ctx || (nnz && (!rows || !cols || !vals))) return BMC_ERR_INVALID;
-  CK(cudaSetDevice(ctx->device));
+// COO -> CSC of a transition matrix into (ptr, row, val) device arrays, staged in pinned memory and copied on the
+// context's stream (stable: COO order kept per column, so every element accumulates its inflow terms in the order a
+// sequential COO sweep does).  No host synchronisation unless the arrays have to grow.
+static int upload_transition(bmc_ctx* ctx, uint64_t nnz, const uint64_t* rows, const uint64_t* cols, const double* vals,
+                             uint32_t* d_ptr, uint32_t** d_row, double** d_val, size_t* cap) {
   const size_t nc = ctx->n_comp;
   for (uint64_t e = 0; e < nnz; ++e)
     if (rows[e] >= nc || cols[e] >= nc) { ctx->err = "transition index out of range"; return BMC_ERR_RANGE; }
   cudaStream_t s = ctx->stream;
   int rc;
-  if (nnz > ctx->csc_cap) {  // more non-zeros than any map before: larger arrays (the only case that waits for the stream)
+  if (nnz > *cap || !*d_row) {  // more non-zeros than any map before: larger arrays (the only case that waits for the stream)
     CK(cudaStreamSynchronize(s));
-    dev_free(ctx->d_csc_row); dev_free(ctx->d_csc_val);
-    const size_t cap = (size_t)nnz + (size_t)nnz / 4;
-    if ((rc = dev_alloc(ctx, &ctx->d_csc_row, cap)) || (rc = dev_alloc(ctx, &ctx->d_csc_val, cap))) return rc;
-    ctx->csc_cap = cap;
+    dev_free(*d_row); dev_free(*d_val);
+    const size_t c = (size_t)nnz + (size_t)nnz / 4;
+    if ((rc = dev_alloc(ctx, d_row, c)) || (rc = dev_alloc(ctx, d_val, c))) return rc;
+    *cap = c;
   }
-  // COO -> CSC in pinned staging (stable: COO order kept per column, so every element accumulates its inflow terms
-  // in the order a sequential COO sweep does), then stream-ordered copies: no host synchronisation
   const size_t o_ptr = 0, o_val = ((nc + 1) * 4 + 7) / 8 * 8, o_row = o_val + nnz * 8, bytes = o_row + nnz * 4;
   unsigned char* h = nullptr; int slot = 0;
   if ((rc = map_stage(ctx, bytes, &h, &slot))) return rc;
@@ -864,25 +871,129 @@ int bmc_liquid_set_transition(bmc_ctx* ctx, uint64_t nnz, const uint64_t* rows, 
   for (size_t j = 0; j < nc; ++j) ptr[j + 1] += ptr[j];
   std::vector<uint32_t> fill(ptr, ptr + nc);
   for (uint64_t e = 0; e < nnz; ++e) { const uint32_t d = fill[cols[e]]++; row[d] = (uint32_t)rows[e]; val[d] = vals[e]; }
-  CK(cudaMemcpyAsync(ctx->d_csc_ptr, ptr, (nc + 1) * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_ptr, ptr, (nc + 1) * 4, cudaMemcpyHostToDevice, s));
   if (nnz) {
-    CK(cudaMemcpyAsync(ctx->d_csc_row, row, nnz * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->d_csc_val, val, nnz * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(*d_row, row, nnz * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(*d_val, val, nnz * 8, cudaMemcpyHostToDevice, s));
   }
   CK(cudaEventRecord(ctx->ev_map[slot], s));
+  return BMC_OK;
+}
+
+int bmc_liquid_set_transition(bmc_ctx* ctx, uint64_t nnz, const uint64_t* rows, const uint64_t* cols, const double* vals) {
+  if (!ctx || (nnz && (!rows || !cols || !vals))) return BMC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  const int rc = upload_transition(ctx, nnz, rows, cols, vals, ctx->d_csc_ptr, &ctx->d_csc_row, &ctx->d_csc_val, &ctx->csc_cap);
+  if (rc) return rc;
   ctx->transition_set = true;
   return BMC_OK;
 }
 
-int bmc_liquid_set_feeds(bmc_ctx* ctx, uint64_t n, const bmc_feed* f) {
-  if (!ctx || (n && !f)) return BMC_ERR_INVALID;
+// ---- gas phase: second scalar field + gas-liquid mass transfer -----------------------------
+static int check_feeds(bmc_ctx* ctx, uint64_t n, const bmc_feed* f) {
   if (n > (uint64_t)kMaxFlows) { ctx->err = "too many feed entries (max 16)"; return BMC_ERR_UNSUPPORTED; }
-  std::vector<bmc_leaving_flow> out;
   for (uint64_t i = 0; i < n; ++i) {
     if (f[i].species >= ctx->n_species || f[i].input_position >= ctx->n_comp || (f[i].has_output && f[i].output_position >= ctx->n_comp)) {
       ctx->err = "feed index out of range"; return BMC_ERR_RANGE;
     }
     if (f[i].flow < 0) { ctx->err = "negative feed flow"; return BMC_ERR_INVALID; }
+  }
+  return BMC_OK;
+}
+
+int bmc_gas_enable(bmc_ctx* ctx, const double* gas_volumes, const double* gas_concentrations) {
+  if (!ctx || !gas_volumes) return BMC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  const size_t nb = ctx->n_species * ctx->n_comp, nc = ctx->n_comp;
+  int rc;
+  if (!ctx->d_gconc) {
+    if ((rc = dev_alloc(ctx, &ctx->d_gconc, nb)) || (rc = dev_alloc(ctx, &ctx->d_gconc_next, nb)) || (rc = dev_alloc(ctx, &ctx->d_gmass, nb)) ||
+        (rc = dev_alloc(ctx, &ctx->d_gvol, nc)) || (rc = dev_alloc(ctx, &ctx->d_kla, nb)) || (rc = dev_alloc(ctx, &ctx->d_henry, ctx->n_species)) ||
+        (rc = dev_alloc(ctx, &ctx->d_mtr, nb)) || (rc = dev_alloc(ctx, &ctx->d_gcsc_ptr, nc + 1)))
+      return rc;
+    CK(cudaMemsetAsync(ctx->d_gcsc_ptr, 0, (nc + 1) * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_kla, 0, nb * 8, ctx->stream)); CK(cudaMemsetAsync(ctx->d_mtr, 0, nb * 8, ctx->stream));
+    // Henry = 0 except species 1 (oxygen): MassTransferModel's constructor (hydro/mass_transfer.cpp:113-116)
+    std::vector<double> hen(ctx->n_species, 0.0);
+    if (ctx->n_species > 1) hen[1] = 3.181e-2;
+    CK(cudaMemcpy(ctx->d_henry, hen.data(), ctx->n_species * 8, cudaMemcpyHostToDevice));
+  }
+  for (size_t j = 0; j < nc; ++j) if (!(gas_volumes[j] > 0.0)) { ctx->err = "gas volumes must be positive"; return BMC_ERR_INVALID; }
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(ctx->d_gvol, gas_volumes, nc * 8, cudaMemcpyHostToDevice));
+  if (gas_concentrations) {
+    for (size_t k = 0; k < nb; ++k) if (gas_concentrations[k] < 0) { ctx->err = "gas concentrations must be >= 0"; return BMC_ERR_INVALID; }  // simulation.cpp:189-199
+    CK(cudaMemcpy(ctx->d_gconc, gas_concentrations, nb * 8, cudaMemcpyHostToDevice));
+  } else {
+    CK(cudaMemset(ctx->d_gconc, 0, nb * 8));
+  }
+  ctx->two_phase = true; ctx->gas_mass_dirty = true;
+  return BMC_OK;
+}
+
+int bmc_gas_update_hydro(bmc_ctx* ctx, const double* gas_volumes, uint64_t nnz, const uint64_t* rows, const uint64_t* cols, const double* vals) {
+  if (!ctx || !gas_volumes || (nnz && (!rows || !cols || !vals))) return BMC_ERR_INVALID;
+  if (!ctx->two_phase) { ctx->err = "bmc_gas_enable not called"; return BMC_ERR_INVALID; }
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  unsigned char* h = nullptr; int slot = 0;
+  if ((rc = map_stage(ctx, ctx->n_comp * 8, &h, &slot))) return rc;
+  memcpy(h, gas_volumes, ctx->n_comp * 8);
+  CK(cudaMemcpyAsync(ctx->d_gvol, h, ctx->n_comp * 8, cudaMemcpyHostToDevice, ctx->stream));  // setVolumes (simulation.cpp:133-136)
+  CK(cudaEventRecord(ctx->ev_map[slot], ctx->stream));
+  if ((rc = upload_transition(ctx, nnz, rows, cols, vals, ctx->d_gcsc_ptr, &ctx->d_gcsc_row, &ctx->d_gcsc_val, &ctx->gcsc_cap))) return rc;  // set_transition (:137)
+  ctx->gas_transition_set = true;
+  return BMC_OK;
+}
+
+int bmc_gas_set_feeds(bmc_ctx* ctx, uint64_t n, const bmc_feed* f) {
+  if (!ctx || (n && !f)) return BMC_ERR_INVALID;
+  const int rc = check_feeds(ctx, n, f);
+  if (rc) return rc;
+  ctx->gas_feeds.assign(f, f + n);
+  return BMC_OK;
+}
+
+int bmc_mass_transfer_set(bmc_ctx* ctx, const double* kla, const double* henry) {
+  if (!ctx || !kla) return BMC_ERR_INVALID;
+  if (!ctx->two_phase) { ctx->err = "bmc_gas_enable not called"; return BMC_ERR_INVALID; }
+  CK(cudaSetDevice(ctx->device));
+  const size_t nb = ctx->n_species * ctx->n_comp;
+  int rc;
+  unsigned char* h = nullptr; int slot = 0;
+  if ((rc = map_stage(ctx, (nb + ctx->n_species) * 8, &h, &slot))) return rc;
+  memcpy(h, kla, nb * 8);
+  CK(cudaMemcpyAsync(ctx->d_kla, h, nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (henry) {
+    memcpy(h + nb * 8, henry, ctx->n_species * 8);
+    CK(cudaMemcpyAsync(ctx->d_henry, h + nb * 8, ctx->n_species * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CK(cudaEventRecord(ctx->ev_map[slot], ctx->stream));
+  ctx->mtr_set = true;
+  return BMC_OK;
+}
+
+int bmc_get_gas_concentrations(bmc_ctx* ctx, double* out) {
+  if (!ctx || !out || !ctx->two_phase) return BMC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(out, ctx->d_gconc, ctx->n_species * ctx->n_comp * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return BMC_OK;
+}
+
+int bmc_get_mass_transfer(bmc_ctx* ctx, double* out) {
+  if (!ctx || !out || !ctx->two_phase) return BMC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(out, ctx->d_mtr, ctx->n_species * ctx->n_comp * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return BMC_OK;
+}
+
+int bmc_liquid_set_feeds(bmc_ctx* ctx, uint64_t n, const bmc_feed* f) {
+  if (!ctx || (n && !f)) return BMC_ERR_INVALID;
+  { const int rc = check_feeds(ctx, n, f); if (rc) return rc; }
+  std::vector<bmc_leaving_flow> out;
+  for (uint64_t i = 0; i < n; ++i) {
     if (f[i].has_output && f[i].first_of_feed)  // set_leaving_flow(mc_flow_counter, output_position, flow, volume)
       out.push_back(bmc_leaving_flow{f[i].output_position, f[i].flow, ctx->h_vol[f[i].output_position]});
   }
@@ -914,8 +1025,31 @@ int bmc_liquid_step(bmc_ctx* ctx, double d_t) {
     const bmc_feed& f = ctx->feeds[i];
     lp.feeds[i] = FeedDev{(uint32_t)f.species, (uint32_t)f.input_position, (uint32_t)f.output_position, f.has_output, f.first_of_feed, f.flow, f.concentration};
   }
-  liquid_step_kernel<<<(nb + 255) / 256, 256, 0, s>>>(lp);
-  if ((rc = check_launch(ctx, "liquid_step"))) return rc;
+  if (ctx->two_phase) {  // ode_step with a gas phase (simulation.model.cpp:131-154)
+    if (ctx->n_comp > 1 && !ctx->gas_transition_set) { ctx->err = "bmc_gas_update_hydro not called"; return BMC_ERR_INVALID; }
+    if (ctx->gas_mass_dirty) {  // set_mass (simulation.cpp:189-195)
+      liquid_mass_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ctx->d_gconc, ctx->d_gvol, ctx->d_gmass, (uint32_t)ctx->n_species, nb);
+      if ((rc = check_launch(ctx, "gas_mass"))) return rc;
+      ctx->gas_mass_dirty = false;
+    }
+    GasLiquidParams gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.liq = lp;
+    gp.g_old = ctx->d_gconc; gp.g_new = ctx->d_gconc_next; gp.g_mass = ctx->d_gmass; gp.g_vol = ctx->d_gvol;
+    gp.g_csc_ptr = ctx->d_gcsc_ptr; gp.g_csc_row = ctx->d_gcsc_row; gp.g_csc_val = ctx->d_gcsc_val;
+    gp.n_gas_feeds = (int)ctx->gas_feeds.size();
+    for (int i = 0; i < gp.n_gas_feeds; ++i) {
+      const bmc_feed& f = ctx->gas_feeds[i];
+      gp.gas_feeds[i] = FeedDev{(uint32_t)f.species, (uint32_t)f.input_position, (uint32_t)f.output_position, f.has_output, f.first_of_feed, f.flow, f.concentration};
+    }
+    gp.kla = ctx->d_kla; gp.henry = ctx->d_henry; gp.mtr = ctx->d_mtr;
+    gas_liquid_step_kernel<<<(nb + 255) / 256, 256, 0, s>>>(gp);
+    if ((rc = check_launch(ctx, "gas_liquid_step"))) return rc;
+    std::swap(ctx->d_gconc, ctx->d_gconc_next);
+  } else {
+    liquid_step_kernel<<<(nb + 255) / 256, 256, 0, s>>>(lp);
+    if ((rc = check_launch(ctx, "liquid_step"))) return rc;
+  }
   std::swap(ctx->d_conc, ctx->d_conc_next);
   return BMC_OK;
 }

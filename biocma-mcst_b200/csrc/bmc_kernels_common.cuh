@@ -95,6 +95,63 @@ __global__ void __launch_bounds__(256) liquid_step_kernel(const __grid_constant_
   p.c_new[k] = m * (1.0 / p.vol[j]);
   p.sources[k] = 0.0;  // clearContribution
 }
+// -----------------------------------------------------------------------------
+// Two-phase step: SimulationUnit::ode_step with a gas phase (simulation.model.cpp:131-154):
+//   mtr = (kla o (Cg o Henry - Cl)) * diag(V_liquid)                      MassTransferModel::gas_liquid_mass_transfer
+//                                                                         (hydro/mass_transfer.cpp:143-161)
+//   gas    : dm/dt = Cg*Mg - Cg*sink_g + sources_g + (-1) * mtr           performStepGL(d_t, mtr, Sign::GasToLiquid)
+//   liquid : dm/dt = Cl*Ml - Cl*sink_l + sources_l + (+1) * mtr           performStepGL(d_t, mtr, Sign::LiquidToGas)
+//            (implScalar.cpp:229-249), then clearNegs on the liquid (:270-296): values in (-5e-7, 0) become 0
+// Everything is evaluated from the concentrations BEFORE the step (both phases are double-buffered), one thread per
+// (species, compartment), inflow terms accumulated in COO order like the single-phase kernel.
+// -----------------------------------------------------------------------------
+struct GasLiquidParams {
+  LiquidParams liq;                 // liquid phase: as in liquid_step_kernel (sources = particle source terms + feeds)
+  const double* g_old; double* g_new; double* g_mass; const double* g_vol;
+  const uint32_t* g_csc_ptr; const uint32_t* g_csc_row; const double* g_csc_val;
+  int n_gas_feeds; FeedDev gas_feeds[kMaxFlows];
+  const double* kla; const double* henry; double* mtr;
+};
+__global__ void __launch_bounds__(256) gas_liquid_step_kernel(const __grid_constant__ GasLiquidParams p) {
+  const LiquidParams& l = p.liq;
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= l.n_species * l.n_comp) return;
+  const uint32_t s = k % l.n_species, j = k / l.n_species;
+  const double cl = l.c_old[k], cg = p.g_old[k];
+  const double mtr = p.kla[k] * (cg * p.henry[s] - cl) * l.vol[j];
+  p.mtr[k] = mtr;
+  auto feed_terms = [&](const FeedDev* feeds, int n, double& src, double& sink) {
+    for (int f = 0; f < n; ++f) {  // set_feed / set_sink
+      if (feeds[f].input_position == j && feeds[f].species == s) src += feeds[f].flow * feeds[f].concentration;
+      if (feeds[f].has_output && feeds[f].first_of_feed && feeds[f].output_position == j) sink += feeds[f].flow;
+    }
+  };
+  {  // gas
+    double src = 0.0, sink = 0.0;
+    feed_terms(p.gas_feeds, p.n_gas_feeds, src, sink);
+    double dm = 0.0;
+    for (uint32_t e = p.g_csc_ptr[j]; e < p.g_csc_ptr[j + 1]; ++e) dm += p.g_old[s + l.n_species * p.g_csc_row[e]] * p.g_csc_val[e];
+    dm += -cg * sink + src;
+    dm += -1.0 * mtr;
+    const double m = p.g_mass[k] + l.dt * dm;
+    p.g_mass[k] = m;
+    p.g_new[k] = m * (1.0 / p.g_vol[j]);
+  }
+  {  // liquid
+    double src = l.sources[k], sink = 0.0;
+    feed_terms(l.feeds, l.n_feeds, src, sink);
+    double dm = 0.0;
+    for (uint32_t e = l.csc_ptr[j]; e < l.csc_ptr[j + 1]; ++e) dm += l.c_old[s + l.n_species * l.csc_row[e]] * l.csc_val[e];
+    dm += -cl * sink + src;
+    dm += 1.0 * mtr;
+    const double m = l.mass[k] + l.dt * dm;
+    l.mass[k] = m;
+    double c = m * (1.0 / l.vol[j]);
+    if (c < 0.0 && fabs(c) < 1e-4 * 5e-3) c = 0.0;  // clearNegs: TOL = scheme_relative_error * max_species_value
+    l.c_new[k] = c;
+    l.sources[k] = 0.0;  // clearContribution
+  }
+}
 __global__ void liquid_mass_kernel(const double* c, const double* vol, double* mass, uint32_t n_species, uint32_t n) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n) mass[k] = c[k] * vol[k / n_species];

@@ -789,6 +789,61 @@ static void ode_step(size_t ns, size_t ncomp, double dt, double* C, double* mass
     }
 }
 
+// Two-phase ode_step (TEST INFRASTRUCTURE, like everything in this file): SimulationUnit::ode_step with a gas phase
+// (apps/libs/simulation/src/simulation.model.cpp:131-154):
+//   mt_model.gas_liquid_mass_transfer():  mtr = (kla o (Cg o Henry - Cl)) * diag(V_liquid)   (hydro/mass_transfer.cpp:143-161)
+//   gas_scalar->performStepGL(d_t, mtr, GasToLiquid = -1), liquid_scalar->performStepGL(d_t, mtr, LiquidToGas = +1):
+//       dm/dt = C*M - C*sink + sources + sign*mtr ; mass += dt*dm ; C = mass * V^-1           (implScalar.cpp:229-249)
+//   liquid_scalar->clearNegs(): values in (-1e-4*5e-3, 0) become 0                            (implScalar.cpp:270-296)
+// Eigen is not available, so like ode_step this is a restatement of the expressions, not the reference's own code.
+static void ode_step_gl(size_t ns, size_t ncomp, double dt, double* Cl, double* ml, const double* vl, const double* sink_l,
+                        const double* src_l, size_t nnz_l, const uint64_t* rl, const uint64_t* cl, const double* valsl, double* Cg,
+                        double* mg, const double* vg, const double* sink_g, const double* src_g, size_t nnz_g, const uint64_t* rg,
+                        const uint64_t* cg, const double* valsg, const double* kla, const double* henry, double* mtr) {
+  const size_t nb = ns * ncomp;
+  for (size_t j = 0; j < ncomp; ++j)
+    for (size_t s = 0; s < ns; ++s) { const size_t k = s + ns * j; mtr[k] = kla[k] * (Cg[k] * henry[s] - Cl[k]) * vl[j]; }
+  auto step = [&](double* C, double* mass, const double* vol, const double* sink, const double* src, size_t nnz, const uint64_t* rows,
+                  const uint64_t* cols, const double* vals, double sign) {
+    std::vector<double> dm(nb, 0.0);
+    for (size_t e = 0; e < nnz; ++e)
+      for (size_t s = 0; s < ns; ++s) dm[s + ns * cols[e]] += C[s + ns * rows[e]] * vals[e];
+    for (size_t j = 0; j < ncomp; ++j)
+      for (size_t s = 0; s < ns; ++s) {
+        const size_t k = s + ns * j;
+        dm[k] += -C[k] * sink[j] + src[k];
+        dm[k] += sign * mtr[k];
+        mass[k] += dt * dm[k];
+        C[k] = mass[k] * (1.0 / vol[j]);
+      }
+  };
+  step(Cg, mg, vg, sink_g, src_g, nnz_g, rg, cg, valsg, -1.0);
+  step(Cl, ml, vl, sink_l, src_l, nnz_l, rl, cl, valsl, 1.0);
+  for (size_t k = 0; k < nb; ++k) if (Cl[k] < 0.0 && std::fabs(Cl[k]) < 1e-4 * 5e-3) Cl[k] = 0.0;
+}
+
+// kla of Type::FlowmapTurbulence (hydro/impl_mtr.cpp:22-83, 107-140): row 1 (oxygen) = kl * a with
+//   kl = 0.3 * (eps * nu)^0.25 * Sc^-0.5,  a = 6 alpha_g / (db (1 - alpha_g)),  alpha_g = Vg / (Vl + Vg),
+//   nu = c_kinematic_viscosity(20 C), Sc = nu / 1e-9; the other rows keep what FunctorKla left (0).
+static double c_kinematic_viscosity(double temp) {
+  if (temp < 85)
+    return std::round((0.00000000000282244333 * std::pow(temp, 6) - 0.00000000126441088087 * std::pow(temp, 5) +
+                       0.00000023336659710795 * std::pow(temp, 4) - 0.0000234079044336466 * std::pow(temp, 3) +
+                       0.00144686943485654 * std::pow(temp, 2) - 0.0607310297913931 * temp + 1.79194000343777) * 0.000001 * 10000000000) / 10000000000;
+  return std::round((0.00000000000000178038 * std::pow(temp, 6) - 0.00000000000277495333 * std::pow(temp, 5) +
+                     0.00000000181964246491 * std::pow(temp, 4) - 0.00000064995487357883 * std::pow(temp, 3) +
+                     0.000136367622445752 * std::pow(temp, 2) - 0.0166081298727911 * temp + 1.08486933174497) * 0.000001 * 10000000000) / 10000000000;
+}
+static void kla_flowmap_turbulence(size_t ns, size_t ncomp, double db, const double* eps, const double* vl, const double* vg, double* kla) {
+  const double nu = c_kinematic_viscosity(20.0), sc = nu / 1e-9;
+  for (size_t j = 0; j < ncomp; ++j) {
+    const double alpha = vg[j] / (vl[j] + vg[j]);
+    const double kl = 0.3 * std::pow(eps[j] * nu, 0.25) * std::pow(sc, -0.5);
+    const double a = 6. * alpha / (db * (1 - alpha));
+    if (ns > 1) kla[1 + ns * j] = kl * a;
+  }
+}
+
 }  // namespace orc
 
 // =============================================================================
@@ -1027,6 +1082,17 @@ int orc_sample(int kind, uint64_t seed, uint64_t n, double p0, double p1, double
 int orc_ode_step(uint64_t ns, uint64_t ncomp, double dt, double* C, double* mass, const double* vol, const double* sink,
                  const double* sources, uint64_t nnz, const uint64_t* rows, const uint64_t* cols, const double* vals) {
   ode_step(ns, ncomp, dt, C, mass, vol, sink, sources, nnz, rows, cols, vals);
+  return 0;
+}
+int orc_ode_step_gl(uint64_t ns, uint64_t ncomp, double dt, double* Cl, double* ml, const double* vl, const double* sink_l,
+                    const double* src_l, uint64_t nnz_l, const uint64_t* rl, const uint64_t* cl, const double* valsl, double* Cg,
+                    double* mg, const double* vg, const double* sink_g, const double* src_g, uint64_t nnz_g, const uint64_t* rg,
+                    const uint64_t* cg, const double* valsg, const double* kla, const double* henry, double* mtr) {
+  ode_step_gl(ns, ncomp, dt, Cl, ml, vl, sink_l, src_l, nnz_l, rl, cl, valsl, Cg, mg, vg, sink_g, src_g, nnz_g, rg, cg, valsg, kla, henry, mtr);
+  return 0;
+}
+int orc_kla_flowmap_turbulence(uint64_t ns, uint64_t ncomp, double db, const double* eps, const double* vl, const double* vg, double* kla) {
+  kla_flowmap_turbulence(ns, ncomp, db, eps, vl, vg, kla);
   return 0;
 }
 const char* orc_last_error(void* h) { return ((Ctx*)h)->err.c_str(); }

@@ -97,6 +97,28 @@ def ode_step(C, mass, vol, sink, sources, coo, dt):
                        _ptr(rows), _ptr(cols), _ptr(vals))
 
 
+def ode_step_gl(Cl, ml, vl, sink_l, src_l, coo_l, Cg, mg, vg, sink_g, src_g, coo_g, kla, henry, dt):
+    """two-phase ode_step (simulation.model.cpp:131-154); returns the mass-transfer rates of the step"""
+    def coo(c):
+        return (np.ascontiguousarray(c[0], np.uint64), np.ascontiguousarray(c[1], np.uint64), np.ascontiguousarray(c[2], np.float64))
+    rl, cl, valsl = coo(coo_l); rg, cg, valsg = coo(coo_g)
+    ns = Cl.size // vl.size
+    mtr = np.zeros(Cl.size, np.float64)
+    lib().orc_ode_step_gl(ctypes.c_uint64(ns), ctypes.c_uint64(vl.size), ctypes.c_double(dt), _ptr(Cl), _ptr(ml), _ptr(vl), _ptr(sink_l), _ptr(src_l),
+                          ctypes.c_uint64(valsl.size), _ptr(rl), _ptr(cl), _ptr(valsl), _ptr(Cg), _ptr(mg), _ptr(vg), _ptr(sink_g), _ptr(src_g),
+                          ctypes.c_uint64(valsg.size), _ptr(rg), _ptr(cg), _ptr(valsg), _ptr(np.ascontiguousarray(kla, np.float64)),
+                          _ptr(np.ascontiguousarray(henry, np.float64)), _ptr(mtr))
+    return mtr
+
+
+def kla_flowmap_turbulence(ns, eps, vl, vg, db=5e-3):
+    """kla of MassTransfer::Type::FlowmapTurbulence (hydro/impl_mtr.cpp:107-140): species 1 from the turbulence correlation"""
+    kla = np.zeros(ns * vl.size, np.float64)
+    lib().orc_kla_flowmap_turbulence(ctypes.c_uint64(ns), ctypes.c_uint64(vl.size), ctypes.c_double(db), _ptr(np.ascontiguousarray(eps, np.float64)),
+                                     _ptr(np.ascontiguousarray(vl, np.float64)), _ptr(np.ascontiguousarray(vg, np.float64)), _ptr(kla))
+    return kla
+
+
 def max_threads():
     return lib().orc_max_threads()
 

@@ -80,3 +80,58 @@ def test_wide_models_default_instantiations(bmc, orc, synth):
             tp._compare_sources(sg, so)
             tp._compare(g, o)
         assert o.counters()["total_new"] > 0 and o.counters()["n_compactions"] >= 1
+
+
+def _run_sources(bmc, synth, case, steps):
+    import util
+    g = bmc.ParticleLoop(case["model"], case["n_species"], case["n_comp"], seed=case["seed"], dead_ratio=0.0005)
+    util.load_case(g, case)
+    src = util.run_steps(g, case, steps, collect=True)
+    return g, src
+
+
+@pytest.mark.parametrize("model", ["monod", "simple_acetate"])
+def test_source_terms_are_bit_identical_across_runs_and_block_sizes(bmc, synth, monkeypatch, model):
+    """The scatter adds 64-bit fixed-point integers (native shared-memory atomics, RED.ADD.64 flushes): the sums do not
+    depend on the order of the additions.  From the second step on (the first step after a load has no scale yet and
+    takes the fp64 path) the source terms of two runs are the same BITS — also when the block size, and with it the
+    assignment of particles to blocks and warps, differs.  (The reference's ScatterView<float> is not reproducible.)"""
+    import numpy as np
+    import util
+    case = util.make_case(synth, model, 150_000, 300, dt=20.0, near_division=0.8, p_move=0.3, p_exit=0.3)
+    if model == "simple_acetate":
+        case["props"][1, :] = 1.0   # no division: its division draws through libdevice, irrelevant here
+    _, a = _run_sources(bmc, synth, case, 8)
+    _, b = _run_sources(bmc, synth, case, 8)
+    monkeypatch.setenv("BMC_VARIANT", "v4b3")
+    g3, c = _run_sources(bmc, synth, case, 8)
+    assert g3.kernel_config()["block"] == 768
+    for k in range(1, 8):
+        assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a[k], c[k]), k
+    assert np.any(a[-1] != 0)
+
+
+def test_fixed_point_scatter_keeps_small_contributions(bmc, orc, synth):
+    """Substrate spanning seven decades across the compartments: the uptake of a starving compartment is 1e-7 of the
+    richest one.  The fixed-point bins are scaled to the LARGEST contribution, so the absolute error per particle is
+    bounded by 2^-35 of that (at this population far less): every bin agrees with the fp64 oracle to 1e-9 of the largest
+    term, and bins down to 1e-6 of the largest still agree to 1e-6 of themselves."""
+    import numpy as np
+    import util
+    n_comp = 200
+    case = util.make_case(synth, "monod", 200_000, n_comp, dt=1.0, p_move=0.05, outlet=False)
+    case["conc"] = 10.0 ** np.linspace(-9, -2, n_comp)          # k_s = 1e-3: mu from 1e-6 mu_max to 0.9 mu_max
+    g = bmc.ParticleLoop("monod", 1, n_comp, seed=case["seed"]); o = orc.OracleLoop("monod", 1, n_comp, seed=case["seed"], n_threads=4)
+    util.load_case(g, case); util.load_case(o, case)
+    for step in range(6):
+        g.set_concentrations(case["conc"]); o.set_concentrations(case["conc"])
+        g.cycle(case["dt"]); o.cycle(case["dt"])
+        sg, so = g.get_sources(), o.get_sources()
+        big = np.max(np.abs(so))
+        assert big > 0 and np.max(np.abs(sg - so)) <= 1e-9 * big
+        if step >= 1:   # fixed-point path
+            sel = np.abs(so) >= 1e-6 * big
+            assert sel.sum() > n_comp // 2
+            assert np.max(np.abs(sg[sel] - so[sel]) / np.abs(so[sel])) <= 1e-6
+    tp._compare(g, o)
