@@ -51,6 +51,24 @@ def test_step_kernel_register_and_stack_budget(model):
             continue   # variant not instantiated for this model
         for k, v in hits.items():
             assert v["reg"] <= max_reg, (k, v)
-            assert v["stack"] <= (16 if wb == 3 else 80) and v["local"] == 0, (k, v)   # a handful of spilled invariants at most
+            # 768 threads: spill-free.  1024 threads x 64 registers: the spills sit in the post-cycle phase (compaction,
+            # commit), executed once per warp and step — the particle-pass loop itself has none (checked below)
+            assert v["stack"] <= (16 if wb == 3 else 128) and v["local"] == 0, (k, v)
             assert v["shared"] <= 14 * 1024, (k, v)                      # static shared memory reserve of configure_launch
     assert any(f"{model}ELi4ELi4ELb1E" in k for k in res), "default variant missing"
+
+
+def test_particle_pass_loop_of_the_headline_kernel_has_no_spills():
+    # SASS of cycle_kernel<Monod, 4, 4, true>: every local-memory access lies behind the last 128-bit particle-column
+    # load of the pass, i.e. in the post-cycle phase
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe) or not os.path.exists(LIB):
+        pytest.skip("cuobjdump or the built library not available")
+    out = subprocess.run([exe, "-sass", "-fun", "_ZN3bmc12cycle_kernelINS_5MonodELi4ELi4ELb1EEEvNS_11CycleParamsE", LIB],
+                         capture_output=True, text=True, timeout=300).stdout
+    lines = [l for l in out.splitlines() if re.match(r"\s+/\*[0-9a-f]{4,5}\*/", l)]
+    assert len(lines) > 2000
+    stores = [i for i, l in enumerate(lines) if "STG.E.128" in l]
+    local = [i for i, l in enumerate(lines) if re.search(r"\b(STL|LDL)\b", l)]
+    # the pass stores its columns with STG.E.128; the first of them marks the body, the last one its end
+    assert stores and (not local or min(local) > max(stores)), (min(local), max(stores))
