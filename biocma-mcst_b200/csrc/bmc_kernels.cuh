@@ -25,13 +25,16 @@ namespace bmc {
 // HURT: with 32 resident warps per SM and more than ~3e7 particles the step becomes 60-90 % slower
 // (1e8 particles, monod: 1620 us with the hints, 855 us without), so plain accesses are the default.
 #ifndef BMC_STREAM_HINTS
-#define BMC_STREAM_HINTS 0
+#define BMC_STREAM_HINTS 0   // tuning builds: 1 = loads, 2 = stores, 3 = both with the cache-streaming policy
 #endif
-#if BMC_STREAM_HINTS
+#if BMC_STREAM_HINTS & 1
 #define BMC_LD(p) __ldcs(p)
-#define BMC_ST(p, v) __stcs(p, v)
 #else
 #define BMC_LD(p) (*(p))
+#endif
+#if BMC_STREAM_HINTS & 2
+#define BMC_ST(p, v) __stcs(p, v)
+#else
 #define BMC_ST(p, v) (*(p) = (v))
 #endif
 
@@ -617,10 +620,12 @@ static __device__ __forceinline__ void post_cycle_body(const PostParams& p) {
   // Newborn of mother i goes to new_n + (number of dividing mothers with a smaller slot index).
   constexpr unsigned kSmallAdd = kMaxGrid;  // records that fit the shared scratch: ranked by direct comparison
   if (n_add && n_add <= kSmallAdd) {  // uniform across the grid; the usual case (a few hundred divisions per step)
-    if ((unsigned long long)blockIdx.x * blockDim.x < n_add) {  // blocks that have a newborn to place
+    // newborns are placed by the LAST blocks of the grid: the first ones are busy publishing the source terms
+    const unsigned rblock = gridDim.x - 1u - blockIdx.x;
+    if ((unsigned long long)rblock * blockDim.x < n_add) {  // blocks that have a newborn to place
       for (unsigned j = threadIdx.x; j < (unsigned)n_add; j += blockDim.x) s_pref[j] = __ldcg(p.buf_mother + j);
       __syncthreads();
-      const unsigned long long j = gtid;
+      const unsigned long long j = (unsigned long long)rblock * blockDim.x + threadIdx.x;
       if (j < n_add) {
         const uint32_t mother = s_pref[j];
         const uint32_t npos = __ldcg(p.buf_pos + j);
