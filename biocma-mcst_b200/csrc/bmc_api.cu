@@ -78,6 +78,9 @@ struct bmc_ctx {
   DevState* h_st = nullptr;     // pinned landing buffer of sync_state
   // capacity policy (ensure_room): zero-copy mirror written by the commit thread of every step
   PinState* h_pin = nullptr; PinState* d_pin = nullptr;
+  // zero-copy mirror of the published sources ({value, tag} records): bmc_get_sources reads it without a CUDA call
+  unsigned long long* h_src_mirror = nullptr; unsigned long long* d_src_mirror = nullptr;
+  uint64_t src_mirror_tag = 0;  // tag of the cycle whose sources are (or will be) in the mirror; 0 = mirror not current
   uint64_t host_step = 0;       // cycles enqueued since the particles were (re)loaded
   uint64_t recent_max_add = 0;  // decaying maximum of the newborns per step seen in the mirror
   uint64_t pin_seen_step = ~0ull, pin_history = 0;  // last mirrored step looked at, number of distinct ones since the (re)load
@@ -303,6 +306,7 @@ static int finish_pending_sum(bmc_ctx* ctx) {
   PeerExchange x;
   fill_peer_exchange(ctx, x, 0, ctx->p2p_pending);
   ctx->p2p_pending = 0; ctx->p2p_published = 0;  // d_sources now holds the global sum
+  ctx->src_mirror_tag = 0;                         // ... which the host mirror of the last cycle does not
   p2p_exchange_kernel<<<1, 1024, 0, ctx->stream>>>(x, ctx->d_sources, (uint32_t)(ctx->n_species * ctx->n_comp), ctx->st);
   return check_launch(ctx, "p2p_exchange");
 }
@@ -545,6 +549,12 @@ int bmc_create(bmc_ctx** out, const bmc_config* cfg) {
   if (!ck(cudaHostAlloc((void**)&ctx->h_pin, sizeof(PinState), cudaHostAllocMapped), "cudaHostAlloc")) return fail(BMC_ERR_NOMEM);
   memset(ctx->h_pin, 0, sizeof(PinState));
   if (!ck(cudaHostGetDevicePointer((void**)&ctx->d_pin, ctx->h_pin, 0), "cudaHostGetDevicePointer")) return fail(BMC_ERR_CUDA);
+  {
+    const size_t nbm = (size_t)cfg->n_species * (size_t)cfg->n_compartments;
+    if (!ck(cudaHostAlloc((void**)&ctx->h_src_mirror, nbm * 16, cudaHostAllocMapped), "cudaHostAlloc")) return fail(BMC_ERR_NOMEM);
+    memset(ctx->h_src_mirror, 0, nbm * 16);
+    if (!ck(cudaHostGetDevicePointer((void**)&ctx->d_src_mirror, ctx->h_src_mirror, 0), "cudaHostGetDevicePointer")) return fail(BMC_ERR_CUDA);
+  }
   if (const char* e = getenv("BMC_CAPACITY_MODE")) ctx->exact_capacity = std::string(e) == "exact";
   const size_t nb = ctx->n_species * ctx->n_comp;
   int rc;
@@ -598,6 +608,7 @@ int bmc_destroy(bmc_ctx** h) {
   if (c->d_stage) cudaFree(c->d_stage);
   if (c->h_st) cudaFreeHost(c->h_st);
   if (c->h_pin) cudaFreeHost(c->h_pin);
+  if (c->h_src_mirror) cudaFreeHost(c->h_src_mirror);
   for (int i = 0; i < bmc_ctx::kPinRing; ++i) { if (c->h_pin_in[i]) cudaFreeHost(c->h_pin_in[i]); if (c->ev_pin_in[i]) cudaEventDestroy(c->ev_pin_in[i]); }
   if (c->h_pin_out) cudaFreeHost(c->h_pin_out);
   for (int i = 0; i < bmc_ctx::kMapRing; ++i) { if (c->h_map[i]) cudaFreeHost(c->h_map[i]); if (c->ev_map[i]) cudaEventDestroy(c->ev_map[i]); }
@@ -1011,6 +1022,7 @@ int bmc_liquid_step(bmc_ctx* ctx, double d_t) {
   int rc;
   if ((rc = finish_pending_sum(ctx))) return rc;
   ctx->p2p_published = 0;  // the sources are consumed (cleared) by this step
+  ctx->src_mirror_tag = 0;
   if (ctx->mass_dirty) {
     liquid_mass_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ctx->d_conc, ctx->d_vol, ctx->d_mass, (uint32_t)ctx->n_species, nb);
     if ((rc = check_launch(ctx, "liquid_mass"))) return rc;
@@ -1058,6 +1070,29 @@ int bmc_get_sources(bmc_ctx* ctx, double* out) {
   if (!ctx || !out) return BMC_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
   const size_t bytes = ctx->n_species * ctx->n_comp * 8;
+  if (ctx->src_mirror_tag && !ctx->p2p_pending) {
+    // The last thing that wrote the sources was a cycle, whose publish phase also stored every value, tagged, into
+    // pinned host memory: wait for the tags (no CUDA call, no copy, no stream synchronisation) and read them.
+    const size_t nb = ctx->n_species * ctx->n_comp;
+    const volatile unsigned long long* m = ctx->h_src_mirror;
+    const unsigned long long tag = ctx->src_mirror_tag;
+    unsigned spins = 0;
+    bool ok = true;
+    for (size_t k = 0; k < nb && ok; ++k) {
+      while (m[2 * k + 1] != tag) {
+        if ((++spins & 0xfffu) == 0u) {  // a fault on the device must not hang the host
+          const cudaError_t q = cudaStreamQuery(ctx->stream);
+          if (q == cudaSuccess) { if (m[2 * k + 1] != tag) ok = false; break; }
+          if (q != cudaErrorNotReady) { ctx->err = std::string("cudaStreamQuery: ") + cudaGetErrorString(q); return BMC_ERR_CUDA; }
+        }
+      }
+    }
+    if (ok) {
+      std::atomic_thread_fence(std::memory_order_acquire);
+      for (size_t k = 0; k < nb; ++k) { const unsigned long long v = m[2 * k]; memcpy(out + k, &v, 8); }
+      return BMC_OK;
+    }
+  }
   { int rc = finish_pending_sum(ctx); if (rc) return rc; }
   CK(cudaMemcpyAsync(ctx->h_pin_out, ctx->d_sources, bytes, cudaMemcpyDeviceToHost, ctx->stream));  // pinned: one DMA, no staging
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1127,6 +1162,9 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   p.post.newborn_stamp_hyd = ctx->lazy_ages ? (uint32_t)(ctx->hyd_clock + (enable_leave ? 1u : 0u)) : 0u;
   p.post.tab_idx_div = (uint32_t)ctx->host_step; p.post.tab_idx_hyd = (uint32_t)ctx->hyd_clock;
   p.post.tab_extend = ctx->lazy_ages ? 1 : 0; p.post.enable_leave = enable_leave ? 1 : 0; p.post.dt_f = (float)d_t; p.post.dt = d_t;
+  // tags are unique per context life (launch counter), never 0
+  ctx->src_mirror_tag = ctx->launches + 1;
+  p.post.src_mirror = ctx->d_src_mirror; p.post.src_tag = ctx->src_mirror_tag;
   if (ctx->p2p_on) {  // this step publishes its sources to the peers and finishes the previous all-reduce, if one is pending
     // (peers that are contexts on the SAME device — the test harness — cannot be waited for from inside a kernel that
     // fills the device: their all-reduce is finished by the small kernel instead)
@@ -1363,7 +1401,7 @@ int bmc_checkpoint_load(bmc_ctx* ctx, const void* buffer, uint64_t bytes) {
   const uint64_t nb = ctx->n_species * ctx->n_comp;
   CK(cudaMemcpyAsync(ctx->d_conc, in, nb * 8, cudaMemcpyHostToDevice, s)); in += nb * 8;
   CK(cudaMemcpyAsync(ctx->d_sources, in, nb * 8, cudaMemcpyHostToDevice, s)); in += nb * 8;
-  ctx->mass_dirty = true;
+  ctx->mass_dirty = true; ctx->src_mirror_tag = 0; ctx->p2p_pending = 0; ctx->p2p_published = 0;
   for (int k = 0; k < ctx->vt.n_var; ++k) { CK(cudaMemcpyAsync(ctx->props + (size_t)k * ctx->cap, in, n * 4, cudaMemcpyHostToDevice, s)); in += n * 4; }
   CK(cudaMemcpyAsync(ctx->pos, in, n * 4, cudaMemcpyHostToDevice, s)); in += n * 4;
   CK(cudaMemcpyAsync(ctx->status, in, n, cudaMemcpyHostToDevice, s)); in += n;
@@ -1605,6 +1643,7 @@ int bmc_allreduce_sources(bmc_ctx* ctx) {
   }
   if (!ctx->nccl_comm) { ctx->err = "bmc_comm_init / bmc_p2p_attach not called"; return BMC_ERR_INVALID; }
   CK(cudaSetDevice(ctx->device));
+  ctx->src_mirror_tag = 0;
   // ncclFloat64 = 8, ncclSum = 0
   const int r = g_nccl.AllReduce(ctx->d_sources, ctx->d_sources, ctx->n_species * ctx->n_comp, 8, 0, ctx->nccl_comm, ctx->stream);
   if (r != 0) { ctx->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return BMC_ERR_NCCL; }

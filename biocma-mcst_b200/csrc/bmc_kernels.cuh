@@ -208,6 +208,9 @@ struct PostParams {
   double allocation_factor, buffer_ratio, shrink_ratio;  // RuntimeParameters of _resize / __allocate_buffer__ / remove_inactive_particles
   PinState* pin;                                         // device pointer of the pinned host mirror
   PeerExchange px;                                       // multi-GPU: publish this step's sources to the peers (commit block)
+  // host mirror of the published sources (pinned, device-mapped): n_bins records {value bits, tag}, each written with ONE
+  // 16-byte store, so the host needs neither a copy nor a fence to read them — it waits until every tag is this step's
+  unsigned long long* src_mirror; unsigned long long src_tag;
   int count_step;  // 1 when called from a cycle, 0 from force_remove_dead
   // step-stamped ages (bmc_kernels.cuh): stamp given to newborns (0 = eager float ages, bits of 0.f)
   // and the per-step extension of the age tables A_div / A_hyd
@@ -493,6 +496,8 @@ static __device__ __forceinline__ void post_cycle_body(const PostParams& p) {
       }
       p.sources[k] = s;
       p.acc[k] = 0.0;
+      if (p.src_mirror)
+        asm volatile("st.volatile.v2.u64 [%0], {%1, %2};" ::"l"(p.src_mirror + 2 * k), "l"((unsigned long long)__double_as_longlong(s)), "l"(p.src_tag) : "memory");
     }
   }
   BMC_STAMP(st, 5);
