@@ -1020,7 +1020,11 @@ int bmc_liquid_step(bmc_ctx* ctx, double d_t) {
   cudaStream_t s = ctx->stream;
   const uint32_t nb = (uint32_t)(ctx->n_species * ctx->n_comp);
   int rc;
-  if ((rc = finish_pending_sum(ctx))) return rc;
+  // a pending all-reduce of the sources is finished INSIDE the liquid kernel (every element sums what the ranks
+  // published): cycle -> allreduce -> liquid step costs no extra launch.  (Contexts sharing one device use the small kernel.)
+  const unsigned long long consume = (ctx->p2p_pending && ctx->p2p_ipc) ? ctx->p2p_pending : 0ull;
+  if (consume) ctx->p2p_pending = 0;
+  else if ((rc = finish_pending_sum(ctx))) return rc;
   ctx->p2p_published = 0;  // the sources are consumed (cleared) by this step
   ctx->src_mirror_tag = 0;
   if (ctx->mass_dirty) {
@@ -1033,6 +1037,7 @@ int bmc_liquid_step(bmc_ctx* ctx, double d_t) {
   lp.c_old = ctx->d_conc; lp.c_new = ctx->d_conc_next; lp.mass = ctx->d_mass; lp.vol = ctx->d_vol; lp.sources = ctx->d_sources;
   lp.csc_ptr = ctx->d_csc_ptr; lp.csc_row = ctx->d_csc_row; lp.csc_val = ctx->d_csc_val;
   lp.n_species = (uint32_t)ctx->n_species; lp.n_comp = (uint32_t)ctx->n_comp; lp.dt = d_t; lp.n_feeds = (int)ctx->feeds.size();
+  fill_peer_exchange(ctx, lp.px, 0, consume);
   for (int i = 0; i < lp.n_feeds; ++i) {
     const bmc_feed& f = ctx->feeds[i];
     lp.feeds[i] = FeedDev{(uint32_t)f.species, (uint32_t)f.input_position, (uint32_t)f.output_position, f.has_output, f.first_of_feed, f.flow, f.concentration};
@@ -1055,11 +1060,11 @@ int bmc_liquid_step(bmc_ctx* ctx, double d_t) {
       gp.gas_feeds[i] = FeedDev{(uint32_t)f.species, (uint32_t)f.input_position, (uint32_t)f.output_position, f.has_output, f.first_of_feed, f.flow, f.concentration};
     }
     gp.kla = ctx->d_kla; gp.henry = ctx->d_henry; gp.mtr = ctx->d_mtr;
-    gas_liquid_step_kernel<<<(nb + 255) / 256, 256, 0, s>>>(gp);
+    gas_liquid_step_kernel<<<(nb + 255) / 256, 256, 0, s>>>(gp, &ctx->st->error);
     if ((rc = check_launch(ctx, "gas_liquid_step"))) return rc;
     std::swap(ctx->d_gconc, ctx->d_gconc_next);
   } else {
-    liquid_step_kernel<<<(nb + 255) / 256, 256, 0, s>>>(lp);
+    liquid_step_kernel<<<(nb + 255) / 256, 256, 0, s>>>(lp, &ctx->st->error);
     if ((rc = check_launch(ctx, "liquid_step"))) return rc;
   }
   std::swap(ctx->d_conc, ctx->d_conc_next);

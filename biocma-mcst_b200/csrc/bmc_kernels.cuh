@@ -172,6 +172,13 @@ __device__ __forceinline__ void p2p_publish(const PeerExchange& x, const double*
   // release: the block barrier orders every thread's stores before thread 0's system-scope fence (cumulative)
   if (threadIdx.x == 0) { __threadfence_system(); *p2p_flag(x.base[x.rank]) = x.publish_epoch; }
 }
+// The two-buffer argument holds when every rank finishes the all-reduce of every epoch it publishes (the SPMD loop
+// cycle -> bmc_allreduce_sources).  A rank that skips some lets a peer run two epochs ahead and overwrite the buffer
+// being read: detected here (the peer's flag has reached consume_epoch + 2) and reported like a missing peer.
+__device__ __forceinline__ void p2p_check_not_overrun(const PeerExchange& x, unsigned int* error) {
+  __syncthreads();
+  if ((int)threadIdx.x < x.world && (int)threadIdx.x != x.rank && *p2p_flag(x.base[threadIdx.x]) >= x.consume_epoch + 2ull) atomicOr(error, 4u);
+}
 // executed by one whole block
 __device__ __forceinline__ void p2p_consume(const PeerExchange& x, double* sources, uint32_t n, unsigned int* error) {
   if ((int)threadIdx.x < x.world && (int)threadIdx.x != x.rank) {
@@ -189,6 +196,7 @@ __device__ __forceinline__ void p2p_consume(const PeerExchange& x, double* sourc
     for (int r = 0; r < x.world; ++r) a += *reinterpret_cast<volatile double*>(p2p_buf(x.base[r], n, par) + k);
     sources[k] = a;
   }
+  p2p_check_not_overrun(x, error);
 }
 
 struct PostParams {

@@ -76,12 +76,37 @@ struct LiquidParams {
   const double* c_old; double* c_new; double* mass; const double* vol; double* sources;
   const uint32_t* csc_ptr; const uint32_t* csc_row; const double* csc_val;
   uint32_t n_species, n_comp; double dt; int n_feeds; FeedDev feeds[kMaxFlows];
+  PeerExchange px;  // multi-GPU: a pending all-reduce of the sources is finished HERE (consume_epoch != 0): every element
+                    // is the sum over the ranks of the peers' published buffers, in rank order
 };
-__global__ void __launch_bounds__(256) liquid_step_kernel(const __grid_constant__ LiquidParams p) {
+// source term of element k: the local vector, or — when the all-reduce of the last cycle is still pending — the sum of
+// what every rank published (bmc_kernels.cuh: PeerExchange).  Called by EVERY thread of the block (it contains a barrier).
+__device__ __forceinline__ double liquid_source(const LiquidParams& p, uint32_t k, bool active, unsigned int* error) {
+  if (p.px.world > 1 && p.px.consume_epoch) {
+    if ((int)threadIdx.x < p.px.world && (int)threadIdx.x != p.px.rank) {
+      volatile unsigned long long* f = p2p_flag(p.px.base[threadIdx.x]);
+      const long long t0 = clock64();
+      while (*f < p.px.consume_epoch) {
+        if (clock64() - t0 > p.px.spin_limit) { atomicOr(error, 4u); break; }
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+    const unsigned par = (unsigned)(p.px.consume_epoch & 1ull);
+    double a = 0.0;
+    if (active)
+      for (int r = 0; r < p.px.world; ++r) a += *reinterpret_cast<volatile double*>(p2p_buf(p.px.base[r], p.n_species * p.n_comp, par) + k);
+    p2p_check_not_overrun(p.px, error);
+    return a;
+  }
+  return active ? p.sources[k] : 0.0;
+}
+__global__ void __launch_bounds__(256) liquid_step_kernel(const __grid_constant__ LiquidParams p, unsigned int* error) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= p.n_species * p.n_comp) return;
+  const bool active = k < p.n_species * p.n_comp;
+  double src = liquid_source(p, k, active, error), sink = 0.0;
+  if (!active) return;
   const uint32_t s = k % p.n_species, j = k / p.n_species;
-  double src = p.sources[k], sink = 0.0;
   for (int f = 0; f < p.n_feeds; ++f) {  // set_feed / set_sink
     if (p.feeds[f].input_position == j && p.feeds[f].species == s) src += p.feeds[f].flow * p.feeds[f].concentration;
     if (p.feeds[f].has_output && p.feeds[f].first_of_feed && p.feeds[f].output_position == j) sink += p.feeds[f].flow;
@@ -112,10 +137,12 @@ struct GasLiquidParams {
   int n_gas_feeds; FeedDev gas_feeds[kMaxFlows];
   const double* kla; const double* henry; double* mtr;
 };
-__global__ void __launch_bounds__(256) gas_liquid_step_kernel(const __grid_constant__ GasLiquidParams p) {
+__global__ void __launch_bounds__(256) gas_liquid_step_kernel(const __grid_constant__ GasLiquidParams p, unsigned int* error) {
   const LiquidParams& l = p.liq;
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= l.n_species * l.n_comp) return;
+  const bool active = k < l.n_species * l.n_comp;
+  const double src_particles = liquid_source(l, k, active, error);
+  if (!active) return;
   const uint32_t s = k % l.n_species, j = k / l.n_species;
   const double cl = l.c_old[k], cg = p.g_old[k];
   const double mtr = p.kla[k] * (cg * p.henry[s] - cl) * l.vol[j];
@@ -138,7 +165,7 @@ __global__ void __launch_bounds__(256) gas_liquid_step_kernel(const __grid_const
     p.g_new[k] = m * (1.0 / p.g_vol[j]);
   }
   {  // liquid
-    double src = l.sources[k], sink = 0.0;
+    double src = src_particles, sink = 0.0;
     feed_terms(l.feeds, l.n_feeds, src, sink);
     double dm = 0.0;
     for (uint32_t e = l.csc_ptr[j]; e < l.csc_ptr[j + 1]; ++e) dm += l.c_old[s + l.n_species * l.csc_row[e]] * l.csc_val[e];
