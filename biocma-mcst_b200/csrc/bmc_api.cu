@@ -89,7 +89,7 @@ struct bmc_ctx {
   // launch config
   int n_sm = 148, grid_cycle = 148, blocks_per_sm = 1; size_t smem_bins = 0; int bins_in_smem = 0;
   uint64_t launches = 0;
-  size_t queue_offset = 0, smem_total = 0; int ctab_in_smem = 0; size_t ctab_offset = 0; int grid_post = 148;
+  size_t queue_offset = 0, smem_total = 0, stage_offset = 0, stage_warp_bytes = 0; int ctab_in_smem = 0; size_t ctab_offset = 0; int grid_post = 148;
   int grid_cycle_eager = 148; size_t smem_eager = 0;
   bool fuse_post = true;  // whole step in one cooperative launch (BMC_FUSE_POST=0: particle pass + post_only_kernel)
   // staging
@@ -259,6 +259,18 @@ static int configure_launch(bmc_ctx* ctx) {
   ctx->queue_offset = (ctx->ctab_offset + (ctx->ctab_in_smem ? ctab_bytes : 0) + 127) / 128 * 128;
   ctx->smem_total = ctx->queue_offset + queue_bytes;
   if (ctx->smem_total > smem_budget) { ctx->err = "shared memory budget exceeded"; return BMC_ERR_UNSUPPORTED; }
+  // prefetch staging (VEC == 4): one buffer per warp holding the columns of ONE group — pos, the read properties, both
+  // ages (eager kernel) and the status bytes — when it fits beside bins, table and queues (BMC_PREFETCH=0 turns it off)
+  ctx->stage_offset = 0; ctx->stage_warp_bytes = 0;
+  {
+    const char* e = getenv("BMC_PREFETCH");
+    const size_t warp_bytes = (size_t)(1 + ctx->vt.n_read + 2) * 128 * (size_t)ctx->vt.vec + 128;
+    const size_t stage_off = (ctx->smem_total + 127) / 128 * 128;
+    const size_t total = stage_off + warp_bytes * (size_t)(std::max(ctx->vt.block, ctx->vt.block_eager) / 32);
+    if (ctx->vt.vec == 4 && !(e && atoi(e) == 0) && total + static_reserve <= smem_budget) {
+      ctx->stage_offset = stage_off; ctx->stage_warp_bytes = warp_bytes; ctx->smem_total = total;
+    }
+  }
   ctx->smem_eager = ctx->smem_total;
   ctx->grid_post = ctx->n_sm;           // cooperative launch: one block per SM is always co-resident
   if (const char* e = getenv("BMC_FUSE_POST")) ctx->fuse_post = atoi(e) != 0;
@@ -284,9 +296,9 @@ static int configure_launch(bmc_ctx* ctx) {
   if (getenv("BMC_VERBOSE")) {
     cudaFuncAttributes fa{};
     cudaFuncGetAttributes(&fa, ctx->vt.cycle_fn);
-    fprintf(stderr, "[bmc] step kernel: grid %d (%d blocks/SM x %d SMs) x %d threads, %d regs, smem static %zu + dynamic %zu B (bins %zu, table %s, queues %zu), eager grid %d\n",
+    fprintf(stderr, "[bmc] step kernel: grid %d (%d blocks/SM x %d SMs) x %d threads, %d regs, smem static %zu + dynamic %zu B (bins %zu, table %s, queues %zu, prefetch staging %zu per warp), eager grid %d\n",
             ctx->grid_cycle, ctx->blocks_per_sm, ctx->n_sm, ctx->vt.block, fa.numRegs, fa.sharedSizeBytes, ctx->smem_total, ctx->smem_bins,
-            ctx->ctab_in_smem ? "smem" : "global", queue_bytes, ctx->grid_cycle_eager);
+            ctx->ctab_in_smem ? "smem" : "global", queue_bytes, ctx->stage_warp_bytes, ctx->grid_cycle_eager);
   }
   return BMC_OK;
 }
@@ -1154,6 +1166,7 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   p.step = (uint32_t)ctx->host_step; p.rank = ctx->rank; p.seed_lo = (uint32_t)ctx->seed; p.seed_hi = (uint32_t)(ctx->seed >> 32);
   p.enable_move = enable_move; p.enable_leave = enable_leave; p.bins_in_smem = ctx->bins_in_smem;
   p.queue_offset = (uint32_t)ctx->queue_offset;
+  p.stage_offset = (uint32_t)ctx->stage_offset; p.stage_warp_bytes = (uint32_t)ctx->stage_warp_bytes;
   // Philox constants of this step's three draw blocks, folded on the host (bmc_rng.cuh)
   p.ph0 = philox_pre(p.step, 0u, p.rank, p.seed_lo, p.seed_hi);  // u1: leaves its compartment
   p.ph1 = philox_pre(p.step, 1u, p.rank, p.seed_lo, p.seed_hi);  // u3: outlet test

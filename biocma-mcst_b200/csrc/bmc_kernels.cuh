@@ -256,6 +256,8 @@ struct CycleParams {
   PhiloxPre ph0, ph1, ph2;  // host-folded Philox constants of draw blocks 0 (u1), 1 (u3), 2 (u2) for this step (bmc_rng.cuh)
   int enable_move, enable_leave, bins_in_smem;
   uint32_t queue_offset;  // byte offset of the per-warp deferred queues inside dynamic shared memory
+  // prefetch staging (VEC == 4 only): byte offset of the per-warp staging buffers and their size (0 = no prefetch)
+  uint32_t stage_offset, stage_warp_bytes;
   PostParams post;   // second phase of the step (post_cycle_body)
   int fuse_post;     // 1 = run it in this launch behind a grid barrier (cooperative launch), 0 = post_only_kernel follows
 };
@@ -824,6 +826,16 @@ template <class M> struct ReadCols {
 // entries of a warp's deferred queue: one group can add 32*VEC candidates to at most 31 waiting ones
 __host__ __device__ constexpr uint32_t queue_entries(int vec) { return 32u * (uint32_t)vec + 32u; }
 
+// Ampere-style asynchronous copies (LDGSTS): global -> shared without a register in between, completion per thread
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <int VEC> struct MaskIO;
 template <> struct MaskIO<4> { static __device__ __forceinline__ void st(uint32_t* p, const unsigned (&w)[4]) { *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]); } };
 template <> struct MaskIO<2> { static __device__ __forceinline__ void st(uint32_t* p, const unsigned (&w)[2]) { *reinterpret_cast<uint2*>(p) = make_uint2(w[0], w[1]); } };
@@ -864,6 +876,15 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
   unsigned int* const s_bins = reinterpret_cast<unsigned int*>(s_dyn);  // bin k = words (2k: low, 2k+1: high)
   uint32_t* const s_ctab = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(s_dyn) + p.ctab_offset);
   uint32_t* const s_queue = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(s_dyn) + p.queue_offset) + warp * queue_entries(VEC);
+  // Prefetch (VEC == 4): while a warp computes group n, the columns of its group n+1 are already on their way into a
+  // warp-private staging buffer (cp.async: no registers are held by loads in flight, which is what lets a 64-register
+  // kernel keep two groups per warp in flight).  Every lane copies exactly the bytes it will read back itself, so the
+  // only synchronisation is the lane's own cp.async.wait_group.  A compute-free kernel with this access pattern needs
+  // ~48 KB of loads in flight per SM to saturate HBM (tools/dbg/streams_bw_occ.cu); without the prefetch the warps of
+  // an SM spend only part of their time waiting for loads and fall short of that.
+  const bool pf = VEC == 4 && p.stage_warp_bytes != 0u;
+  unsigned char* const s_stage = reinterpret_cast<unsigned char*>(s_dyn) + p.stage_offset + (size_t)warp * p.stage_warp_bytes + lane * 16u;
+  constexpr int kColBytes = 32 * 4 * VEC;  // one staged column of a group
 
   BMC_STAMP(p.st, 0);
 #if defined(BMC_TIMELINE)
@@ -975,31 +996,75 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
 
   // Every group but the last is entirely below n_used: the body is instantiated twice so that the
   // common case carries no per-slot range checks (FULL), the ragged tail keeps them.
-  auto body = [&](auto full_tag, const uint32_t g) {
+  // issue the asynchronous copies of group g's columns into this warp's staging buffer (order: pos, [ages], read props, status)
+  auto stage_issue = [&](const uint32_t g) {
+    const uint32_t i_raw = g * kGroup + lane * VEC;
+    const uint32_t i0 = i_raw < n_used ? i_raw : 0u;  // dead lanes of the ragged last group shadow slot 0
+    unsigned char* dst = s_stage;
+    cp_async16(dst, p.pos + i0); dst += kColBytes;
+    if constexpr (!LAZY) {
+      cp_async16(dst, p.age_div + i0); dst += kColBytes;
+      if (p.enable_leave) { cp_async16(dst, p.age_hyd + i0); dst += kColBytes; }
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+      if (!col_flag(M::write_only_mask, k)) { cp_async16(dst, p.props + (size_t)k * p.cap + i0); dst += kColBytes; }
+    cp_async4(dst - lane * 12u, p.status + i0);  // status: 4 bytes per lane, packed behind the columns
+    cp_async_commit();
+  };
+
+  // `mid` runs once per group after the model update has consumed every loaded value: it resolves the warp's next
+  // group and (with the prefetch) starts its copies, which then overlap the rest of this group
+  auto body = [&](auto full_tag, const uint32_t g, auto&& mid) {
     constexpr bool FULL = decltype(full_tag)::value;
     const uint32_t i_raw = g * kGroup + lane * VEC;
     const bool live = FULL || i_raw < n_used;    // false only in the ragged end of the last group
     const uint32_t i0 = live ? i_raw : 0u;       // dead lanes shadow slot 0 (loads stay in range, nothing is stored)
 
-    // ---- front-batched global loads (all independent) ----
     uint32_t pos[VEC]; float adiv[VEC], ahyd[VEC]; float v[VEC][NV], old[VEC][NV];
-    const uint32_t stw = VecIO<VEC>::ldb(p.status + i0);
-    VecIO<VEC>::ldu(p.pos + i0, pos);
-    if constexpr (!LAZY) {
-      VecIO<VEC>::ldf(p.age_div + i0, adiv);
-      if (p.enable_leave) VecIO<VEC>::ldf(p.age_hyd + i0, ahyd);
-    }
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      float col[VEC];
-      if (col_flag(M::write_only_mask, k)) {
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) col[q] = 0.f;
-      } else {
-        VecIO<VEC>::ldf(p.props + (size_t)k * p.cap + i0, col);
+    uint32_t stw;
+    if (pf) {
+      // ---- the columns were staged by this lane's own asynchronous copies, issued one group ago ----
+      cp_async_wait_all();
+      const unsigned char* src = s_stage;
+      VecIO<VEC>::ldu_plain(reinterpret_cast<const uint32_t*>(src), pos); src += kColBytes;
+      if constexpr (!LAZY) {
+        VecIO<VEC>::ldf_plain(reinterpret_cast<const float*>(src), adiv); src += kColBytes;
+        if (p.enable_leave) { VecIO<VEC>::ldf_plain(reinterpret_cast<const float*>(src), ahyd); src += kColBytes; }
       }
 #pragma unroll
-      for (int q = 0; q < VEC; ++q) { v[q][k] = col[q]; old[q][k] = col[q]; }
+      for (int k = 0; k < NV; ++k) {
+        float col[VEC];
+        if (col_flag(M::write_only_mask, k)) {
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) col[q] = 0.f;
+        } else {
+          VecIO<VEC>::ldf_plain(reinterpret_cast<const float*>(src), col); src += kColBytes;
+        }
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) { v[q][k] = col[q]; old[q][k] = col[q]; }
+      }
+      stw = *reinterpret_cast<const uint32_t*>(src - lane * 12u);
+    } else {
+      // ---- front-batched global loads (all independent) ----
+      stw = VecIO<VEC>::ldb(p.status + i0);
+      VecIO<VEC>::ldu(p.pos + i0, pos);
+      if constexpr (!LAZY) {
+        VecIO<VEC>::ldf(p.age_div + i0, adiv);
+        if (p.enable_leave) VecIO<VEC>::ldf(p.age_hyd + i0, ahyd);
+      }
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        float col[VEC];
+        if (col_flag(M::write_only_mask, k)) {
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) col[q] = 0.f;
+        } else {
+          VecIO<VEC>::ldf(p.props + (size_t)k * p.cap + i0, col);
+        }
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) { v[q][k] = col[q]; old[q][k] = col[q]; }
+      }
     }
     if (LAZY || !p.enable_leave) {
 #pragma unroll
@@ -1074,6 +1139,7 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
       const Status s = M::update(gen, p.dt_f, i0 + q, RegRow{v[q]}, RegRow{contrib[q]}, (size_t)pos[q], conc);
       div_nib |= (unsigned)(idle[q] && s == Division) << q;
     }
+    mid();  // every loaded value has been consumed: the staging buffer is free for the next group
 
     // ---- contribution scatter at the PRE-move position (Q15) -----------------
     if (single_comp) {
@@ -1227,10 +1293,11 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
     volatile unsigned* const v_left = s_chunk_left;
     volatile unsigned* const v_base = s_chunk_base;
     uint32_t s = blockIdx.x * kWarps + warp;  // first group: the warp's own index
+    if (pf && s < n_groups) stage_issue(s);
 #pragma unroll 1
     while (s < n_groups) {
       unsigned t = 0;
-      if (lane == 0) {  // draw the ticket of the NEXT group now, resolve it after this group
+      if (lane == 0) {  // draw the ticket of the NEXT group now, resolve it in the middle of this group
         t = atomicAdd(&s_ticket, 1u);
         const unsigned c = t / kWarps, o = t - c * kWarps, slot = c % kRing;
         if (o == 0u) {
@@ -1242,16 +1309,21 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
           v_seq[slot] = c + 1u;
         }
       }
-      if ((unsigned long long)(s + 1u) * kGroup <= n_used) body(FullTile{}, s);
-      else body(RaggedTile{}, s);
-      if (lane == 0) {
-        const unsigned c = t / kWarps, o = t - c * kWarps, slot = c % kRing;
-        while (v_seq[slot] != c + 1u) { }
-        __threadfence_block();
-        s = v_base[slot] + o;
-        atomicSub(&s_chunk_left[slot], 1u);
-      }
-      s = __shfl_sync(kFull, s, 0);
+      uint32_t s_next = 0;
+      auto mid = [&]() {
+        if (lane == 0) {
+          const unsigned c = t / kWarps, o = t - c * kWarps, slot = c % kRing;
+          while (v_seq[slot] != c + 1u) { }
+          __threadfence_block();
+          s_next = v_base[slot] + o;
+          atomicSub(&s_chunk_left[slot], 1u);
+        }
+        s_next = __shfl_sync(kFull, s_next, 0);
+        if (pf && s_next < n_groups) stage_issue(s_next);
+      };
+      if ((unsigned long long)(s + 1u) * kGroup <= n_used) body(FullTile{}, s, mid);
+      else body(RaggedTile{}, s, mid);
+      s = s_next;
     }
     __syncwarp();
     if (lane < qn) deferred(s_queue[lane]);  // what is left in the queue (< 32 entries)

@@ -11,6 +11,7 @@ struct ModelVT {
   int n_var, n_c, vec, minb;
   int block, block_eager;  // threads per block of cycle_fn / cycle_eager_fn (one block per SM)
   int ct;              // 32-bit words per compartment-table row
+  int n_read;          // property columns the pass loads (n_var minus the write-only ones): sizes the prefetch staging
   // kernel handles: addresses of __global__ instantiations, or cudaKernel_t of a JIT-compiled
   // user model; all launched with cudaLaunchKernel(handle, grid, block, {&params}, smem, stream)
   const void* cycle_fn;   // (CycleParams)  block = 256*minb threads, one block per SM; step-stamped ages (bmc_kernels.cuh)
@@ -27,7 +28,7 @@ template <class M, int VEC, int MINB, int MINB_E> static ModelVT make_vt() {
   ModelVT v;
   v.n_var = M::n_var; v.n_c = M::n_c; v.vec = VEC; v.minb = MINB;
   v.block = kBlock * MINB; v.block_eager = kBlock * MINB_E;
-  v.ct = 1 + M::n_pre;
+  v.ct = 1 + M::n_pre; v.n_read = ReadCols<M>::value;
   v.cycle_fn = (const void*)cycle_kernel<M, VEC, MINB, true>;
   v.cycle_eager_fn = (const void*)cycle_kernel<M, VEC, MINB_E, false>;
   v.pre_fn = (const void*)pre_step_kernel<M>;
