@@ -1139,7 +1139,7 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
       const Status s = M::update(gen, p.dt_f, i0 + q, RegRow{v[q]}, RegRow{contrib[q]}, (size_t)pos[q], conc);
       div_nib |= (unsigned)(idle[q] && s == Division) << q;
     }
-    mid();  // every loaded value has been consumed: the staging buffer is free for the next group
+    if constexpr (VEC == 4) mid();  // every loaded value has been consumed: the staging buffer is free for the next group
 
     // ---- contribution scatter at the PRE-move position (Q15) -----------------
     if (single_comp) {
@@ -1309,21 +1309,43 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
           v_seq[slot] = c + 1u;
         }
       }
-      uint32_t s_next = 0;
-      auto mid = [&]() {
+      if constexpr (VEC == 4) {
+        uint32_t s_next = 0;
+        auto resolve = [&]() {
+          if (lane == 0) {
+            const unsigned c = t / kWarps, o = t - c * kWarps, slot = c % kRing;
+            while (v_seq[slot] != c + 1u) { }
+            __threadfence_block();
+            s_next = v_base[slot] + o;
+            atomicSub(&s_chunk_left[slot], 1u);
+          }
+          s_next = __shfl_sync(kFull, s_next, 0);
+        };
+        // with the prefetch the next group must be known in the middle of this one (its copies overlap the rest of the
+        // body); without it the ticket is resolved at the end, when the shared-memory atomic has long returned
+        auto mid = [&]() {
+          if (pf) {
+            resolve();
+            if (s_next < n_groups) stage_issue(s_next);
+          }
+        };
+        if ((unsigned long long)(s + 1u) * kGroup <= n_used) body(FullTile{}, s, mid);
+        else body(RaggedTile{}, s, mid);
+        if (!pf) resolve();
+        s = s_next;
+      } else {
+        auto nothing = []() {};
+        if ((unsigned long long)(s + 1u) * kGroup <= n_used) body(FullTile{}, s, nothing);
+        else body(RaggedTile{}, s, nothing);
         if (lane == 0) {
           const unsigned c = t / kWarps, o = t - c * kWarps, slot = c % kRing;
           while (v_seq[slot] != c + 1u) { }
           __threadfence_block();
-          s_next = v_base[slot] + o;
+          s = v_base[slot] + o;
           atomicSub(&s_chunk_left[slot], 1u);
         }
-        s_next = __shfl_sync(kFull, s_next, 0);
-        if (pf && s_next < n_groups) stage_issue(s_next);
-      };
-      if ((unsigned long long)(s + 1u) * kGroup <= n_used) body(FullTile{}, s, mid);
-      else body(RaggedTile{}, s, mid);
-      s = s_next;
+        s = __shfl_sync(kFull, s, 0);
+      }
     }
     __syncwarp();
     if (lane < qn) deferred(s_queue[lane]);  // what is left in the queue (< 32 entries)
