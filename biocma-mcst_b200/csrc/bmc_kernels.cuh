@@ -718,8 +718,39 @@ static __device__ __forceinline__ void post_cycle_body(const PostParams& p) {
     }
   }
   BMC_STAMP(st, 7);
-  // commit: the last block to get here (every other block is done reading the counters and has published its bins)
+  // commit: the last block to get here (every other block is done reading the counters and has published its bins).
+  // Everything the commit needs is stable since the grid barrier, so EVERY block fetches it and does the arithmetic
+  // before it takes its ticket (redundantly, but off the critical path): the commit itself is then a handful of
+  // stores, not a chain of dependent L2 round trips at the very end of the step.
   __shared__ unsigned s_last;
+  __shared__ float s_fb[8], s_fs[8];
+  const unsigned long long n = new_n + n_add;
+  unsigned long long pre_waiting = 0, pre_total_out = 0, pre_ncompact = 0, pre_total_new = 0, pre_step = 0, la = 0, lb = 0;
+  unsigned pre_error = 0;
+  float pre_tab_div = 0.f, pre_tab_hyd = 0.f;
+  if (threadIdx.x == 0) {
+    pre_waiting = __ldcg(&st->step_waiting); pre_total_out = __ldcg(&st->total_out); pre_ncompact = __ldcg(&st->n_compactions);
+    pre_total_new = __ldcg(&st->total_new); pre_step = __ldcg(&st->step); la = __ldcg(&st->logical_alloc); lb = __ldcg(&st->logical_buf);
+    pre_error = __ldcg(&st->error);
+    if (p.tab_extend) { pre_tab_div = __ldcg(p.tab_div + p.tab_idx_div); if (p.enable_leave) pre_tab_hyd = __ldcg(p.tab_hyd + p.tab_idx_hyd); }
+  }
+  if (threadIdx.x < 8 && p.count_step) {
+    // Fixed-point scatter of the particle pass: next step's admission bound and scale per species from this step's
+    // largest |contribution| m, with m < 2^e_m and n <= 2^e_n particles:
+    //   bound = 2^(e_m + 2)   a contribution may grow 4x from one step to the next before it takes the fp64 path
+    //   scale = 2^(62 - e_n - e_m - 2)   so that n contributions at the bound stay below 2^62
+    const int j = (int)threadIdx.x;
+    const int e_n = n > 1ull ? 64 - __clzll((long long)(n - 1ull)) : 0;
+    const float m = __uint_as_float(__ldcg(&st->src_max[j]));
+    float bound = 0.0f, scale = 1.0f;  // nothing seen: only exact zeros are admitted (they add nothing)
+    if (j < p.n_c && m > 0.0f && m < 3.0e38f) {
+      int e_m;
+      (void)frexpf(m, &e_m);  // m = f * 2^e_m, 0.5 <= f < 1
+      const int kexp = 62 - e_n - e_m - 2;
+      if (kexp >= -120 && kexp <= 120 && e_m + 2 <= 120 && e_m >= -120) { bound = ldexpf(1.0f, e_m + 2); scale = ldexpf(1.0f, kexp); }
+    }
+    s_fb[j] = bound; s_fs[j] = scale;
+  }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(&st->done_blocks, 1u) == gridDim.x - 1) ? 1u : 0u;
@@ -727,23 +758,23 @@ static __device__ __forceinline__ void post_cycle_body(const PostParams& p) {
   if (!s_last) return;
   __threadfence();
   if (p.count_step && p.px.world > 1 && p.px.publish_epoch) p2p_publish(p.px, p.sources, p.n_bins);  // whole block
+  if (threadIdx.x < 8 && p.count_step) { st->src_max[threadIdx.x] = 0u; st->src_bound[threadIdx.x] = s_fb[threadIdx.x]; st->src_scale[threadIdx.x] = s_fs[threadIdx.x]; }
   if (threadIdx.x == 0) {
     st->done_blocks = 0; st->next_group = 0;
-    if (p.count_step) { st->last_out = out; st->last_dead = 0; st->last_waiting = st->step_waiting; }  // a forced compaction is not a step
-    st->total_out += out;
+    if (p.count_step) { st->last_out = out; st->last_dead = 0; st->last_waiting = pre_waiting; }  // a forced compaction is not a step
+    st->total_out = pre_total_out + out;
     st->step_exit = 0; st->step_waiting = 0; st->buf_index = 0; st->force_compact = 0;
     st->inactive = do_compact ? 0ull : inactive;
-    if (do_compact) st->n_compactions += 1;
+    if (do_compact) st->n_compactions = pre_ncompact + 1ull;
     st->do_compact = do_compact ? 1u : 0u; st->cmp_old_n = old_n; st->cmp_new_n = new_n; st->n_add = n_add;  // for inspection
-    const unsigned long long n = new_n + n_add;
     st->n_used = n;
-    st->total_new += n_add;
-    st->step += (unsigned long long)p.count_step;
+    st->total_new = pre_total_new + n_add;
+    const unsigned long long step_now = pre_step + (unsigned long long)p.count_step;
+    st->step = step_now;
     // the reference's extents after this post_cycle: shrink after a compaction (remove_inactive_particles,
     // particles_container.hpp:784-797), _resize + __allocate_buffer__ in merge_buffer (:575-599, returns early
     // without newborns)
-    unsigned long long la = st->logical_alloc, lb = st->logical_buf;
-    if (s_plan[3] > s_plan[4] && s_plan[4] < lb) atomicOr(&st->error, kErrCapacity);  // divisions refused by the PHYSICAL room
+    if (s_plan[3] > s_plan[4] && s_plan[4] < lb) { atomicOr(&st->error, kErrCapacity); pre_error |= kErrCapacity; }  // divisions refused by the PHYSICAL room
     if (do_compact && new_n != 0ull && new_n <= (unsigned long long)(p.shrink_ratio * (double)la)) {
       const unsigned long long ns = (unsigned long long)((double)new_n * p.allocation_factor);
       if (ns > 0ull) la = (unsigned long long)ceil((double)ns * p.allocation_factor);  // _resize(n_used * factor, force)
@@ -755,30 +786,10 @@ static __device__ __forceinline__ void post_cycle_body(const PostParams& p) {
     const unsigned long long room = p.cap > n ? p.cap - n : 0ull;
     unsigned long long eff = lb < p.buf_cap ? lb : p.buf_cap;
     st->buf_cap_eff = eff < room ? eff : room;
-    // host mirror (zero-copy), as early as the values exist: the stores travel while the rest of the commit runs
-    if (p.pin) pin_write(p.pin, st->step, n, n_add, la, lb, *reinterpret_cast<volatile unsigned*>(&st->error));
-    if (p.count_step) {
-      // Fixed-point scatter of the particle pass: next step's admission bound and scale per species from this step's
-      // largest |contribution| m, with m < 2^e_m and n <= 2^e_n particles:
-      //   bound = 2^(e_m + 2)   a contribution may grow 4x from one step to the next before it takes the fp64 path
-      //   scale = 2^(62 - e_n - e_m - 2)   so that n contributions at the bound stay below 2^62
-      const int e_n = n > 1ull ? 64 - __clzll((long long)(n - 1ull)) : 0;
-      for (int j = 0; j < 8; ++j) {
-        const float m = __uint_as_float(st->src_max[j]);
-        st->src_max[j] = 0u;
-        float bound = 0.0f, scale = 1.0f;  // nothing seen: only exact zeros are admitted (they add nothing)
-        if (j < p.n_c && m > 0.0f && m < 3.0e38f) {
-          int e_m;
-          (void)frexpf(m, &e_m);  // m = f * 2^e_m, 0.5 <= f < 1
-          const int kexp = 62 - e_n - e_m - 2;
-          if (kexp >= -120 && kexp <= 120 && e_m + 2 <= 120 && e_m >= -120) { bound = ldexpf(1.0f, e_m + 2); scale = ldexpf(1.0f, kexp); }
-        }
-        st->src_bound[j] = bound; st->src_scale[j] = scale;
-      }
-    }
+    if (p.pin) pin_write(p.pin, step_now, n, n_add, la, lb, pre_error);  // host mirror (zero-copy)
     if (p.tab_extend) {  // A[k+1] = fl(A[k] + d_t): exactly the accumulation an eagerly updated age goes through
-      p.tab_div[p.tab_idx_div + 1] = p.tab_div[p.tab_idx_div] + p.dt_f;                                  // model_kernel.hpp:191 (float d_t)
-      if (p.enable_leave) p.tab_hyd[p.tab_idx_hyd + 1] = (float)((double)p.tab_hyd[p.tab_idx_hyd] + p.dt);  // move_kernel.hpp:596 (double d_t)
+      p.tab_div[p.tab_idx_div + 1] = pre_tab_div + p.dt_f;                                  // model_kernel.hpp:191 (float d_t)
+      if (p.enable_leave) p.tab_hyd[p.tab_idx_hyd + 1] = (float)((double)pre_tab_hyd + p.dt);  // move_kernel.hpp:596 (double d_t)
     }
   }
 }
