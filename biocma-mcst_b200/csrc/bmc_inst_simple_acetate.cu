@@ -2,5 +2,5 @@
 #include "bmc_model_vt.cuh"
 
 namespace bmc {
-bool pick_simple_acetate(const std::string& var, ModelVT& vt) { return pick_variant<SimpleAcetate, 4, 4, 3>(var, vt); }
+bool pick_simple_acetate(const std::string& var, ModelVT& vt) { return pick_variant<SimpleAcetate, 4, 3, 4>(var, vt); }
 }  // namespace bmc

@@ -857,6 +857,15 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
   constexpr int NV = M::n_var, NC = M::n_c, CT = 1 + M::n_pre;
   constexpr uint32_t kGroup = 32 * VEC;         // slots per group: the work unit of one warp
   constexpr unsigned kFull = 0xffffffffu;
+  // Rows of 8 words (two doubles among the model terms, simple_acetate): in shared memory the table is kept PLANAR
+  // (word k of compartment c at [k * n_comp + c]) — 32 lanes gathering the same word of 32 random compartments then
+  // spread over all 32 banks.  (Measured at 1.25e8 particles: 32-byte rows fetched with two 128-bit gathers, which put
+  // every lane on one of four bank groups, 2.25 ms per step; two planes of 16-byte half rows 2.02; word planes 1.94.)
+  // The model terms are fetched right before the particle's update, so that the terms of the VEC particles of a thread
+  // are not all live at once.  The global-memory form of the table (n_comp too large for shared memory) stays
+  // row-major: one row = one sector.
+  constexpr bool kPlanar = (CT == 8);
+  auto planar_word = [&](uint32_t c, int k) -> uint32_t { return (uint32_t)k * p.n_comp + c; };
   // dynamic shared memory: [n_species * n_comp] 64-bit source bins when bins_in_smem, the compartment table when
   // ctab_in_smem, one deferred queue per warp
   extern __shared__ __align__(128) unsigned long long s_dyn[];
@@ -884,7 +893,10 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
   const uint32_t n_bins = p.n_species * p.n_comp;
   const bool single_comp = (p.n_comp == 1);
   const bool smem_bins = p.bins_in_smem && !single_comp;
-  unsigned int* const s_bins = reinterpret_cast<unsigned int*>(s_dyn);  // bin k = words (2k: low, 2k+1: high)
+  // bin k = low word s_bins[k], high word s_bins[n_bins + k]: the low words, which take (nearly) all the atomics, are
+  // contiguous, so that the 32 lanes of a warp spread over all 32 banks (interleaved low/high words used 16 of them)
+  unsigned int* const s_bins = reinterpret_cast<unsigned int*>(s_dyn);
+  unsigned int* const s_bins_hi = s_bins + n_bins;
   uint32_t* const s_ctab = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(s_dyn) + p.ctab_offset);
   uint32_t* const s_queue = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(s_dyn) + p.queue_offset) + warp * queue_entries(VEC);
   // Prefetch (VEC == 4): while a warp computes group n, the columns of its group n+1 are already on their way into a
@@ -916,7 +928,7 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
       float row[CT];
       compartment_row<M>(p.diag, p.vol, p.dt, p.conc, p.n_species, p.enable_move, p.outlets, p.n_flows, c, row);
 #pragma unroll
-      for (int k = 0; k < CT; ++k) s_ctab[c * CT + k] = __float_as_uint(row[k]);
+      for (int k = 0; k < CT; ++k) s_ctab[kPlanar ? planar_word(c, k) : c * CT + k] = __float_as_uint(row[k]);
     }
   }
   // Scatter (c): fixed-point accumulation.  sm_100a has a native shared-memory atomic for 32-bit integers only
@@ -954,7 +966,7 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
   (void)stamps_hyd; (void)stamps_div;
 
   auto ctab_word0 = [&](uint32_t c) -> uint32_t {
-    return p.ctab_in_smem ? s_ctab[c * CT] : __ldg(reinterpret_cast<const uint32_t*>(p.ctab) + (size_t)c * CT);
+    return p.ctab_in_smem ? s_ctab[kPlanar ? c : c * CT] : __ldg(reinterpret_cast<const uint32_t*>(p.ctab) + (size_t)c * CT);
   };
 
   // ---- move + leave of one queued slot (one per lane) ------------------------------------------------
@@ -1097,12 +1109,14 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
     constexpr unsigned kAll = (1u << VEC) - 1u;
 
     // ---- compartment rows: leave threshold / outlet flag + model terms, one gather per particle
+    constexpr bool kLateTerms = kPlanar;  // only word 0 is fetched here
     uint32_t cw0[VEC]; float cterm[VEC][CT];  // cterm[q][1..] = compartment_terms (index 0 unused)
 #pragma unroll
     for (int q = 0; q < VEC; ++q) {
       if (p.ctab_in_smem) {
         const uint32_t* row = s_ctab + pos[q] * CT;
         if constexpr (CT == 2) { const uint2 t = *reinterpret_cast<const uint2*>(row); cw0[q] = t.x; cterm[q][1] = __uint_as_float(t.y); }
+        else if constexpr (kLateTerms) cw0[q] = s_ctab[pos[q]];
         else {
           cw0[q] = row[0];
 #pragma unroll
@@ -1114,7 +1128,8 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
         else if constexpr (CT == 4) {
           const uint4 t = __ldg(reinterpret_cast<const uint4*>(row));
           cw0[q] = t.x; cterm[q][1] = __uint_as_float(t.y); cterm[q][2] = __uint_as_float(t.z); cterm[q][3] = __uint_as_float(t.w);
-        } else {
+        } else if constexpr (kLateTerms) cw0[q] = __ldg(row);
+        else {
           cw0[q] = __ldg(row);
 #pragma unroll
           for (int k = 1; k < CT; ++k) cterm[q][k] = __uint_as_float(__ldg(row + k));
@@ -1146,6 +1161,18 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
     for (int q = 0; q < VEC; ++q) {
       if constexpr (!LAZY) adiv[q] = idle[q] ? adiv[q] + p.dt_f : adiv[q];  // ages(i,1) += _d_t  (model_kernel.hpp:191)
       Gen gen(p.seed_lo, p.seed_hi, p.rank, (uint32_t)(i0 + q), p.step, 2u);
+      if constexpr (kLateTerms) {
+        if (p.ctab_in_smem) {
+#pragma unroll
+          for (int k = 1; k < CT - 1; ++k) cterm[q][k] = __uint_as_float(s_ctab[planar_word(pos[q], k)]);  // word 7 is padding
+          cterm[q][CT - 1] = 0.f;
+        } else {
+          const uint4* row = reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(p.ctab) + (size_t)pos[q] * CT);
+          const uint4 t = __ldg(row), u = __ldg(row + 1);
+          cterm[q][1] = __uint_as_float(t.y); cterm[q][2] = __uint_as_float(t.z); cterm[q][3] = __uint_as_float(t.w);
+          cterm[q][4] = __uint_as_float(u.x); cterm[q][5] = __uint_as_float(u.y); cterm[q][6] = __uint_as_float(u.z); cterm[q][7] = __uint_as_float(u.w);
+        }
+      }
       const ConcView conc{p.conc, p.n_species, &cterm[q][1]};
       const Status s = M::update(gen, p.dt_f, i0 + q, RegRow{v[q]}, RegRow{contrib[q]}, (size_t)pos[q], conc);
       div_nib |= (unsigned)(idle[q] && s == Division) << q;
@@ -1171,9 +1198,9 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
           if (adm) {
             const long long fix = __float2ll_rn(c * fx_scale[j]);
             const uint32_t lo = (uint32_t)fix, hi = (uint32_t)((unsigned long long)fix >> 32);
-            unsigned int* bin = s_bins + 2u * ((uint32_t)j + p.n_species * pos[q]);
-            const uint32_t was = atomicAdd(bin, lo);
-            atomicAdd(bin + 1, hi + (uint32_t)((uint32_t)(was + lo) < lo));
+            const uint32_t b = (uint32_t)j + p.n_species * pos[q];
+            const uint32_t was = atomicAdd(s_bins + b, lo);
+            atomicAdd(s_bins_hi + b, hi + (uint32_t)((uint32_t)(was + lo) < lo));
           }
           slow |= (unsigned)(idle[q] && !adm) << q;
         }
@@ -1401,7 +1428,7 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
     const uint32_t rot = (uint32_t)(((unsigned long long)blockIdx.x * n_bins) / gridDim.x);
     for (uint32_t k0 = threadIdx.x; k0 < n_bins; k0 += BLOCK) {
       uint32_t k = k0 + rot; if (k >= n_bins) k -= n_bins;
-      const unsigned long long a = s_dyn[k];
+      const unsigned long long a = (unsigned long long)s_bins[k] | ((unsigned long long)s_bins_hi[k] << 32);
       if (a != 0ull) atomicAdd(p.acc_fix + k, a);
     }
   }

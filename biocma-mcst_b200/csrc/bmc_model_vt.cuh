@@ -44,7 +44,7 @@ template <class M, int VEC, int MINB, int MINB_E> static ModelVT make_vt() {
 //   DEF = 4: 1024 threads x <= 64 registers (eager ages: 768 x <= 80), ALT = 3: 768 x <= 80
 template <class M, int VEC, int DEF, int ALT = DEF> static bool pick_variant(const std::string& var, ModelVT& vt) {
   constexpr int DEF_E = DEF > 3 ? 3 : DEF, ALT_E = ALT > 3 ? 3 : ALT;
-  if (ALT != DEF && var.size() == 4 && var[0] == 'v' && var[2] == 'b' && var[1] - '0' == VEC && var[3] - '0' == ALT) {
+  if (ALT != DEF && (var == "alt" || (var.size() == 4 && var[0] == 'v' && var[2] == 'b' && var[1] - '0' == VEC && var[3] - '0' == ALT))) {
     vt = make_vt<M, VEC, ALT, ALT_E>();
     return true;
   }

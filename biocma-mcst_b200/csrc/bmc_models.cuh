@@ -55,6 +55,11 @@ struct ConcView {
     return __ldg(base + s + (size_t)n_species * pos);
   }
   __device__ __forceinline__ float term(int k) const { return pre[k]; }
+  // a double stored by compartment_terms in words k (low) and k + 1 (high) with put_term_d
+  __device__ __forceinline__ double term_d(int k) const { return __hiloint2double(__float_as_int(pre[k + 1]), __float_as_int(pre[k])); }
+  __device__ static __forceinline__ void put_term_d(float* out, int k, double v) {
+    out[k] = __int_as_float(__double2loint(v)); out[k + 1] = __int_as_float(__double2hiint(v));
+  }
 };
 // Config view of configurable models (fixed_length.hpp:25): config(idx)
 struct ConfigView {
@@ -212,7 +217,9 @@ struct Monod {
 // simple_acetate — apps/libs/models/public/models/simple_acetate.hpp:26-248
 // =============================================================================
 struct SimpleAcetate {
-  static constexpr int n_var = 9, n_c = 2, n_pre = 0;
+  // compartment terms: 1/(c0 + k_s), 1/(c1 + k_a) as floats, c0 and c1 as doubles (two words each), one word of
+  // padding: a row of the compartment table is 8 words, fetched with two 128-bit gathers
+  static constexpr int n_var = 9, n_c = 2, n_pre = 7;
   enum particle_var { length = 0, l_max, a_p, a_max, a_e, a_e_s, a_e_a, phi_s, phi_a };
   // a_e is read by division AFTER update wrote it in the same cycle -> still write-only for loading
   static constexpr uint64_t write_only_mask = (1u << a_e) | (1u << a_e_s) | (1u << a_e_a) | (1u << phi_s) | (1u << phi_a);
@@ -248,10 +255,12 @@ struct SimpleAcetate {
   __device__ static Status update(Gen&, float d_t, size_t idx, const A& arr, const C& arr_contribs,
                                   size_t position_index, const Conc& c) {  // :154-204
     const float adm0 = arr(idx, a_max), adm1 = arr(idx, a_max) / 3;
-    const double c0 = c(0, position_index), c1 = c(1, position_index);
-    float inv = (float)(1. / (c0 + k_s));
+    // c0, c1 and the two reciprocals depend on the compartment only (two fp64 divisions and two 8-byte gathers per
+    // particle otherwise): hoisted to compartment_terms, same expressions, same bits
+    const double c0 = c.term_d(2), c1 = c.term_d(4);
+    float inv = c.term(0);  // (float)(1. / (c0 + k_s))
     const float D0 = (float)(adm0 * c0 * inv);
-    inv = (float)(1. / (c1 + k_a));
+    inv = c.term(1);        // (float)(1. / (c1 + k_a))
     const float D1 = (float)(adm1 * c1 * inv);
     arr(idx, a_e) = 0.0f;
     const float U0 = fminf(D0, arr(idx, a_p));
@@ -270,6 +279,14 @@ struct SimpleAcetate {
     arr_contribs(idx, 0) = ps;
     arr_contribs(idx, 1) = pA;
     return check_div(arr(idx, length), arr(idx, l_max));
+  }
+  template <class Conc> __device__ static void compartment_terms(const Conc& c, size_t position_index, float* out) {  // :160-166
+    const double c0 = c(0, position_index), c1 = c(1, position_index);
+    out[0] = (float)(1. / (c0 + k_s));
+    out[1] = (float)(1. / (c1 + k_a));
+    Conc::put_term_d(out, 2, c0);
+    Conc::put_term_d(out, 4, c1);
+    out[6] = 0.0f;
   }
   template <class A, class B>
   __device__ static void division(Gen& g, size_t idx, size_t idx2, const A& arr, const B& buffer_arr) {  // :206-246

@@ -1,6 +1,6 @@
 """Every instantiation of the step kernel that the library ships is run through the parity cases.
 
-Each model has its default block size and at most one alternative, selected by BMC_VARIANT (read at bmc_create);
+Each model has its default block size and at most one alternative, selected by BMC_VARIANT=alt (read at bmc_create);
 the eager-age kernel of a variant is a third instantiation (exercised by the cases with caller-supplied ages or a
 changing time step).  `kernel_config()` proves which instantiation ran."""
 import pytest
@@ -12,7 +12,7 @@ import test_reference_sources as tr
 pytestmark = pytest.mark.gpu
 
 # model -> (default block, alternative variant, its block): bmc_inst_*.cu
-ALT = {"fixed_length": (1024, "v4b3", 768), "monod": (1024, "v4b3", 768), "simple_acetate": (1024, "v4b3", 768)}
+ALT = {"fixed_length": (1024, "v4b3", 768), "monod": (1024, "v4b3", 768), "simple_acetate": (768, "v4b4", 1024)}
 
 
 @pytest.mark.parametrize("model", sorted(ALT))
@@ -22,46 +22,47 @@ def test_variant_selection(bmc, monkeypatch, model):
     monkeypatch.setenv("BMC_VARIANT", ALT[model][1])
     k = bmc.ParticleLoop(model, ns, 8).kernel_config()
     assert k["block"] == ALT[model][2] and k["vec"] == 4
-    assert bmc.ParticleLoop("wide_udf", 4, 8, n_var_udf=8).kernel_config()["block"] == 768
+    # the 8-property wide model ships 1024 (default) and 768 ("v4b3") threads
+    assert bmc.ParticleLoop("wide_udf", 4, 8, n_var_udf=8).kernel_config()["block"] == (768 if ALT[model][1] == "v4b3" else 1024)
     monkeypatch.setenv("BMC_VARIANT", "v9b9")   # unknown: ignored
     assert bmc.ParticleLoop(model, ns, 8).kernel_config()["block"] == ALT[model][0]
 
 
 @pytest.mark.parametrize("model", ["fixed_length", "monod", "wide_udf"])
 def test_alt_many_steps_division_exit_compaction(bmc, orc, synth, monkeypatch, model):
-    monkeypatch.setenv("BMC_VARIANT", "v4b3")
+    monkeypatch.setenv("BMC_VARIANT", "alt")
     tp.test_many_steps_division_exit_compaction(bmc, orc, synth, model)
 
 
 def test_alt_simple_acetate(bmc, orc, synth, monkeypatch):
-    monkeypatch.setenv("BMC_VARIANT", "v4b3")
+    monkeypatch.setenv("BMC_VARIANT", "alt")
     tp.test_simple_acetate_deterministic_part(bmc, orc, synth)
 
 
 def test_alt_large_compartment_tables(bmc, orc, synth, monkeypatch):
-    monkeypatch.setenv("BMC_VARIANT", "v4b3")
+    monkeypatch.setenv("BMC_VARIANT", "alt")
     tp.test_large_compartment_tables(bmc, orc, synth)
 
 
 def test_alt_synchronised_population(bmc, orc, synth, monkeypatch):
-    monkeypatch.setenv("BMC_VARIANT", "v4b3")
+    monkeypatch.setenv("BMC_VARIANT", "alt")
     tp.test_synchronised_population_many_divisions_in_one_step(bmc, orc, synth)
 
 
 @pytest.mark.parametrize("name", tr.NAMES)
 def test_alt_reproduces_reference_fixture(bmc, monkeypatch, name):
-    monkeypatch.setenv("BMC_VARIANT", "v4b3")
+    monkeypatch.setenv("BMC_VARIANT", "alt")
     tr.test_cuda_reproduces_reference_fixture(bmc, name)
 
 
 @pytest.mark.parametrize("model", ["fixed_length", "monod"])
 def test_alt_stamped_ages(bmc, orc, synth, monkeypatch, model):
-    monkeypatch.setenv("BMC_VARIANT", "v4b3")
+    monkeypatch.setenv("BMC_VARIANT", "alt")
     ta.test_stamped_ages_many_steps(bmc, orc, synth, model)
 
 
 def test_alt_eager_ages(bmc, orc, synth, monkeypatch):
-    monkeypatch.setenv("BMC_VARIANT", "v4b3")
+    monkeypatch.setenv("BMC_VARIANT", "alt")
     ta.test_nonzero_initial_ages_use_the_eager_kernel(bmc, orc, synth)
     ta.test_time_step_change_switches_to_eager(bmc, orc, synth)
     ta.test_outlet_switched_on_mid_run(bmc, orc, synth)
@@ -103,9 +104,9 @@ def test_source_terms_are_bit_identical_across_runs_and_block_sizes(bmc, synth, 
         case["props"][1, :] = 1.0   # no division: its division draws through libdevice, irrelevant here
     _, a = _run_sources(bmc, synth, case, 8)
     _, b = _run_sources(bmc, synth, case, 8)
-    monkeypatch.setenv("BMC_VARIANT", "v4b3")
+    monkeypatch.setenv("BMC_VARIANT", "alt")
     g3, c = _run_sources(bmc, synth, case, 8)
-    assert g3.kernel_config()["block"] == 768
+    assert g3.kernel_config()["block"] == ALT[model][2]
     for k in range(1, 8):
         assert np.array_equal(a[k], b[k]), k
         assert np.array_equal(a[k], c[k]), k
