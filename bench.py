@@ -12,7 +12,9 @@ carries, under "configs", one sub-record per BASELINE configuration measured the
 the same run: c2 (configs[1] at its own 1e7 particles), c2_eager (the same with ages updated
 eagerly, i.e. the 57 B/particle layout of SURVEY.md §8d), c3 (1e8 particles, division + outlet
 + compaction inside the timed region), c4 (10 000 compartments, 1.25e8 particles = the 8-GPU
-shard of configs[3]) and c5 (32-property UDF model, 2.5e8 particles = the shard of configs[4]).
+shard of configs[3]), c5 (32-property UDF model, 2.5e8 particles = the shard of configs[4]), and fl_ns / sa_ns
+(fixed_length and simple_acetate, the two models of the reference's default build, at the headline's
+1.25e8 particles).
 
   value     : whole-job particle-steps/s, state resident in HBM, no host sync
               inside the timed region, one all-reduce of the source vector
@@ -63,8 +65,12 @@ WORKLOADS = {
     # other built-in models on the c2 shape
     "fl": ("fixed_length", 500, 10_000_000, 0.1, 0.0, 1e-3),
     "sa": ("simple_acetate", 500, 10_000_000, 0.1, 0.0, 1e-3),
+    # the two models of the reference's default build (meson_options.txt: model_list_name) at the north-star population
+    "fl_ns": ("fixed_length", 500, 125_000_000, 0.1, 0.0, 1e-3),
+    "sa_ns": ("simple_acetate", 500, 125_000_000, 0.1, 0.0, 1e-3),
 }
-SUB_RECORDS = ("c2", "c2_eager", "c3", "c4", "c5")   # measured after the headline at N = 1 (each on a fresh context)
+# measured after the headline at N = 1 (each on a fresh context)
+SUB_RECORDS = ("c2", "c2_eager", "c3", "c4", "c5", "fl_ns", "sa_ns")
 
 
 def workload_label(wl, n_per_gpu=None):

@@ -894,6 +894,27 @@ static int upload_transition(bmc_ctx* ctx, uint64_t nnz, const uint64_t* rows, c
   for (size_t j = 0; j < nc; ++j) ptr[j + 1] += ptr[j];
   std::vector<uint32_t> fill(ptr, ptr + nc);
   for (uint64_t e = 0; e < nnz; ++e) { const uint32_t d = fill[cols[e]]++; row[d] = (uint32_t)rows[e]; val[d] = vals[e]; }
+  // The reference builds an Eigen::SparseMatrix from the triplets (sparse_from_coo, implScalar.cpp:79-129): duplicate
+  // entries are summed and the rows of a column end up in ascending order, which is the order `c * m_transition` adds
+  // the inflow terms of an element in.  Same here: every column sorted by row (stable), duplicates merged in input order.
+  {
+    std::vector<std::pair<uint32_t, double>> col;
+    uint32_t out = 0, begin = 0;
+    for (size_t j = 0; j < nc; ++j) {
+      const uint32_t end = ptr[j + 1];
+      col.clear();
+      for (uint32_t e = begin; e < end; ++e) col.emplace_back(row[e], val[e]);
+      std::stable_sort(col.begin(), col.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+      ptr[j] = out;
+      for (size_t e = 0; e < col.size(); ++e) {
+        if (e > 0 && col[e].first == col[e - 1].first) val[out - 1] += col[e].second;
+        else { row[out] = col[e].first; val[out] = col[e].second; ++out; }
+      }
+      begin = end;
+    }
+    ptr[nc] = out;
+    nnz = out;
+  }
   CK(cudaMemcpyAsync(d_ptr, ptr, (nc + 1) * 4, cudaMemcpyHostToDevice, s));
   if (nnz) {
     CK(cudaMemcpyAsync(*d_row, row, nnz * 4, cudaMemcpyHostToDevice, s));

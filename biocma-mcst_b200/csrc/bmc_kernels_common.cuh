@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) liquid_step_kernel(const __grid_constant_
   double dm = 0.0;
   for (uint32_t e = p.csc_ptr[j]; e < p.csc_ptr[j + 1]; ++e) dm += p.c_old[s + p.n_species * p.csc_row[e]] * p.csc_val[e];
   const double c = p.c_old[k];
-  dm += -c * sink + src;
+  dm = (dm - c * sink) + src;  // `c * m_transition - c * sink + _sources`, coefficient-wise, left to right (implScalar.cpp:259)
   const double m = p.mass[k] + p.dt * dm;
   p.mass[k] = m;
   p.c_new[k] = m * (1.0 / p.vol[j]);
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) gas_liquid_step_kernel(const __grid_const
     feed_terms(p.gas_feeds, p.n_gas_feeds, src, sink);
     double dm = 0.0;
     for (uint32_t e = p.g_csc_ptr[j]; e < p.g_csc_ptr[j + 1]; ++e) dm += p.g_old[s + l.n_species * p.g_csc_row[e]] * p.g_csc_val[e];
-    dm += -cg * sink + src;
+    dm = (dm - cg * sink) + src;  // `c * m_transition - c * sink + _sources + float(sign) * mtr` (implScalar.cpp:237-238)
     dm += -1.0 * mtr;
     const double m = p.g_mass[k] + l.dt * dm;
     p.g_mass[k] = m;
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) gas_liquid_step_kernel(const __grid_const
     feed_terms(l.feeds, l.n_feeds, src, sink);
     double dm = 0.0;
     for (uint32_t e = l.csc_ptr[j]; e < l.csc_ptr[j + 1]; ++e) dm += l.c_old[s + l.n_species * l.csc_row[e]] * l.csc_val[e];
-    dm += -cl * sink + src;
+    dm = (dm - cl * sink) + src;
     dm += 1.0 * mtr;
     const double m = l.mass[k] + l.dt * dm;
     l.mass[k] = m;

@@ -774,16 +774,31 @@ static void dispatch_cycle(Ctx& c, double d_t) {
 //   dm/dt = C*M - C*sink + sources ; mass += dt*dm ; C = mass * V^-1
 // with M the (n_comp x n_comp) transition matrix given as COO (rows, cols,
 // vals) and C (n_species x n_comp) species-fastest.
+// sparse_from_coo (implScalar.cpp:79-129): the triplets become a compressed sparse matrix — duplicates summed, the rows
+// of a column ascending — and `c * m_transition` adds the terms of an element in that order.  Returns (col, row, value)
+// sorted accordingly.
+struct CooEntry { uint64_t col, row; double val; };
+static std::vector<CooEntry> compressed_transition(size_t nnz, const uint64_t* rows, const uint64_t* cols, const double* vals) {
+  std::vector<CooEntry> t(nnz);
+  for (size_t e = 0; e < nnz; ++e) t[e] = CooEntry{cols[e], rows[e], vals[e]};
+  std::stable_sort(t.begin(), t.end(), [](const CooEntry& a, const CooEntry& b) { return a.col != b.col ? a.col < b.col : a.row < b.row; });
+  std::vector<CooEntry> out;
+  for (const CooEntry& e : t) {
+    if (!out.empty() && out.back().col == e.col && out.back().row == e.row) out.back().val += e.val;
+    else out.push_back(e);
+  }
+  return out;
+}
 static void ode_step(size_t ns, size_t ncomp, double dt, double* C, double* mass, const double* vol,
                      const double* sink, const double* sources, size_t nnz, const uint64_t* rows,
                      const uint64_t* cols, const double* vals) {
   std::vector<double> dm(ns * ncomp, 0.0);
-  for (size_t e = 0; e < nnz; ++e)
-    for (size_t s = 0; s < ns; ++s) dm[s + ns * cols[e]] += C[s + ns * rows[e]] * vals[e];
+  for (const CooEntry& e : compressed_transition(nnz, rows, cols, vals))
+    for (size_t s = 0; s < ns; ++s) dm[s + ns * e.col] += C[s + ns * e.row] * e.val;
   for (size_t j = 0; j < ncomp; ++j)
     for (size_t s = 0; s < ns; ++s) {
       const size_t k = s + ns * j;
-      dm[k] += -C[k] * sink[j] + sources[k];
+      dm[k] = (dm[k] - C[k] * sink[j]) + sources[k];  // Eigen evaluates `c*M - c*sink + sources` coefficient-wise, left to right
       mass[k] += dt * dm[k];
       C[k] = mass[k] * (1.0 / vol[j]);
     }
@@ -795,7 +810,8 @@ static void ode_step(size_t ns, size_t ncomp, double dt, double* C, double* mass
 //   gas_scalar->performStepGL(d_t, mtr, GasToLiquid = -1), liquid_scalar->performStepGL(d_t, mtr, LiquidToGas = +1):
 //       dm/dt = C*M - C*sink + sources + sign*mtr ; mass += dt*dm ; C = mass * V^-1           (implScalar.cpp:229-249)
 //   liquid_scalar->clearNegs(): values in (-1e-4*5e-3, 0) become 0                            (implScalar.cpp:270-296)
-// Eigen is not available, so like ode_step this is a restatement of the expressions, not the reference's own code.
+// Pinned against the reference's own implScalar.cpp / mass_transfer.cpp compiled over oracle/eigen_shim
+// (oracle/ref_liquid.cpp, tests/test_reference_liquid.py: bit-identical trajectories).
 static void ode_step_gl(size_t ns, size_t ncomp, double dt, double* Cl, double* ml, const double* vl, const double* sink_l,
                         const double* src_l, size_t nnz_l, const uint64_t* rl, const uint64_t* cl, const double* valsl, double* Cg,
                         double* mg, const double* vg, const double* sink_g, const double* src_g, size_t nnz_g, const uint64_t* rg,
@@ -806,12 +822,12 @@ static void ode_step_gl(size_t ns, size_t ncomp, double dt, double* Cl, double* 
   auto step = [&](double* C, double* mass, const double* vol, const double* sink, const double* src, size_t nnz, const uint64_t* rows,
                   const uint64_t* cols, const double* vals, double sign) {
     std::vector<double> dm(nb, 0.0);
-    for (size_t e = 0; e < nnz; ++e)
-      for (size_t s = 0; s < ns; ++s) dm[s + ns * cols[e]] += C[s + ns * rows[e]] * vals[e];
+    for (const CooEntry& e : compressed_transition(nnz, rows, cols, vals))
+      for (size_t s = 0; s < ns; ++s) dm[s + ns * e.col] += C[s + ns * e.row] * e.val;
     for (size_t j = 0; j < ncomp; ++j)
       for (size_t s = 0; s < ns; ++s) {
         const size_t k = s + ns * j;
-        dm[k] += -C[k] * sink[j] + src[k];
+        dm[k] = (dm[k] - C[k] * sink[j]) + src[k];
         dm[k] += sign * mtr[k];
         mass[k] += dt * dm[k];
         C[k] = mass[k] * (1.0 / vol[j]);

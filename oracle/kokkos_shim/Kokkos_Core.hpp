@@ -484,6 +484,31 @@ template <class... Props> class RangePolicy {
   size_t end() const { return e_; }
 };
 
+// MDRangePolicy<Space, Rank<2, outer, inner>>({b0, b1}, {e0, e1}): the two-dimensional form the reference's liquid solver
+// uses; Iterate::Left makes the FIRST index the fastest
+enum class Iterate { Default, Left, Right };
+template <unsigned N, Iterate Outer = Iterate::Default, Iterate Inner = Iterate::Default> struct Rank { static constexpr unsigned rank = N; static constexpr Iterate outer = Outer; };
+template <class... Props> class MDRangePolicy {
+  template <class P> struct IsRank : std::false_type {};
+  template <unsigned N, Iterate O, Iterate I> struct IsRank<Rank<N, O, I>> : std::true_type {};
+  template <class... Q> struct PickRank { using type = Rank<2>; };
+  template <class Q0, class... Q> struct PickRank<Q0, Q...> { using type = std::conditional_t<IsRank<Q0>::value, Q0, typename PickRank<Q...>::type>; };
+ public:
+  using rank_type = typename PickRank<Props...>::type;
+  static_assert(rank_type::rank == 2, "kokkos_shim: MDRangePolicy is provided for rank 2");
+  template <class B, class E> MDRangePolicy(std::initializer_list<B> b, std::initializer_list<E> e) {
+    size_t k = 0; for (auto x : b) b_[k++] = (size_t)x;
+    k = 0; for (auto x : e) e_[k++] = (size_t)x;
+  }
+  size_t b_[2] = {0, 0}, e_[2] = {0, 0};
+};
+template <class F, class... P> void parallel_for(const std::string& label, const MDRangePolicy<P...>& pol, const F& f) {
+  shim::kernel_begin(label);
+  if (MDRangePolicy<P...>::rank_type::outer == Iterate::Left) { for (size_t j = pol.b_[1]; j < pol.e_[1]; ++j) for (size_t i = pol.b_[0]; i < pol.e_[0]; ++i) f((int)i, (int)j); }
+  else { for (size_t i = pol.b_[0]; i < pol.e_[0]; ++i) for (size_t j = pol.b_[1]; j < pol.e_[1]; ++j) f((int)i, (int)j); }
+  shim::kernel_end();
+}
+
 struct NestedRange { size_t b, e; };
 inline NestedRange TeamThreadRange(const HostTeamMember&, size_t n) { return {0, n}; }
 inline NestedRange TeamThreadRange(const HostTeamMember&, size_t b, size_t e) { return {b, e}; }

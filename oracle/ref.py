@@ -277,3 +277,106 @@ class RefLoop:
         return dict(events={EVENTS[i]: c[i] for i in range(6)}, n_used=c[6], n_inactive=c[7], last_out=c[8],
                     last_dead=c[9], last_waiting_allocation=c[10], buffer_index=c[11], capacity=c[12], total_out=c[13],
                     total_new=c[14], n_compactions=c[15])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's own liquid / gas scalar solver (oracle/ref_liquid.cpp: implScalar.cpp + hydro/mass_transfer.cpp over
+# oracle/eigen_shim, rust_shim, kokkos_shim).  TEST INFRASTRUCTURE.
+LIQUID_LIB_PATH = os.path.join(_HERE, "_ref", "libbmc_ref_liquid.so")
+_liq = None
+
+
+def liquid_available():
+    return os.path.exists(LIQUID_LIB_PATH) or can_build()
+
+
+def liquid_lib():
+    global _liq
+    if _liq is None:
+        if not os.path.exists(LIQUID_LIB_PATH):
+            build()
+        L = ctypes.CDLL(LIQUID_LIB_PATH)
+        vp, u64, dbl, ci = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_double, ctypes.c_int
+        L.refl_create.restype = vp; L.refl_create.argtypes = [u64, u64, vp]
+        L.refl_destroy.restype = None; L.refl_destroy.argtypes = [vp]
+        L.refl_enable_gas.argtypes = [vp, vp, vp]
+        L.refl_set_kla_henry.argtypes = [vp, vp, vp]
+        L.refl_get_henry.argtypes = [vp, vp]
+        L.refl_set_hydro.argtypes = [vp, ci, vp, vp, u64, vp, vp, vp]
+        L.refl_set_concentration.argtypes = [vp, ci, vp]
+        L.refl_get_concentration.argtypes = [vp, ci, vp]
+        L.refl_get_mtr.argtypes = [vp, vp]
+        L.refl_step.argtypes = [vp, dbl] + [vp] * 8
+        _liq = L
+    return _liq
+
+
+class RefLiquid:
+    """ScalarSimulation (liquid, optionally gas + MassTransferModel) of the reference, stepped the way its main loop does:
+    update_feed -> ode_step -> clearContribution.  Concentrations are species-fastest flat arrays like everywhere else."""
+
+    def __init__(self, n_species, n_comp, volumes):
+        self.L = liquid_lib()
+        self.ns, self.nc = int(n_species), int(n_comp)
+        v = np.ascontiguousarray(volumes, np.float64)
+        self.h = self.L.refl_create(self.ns, self.nc, _ptr(v))
+        self.two_phase = False
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.refl_destroy(self.h); self.h = None
+
+    def set_hydro(self, volumes, coo, gas=False):
+        """updateScalarHydro: volumes, their inverses (rcmtool hands over 1/V) and the transition matrix as COO"""
+        v = np.ascontiguousarray(volumes, np.float64)
+        inv = np.ascontiguousarray(1.0 / v)
+        rows, cols, vals = (np.ascontiguousarray(coo[0], np.uint64), np.ascontiguousarray(coo[1], np.uint64), np.ascontiguousarray(coo[2], np.float64))
+        assert self.L.refl_set_hydro(self.h, int(gas), _ptr(v), _ptr(inv), vals.size, _ptr(rows), _ptr(cols), _ptr(vals)) == 0
+
+    def enable_gas(self, gas_volumes, kla_per_species):
+        gv = np.ascontiguousarray(gas_volumes, np.float64); k = np.ascontiguousarray(kla_per_species, np.float64)
+        assert k.size == self.ns
+        assert self.L.refl_enable_gas(self.h, _ptr(gv), _ptr(k)) == 0
+        self.two_phase = True
+
+    def set_kla_henry(self, kla, henry):
+        k = np.ascontiguousarray(kla, np.float64); hh = np.ascontiguousarray(henry, np.float64)
+        assert k.size == self.ns * self.nc and hh.size == self.ns
+        assert self.L.refl_set_kla_henry(self.h, _ptr(k), _ptr(hh)) == 0
+
+    def default_henry(self):
+        out = np.empty(self.ns)
+        assert self.L.refl_get_henry(self.h, _ptr(out)) == 0
+        return out
+
+    def set_concentration(self, c, gas=False):
+        c = np.ascontiguousarray(c, np.float64)
+        assert self.L.refl_set_concentration(self.h, int(gas), _ptr(c)) == 0
+
+    def concentration(self, gas=False):
+        out = np.empty(self.ns * self.nc)
+        assert self.L.refl_get_concentration(self.h, int(gas), _ptr(out)) == 0
+        return out
+
+    def mass_transfer(self):
+        out = np.empty(self.ns * self.nc)
+        assert self.L.refl_get_mtr(self.h, _ptr(out)) == 0
+        return out
+
+    def step(self, d_t, mc_sources=None, feeds=(), gas_feeds=()):
+        """feeds: dicts {species, input_position, flow, concentration, output_position?, first_of_feed?} (one dict per
+        (feed, species) pair like the C ABI's bmc_feed; the sink of a feed is set once, by its first entry)"""
+        def pack(fs):
+            sp = np.array([f["species"] for f in fs], np.uint64); ip = np.array([f["input_position"] for f in fs], np.uint64)
+            val = np.array([f["flow"] * f["concentration"] for f in fs], np.float64)   # set_scalar_feed: fd.flow * concentration
+            sk = [f for f in fs if f.get("output_position") is not None and f.get("first_of_feed", 1)]
+            sc = np.array([f["output_position"] for f in sk], np.uint64); sf = np.array([f["flow"] for f in sk], np.float64)
+            return sp, ip, val, sc, sf
+
+        a, b = pack(list(feeds)), pack(list(gas_feeds))
+        n_f = (ctypes.c_uint64 * 2)(a[0].size, b[0].size); n_s = (ctypes.c_uint64 * 2)(a[3].size, b[3].size)
+        pairs = [(ctypes.c_void_p * 2)(a[i].ctypes.data if a[i].size else None, b[i].ctypes.data if b[i].size else None) for i in range(5)]
+        src = None if mc_sources is None else np.ascontiguousarray(mc_sources, np.float64)
+        rc = self.L.refl_step(self.h, float(d_t), _ptr(src), ctypes.addressof(n_f), ctypes.addressof(pairs[0]), ctypes.addressof(pairs[1]),
+                              ctypes.addressof(pairs[2]), ctypes.addressof(n_s), ctypes.addressof(pairs[3]), ctypes.addressof(pairs[4]))
+        assert rc == 0

@@ -38,7 +38,7 @@ def to_bytes(v, u):
     return float(v.replace(",", "")) * mult
 
 
-for name in ("ns", "c2", "c2_eager", "c3", "c4"):
+for name in ("ns", "c2", "c2_eager", "c3", "c4", "fl_ns", "sa_ns"):
     rep = os.path.join(G, f"{tag}_cycle_{name}.ncu-rep")
     if not os.path.exists(rep):
         continue
