@@ -92,6 +92,7 @@ struct bmc_ctx {
   size_t queue_offset = 0, smem_total = 0, stage_offset = 0, stage_warp_bytes = 0; int ctab_in_smem = 0; size_t ctab_offset = 0; int grid_post = 148;
   int grid_cycle_eager = 148; size_t smem_eager = 0;
   bool fuse_post = true;  // whole step in one cooperative launch (BMC_FUSE_POST=0: particle pass + post_only_kernel)
+  uint32_t dyn_min = 4, dyn_shift = 0;  // dynamically drawn tail of the particle pass (CycleParams; default from the model's launch table; BMC_DYN_MIN, BMC_DYN_SHIFT: tuning)
   // staging
   void* d_stage = nullptr; size_t stage_bytes = 0;
   // profiling
@@ -274,6 +275,9 @@ static int configure_launch(bmc_ctx* ctx) {
   ctx->smem_eager = ctx->smem_total;
   ctx->grid_post = ctx->n_sm;           // cooperative launch: one block per SM is always co-resident
   if (const char* e = getenv("BMC_FUSE_POST")) ctx->fuse_post = atoi(e) != 0;
+  ctx->dyn_shift = (uint32_t)ctx->vt.dyn_shift;
+  if (const char* e = getenv("BMC_DYN_MIN")) ctx->dyn_min = (uint32_t)std::max(1, atoi(e));
+  if (const char* e = getenv("BMC_DYN_SHIFT")) ctx->dyn_shift = (uint32_t)std::min(31, std::max(0, atoi(e)));
   const char* env = getenv("BMC_BLOCKS_PER_SM");
   auto grid_of = [&](const void* fn, int block, size_t smem, int& grid, int* occ_out) -> int {
     // always: static shared memory of the kernel counts against the 48 KB default as well
@@ -1188,6 +1192,7 @@ int bmc_cycle(bmc_ctx* ctx, double d_t) {
   p.enable_move = enable_move; p.enable_leave = enable_leave; p.bins_in_smem = ctx->bins_in_smem;
   p.queue_offset = (uint32_t)ctx->queue_offset;
   p.stage_offset = (uint32_t)ctx->stage_offset; p.stage_warp_bytes = (uint32_t)ctx->stage_warp_bytes;
+  p.dyn_min = ctx->dyn_min; p.dyn_shift = ctx->dyn_shift;
   // Philox constants of this step's three draw blocks, folded on the host (bmc_rng.cuh)
   p.ph0 = philox_pre(p.step, 0u, p.rank, p.seed_lo, p.seed_hi);  // u1: leaves its compartment
   p.ph1 = philox_pre(p.step, 1u, p.rank, p.seed_lo, p.seed_hi);  // u3: outlet test

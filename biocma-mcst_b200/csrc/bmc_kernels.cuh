@@ -258,6 +258,9 @@ struct CycleParams {
   uint32_t queue_offset;  // byte offset of the per-warp deferred queues inside dynamic shared memory
   // prefetch staging (VEC == 4 only): byte offset of the per-warp staging buffers and their size (0 = no prefetch)
   uint32_t stage_offset, stage_warp_bytes;
+  // work distribution of the particle pass: groups per warp drawn dynamically at the end of the pass = max(dyn_min,
+  // groups per warp >> dyn_shift); the rest is grid-stride (cycle_body).  dyn_shift = 0: everything dynamic.
+  uint32_t dyn_min, dyn_shift;
   PostParams post;   // second phase of the step (post_cycle_body)
   int fuse_post;     // 1 = run it in this launch behind a grid barrier (cooperative launch), 0 = post_only_kernel follows
 };
@@ -1330,17 +1333,27 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
     volatile unsigned* const v_seq = s_chunk_seq;
     volatile unsigned* const v_left = s_chunk_left;
     volatile unsigned* const v_base = s_chunk_base;
+    // Static head, dynamic tail.  The tickets cost ~45 instructions per group and thread; most of the pass does not need
+    // them: the first `rounds` groups of a warp are its grid-stride groups w, w + W, w + 2W ... (W = warps of the grid:
+    // the groups in flight still form one window moving through the columns), and only the last groups — an eighth of
+    // the pass, at least four per warp — are drawn dynamically, which is what evens out blocks that started late or
+    // run slower.  rounds == 1 is the fully dynamic scheme.
+    const uint32_t per_warp = n_groups / total_warps;
+    const uint32_t dyn = max(p.dyn_min, per_warp >> p.dyn_shift);
+    const uint32_t rounds = per_warp > dyn ? per_warp - dyn : 1u;
+    const uint32_t n_static = rounds * total_warps;  // groups below this index are assigned statically
     uint32_t s = blockIdx.x * kWarps + warp;  // first group: the warp's own index
     if (pf && s < n_groups) stage_issue(s);
 #pragma unroll 1
     while (s < n_groups) {
+      const bool stat = s + total_warps < n_static;  // warp-uniform: the next group is this warp's next grid-stride group
       unsigned t = 0;
-      if (lane == 0) {  // draw the ticket of the NEXT group now, resolve it in the middle of this group
+      if (!stat && lane == 0) {  // draw the ticket of the NEXT group now, resolve it in the middle of this group
         t = atomicAdd(&s_ticket, 1u);
         const unsigned c = t / kWarps, o = t - c * kWarps, slot = c % kRing;
         if (o == 0u) {
           while (v_left[slot] != 0u) { }  // previous chunk of this slot still has unresolved tickets (practically never)
-          const unsigned base = total_warps + atomicAdd(&p.st->next_group, (unsigned)kWarps);
+          const unsigned base = n_static + atomicAdd(&p.st->next_group, (unsigned)kWarps);
           v_base[slot] = base;
           v_left[slot] = (unsigned)kWarps;
           __threadfence_block();
@@ -1350,6 +1363,7 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
       if constexpr (VEC == 4) {
         uint32_t s_next = 0;
         auto resolve = [&]() {
+          if (stat) { s_next = s + total_warps; return; }
           if (lane == 0) {
             const unsigned c = t / kWarps, o = t - c * kWarps, slot = c % kRing;
             while (v_seq[slot] != c + 1u) { }
@@ -1375,6 +1389,7 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
         auto nothing = []() {};
         if ((unsigned long long)(s + 1u) * kGroup <= n_used) body(FullTile{}, s, nothing);
         else body(RaggedTile{}, s, nothing);
+        if (stat) { s += total_warps; continue; }
         if (lane == 0) {
           const unsigned c = t / kWarps, o = t - c * kWarps, slot = c % kRing;
           while (v_seq[slot] != c + 1u) { }

@@ -12,6 +12,7 @@ struct ModelVT {
   int block, block_eager;  // threads per block of cycle_fn / cycle_eager_fn (one block per SM)
   int ct;              // 32-bit words per compartment-table row
   int n_read;          // property columns the pass loads (n_var minus the write-only ones): sizes the prefetch staging
+  int dyn_shift;       // default work distribution of the particle pass (CycleParams::dyn_shift), DynTail below
   // kernel handles: addresses of __global__ instantiations, or cudaKernel_t of a JIT-compiled
   // user model; all launched with cudaLaunchKernel(handle, grid, block, {&params}, smem, stream)
   const void* cycle_fn;   // (CycleParams)  block = 256*minb threads, one block per SM; step-stamped ages (bmc_kernels.cuh)
@@ -22,13 +23,23 @@ struct ModelVT {
   void* jit_library;      // cudaLibrary_t of a user model (unloaded with the context), else nullptr
 };
 
+// Work distribution of the particle pass (cycle_body): groups per warp >> shift are drawn dynamically at the end of the
+// pass, the rest is grid-stride; 0 = every group dynamic.  Measured at 1.25e8 particles on a B200: the models whose
+// pass is bound by instruction issue gain what the tickets cost (fixed_length 0.601 -> 0.553 ms per step,
+// simple_acetate 1.99 -> 1.91 with an eighth dynamic), the HBM-bound monod pass LOSES with any static share (0.802 ->
+// 0.838 with a quarter dynamic, 0.878 with an eighth): when the memory system is the limit the SMs do not progress at
+// the same rate, and only the fully dynamic scheme keeps all of them busy until the end.
+template <class M> struct DynTail { static constexpr int shift = 0; };
+template <> struct DynTail<FixedLength> { static constexpr int shift = 3; };
+template <> struct DynTail<SimpleAcetate> { static constexpr int shift = 3; };
+
 // MINB = 256-thread units per block of the stamped-age kernel, MINB_E of the eager-age kernel (two more
 // columns in flight per slot: more registers per thread, fewer threads)
 template <class M, int VEC, int MINB, int MINB_E> static ModelVT make_vt() {
   ModelVT v;
   v.n_var = M::n_var; v.n_c = M::n_c; v.vec = VEC; v.minb = MINB;
   v.block = kBlock * MINB; v.block_eager = kBlock * MINB_E;
-  v.ct = 1 + M::n_pre; v.n_read = ReadCols<M>::value;
+  v.ct = 1 + M::n_pre; v.n_read = ReadCols<M>::value; v.dyn_shift = DynTail<M>::shift;
   v.cycle_fn = (const void*)cycle_kernel<M, VEC, MINB, true>;
   v.cycle_eager_fn = (const void*)cycle_kernel<M, VEC, MINB_E, false>;
   v.pre_fn = (const void*)pre_step_kernel<M>;

@@ -136,3 +136,29 @@ def test_fixed_point_scatter_keeps_small_contributions(bmc, orc, synth):
             assert sel.sum() > n_comp // 2
             assert np.max(np.abs(sg[sel] - so[sel]) / np.abs(so[sel])) <= 1e-6
     tp._compare(g, o)
+
+
+@pytest.mark.parametrize("model,n", [("fixed_length", 2_000_077), ("monod", 2_000_077), ("simple_acetate", 1_500_013), ("wide_udf", 400_019)])
+def test_static_head_dynamic_tail_work_distribution(bmc, orc, synth, monkeypatch, model, n):
+    """Work distribution of the particle pass (cycle_body): the first groups of a warp are its grid-stride groups, the
+    last ones are drawn dynamically.  Small populations never reach the static part (fewer groups than warps), so this
+    case is sized for two static rounds followed by the dynamic tail (BMC_DYN_MIN=1, BMC_DYN_SHIFT=2: a quarter of three
+    groups per warp rounds to the minimum of one), on every kernel family — and must be bit-identical to the oracle like
+    the fully dynamic scheme."""
+    import util
+    monkeypatch.setenv("BMC_DYN_MIN", "1")
+    monkeypatch.setenv("BMC_DYN_SHIFT", "2")
+    kw = dict(n_var_udf=32) if model == "wide_udf" else {}   # VEC = 1 kernel: the other loop text of cycle_body
+    case = util.make_case(synth, model, n, 60, dt=20.0, near_division=0.8, p_move=0.3, p_exit=0.3, **kw)
+    if model == "simple_acetate":
+        case["props"][1, :] = 1.0   # no division: its division draws through libdevice
+    g, o = tp._pair(bmc, orc, case, dead_ratio=0.0005)
+    k = g.kernel_config()
+    groups = (n + 32 * k["vec"] - 1) // (32 * k["vec"])
+    assert groups // (k["grid"] * k["block"] // 32) >= 3, "population too small to reach the static rounds on this device"
+    util.load_case(g, case); util.load_case(o, case)
+    sg = util.run_steps(g, case, 3, collect=True); so = util.run_steps(o, case, 3, collect=True)
+    tp._compare_sources(sg, so)
+    tp._compare(g, o)
+    c = o.counters()
+    assert c["total_out"] > 0 and (model == "simple_acetate" or c["total_new"] > 0)
