@@ -458,6 +458,10 @@ def measure(D, pkg, synth, wl, n_per_gpu, steps, warmup, e2e_steps, eager=False,
     rec = {
         "value": live_tot * steps / (ms * 1e-3), "unit": "particle-steps/s", "steps": steps, "warmup": warmup,
         "ms_per_step": ms / steps, "config": workload_config(wl, n_per_gpu, n_var),
+        # particles actually stepped (mean over the timed region, all ranks): what `value` and `roofline` are computed from.
+        # Differs from the configured population where the model's own initial state divides at once (simple_acetate
+        # draws length and l_max from the same law, simple_acetate.hpp:132-152: half the cells divide in the first step)
+        "live_particles": live_tot,
         "parallelism": f"particle-sharded x{world}, replicated liquid state, {collective}" if world > 1 else "single GPU",
         "e2e": {"value": live_e2e_tot * e2e_steps / (ms_e2e * 1e-3), "unit": "particle-steps/s", "h2d_bytes_per_step": nb,
                 "d2h_bytes_per_step": nb, "ms_per_step": ms_e2e / e2e_steps},
@@ -532,7 +536,7 @@ def main():
         line = {"metric": "particle-steps/sec", "value": rec["value"], "unit": rec["unit"], "n_gpus": D.world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": rec["config"], "parallelism": rec["parallelism"],
-                "e2e": rec["e2e"], "gpu_launches": rec["gpu_launches"], "roofline": rec["roofline"],
+                "e2e": rec["e2e"], "gpu_launches": rec["gpu_launches"], "live_particles": rec["live_particles"], "roofline": rec["roofline"],
                 "events_in_timed_region": rec["events_in_timed_region"], "clocks": clocks}
         if "collective_check" in rec:
             line["collective_check"] = rec["collective_check"]
@@ -543,7 +547,8 @@ def main():
             swl, eager = (name[:-6], True) if name.endswith("_eager") else (name, False)
             try:
                 r = measure(D, pkg, synth, swl, WORKLOADS[swl][2], args.configs_steps, max(3, min(args.warmup, 5)), args.configs_steps, eager=eager)
-                subs[name] = {k: r[k] for k in ("value", "unit", "steps", "ms_per_step", "config", "e2e", "roofline", "events_in_timed_region")}
+                subs[name] = {k: r[k] for k in ("value", "unit", "steps", "ms_per_step", "live_particles", "config", "e2e", "roofline",
+                                                "events_in_timed_region")}
             except Exception as e:  # noqa: BLE001 - a sub-record must not take the headline down
                 subs[name] = {"error": f"{type(e).__name__}: {e}"}
         line["configs"] = subs
