@@ -862,7 +862,7 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
   constexpr unsigned kFull = 0xffffffffu;
   // Rows of 8 words (two doubles among the model terms, simple_acetate): in shared memory the table is kept PLANAR
   // (word k of compartment c at [k * n_comp + c]) — 32 lanes gathering the same word of 32 random compartments then
-  // spread over all 32 banks.  (Measured at 1.25e8 particles: 32-byte rows fetched with two 128-bit gathers, which put
+  // spread over all 32 banks.  (Measured on the sa_ns workload of bench.py, 1.875e8 live particles: 32-byte rows fetched with two 128-bit gathers, which put
   // every lane on one of four bank groups, 2.25 ms per step; two planes of 16-byte half rows 2.02; word planes 1.94.)
   // The model terms are fetched right before the particle's update, so that the terms of the VEC particles of a thread
   // are not all live at once.  The global-memory form of the table (n_comp too large for shared memory) stays

@@ -26,7 +26,7 @@ struct ModelVT {
 // Work distribution of the particle pass (cycle_body): groups per warp >> shift are drawn dynamically at the end of the
 // pass, the rest is grid-stride; 0 = every group dynamic.  Measured at 1.25e8 particles on a B200: the models whose
 // pass is bound by instruction issue gain what the tickets cost (fixed_length 0.601 -> 0.553 ms per step,
-// simple_acetate 1.99 -> 1.91 with an eighth dynamic), the HBM-bound monod pass LOSES with any static share (0.802 ->
+// simple_acetate, 1.875e8 live particles, 1.99 -> 1.91 with an eighth dynamic), the HBM-bound monod pass LOSES with any static share (0.802 ->
 // 0.838 with a quarter dynamic, 0.878 with an eighth): when the memory system is the limit the SMs do not progress at
 // the same rate, and only the fully dynamic scheme keeps all of them busy until the end.
 template <class M> struct DynTail { static constexpr int shift = 0; };
