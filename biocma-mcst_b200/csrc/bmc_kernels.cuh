@@ -876,6 +876,11 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
   __shared__ unsigned s_fxmax[8];              // largest |contribution| per species seen by this block (float bits)
   // work distribution (see below): ticket counter + a ring of chunk descriptors
   constexpr unsigned kRing = 8;
+  // groups a block draws from the device-wide counter at a time: small enough that the blocks run out of work together
+  // at the end of the pass, large enough that the same-address L2 atomic stays far from its limit (~0.8 per ns: 1.25e8
+  // particles are 122 000 chunks per 800 us).  Same box, 32 / 16 / 8 groups: 1.25e8 particles 802.1 / 798.2 / 796.6 us
+  // per step, 1e7 particles 81.8 / 81.4 / 81.4.
+  constexpr int kChunk = 8;
   __shared__ unsigned s_ticket;
   __shared__ unsigned s_chunk_base[kRing];     // first group of chunk c (slot c % kRing) ...
   __shared__ unsigned s_chunk_seq[kRing];      // ... valid when == c + 1
@@ -886,7 +891,7 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
   // Work distribution: the slots are cut into groups of 32*VEC; every warp of the (persistent, fully
   // resident) grid starts with the group of its own index and then draws further groups dynamically, so
   // that blocks which start late or run on a slower SM simply process fewer groups.  Two levels: a
-  // BLOCK draws chunks of kWarps consecutive groups from the device-wide counter, its warps draw
+  // BLOCK draws chunks of kChunk (8) consecutive groups from the device-wide counter, its warps draw
   // single groups of the chunk with a shared-memory ticket.  (One L2 atomic per GROUP on one address
   // was the limiter of the whole pass: same-address atomics retire at ~0.8 per ns on a B200, i.e.
   // 78 125 groups of a 1e7-particle step could not be handed out in less than ~95 us — the time per
@@ -1324,8 +1329,8 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
   };
 
   {
-    // Ticket t of a block -> chunk c = t / kWarps, offset o = t % kWarps.  The warp that draws o == 0 fetches the
-    // chunk from the device-wide counter (the only L2 atomic: one per kWarps groups) and publishes its first group
+    // Ticket t of a block -> chunk c = t / kChunk, offset o = t % kChunk.  The warp that draws o == 0 fetches the
+    // chunk from the device-wide counter (the only L2 atomic: one per kChunk groups) and publishes its first group
     // in ring slot c % kRing; the other warps of the chunk read it when they need their group (normally long after).
     // A slot is reused only when every ticket of its previous chunk has been resolved (s_chunk_left), so a warp can
     // never read the base of a later chunk.  Every warp holds at most one unresolved ticket and resolves it before
@@ -1350,12 +1355,12 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
       unsigned t = 0;
       if (!stat && lane == 0) {  // draw the ticket of the NEXT group now, resolve it in the middle of this group
         t = atomicAdd(&s_ticket, 1u);
-        const unsigned c = t / kWarps, o = t - c * kWarps, slot = c % kRing;
+        const unsigned c = t / kChunk, o = t - c * kChunk, slot = c % kRing;
         if (o == 0u) {
           while (v_left[slot] != 0u) { }  // previous chunk of this slot still has unresolved tickets (practically never)
-          const unsigned base = n_static + atomicAdd(&p.st->next_group, (unsigned)kWarps);
+          const unsigned base = n_static + atomicAdd(&p.st->next_group, (unsigned)kChunk);
           v_base[slot] = base;
-          v_left[slot] = (unsigned)kWarps;
+          v_left[slot] = (unsigned)kChunk;
           __threadfence_block();
           v_seq[slot] = c + 1u;
         }
@@ -1365,7 +1370,7 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
         auto resolve = [&]() {
           if (stat) { s_next = s + total_warps; return; }
           if (lane == 0) {
-            const unsigned c = t / kWarps, o = t - c * kWarps, slot = c % kRing;
+            const unsigned c = t / kChunk, o = t - c * kChunk, slot = c % kRing;
             while (v_seq[slot] != c + 1u) { }
             __threadfence_block();
             s_next = v_base[slot] + o;
@@ -1391,7 +1396,7 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
         else body(RaggedTile{}, s, nothing);
         if (stat) { s += total_warps; continue; }
         if (lane == 0) {
-          const unsigned c = t / kWarps, o = t - c * kWarps, slot = c % kRing;
+          const unsigned c = t / kChunk, o = t - c * kChunk, slot = c % kRing;
           while (v_seq[slot] != c + 1u) { }
           __threadfence_block();
           s = v_base[slot] + o;

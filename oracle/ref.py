@@ -301,6 +301,8 @@ def liquid_lib():
         L.refl_destroy.restype = None; L.refl_destroy.argtypes = [vp]
         L.refl_enable_gas.argtypes = [vp, vp, vp]
         L.refl_set_kla_henry.argtypes = [vp, vp, vp]
+        L.refl_enable_gas_turbulence.argtypes = [vp, vp]
+        L.refl_update_mass_transfer.argtypes = [vp, vp, vp, vp, vp]
         L.refl_get_henry.argtypes = [vp, vp]
         L.refl_set_hydro.argtypes = [vp, ci, vp, vp, u64, vp, vp, vp]
         L.refl_set_concentration.argtypes = [vp, ci, vp]
@@ -338,6 +340,19 @@ class RefLiquid:
         assert k.size == self.ns
         assert self.L.refl_enable_gas(self.h, _ptr(gv), _ptr(k)) == 0
         self.two_phase = True
+
+    def enable_gas_turbulence(self, gas_volumes):
+        """gas phase + MassTransferModel of Type::FlowmapTurbulence (kla from the turbulence correlation, impl_mtr.cpp)"""
+        gv = np.ascontiguousarray(gas_volumes, np.float64)
+        assert self.L.refl_enable_gas_turbulence(self.h, _ptr(gv)) == 0
+        self.two_phase = True
+
+    def update_mass_transfer(self, liquid_volumes, gas_volumes, energy_dissipation):
+        """MassTransferModel::update(state): returns the kla field (species-fastest) the reference derives from the state"""
+        vl, vg, eps = (np.ascontiguousarray(x, np.float64) for x in (liquid_volumes, gas_volumes, energy_dissipation))
+        out = np.empty(self.ns * self.nc)
+        assert self.L.refl_update_mass_transfer(self.h, _ptr(vl), _ptr(vg), _ptr(eps), _ptr(out)) == 0
+        return out
 
     def set_kla_henry(self, kla, henry):
         k = np.ascontiguousarray(kla, np.float64); hh = np.ascontiguousarray(henry, np.float64)

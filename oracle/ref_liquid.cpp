@@ -25,13 +25,6 @@
 #include <scalar_simulation.hpp>
 #include <simulation/mass_transfer.hpp>
 
-namespace Simulation::MassTransfer::Impl {
-// referenced by MassTransferModel::update (rcmtool iteration states); never called here
-void flowmap_gas_liquid_mass_transfer(MassTransferProxy&, const Eigen::ArrayXXd&, const Eigen::ArrayXXd&, const Eigen::MatrixXd&,
-                                      const CmaUtils::IterationStatePtrType&) {}
-void fixed_kla_gas_liquid_mass_transfer(MassTransferProxy&, const Eigen::ArrayXXd&, const Eigen::ArrayXXd&, const Eigen::MatrixXd&,
-                                        const CmaUtils::IterationStatePtrType&) {}
-}  // namespace Simulation::MassTransfer::Impl
 
 namespace {
 using Simulation::ScalarSimulation;
@@ -67,6 +60,27 @@ int refl_set_kla_henry(void* p, const double* kla, const double* henry) {  // kl
   auto& px = *h->mt->proxy();
   for (size_t j = 0; j < h->nc; ++j) for (size_t s = 0; s < h->ns; ++s) px.kla((Eigen::Index)s, (Eigen::Index)j) = kla[s + h->ns * j];
   for (size_t s = 0; s < h->ns; ++s) px.Henry((Eigen::Index)s) = henry[s];
+  return 0;
+}
+// MassTransferModel of Type::FlowmapTurbulence: update(state) evaluates the kl / interfacial-area correlations of
+// hydro/impl_mtr.cpp:22-149 from the state's volumes and energy dissipation and stores kla row 1 (oxygen) in the proxy
+int refl_enable_gas_turbulence(void* p, const double* gas_vol) {
+  auto* h = static_cast<RefLiquid*>(p);
+  std::vector<double> v(gas_vol, gas_vol + h->nc);
+  h->gas.reset(Simulation::makeScalarSimulation(h->nc, h->ns, std::span<double>(v)));
+  h->mt = std::make_unique<Simulation::MassTransfer::MassTransferModel>(
+      Simulation::MassTransfer::Type::MtrTypeVariant(Simulation::MassTransfer::Type::FlowmapTurbulence{}), h->liq, h->gas);
+  return 0;
+}
+int refl_update_mass_transfer(void* p, const double* liq_vol, const double* gas_vol, const double* eps, double* kla_out) {
+  auto* h = static_cast<RefLiquid*>(p);
+  if (!h->mt) return -1;
+  auto* st = new IterationStateWrapper;
+  st->liq.vol.assign(liq_vol, liq_vol + h->nc); st->gas.vol.assign(gas_vol, gas_vol + h->nc); st->energy_dissipation.assign(eps, eps + h->nc);
+  CmaUtils::IterationStatePtrType state(st);
+  h->mt->update(state);
+  const auto& px = *h->mt->proxy();
+  for (size_t j = 0; j < h->nc; ++j) for (size_t s = 0; s < h->ns; ++s) kla_out[s + h->ns * j] = px.kla((Eigen::Index)s, (Eigen::Index)j);
   return 0;
 }
 int refl_get_henry(void* p, double* henry) {  // what the reference's constructor put there (mass_transfer.cpp:116-119)

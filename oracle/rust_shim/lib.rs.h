@@ -21,7 +21,19 @@ template <class T> class Box {
 }  // namespace rust
 
 struct TransitionerWrapper;
-struct IterationStateWrapper;
+// what hydro/impl_mtr.cpp reads from an iteration state: the volumes of both phases and the named per-compartment
+// field "energy_dissipation"
+struct PhaseStateWrapper {
+  std::vector<double> vol;
+  std::span<const double> volume() const { return {vol.data(), vol.size()}; }
+};
+struct IterationStateWrapper {
+  PhaseStateWrapper liq, gas;
+  std::vector<double> energy_dissipation;
+  const PhaseStateWrapper* get_liquid() const { return &liq; }
+  const PhaseStateWrapper* get_gas() const { return &gas; }
+  std::span<const double> get_misc(const char*) const { return {energy_dissipation.data(), energy_dissipation.size()}; }
+};
 struct CooMatrixWrap {
   std::size_t n = 0;
   std::vector<std::size_t> r, c;

@@ -1,6 +1,7 @@
 """Liquid / gas scalar solver pinned to the REFERENCE'S OWN sources: apps/libs/simulation/src/implScalar.cpp
 (ScalarSimulation::performStep, performStepGL, clearNegs, set_transition, set_mass) and src/hydro/mass_transfer.cpp
-(MassTransferModel::gas_liquid_mass_transfer) are compiled where they lie over oracle/eigen_shim (Eigen is a system
+(MassTransferModel::gas_liquid_mass_transfer, update) and src/hydro/impl_mtr.cpp (the kla correlation of
+Type::FlowmapTurbulence) are compiled where they lie over oracle/eigen_shim (Eigen is a system
 package of the reference's build, absent from this image), oracle/rust_shim and oracle/kokkos_shim into
 oracle/_ref/libbmc_ref_liquid.so; oracle/ref_liquid.cpp adds the per-step call sequence of the reference's main loop
 (update_feed -> ode_step -> clearContribution).
@@ -111,6 +112,42 @@ def test_oracle_clear_negs_equals_reference_solver(orc):
         got = R.concentration()
         assert np.array_equal(got.view(np.uint64), Cl.view(np.uint64))
         assert (got[1] == 0.0) == clipped and (clipped or got[1] < 0.0)
+
+
+def test_kla_turbulence_correlation_equals_reference(orc, synth):
+    """Type::FlowmapTurbulence: kl = 0.3 (eps nu)^0.25 Sc^-0.5, a = 6 alpha / (db (1 - alpha)) (hydro/impl_mtr.cpp:22-149, the
+    reference's own source over the Eigen stand-in) against the oracle's restatement and the host layer (cma.py) that
+    feeds bmc_mass_transfer_set; then a two-phase trajectory driven by the reference's own kla field."""
+    from _bmc_loader import load_pkg
+    cma = __import__("importlib").import_module(load_pkg().__name__ + ".cma")
+    ns, n_comp, dt = 2, 120, 0.05
+    fm_l = synth.make_flowmap(n_comp, dt, p_move=0.05, seed=7); fm_g = synth.make_flowmap(n_comp, dt, p_move=0.2, seed=8)
+    rng = np.random.default_rng(9)
+    vl = np.ascontiguousarray(fm_l["volumes"], np.float64)
+    vg = np.ascontiguousarray(0.03 * vl * (0.5 + rng.random(n_comp)), np.float64)
+    eps = 0.2 + rng.random(n_comp)
+    R = refmod.RefLiquid(ns, n_comp, vl); R.set_hydro(vl, fm_l["coo"])
+    R.enable_gas_turbulence(vg)
+    coo_g = (fm_g["coo"][0], fm_g["coo"][1], 0.01 * fm_g["coo"][2])
+    R.set_hydro(vg, coo_g, gas=True)
+    Cl = np.ascontiguousarray(np.stack([2.0 + rng.random(n_comp), 1e-3 * rng.random(n_comp)], axis=1).ravel())
+    Cg = np.ascontiguousarray(np.stack([np.zeros(n_comp), 0.25 + 0.05 * rng.random(n_comp)], axis=1).ravel())
+    R.set_concentration(Cl); R.set_concentration(Cg, gas=True)
+    kla_ref = R.update_mass_transfer(vl, vg, eps)
+    kla_orc = orc.kla_flowmap_turbulence(ns, eps, vl, vg)
+    kla_host = cma.kla_flowmap_turbulence(ns, eps, vl, vg)
+    assert np.all(kla_ref[0::2] == 0) and np.all(kla_ref[1::2] > 0)
+    assert np.array_equal(kla_ref.view(np.uint64), kla_orc.view(np.uint64)), np.max(np.abs(kla_ref - kla_orc) / kla_ref.max())
+    np.testing.assert_allclose(kla_host, kla_ref, rtol=1e-13, atol=0)     # numpy's pow against libm's
+    henry = R.default_henry()
+    ml, mg = Cl * np.repeat(vl, ns), Cg * np.repeat(vg, ns)
+    z1, z2 = np.zeros(n_comp), np.zeros(ns * n_comp)
+    for step in range(50):
+        mtr = orc.ode_step_gl(Cl, ml, vl, z1, z2, fm_l["coo"], Cg, mg, vg, z1, z2.copy(), coo_g, kla_ref, henry, dt)
+        R.step(dt)
+        assert np.array_equal(R.mass_transfer().view(np.uint64), mtr.view(np.uint64)), step
+        assert np.array_equal(R.concentration().view(np.uint64), Cl.view(np.uint64)), step
+        assert np.array_equal(R.concentration(gas=True).view(np.uint64), Cg.view(np.uint64)), step
 
 
 # ------------------------------------------------------------------------------------------------- CUDA path (C ABI)
