@@ -322,8 +322,11 @@ static int finish_pending_sum(bmc_ctx* ctx) {
   PeerExchange x;
   fill_peer_exchange(ctx, x, 0, ctx->p2p_pending);
   ctx->p2p_pending = 0; ctx->p2p_published = 0;  // d_sources now holds the global sum
-  ctx->src_mirror_tag = 0;                         // ... which the host mirror of the last cycle does not
-  p2p_exchange_kernel<<<1, 1024, 0, ctx->stream>>>(x, ctx->d_sources, (uint32_t)(ctx->n_species * ctx->n_comp), ctx->st);
+  // ... which the host mirror of the last cycle does not: the kernel rewrites it with the summed values under a new tag,
+  // so that bmc_get_sources can still read the result without a copy or a stream synchronisation
+  ctx->src_mirror_tag = ctx->d_src_mirror ? ctx->launches + 1 : 0;
+  p2p_exchange_kernel<<<1, 1024, 0, ctx->stream>>>(x, ctx->d_sources, (uint32_t)(ctx->n_species * ctx->n_comp), ctx->st, ctx->d_src_mirror,
+                                                   ctx->src_mirror_tag);
   return check_launch(ctx, "p2p_exchange");
 }
 
@@ -1112,7 +1115,9 @@ int bmc_get_sources(bmc_ctx* ctx, double* out) {
   if (!ctx || !out) return BMC_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
   const size_t bytes = ctx->n_species * ctx->n_comp * 8;
-  if (ctx->src_mirror_tag && !ctx->p2p_pending) {
+  // a pending all-reduce is finished first (one small kernel, which also refreshes the tagged host mirror)
+  { int rc = finish_pending_sum(ctx); if (rc) return rc; }
+  if (ctx->src_mirror_tag) {
     // The last thing that wrote the sources was a cycle, whose publish phase also stored every value, tagged, into
     // pinned host memory: wait for the tags (no CUDA call, no copy, no stream synchronisation) and read them.
     const size_t nb = ctx->n_species * ctx->n_comp;
@@ -1135,7 +1140,6 @@ int bmc_get_sources(bmc_ctx* ctx, double* out) {
       return BMC_OK;
     }
   }
-  { int rc = finish_pending_sum(ctx); if (rc) return rc; }
   CK(cudaMemcpyAsync(ctx->h_pin_out, ctx->d_sources, bytes, cudaMemcpyDeviceToHost, ctx->stream));  // pinned: one DMA, no staging
   CK(cudaStreamSynchronize(ctx->stream));
   memcpy(out, ctx->h_pin_out, bytes);
@@ -1678,7 +1682,7 @@ int bmc_allreduce_sources(bmc_ctx* ctx) {
     if (!ctx->p2p_published) {  // the sources were not published by a cycle (first call after a load, liquid step in between, ...)
       PeerExchange x;
       fill_peer_exchange(ctx, x, ++ctx->p2p_epoch, 0);
-      p2p_exchange_kernel<<<1, 1024, 0, ctx->stream>>>(x, ctx->d_sources, (uint32_t)(ctx->n_species * ctx->n_comp), ctx->st);
+      p2p_exchange_kernel<<<1, 1024, 0, ctx->stream>>>(x, ctx->d_sources, (uint32_t)(ctx->n_species * ctx->n_comp), ctx->st, nullptr, 0ull);
       if ((rc = check_launch(ctx, "p2p_exchange"))) return rc;
       ctx->p2p_published = ctx->p2p_epoch;
     }

@@ -179,8 +179,10 @@ __device__ __forceinline__ void p2p_check_not_overrun(const PeerExchange& x, uns
   __syncthreads();
   if ((int)threadIdx.x < x.world && (int)threadIdx.x != x.rank && *p2p_flag(x.base[threadIdx.x]) >= x.consume_epoch + 2ull) atomicOr(error, 4u);
 }
-// executed by one whole block
-__device__ __forceinline__ void p2p_consume(const PeerExchange& x, double* sources, uint32_t n, unsigned int* error) {
+// executed by one whole block.  `mirror` (optional): pinned host records {value bits, tag} like the publish phase of the
+// step kernel writes them (PostParams::src_mirror), so that a host reader needs neither a copy nor a stream synchronisation
+__device__ __forceinline__ void p2p_consume(const PeerExchange& x, double* sources, uint32_t n, unsigned int* error,
+                                            unsigned long long* mirror = nullptr, unsigned long long tag = 0ull) {
   if ((int)threadIdx.x < x.world && (int)threadIdx.x != x.rank) {
     volatile unsigned long long* f = p2p_flag(x.base[threadIdx.x]);
     const long long t0 = clock64();
@@ -195,6 +197,8 @@ __device__ __forceinline__ void p2p_consume(const PeerExchange& x, double* sourc
     double a = 0.0;
     for (int r = 0; r < x.world; ++r) a += *reinterpret_cast<volatile double*>(p2p_buf(x.base[r], n, par) + k);
     sources[k] = a;
+    if (mirror)
+      asm volatile("st.volatile.v2.u64 [%0], {%1, %2};" ::"l"(mirror + 2 * k), "l"((unsigned long long)__double_as_longlong(a)), "l"(tag) : "memory");
   }
   p2p_check_not_overrun(x, error);
 }

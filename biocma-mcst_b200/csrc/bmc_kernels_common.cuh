@@ -218,9 +218,10 @@ __global__ void fill_u8_kernel(uint8_t* p, size_t n, uint8_t v) {
 
 // Peer exchange outside the step kernel (bmc_kernels.cuh: PeerExchange): publish the current sources when no cycle
 // has published them, and/or finish the all-reduce when something other than the next cycle reads the sources first.
-__global__ void __launch_bounds__(1024) p2p_exchange_kernel(const __grid_constant__ PeerExchange x, double* sources, uint32_t n, DevState* st) {
+__global__ void __launch_bounds__(1024) p2p_exchange_kernel(const __grid_constant__ PeerExchange x, double* sources, uint32_t n, DevState* st,
+                                                            unsigned long long* mirror, unsigned long long tag) {
   if (x.publish_epoch) p2p_publish(x, sources, n);
-  if (x.consume_epoch) { __syncthreads(); p2p_consume(x, sources, n, &st->error); }
+  if (x.consume_epoch) { __syncthreads(); p2p_consume(x, sources, n, &st->error, mirror, tag); }
 }
 
 }  // namespace bmc
