@@ -880,11 +880,12 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
   __shared__ unsigned s_fxmax[8];              // largest |contribution| per species seen by this block (float bits)
   // work distribution (see below): ticket counter + a ring of chunk descriptors
   constexpr unsigned kRing = 8;
-  // groups a block draws from the device-wide counter at a time: small enough that the blocks run out of work together
-  // at the end of the pass, large enough that the same-address L2 atomic stays far from its limit (~0.8 per ns: 1.25e8
-  // particles are 122 000 chunks per 800 us).  Same box, 32 / 16 / 8 groups: 1.25e8 particles 802.1 / 798.2 / 796.6 us
-  // per step, 1e7 particles 81.8 / 81.4 / 81.4.
-  constexpr int kChunk = 8;
+  // groups a block draws from the device-wide counter at a time = one per warp.  (8-group chunks let the blocks run out
+  // of work closer together — 802 -> 797 us per step at 1.25e8 particles — but the case without prefetch staging (10 000
+  // compartments) then hung in the ring hand-off: with a chunk smaller than the number of warps, the fetcher of chunk
+  // c + kRing can find the slot of chunk c free BEFORE the fetcher of chunk c has published it.  One chunk per round of
+  // the block's warps rules that out: chunk c + kRing is 8 x kWarps tickets later, more than the warps can hold.)
+  constexpr int kChunk = kWarps;
   __shared__ unsigned s_ticket;
   __shared__ unsigned s_chunk_base[kRing];     // first group of chunk c (slot c % kRing) ...
   __shared__ unsigned s_chunk_seq[kRing];      // ... valid when == c + 1
@@ -895,7 +896,7 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
   // Work distribution: the slots are cut into groups of 32*VEC; every warp of the (persistent, fully
   // resident) grid starts with the group of its own index and then draws further groups dynamically, so
   // that blocks which start late or run on a slower SM simply process fewer groups.  Two levels: a
-  // BLOCK draws chunks of kChunk (8) consecutive groups from the device-wide counter, its warps draw
+  // BLOCK draws chunks of kChunk (= kWarps) consecutive groups from the device-wide counter, its warps draw
   // single groups of the chunk with a shared-memory ticket.  (One L2 atomic per GROUP on one address
   // was the limiter of the whole pass: same-address atomics retire at ~0.8 per ns on a B200, i.e.
   // 78 125 groups of a 1e7-particle step could not be handed out in less than ~95 us — the time per
