@@ -162,3 +162,21 @@ def test_static_head_dynamic_tail_work_distribution(bmc, orc, synth, monkeypatch
     tp._compare(g, o)
     c = o.counters()
     assert c["total_out"] > 0 and (model == "simple_acetate" or c["total_new"] > 0)
+
+
+@pytest.mark.parametrize("model,n", [("monod", 2_000_077), ("fixed_length", 1_200_031)])
+def test_pass_without_prefetch_staging(bmc, orc, synth, monkeypatch, model, n):
+    """The particle pass without the cp.async staging (BMC_PREFETCH=0; what a 10 000-compartment case runs, whose bins and
+    table leave no room for it): tickets are resolved at the end of a group instead of in the middle.  Sized so that
+    every block goes through the ring of chunk descriptors several times (a chunk size smaller than the number of warps
+    once deadlocked exactly this path), bit-identical to the oracle."""
+    import util
+    monkeypatch.setenv("BMC_PREFETCH", "0")
+    monkeypatch.setenv("BMC_DYN_SHIFT", "0")
+    case = util.make_case(synth, model, n, 60, dt=20.0, near_division=0.8, p_move=0.3, p_exit=0.3)
+    g, o = tp._pair(bmc, orc, case, dead_ratio=0.0005)
+    util.load_case(g, case); util.load_case(o, case)
+    sg = util.run_steps(g, case, 3, collect=True); so = util.run_steps(o, case, 3, collect=True)
+    tp._compare_sources(sg, so)
+    tp._compare(g, o)
+    assert o.counters()["total_out"] > 0 and o.counters()["total_new"] > 0
