@@ -18,9 +18,15 @@ P = os.path.join(ROOT, "profiles")
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402  (workload table)
 
-commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True, cwd=ROOT).stdout.strip()
+commit = os.environ.get("PROFILE_COMMIT") or subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True, cwd=ROOT).stdout.strip()
 dirty = subprocess.run(["git", "status", "--porcelain", "biocma-mcst_b200/csrc"], capture_output=True, text=True, cwd=ROOT).stdout.strip()
 commit += "+" if dirty else ""
+# entries of workloads without a new capture are kept (they carry the commit and the capture they came from)
+try:
+    with open(os.path.join(P, "traffic.json")) as _f:
+        _old_traffic = json.load(_f)
+except Exception:  # noqa: BLE001
+    _old_traffic = {}
 traffic = {"note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step kernel (ncu --set full --clock-control none, "
                    "7th launch of `bench.py --workload <w> --steps 8 --warmup 3`); bench.py reports an entry only when the kernel "
                    "instantiation it ran has the same block size and vector width"}
@@ -73,6 +79,9 @@ if os.path.exists(c5):
             f.write(f"{k} {v}\n")
     print("c5", f"{dram/1e9:.2f} GB", f"{dram / bench.WORKLOADS['c5'][2]:.1f} B/particle")
 
+for _k, _v in _old_traffic.items():
+    if _k != "note" and _k not in traffic:
+        traffic[_k] = _v
 with open(os.path.join(P, "traffic.json"), "w") as f:
     json.dump(traffic, f, indent=1)
 
