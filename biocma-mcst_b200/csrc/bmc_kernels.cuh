@@ -871,7 +871,7 @@ template <class M, int VEC, bool LAZY, int BLOCK> __device__ __forceinline__ voi
   // The model terms are fetched right before the particle's update, so that the terms of the VEC particles of a thread
   // are not all live at once.  The global-memory form of the table (n_comp too large for shared memory) stays
   // row-major: one row = one sector.
-  constexpr bool kPlanar = (CT == 8);
+  constexpr bool kPlanar = PlanarTable<M>::value && CT == 8;
   auto planar_word = [&](uint32_t c, int k) -> uint32_t { return (uint32_t)k * p.n_comp + c; };
   // dynamic shared memory: [n_species * n_comp] 64-bit source bins when bins_in_smem, the compartment table when
   // ctab_in_smem, one deferred queue per warp

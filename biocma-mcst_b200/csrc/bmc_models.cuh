@@ -213,6 +213,11 @@ struct Monod {
   }
 };
 
+// Layout hint for the compartment table in shared memory (cycle_body): a model whose row is 8 words with the LAST one
+// unused may ask for word planes instead of 32-byte rows (gathers of 32 random compartments then spread over all
+// banks).  Off unless a model specialises it; user models keep the row-major table.
+template <class M> struct PlanarTable { static constexpr bool value = false; };
+
 // =============================================================================
 // simple_acetate — apps/libs/models/public/models/simple_acetate.hpp:26-248
 // =============================================================================
@@ -309,6 +314,9 @@ struct SimpleAcetate {
     for (int i = a_e; i < n_var; ++i) buffer_arr(idx2, i) = 0.0f;  // export-only, rewritten by first update
   }
 };
+
+template <> struct PlanarTable<SimpleAcetate> { static constexpr bool value = true; };  // words 1..6 used, word 7 padding
+static_assert(SimpleAcetate::n_pre == 7, "PlanarTable: 8-word rows");
 
 // =============================================================================
 // Wide UDF — synthetic multi-metabolite user model (BASELINE.json configs[4]),
