@@ -395,3 +395,97 @@ class RefLiquid:
         rc = self.L.refl_step(self.h, float(d_t), _ptr(src), ctypes.addressof(n_f), ctypes.addressof(pairs[0]), ctypes.addressof(pairs[1]),
                               ctypes.addressof(pairs[2]), ctypes.addressof(n_s), ctypes.addressof(pairs[3]), ctypes.addressof(pairs[4]))
         assert rc == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's own SimulationUnit stepped by the body of its main loop (oracle/ref_sim.cpp).  TEST INFRASTRUCTURE.
+SIM_LIB_PATH = os.path.join(_HERE, "_ref", "libbmc_ref_sim.so")
+_sim = None
+
+
+def sim_available():
+    return os.path.exists(SIM_LIB_PATH) or can_build()
+
+
+def sim_lib():
+    global _sim
+    if _sim is None:
+        if not os.path.exists(SIM_LIB_PATH):
+            build()
+        L = ctypes.CDLL(SIM_LIB_PATH)
+        vp, u64, dbl, ci = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_double, ctypes.c_int
+        L.rsim_create.restype = vp
+        L.rsim_create.argtypes = [ci, u64, u64, u64, vp, vp, u64, vp, vp, vp, vp, vp]
+        L.rsim_destroy.restype = None; L.rsim_destroy.argtypes = [vp]
+        L.rsim_last_error.restype = ctypes.c_char_p; L.rsim_last_error.argtypes = [vp]
+        L.rsim_set_particles.argtypes = [vp, u64, vp, vp, dbl]
+        L.rsim_get_particles.argtypes = [vp, u64, vp, vp, vp, vp, vp]
+        L.rsim_update_hydro.argtypes = [vp, vp, vp, vp, vp, u64, u64, vp, vp, vp]
+        L.rsim_step.argtypes = [vp, dbl]
+        L.rsim_get_concentrations.argtypes = [vp, vp]
+        L.rsim_get_sources.argtypes = [vp, vp]
+        L.rsim_get_counters.argtypes = [vp, vp]
+        L.ref_set_threads.argtypes = [ci]; L.ref_set_threads.restype = None
+        _sim = L
+    return _sim
+
+
+class RefSim:
+    """Simulation::SimulationUnit of the reference with a liquid phase and constant feeds; `step` is one iteration of the
+    reference's main loop: update_feed, ode_step, advance, clearContribution, cycleProcess."""
+
+    def __init__(self, model, n_species, n_comp, volumes, c0, feeds=(), seed=2024):
+        self.L = sim_lib()
+        self.L.ref_set_threads(1)
+        self.model = MODEL_IDS[model]
+        self.ns, self.nc = int(n_species), int(n_comp)
+        v = np.ascontiguousarray(volumes, np.float64); c = np.ascontiguousarray(c0, np.float64)
+        fs = np.array([f["species"] for f in feeds], np.uint64); fi = np.array([f["input_position"] for f in feeds], np.uint64)
+        fo = np.array([f["output_position"] for f in feeds], np.uint64)
+        ff = np.array([f["flow"] for f in feeds], np.float64); fc = np.array([f["concentration"] for f in feeds], np.float64)
+        self.h = self.L.rsim_create(self.model, self.ns, self.nc, seed, _ptr(v), _ptr(c), len(feeds), _ptr(fs), _ptr(fi), _ptr(fo), _ptr(ff), _ptr(fc))
+        assert self.h, "rsim_create failed"
+        self.n_var = {0: 2, 1: 6}[self.model]
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.rsim_destroy(self.h); self.h = None
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.L.rsim_last_error(self.h).decode())
+
+    def set_particles(self, props, position, weight):
+        props = np.ascontiguousarray(props, np.float32); pos = np.ascontiguousarray(position, np.uint64)
+        self._ck(self.L.rsim_set_particles(self.h, props.shape[1], _ptr(props), _ptr(pos), float(weight)))
+
+    def update_hydro(self, fm):
+        """SimulationUnit::updateHydro from one flow map of biocma_mcst_b200.synth.make_flowmap"""
+        vol = np.ascontiguousarray(fm["volumes"], np.float64); neigh = np.ascontiguousarray(fm["neighbors"], np.uint64)
+        proba = np.ascontiguousarray(fm["cdf"], np.float64); out = np.ascontiguousarray(fm["out_flows"], np.float64)
+        rows, cols, vals = (np.ascontiguousarray(fm["coo"][0], np.uint64), np.ascontiguousarray(fm["coo"][1], np.uint64),
+                            np.ascontiguousarray(fm["coo"][2], np.float64))
+        m = neigh.size // vol.size
+        self._ck(self.L.rsim_update_hydro(self.h, _ptr(vol), _ptr(neigh), _ptr(proba), _ptr(out), m, vals.size, _ptr(rows), _ptr(cols), _ptr(vals)))
+
+    def step(self, d_t):
+        self._ck(self.L.rsim_step(self.h, float(d_t)))
+
+    def concentrations(self):
+        out = np.empty(self.ns * self.nc); self._ck(self.L.rsim_get_concentrations(self.h, _ptr(out))); return out
+
+    def sources(self):
+        out = np.empty(self.ns * self.nc); self._ck(self.L.rsim_get_sources(self.h, _ptr(out))); return out
+
+    def counters(self):
+        c = (ctypes.c_ulonglong * 16)()
+        self._ck(self.L.rsim_get_counters(self.h, c))
+        return dict(events=dict(zip(EVENTS, c[0:6])), n_used=c[6], n_inactive=c[7], last_out=c[8], last_dead=c[9],
+                    last_waiting_allocation=c[10], capacity=c[12], total_out=c[13], total_new=c[14], n_compactions=c[15])
+
+    def get_particles(self, n=None):
+        n = self.counters()["n_used"] if n is None else int(n)
+        props = np.empty((self.n_var, n), np.float32); pos = np.empty(n, np.uint64); st = np.empty(n, np.uint8)
+        ah = np.empty(n, np.float32); ad = np.empty(n, np.float32)
+        self._ck(self.L.rsim_get_particles(self.h, n, _ptr(props), _ptr(pos), _ptr(st), _ptr(ah), _ptr(ad)))
+        return dict(props=props, position=pos, status=st, age_hyd=ah, age_div=ad)
