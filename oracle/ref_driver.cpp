@@ -22,8 +22,10 @@
 //     Common::c_league_size         common/src/common.cpp
 //     PostProcessing::get_properties core/post_process.hpp:173-250 (+ GetPropertiesFunctor :33-147)
 //   what this file adds
-//     the body of SimulationUnit::cycleProcess / post_cycle (simulation/simulation.hpp:183-239), which
-//     cannot be instantiated here (SimulationUnit needs Eigen + rcmtool): the same calls in the same order;
+//     the body of SimulationUnit::cycleProcess / post_cycle (simulation/simulation.hpp:183-239): the same calls in the
+//     same order, on a bare container + domain + concentration view so that every input of a step can be set from
+//     outside (the fixtures).  The reference's SimulationUnit ITSELF runs in oracle/ref_sim.cpp (Eigen and rcmtool
+//     stand-ins), where nothing of the step is restated; tests/test_reference_simulation_unit.py ties the two together;
 //     Tap<M>: forwards every model hook unchanged after telling the shim's random generator which particle
 //     it serves (the reference's pool is not indexable by particle; DESIGN.md §4 defines the streams);
 //     MonodQ1: SURVEY.md Q1 — monod.hpp predates the 7-argument hook concept and has no n_c; the wrapper
