@@ -425,6 +425,10 @@ def sim_lib():
         L.rsim_get_concentrations.argtypes = [vp, vp]
         L.rsim_get_sources.argtypes = [vp, vp]
         L.rsim_get_counters.argtypes = [vp, vp]
+        L.rsim_create_two_phase.restype = vp
+        L.rsim_create_two_phase.argtypes = [ci, u64, u64, u64, vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, u64, vp, vp, vp, vp, vp, vp]
+        L.rsim_set_gas_hydro.argtypes = [vp, vp, u64, vp, vp, vp, vp]
+        L.rsim_get_gas.argtypes = [vp, vp, vp]
         L.ref_set_threads.argtypes = [ci]; L.ref_set_threads.restype = None
         _sim = L
     return _sim
@@ -434,18 +438,30 @@ class RefSim:
     """Simulation::SimulationUnit of the reference with a liquid phase and constant feeds; `step` is one iteration of the
     reference's main loop: update_feed, ode_step, advance, clearContribution, cycleProcess."""
 
-    def __init__(self, model, n_species, n_comp, volumes, c0, feeds=(), seed=2024):
+    def __init__(self, model, n_species, n_comp, volumes, c0, feeds=(), seed=2024, gas=None):
+        """gas: None, or dict(volumes, c0, feeds, kla_fixed) for a two-phase unit (kla_fixed None = turbulence correlation)"""
         self.L = sim_lib()
         self.L.ref_set_threads(1)
         self.model = MODEL_IDS[model]
         self.ns, self.nc = int(n_species), int(n_comp)
         v = np.ascontiguousarray(volumes, np.float64); c = np.ascontiguousarray(c0, np.float64)
-        fs = np.array([f["species"] for f in feeds], np.uint64); fi = np.array([f["input_position"] for f in feeds], np.uint64)
-        fo = np.array([f["output_position"] for f in feeds], np.uint64)
-        ff = np.array([f["flow"] for f in feeds], np.float64); fc = np.array([f["concentration"] for f in feeds], np.float64)
-        self.h = self.L.rsim_create(self.model, self.ns, self.nc, seed, _ptr(v), _ptr(c), len(feeds), _ptr(fs), _ptr(fi), _ptr(fo), _ptr(ff), _ptr(fc))
+
+        def pack(fl):
+            return (np.array([f["species"] for f in fl], np.uint64), np.array([f["input_position"] for f in fl], np.uint64),
+                    np.array([f["output_position"] for f in fl], np.uint64), np.array([f["flow"] for f in fl], np.float64),
+                    np.array([f["concentration"] for f in fl], np.float64))
+        fs, fi, fo, ff, fc = pack(feeds)
+        if gas is None:
+            self.h = self.L.rsim_create(self.model, self.ns, self.nc, seed, _ptr(v), _ptr(c), len(feeds), _ptr(fs), _ptr(fi), _ptr(fo), _ptr(ff), _ptr(fc))
+        else:
+            gv = np.ascontiguousarray(gas["volumes"], np.float64); g0 = np.ascontiguousarray(gas["c0"], np.float64)
+            gs, gi, go, gf, gc = pack(gas.get("feeds", ()))
+            kf = None if gas.get("kla_fixed") is None else np.ascontiguousarray(gas["kla_fixed"], np.float64)
+            self.h = self.L.rsim_create_two_phase(self.model, self.ns, self.nc, seed, _ptr(v), _ptr(c), len(feeds), _ptr(fs), _ptr(fi), _ptr(fo), _ptr(ff),
+                                                  _ptr(fc), _ptr(gv), _ptr(g0), len(gas.get("feeds", ())), _ptr(gs), _ptr(gi), _ptr(go), _ptr(gf), _ptr(gc),
+                                                  _ptr(kf))
         assert self.h, "rsim_create failed"
-        self.n_var = {0: 2, 1: 6}[self.model]
+        self.n_var = {0: 2, 1: 6, 2: 9}[self.model]
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -467,6 +483,19 @@ class RefSim:
                             np.ascontiguousarray(fm["coo"][2], np.float64))
         m = neigh.size // vol.size
         self._ck(self.L.rsim_update_hydro(self.h, _ptr(vol), _ptr(neigh), _ptr(proba), _ptr(out), m, vals.size, _ptr(rows), _ptr(cols), _ptr(vals)))
+
+    def set_gas_hydro(self, gas_volumes, coo, energy_dissipation=None):
+        """the gas part of the iteration state the next update_hydro hands to SimulationUnit::updateHydro"""
+        gv = np.ascontiguousarray(gas_volumes, np.float64)
+        rows, cols, vals = (np.ascontiguousarray(coo[0], np.uint64), np.ascontiguousarray(coo[1], np.uint64), np.ascontiguousarray(coo[2], np.float64))
+        eps = np.ascontiguousarray(np.ones(self.nc) if energy_dissipation is None else energy_dissipation, np.float64)
+        self._ck(self.L.rsim_set_gas_hydro(self.h, _ptr(gv), vals.size, _ptr(rows), _ptr(cols), _ptr(vals), _ptr(eps)))
+
+    def gas(self):
+        """(gas concentrations, mass-transfer rates of the last step), species fastest"""
+        c = np.empty(self.ns * self.nc); m = np.empty(self.ns * self.nc)
+        self._ck(self.L.rsim_get_gas(self.h, _ptr(c), _ptr(m)))
+        return c, m
 
     def step(self, d_t):
         self._ck(self.L.rsim_step(self.h, float(d_t)))

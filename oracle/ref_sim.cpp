@@ -33,6 +33,9 @@ struct ISim {
   virtual void get_particles(size_t n, float* props, uint64_t* pos, uint8_t* st, float* ah, float* ad) = 0;
   virtual void update_hydro(const double* vol, const uint64_t* neigh, const double* proba, const double* out_flows, size_t m, size_t nnz,
                             const uint64_t* rows, const uint64_t* cols, const double* vals) = 0;
+  // two-phase cases: the gas part of the NEXT update_hydro's iteration state (volumes, transition, energy dissipation)
+  virtual void set_gas_hydro(const double* gvol, size_t nnz, const uint64_t* rows, const uint64_t* cols, const double* vals, const double* eps) = 0;
+  virtual void get_gas(double* conc, double* mtr) = 0;
   virtual void step(double d_t) = 0;
   virtual void get_concentrations(double* out) = 0;
   virtual void get_sources(double* out) = 0;
@@ -44,7 +47,8 @@ template <class M> struct Sim final : ISim {
   using Functors = Simulation::KernelInline::CycleFunctors<ComputeSpace, M>;
   size_t ns, nc;
   uint64_t seed; uint32_t rank = 0, step_id = 0;
-  std::vector<double> vol;
+  std::vector<double> vol, gvol;
+  PhaseStateWrapper gas_state; std::vector<double> eps; bool two_phase = false;
   std::unique_ptr<Simulation::SimulationUnit> sim;
   Container container;
   std::unique_ptr<Functors> functors;
@@ -52,9 +56,15 @@ template <class M> struct Sim final : ISim {
   KernelDispatchOptions opts{};
   unsigned long long total_out = 0, total_new = 0, n_compactions = 0, last_out = 0, last_waiting = 0;
 
+  // gas_volumes != nullptr: two-phase flow (gas concentrations g0, gas feeds, mass transfer: kla_fixed per species, or the
+  // turbulence correlation when kla_fixed == nullptr)
   Sim(size_t n_species, size_t n_comp, uint64_t seed_, const double* volumes, const double* c0, size_t n_feeds, const uint64_t* f_species,
-      const uint64_t* f_in, const uint64_t* f_out, const double* f_flow, const double* f_conc)
+      const uint64_t* f_in, const uint64_t* f_out, const double* f_flow, const double* f_conc, const double* gas_volumes = nullptr,
+      const double* g0 = nullptr, size_t n_gas_feeds = 0, const uint64_t* gf_species = nullptr, const uint64_t* gf_in = nullptr,
+      const uint64_t* gf_out = nullptr, const double* gf_flow = nullptr, const double* gf_conc = nullptr, const double* kla_fixed = nullptr)
       : ns(n_species), nc(n_comp), seed(seed_), vol(volumes, volumes + n_comp) {
+    two_phase = gas_volumes != nullptr;
+    if (two_phase) gvol.assign(gas_volumes, gas_volumes + n_comp);
     auto unit = std::make_unique<MC::MonteCarloUnit>();
     unit->domain = MC::ReactorDomain(std::span<double>(vol));  // mc/public/mc/mcinit.hpp:83
     // concentrations from a functor, like ScalarInitialiserType::Uniform / Local (scalar_factory.cpp)
@@ -62,11 +72,35 @@ template <class M> struct Sim final : ISim {
     Simulation::ScalarInitializer si{};
     si.n_species = ns; si.volumesliq = std::span<double>(vol); si.type = Simulation::ScalarInitialiserType::Local;
     si.liquid_f_init = [init, n_species](std::size_t i, std::size_t j) { return init[i + n_species * j]; };
-    si.gas_flow = false;
+    si.gas_flow = two_phase;
+    if (two_phase) {
+      std::vector<double> ginit(g0, g0 + ns * nc);
+      si.volumesgas = std::span<double>(gvol);
+      si.gas_f_init = [ginit, n_species](std::size_t i, std::size_t j) { return ginit[i + n_species * j]; };
+    }
     auto feed = Simulation::Feed::SimulationFeed::empty();
+    for (size_t k = 0; k < n_gas_feeds; ++k)
+      feed.add_gas(Simulation::Feed::FeedFactory::constant(gf_flow[k], gf_conc[k], gf_species[k], gf_in[k], std::optional<std::size_t>(gf_out[k])));
     for (size_t k = 0; k < n_feeds; ++k)  // one descriptor per entry: FeedFactory::constant (feed_descriptor.cpp:97-112)
       feed.add_liquid(Simulation::Feed::FeedFactory::constant(f_flow[k], f_conc[k], f_species[k], f_in[k], std::optional<std::size_t>(f_out[k])));
     sim = std::make_unique<Simulation::SimulationUnit>(std::move(unit), std::move(si), std::optional<Simulation::Feed::SimulationFeed>(std::move(feed)));
+    if (two_phase) {  // global_initaliser.cpp: simulation->setMtrModel(...)
+      if (kla_fixed) sim->setMtrModel(Simulation::MassTransfer::Type::MtrTypeVariant(Simulation::MassTransfer::Type::FixedKla{std::vector<double>(kla_fixed, kla_fixed + ns)}));
+      else sim->setMtrModel(Simulation::MassTransfer::Type::MtrTypeVariant(Simulation::MassTransfer::Type::FlowmapTurbulence{}));
+    }
+  }
+  void set_gas_hydro(const double* gv, size_t nnz, const uint64_t* rows, const uint64_t* cols, const double* vals, const double* e) override {
+    gas_state.vol.assign(gv, gv + nc); gas_state.inv_vol.resize(nc);
+    for (size_t j = 0; j < nc; ++j) gas_state.inv_vol[j] = 1.0 / gv[j];
+    gas_state.out.assign(nc, 0.0);
+    gas_state.coo.n = nc; gas_state.coo.r.assign(rows, rows + nnz); gas_state.coo.c.assign(cols, cols + nnz); gas_state.coo.v.assign(vals, vals + nnz);
+    eps.assign(e, e + nc);
+  }
+  void get_gas(double* conc, double* mtr) override {
+    const auto g = sim->getter().getCgasData();
+    const auto m = sim->getter().getMTRData();
+    if (!g || !m) throw std::runtime_error("no gas phase");
+    for (size_t k = 0; k < ns * nc; ++k) { conc[k] = (*g)[k]; mtr[k] = (*m)[k]; }
   }
 
   void set_particles(size_t n, const float* props, const uint64_t* pos, double weight) override {
@@ -96,6 +130,7 @@ template <class M> struct Sim final : ISim {
     st->liq.out.assign(out_flows, out_flows + nc);
     st->liq.coo.n = nc; st->liq.coo.r.assign(rows, rows + nnz); st->liq.coo.c.assign(cols, cols + nnz); st->liq.coo.v.assign(vals, vals + nnz);
     st->neighbors.assign(neigh, neigh + nc * m); st->probability_leaving.assign(proba, proba + nc * m);
+    if (two_phase) { st->gas = gas_state; st->with_gas = true; st->energy_dissipation = eps; }
     CmaUtils::IterationStatePtrType state(st);
     sim->updateHydro(state);
     functors.reset();
@@ -173,4 +208,21 @@ int rsim_step(void* h, double d_t) { auto* s = static_cast<ISim*>(h); SIM_TRY(s,
 int rsim_get_concentrations(void* h, double* out) { auto* s = static_cast<ISim*>(h); SIM_TRY(s, s->get_concentrations(out)); }
 int rsim_get_sources(void* h, double* out) { auto* s = static_cast<ISim*>(h); SIM_TRY(s, s->get_sources(out)); }
 int rsim_get_counters(void* h, unsigned long long* c) { auto* s = static_cast<ISim*>(h); SIM_TRY(s, s->counters(c)); }
+// two-phase SimulationUnit (model ids as above); kla_fixed == NULL selects Type::FlowmapTurbulence
+void* rsim_create_two_phase(int model, uint64_t n_species, uint64_t n_comp, uint64_t seed, const double* volumes, const double* c0, uint64_t n_feeds,
+                            const uint64_t* f_species, const uint64_t* f_in, const uint64_t* f_out, const double* f_flow, const double* f_conc,
+                            const double* gas_volumes, const double* g0, uint64_t n_gas_feeds, const uint64_t* gf_species, const uint64_t* gf_in,
+                            const uint64_t* gf_out, const double* gf_flow, const double* gf_conc, const double* kla_fixed) {
+  try {
+    if (model == 0) return new Sim<Tap<Models::FixedLength>>(n_species, n_comp, seed, volumes, c0, n_feeds, f_species, f_in, f_out, f_flow, f_conc,
+                                                             gas_volumes, g0, n_gas_feeds, gf_species, gf_in, gf_out, gf_flow, gf_conc, kla_fixed);
+    if (model == 2) return new Sim<Tap<Models::SimpleAcetate>>(n_species, n_comp, seed, volumes, c0, n_feeds, f_species, f_in, f_out, f_flow, f_conc,
+                                                               gas_volumes, g0, n_gas_feeds, gf_species, gf_in, gf_out, gf_flow, gf_conc, kla_fixed);
+  } catch (const std::exception& e) { std::fprintf(stderr, "rsim_create_two_phase: %s\n", e.what()); }
+  return nullptr;
+}
+int rsim_set_gas_hydro(void* h, const double* gvol, uint64_t nnz, const uint64_t* rows, const uint64_t* cols, const double* vals, const double* eps) {
+  auto* s = static_cast<ISim*>(h); SIM_TRY(s, s->set_gas_hydro(gvol, nnz, rows, cols, vals, eps));
+}
+int rsim_get_gas(void* h, double* conc, double* mtr) { auto* s = static_cast<ISim*>(h); SIM_TRY(s, s->get_gas(conc, mtr)); }
 }  // extern "C"
